@@ -1,0 +1,175 @@
+/*
+ * vodagg.h -- C ABI of libvodagg.so: hand-written sm_100a CUDA kernels for the
+ * multi-frame feature-aggregation hot path of the MMTracking / MMDetection
+ * video-object-detection stack (SELSA, TemporalRoIAlign, FGFA/DFF warp,
+ * RoIAlign, batched NMS).
+ *
+ * Conventions:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     its name ends in _host.  No torch types, no allocation inside the
+ *     library, no retained pointers, no host synchronisation: every entry
+ *     point only enqueues work on `stream` and is CUDA-graph capturable.
+ *   - workspace is caller-provided; ask vod_*_workspace_bytes() first.
+ *   - return value: 0 = ok; <0 = error (VOD_E_*).  vod_last_error() gives a
+ *     thread-local message.  Nothing throws or aborts.
+ *   - re-entrant: no global mutable state except lazily created, immutable
+ *     function attributes / driver entry points.
+ *
+ * "replaces" lines cite the reference interface each entry point sits behind
+ * (paths relative to the reference root).
+ */
+#ifndef VODAGG_H_
+#define VODAGG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *vod_stream_t; /* cudaStream_t */
+
+#define VOD_OK 0
+#define VOD_E_BADARG (-1)      /* null pointer / bad size / unsupported shape */
+#define VOD_E_LAUNCH (-2)      /* cudaGetLastError() after a launch */
+#define VOD_E_WORKSPACE (-3)   /* workspace too small */
+#define VOD_E_UNSUPPORTED (-4) /* shape not supported by this kernel variant */
+
+#define VOD_DTYPE_F32 0
+#define VOD_DTYPE_BF16 1
+
+int vod_version(void);
+const char *vod_last_error(void);
+/* 1 when the visible device is compute capability 10.x (tcgen05 / TMEM / TMA paths usable). */
+int vod_device_is_sm100(void);
+
+/* ------------------------------------------------------------------ layout
+ * NCHW fp32 -> NHWC fp32 (+ optional per-pixel ||x||_2 over C and optional
+ * L2-normalised bf16 copy [B*H*W, C]).  Feeds (1) and (4).
+ * replaces: the .permute(...).contiguous() / x / x.norm(p=2, dim=1) passes at
+ *   mmtracking/mmtrack/models/roi_heads/roi_extractors/temporal_roi_align.py:127-140,159-161
+ */
+int vod_nchw_to_nhwc(const float *in_nchw, float *out_nhwc, float *norm_out /*nullable*/,
+                     void *out_unit_bf16 /*nullable*/, int B, int C, int H, int W,
+                     vod_stream_t stream);
+/* rows [R, C] fp32 -> ||row||_2, unit-norm bf16 rows (either output nullable). */
+int vod_rows_l2norm(const float *rows, float *norm_out, void *out_unit_bf16, int R, int C,
+                    vod_stream_t stream);
+
+/* -------------------------------------------------------------- (1) RoIAlign
+ * Aligned/legacy average RoIAlign over NHWC features; one launch covers the
+ * key frame plus all reference frames (rois[:,0] is the frame index).
+ *   feat_nhwc [B,H,W,C] fp32; rois [K,5] = (b, x1, y1, x2, y2) image px;
+ *   out_layout 0: out [K,C,ph,pw] (the reference's layout); 1: out [K,ph,pw,C].
+ * replaces: mmcv.ops.RoIAlign.forward as constructed at
+ *   mmdetection/mmdet/models/roi_heads/roi_extractors/base_roi_extractor.py:49-55 and called at
+ *   mmdetection/mmdet/models/roi_heads/roi_extractors/single_level_roi_extractor.py:72-75
+ */
+int vod_roi_align_fwd(const float *feat_nhwc, const float *rois, float *out, int B, int C, int H,
+                      int W, int K, int ph, int pw, float spatial_scale, int sampling_ratio,
+                      int aligned, int out_layout, vod_stream_t stream);
+
+/* ------------------------------------------------- (2) flow warp / FGFA weights
+ * x [N,C,H,W], flow [N,2,Hf,Wf] (channel 0 = dx, 1 = dy, flow-image px) -> out [N,C,H,W].
+ * replaces: mmtrack.core.flow_warp_feats, mmtracking/mmtrack/core/motion/flow.py:4-41
+ */
+int vod_flow_warp(const float *x, const float *flow, float *out, int N, int C, int H, int W, int Hf,
+                  int Wf, vod_stream_t stream);
+/* key_emb [1,C,H,W], ref_emb [T,C,H,W], ref_x [T,Cx,H,W] -> out [1,Cx,H,W]:
+ * cosine(key_emb, ref_emb[t]) over C, softmax over t, weighted sum of ref_x.
+ * replaces: the weighting half of EmbedAggregator.forward,
+ *   mmtracking/mmtrack/models/aggregators/embed_aggregator.py:71-81
+ */
+int vod_embed_weighted_sum(const float *key_emb, const float *ref_emb, const float *ref_x,
+                           float *out, int T, int C, int Cx, int HW, vod_stream_t stream);
+/* Same weighting, but the weighted operand is re-warped on the fly from the raw
+ * feature memory + flows (the warped tensor is never re-read); slot `key_slot`
+ * (or -1) uses key_x un-warped, as FGFA does at mmtracking/mmtrack/models/vid/fgfa.py:277-282.
+ */
+int vod_fgfa_warp_weighted_sum(const float *key_emb, const float *ref_emb, const float *raw_x,
+                               const float *flow, const float *key_x, int key_slot, float *out,
+                               int T, int C, int Cx, int H, int W, int Hf, int Wf,
+                               vod_stream_t stream);
+
+/* ------------------------------------------------------ (3) SELSA aggregation
+ * Per-head softmax(Q K^T * scale) V.  q [N, heads*d], k [M, heads*d] row-major
+ * (head h = columns h*d..h*d+d-1) -> out [N, heads*d] fp32.
+ *   v_layout 0: v [M, heads*d] row-major (ldv ignored)
+ *   v_layout 1: v is V^T [heads*d, ldv] row-major, ldv >= M (what a projection GEMM can emit
+ *               directly; the tensor-core path consumes it without a transposition pass)
+ * dtype: VOD_DTYPE_F32 (tf32 tensor-core math when d == 64 on sm_100, otherwise fp32 SIMT)
+ *        or VOD_DTYPE_BF16 inputs (bf16 tensor-core math, fp32 accumulate/softmax).
+ * impl: 0 auto, 1 fp32 SIMT, 2 tcgen05 (error if unsupported shape/device).
+ * replaces: the bmm/softmax/bmm core of SelsaAggregator.forward,
+ *   mmtracking/mmtrack/models/aggregators/selsa_aggregator.py:51-70
+ */
+size_t vod_selsa_attn_workspace_bytes(int N, int M, int heads, int d);
+int vod_selsa_attn(const void *q, const void *k, const void *v, float *out, int N, int M, int heads,
+                   int d, float scale, int dtype, int v_layout, int ldv, int impl, void *ws,
+                   size_t ws_bytes, vod_stream_t stream);
+
+/* ------------------------------- (4) TemporalRoIAlign: most-similar sampling
+ * roi_feats [N*P, C] fp32 (P = ph*pw bins, NHWC-style rows), ref_nhwc [T, HW, C] fp32.
+ * For every (row, frame): cosine similarity against all HW locations, top-k
+ * (k <= 4), softmax over the k values, weighted sum of the raw ref features.
+ *   out     [T, N*P, C] fp32  (row-major; the host views it as [T,N,ph,pw,C])
+ *   idx_out [N*P, T, k] int32 flat h*W+w locations, descending similarity (nullable)
+ *   val_out [N*P, T, k] fp32 similarities (nullable)
+ * impl: 0 auto, 1 exact fp32 SIMT scan, 2 bf16 tcgen05 candidate GEMM + exact fp32 re-score.
+ * replaces: TemporalRoIAlign.most_similar_roi_align,
+ *   mmtracking/mmtrack/models/roi_heads/roi_extractors/temporal_roi_align.py:99-181
+ */
+size_t vod_msra_workspace_bytes(int NP, int C, int T, int HW, int k);
+/* ref_norm [T*HW] fp32 and ref_unit_bf16 [T*HW, C] may be passed when the caller already has them
+ * from vod_nchw_to_nhwc (nullable: recomputed into the workspace). */
+int vod_msra_topk_sample(const float *roi_feats, const float *ref_nhwc, const float *ref_norm,
+                         const void *ref_unit_bf16, float *out, int *idx_out, float *val_out, int NP,
+                         int C, int T, int HW, int k, int impl, void *ws, size_t ws_bytes,
+                         vod_stream_t stream);
+
+/* ------------------------- (4') TemporalRoIAlign: temporal attention weighting
+ * x_all, emb_all [T1, N, P, C] fp32 (frame 0 = the key's own RoI features);
+ * per (n, bin, head) dot(emb[t], emb[0]) over C/heads channels / sqrt(C/heads),
+ * softmax over t, out = sum_t w * x_all[t].
+ *   out_layout 0: out [N, C, P] (== [N,C,ph,pw]); 1: out [N, P, C].
+ *   heads <= 0: plain mean over T1 (temporal_roi_align.py:203-206); emb_all may be null.
+ * replaces: the weighting half of temporal_attentional_feature_aggregation,
+ *   mmtracking/mmtrack/models/roi_heads/roi_extractors/temporal_roi_align.py:77-97
+ */
+int vod_tafa_weighted_sum(const float *x_all, const float *emb_all, float *out, int T1, int N, int P,
+                          int C, int heads, int out_layout, vod_stream_t stream);
+
+/* -------------------------------------------------------- (5) batched NMS
+ * Bitmask NMS with the sort, mask and the greedy sweep all on the device (no
+ * host round trip).  Boxes of `n_images` independent images are concatenated;
+ * seg_offsets_host [n_images+1] gives each image's [begin, end) range.
+ *   boxes [n,4] fp32 (x1,y1,x2,y2), scores [n] fp32, labels [n] int64 (nullable)
+ *   mode 0: class-agnostic (labels ignored)
+ *   mode 1: mmcv coordinate-offset trick: boxes + label * (max(boxes of the image) + 1)
+ *   mode 2: class-aware on raw coordinates (mmcv's per-class split path, n >= split_thr)
+ *   keep_out  [n] int64: per image, kept indices relative to the image's first box, in
+ *             descending-score order, written at keep_out[seg_begin ...]
+ *   num_keep_out [n_images] int32
+ *   max_keep <= 0: unlimited; else the sweep stops after max_keep survivors per image.
+ * replaces: mmcv.ops.nms.batched_nms / mmcv.ops.nms (mmcv-full 1.2.x, un-vendored) as called at
+ *   mmdetection/mmdet/core/post_processing/bbox_nms.py:84 and
+ *   mmdetection/mmdet/models/dense_heads/rpn_head.py:233-235
+ */
+size_t vod_nms_workspace_bytes(int n_total, int max_seg);
+int vod_batched_nms(const float *boxes, const float *scores, const int64_t *labels, int n_total,
+                    const int *seg_offsets_host, int n_images, float iou_thr, int mode, int max_keep,
+                    int64_t *keep_out, int *num_keep_out, void *ws, size_t ws_bytes,
+                    vod_stream_t stream);
+
+/* ------------------------------------------------------------ diagnostics
+ * Plain tcgen05 GEMM used by the unit tests to validate descriptors/pipeline:
+ * D[M,N] (fp32) = A[M,K] * B[N,K]^T, A/B row-major (K contiguous), dtype bf16 or fp32(tf32).
+ */
+int vod_test_gemm_nt(const void *a, const void *b, float *d, int M, int N, int K, int dtype,
+                     vod_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VODAGG_H_ */

@@ -1,0 +1,114 @@
+"""ctypes binding of libvodagg.so (the C ABI declared in include/vodagg.h).
+
+The product path has NO fallback: if the library is missing or a call fails the
+wrappers raise.  Nothing here imports the oracle.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libvodagg.so')
+
+VOD_DTYPE_F32 = 0
+VOD_DTYPE_BF16 = 1
+
+_c = ctypes
+_P = _c.c_void_p
+_I = _c.c_int
+_F = _c.c_float
+_SZ = _c.c_size_t
+
+# symbol -> (restype, argtypes); must list every symbol include/vodagg.h declares
+SIGNATURES = {
+    'vod_version': (_I, []),
+    'vod_last_error': (_c.c_char_p, []),
+    'vod_device_is_sm100': (_I, []),
+    'vod_nchw_to_nhwc': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    'vod_rows_l2norm': (_I, [_P, _P, _P, _I, _I, _P]),
+    'vod_roi_align_fwd': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _I, _P]),
+    'vod_flow_warp': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    'vod_embed_weighted_sum': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    'vod_fgfa_warp_weighted_sum': (_I, [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'vod_selsa_attn_workspace_bytes': (_SZ, [_I, _I, _I, _I]),
+    'vod_selsa_attn': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _I, _I, _I, _P, _SZ, _P]),
+    'vod_msra_workspace_bytes': (_SZ, [_I, _I, _I, _I, _I]),
+    'vod_msra_topk_sample': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _SZ, _P]),
+    'vod_tafa_weighted_sum': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    'vod_nms_workspace_bytes': (_SZ, [_I, _I]),
+    'vod_batched_nms': (_I, [_P, _P, _P, _I, _c.POINTER(_I), _I, _F, _I, _I, _P, _P, _P, _SZ, _P]),
+    'vod_test_gemm_nt': (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+}
+
+_lib = None
+_lock = threading.Lock()
+launch_count = 0  # number of kernel-launching C-ABI calls made through this module (bench bookkeeping)
+
+
+class VodError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads libvodagg.so; raises if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise VodError(
+                        'libvodagg.so not found at %s: build it with '
+                        '`python -m lowlightenvironmentvideoobjectdetection_b200.build` '
+                        '(there is no CPU / PyTorch fallback for these ops)' % LIB_PATH)
+                lib = ctypes.CDLL(LIB_PATH)
+                for name, (res, args) in SIGNATURES.items():
+                    fn = getattr(lib, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = lib
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().vod_last_error()
+        raise VodError('%s failed (%d): %s' % (what, rc, msg.decode() if msg else ''))
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def call(name, *args):
+    """Invoke a kernel-launching entry point and raise on a non-zero status."""
+    global launch_count
+    launch_count += 1
+    check(getattr(load(), name)(*args), name)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise VodError('vodagg ops run on CUDA tensors only (got a %s tensor); '
+                           'there is no CPU fallback' % t.device.type)
+
+
+class Workspace:
+    """Grow-only per-device scratch buffer (1024-byte aligned, as torch's allocator returns)."""
+
+    def __init__(self):
+        self._buf = {}
+
+    def get(self, nbytes, device):
+        key = (device.type, device.index)
+        buf = self._buf.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 1024), dtype=torch.uint8, device=device)
+            self._buf[key] = buf
+        return buf

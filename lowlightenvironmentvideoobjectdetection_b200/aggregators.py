@@ -1,0 +1,137 @@
+"""B200-native drop-ins for mmtrack's AGGREGATORS (same registry names, ctor kwargs, forward
+signatures and parameter names, so reference configs and checkpoints apply unchanged).
+
+  SelsaAggregator  mmtracking/mmtrack/models/aggregators/selsa_aggregator.py:7-73
+  EmbedAggregator  mmtracking/mmtrack/models/aggregators/embed_aggregator.py:8-81
+
+The linear / conv projections stay library GEMMs (cuBLAS / cuDNN via nn.Linear / nn.Conv2d, as the
+reference); the similarity-softmax-weighted-sum cores run in hand-written sm_100a kernels and never
+materialise the [heads, N, M] weight tensor or the normalised embedding copies.  Inference path only
+(the kernels have no backward).
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .registry import AGGREGATORS, ConvModule
+
+
+@AGGREGATORS.register_module()
+class SelsaAggregator(nn.Module):
+    """Selsa aggregator module ("Sequence Level Semantics Aggregation for Video Object Detection").
+
+    Args:
+        in_channels (int): The number of channels of the features of proposal.
+        num_attention_blocks (int): The number of attention blocks used in selsa aggregator module.
+            Defaults to 16.
+    """
+
+    def __init__(self, in_channels, num_attention_blocks=16):
+        super(SelsaAggregator, self).__init__()
+        self.fc_embed = nn.Linear(in_channels, in_channels)
+        self.ref_fc_embed = nn.Linear(in_channels, in_channels)
+        self.fc = nn.Linear(in_channels, in_channels)
+        self.ref_fc = nn.Linear(in_channels, in_channels)
+        self.num_attention_blocks = num_attention_blocks
+        self.impl = ops.IMPL_AUTO          # test hook: force the SIMT or tcgen05 kernel
+        self.compute_dtype = torch.float32  # torch.bfloat16 selects bf16 tensor-core math (stated tolerance)
+
+    @torch.no_grad()
+    def forward(self, x, ref_x):
+        """Aggregate the features `ref_x` of reference proposals.
+
+        Args:
+            x (Tensor): of shape [N, C]. N is the number of key frame proposals.
+            ref_x (Tensor): of shape [M, C]. M is the number of reference frame proposals.
+
+        Returns:
+            Tensor: The aggregated features of key frame proposals with shape [N, C].
+        """
+        roi_n, ref_roi_n = x.shape[0], ref_x.shape[0]
+        in_dtype = x.dtype
+        x, ref_x = x.float(), ref_x.float()
+        q = self.fc_embed(x)                                   # selsa_aggregator.py:50
+        k = self.ref_fc_embed(ref_x)                           # :55
+        d = q.shape[1] // self.num_attention_blocks
+        use_vt = (d == 64 and ref_roi_n > 0)
+        if use_vt:
+            # ref_fc (:64) emitted directly as V^T [C, M] (same GEMM, no transposition pass): the
+            # tensor-core kernel wants the reference axis contiguous for the P.V product.
+            ldv = (ref_roi_n + 7) // 8 * 8
+            vt = torch.empty((q.shape[1], ldv), dtype=torch.float32, device=x.device)
+            if ldv != ref_roi_n:
+                vt[:, ref_roi_n:].zero_()
+            torch.addmm(self.ref_fc.bias.float()[:, None], self.ref_fc.weight.float(), ref_x.t(), out=vt[:, :ref_roi_n])
+            v = vt
+        else:
+            v = self.ref_fc(ref_x)
+        if self.compute_dtype == torch.bfloat16:
+            q, k, v = q.bfloat16(), k.bfloat16(), v.bfloat16()
+        o = ops.selsa_attention(q, k, v, self.num_attention_blocks, v_transposed=use_vt, impl=self.impl)  # :61-70
+        x_new = self.fc(o.view(roi_n, -1))                     # :72
+        return x_new.to(in_dtype)
+
+
+@AGGREGATORS.register_module()
+class EmbedAggregator(nn.Module):
+    """Embedding convs to aggregate multi feature maps ("Flow-Guided Feature Aggregation").
+
+    Args:
+        num_convs (int): Number of embedding convs.
+        channels (int): Channels of embedding convs. Defaults to 256.
+        kernel_size (int): Kernel size of embedding convs, Defaults to 3.
+        norm_cfg (dict): Configuration of normlization method after each conv. Defaults to None.
+        act_cfg (dict): Configuration of activation method after each conv. Defaults to dict(type='ReLU').
+    """
+
+    def __init__(self, num_convs=1, channels=256, kernel_size=3, norm_cfg=None, act_cfg=dict(type='ReLU')):
+        super(EmbedAggregator, self).__init__()
+        assert num_convs > 0, 'The number of convs must be bigger than 1.'
+        self.embed_convs = nn.ModuleList()
+        for i in range(num_convs):
+            if i == num_convs - 1:
+                new_norm_cfg = None
+                new_act_cfg = None
+            else:
+                new_norm_cfg = norm_cfg
+                new_act_cfg = act_cfg
+            self.embed_convs.append(
+                ConvModule(in_channels=channels, out_channels=channels, kernel_size=kernel_size,
+                           padding=(kernel_size - 1) // 2, norm_cfg=new_norm_cfg, act_cfg=new_act_cfg))
+
+    def _embed(self, t):
+        for embed_conv in self.embed_convs:
+            t = embed_conv(t)
+        return t
+
+    @torch.no_grad()
+    def forward(self, x, ref_x):
+        """Aggregate reference feature maps `ref_x`.
+
+        Args:
+            x (Tensor): of shape [1, C, H, W]
+            ref_x (Tensor): of shape [N, C, H, W]. N is the number of reference feature maps.
+
+        Returns:
+            Tensor: The aggregated feature map with shape [1, C, H, W].
+        """
+        assert len(x.shape) == 4 and len(x) == 1, "Only support 'batch_size == 1' for x"
+        x_embed = self._embed(x.float())                        # embed_aggregator.py:68-70
+        ref_x_embed = self._embed(ref_x.float())                # :73-75
+        # :71-81 fused: cosine over C, softmax over frames, weighted sum of the raw ref features
+        return ops.embed_weighted_sum(x_embed, ref_x_embed, ref_x).to(x.dtype)
+
+    @torch.no_grad()
+    def forward_fused_warp(self, x, raw_ref_x, flows, key_slot=-1):
+        """FGFA step with the warp fused into the weighting (mmtracking/mmtrack/models/vid/fgfa.py:275-283):
+        ``raw_ref_x`` are the un-warped memory features, ``flows`` the key->ref flows.  The warped maps are
+        produced once for the embed convs; the weighted sum re-warps on the fly instead of re-reading them.
+        Slot ``key_slot`` (the key frame's own position in the memory) is taken from ``x`` un-warped."""
+        from .motion import flow_warp_feats
+        assert len(x.shape) == 4 and len(x) == 1, "Only support 'batch_size == 1' for x"
+        warped = flow_warp_feats(raw_ref_x, flows)
+        if key_slot >= 0:
+            warped[key_slot] = x[0]
+        x_embed = self._embed(x.float())
+        ref_x_embed = self._embed(warped.float())
+        return ops.fgfa_warp_weighted_sum(x_embed, ref_x_embed, raw_ref_x, flows, key_x=x, key_slot=key_slot).to(x.dtype)

@@ -1,0 +1,85 @@
+"""Builds libvodagg.so (hand-written sm_100a CUDA kernels + C ABI) in-tree with nvcc.
+
+    python -m lowlightenvironmentvideoobjectdetection_b200.build [--force]
+
+nvcc cross-compiles without a GPU; the .so lands next to this file so it travels
+with the repo snapshot to the GPU box (it is git-ignored, not gpurun-ignored).
+"""
+import concurrent.futures
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, 'csrc')
+LIB_PATH = os.path.join(_HERE, 'libvodagg.so')
+_OBJ_DIR = os.path.join(_HERE, '_build', 'obj')
+
+SOURCES = ['common.cu', 'nms.cu', 'roi_align.cu', 'layout.cu', 'warp.cu', 'tafa.cu', 'selsa.cu',
+           'selsa_tc.cu', 'msra_gemm.cu', 'gemm_test.cu']
+
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+              '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
+
+
+def _nvcc():
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(nvcc):
+        raise RuntimeError('nvcc not found; cannot build libvodagg.so')
+    return nvcc
+
+
+def _host_cxx():
+    for c in ('/usr/bin/g++', shutil.which('g++')):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError('g++ not found')
+
+
+def _digest():
+    h = hashlib.sha256()
+    names = sorted(os.listdir(CSRC)) + ['../../include/vodagg.h']
+    for n in names:
+        p = os.path.join(CSRC, n)
+        if os.path.isfile(p):
+            h.update(n.encode())
+            h.update(open(p, 'rb').read())
+    h.update(' '.join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build_library(force=False, verbose=False):
+    """Compile every .cu for sm_100a and link libvodagg.so. Returns the library path."""
+    stamp = os.path.join(_HERE, '_build', 'stamp')
+    digest = _digest()
+    if (not force and os.path.exists(LIB_PATH) and os.path.exists(stamp)
+            and open(stamp).read().strip() == digest):
+        return LIB_PATH
+    nvcc, cxx = _nvcc(), _host_cxx()
+    os.makedirs(_OBJ_DIR, exist_ok=True)
+
+    def compile_one(src):
+        obj = os.path.join(_OBJ_DIR, src.replace('.cu', '.o'))
+        cmd = [nvcc, '-ccbin', cxx] + NVCC_FLAGS + ['-c', os.path.join(CSRC, src), '-o', obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError('nvcc failed for %s:\n%s\n%s' % (src, r.stdout, r.stderr))
+        if verbose and r.stderr:
+            print(r.stderr)
+        return obj
+
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    cmd = [nvcc, '-ccbin', cxx, '-shared', '-o', LIB_PATH] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a']
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))
+    with open(stamp, 'w') as f:
+        f.write(digest)
+    return LIB_PATH
+
+
+if __name__ == '__main__':
+    print(build_library(force='--force' in sys.argv, verbose='-v' in sys.argv))

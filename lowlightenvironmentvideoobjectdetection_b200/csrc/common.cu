@@ -1,0 +1,35 @@
+// common.cu -- error reporting + version for libvodagg.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace vod {
+
+char *last_error_buf() {
+    static thread_local char buf[512] = {0};
+    return buf;
+}
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(last_error_buf(), 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+}  // namespace vod
+
+extern "C" int vod_version(void) { return 100; }
+
+extern "C" const char *vod_last_error(void) { return vod::last_error_buf(); }
+
+extern "C" int vod_device_is_sm100(void) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return major == 10;
+}

@@ -1,0 +1,162 @@
+// gemm_test.cu -- host-side TMA tensor-map construction + a plain tcgen05 GEMM (D = A * B^T) used by
+// tests/test_gpu_tc.py to validate the descriptor / pipeline building blocks of tc.cuh in isolation
+// before they are trusted inside the fused SELSA and most-similar-location kernels.
+//
+// Kernel shape: one CTA per 128x128 output tile, 4-stage TMA->smem ring (128-byte K slices, SWIZZLE_128B),
+// warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread, accumulator in TMEM),
+// warps 2..5 = epilogue (tcgen05.ld 32x32b -> global).
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace vod {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;  // immutable once resolved
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+int make_tmap_2d_sw128(CUtensorMap *map, const void *base, int elem_bytes, uint64_t rows, uint64_t cols,
+                       uint64_t row_stride_bytes, uint32_t box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return fail(VOD_E_LAUNCH, "cuTensorMapEncodeTiled entry point unavailable");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (row_stride_bytes & 15))
+        return fail(VOD_E_BADARG, "TMA operand needs 16-byte aligned base and row stride");
+    // fp32 operands of kind::tf32 MMAs: TFLOAT32 makes the TMA unit round to tf32 while loading (the MMA
+    // would otherwise truncate the low 13 mantissa bits, a biased error of ~5e-4 relative).
+    CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(VOD_E_LAUNCH, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return VOD_OK;
+}
+
+constexpr int kGtStages = 4;
+constexpr int kGtTileBytes = 128 * 128;  // 128 rows x 128 B
+constexpr int kGtThreads = 192;
+
+template <bool BF16>
+__global__ void __launch_bounds__(kGtThreads, 1)
+gemm_nt_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, float *__restrict__ D,
+               int M, int N, int K) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sa = smem;                                   // [stages][16 KB]
+    uint8_t *sb = smem + kGtStages * kGtTileBytes;        // [stages][16 KB]
+    __shared__ uint64_t full_bar[kGtStages], empty_bar[kGtStages], acc_bar;
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 128;
+    constexpr int kElemsPerSlice = BF16 ? 64 : 32;  // 128 bytes of K
+    const int nkb = (K + kElemsPerSlice - 1) / kElemsPerSlice;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kGtStages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+        tc::mbar_init(&acc_bar, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(&tmem_slot, 128);
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 0) {
+        if (tc::elect_one()) {
+            tc::tma_prefetch_desc(&tm_a);
+            tc::tma_prefetch_desc(&tm_b);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % kGtStages;
+                const uint32_t ph = (kb / kGtStages) & 1;
+                tc::mbar_wait(&empty_bar[s], ph ^ 1);
+                tc::mbar_arrive_expect_tx(&full_bar[s], 2 * kGtTileBytes);
+                tc::tma_load_2d(sa + s * kGtTileBytes, &tm_a, &full_bar[s], kb * kElemsPerSlice, m0);
+                tc::tma_load_2d(sb + s * kGtTileBytes, &tm_b, &full_bar[s], kb * kElemsPerSlice, n0);
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = tc::umma_idesc(BF16 ? tc::kFmtBF16 : tc::kFmtTF32, 128, 128);
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % kGtStages;
+            const uint32_t ph = (kb / kGtStages) & 1;
+            tc::mbar_wait(&full_bar[s], ph);
+            tc::tcgen05_fence_after();
+            if (tc::elect_one()) {
+                const uint32_t a0 = tc::smem_u32(sa + s * kGtTileBytes), b0 = tc::smem_u32(sb + s * kGtTileBytes);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {  // 4 x 32-byte K steps per 128-byte slice (UMMA_K = 16 bf16 / 8 tf32)
+                    const uint64_t ad = tc::umma_desc_k_sw128(a0 + k * 32), bd = tc::umma_desc_k_sw128(b0 + k * 32);
+                    if (BF16) tc::umma_f16(tmem, ad, bd, idesc, (kb | k) != 0);
+                    else tc::umma_tf32(tmem, ad, bd, idesc, (kb | k) != 0);
+                }
+                tc::umma_commit(&empty_bar[s]);
+                if (kb == nkb - 1) tc::umma_commit(&acc_bar);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+        tc::mbar_wait(&acc_bar, 0);
+        tc::tcgen05_fence_after();
+        const int row = m0 + quarter * 32 + lane;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            uint32_t r[32];
+            tc::tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + c * 32, r);
+            tc::tmem_ld_wait();
+            if (row < M) {
+                for (int j = 0; j < 32; ++j) {
+                    const int col = n0 + c * 32 + j;
+                    if (col < N) D[(size_t)row * N + col] = __uint_as_float(r[j]);
+                }
+            }
+        }
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem, 128);
+}
+
+}  // namespace vod
+
+using namespace vod;
+
+extern "C" int vod_test_gemm_nt(const void *a, const void *b, float *d, int M, int N, int K, int dtype,
+                                vod_stream_t stream) {
+    VOD_REQUIRE(a && b && d && M > 0 && N > 0 && K > 0, "vod_test_gemm_nt: bad args");
+    VOD_REQUIRE(dtype == VOD_DTYPE_F32 || dtype == VOD_DTYPE_BF16, "vod_test_gemm_nt: dtype");
+    if (!vod_device_is_sm100()) return fail(VOD_E_UNSUPPORTED, "vod_test_gemm_nt: device is not sm_100");
+    const int eb = dtype == VOD_DTYPE_BF16 ? 2 : 4;
+    CUtensorMap ta, tb;
+    int rc = make_tmap_2d_sw128(&ta, a, eb, M, K, (uint64_t)K * eb, 128);
+    if (rc) return rc;
+    rc = make_tmap_2d_sw128(&tb, b, eb, N, K, (uint64_t)K * eb, 128);
+    if (rc) return rc;
+    const int smem = 2 * kGtStages * kGtTileBytes + 1024;
+    dim3 grid(ceil_div(N, 128), ceil_div(M, 128));
+    if (dtype == VOD_DTYPE_BF16) {
+        cudaFuncSetAttribute(gemm_nt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        gemm_nt_kernel<true><<<grid, kGtThreads, smem, as_stream(stream)>>>(ta, tb, d, M, N, K);
+    } else {
+        cudaFuncSetAttribute(gemm_nt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        gemm_nt_kernel<false><<<grid, kGtThreads, smem, as_stream(stream)>>>(ta, tb, d, M, N, K);
+    }
+    return check_launch("vod_test_gemm_nt");
+}

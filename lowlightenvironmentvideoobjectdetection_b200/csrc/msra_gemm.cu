@@ -1,0 +1,275 @@
+// msra_gemm.cu -- (4) TemporalRoIAlign most-similar-location search on the tensor cores (sm_100a).
+//
+// Restates TemporalRoIAlign.most_similar_roi_align,
+// mmtracking/mmtrack/models/roi_heads/roi_extractors/temporal_roi_align.py:99-181:
+//   sim[row, t, loc] = <roi_unit[row, :], ref_unit[t, loc, :]>,  top-k over loc per (row, t).
+// The [N*49, T*HW] similarity matrix (2.1 GB fp32 at N=300, T=15) is never written: the epilogue keeps a
+// running top-8 per (row, frame) in registers while the accumulator tile is read out of TMEM.  The
+// candidates are then re-scored in exact fp32 (msra_rescore_kernel, tafa.cu) so that the selected
+// locations match the fp32 reference; the bf16 GEMM is only a pre-filter.
+//
+// Persistent kernel, one CTA per SM, 192 threads; a work unit = (128-row tile, frame t):
+//   warp 4   TMA producer: the A tile (128 rows x C, K-major bf16, 128B swizzle) stays resident in shared
+//            memory while the unit's B tiles (128 locations x 64 channels per stage) stream through a ring
+//   warp 5   MMA issuer: tcgen05.mma kind::f16 (bf16 in, fp32 accumulate), 128x128 accumulator,
+//            double buffered in TMEM (2 x 128 columns)
+//   warps 0-3 epilogue: thread = row; tcgen05.ld 32 columns at a time, threshold-filtered insertion
+//            into a sorted top-8 held in registers; one 32-byte store per (row, frame) at the end
+// Units are assigned to CTAs in contiguous ranges so the A tile is reloaded only when the row tile changes.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "msra.cuh"
+#include "tc.cuh"
+
+namespace vod {
+
+constexpr int kMgBM = 128;           // rows per tile
+constexpr int kMgBN = 128;           // locations per accumulator tile
+constexpr int kMgSlice = 64;         // bf16 elements per 128-byte K slice
+constexpr int kMgMaxSlices = 8;      // C <= 512
+constexpr int kMgStages = 5;
+constexpr int kMgTile = 128 * 128;   // bytes of one [128 x 128 B] slice tile
+constexpr int kMgThreads = 192;
+constexpr int kMgSmem = kMgMaxSlices * kMgTile + kMgStages * kMgTile + 1024;
+
+struct MgParams {
+    int *cand;      // [NP, T, kMsraCand]
+    int NP, T, HW, nslices, row_tiles, ntiles;  // ntiles = ceil(HW / 128)
+    int units;      // row_tiles * T
+};
+
+__global__ void __launch_bounds__(kMgThreads, 1)
+msra_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                      const MgParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sA = smem;                               // [nslices][16 KB]
+    uint8_t *sB = smem + kMgMaxSlices * kMgTile;      // [stages][16 KB]
+    __shared__ uint64_t a_full, a_empty, b_full[kMgStages], b_empty[kMgStages], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // contiguous unit range of this CTA
+    const int per = p.units / gridDim.x, rem = p.units % gridDim.x;
+    const int u0 = blockIdx.x * per + min((int)blockIdx.x, rem);
+    const int u1 = u0 + per + ((int)blockIdx.x < rem ? 1 : 0);
+
+    if (threadIdx.x == 0) {
+        tc::mbar_init(&a_full, 1);
+        tc::mbar_init(&a_empty, 1);
+        for (int i = 0; i < kMgStages; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 5) tc::tmem_alloc(&tmem_slot, 256);
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 4) {
+        // ------------------------------------------------------------------ TMA producer
+        if (tc::elect_one()) {
+            tc::tma_prefetch_desc(&tm_a); tc::tma_prefetch_desc(&tm_b);
+            int cur_rt = -1, a_loads = 0;
+            long it = 0;  // global B-stage counter
+            for (int u = u0; u < u1; ++u) {
+                const int rt = u / p.T, t = u % p.T;
+                if (rt != cur_rt) {
+                    // the MMA warp signals a_empty when the last MMA reading the old A tile has completed
+                    tc::mbar_wait(&a_empty, (a_loads & 1) ^ 1);
+                    tc::mbar_arrive_expect_tx(&a_full, p.nslices * kMgTile);
+                    for (int s = 0; s < p.nslices; ++s)
+                        tc::tma_load_2d(sA + s * kMgTile, &tm_a, &a_full, s * kMgSlice, rt * kMgBM);
+                    cur_rt = rt;
+                    ++a_loads;
+                }
+                for (int nt = 0; nt < p.ntiles; ++nt) {
+                    for (int s = 0; s < p.nslices; ++s, ++it) {
+                        const int st = (int)(it % kMgStages);
+                        const uint32_t ph = (uint32_t)((it / kMgStages) & 1);
+                        tc::mbar_wait(&b_empty[st], ph ^ 1);
+                        tc::mbar_arrive_expect_tx(&b_full[st], kMgTile);
+                        tc::tma_load_2d(sB + st * kMgTile, &tm_b, &b_full[st], s * kMgSlice, t * p.HW + nt * kMgBN);
+                    }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ------------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = tc::umma_idesc(tc::kFmtBF16, kMgBM, kMgBN);
+        int cur_rt = -1, a_loads = 0;
+        long it = 0, tile_it = 0;
+        for (int u = u0; u < u1; ++u) {
+            const int rt = u / p.T;
+            const bool last_of_rt = (u + 1 == u1) || ((u + 1) / p.T != rt);
+            if (rt != cur_rt) {
+                tc::mbar_wait(&a_full, a_loads & 1);
+                cur_rt = rt;
+                ++a_loads;
+            }
+            for (int nt = 0; nt < p.ntiles; ++nt, ++tile_it) {
+                const int buf = (int)(tile_it & 1);
+                tc::mbar_wait(&acc_empty[buf], (uint32_t)(((tile_it >> 1) & 1) ^ 1));
+                tc::tcgen05_fence_after();
+                for (int s = 0; s < p.nslices; ++s, ++it) {
+                    const int st = (int)(it % kMgStages);
+                    tc::mbar_wait(&b_full[st], (uint32_t)((it / kMgStages) & 1));
+                    tc::tcgen05_fence_after();
+                    if (tc::elect_one()) {
+                        const uint32_t a0 = tc::smem_u32(sA + s * kMgTile), b0 = tc::smem_u32(sB + st * kMgTile);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            tc::umma_f16(tmem + buf * kMgBN, tc::umma_desc_k_sw128(a0 + k * 32),
+                                         tc::umma_desc_k_sw128(b0 + k * 32), idesc, (s | k) != 0);
+                        tc::umma_commit(&b_empty[st]);
+                        if (s == p.nslices - 1) {
+                            tc::umma_commit(&acc_full[buf]);
+                            if (last_of_rt && nt == p.ntiles - 1) tc::umma_commit(&a_empty);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: running top-8 per row
+        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+        long tile_it = 0;
+        for (int u = u0; u < u1; ++u) {
+            const int rt = u / p.T, t = u % p.T;
+            float val[kMsraCand];
+            int loc[kMsraCand];
+#pragma unroll
+            for (int i = 0; i < kMsraCand; ++i) { val[i] = -INFINITY; loc[i] = -1; }
+            for (int nt = 0; nt < p.ntiles; ++nt, ++tile_it) {
+                const int buf = (int)(tile_it & 1);
+                tc::mbar_wait(&acc_full[buf], (uint32_t)((tile_it >> 1) & 1));
+                tc::tcgen05_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < kMgBN / 32; ++c) {
+                    uint32_t r[32];
+                    tc::tmem_ld_32x32(tl + buf * kMgBN + c * 32, r);
+                    tc::tmem_ld_wait();
+                    const int base = nt * kMgBN + c * 32;
+                    const int nvalid = p.HW - base;  // columns of this frame that exist
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float v = __uint_as_float(r[j]);
+                        if (j < nvalid && v > val[kMsraCand - 1]) {
+                            // sorted insertion (descending); strict '>' keeps the earlier location on ties
+                            float cv = v; int cl = base + j;
+#pragma unroll
+                            for (int q = 0; q < kMsraCand; ++q) {
+                                if (cv > val[q]) {
+                                    const float tv = val[q]; const int tl2 = loc[q];
+                                    val[q] = cv; loc[q] = cl; cv = tv; cl = tl2;
+                                }
+                            }
+                        }
+                    }
+                }
+                tc::tcgen05_fence_before();
+                tc::mbar_arrive(&acc_empty[buf]);
+            }
+            const int row = rt * kMgBM + warp * 32 + lane;
+            if (row < p.NP) {
+                int4 *dst = reinterpret_cast<int4 *>(p.cand + ((size_t)row * p.T + t) * kMsraCand);
+                dst[0] = make_int4(loc[0], loc[1], loc[2], loc[3]);
+                dst[1] = make_int4(loc[4], loc[5], loc[6], loc[7]);
+            }
+        }
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 5) tc::tmem_dealloc(tmem, 256);
+}
+
+bool msra_gemm_supported(int NP, int C, int T, int HW) {
+    return NP > 0 && T > 0 && HW > 0 && C % kMgSlice == 0 && C / kMgSlice <= kMgMaxSlices;
+}
+
+int msra_launch_gemm_topk(const void *roi_unit_bf16, const void *ref_unit_bf16, int *cand, int NP, int NP_pad, int C,
+                          int T, int HW, cudaStream_t st) {
+    (void)NP_pad;
+    CUtensorMap ta, tb;
+    int rc;
+    if ((rc = make_tmap_2d_sw128(&ta, roi_unit_bf16, 2, NP, C, (uint64_t)C * 2, kMgBM))) return rc;
+    if ((rc = make_tmap_2d_sw128(&tb, ref_unit_bf16, 2, (uint64_t)T * HW, C, (uint64_t)C * 2, kMgBN))) return rc;
+    MgParams p;
+    p.cand = cand; p.NP = NP; p.T = T; p.HW = HW;
+    p.nslices = C / kMgSlice;
+    p.row_tiles = ceil_div(NP, kMgBM);
+    p.ntiles = ceil_div(HW, kMgBN);
+    p.units = p.row_tiles * T;
+    cudaFuncSetAttribute(msra_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMgSmem);
+    const int grid = min(kNumSMs, p.units);
+    msra_gemm_topk_kernel<<<grid, kMgThreads, kMgSmem, st>>>(ta, tb, p);
+    return check_launch("msra_gemm_topk");
+}
+
+}  // namespace vod
+
+using namespace vod;
+
+namespace {
+struct MsraWs {
+    size_t roi_norm, ref_norm, roi_unit, ref_unit, cand, bytes;
+};
+MsraWs msra_ws(int NP, int C, int T, int HW) {
+    MsraWs w;
+    size_t o = 0;
+    w.roi_norm = o; o = align_up(o + sizeof(float) * (size_t)NP, 256);
+    w.ref_norm = o; o = align_up(o + sizeof(float) * (size_t)T * HW, 256);
+    w.roi_unit = o; o = align_up(o + 2 * (size_t)NP * C, 1024);
+    w.ref_unit = o; o = align_up(o + 2 * (size_t)T * HW * C, 1024);
+    w.cand = o;     o = align_up(o + sizeof(int) * (size_t)NP * T * kMsraCand, 256);
+    w.bytes = o;
+    return w;
+}
+}  // namespace
+
+extern "C" size_t vod_msra_workspace_bytes(int NP, int C, int T, int HW, int k) {
+    (void)k;
+    if (NP <= 0 || T <= 0) return 256;
+    return msra_ws(NP, C, T, HW).bytes;
+}
+
+extern "C" int vod_msra_topk_sample(const float *roi_feats, const float *ref_nhwc, const float *ref_norm,
+                                    const void *ref_unit_bf16, float *out, int *idx_out, float *val_out, int NP, int C,
+                                    int T, int HW, int k, int impl, void *ws, size_t ws_bytes, vod_stream_t stream) {
+    if (NP == 0 || T == 0) return VOD_OK;
+    VOD_REQUIRE(roi_feats && ref_nhwc && out && ws, "vod_msra_topk_sample: null pointer");
+    VOD_REQUIRE(NP > 0 && C > 0 && T > 0 && HW > 0, "vod_msra_topk_sample: bad dims");
+    VOD_REQUIRE(k >= 1 && k <= kMsraMaxK && k <= HW, "vod_msra_topk_sample: k=%d not in [1,%d]", k, kMsraMaxK);
+    VOD_REQUIRE(impl >= 0 && impl <= 2, "vod_msra_topk_sample: impl");
+    VOD_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "vod_msra_topk_sample: workspace must be 1024-byte aligned");
+    const MsraWs w = msra_ws(NP, C, T, HW);
+    if (ws_bytes < w.bytes) return fail(VOD_E_WORKSPACE, "vod_msra_topk_sample: workspace %zu < %zu", ws_bytes, w.bytes);
+    uint8_t *wsb = reinterpret_cast<uint8_t *>(ws);
+    const bool tc_ok = msra_gemm_supported(NP, C, T, HW) && HW >= kMsraCand && vod_device_is_sm100();
+    if (impl == 2 && !tc_ok) return fail(VOD_E_UNSUPPORTED, "vod_msra_topk_sample: tcgen05 path needs C %% 64 == 0, C <= 512, sm_100");
+    const bool use_tc = impl == 2 || (impl == 0 && tc_ok);
+
+    float *roi_norm = reinterpret_cast<float *>(wsb + w.roi_norm);
+    void *roi_unit = use_tc ? wsb + w.roi_unit : nullptr;
+    int rc = vod_rows_l2norm(roi_feats, roi_norm, roi_unit, NP, C, stream);
+    if (rc) return rc;
+    const float *rn = ref_norm;
+    const void *ru = ref_unit_bf16;
+    if (!rn || (use_tc && !ru)) {
+        float *rn_ws = reinterpret_cast<float *>(wsb + w.ref_norm);
+        void *ru_ws = use_tc ? wsb + w.ref_unit : nullptr;
+        rc = vod_rows_l2norm(ref_nhwc, rn_ws, ru_ws, T * HW, C, stream);
+        if (rc) return rc;
+        rn = rn_ws;
+        if (use_tc) ru = ru_ws;
+    }
+    cudaStream_t st = as_stream(stream);
+    if (!use_tc) return msra_launch_scan(roi_feats, ref_nhwc, roi_norm, rn, out, idx_out, val_out, NP, C, T, HW, k, st);
+    int *cand = reinterpret_cast<int *>(wsb + w.cand);
+    rc = msra_launch_gemm_topk(roi_unit, ru, cand, NP, NP, C, T, HW, st);
+    if (rc) return rc;
+    return msra_launch_rescore(roi_feats, ref_nhwc, roi_norm, rn, cand, kMsraCand, out, idx_out, val_out, NP, C, T, HW, k, st);
+}

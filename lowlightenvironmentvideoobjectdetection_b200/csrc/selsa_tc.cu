@@ -1,0 +1,419 @@
+// selsa_tc.cu -- (3) SELSA similarity-softmax-weighted-sum as a fused tcgen05/TMEM kernel (sm_100a).
+//
+//   O_h = softmax(Q_h K_h^T * scale) V_h,   Q_h [N,64], K_h [M,64], V_h [M,64]   (per head h)
+//   restates mmtracking/mmtrack/models/aggregators/selsa_aggregator.py:51-70 without the [heads,N,M] tensor.
+//
+// One CTA = (128 query rows, head, split of the reference axis).  192 threads:
+//   warps 0-3  softmax: thread = query row; S chunk read from TMEM with tcgen05.ld, online softmax held
+//              entirely in registers (row max / row sum are thread-local, no shuffles), probabilities
+//              written to shared memory in the 128B-swizzled K-major operand layout, partial O read
+//              back from TMEM and accumulated in registers with the running-max correction.
+//   warp 4     TMA producer: Q once, then a 3-stage ring of (K chunk, V^T chunk) tiles.
+//   warp 5     MMA issuer: S = Q K^T (kind::tf32 or kind::f16/bf16) into a double-buffered TMEM
+//              accumulator, O_chunk = P V into a third TMEM accumulator; completion via tcgen05.commit.
+// Reference rows are processed in chunks of 64.  When N*heads/128 CTAs cannot fill 148 SMs the reference
+// axis is split across CTAs and the partial (acc, max, sum) triples are merged by selsa_merge_kernel.
+//
+// TMEM columns: [0,64) S buffer 0, [64,128) S buffer 1, [128,192) O chunk.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "selsa.cuh"
+#include "tc.cuh"
+
+namespace vod {
+
+constexpr int kBM = 128;
+constexpr int kBN = 64;
+constexpr int kHD = 64;
+constexpr int kKvStages = 3;
+constexpr int kSelsaThreads = 192;
+constexpr int kSelsaTmemCols = 256;
+
+template <bool BF16>
+struct SelsaCfg {
+    static constexpr int kElem = BF16 ? 2 : 4;
+    static constexpr int kSliceElems = 128 / kElem;         // elements per 128-byte K slice
+    static constexpr int kSlices = kHD / kSliceElems;       // slices along d (QK^T) and along refs (PV): kBN == kHD
+    static constexpr int kQBytes = kSlices * kBM * 128;
+    static constexpr int kKBytes = kSlices * kBN * 128;
+    static constexpr int kVBytes = kSlices * kHD * 128;
+    static constexpr int kPBytes = kSlices * kBM * 128;
+    static constexpr int kSmem = kQBytes + kKvStages * (kKBytes + kVBytes) + 2 * kPBytes + 1024;
+};
+
+struct SelsaParams {
+    float *out;        // [N, D]
+    float *part_acc;   // [S][heads][Npad][64]
+    float *part_m;     // [S][heads][Npad]
+    float *part_l;     // [S][heads][Npad]
+    int N, M, heads, D, Npad, splits, chunks_per_split, nchunks;
+    float scale_log2;  // scale * log2(e)
+};
+
+__device__ __forceinline__ uint32_t f32_to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(kSelsaThreads, 1)
+selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                const __grid_constant__ CUtensorMap tm_v, const SelsaParams p) {
+    using Cfg = SelsaCfg<BF16>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sQ = smem;
+    uint8_t *sK = sQ + Cfg::kQBytes;
+    uint8_t *sV = sK + kKvStages * Cfg::kKBytes;
+    uint8_t *sP = sV + kKvStages * Cfg::kVBytes;
+    __shared__ uint64_t q_full, kv_full[kKvStages], kv_empty[kKvStages], s_full[2], s_empty[2], p_full[2], p_empty[2],
+        o_full, o_empty;
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rt = blockIdx.x, h = blockIdx.y, split = blockIdx.z;
+    const int c0 = split * p.chunks_per_split;
+    const int n = min(p.chunks_per_split, p.nchunks - c0);  // chunks of this CTA (>= 1 by construction)
+
+    if (threadIdx.x == 0) {
+        tc::mbar_init(&q_full, 1);
+        for (int i = 0; i < kKvStages; ++i) { tc::mbar_init(&kv_full[i], 1); tc::mbar_init(&kv_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 128);
+            tc::mbar_init(&p_full[i], 128); tc::mbar_init(&p_empty[i], 1);
+        }
+        tc::mbar_init(&o_full, 1);
+        tc::mbar_init(&o_empty, 128);
+        tc::fence_barrier_init();
+    }
+    if (warp == 5) tc::tmem_alloc(&tmem_slot, kSelsaTmemCols);
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 4) {
+        // ------------------------------------------------------------------ TMA producer
+        if (tc::elect_one()) {
+            tc::tma_prefetch_desc(&tm_q); tc::tma_prefetch_desc(&tm_k); tc::tma_prefetch_desc(&tm_v);
+            tc::mbar_arrive_expect_tx(&q_full, Cfg::kQBytes);
+            for (int sl = 0; sl < Cfg::kSlices; ++sl)
+                tc::tma_load_2d(sQ + sl * kBM * 128, &tm_q, &q_full, h * kHD + sl * Cfg::kSliceElems, rt * kBM);
+            for (int j = 0; j < n; ++j) {
+                const int st = j % kKvStages;
+                const uint32_t ph = (j / kKvStages) & 1;
+                tc::mbar_wait(&kv_empty[st], ph ^ 1);
+                tc::mbar_arrive_expect_tx(&kv_full[st], Cfg::kKBytes + Cfg::kVBytes);
+                const int r0 = (c0 + j) * kBN;
+                for (int sl = 0; sl < Cfg::kSlices; ++sl) {
+                    tc::tma_load_2d(sK + st * Cfg::kKBytes + sl * kBN * 128, &tm_k, &kv_full[st],
+                                    h * kHD + sl * Cfg::kSliceElems, r0);
+                    tc::tma_load_2d(sV + st * Cfg::kVBytes + sl * kHD * 128, &tm_v, &kv_full[st],
+                                    r0 + sl * Cfg::kSliceElems, h * kHD);
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ------------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = tc::umma_idesc(BF16 ? tc::kFmtBF16 : tc::kFmtTF32, kBM, kBN);  // M=128, N=64 for both GEMMs
+        auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
+            if (BF16) tc::umma_f16(d, a, b, idesc, acc); else tc::umma_tf32(d, a, b, idesc, acc);
+        };
+        auto issue_s = [&](int j) {
+            const int st = j % kKvStages, buf = j & 1;
+            tc::mbar_wait(&kv_full[st], (j / kKvStages) & 1);
+            tc::mbar_wait(&s_empty[buf], ((j >> 1) & 1) ^ 1);
+            tc::tcgen05_fence_after();
+            if (tc::elect_one()) {
+                const uint32_t qa = tc::smem_u32(sQ), ka = tc::smem_u32(sK + st * Cfg::kKBytes);
+#pragma unroll
+                for (int sl = 0; sl < Cfg::kSlices; ++sl)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        mma(tmem + buf * kBN, tc::umma_desc_k_sw128(qa + sl * kBM * 128 + k * 32),
+                            tc::umma_desc_k_sw128(ka + sl * kBN * 128 + k * 32), (sl | k) != 0);
+                tc::umma_commit(&s_full[buf]);
+            }
+            __syncwarp();
+        };
+        tc::mbar_wait(&q_full, 0);
+        issue_s(0);
+        for (int j = 0; j < n; ++j) {
+            if (j + 1 < n) issue_s(j + 1);
+            const int st = j % kKvStages, buf = j & 1;
+            tc::mbar_wait(&p_full[buf], (j >> 1) & 1);
+            tc::mbar_wait(&o_empty, (j & 1) ^ 1);
+            tc::tcgen05_fence_after();
+            if (tc::elect_one()) {
+                const uint32_t pa = tc::smem_u32(sP + buf * Cfg::kPBytes), va = tc::smem_u32(sV + st * Cfg::kVBytes);
+#pragma unroll
+                for (int sl = 0; sl < Cfg::kSlices; ++sl)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        mma(tmem + 2 * kBN, tc::umma_desc_k_sw128(pa + sl * kBM * 128 + k * 32),
+                            tc::umma_desc_k_sw128(va + sl * kHD * 128 + k * 32), (sl | k) != 0);
+                tc::umma_commit(&o_full);
+                tc::umma_commit(&kv_empty[st]);
+                tc::umma_commit(&p_empty[buf]);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ------------------------------------------------------------------ softmax / accumulate (warps 0-3)
+        const int r = warp * 32 + lane;                       // row within the tile == TMEM lane
+        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+        float acc[kHD];
+#pragma unroll
+        for (int i = 0; i < kHD; ++i) acc[i] = 0.f;
+        float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
+        const uint32_t prow = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+        const uint32_t rx = (uint32_t)(r & 7);
+
+        auto consume_o = [&](int j) {
+            tc::mbar_wait(&o_full, j & 1);
+            tc::tcgen05_fence_after();
+            uint32_t o0[32], o1[32];
+            tc::tmem_ld_32x32(tl + 2 * kBN, o0);
+            tc::tmem_ld_32x32(tl + 2 * kBN + 32, o1);
+            tc::tmem_ld_wait();
+            tc::tcgen05_fence_before();
+            tc::mbar_arrive(&o_empty);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                acc[i] = fmaf(acc[i], corr_prev, __uint_as_float(o0[i]));
+                acc[32 + i] = fmaf(acc[32 + i], corr_prev, __uint_as_float(o1[i]));
+            }
+        };
+
+        for (int j = 0; j < n; ++j) {
+            const int buf = j & 1;
+            tc::mbar_wait(&s_full[buf], (j >> 1) & 1);
+            tc::tcgen05_fence_after();
+            uint32_t s0[32], s1[32];
+            tc::tmem_ld_32x32(tl + buf * kBN, s0);
+            tc::tmem_ld_32x32(tl + buf * kBN + 32, s1);
+            tc::tmem_ld_wait();
+            tc::tcgen05_fence_before();
+            tc::mbar_arrive(&s_empty[buf]);
+
+            const int valid = min(kBN, p.M - (c0 + j) * kBN);  // reference rows of this chunk that exist
+            float s[kBN];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                s[i] = i < valid ? __uint_as_float(s0[i]) * p.scale_log2 : -INFINITY;
+                s[32 + i] = 32 + i < valid ? __uint_as_float(s1[i]) * p.scale_log2 : -INFINITY;
+                mx = fmaxf(mx, fmaxf(s[i], s[32 + i]));
+            }
+            const float m_new = fmaxf(m_run, mx);
+            const float corr = exp2f(m_run - m_new);  // m_run = -inf on the first chunk -> 0
+            float rowsum = 0.f;
+#pragma unroll
+            for (int i = 0; i < kBN; ++i) { s[i] = exp2f(s[i] - m_new); rowsum += s[i]; }
+            l_run = fmaf(l_run, corr, rowsum);
+
+            tc::mbar_wait(&p_empty[buf], ((j >> 1) & 1) ^ 1);
+            uint8_t *pb = sP + buf * Cfg::kPBytes + prow;
+            if (BF16) {
+#pragma unroll
+                for (uint32_t c16 = 0; c16 < 8; ++c16) {
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(s[c16 * 8 + 0], s[c16 * 8 + 1]);
+                    __nv_bfloat162 h1 = __floats2bfloat162_rn(s[c16 * 8 + 2], s[c16 * 8 + 3]);
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(s[c16 * 8 + 4], s[c16 * 8 + 5]);
+                    __nv_bfloat162 h3 = __floats2bfloat162_rn(s[c16 * 8 + 6], s[c16 * 8 + 7]);
+                    uint4 v;
+                    v.x = *reinterpret_cast<uint32_t *>(&h0); v.y = *reinterpret_cast<uint32_t *>(&h1);
+                    v.z = *reinterpret_cast<uint32_t *>(&h2); v.w = *reinterpret_cast<uint32_t *>(&h3);
+                    *reinterpret_cast<uint4 *>(pb + ((c16 ^ rx) << 4)) = v;
+                }
+            } else {
+#pragma unroll
+                for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+                    for (uint32_t c16 = 0; c16 < 8; ++c16) {
+                        uint4 v;
+                        v.x = f32_to_tf32(s[sl * 32 + c16 * 4 + 0]); v.y = f32_to_tf32(s[sl * 32 + c16 * 4 + 1]);
+                        v.z = f32_to_tf32(s[sl * 32 + c16 * 4 + 2]); v.w = f32_to_tf32(s[sl * 32 + c16 * 4 + 3]);
+                        *reinterpret_cast<uint4 *>(pb + sl * kBM * 128 + ((c16 ^ rx) << 4)) = v;
+                    }
+            }
+            tc::fence_proxy_async();
+            tc::mbar_arrive(&p_full[buf]);
+
+            if (j > 0) consume_o(j - 1);
+            corr_prev = corr;
+            m_run = m_new;
+        }
+        consume_o(n - 1);
+
+        const int row = rt * kBM + r;
+        if (row < p.N) {
+            if (p.splits == 1) {
+                const float inv = 1.0f / l_run;
+                float *dst = p.out + (size_t)row * p.D + h * kHD;
+#pragma unroll
+                for (int i = 0; i < kHD; i += 4)
+                    *reinterpret_cast<float4 *>(dst + i) =
+                        make_float4(acc[i] * inv, acc[i + 1] * inv, acc[i + 2] * inv, acc[i + 3] * inv);
+            } else {
+                const size_t pr = ((size_t)split * p.heads + h) * p.Npad + row;
+                float *dst = p.part_acc + pr * kHD;
+#pragma unroll
+                for (int i = 0; i < kHD; i += 4)
+                    *reinterpret_cast<float4 *>(dst + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+                p.part_m[pr] = m_run;
+                p.part_l[pr] = l_run;
+            }
+        }
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 5) tc::tmem_dealloc(tmem, kSelsaTmemCols);
+}
+
+// out[n, h*64 + c] = sum_s acc_s * 2^(m_s - m*) / sum_s l_s * 2^(m_s - m*)
+__global__ void __launch_bounds__(256)
+selsa_merge_kernel(const SelsaParams p) {
+    const long idx = (long)blockIdx.x * 256 + threadIdx.x;  // (n, h, c4) with c4 = group of 4 channels
+    const long total = (long)p.N * p.heads * (kHD / 4);
+    if (idx >= total) return;
+    const int c4 = (int)(idx % (kHD / 4));
+    const int h = (int)((idx / (kHD / 4)) % p.heads);
+    const int n = (int)(idx / ((kHD / 4) * p.heads));
+    float mstar = -INFINITY;
+    for (int s = 0; s < p.splits; ++s) mstar = fmaxf(mstar, p.part_m[((size_t)s * p.heads + h) * p.Npad + n]);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    float l = 0.f;
+    for (int s = 0; s < p.splits; ++s) {
+        const size_t pr = ((size_t)s * p.heads + h) * p.Npad + n;
+        const float w = exp2f(p.part_m[pr] - mstar);
+        const float4 v = *reinterpret_cast<const float4 *>(p.part_acc + pr * kHD + c4 * 4);
+        a.x = fmaf(v.x, w, a.x); a.y = fmaf(v.y, w, a.y); a.z = fmaf(v.z, w, a.z); a.w = fmaf(v.w, w, a.w);
+        l = fmaf(p.part_l[pr], w, l);
+    }
+    const float inv = 1.0f / l;
+    *reinterpret_cast<float4 *>(p.out + (size_t)n * p.D + h * kHD + c4 * 4) = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
+}
+
+// [M, D] -> [D, ldv] transposition for callers that hand V row-major (v_layout 0)
+__global__ void __launch_bounds__(256)
+transpose_rows_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int M, int D, int ldv, int elem) {
+    __shared__ uint32_t tile[32][33];
+    const int m0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8) {
+        const int m = m0 + i, d = d0 + tx;
+        uint32_t v = 0;
+        if (m < M && d < D) v = elem == 4 ? reinterpret_cast<const uint32_t *>(in)[(size_t)m * D + d]
+                                          : reinterpret_cast<const uint16_t *>(in)[(size_t)m * D + d];
+        tile[i][tx] = v;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int d = d0 + i, m = m0 + tx;
+        if (d < D && m < ldv) {
+            const uint32_t v = m < M ? tile[tx][i] : 0u;
+            if (elem == 4) reinterpret_cast<uint32_t *>(out)[(size_t)d * ldv + m] = v;
+            else reinterpret_cast<uint16_t *>(out)[(size_t)d * ldv + m] = (uint16_t)v;
+        }
+    }
+}
+
+static int pick_splits(int N, int M, int heads) {
+    const int units = ceil_div(N, kBM) * heads;
+    const int nchunks = ceil_div(M, kBN);
+    int s = max(1, kNumSMs / units);
+    s = min(s, max(1, nchunks / 4));  // at least 4 chunks per split
+    return min(s, 16);
+}
+
+struct SelsaWs {
+    size_t vt_off, acc_off, m_off, l_off, bytes;
+    int splits, Npad, ldv;
+};
+static SelsaWs selsa_ws_layout(int N, int M, int heads) {
+    SelsaWs w;
+    w.splits = pick_splits(N, M, heads);
+    w.Npad = ceil_div(N, kBM) * kBM;
+    w.ldv = (int)align_up((size_t)M, 8);
+    size_t o = 0;
+    w.vt_off = o;  o = align_up(o + (size_t)heads * kHD * w.ldv * 4, 1024);   // worst case fp32 V^T copy
+    w.acc_off = o; o = align_up(o + (size_t)w.splits * heads * w.Npad * kHD * 4, 256);
+    w.m_off = o;   o = align_up(o + (size_t)w.splits * heads * w.Npad * 4, 256);
+    w.l_off = o;   o = align_up(o + (size_t)w.splits * heads * w.Npad * 4, 256);
+    w.bytes = o;
+    return w;
+}
+
+bool selsa_tc_supported(int N, int M, int heads, int d, int dtype, const void *q, const void *k, const void *v,
+                        int v_layout, int ldv) {
+    if (d != kHD || N <= 0 || M <= 0) return false;
+    const int eb = dtype == VOD_DTYPE_BF16 ? 2 : 4;
+    if (((size_t)heads * d * eb) & 15) return false;
+    if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15) return false;
+    if (v_layout == 1 && (((size_t)ldv * eb) & 15)) return false;
+    if (ceil_div(N, kBM) > 65535 || heads > 65535) return false;
+    return true;
+}
+
+size_t selsa_tc_workspace_bytes(int N, int M, int heads, int d) {
+    if (d != kHD || N <= 0 || M <= 0) return 256;
+    return selsa_ws_layout(N, M, heads).bytes;
+}
+
+template <bool BF16>
+static int launch_tc(const void *q, const void *k, const void *vt, int ldv, float *out, int N, int M, int heads,
+                     float scale, const SelsaWs &w, uint8_t *ws, cudaStream_t st) {
+    using Cfg = SelsaCfg<BF16>;
+    const int D = heads * kHD;
+    CUtensorMap tq, tk, tv;
+    int rc;
+    if ((rc = make_tmap_2d_sw128(&tq, q, Cfg::kElem, N, D, (uint64_t)D * Cfg::kElem, kBM))) return rc;
+    if ((rc = make_tmap_2d_sw128(&tk, k, Cfg::kElem, M, D, (uint64_t)D * Cfg::kElem, kBN))) return rc;
+    // V^T [D, M] with row stride ldv: columns >= M are out of bounds -> zero fill
+    if ((rc = make_tmap_2d_sw128(&tv, vt, Cfg::kElem, D, M, (uint64_t)ldv * Cfg::kElem, kHD))) return rc;
+    SelsaParams p;
+    p.out = out;
+    p.part_acc = reinterpret_cast<float *>(ws + w.acc_off);
+    p.part_m = reinterpret_cast<float *>(ws + w.m_off);
+    p.part_l = reinterpret_cast<float *>(ws + w.l_off);
+    p.N = N; p.M = M; p.heads = heads; p.D = D; p.Npad = w.Npad;
+    p.nchunks = ceil_div(M, kBN);
+    p.chunks_per_split = ceil_div(p.nchunks, w.splits);
+    p.splits = ceil_div(p.nchunks, p.chunks_per_split);  // no empty split
+    p.scale_log2 = scale * 1.4426950408889634f;
+    auto kern = selsa_tc_kernel<BF16>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+    dim3 grid(ceil_div(N, kBM), heads, p.splits);
+    kern<<<grid, kSelsaThreads, Cfg::kSmem, st>>>(tq, tk, tv, p);
+    if (p.splits > 1) {
+        const long total = (long)N * heads * (kHD / 4);
+        selsa_merge_kernel<<<(unsigned)ceil_div(total, 256L), 256, 0, st>>>(p);
+    }
+    return check_launch("vod_selsa_attn(tcgen05)");
+}
+
+int selsa_tc_launch(const void *q, const void *k, const void *v, float *out, int N, int M, int heads, int d, float scale,
+                    int dtype, int v_layout, int ldv, void *ws, size_t ws_bytes, cudaStream_t st) {
+    (void)d;
+    const SelsaWs w = selsa_ws_layout(N, M, heads);
+    if (!ws || ws_bytes < w.bytes) return fail(VOD_E_WORKSPACE, "vod_selsa_attn: workspace %zu < %zu", ws_bytes, w.bytes);
+    uint8_t *wsb = reinterpret_cast<uint8_t *>(ws);
+    if ((reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return fail(VOD_E_BADARG, "vod_selsa_attn: workspace must be 1024-byte aligned");
+    const int eb = dtype == VOD_DTYPE_BF16 ? 2 : 4;
+    const void *vt = v;
+    int ld = ldv;
+    if (v_layout == 0) {
+        const int D = heads * kHD;
+        dim3 grid(ceil_div(w.ldv, 32), ceil_div(D, 32));
+        transpose_rows_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t *>(v), wsb + w.vt_off, M, D, w.ldv, eb);
+        vt = wsb + w.vt_off;
+        ld = w.ldv;
+    }
+    if (dtype == VOD_DTYPE_BF16) return launch_tc<true>(q, k, vt, ld, out, N, M, heads, scale, w, wsb, st);
+    return launch_tc<false>(q, k, vt, ld, out, N, M, heads, scale, w, wsb, st);
+}
+
+}  // namespace vod

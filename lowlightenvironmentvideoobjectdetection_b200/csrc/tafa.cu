@@ -1,0 +1,331 @@
+// tafa.cu -- TemporalRoIAlign device code that is not the tensor-core GEMM:
+//   * tafa_weighted_sum : weighting half of temporal_attentional_feature_aggregation,
+//       mmtracking/mmtrack/models/roi_heads/roi_extractors/temporal_roi_align.py:77-97  (HBM-bound)
+//   * msra_scan_kernel  : exact fp32 most-similar-location scan (generic shapes / small cases),
+//       temporal_roi_align.py:124-181
+//   * msra_rescore_kernel: exact fp32 re-score of the tensor-core candidates + top-k + softmax +
+//       gather (the tail of the tcgen05 path in msra_gemm.cu)
+// All operate on NHWC-style rows ([.., C] contiguous): a warp covers 128 channels per 128-bit load.
+#include "common.cuh"
+#include "msra.cuh"
+
+namespace vod {
+
+// ------------------------------------------------------------------------------------ TAFA
+constexpr int kTafaWarps = 8;
+constexpr int kTafaMaxT = 64;
+
+// CTA = (n, head).  VEC=4: lanes own 4 consecutive channels, chunks of 128 channels.
+template <int VEC>
+__global__ void __launch_bounds__(kTafaWarps * 32)
+tafa_kernel(const float *__restrict__ x_all, const float *__restrict__ emb_all, float *__restrict__ out, int T1,
+            int N, int P, int C, int hs, float scale, int use_attn, int out_layout) {
+    extern __shared__ __align__(16) float tile[];          // [hs][P] (layout 0)
+    __shared__ float s_w[kTafaWarps][kTafaMaxT];
+    constexpr int CH = 32 * VEC;
+    const int n = blockIdx.x, head = blockIdx.y;
+    const int c_head = head * hs;
+    const int hs_eff = min(hs, C - c_head);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t frame_stride = (size_t)N * P * C;
+    const int nch = ceil_div(hs_eff, CH);
+
+    for (int p = warp; p < P; p += kTafaWarps) {
+        const size_t base = ((size_t)n * P + p) * C + c_head + lane * VEC;
+        float *w = s_w[warp];
+        if (use_attn) {
+            // logits_t = <emb[t], emb[0]>_head * scale
+            for (int t = 0; t < T1; ++t) {
+                float d = 0.f;
+                for (int ch = 0; ch < nch; ++ch) {
+                    if (ch * CH + lane * VEC < hs_eff) {
+                        if (VEC == 4) {
+                            float4 a = ldg_f4(emb_all + base + ch * CH);
+                            float4 b = ldg_f4(emb_all + (size_t)t * frame_stride + base + ch * CH);
+                            d = fmaf(a.x, b.x, d); d = fmaf(a.y, b.y, d); d = fmaf(a.z, b.z, d); d = fmaf(a.w, b.w, d);
+                        } else {
+                            d = fmaf(__ldg(emb_all + base + ch * CH), __ldg(emb_all + (size_t)t * frame_stride + base + ch * CH), d);
+                        }
+                    }
+                }
+                d = warp_sum(d);
+                if (lane == 0) w[t] = d * scale;
+            }
+            __syncwarp();
+            float m = -INFINITY;
+            for (int t = 0; t < T1; ++t) m = fmaxf(m, w[t]);
+            float sum = 0.f;
+            for (int t = 0; t < T1; ++t) sum += expf(w[t] - m);
+            __syncwarp();
+            if (lane == 0)
+                for (int t = 0; t < T1; ++t) w[t] = expf(w[t] - m) / sum;
+            __syncwarp();
+        }
+        const float uniform = 1.0f / (float)T1;
+        for (int ch = 0; ch < nch; ++ch) {
+            const bool on = ch * CH + lane * VEC < hs_eff;
+            float acc[VEC];
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) acc[q] = 0.f;
+            if (on) {
+#pragma unroll 4
+                for (int t = 0; t < T1; ++t) {
+                    const float wt = use_attn ? w[t] : uniform;
+                    if (VEC == 4) {
+                        float4 v = ldg_f4(x_all + (size_t)t * frame_stride + base + ch * CH);
+                        acc[0] = fmaf(wt, v.x, acc[0]); acc[1 % VEC] = fmaf(wt, v.y, acc[1 % VEC]);
+                        acc[2 % VEC] = fmaf(wt, v.z, acc[2 % VEC]); acc[3 % VEC] = fmaf(wt, v.w, acc[3 % VEC]);
+                    } else {
+                        acc[0] = fmaf(wt, __ldg(x_all + (size_t)t * frame_stride + base + ch * CH), acc[0]);
+                    }
+                }
+                if (out_layout == 0) {
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) tile[(ch * CH + lane * VEC + q) * P + p] = acc[q];
+                } else {
+                    float *dst = out + base + ch * CH;
+                    if (VEC == 4) stg_cs_f4(dst, make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]));
+                    else dst[0] = acc[0];
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (out_layout != 0) return;
+    __syncthreads();
+    const int total = hs_eff * P;
+    float *dst = out + ((size_t)n * C + c_head) * P;
+    if (VEC == 4 && (total & 3) == 0 && ((((size_t)n * C + c_head) * P) & 3) == 0) {
+        const float4 *s4 = reinterpret_cast<const float4 *>(tile);
+        for (int t = threadIdx.x; t < total / 4; t += kTafaWarps * 32) stg_cs_f4(dst + 4 * t, s4[t]);
+    } else {
+        for (int t = threadIdx.x; t < total; t += kTafaWarps * 32) dst[t] = tile[t];
+    }
+}
+
+// ------------------------------------------------------------------------------------ MSRA
+// Shared tail: given this warp's k best (value, location) pairs (sorted descending, warp-uniform),
+// softmax over the k values (temporal_roi_align.py:155) and weighted gather of the raw reference
+// features (temporal_roi_align.py:165-176).
+template <int KMAX>
+__device__ __forceinline__ void msra_emit(const float *__restrict__ ref_t /*[HW,C]*/, float *__restrict__ out_row,
+                                          int *__restrict__ idx_out, float *__restrict__ val_out, const float *val,
+                                          const int *loc, int k, int C, int lane) {
+    // No comparable candidate (an all-zero RoI row or reference pixel makes every similarity NaN, the
+    // reference divides by a zero norm without an epsilon): the reference's output row is NaN too.
+    if (!(loc[0] >= 0 && loc[0] != 0x7fffffff) || (k > 1 && !(loc[k - 1] >= 0 && loc[k - 1] != 0x7fffffff))) {
+        const float qnan = __int_as_float(0x7fc00000);
+        for (int c = lane; c < C; c += 32) out_row[c] = qnan;
+        if (lane < k) {
+            if (idx_out) idx_out[lane] = 0;
+            if (val_out) val_out[lane] = qnan;
+        }
+        return;
+    }
+    float w[KMAX];
+    float m = val[0], sum = 0.f;
+#pragma unroll
+    for (int q = 0; q < KMAX; ++q) if (q < k) { w[q] = expf(val[q] - m); sum += w[q]; }
+#pragma unroll
+    for (int q = 0; q < KMAX; ++q) if (q < k) w[q] = w[q] / sum;
+    if (lane < k) {
+        // pick element `lane` without dynamic register indexing
+        float v = val[0]; int l = loc[0];
+#pragma unroll
+        for (int q = 1; q < KMAX; ++q) if (lane == q) { v = val[q]; l = loc[q]; }
+        if (idx_out) idx_out[lane] = l;
+        if (val_out) val_out[lane] = v;
+    }
+    if ((C & 3) == 0) {
+        for (int c = lane * 4; c < C; c += 128) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < KMAX; ++q) if (q < k) {
+                float4 v = ldg_f4(ref_t + (size_t)loc[q] * C + c);
+                // topk_feats * topk_weights summed over k (temporal_roi_align.py:170-172)
+                acc.x += v.x * w[q]; acc.y += v.y * w[q]; acc.z += v.z * w[q]; acc.w += v.w * w[q];
+            }
+            stg_cs_f4(out_row + c, acc);
+        }
+    } else {
+        for (int c = lane; c < C; c += 32) {
+            float acc = 0.f;
+#pragma unroll
+            for (int q = 0; q < KMAX; ++q) if (q < k) acc += __ldg(ref_t + (size_t)loc[q] * C + c) * w[q];
+            out_row[c] = acc;
+        }
+    }
+}
+
+// insert (v, l) into a descending sorted list of length KMAX (ties: smaller location first)
+template <int KMAX>
+__device__ __forceinline__ void topk_insert(float (&val)[KMAX], int (&loc)[KMAX], float v, int l) {
+#pragma unroll
+    for (int q = 0; q < KMAX; ++q) {
+        bool better = (v > val[q]) || (v == val[q] && l < loc[q]);
+        if (better) {
+            float tv = val[q]; int tl = loc[q];
+            val[q] = v; loc[q] = l; v = tv; l = tl;
+        }
+    }
+}
+
+// warp-wide merge of per-lane sorted lists into the warp's top-k (result warp-uniform)
+template <int KMAX>
+__device__ __forceinline__ void topk_warp_merge(float (&val)[KMAX], int (&loc)[KMAX], int k, int lane) {
+    float rv[KMAX]; int rl[KMAX];
+#pragma unroll
+    for (int q = 0; q < KMAX; ++q) { rv[q] = -INFINITY; rl[q] = 0x7fffffff; }
+#pragma unroll
+    for (int r = 0; r < KMAX; ++r) {
+        if (r < k) {
+            float bv = val[0]; int bl = loc[0];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+                if (ov > bv || (ov == bv && ol < bl)) { bv = ov; bl = ol; }
+            }
+            rv[r] = bv; rl[r] = bl;
+            if (val[0] == bv && loc[0] == bl) {  // the owning lane pops its head
+#pragma unroll
+                for (int q = 0; q + 1 < KMAX; ++q) { val[q] = val[q + 1]; loc[q] = loc[q + 1]; }
+                val[KMAX - 1] = -INFINITY; loc[KMAX - 1] = 0x7fffffff;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < KMAX; ++q) { val[q] = rv[q]; loc[q] = rl[q]; }
+}
+
+constexpr int kScanWarps = 8;
+
+// warp = (row, t) task; lane scans locations lane, lane+32, ...; exact fp32:
+//   sim = sum_c (roi[c] / |roi|) * (ref[c] / |ref|)      (temporal_roi_align.py:127-142)
+__global__ void __launch_bounds__(kScanWarps * 32)
+msra_scan_kernel(const float *__restrict__ roi, const float *__restrict__ ref, const float *__restrict__ roi_norm,
+                 const float *__restrict__ ref_norm, float *__restrict__ out, int *__restrict__ idx_out,
+                 float *__restrict__ val_out, int NP, int C, int T, int HW, int k) {
+    extern __shared__ float s_roi[];  // [kScanWarps][C]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long task = (long)blockIdx.x * kScanWarps + warp;
+    if (task >= (long)NP * T) return;
+    const int row = (int)(task / T), t = (int)(task % T);
+    float *q = s_roi + (size_t)warp * C;
+    const float qn = roi_norm[row];
+    for (int c = lane; c < C; c += 32) q[c] = __fdiv_rn(__ldg(roi + (size_t)row * C + c), qn);
+    __syncwarp();
+    const float *ref_t = ref + (size_t)t * HW * C;
+    float val[kMsraMaxK]; int loc[kMsraMaxK];
+#pragma unroll
+    for (int i = 0; i < kMsraMaxK; ++i) { val[i] = -INFINITY; loc[i] = 0x7fffffff; }
+    for (int l = lane; l < HW; l += 32) {
+        const float rn = ref_norm[(size_t)t * HW + l];
+        const float *r = ref_t + (size_t)l * C;
+        float s = 0.f;
+        for (int c = 0; c < C; ++c) s = fmaf(q[c], __fdiv_rn(__ldg(r + c), rn), s);
+        topk_insert<kMsraMaxK>(val, loc, s, l);
+    }
+    topk_warp_merge<kMsraMaxK>(val, loc, k, lane);
+    msra_emit<kMsraMaxK>(ref_t, out + ((size_t)t * NP + row) * C, idx_out ? idx_out + ((size_t)row * T + t) * k : nullptr,
+                         val_out ? val_out + ((size_t)row * T + t) * k : nullptr, val, loc, k, C, lane);
+}
+
+// warp = (row, t) task; candidates cand[(row*T + t)*KC + j] (location or -1) from the tensor-core pass.
+__global__ void __launch_bounds__(kScanWarps * 32)
+msra_rescore_kernel(const float *__restrict__ roi, const float *__restrict__ ref, const float *__restrict__ roi_norm,
+                    const float *__restrict__ ref_norm, const int *__restrict__ cand, int KC,
+                    float *__restrict__ out, int *__restrict__ idx_out, float *__restrict__ val_out, int NP, int C,
+                    int T, int HW, int k) {
+    extern __shared__ float s_roi[];  // [kScanWarps][C]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long task = (long)blockIdx.x * kScanWarps + warp;
+    if (task >= (long)NP * T) return;
+    const int row = (int)(task / T), t = (int)(task % T);
+    float *q = s_roi + (size_t)warp * C;
+    const float qn = roi_norm[row];
+    for (int c = lane; c < C; c += 32) q[c] = __fdiv_rn(__ldg(roi + (size_t)row * C + c), qn);
+    __syncwarp();
+    const float *ref_t = ref + (size_t)t * HW * C;
+    float val[kMsraMaxK]; int loc[kMsraMaxK];
+#pragma unroll
+    for (int i = 0; i < kMsraMaxK; ++i) { val[i] = -INFINITY; loc[i] = 0x7fffffff; }
+    const int *cd = cand + (size_t)task * KC;
+    for (int j = 0; j < KC; ++j) {
+        const int l = cd[j];
+        if (l < 0 || l >= HW) continue;  // warp-uniform
+        const float rn = ref_norm[(size_t)t * HW + l];
+        const float *r = ref_t + (size_t)l * C;
+        float s = 0.f;
+        if ((C & 3) == 0) {
+            for (int c = lane * 4; c < C; c += 128) {
+                float4 v = ldg_f4(r + c);
+                s = fmaf(q[c], __fdiv_rn(v.x, rn), s); s = fmaf(q[c + 1], __fdiv_rn(v.y, rn), s);
+                s = fmaf(q[c + 2], __fdiv_rn(v.z, rn), s); s = fmaf(q[c + 3], __fdiv_rn(v.w, rn), s);
+            }
+        } else {
+            for (int c = lane; c < C; c += 32) s = fmaf(q[c], __fdiv_rn(__ldg(r + c), rn), s);
+        }
+        s = warp_sum(s);
+        topk_insert<kMsraMaxK>(val, loc, s, l);  // identical on all lanes
+    }
+    msra_emit<kMsraMaxK>(ref_t, out + ((size_t)t * NP + row) * C, idx_out ? idx_out + ((size_t)row * T + t) * k : nullptr,
+                         val_out ? val_out + ((size_t)row * T + t) * k : nullptr, val, loc, k, C, lane);
+}
+
+int msra_launch_scan(const float *roi, const float *ref, const float *roi_norm, const float *ref_norm, float *out,
+                     int *idx_out, float *val_out, int NP, int C, int T, int HW, int k, cudaStream_t st) {
+    size_t smem = sizeof(float) * kScanWarps * C;
+    if (smem > 40 * 1024) cudaFuncSetAttribute(msra_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    long tasks = (long)NP * T;
+    msra_scan_kernel<<<(unsigned)ceil_div(tasks, (long)kScanWarps), kScanWarps * 32, smem, st>>>(
+        roi, ref, roi_norm, ref_norm, out, idx_out, val_out, NP, C, T, HW, k);
+    return check_launch("msra_scan");
+}
+
+int msra_launch_rescore(const float *roi, const float *ref, const float *roi_norm, const float *ref_norm,
+                        const int *cand, int KC, float *out, int *idx_out, float *val_out, int NP, int C, int T,
+                        int HW, int k, cudaStream_t st) {
+    size_t smem = sizeof(float) * kScanWarps * C;
+    if (smem > 40 * 1024) cudaFuncSetAttribute(msra_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    long tasks = (long)NP * T;
+    msra_rescore_kernel<<<(unsigned)ceil_div(tasks, (long)kScanWarps), kScanWarps * 32, smem, st>>>(
+        roi, ref, roi_norm, ref_norm, cand, KC, out, idx_out, val_out, NP, C, T, HW, k);
+    return check_launch("msra_rescore");
+}
+
+}  // namespace vod
+
+using namespace vod;
+
+extern "C" int vod_tafa_weighted_sum(const float *x_all, const float *emb_all, float *out, int T1, int N, int P,
+                                     int C, int heads, int out_layout, vod_stream_t stream) {
+    if (N == 0) return VOD_OK;
+    VOD_REQUIRE(x_all && out, "vod_tafa_weighted_sum: null pointer");
+    VOD_REQUIRE(T1 > 0 && T1 <= kTafaMaxT, "vod_tafa_weighted_sum: T1=%d not in [1,%d]", T1, kTafaMaxT);
+    VOD_REQUIRE(N > 0 && P > 0 && C > 0, "vod_tafa_weighted_sum: bad dims");
+    VOD_REQUIRE(out_layout == 0 || out_layout == 1, "vod_tafa_weighted_sum: out_layout");
+    const int use_attn = heads > 0;
+    VOD_REQUIRE(!use_attn || emb_all, "vod_tafa_weighted_sum: emb_all required when heads > 0");
+    VOD_REQUIRE(!use_attn || C % heads == 0, "vod_tafa_weighted_sum: C=%d not divisible by heads=%d", C, heads);
+    int hs = use_attn ? C / heads : min(C, 128);
+    int groups = use_attn ? heads : ceil_div(C, hs);
+    // reference: / float(c_embed / num_attention_blocks) ** 0.5 (temporal_roi_align.py:86-87)
+    float scale = use_attn ? (float)(1.0 / sqrt((double)C / (double)heads)) : 1.f;
+    size_t smem = out_layout == 0 ? sizeof(float) * (size_t)hs * P : 0;
+    VOD_REQUIRE(smem <= 200 * 1024, "vod_tafa_weighted_sum: head size %d x %d bins too large", hs, P);
+    const bool vec4 = (hs % 4 == 0) && (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(x_all) & 15) == 0) &&
+                      (!emb_all || (reinterpret_cast<uintptr_t>(emb_all) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    dim3 grid(N, groups);
+    if (vec4) {
+        if (smem > 40 * 1024) cudaFuncSetAttribute(tafa_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        tafa_kernel<4><<<grid, kTafaWarps * 32, smem, as_stream(stream)>>>(x_all, emb_all, out, T1, N, P, C, hs, scale,
+                                                                         use_attn, out_layout);
+    } else {
+        if (smem > 40 * 1024) cudaFuncSetAttribute(tafa_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        tafa_kernel<1><<<grid, kTafaWarps * 32, smem, as_stream(stream)>>>(x_all, emb_all, out, T1, N, P, C, hs, scale,
+                                                                         use_attn, out_layout);
+    }
+    return check_launch("vod_tafa_weighted_sum");
+}

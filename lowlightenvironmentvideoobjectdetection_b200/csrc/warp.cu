@@ -1,0 +1,262 @@
+// warp.cu -- (2) flow-guided bilinear warp and the FGFA cosine-similarity weighting.
+//   flow_warp        : mmtracking/mmtrack/core/motion/flow.py:4-41 (closed form)
+//   embed weighting  : mmtracking/mmtrack/models/aggregators/embed_aggregator.py:71-81
+//   fused variant    : the weighting re-warps the raw feature memory on the fly, as FGFA uses it at
+//                      mmtracking/mmtrack/models/vid/fgfa.py:275-283
+// All three are HBM-bound and NCHW-native (the tensors come from / go to cuDNN convs in NCHW):
+// thread = pixel (w fastest) so every tap of a warp is a coalesced run of one channel plane.
+#include "common.cuh"
+
+namespace vod {
+
+struct Taps {
+    int i00, i01, i10, i11;   // plane offsets
+    float w00, w01, w10, w11; // nw, ne, sw, se
+};
+
+// src index/lerp of ATen upsample_bilinear2d(align_corners=False) with a user scale factor
+__device__ __forceinline__ void resize_src(int dst, float inv_scale, int in_size, int &i0, int &i1, float &l1) {
+    float src = __fsub_rn(__fmul_rn((float)dst + 0.5f, inv_scale), 0.5f);
+    if (src < 0.f) src = 0.f;
+    int a = (int)src;
+    if (a > in_size - 1) a = in_size - 1;
+    i0 = a;
+    i1 = a + (a < in_size - 1 ? 1 : 0);
+    l1 = src - (float)a;
+}
+
+// Taps of pixel (h, w) of frame n: resized+scaled flow -> normalised grid -> border-clamped bilinear.
+__device__ __forceinline__ Taps make_taps(const float *__restrict__ flow_n, int h, int w, int H, int W, int Hf,
+                                          int Wf, float s, float inv_s) {
+    int y0, y1, x0, x1;
+    float ly, lx;
+    resize_src(h, inv_s, Hf, y0, y1, ly);
+    resize_src(w, inv_s, Wf, x0, x1, lx);
+    float f[2];
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+        const float *p = flow_n + (size_t)ch * Hf * Wf;
+        float a = __ldg(p + (size_t)y0 * Wf + x0), b = __ldg(p + (size_t)y0 * Wf + x1);
+        float c = __ldg(p + (size_t)y1 * Wf + x0), d = __ldg(p + (size_t)y1 * Wf + x1);
+        float top = __fadd_rn(__fmul_rn(1.0f - lx, a), __fmul_rn(lx, b));
+        float bot = __fadd_rn(__fmul_rn(1.0f - lx, c), __fmul_rn(lx, d));
+        f[ch] = __fmul_rn(__fadd_rn(__fmul_rn(1.0f - ly, top), __fmul_rn(ly, bot)), s);
+    }
+    // grid = (w + fx) / W * 2 - 1  (flow.py:33-34), then align_corners=True un-normalisation + border clamp
+    float gx = __fsub_rn(__fmul_rn(__fdiv_rn(__fadd_rn((float)w, f[0]), (float)W), 2.0f), 1.0f);
+    float gy = __fsub_rn(__fmul_rn(__fdiv_rn(__fadd_rn((float)h, f[1]), (float)H), 2.0f), 1.0f);
+    float px = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.0f), 2.0f), (float)(W - 1));
+    float py = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.0f), 2.0f), (float)(H - 1));
+    px = fminf(fmaxf(px, 0.f), (float)(W - 1));
+    py = fminf(fmaxf(py, 0.f), (float)(H - 1));
+    int ix0 = (int)floorf(px), iy0 = (int)floorf(py);
+    float tx = px - (float)ix0, ty = py - (float)iy0;
+    int ix1 = ix0 + 1, iy1 = iy0 + 1;
+    bool vx = ix1 <= W - 1, vy = iy1 <= H - 1;
+    if (!vx) ix1 = W - 1;
+    if (!vy) iy1 = H - 1;
+    Taps t;
+    t.i00 = iy0 * W + ix0; t.i01 = iy0 * W + ix1; t.i10 = iy1 * W + ix0; t.i11 = iy1 * W + ix1;
+    t.w00 = (1.0f - tx) * (1.0f - ty);
+    t.w01 = vx ? tx * (1.0f - ty) : 0.f;
+    t.w10 = vy ? (1.0f - tx) * ty : 0.f;
+    t.w11 = (vx && vy) ? tx * ty : 0.f;
+    return t;
+}
+
+__device__ __forceinline__ float apply_taps(const float *__restrict__ plane, const Taps &t) {
+    float v = __ldg(plane + t.i00) * t.w00;
+    v = fmaf(__ldg(plane + t.i01), t.w01, v);
+    v = fmaf(__ldg(plane + t.i10), t.w10, v);
+    v = fmaf(__ldg(plane + t.i11), t.w11, v);
+    return v;
+}
+
+constexpr int kWarpPix = 128;   // pixels per CTA
+constexpr int kWarpCh = 64;     // channels per CTA
+
+// grid (pixel blocks, channel chunks, N)
+__global__ void __launch_bounds__(kWarpPix)
+flow_warp_kernel(const float *__restrict__ x, const float *__restrict__ flow, float *__restrict__ out, int C,
+                 int H, int W, int Hf, int Wf, float s, float inv_s) {
+    const int n = blockIdx.z;
+    const int p = blockIdx.x * kWarpPix + threadIdx.x;
+    const int HW = H * W;
+    if (p >= HW) return;
+    const Taps t = make_taps(flow + (size_t)n * 2 * Hf * Wf, p / W, p % W, H, W, Hf, Wf, s, inv_s);
+    const int c0 = blockIdx.y * kWarpCh, c1 = min(C, c0 + kWarpCh);
+    const float *xp = x + ((size_t)n * C + c0) * HW;
+    float *op = out + ((size_t)n * C + c0) * HW + p;
+    int c = c0;
+    for (; c + 4 <= c1; c += 4) {
+        float v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = apply_taps(xp + (size_t)(c - c0 + q) * HW, t);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) __stcs(op + (size_t)(c - c0 + q) * HW, v[q]);
+    }
+    for (; c < c1; ++c) __stcs(op + (size_t)(c - c0) * HW, apply_taps(xp + (size_t)(c - c0) * HW, t));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Embed weighting.  CTA = 8 pixels x 32 channel lanes (256 threads).
+//   phase A: per frame t, dot(e_t, e_k), |e_t|^2, |e_k|^2 over C  -> cos_t -> softmax over t
+//   phase B: out[c] = sum_t w_t * ref_x[t][c]   (or the on-the-fly warp of raw_x[t][c])
+constexpr int kEwPix = 8;
+constexpr int kEwLanes = 32;
+constexpr int kEwTch = 8;  // frames per register pass
+
+template <bool FUSED_WARP>
+__global__ void __launch_bounds__(kEwPix *kEwLanes)
+embed_weighted_sum_kernel(const float *__restrict__ key_emb, const float *__restrict__ ref_emb,
+                          const float *__restrict__ ref_x, const float *__restrict__ flow,
+                          const float *__restrict__ key_x, int key_slot, float *__restrict__ out, int T,
+                          int C, int Cx, int H, int W, int Hf, int Wf, float s, float inv_s) {
+    extern __shared__ float sm[];
+    // layout: wts[T][8] | red[3][32][8] | (FUSED) taps[T][8] (8 words each)
+    float *wts = sm;
+    float *red = wts + (size_t)T * kEwPix;
+    Taps *taps = reinterpret_cast<Taps *>(red + 3 * kEwLanes * kEwPix);
+    const int HW = H * W;
+    const int pl = threadIdx.x % kEwPix, cg = threadIdx.x / kEwPix;
+    const int p = blockIdx.x * kEwPix + pl;
+    const bool pv = p < HW;
+    const int pc = pv ? p : HW - 1;
+
+    // |e_k|^2
+    float kk = 0.f;
+    for (int c = cg; c < C; c += kEwLanes) { float v = __ldg(key_emb + (size_t)c * HW + pc); kk = fmaf(v, v, kk); }
+    red[(0 * kEwLanes + cg) * kEwPix + pl] = kk;
+    __syncthreads();
+    if (cg == 0) {
+        float a = 0.f;
+        for (int g = 0; g < kEwLanes; ++g) a += red[(0 * kEwLanes + g) * kEwPix + pl];
+        red[(2 * kEwLanes + 0) * kEwPix + pl] = a;  // stash |e_k|^2
+    }
+    __syncthreads();
+    const float knorm = sqrtf(red[(2 * kEwLanes + 0) * kEwPix + pl]);
+    __syncthreads();
+
+    for (int t0 = 0; t0 < T; t0 += kEwTch) {
+        float dot[kEwTch], nn[kEwTch];
+#pragma unroll
+        for (int q = 0; q < kEwTch; ++q) { dot[q] = 0.f; nn[q] = 0.f; }
+        for (int c = cg; c < C; c += kEwLanes) {
+            const float kv = __ldg(key_emb + (size_t)c * HW + pc);
+#pragma unroll
+            for (int q = 0; q < kEwTch; ++q) {
+                if (t0 + q < T) {
+                    float v = __ldg(ref_emb + ((size_t)(t0 + q) * C + c) * HW + pc);
+                    dot[q] = fmaf(v, kv, dot[q]);
+                    nn[q] = fmaf(v, v, nn[q]);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kEwTch; ++q) {
+            if (t0 + q < T) {  // uniform
+                red[(0 * kEwLanes + cg) * kEwPix + pl] = dot[q];
+                red[(1 * kEwLanes + cg) * kEwPix + pl] = nn[q];
+                __syncthreads();
+                if (cg == 0) {
+                    float d = 0.f, n2 = 0.f;
+                    for (int g = 0; g < kEwLanes; ++g) {
+                        d += red[(0 * kEwLanes + g) * kEwPix + pl];
+                        n2 += red[(1 * kEwLanes + g) * kEwPix + pl];
+                    }
+                    // (e_t/|e_t|) . (e_k/|e_k|): no epsilon, as the reference (embed_aggregator.py:71,76)
+                    wts[(t0 + q) * kEwPix + pl] = d / (sqrtf(n2) * knorm);
+                }
+                __syncthreads();
+            }
+        }
+    }
+    // softmax over t (thread per pixel), and the warp taps for the fused variant
+    if (cg == 0) {
+        float m = -INFINITY;
+        for (int t = 0; t < T; ++t) m = fmaxf(m, wts[t * kEwPix + pl]);
+        float sum = 0.f;
+        for (int t = 0; t < T; ++t) { float e = expf(wts[t * kEwPix + pl] - m); wts[t * kEwPix + pl] = e; sum += e; }
+        for (int t = 0; t < T; ++t) wts[t * kEwPix + pl] = wts[t * kEwPix + pl] / sum;
+    }
+    if (FUSED_WARP) {
+        for (int t = cg; t < T; t += kEwLanes)
+            taps[t * kEwPix + pl] = make_taps(flow + (size_t)t * 2 * Hf * Wf, pc / W, pc % W, H, W, Hf, Wf, s, inv_s);
+    }
+    __syncthreads();
+    if (!pv) return;
+    for (int c = cg; c < Cx; c += kEwLanes) {
+        float acc = 0.f;
+        for (int t = 0; t < T; ++t) {
+            float v;
+            if (FUSED_WARP) {
+                if (t == key_slot) v = __ldg(key_x + (size_t)c * HW + p);
+                else v = apply_taps(ref_x + ((size_t)t * Cx + c) * HW, taps[t * kEwPix + pl]);
+            } else {
+                v = __ldg(ref_x + ((size_t)t * Cx + c) * HW + p);
+            }
+            acc = fmaf(v, wts[t * kEwPix + pl], acc);
+        }
+        __stcs(out + (size_t)c * HW + p, acc);
+    }
+}
+
+static void flow_scale(int W, int Wf, float &s, float &inv_s) {
+    double sd = (double)W / (double)Wf;  // python float scale_factor, flow.py:17
+    s = (float)sd;
+    inv_s = (float)(1.0 / sd);           // ATen: static_cast<float>(1.0 / scale_factor)
+}
+
+}  // namespace vod
+
+using namespace vod;
+
+extern "C" int vod_flow_warp(const float *x, const float *flow, float *out, int N, int C, int H, int W, int Hf,
+                             int Wf, vod_stream_t stream) {
+    if (N == 0 || C == 0) return VOD_OK;
+    VOD_REQUIRE(x && flow && out, "vod_flow_warp: null pointer");
+    VOD_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && Hf > 0 && Wf > 0, "vod_flow_warp: bad dims");
+    VOD_REQUIRE(N <= 65535, "vod_flow_warp: N too large");
+    float s, inv_s;
+    flow_scale(W, Wf, s, inv_s);
+    dim3 grid(ceil_div(H * W, kWarpPix), ceil_div(C, kWarpCh), N);
+    flow_warp_kernel<<<grid, kWarpPix, 0, as_stream(stream)>>>(x, flow, out, C, H, W, Hf, Wf, s, inv_s);
+    return check_launch("vod_flow_warp");
+}
+
+static int launch_embed(bool fused, const float *key_emb, const float *ref_emb, const float *ref_x,
+                        const float *flow, const float *key_x, int key_slot, float *out, int T, int C, int Cx,
+                        int H, int W, int Hf, int Wf, vod_stream_t stream) {
+    VOD_REQUIRE(key_emb && ref_emb && ref_x && out, "vod_embed_weighted_sum: null pointer");
+    VOD_REQUIRE(T > 0 && C > 0 && Cx > 0 && H > 0 && W > 0, "vod_embed_weighted_sum: bad dims");
+    size_t smem = sizeof(float) * ((size_t)T * kEwPix + 3 * kEwLanes * kEwPix) + (fused ? sizeof(Taps) * (size_t)T * kEwPix : 0);
+    VOD_REQUIRE(smem <= 200 * 1024, "vod_embed_weighted_sum: T=%d too large", T);
+    float s = 1.f, inv_s = 1.f;
+    if (fused) flow_scale(W, Wf, s, inv_s);
+    dim3 grid(ceil_div(H * W, kEwPix));
+    if (fused) {
+        if (smem > 40 * 1024)
+            cudaFuncSetAttribute(embed_weighted_sum_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        embed_weighted_sum_kernel<true><<<grid, kEwPix * kEwLanes, smem, as_stream(stream)>>>(
+            key_emb, ref_emb, ref_x, flow, key_x, key_slot, out, T, C, Cx, H, W, Hf, Wf, s, inv_s);
+    } else {
+        if (smem > 40 * 1024)
+            cudaFuncSetAttribute(embed_weighted_sum_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        embed_weighted_sum_kernel<false><<<grid, kEwPix * kEwLanes, smem, as_stream(stream)>>>(
+            key_emb, ref_emb, ref_x, nullptr, nullptr, -1, out, T, C, Cx, H, W, 1, 1, s, inv_s);
+    }
+    return check_launch("vod_embed_weighted_sum");
+}
+
+extern "C" int vod_embed_weighted_sum(const float *key_emb, const float *ref_emb, const float *ref_x, float *out,
+                                      int T, int C, int Cx, int HW, vod_stream_t stream) {
+    return launch_embed(false, key_emb, ref_emb, ref_x, nullptr, nullptr, -1, out, T, C, Cx, 1, HW, 1, 1, stream);
+}
+
+extern "C" int vod_fgfa_warp_weighted_sum(const float *key_emb, const float *ref_emb, const float *raw_x,
+                                          const float *flow, const float *key_x, int key_slot, float *out, int T,
+                                          int C, int Cx, int H, int W, int Hf, int Wf, vod_stream_t stream) {
+    VOD_REQUIRE(flow, "vod_fgfa_warp_weighted_sum: null flow");
+    VOD_REQUIRE(key_slot < 0 || key_x, "vod_fgfa_warp_weighted_sum: key_x required with key_slot");
+    return launch_embed(true, key_emb, ref_emb, raw_x, flow, key_x, key_slot, out, T, C, Cx, H, W, Hf, Wf, stream);
+}

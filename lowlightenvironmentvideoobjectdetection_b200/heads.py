@@ -1,0 +1,131 @@
+"""Callers of the hot path, restated as thin host Python (they stay Python/torch in the reference too;
+the FC layers remain nn.Linear / cuBLAS).  Inference only.
+
+  SelsaBBoxHead  mmtracking/mmtrack/models/roi_heads/bbox_heads/selsa_bbox_head.py:8-84 on top of
+                 mmdet ConvFCBBoxHead (mmdetection/mmdet/models/roi_heads/bbox_heads/convfc_bbox_head.py:85-124)
+                 and BBoxHead.get_bboxes (mmdetection/mmdet/models/roi_heads/bbox_heads/bbox_head.py:269-373)
+  SelsaRoIHead   mmtracking/mmtrack/models/roi_heads/selsa_roi_head.py:80-97,147-187
+
+Parameter names follow the reference state_dict: shared_fcs.{i}, aggregator.{i}.{fc_embed,ref_fc_embed,fc,ref_fc},
+fc_cls, fc_reg, bbox_roi_extractor.embed_network.conv.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .post_processing import bbox2roi, delta2bbox, multiclass_nms
+from .registry import HEADS, build_aggregator, build_roi_extractor
+
+
+@HEADS.register_module()
+class SelsaBBoxHead(nn.Module):
+    """Shared-FC bbox head with a SELSA aggregator after every shared FC (no shared convs / avg pool,
+    as in every config of the reference)."""
+
+    def __init__(self, aggregator, num_shared_fcs=2, in_channels=512, fc_out_channels=1024, roi_feat_size=7,
+                 num_classes=30, reg_class_agnostic=False, target_means=(0., 0., 0., 0.),
+                 target_stds=(0.2, 0.2, 0.2, 0.2), **kwargs):
+        super().__init__()
+        self.num_shared_fcs = num_shared_fcs
+        self.num_classes = num_classes
+        self.reg_class_agnostic = reg_class_agnostic
+        self.target_means, self.target_stds = tuple(target_means), tuple(target_stds)
+        self.shared_fcs = nn.ModuleList()
+        last = in_channels * roi_feat_size * roi_feat_size
+        for _ in range(num_shared_fcs):
+            self.shared_fcs.append(nn.Linear(last, fc_out_channels))
+            last = fc_out_channels
+        self.fc_cls = nn.Linear(last, num_classes + 1)
+        self.fc_reg = nn.Linear(last, 4 if reg_class_agnostic else 4 * num_classes)
+        self.aggregator = nn.ModuleList([build_aggregator(aggregator) for _ in range(num_shared_fcs)])
+        self.init_weights()
+
+    def init_weights(self):
+        """mmdet defaults: xavier for shared fcs, N(0, 0.01) for fc_cls, N(0, 0.001) for fc_reg."""
+        for fc in self.shared_fcs:
+            nn.init.xavier_uniform_(fc.weight)
+            nn.init.constant_(fc.bias, 0)
+        nn.init.normal_(self.fc_cls.weight, 0, 0.01)
+        nn.init.constant_(self.fc_cls.bias, 0)
+        nn.init.normal_(self.fc_reg.weight, 0, 0.001)
+        nn.init.constant_(self.fc_reg.bias, 0)
+
+    @torch.no_grad()
+    def forward(self, x, ref_x):
+        """x [N, C, 7, 7] key RoI features, ref_x [M, C, 7, 7] reference RoI features
+        -> (cls_score [N, classes+1], bbox_pred [N, 4*classes])   (selsa_bbox_head.py:25-84)."""
+        x = x.flatten(1)
+        ref_x = ref_x.flatten(1)
+        for i, fc in enumerate(self.shared_fcs):
+            x = fc(x)
+            ref_x = fc(ref_x)
+            x = x + self.aggregator[i](x, ref_x)   # aggregator sees the PRE-ReLU features (:56)
+            ref_x = F.relu(ref_x)
+            x = F.relu(x)
+        return self.fc_cls(x), self.fc_reg(x)
+
+    @torch.no_grad()
+    def get_bboxes(self, rois, cls_score, bbox_pred, img_shape, scale_factor, rescale=False, cfg=None):
+        """bbox_head.py:269-373 (non-batch mode)."""
+        scores = F.softmax(cls_score, dim=-1)
+        bboxes = delta2bbox(rois[:, 1:], bbox_pred, self.target_means, self.target_stds, max_shape=img_shape)
+        if rescale and bboxes.size(0) > 0:
+            sf = bboxes.new_tensor(scale_factor)
+            bboxes = (bboxes.view(bboxes.size(0), -1, 4) / sf).view(bboxes.size(0), -1)
+        if cfg is None:
+            return bboxes, scores
+        return multiclass_nms(bboxes, scores, cfg['score_thr'], cfg['nms'], cfg['max_per_img'])
+
+
+@HEADS.register_module()
+class SelsaRoIHead(nn.Module):
+    """selsa roi head (bbox branch, test path)."""
+
+    def __init__(self, bbox_roi_extractor, bbox_head, test_cfg=None, **kwargs):
+        super().__init__()
+        self.bbox_roi_extractor = build_roi_extractor(bbox_roi_extractor)
+        head_cfg = dict(bbox_head)
+        head_cfg.setdefault('type', 'SelsaBBoxHead')
+        if 'bbox_coder' in head_cfg:
+            coder = head_cfg.pop('bbox_coder')
+            head_cfg.setdefault('target_means', coder.get('target_means', (0., 0., 0., 0.)))
+            head_cfg.setdefault('target_stds', coder.get('target_stds', (0.2, 0.2, 0.2, 0.2)))
+        self.bbox_head = HEADS.build(head_cfg)
+        self.test_cfg = test_cfg or dict(score_thr=0.0001, nms=dict(type='nms', iou_threshold=0.5), max_per_img=100)
+
+    @torch.no_grad()
+    def _bbox_forward(self, x, ref_x, rois, ref_rois):
+        """selsa_roi_head.py:80-97."""
+        n_in = self.bbox_roi_extractor.num_inputs
+        bbox_feats = self.bbox_roi_extractor(x[:n_in], rois, ref_feats=ref_x[:n_in])
+        ref_bbox_feats = self.bbox_roi_extractor(ref_x[:n_in], ref_rois)
+        cls_score, bbox_pred = self.bbox_head(bbox_feats, ref_bbox_feats)
+        return dict(cls_score=cls_score, bbox_pred=bbox_pred, bbox_feats=bbox_feats)
+
+    @torch.no_grad()
+    def simple_test_bboxes(self, x, ref_x, proposals, ref_proposals, img_metas, rcnn_test_cfg, rescale=False):
+        """selsa_roi_head.py:147-187."""
+        rois = bbox2roi(proposals)
+        ref_rois = bbox2roi(ref_proposals)
+        bbox_results = self._bbox_forward(x, ref_x, rois, ref_rois)
+        img_shapes = tuple(meta['img_shape'] for meta in img_metas)
+        scale_factors = tuple(meta['scale_factor'] for meta in img_metas)
+        cls_score, bbox_pred = bbox_results['cls_score'], bbox_results['bbox_pred']
+        num_per_img = tuple(len(p) for p in proposals)
+        rois = rois.split(num_per_img, 0)
+        cls_score = cls_score.split(num_per_img, 0)
+        bbox_pred = bbox_pred.split(num_per_img, 0)
+        det_bboxes, det_labels = [], []
+        for i in range(len(proposals)):
+            det_bbox, det_label = self.bbox_head.get_bboxes(rois[i], cls_score[i], bbox_pred[i], img_shapes[i],
+                                                            scale_factors[i], rescale=rescale, cfg=rcnn_test_cfg)
+            det_bboxes.append(det_bbox)
+            det_labels.append(det_label)
+        return det_bboxes, det_labels
+
+    @torch.no_grad()
+    def simple_test(self, x, ref_x, proposals_list, ref_proposals_list, img_metas, proposals=None, rescale=False):
+        """selsa_roi_head.py:115-145; returns (det_bboxes, det_labels) lists (device tensors; the
+        per-class numpy split of bbox2result is left to the caller)."""
+        return self.simple_test_bboxes(x, ref_x, proposals_list, ref_proposals_list, img_metas, self.test_cfg,
+                                       rescale=rescale)

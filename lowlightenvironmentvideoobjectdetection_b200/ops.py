@@ -1,0 +1,318 @@
+"""Host-side mirror of the mmcv symbols the hot path binds, plus thin functional
+wrappers over the C ABI (include/vodagg.h).  PyTorch is used only for device
+memory and streams; every op below launches hand-written sm_100a kernels from
+libvodagg.so and raises if the library or a CUDA device is missing.
+
+Mirrors (reference call sites, paths relative to the reference root):
+  RoIAlign      mmcv.ops.RoIAlign, built at
+                mmdetection/mmdet/models/roi_heads/roi_extractors/base_roi_extractor.py:49-55
+  nms           mmcv.ops.nms
+  batched_nms   mmcv.ops.nms.batched_nms, called at
+                mmdetection/mmdet/core/post_processing/bbox_nms.py:84 and
+                mmdetection/mmdet/models/dense_heads/rpn_head.py:233-235
+"""
+import ctypes
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+_ws = _lib.Workspace()
+
+
+def _pair(x):
+    return (int(x), int(x)) if isinstance(x, int) else (int(x[0]), int(x[1]))
+
+
+def _f32c(t):
+    """fp32 + contiguous view of a tensor (no copy when already so)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# ----------------------------------------------------------------------------- layout
+def to_nhwc(x, want_norm=False, want_unit_bf16=False):
+    """[B,C,H,W] fp32 -> ([B,H,W,C] fp32 contiguous, norm [B*H*W] | None, unit bf16 [B*H*W, C] | None).
+
+    A channels_last input is consumed in place (zero copy) unless norms are requested."""
+    _lib.require_cuda(x)
+    assert x.dim() == 4
+    x = x.float() if x.dtype != torch.float32 else x
+    B, C, H, W = x.shape
+    if not (want_norm or want_unit_bf16) and x.is_contiguous(memory_format=torch.channels_last) and B * C * H * W > 0:
+        return x.permute(0, 2, 3, 1), None, None
+    nhwc = torch.empty((B, H, W, C), dtype=torch.float32, device=x.device)
+    norm = torch.empty((B * H * W,), dtype=torch.float32, device=x.device) if (want_norm or want_unit_bf16) else None
+    unit = torch.empty((B * H * W, C), dtype=torch.bfloat16, device=x.device) if want_unit_bf16 else None
+    if x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous():
+        # already NHWC in memory: only the norms / unit copy are missing
+        nhwc = x.permute(0, 2, 3, 1)
+        if B * H * W:
+            _lib.call('vod_rows_l2norm', _lib.ptr(nhwc), _lib.ptr(norm), _lib.ptr(unit), B * H * W, C,
+                      _lib.stream_ptr(x.device))
+        return nhwc, norm, unit
+    x = x.contiguous()
+    if B * H * W:
+        _lib.call('vod_nchw_to_nhwc', _lib.ptr(x), _lib.ptr(nhwc), _lib.ptr(norm), _lib.ptr(unit), B, C, H, W,
+                  _lib.stream_ptr(x.device))
+    return nhwc, norm, unit
+
+
+# ----------------------------------------------------------------------------- (1) RoIAlign
+def roi_align_nhwc(feat_nhwc, rois, output_size, spatial_scale=1.0, sampling_ratio=0, aligned=True,
+                   out_nhwc=False, out=None):
+    """feat_nhwc [B,H,W,C] contiguous fp32, rois [K,5] -> [K,C,ph,pw] (or [K,ph,pw,C] when out_nhwc).
+    ``out``: optional preallocated contiguous fp32 destination of that many elements."""
+    _lib.require_cuda(feat_nhwc, rois)
+    ph, pw = _pair(output_size)
+    B, H, W, C = feat_nhwc.shape
+    rois = _f32c(rois)
+    K = rois.shape[0]
+    shape = (K, ph, pw, C) if out_nhwc else (K, C, ph, pw)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=feat_nhwc.device)
+    else:
+        assert out.is_contiguous() and out.dtype == torch.float32 and out.numel() == K * ph * pw * C
+    if K:
+        assert feat_nhwc.is_contiguous() and feat_nhwc.dtype == torch.float32
+        _lib.call('vod_roi_align_fwd', _lib.ptr(feat_nhwc), _lib.ptr(rois), _lib.ptr(out), B, C, H, W, K, ph, pw,
+                  float(spatial_scale), int(sampling_ratio), int(bool(aligned)), int(bool(out_nhwc)),
+                  _lib.stream_ptr(feat_nhwc.device))
+    return out
+
+
+def roi_align(input, rois, output_size, spatial_scale=1.0, sampling_ratio=0, pool_mode='avg', aligned=True):
+    """Functional mmcv.ops.roi_align (NCHW in, [K,C,ph,pw] out)."""
+    if pool_mode != 'avg':
+        raise NotImplementedError("vodagg RoIAlign implements pool_mode='avg' only (the reference's configs)")
+    nhwc, _, _ = to_nhwc(input)
+    return roi_align_nhwc(nhwc.contiguous(), rois, output_size, spatial_scale, sampling_ratio, aligned)
+
+
+class RoIAlign(nn.Module):
+    """Drop-in for mmcv.ops.RoIAlign (mmcv-full 1.2.x signature)."""
+
+    def __init__(self, output_size, spatial_scale=1.0, sampling_ratio=0, pool_mode='avg', aligned=True,
+                 use_torchvision=False):
+        super().__init__()
+        self.output_size = _pair(output_size)
+        self.spatial_scale = float(spatial_scale)
+        self.sampling_ratio = int(sampling_ratio)
+        self.pool_mode = pool_mode
+        self.aligned = aligned
+        self.use_torchvision = use_torchvision  # accepted for signature parity; the CUDA kernel is always used
+
+    def forward(self, input, rois):
+        return roi_align(input, rois, self.output_size, self.spatial_scale, self.sampling_ratio, self.pool_mode,
+                         self.aligned)
+
+    def __repr__(self):
+        return ('%s(output_size=%s, spatial_scale=%s, sampling_ratio=%s, pool_mode=%s, aligned=%s)' %
+                (self.__class__.__name__, self.output_size, self.spatial_scale, self.sampling_ratio, self.pool_mode,
+                 self.aligned))
+
+
+# ----------------------------------------------------------------------------- (5) NMS
+NMS_MODE_AGNOSTIC, NMS_MODE_OFFSET, NMS_MODE_CLASS = 0, 1, 2
+
+
+def nms_device(boxes, scores, labels, iou_threshold, mode, seg_offsets=None, max_keep=-1):
+    """Raw device NMS.  Returns (keep [n] int64 padded, num_keep [n_images] int32), both on the device, no sync.
+
+    keep holds, per image, indices relative to the image's first box in descending-score order."""
+    _lib.require_cuda(boxes, scores, labels)
+    boxes = _f32c(boxes)
+    scores = _f32c(scores)
+    n = boxes.shape[0]
+    if seg_offsets is None:
+        seg_offsets = [0, n]
+    n_images = len(seg_offsets) - 1
+    max_seg = max([seg_offsets[i + 1] - seg_offsets[i] for i in range(n_images)] + [0])
+    dev = boxes.device
+    keep = torch.empty((max(n, 1),), dtype=torch.int64, device=dev)
+    num_keep = torch.empty((n_images,), dtype=torch.int32, device=dev)
+    if labels is not None:
+        labels = labels.to(torch.int64).contiguous()
+    lib = _lib.load()
+    ws_bytes = lib.vod_nms_workspace_bytes(n, max_seg)
+    ws = _ws.get(ws_bytes, dev)
+    offs = (ctypes.c_int * (n_images + 1))(*[int(o) for o in seg_offsets])
+    _lib.call('vod_batched_nms', _lib.ptr(boxes), _lib.ptr(scores), _lib.ptr(labels), n, offs, n_images,
+              float(iou_threshold), int(mode), int(max_keep), _lib.ptr(keep), _lib.ptr(num_keep), _lib.ptr(ws),
+              ws.numel(), _lib.stream_ptr(dev))
+    return keep, num_keep
+
+
+def nms(boxes, scores, iou_threshold, offset=0, score_threshold=0, max_num=-1):
+    """Drop-in for mmcv.ops.nms: returns (dets [k,5], keep [k] int64), keep in descending-score order."""
+    assert boxes.size(1) == 4 and boxes.size(0) == scores.size(0)
+    if offset != 0:
+        raise NotImplementedError('vodagg nms implements offset=0 (mmdet default)')
+    if score_threshold > 0:
+        valid = (scores > score_threshold).nonzero(as_tuple=False).squeeze(1)
+        boxes_v, scores_v = boxes[valid], scores[valid]
+    else:
+        valid, boxes_v, scores_v = None, boxes, scores
+    if boxes_v.shape[0] == 0:
+        keep = torch.zeros((0,), dtype=torch.int64, device=boxes.device)
+    else:
+        keep_pad, num = nms_device(boxes_v, scores_v, None, iou_threshold, NMS_MODE_AGNOSTIC, max_keep=max_num)
+        keep = keep_pad[:int(num.item())]      # the one host sync a variable-length result requires
+    if valid is not None:
+        keep = valid[keep]
+    dets = torch.cat((boxes[keep].float(), scores[keep].float().reshape(-1, 1)), dim=1)
+    return dets, keep
+
+
+def batched_nms(boxes, scores, idxs, nms_cfg, class_agnostic=False):
+    """Drop-in for mmcv.ops.nms.batched_nms (mmcv-full 1.2.x semantics).
+
+    Below ``split_thr`` boxes mmcv adds ``idx * (max_coordinate + 1)`` to every box and runs one NMS;
+    at or above it, it runs NMS per class on the raw coordinates.  Both are reproduced on the device
+    (mode 1 / mode 2 of vod_batched_nms).  ``nms_cfg['max_num']`` (mmcv >= 1.3) bounds the survivors."""
+    nms_cfg_ = dict(nms_cfg)
+    class_agnostic = nms_cfg_.pop('class_agnostic', class_agnostic)
+    nms_type = nms_cfg_.pop('type', 'nms')
+    if nms_type != 'nms':
+        raise NotImplementedError("vodagg batched_nms implements type='nms' (got %r)" % nms_type)
+    split_thr = nms_cfg_.pop('split_thr', 10000)
+    thr = nms_cfg_.pop('iou_threshold', nms_cfg_.pop('iou_thr', None))
+    max_num = nms_cfg_.pop('max_num', -1)
+    n = boxes.shape[0]
+    if n == 0:
+        return boxes.new_zeros((0, 5)), torch.zeros((0,), dtype=torch.int64, device=boxes.device)
+    if class_agnostic:
+        mode = NMS_MODE_AGNOSTIC
+    else:
+        mode = NMS_MODE_OFFSET if n < split_thr else NMS_MODE_CLASS
+    keep_pad, num = nms_device(boxes, scores, None if class_agnostic else idxs, thr, mode, max_keep=max_num)
+    keep = keep_pad[:int(num.item())]
+    dets = torch.cat([boxes[keep].float(), scores[keep].float()[:, None]], -1)
+    return dets, keep
+
+
+# ----------------------------------------------------------------------------- (2) warp / FGFA weighting
+def flow_warp(x, flow):
+    _lib.require_cuda(x, flow)
+    x, flow = _f32c(x), _f32c(flow)
+    N, C, H, W = x.shape
+    out = torch.empty_like(x)
+    if x.numel():
+        _lib.call('vod_flow_warp', _lib.ptr(x), _lib.ptr(flow), _lib.ptr(out), N, C, H, W, flow.shape[2],
+                  flow.shape[3], _lib.stream_ptr(x.device))
+    return out
+
+
+def embed_weighted_sum(key_emb, ref_emb, ref_x):
+    """key_emb [1,C,H,W], ref_emb [T,C,H,W], ref_x [T,Cx,H,W] -> [1,Cx,H,W]."""
+    _lib.require_cuda(key_emb, ref_emb, ref_x)
+    key_emb, ref_emb, ref_x = _f32c(key_emb), _f32c(ref_emb), _f32c(ref_x)
+    T, C, H, W = ref_emb.shape
+    Cx = ref_x.shape[1]
+    out = torch.empty((1, Cx, H, W), dtype=torch.float32, device=ref_x.device)
+    _lib.call('vod_embed_weighted_sum', _lib.ptr(key_emb), _lib.ptr(ref_emb), _lib.ptr(ref_x), _lib.ptr(out), T, C,
+              Cx, H * W, _lib.stream_ptr(ref_x.device))
+    return out
+
+
+def fgfa_warp_weighted_sum(key_emb, ref_emb, raw_x, flow, key_x=None, key_slot=-1):
+    """Weighting with the warp recomputed on the fly from raw features + flows (fgfa.py:275-283)."""
+    _lib.require_cuda(key_emb, ref_emb, raw_x, flow)
+    key_emb, ref_emb, raw_x, flow = _f32c(key_emb), _f32c(ref_emb), _f32c(raw_x), _f32c(flow)
+    key_x = _f32c(key_x) if key_x is not None else None
+    T, C, H, W = ref_emb.shape
+    Cx = raw_x.shape[1]
+    out = torch.empty((1, Cx, H, W), dtype=torch.float32, device=raw_x.device)
+    _lib.call('vod_fgfa_warp_weighted_sum', _lib.ptr(key_emb), _lib.ptr(ref_emb), _lib.ptr(raw_x), _lib.ptr(flow),
+              _lib.ptr(key_x), int(key_slot), _lib.ptr(out), T, C, Cx, H, W, flow.shape[2], flow.shape[3],
+              _lib.stream_ptr(raw_x.device))
+    return out
+
+
+# ----------------------------------------------------------------------------- (3) SELSA attention
+IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
+
+
+def selsa_attention(q, k, v, num_heads, v_transposed=False, impl=IMPL_AUTO):
+    """softmax(Q_h K_h^T / sqrt(d)) V_h per head.  q [N,D], k [M,D], v [M,D] (or V^T [D,ld] when
+    v_transposed; ld >= M).  fp32 or bf16 inputs, fp32 output [N,D]."""
+    _lib.require_cuda(q, k, v)
+    assert q.dtype == k.dtype == v.dtype and q.dtype in (torch.float32, torch.bfloat16)
+    q, k = q.contiguous(), k.contiguous()
+    N, D = q.shape
+    M = k.shape[0]
+    d = D // num_heads
+    assert d * num_heads == D
+    if v_transposed:
+        assert v.shape[0] == D and v.stride(1) == 1 and v.shape[1] >= M
+        ldv = v.stride(0)
+    else:
+        v = v.contiguous()
+        ldv = D
+    out = torch.empty((N, D), dtype=torch.float32, device=q.device)
+    if N == 0:
+        return out
+    lib = _lib.load()
+    ws = _ws.get(lib.vod_selsa_attn_workspace_bytes(N, M, num_heads, d), q.device)
+    # reference: weights = bmm(...) / (x_embed.shape[-1] ** 0.5)   (selsa_aggregator.py:61)
+    scale = 1.0 / math.sqrt(d)
+    _lib.call('vod_selsa_attn', _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(out), N, M, num_heads, d, scale,
+              _lib.VOD_DTYPE_F32 if q.dtype == torch.float32 else _lib.VOD_DTYPE_BF16, int(bool(v_transposed)),
+              int(ldv), int(impl), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(q.device))
+    return out
+
+
+# ----------------------------------------------------------------------------- (4) TemporalRoIAlign pieces
+def msra_topk_sample(roi_rows, ref_nhwc, k=2, ref_norm=None, ref_unit=None, impl=IMPL_AUTO, return_indices=False,
+                     out=None):
+    """roi_rows [NP, C] fp32, ref_nhwc [T, H, W, C] fp32 -> out [T, NP, C] (+ idx [NP,T,k] int32, val fp32)."""
+    _lib.require_cuda(roi_rows, ref_nhwc)
+    roi_rows, ref_nhwc = _f32c(roi_rows), _f32c(ref_nhwc)
+    NP, C = roi_rows.shape
+    T, H, W, _ = ref_nhwc.shape
+    dev = roi_rows.device
+    if out is None:
+        out = torch.empty((T, NP, C), dtype=torch.float32, device=dev)
+    else:
+        assert out.is_contiguous() and out.dtype == torch.float32 and out.numel() == T * NP * C
+    idx = torch.empty((NP, T, k), dtype=torch.int32, device=dev) if return_indices else None
+    val = torch.empty((NP, T, k), dtype=torch.float32, device=dev) if return_indices else None
+    if NP and T:
+        lib = _lib.load()
+        ws = _ws.get(lib.vod_msra_workspace_bytes(NP, C, T, H * W, k), dev)
+        _lib.call('vod_msra_topk_sample', _lib.ptr(roi_rows), _lib.ptr(ref_nhwc), _lib.ptr(ref_norm),
+                  _lib.ptr(ref_unit), _lib.ptr(out), _lib.ptr(idx), _lib.ptr(val), NP, C, T, H * W, int(k), int(impl),
+                  _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev))
+    if return_indices:
+        return out, idx, val
+    return out
+
+
+def tafa_weighted_sum(x_all, emb_all, num_heads, out_nhwc=False):
+    """x_all, emb_all [T1, N, P, C] fp32 -> [N, C, P] (or [N, P, C])."""
+    _lib.require_cuda(x_all, emb_all)
+    assert x_all.is_contiguous() and x_all.dtype == torch.float32
+    T1, N, P, C = x_all.shape
+    if emb_all is not None:
+        assert emb_all.is_contiguous() and emb_all.shape == x_all.shape and emb_all.dtype == torch.float32
+    out = torch.empty((N, P, C) if out_nhwc else (N, C, P), dtype=torch.float32, device=x_all.device)
+    if N:
+        _lib.call('vod_tafa_weighted_sum', _lib.ptr(x_all), _lib.ptr(emb_all), _lib.ptr(out), T1, N, P, C,
+                  int(num_heads), int(bool(out_nhwc)), _lib.stream_ptr(x_all.device))
+    return out
+
+
+def test_gemm_nt(a, b):
+    """D = A @ B^T on the tcgen05 path (unit-test hook for the descriptor/pipeline building blocks)."""
+    _lib.require_cuda(a, b)
+    assert a.dtype == b.dtype and a.dtype in (torch.float32, torch.bfloat16)
+    a, b = a.contiguous(), b.contiguous()
+    M, K = a.shape
+    N = b.shape[0]
+    d = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    _lib.call('vod_test_gemm_nt', _lib.ptr(a), _lib.ptr(b), _lib.ptr(d), M, N, K,
+              _lib.VOD_DTYPE_F32 if a.dtype == torch.float32 else _lib.VOD_DTYPE_BF16, _lib.stream_ptr(a.device))
+    return d

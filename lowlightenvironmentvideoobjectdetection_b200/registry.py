@@ -1,0 +1,185 @@
+"""Minimal stand-ins for the mmcv plumbing the hot-path modules sit behind.
+
+The reference builds its modules through registries (``AGGREGATORS`` at
+mmtracking/mmtrack/models/builder.py:9,53-55; ``ROI_EXTRACTORS`` at
+mmdetection/mmdet/models/builder.py:8,47-49) and ``build_from_cfg``.  mmcv is not
+installable in this image, so the same observable contract is carried here;
+when the real mmtrack / mmdet packages ARE importable, ``register_into_openmmlab``
+registers the B200 modules into their registries (``force=True``) so existing
+configs pick them up unchanged.
+"""
+import functools
+
+import torch
+import torch.nn as nn
+
+
+class Registry:
+    """name -> class table with mmcv.utils.Registry's register_module/get/build contract."""
+
+    def __init__(self, name):
+        self._name = name
+        self._module_dict = {}
+
+    @property
+    def name(self):
+        return self._name
+
+    @property
+    def module_dict(self):
+        return self._module_dict
+
+    def __len__(self):
+        return len(self._module_dict)
+
+    def __contains__(self, key):
+        return key in self._module_dict
+
+    def get(self, key):
+        return self._module_dict.get(key)
+
+    def _register(self, cls, name=None, force=False):
+        key = name or cls.__name__
+        if not force and key in self._module_dict:
+            raise KeyError('%s is already registered in %s' % (key, self._name))
+        self._module_dict[key] = cls
+
+    def register_module(self, name=None, force=False, module=None):
+        if module is not None:
+            self._register(module, name, force)
+            return module
+
+        def _deco(cls):
+            self._register(cls, name, force)
+            return cls
+        return _deco
+
+    def build(self, cfg, default_args=None):
+        return build_from_cfg(cfg, self, default_args)
+
+
+def build_from_cfg(cfg, registry, default_args=None):
+    """mmcv.utils.build_from_cfg: ``cls(**cfg_without_type)``."""
+    if not isinstance(cfg, dict):
+        raise TypeError('cfg must be a dict, but got %s' % type(cfg))
+    if 'type' not in cfg and not (default_args and 'type' in default_args):
+        raise KeyError('`cfg` or `default_args` must contain the key "type"')
+    args = dict(cfg)
+    if default_args is not None:
+        for k, v in default_args.items():
+            args.setdefault(k, v)
+    obj_type = args.pop('type')
+    if isinstance(obj_type, str):
+        obj_cls = registry.get(obj_type)
+        if obj_cls is None:
+            raise KeyError('%s is not in the %s registry' % (obj_type, registry.name))
+    elif isinstance(obj_type, type):
+        obj_cls = obj_type
+    else:
+        raise TypeError('type must be a str or valid type, but got %s' % type(obj_type))
+    return obj_cls(**args)
+
+
+AGGREGATORS = Registry('aggregator')
+ROI_EXTRACTORS = Registry('roi_extractor')
+HEADS = Registry('head')
+
+
+def build_aggregator(cfg):
+    """mmtracking/mmtrack/models/builder.py:53-55."""
+    return build_from_cfg(cfg, AGGREGATORS)
+
+
+def build_roi_extractor(cfg):
+    """mmdetection/mmdet/models/builder.py:47-49."""
+    return build_from_cfg(cfg, ROI_EXTRACTORS)
+
+
+def build_head(cfg):
+    return build_from_cfg(cfg, HEADS)
+
+
+class ConvModule(nn.Module):
+    """The slice of mmcv.cnn.ConvModule the hot-path modules use: conv (+ReLU), sub-modules named
+    ``conv`` / ``activate`` so reference checkpoints load (checkpoint keys).
+    Weights use mmcv's default Kaiming-normal init."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 bias='auto', conv_cfg=None, norm_cfg=None, act_cfg=dict(type='ReLU'), inplace=True, **kwargs):
+        super().__init__()
+        if norm_cfg is not None:
+            raise NotImplementedError('norm layers are not part of the hot path (reference configs use norm_cfg=None)')
+        if conv_cfg is not None and conv_cfg.get('type', 'Conv2d') not in ('Conv2d', 'Conv'):
+            raise NotImplementedError('only plain Conv2d embed convs are supported')
+        self.with_activation = act_cfg is not None
+        self.with_norm = False
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride=stride, padding=padding,
+                              dilation=dilation, groups=groups, bias=(bias == 'auto' or bool(bias)))
+        if self.with_activation:
+            if act_cfg.get('type', 'ReLU') != 'ReLU':
+                raise NotImplementedError('only ReLU activations are supported')
+            self.activate = nn.ReLU(inplace=inplace)
+        nn.init.kaiming_normal_(self.conv.weight, a=0, mode='fan_out', nonlinearity='relu')
+        if self.conv.bias is not None:
+            nn.init.constant_(self.conv.bias, 0)
+
+    def forward(self, x):
+        x = self.conv(x)
+        if self.with_activation:
+            x = self.activate(x)
+        return x
+
+
+def force_fp32(apply_to=None, out_fp16=False):
+    """mmcv.runner.force_fp32: active only when the module sets ``fp16_enabled``; then the named tensor
+    (or tuple-of-tensor) arguments are cast to fp32 and, with ``out_fp16``, the result back to fp16."""
+
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapper(self, *args, **kwargs):
+            if not getattr(self, 'fp16_enabled', False):
+                return fn(self, *args, **kwargs)
+            import inspect
+            names = list(inspect.signature(fn).parameters)[1:]
+
+            def cast(v):
+                if torch.is_tensor(v) and v.dtype in (torch.float16, torch.bfloat16):
+                    return v.float()
+                if isinstance(v, (list, tuple)):
+                    return type(v)(cast(u) for u in v)
+                return v
+            args = list(args)
+            for i, a in enumerate(args):
+                if apply_to is None or (i < len(names) and names[i] in apply_to):
+                    args[i] = cast(a)
+            for k in kwargs:
+                if apply_to is None or k in apply_to:
+                    kwargs[k] = cast(kwargs[k])
+            out = fn(self, *args, **kwargs)
+            if out_fp16 and torch.is_tensor(out):
+                out = out.half()
+            return out
+        return wrapper
+    return deco
+
+
+def register_into_openmmlab():
+    """If the real mmtrack / mmdet packages are importable, register the B200 modules into their
+    registries (same names, force=True) and return the list of registries touched."""
+    touched = []
+    from . import aggregators, roi_extractors
+    try:
+        from mmtrack.models.builder import AGGREGATORS as MM_AGG
+        MM_AGG.register_module(name='SelsaAggregator', force=True, module=aggregators.SelsaAggregator)
+        MM_AGG.register_module(name='EmbedAggregator', force=True, module=aggregators.EmbedAggregator)
+        touched.append('mmtrack.AGGREGATORS')
+    except Exception:
+        pass
+    try:
+        from mmdet.models.builder import ROI_EXTRACTORS as MM_ROI
+        MM_ROI.register_module(name='SingleRoIExtractor', force=True, module=roi_extractors.SingleRoIExtractor)
+        MM_ROI.register_module(name='TemporalRoIAlign', force=True, module=roi_extractors.TemporalRoIAlign)
+        touched.append('mmdet.ROI_EXTRACTORS')
+    except Exception:
+        pass
+    return touched

@@ -1,0 +1,205 @@
+"""B200-native drop-ins for the RoI extractors on the hot path.
+
+  BaseRoIExtractor    mmdetection/mmdet/models/roi_heads/roi_extractors/base_roi_extractor.py:9-83
+  SingleRoIExtractor  mmdetection/mmdet/models/roi_heads/roi_extractors/single_level_roi_extractor.py:9-108
+                      + the mmtrack override that swallows ``ref_feats=`` (**kwargs),
+                      mmtracking/mmtrack/models/roi_heads/roi_extractors/single_level_roi_extractor.py:7-19
+  TemporalRoIAlign    mmtracking/mmtrack/models/roi_heads/roi_extractors/temporal_roi_align.py:9-207
+
+Same registry names, ctor kwargs, forward signatures and parameter names (``embed_network.conv.*``).
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .registry import ROI_EXTRACTORS, ConvModule, force_fp32
+
+
+class BaseRoIExtractor(nn.Module):
+    """Base class for RoI extractor.
+
+    Args:
+        roi_layer (dict): Specify RoI layer type and arguments.
+        out_channels (int): Output channels of RoI layers.
+        featmap_strides (List[int]): Strides of input feature maps.
+    """
+
+    def __init__(self, roi_layer, out_channels, featmap_strides):
+        super(BaseRoIExtractor, self).__init__()
+        self.roi_layers = self.build_roi_layers(roi_layer, featmap_strides)
+        self.out_channels = out_channels
+        self.featmap_strides = featmap_strides
+        self.fp16_enabled = False
+
+    @property
+    def num_inputs(self):
+        """int: Number of input feature maps."""
+        return len(self.featmap_strides)
+
+    def init_weights(self):
+        pass
+
+    def build_roi_layers(self, layer_cfg, featmap_strides):
+        """``getattr(mmcv.ops, type)(spatial_scale=1/s, **cfg)`` per level (base_roi_extractor.py:32-55)."""
+        cfg = layer_cfg.copy()
+        layer_type = cfg.pop('type')
+        assert hasattr(ops, layer_type)
+        layer_cls = getattr(ops, layer_type)
+        return nn.ModuleList([layer_cls(spatial_scale=1 / s, **cfg) for s in featmap_strides])
+
+    def roi_rescale(self, rois, scale_factor):
+        """Scale RoI coordinates by scale factor (base_roi_extractor.py:57-79)."""
+        cx = (rois[:, 1] + rois[:, 3]) * 0.5
+        cy = (rois[:, 2] + rois[:, 4]) * 0.5
+        w = rois[:, 3] - rois[:, 1]
+        h = rois[:, 4] - rois[:, 2]
+        new_w = w * scale_factor
+        new_h = h * scale_factor
+        x1 = cx - new_w * 0.5
+        x2 = cx + new_w * 0.5
+        y1 = cy - new_h * 0.5
+        y2 = cy + new_h * 0.5
+        return torch.stack((rois[:, 0], x1, y1, x2, y2), dim=-1)
+
+
+@ROI_EXTRACTORS.register_module()
+class SingleRoIExtractor(BaseRoIExtractor):
+    """Extract RoI features from a single level feature map (FPN level mapping kept for multi-level
+    inputs; the hot path's R-50-DC5 configs have one stride-16 level and take the single-level branch).
+
+    Args:
+        roi_layer (dict): Specify RoI layer type and arguments.
+        out_channels (int): Output channels of RoI layers.
+        featmap_strides (List[int]): Strides of input feature maps.
+        finest_scale (int): Scale threshold of mapping to level 0. Default: 56.
+    """
+
+    def __init__(self, roi_layer, out_channels, featmap_strides, finest_scale=56):
+        super(SingleRoIExtractor, self).__init__(roi_layer, out_channels, featmap_strides)
+        self.finest_scale = finest_scale
+
+    def map_roi_levels(self, rois, num_levels):
+        """single_level_roi_extractor.py:32-51."""
+        scale = torch.sqrt((rois[:, 3] - rois[:, 1]) * (rois[:, 4] - rois[:, 2]))
+        target_lvls = torch.floor(torch.log2(scale / self.finest_scale + 1e-6))
+        return target_lvls.clamp(min=0, max=num_levels - 1).long()
+
+    def _extract(self, feats, rois, roi_scale_factor=None):
+        out_size = self.roi_layers[0].output_size
+        num_levels = len(feats)
+        roi_feats = feats[0].new_zeros(rois.size(0), self.out_channels, *out_size)
+        if num_levels == 1:
+            if len(rois) == 0:
+                return roi_feats
+            return self.roi_layers[0](feats[0], rois)
+        target_lvls = self.map_roi_levels(rois, num_levels)
+        if roi_scale_factor is not None:
+            rois = self.roi_rescale(rois, roi_scale_factor)
+        for i in range(num_levels):
+            inds = (target_lvls == i).nonzero(as_tuple=False).squeeze(1)
+            if inds.numel() > 0:
+                roi_feats[inds] = self.roi_layers[i](feats[i], rois[inds]).to(roi_feats.dtype)
+        return roi_feats
+
+    @force_fp32(apply_to=('feats', ), out_fp16=True)
+    @torch.no_grad()
+    def forward(self, feats, rois, roi_scale_factor=None, **kwargs):
+        """Forward function (``**kwargs`` swallows ``ref_feats=`` as the mmtrack override does)."""
+        return self._extract(feats, rois, roi_scale_factor)
+
+
+@ROI_EXTRACTORS.register_module()
+class TemporalRoIAlign(SingleRoIExtractor):
+    """Temporal RoI Align module ("Temporal ROI Align for Video Object Recognition").
+
+    Args:
+        num_most_similar_points (int): Number of the most similar points in the Most Similar RoI Align.
+            Defaults to 2.
+        num_temporal_attention_blocks (int): Number of temporal attention blocks in the Temporal
+            Attentional Feature Aggregation.  If not greater than 0, the RoI features are averaged with
+            the Most Similar RoI features instead.  Defaults to 4.
+
+    Device pipeline of ``forward(feats, rois, ref_feats=...)`` (everything stays NHWC, C contiguous):
+      1. vod_nchw_to_nhwc   key / reference maps -> NHWC (+ per-pixel L2 norm, unit-norm bf16 copy)
+      2. vod_roi_align_fwd  key RoI features straight into slot 0 of x_all [T+1, N, 49, C]
+      3. vod_msra_topk_sample  bf16 tcgen05 GEMM with a register top-8 epilogue (the 2.1 GB similarity
+                            tensor is never written) + exact fp32 re-score/top-k/softmax/gather into
+                            slots 1..T of x_all
+      4. embed_network      3x3 conv over the [(T+1)*N, C, 7, 7] channels_last view of x_all (cuDNN)
+      5. vod_tafa_weighted_sum  per-head dot with the key embedding, softmax over frames, weighted sum,
+                            written as [N, C, 7, 7]
+    """
+
+    def __init__(self, num_most_similar_points=2, num_temporal_attention_blocks=4, *args, **kwargs):
+        super(TemporalRoIAlign, self).__init__(*args, **kwargs)
+        self.num_most_similar_points = num_most_similar_points
+        self.num_temporal_attention_blocks = num_temporal_attention_blocks
+        if self.num_temporal_attention_blocks > 0:
+            self.embed_network = ConvModule(self.out_channels, self.out_channels, 3, padding=1, conv_cfg=None,
+                                            norm_cfg=None, act_cfg=None)
+        self.impl = ops.IMPL_AUTO  # test hook: force the exact SIMT scan or the tcgen05 candidate GEMM
+
+    def _stack_key_and_refs(self, feat, rois, ref_feat, return_indices=False):
+        """RoIAlign(key) + most-similar RoI features, stacked as x_all [T+1, N, P, C] (NHWC rows)."""
+        layer = self.roi_layers[0]
+        ph, pw = layer.output_size
+        N = rois.shape[0]
+        T, C = ref_feat.shape[0], ref_feat.shape[1]
+        key_nhwc, _, _ = ops.to_nhwc(feat)
+        want_tc = ref_feat.is_cuda and C % 64 == 0 and C <= 512 and self.impl != ops.IMPL_SIMT
+        ref_nhwc, ref_norm, ref_unit = ops.to_nhwc(ref_feat, want_norm=True, want_unit_bf16=want_tc)
+        x_all = torch.empty((T + 1, N, ph * pw, C), dtype=torch.float32, device=feat.device)
+        # temporal_roi_align.py:186 -- key RoI features, emitted as [N, 49, C] rows into slot 0
+        ops.roi_align_nhwc(key_nhwc.contiguous(), rois, (ph, pw), layer.spatial_scale, layer.sampling_ratio,
+                           layer.aligned, out_nhwc=True, out=x_all[0])
+        # temporal_roi_align.py:99-181
+        res = ops.msra_topk_sample(x_all[0].view(N * ph * pw, C), ref_nhwc.contiguous(),
+                                   k=self.num_most_similar_points, ref_norm=ref_norm, ref_unit=ref_unit,
+                                   impl=self.impl, return_indices=return_indices, out=x_all[1:])
+        return (x_all, res[1], res[2]) if return_indices else x_all
+
+    @torch.no_grad()
+    def most_similar_roi_align(self, roi_feats, ref_feats):
+        """[roi_n, C, h, w], [img_n, C, H, W] -> [img_n, roi_n, C, h, w] (temporal_roi_align.py:99-181)."""
+        roi_n, C, rh, rw = roi_feats.shape
+        ref_nhwc, ref_norm, ref_unit = ops.to_nhwc(ref_feats, want_norm=True,
+                                                   want_unit_bf16=(C % 64 == 0 and C <= 512 and self.impl != ops.IMPL_SIMT))
+        rows = roi_feats.float().permute(0, 2, 3, 1).contiguous().view(roi_n * rh * rw, C)
+        out = ops.msra_topk_sample(rows, ref_nhwc.contiguous(), k=self.num_most_similar_points, ref_norm=ref_norm,
+                                   ref_unit=ref_unit, impl=self.impl)
+        return out.view(ref_feats.shape[0], roi_n, rh, rw, C).permute(0, 1, 4, 2, 3)
+
+    @torch.no_grad()
+    def temporal_attentional_feature_aggregation(self, x, ref_x):
+        """[1, roi_n, C, h, w], [img_n, roi_n, C, h, w] -> [roi_n, C, h, w] (temporal_roi_align.py:44-97)."""
+        x_all = torch.cat((x, ref_x), dim=0).float()
+        img_n, roi_n, C, rh, rw = x_all.shape
+        rows = x_all.permute(0, 1, 3, 4, 2).contiguous().view(img_n, roi_n, rh * rw, C)
+        return self._tafa(rows, rh, rw)
+
+    def _tafa(self, x_all, rh, rw):
+        T1, N, P, C = x_all.shape
+        if self.num_temporal_attention_blocks > 0:
+            # embed conv on the channels_last view: logical [(T+1)*N, C, 7, 7], memory [(T+1)*N, 7, 7, C]
+            patches = x_all.view(T1 * N, rh, rw, C).permute(0, 3, 1, 2)
+            emb = self.embed_network(patches)                              # temporal_roi_align.py:74
+            emb = emb.permute(0, 2, 3, 1).contiguous().view(T1, N, P, C)  # no copy when cuDNN kept channels_last
+            out = ops.tafa_weighted_sum(x_all, emb, self.num_temporal_attention_blocks)
+        else:
+            out = ops.tafa_weighted_sum(x_all, None, 0)                    # plain mean, :203-206
+        return out.view(N, C, rh, rw)
+
+    @force_fp32(apply_to=('feats', 'ref_feats'), out_fp16=True)
+    @torch.no_grad()
+    def forward(self, feats, rois, roi_scale_factor=None, ref_feats=None):
+        """Forward function."""
+        if ref_feats is None:
+            # RoI features of reference-frame proposals: plain RoIAlign (temporal_roi_align.py:188-191)
+            return self._extract(feats, rois, roi_scale_factor)
+        assert len(feats) == 1, 'TemporalRoIAlign hot path expects a single feature level (R-50-DC5 configs)'
+        out_size = self.roi_layers[0].output_size
+        if len(rois) == 0:
+            return feats[0].new_zeros(0, self.out_channels, *out_size)
+        # only the last level of the reference maps is used (:195-196)
+        x_all = self._stack_key_and_refs(feats[0], rois, ref_feats[-1])
+        return self._tafa(x_all, out_size[0], out_size[1]).to(feats[0].dtype)

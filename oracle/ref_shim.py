@@ -1,0 +1,223 @@
+"""oracle/ref_shim.py -- TEST INFRASTRUCTURE ONLY (build container only).
+
+Loads the reference's own hot-path Python files UNMODIFIED from
+``/root/reference`` under small stand-ins for the absent mmcv / mmdet packages
+(SURVEY.md Appendix C).  Used to (i) validate the restatement in
+``oracle/vod_oracle.py`` and (ii) generate the golden vectors committed under
+``tests/golden/`` (``tests/golden/make_golden.py``).  ``/root/reference`` does
+not exist on the GPU box: nothing that runs there imports this module.
+
+Stand-ins (the only arithmetic they carry is the un-vendored mmcv-full ops):
+  mmcv.ops.RoIAlign        -> torchvision.ops.roi_align(aligned=True)   (Appendix A.1)
+  mmcv.ops.nms.batched_nms -> offset trick + torchvision.ops.nms        (Appendix A.5)
+  mmcv.cnn.ConvModule      -> nn.Conv2d (+ReLU), sub-module named .conv
+  mmcv.runner.force_fp32   -> identity decorator
+  mmcv.utils.Registry      -> name -> class table with register_module/build
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import torch
+import torch.nn as nn
+
+REF_ROOT = os.environ.get('VOD_REFERENCE_ROOT', '/root/reference')
+_LOADED = None
+
+
+def available():
+    return os.path.isdir(os.path.join(REF_ROOT, 'mmtracking', 'mmtrack'))
+
+
+class _Registry:
+    def __init__(self, name):
+        self.name = name
+        self.module_dict = {}
+
+    def register_module(self, name=None, force=False, module=None):
+        def _reg(cls):
+            key = name or cls.__name__
+            if key in self.module_dict and not force:
+                raise KeyError('%s already registered in %s' % (key, self.name))
+            self.module_dict[key] = cls
+            return cls
+        if module is not None:
+            return _reg(module)
+        return _reg
+
+    def get(self, key):
+        return self.module_dict.get(key)
+
+
+def _build_from_cfg(cfg, registry, default_args=None):
+    args = dict(cfg)
+    if default_args:
+        for k, v in default_args.items():
+            args.setdefault(k, v)
+    cls = registry.get(args.pop('type'))
+    return cls(**args)
+
+
+class _ConvModule(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0,
+                 conv_cfg=None, norm_cfg=None, act_cfg=dict(type='ReLU'), **kw):
+        super().__init__()
+        assert norm_cfg is None
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride=stride,
+                              padding=padding, bias=True)
+        self.with_activation = act_cfg is not None
+        if self.with_activation:
+            self.activate = nn.ReLU(inplace=False)
+
+    def forward(self, x):
+        x = self.conv(x)
+        if self.with_activation:
+            x = self.activate(x)
+        return x
+
+
+def _force_fp32(apply_to=None, out_fp16=False):
+    def deco(fn):
+        return fn
+    return deco
+
+
+class _RoIAlign(nn.Module):
+    def __init__(self, output_size, spatial_scale=1.0, sampling_ratio=0, pool_mode='avg',
+                 aligned=True, use_torchvision=False):
+        super().__init__()
+        self.output_size = (output_size, output_size) if isinstance(output_size, int) \
+            else tuple(output_size)
+        self.spatial_scale = float(spatial_scale)
+        self.sampling_ratio = int(sampling_ratio)
+        assert pool_mode == 'avg'
+        self.aligned = aligned
+
+    def forward(self, input, rois):
+        from torchvision.ops import roi_align
+        return roi_align(input, rois, self.output_size, self.spatial_scale,
+                         self.sampling_ratio, self.aligned)
+
+
+def _batched_nms(boxes, scores, idxs, nms_cfg, class_agnostic=False):
+    from torchvision.ops import nms as tv_nms
+    nms_cfg_ = dict(nms_cfg)
+    class_agnostic = nms_cfg_.pop('class_agnostic', class_agnostic)
+    if class_agnostic:
+        boxes_for_nms = boxes
+    else:
+        max_coordinate = boxes.max()
+        offsets = idxs.to(boxes) * (max_coordinate + 1)
+        boxes_for_nms = boxes + offsets[:, None]
+    nms_cfg_.pop('type', 'nms')
+    split_thr = nms_cfg_.pop('split_thr', 10000)
+    thr = nms_cfg_.pop('iou_threshold', nms_cfg_.pop('iou_thr', None))
+    if boxes_for_nms.shape[0] < split_thr:
+        keep = tv_nms(boxes_for_nms, scores, thr)
+        boxes = boxes[keep]
+        scores = scores[keep]
+    else:
+        total_mask = scores.new_zeros(scores.size(), dtype=torch.bool)
+        for id in torch.unique(idxs):
+            mask = (idxs == id).nonzero(as_tuple=False).view(-1)
+            keep = tv_nms(boxes_for_nms[mask], scores[mask], thr)
+            total_mask[mask[keep]] = True
+        keep = total_mask.nonzero(as_tuple=False).view(-1)
+        keep = keep[scores[keep].argsort(descending=True)]
+        boxes = boxes[keep]
+        scores = scores[keep]
+    return torch.cat([boxes, scores[:, None]], -1), keep
+
+
+def _mod(name, **attrs):
+    m = types.ModuleType(name)
+    m.__path__ = []  # behave as a package so dotted children resolve
+    for k, v in attrs.items():
+        setattr(m, k, v)
+    sys.modules[name] = m
+    return m
+
+
+def _load(dotted, rel_path):
+    path = os.path.join(REF_ROOT, rel_path)
+    spec = importlib.util.spec_from_file_location(dotted, path)
+    module = importlib.util.module_from_spec(spec)
+    sys.modules[dotted] = module
+    spec.loader.exec_module(module)
+    return module
+
+
+def load():
+    """Returns a namespace with the reference's own classes/functions."""
+    global _LOADED
+    if _LOADED is not None:
+        return _LOADED
+    if not available():
+        raise RuntimeError('reference tree not present at %s' % REF_ROOT)
+    for name in list(sys.modules):
+        if name.split('.')[0] in ('mmcv', 'mmdet', 'mmtrack'):
+            raise RuntimeError('real %s already imported; shim refuses to shadow it' % name)
+
+    ops_nms = _mod('mmcv.ops.nms', batched_nms=_batched_nms)
+    ops = _mod('mmcv.ops', RoIAlign=_RoIAlign, nms=ops_nms, batched_nms=_batched_nms)
+    utils = _mod('mmcv.utils', Registry=_Registry, build_from_cfg=_build_from_cfg)
+    bricks = _mod('mmcv.cnn.bricks', ConvModule=_ConvModule)
+    cnn = _mod('mmcv.cnn', ConvModule=_ConvModule, bricks=bricks)
+    runner = _mod('mmcv.runner', force_fp32=_force_fp32)
+    _mod('mmcv', ops=ops, utils=utils, cnn=cnn, runner=runner)
+
+    ROI_EXTRACTORS = _Registry('roi_extractor')
+    AGGREGATORS = _Registry('aggregator')
+    _mod('mmdet')
+    _mod('mmdet.core')
+    _mod('mmdet.core.bbox')
+    _mod('mmdet.core.bbox.iou_calculators', bbox_overlaps=None)
+    _mod('mmdet.core.post_processing')
+    _mod('mmdet.models')
+    _mod('mmdet.models.builder', ROI_EXTRACTORS=ROI_EXTRACTORS)
+    _mod('mmdet.models.roi_heads')
+    rx = _mod('mmdet.models.roi_heads.roi_extractors')
+    _mod('mmtrack')
+    _mod('mmtrack.core')
+    _mod('mmtrack.core.motion')
+    _mod('mmtrack.models')
+    _mod('mmtrack.models.builder', AGGREGATORS=AGGREGATORS)
+    _mod('mmtrack.models.aggregators')
+    _mod('mmtrack.models.roi_heads')
+    _mod('mmtrack.models.roi_heads.roi_extractors')
+
+    d = 'mmdetection/mmdet/'
+    t = 'mmtracking/mmtrack/'
+    base = _load('mmdet.models.roi_heads.roi_extractors.base_roi_extractor',
+                 d + 'models/roi_heads/roi_extractors/base_roi_extractor.py')
+    single = _load('mmdet.models.roi_heads.roi_extractors.single_level_roi_extractor',
+                   d + 'models/roi_heads/roi_extractors/single_level_roi_extractor.py')
+    rx.BaseRoIExtractor = base.BaseRoIExtractor
+    rx.SingleRoIExtractor = single.SingleRoIExtractor
+    bbox_nms = _load('mmdet.core.post_processing.bbox_nms', d + 'core/post_processing/bbox_nms.py')
+    selsa = _load('mmtrack.models.aggregators.selsa_aggregator',
+                  t + 'models/aggregators/selsa_aggregator.py')
+    embed = _load('mmtrack.models.aggregators.embed_aggregator',
+                  t + 'models/aggregators/embed_aggregator.py')
+    troi = _load('mmtrack.models.roi_heads.roi_extractors.temporal_roi_align',
+                 t + 'models/roi_heads/roi_extractors/temporal_roi_align.py')
+    mm_single = _load('mmtrack.models.roi_heads.roi_extractors.single_level_roi_extractor',
+                      t + 'models/roi_heads/roi_extractors/single_level_roi_extractor.py')
+    flow = _load('mmtrack.core.motion.flow', t + 'core/motion/flow.py')
+
+    ns = types.SimpleNamespace(
+        SelsaAggregator=selsa.SelsaAggregator,
+        EmbedAggregator=embed.EmbedAggregator,
+        TemporalRoIAlign=troi.TemporalRoIAlign,
+        SingleRoIExtractor=mm_single.SingleRoIExtractor,
+        MMDetSingleRoIExtractor=single.SingleRoIExtractor,
+        flow_warp_feats=flow.flow_warp_feats,
+        multiclass_nms=bbox_nms.multiclass_nms,
+        batched_nms=_batched_nms,
+        RoIAlign=_RoIAlign,
+        ROI_EXTRACTORS=ROI_EXTRACTORS,
+        AGGREGATORS=AGGREGATORS,
+    )
+    _LOADED = ns
+    return ns

@@ -1,0 +1,296 @@
+"""Parity of the CUDA hot path (called through the C ABI via the reference-shaped modules) against
+(i) the golden vectors produced by the reference's own unmodified files and (ii) the CPU oracle on
+seeded inputs.  Bars (BASELINE.json north_star): NMS kept indices and top-k sampling locations exact;
+aggregated features within 1e-3 relative error in fp32 (most are ~1e-6)."""
+import pytest
+import torch
+
+import lowlightenvironmentvideoobjectdetection_b200 as vod
+from lowlightenvironmentvideoobjectdetection_b200 import ops
+from oracle import vod_oracle as O
+
+from conftest import params, rel_err
+from helpers import clustered_boxes, rpn_like_rois
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+FEAT_TOL = 1e-3      # north_star bar for aggregated features (fp32)
+TIGHT = 2e-5         # what the non-tensor-core kernels actually achieve
+
+
+# ------------------------------------------------------------------------------------------ (5) NMS
+def _check_nms(boxes, scores, ids, cfg):
+    d0, k0 = O.batched_nms(boxes, scores, ids, cfg)
+    d1, k1 = vod.batched_nms(boxes.to(DEV), scores.to(DEV), ids.to(DEV), cfg)
+    assert k1.dtype == torch.int64
+    assert torch.equal(k1.cpu(), k0), 'kept indices differ'
+    assert torch.equal(d1.cpu(), d0)
+
+
+def test_nms_golden(golden):
+    b, s = golden['rpnnms_boxes'], golden['rpnnms_scores']
+    d, k = vod.batched_nms(b.to(DEV), s.to(DEV), torch.zeros(len(b), dtype=torch.long, device=DEV),
+                           dict(type='nms', iou_threshold=0.7))
+    assert torch.equal(k.cpu(), golden['rpnnms_keep'])
+    assert torch.equal(d.cpu(), golden['rpnnms_dets'])
+    ids = golden['bnms_ids']
+    d, k = vod.batched_nms(b.to(DEV), s.to(DEV), ids.to(DEV), dict(type='nms', iou_threshold=0.5))
+    assert torch.equal(k.cpu(), golden['bnms_keep']) and torch.equal(d.cpu(), golden['bnms_dets'])
+    d, k = vod.batched_nms(b.to(DEV), s.to(DEV), ids.to(DEV), dict(type='nms', iou_threshold=0.5, split_thr=1000))
+    assert torch.equal(k.cpu(), golden['bnms_split_keep']) and torch.equal(d.cpu(), golden['bnms_split_dets'])
+
+
+def test_multiclass_nms_golden(golden):
+    d, l, k = vod.multiclass_nms(golden['mcnms_bboxes'].to(DEV), golden['mcnms_scores'].to(DEV), 0.05,
+                                 dict(type='nms', iou_threshold=0.5), 100, return_inds=True)
+    assert torch.equal(k.cpu(), golden['mcnms_keep'])
+    assert torch.equal(l.cpu(), golden['mcnms_labels'])
+    assert torch.equal(d.cpu(), golden['mcnms_dets'])
+
+
+@pytest.mark.parametrize('n,ncls,thr', [(1, 1, 0.5), (63, 3, 0.5), (64, 1, 0.7), (65, 2, 0.3), (1000, 30, 0.5),
+                                        (6000, 1, 0.7), (9000, 30, 0.5)])
+def test_nms_vs_oracle(n, ncls, thr):
+    g = torch.Generator().manual_seed(n * 7 + ncls)
+    boxes = clustered_boxes(g, n, max(2, n // 40))
+    scores = torch.rand(n, generator=g) + 1e-7 * torch.arange(n)     # distinct by construction
+    ids = torch.randint(0, ncls, (n,), generator=g)
+    _check_nms(boxes, scores, ids, dict(type='nms', iou_threshold=thr))
+
+
+def test_nms_split_path_and_ties():
+    g = torch.Generator().manual_seed(5)
+    n = 3000
+    boxes = clustered_boxes(g, n, 60)
+    ids = torch.randint(0, 8, (n,), generator=g)
+    scores = torch.rand(n, generator=g)
+    _check_nms(boxes, scores, ids, dict(type='nms', iou_threshold=0.5, split_thr=2000))   # per-class path
+    _check_nms(boxes, scores, ids, dict(type='nms', iou_threshold=0.5, class_agnostic=True))
+    # ties: equal scores keep index order (stable), as the oracle's stable sort
+    scores_t = (scores * 8).floor() / 8
+    _check_nms(boxes, scores_t, ids, dict(type='nms', iou_threshold=0.5))
+
+
+def test_nms_max_num_and_empty():
+    g = torch.Generator().manual_seed(6)
+    boxes = clustered_boxes(g, 2000, 30)
+    scores = torch.rand(2000, generator=g)
+    ids = torch.randint(0, 4, (2000,), generator=g)
+    d0, k0 = O.batched_nms(boxes, scores, ids, dict(type='nms', iou_threshold=0.5))
+    d1, k1 = vod.batched_nms(boxes.to(DEV), scores.to(DEV), ids.to(DEV), dict(type='nms', iou_threshold=0.5, max_num=37))
+    assert torch.equal(k1.cpu(), k0[:37])
+    d, k = vod.batched_nms(torch.zeros(0, 4, device=DEV), torch.zeros(0, device=DEV),
+                           torch.zeros(0, dtype=torch.long, device=DEV), dict(type='nms', iou_threshold=0.5))
+    assert d.shape == (0, 5) and k.shape == (0,)
+    d, k = vod.nms(boxes.to(DEV), scores.to(DEV), 0.6)
+    d0, k0 = O.nms(boxes, scores, 0.6)
+    assert torch.equal(k.cpu(), k0)
+
+
+def test_rpn_batched_images():
+    g = torch.Generator().manual_seed(8)
+    props = [clustered_boxes(g, n, 50) for n in (6000, 5000, 6000, 1)]
+    scs = [torch.rand(len(p), generator=g) for p in props]
+    outs = vod.rpn_batched_nms([p.to(DEV) for p in props], [s.to(DEV) for s in scs], 0.7, 300)
+    for p, s, o in zip(props, scs, outs):
+        d0, k0 = O.batched_nms(p, s, torch.zeros(len(p), dtype=torch.long), dict(type='nms', iou_threshold=0.7))
+        assert torch.equal(o.cpu(), d0[:300])
+
+
+# ------------------------------------------------------------------------------------------ (1) RoIAlign
+def test_roi_align_golden(golden):
+    layer = vod.RoIAlign(7, 1 / 16, 2)
+    out = layer(golden['troi_feat'].to(DEV), golden['troi_rois'].to(DEV))
+    assert out.shape == golden['roialign_out'].shape
+    assert rel_err(out, golden['roialign_out']) < TIGHT
+
+
+@pytest.mark.parametrize('C,H,W,K,frames', [(512, 38, 63, 300, 1), (512, 38, 63, 450, 3), (20, 9, 11, 17, 2), (6, 5, 7, 9, 1)])
+def test_roi_align_vs_oracle(C, H, W, K, frames):
+    g = torch.Generator().manual_seed(C + K)
+    feat = torch.randn(frames, C, H, W, generator=g)
+    rois = rpn_like_rois(g, K // frames, frames, W * 16., H * 16.)
+    # edge cases: degenerate, out-of-image and full-image boxes
+    rois[0, 1:] = torch.tensor([10., 10., 10., 10.])
+    rois[1, 1:] = torch.tensor([-200., -100., -50., -20.])
+    rois[2, 1:] = torch.tensor([0., 0., W * 16. - 1, H * 16. - 1])
+    ref = O.roi_align(feat, rois, 7, 1 / 16, 2, True)
+    out = vod.roi_align(feat.to(DEV), rois.to(DEV), 7, 1 / 16, 2, 'avg', True)
+    assert rel_err(out, ref) < TIGHT
+    out_cl = vod.roi_align(feat.to(DEV).contiguous(memory_format=torch.channels_last), rois.to(DEV), 7, 1 / 16, 2)
+    assert rel_err(out_cl, ref) < TIGHT
+    # legacy (aligned=False) and adaptive sampling grid
+    ref2 = O.roi_align(feat, rois, (5, 6), 1 / 16, 0, False)
+    out2 = vod.roi_align(feat.to(DEV), rois.to(DEV), (5, 6), 1 / 16, 0, 'avg', False)
+    assert rel_err(out2, ref2) < TIGHT
+
+
+def test_roi_align_empty_and_extractor(golden):
+    ext = vod.build_roi_extractor(dict(type='SingleRoIExtractor', roi_layer=dict(type='RoIAlign', output_size=7, sampling_ratio=2),
+                                       out_channels=64, featmap_strides=[16])).to(DEV)
+    out = ext((golden['troi_ref'].to(DEV),), golden['troi_ref_rois'].to(DEV), ref_feats=None)
+    assert rel_err(out, golden['troi_ref_out']) < TIGHT
+    out = ext((golden['troi_ref'].to(DEV),), torch.zeros(0, 5, device=DEV))
+    assert out.shape == (0, 64, 7, 7)
+
+
+# ------------------------------------------------------------------------------------------ (2) warp + FGFA weights
+def test_flow_warp_golden(golden):
+    for p in ('warp', 'warp2'):
+        out = vod.flow_warp_feats(golden[p + '_x'].to(DEV), golden[p + '_flow'].to(DEV))
+        assert out.shape == golden[p + '_out'].shape
+        assert (out.cpu() - golden[p + '_out']).abs().max() < 1e-4   # grid rounding, see oracle/vod_oracle.c
+
+
+def test_flow_warp_vs_oracle_and_asserts():
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(3, 512, 38, 63, generator=g)
+    flow = torch.randn(3, 2, 608, 1008, generator=g) * 8
+    flow[0] *= 10   # large displacements exercise the border clamp
+    ref = O.flow_warp_feats(x, flow)
+    out = vod.flow_warp_feats(x.to(DEV), flow.to(DEV))
+    assert rel_err(out, ref) < TIGHT
+    with pytest.raises(AssertionError):
+        vod.flow_warp_feats(torch.randn(2, 8, 32, 32, 32, device=DEV), torch.randn(2, 2, 10, 10, device=DEV))
+    with pytest.raises(AssertionError):
+        vod.flow_warp_feats(torch.randn(2, 8, 32, 32, device=DEV), torch.randn(2, 2, 10, 10, 10, device=DEV))
+    with pytest.raises(AssertionError):
+        vod.flow_warp_feats(torch.randn(2, 8, 32, 32, device=DEV), torch.randn(2, 3, 10, 10, device=DEV))
+
+
+def test_embed_aggregator_golden(golden):
+    m = vod.build_aggregator(dict(type='EmbedAggregator', num_convs=2, channels=16, kernel_size=3))
+    m.load_state_dict(params(golden, 'embed_p.'))
+    m = m.to(DEV)
+    torch.backends.cudnn.allow_tf32 = False
+    out = m(golden['embed_x'].to(DEV), golden['embed_ref_x'].to(DEV))
+    assert out.shape == golden['embed_out'].shape
+    assert rel_err(out, golden['embed_out']) < 1e-4
+    with pytest.raises(AssertionError):
+        vod.EmbedAggregator(num_convs=0, channels=32, kernel_size=3)
+    with pytest.raises(AssertionError):
+        m(torch.randn(2, 16, 10, 14, device=DEV), golden['embed_ref_x'].to(DEV))
+
+
+def test_embed_weighting_vs_oracle_and_fused_warp():
+    g = torch.Generator().manual_seed(12)
+    T, C, H, W = 7, 64, 38, 63
+    key_e, ref_e = torch.randn(1, C, H, W, generator=g), torch.randn(T, C, H, W, generator=g)
+    ref_x = torch.randn(T, C, H, W, generator=g)
+    ref = O.embed_weighted_sum(key_e, ref_e, ref_x)
+    out = ops.embed_weighted_sum(key_e.to(DEV), ref_e.to(DEV), ref_x.to(DEV))
+    assert rel_err(out, ref) < TIGHT
+    # fused: weights from embeddings, operand = on-the-fly warp of the raw memory, key slot un-warped
+    flow = torch.randn(T, 2, H * 16, W * 16, generator=g) * 8
+    key_x = torch.randn(1, C, H, W, generator=g)
+    warped = O.flow_warp_feats(ref_x, flow)
+    warped[3] = key_x[0]
+    ref_f = O.embed_weighted_sum(key_e, ref_e, warped)
+    out_f = ops.fgfa_warp_weighted_sum(key_e.to(DEV), ref_e.to(DEV), ref_x.to(DEV), flow.to(DEV), key_x.to(DEV), 3)
+    assert rel_err(out_f, ref_f) < TIGHT
+
+
+# ------------------------------------------------------------------------------------------ (3) SELSA (SIMT path)
+def test_selsa_aggregator_golden_simt(golden):
+    for pre, heads in (('selsa', 16), ('selsa64', 2)):
+        m = vod.build_aggregator(dict(type='SelsaAggregator', in_channels=128, num_attention_blocks=heads))
+        m.load_state_dict(params(golden, pre + '_p.'))
+        m = m.to(DEV)
+        m.impl = ops.IMPL_SIMT
+        torch.backends.cuda.matmul.allow_tf32 = False
+        out = m(golden[pre + '_x'].to(DEV), golden[pre + '_ref_x'].to(DEV))
+        assert out.shape == golden[pre + '_out'].shape
+        assert rel_err(out, golden[pre + '_out']) < 1e-4
+
+
+def test_selsa_reference_unit_test_shapes():
+    """mmtracking/tests/test_models/test_aggregators.py:32-41 (d = 4 heads of a 16-d feature)."""
+    model = vod.SelsaAggregator(in_channels=16, num_attention_blocks=4).to(DEV)
+    model.train()
+    target_x = torch.randn(2, 16, device=DEV)
+    ref_x = torch.randn(4, 16, device=DEV)
+    agg_x = model(target_x, ref_x)
+    assert agg_x.shape == target_x.shape
+    p = {k: v.cpu() for k, v in model.state_dict().items()}
+    assert rel_err(agg_x, O.selsa_aggregate(target_x.cpu(), ref_x.cpu(), p, 4)) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------ (4) TemporalRoIAlign (exact SIMT path)
+def _troi(golden, blocks, impl):
+    m = vod.build_roi_extractor(dict(type='TemporalRoIAlign', num_most_similar_points=2,
+                                     num_temporal_attention_blocks=blocks,
+                                     roi_layer=dict(type='RoIAlign', output_size=7, sampling_ratio=2),
+                                     out_channels=64, featmap_strides=[16]))
+    if blocks > 0:
+        m.load_state_dict(params(golden, 'troi_p.'))
+    m = m.to(DEV)
+    m.impl = impl
+    return m
+
+
+def test_temporal_roi_align_golden_simt(golden):
+    torch.backends.cudnn.allow_tf32 = False
+    m = _troi(golden, 4, ops.IMPL_SIMT)
+    feat, ref, rois = golden['troi_feat'].to(DEV), golden['troi_ref'].to(DEV), golden['troi_rois'].to(DEV)
+    msra = m.most_similar_roi_align(golden['roialign_out'].to(DEV), ref)
+    assert rel_err(msra, golden['msra_out']) < 1e-4
+    out = m((feat,), rois, ref_feats=(ref,))
+    assert out.shape == golden['troi_out'].shape
+    assert rel_err(out, golden['troi_out']) < 1e-4
+    # reference-frame call: plain RoIAlign
+    assert rel_err(m((ref,), golden['troi_ref_rois'].to(DEV)), golden['troi_ref_out']) < TIGHT
+    # num_temporal_attention_blocks <= 0: mean over key + refs
+    m0 = _troi(golden, 0, ops.IMPL_SIMT)
+    assert rel_err(m0((feat,), rois, ref_feats=(ref,)), golden['troi_mean_out']) < 1e-4
+    # empty rois
+    assert m((feat,), torch.zeros(0, 5, device=DEV), ref_feats=(ref,)).shape == (0, 64, 7, 7)
+
+
+def test_msra_indices_exact_vs_oracle_simt():
+    g = torch.Generator().manual_seed(21)
+    N, C, T, H, W = 5, 64, 3, 12, 20
+    roi = torch.relu(torch.randn(N, C, 7, 7, generator=g))
+    ref = torch.relu(torch.randn(T, C, H, W, generator=g))
+    out0, idx0, sim0 = O.most_similar_roi_align(roi, ref, 2, return_indices=True)
+    ref_nhwc, norm, _ = ops.to_nhwc(ref.to(DEV), want_norm=True)
+    rows = roi.permute(0, 2, 3, 1).reshape(N * 49, C).to(DEV)
+    out1, idx1, val1 = ops.msra_topk_sample(rows, ref_nhwc, 2, ref_norm=norm, impl=ops.IMPL_SIMT, return_indices=True)
+    idx1 = idx1.cpu().long()
+    same = (idx1.sort(dim=2).values == idx0.sort(dim=2).values).all(dim=2)
+    # tie-tolerant exactness: where the set differs the similarity values must be within 1 fp32 ulp-ish
+    if not same.all():
+        bad = (~same).nonzero()
+        for r, t in bad.tolist():
+            v_ours = sim0[r, t, idx1[r, t]]
+            v_ref = sim0[r, t, idx0[r, t]]
+            assert (v_ours.sort().values - v_ref.sort().values).abs().max() <= 1e-6
+    assert same.float().mean() > 0.999
+    got = out1.view(T, N, 7, 7, C).permute(0, 1, 4, 2, 3)
+    assert rel_err(got, out0) < 1e-4
+
+
+def test_tafa_vs_oracle():
+    g = torch.Generator().manual_seed(22)
+    T1, N, C = 16, 9, 512
+    x_all = torch.randn(T1, N, C, 7, 7, generator=g)
+    emb = torch.randn(T1, N, C, 7, 7, generator=g) * 0.3
+    ref = O.tafa_weighted_sum(x_all, emb, 4)
+    xr = x_all.permute(0, 1, 3, 4, 2).reshape(T1, N, 49, C).contiguous().to(DEV)
+    er = emb.permute(0, 1, 3, 4, 2).reshape(T1, N, 49, C).contiguous().to(DEV)
+    out = ops.tafa_weighted_sum(xr, er, 4).view(N, C, 7, 7)
+    assert rel_err(out, ref) < TIGHT
+    out_nhwc = ops.tafa_weighted_sum(xr, er, 4, out_nhwc=True).view(N, 7, 7, C).permute(0, 3, 1, 2)
+    assert rel_err(out_nhwc, ref) < TIGHT
+    mean = ops.tafa_weighted_sum(xr, None, 0).view(N, C, 7, 7)
+    assert rel_err(mean, x_all.mean(0)) < TIGHT
+
+
+def test_layout_kernel():
+    g = torch.Generator().manual_seed(23)
+    x = torch.randn(3, 512, 38, 63, generator=g).to(DEV)
+    nhwc, norm, unit = ops.to_nhwc(x, want_norm=True, want_unit_bf16=True)
+    assert torch.equal(nhwc, x.permute(0, 2, 3, 1).contiguous())
+    ref_norm = x.permute(0, 2, 3, 1).reshape(-1, 512).norm(dim=1)
+    assert rel_err(norm, ref_norm) < 1e-6
+    ref_unit = (x.permute(0, 2, 3, 1).reshape(-1, 512) / ref_norm[:, None]).bfloat16()
+    assert (unit.float() - ref_unit.float()).abs().max() <= 2 ** -8

@@ -1,0 +1,130 @@
+"""tcgen05 / TMEM / TMA building blocks in isolation (run first: everything tensor-core depends on them)."""
+import pytest
+import torch
+
+import lowlightenvironmentvideoobjectdetection_b200 as vod
+from lowlightenvironmentvideoobjectdetection_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('shape', [(128, 128, 64), (256, 384, 512), (300, 200, 96), (77, 130, 40)])
+def test_gemm_bf16(shape):
+    M, N, K = shape
+    g = torch.Generator(device='cuda').manual_seed(1)
+    a = torch.randn(M, K, device='cuda', generator=g).bfloat16()
+    b = torch.randn(N, K, device='cuda', generator=g).bfloat16()
+    d = ops.test_gemm_nt(a, b)
+    ref = a.float() @ b.float().t()
+    err = (d - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-5, err   # bf16 products are exact in fp32; only accumulation order differs
+
+
+@pytest.mark.parametrize('shape', [(128, 128, 32), (256, 256, 64), (300, 200, 100)])
+def test_gemm_tf32(shape):
+    M, N, K = shape
+    g = torch.Generator(device='cuda').manual_seed(2)
+    a = torch.randn(M, K, device='cuda', generator=g)
+    b = torch.randn(N, K, device='cuda', generator=g)
+    d = ops.test_gemm_nt(a, b)
+    ref = a.double() @ b.double().t()
+    err = (d.double() - ref).abs().max().item() / ref.abs().max().item()
+    bias = ((d.double() - ref) * ref.sign()).mean().item() / ref.abs().mean().item()
+    print('tf32 gemm', shape, 'max rel err %.3e' % err, 'signed bias %.3e' % bias)
+    assert err < 2e-3, err   # tf32: 10-bit mantissa operands, fp32 accumulate
+    assert abs(bias) < 1e-4, bias   # operands are ROUNDED to tf32 by the TMA unit, not truncated
+
+
+# ------------------------------------------------------------------------------------------ (3) SELSA on tcgen05
+from oracle import vod_oracle as O  # noqa: E402
+from conftest import params, rel_err  # noqa: E402
+
+SELSA_TF32_TOL = 1e-3    # north_star bar: aggregated features within 1e-3 relative error in fp32 I/O
+SELSA_BF16_TOL = 2e-2    # bf16 operands (8-bit mantissa): stated separately
+
+
+@pytest.mark.parametrize('N,M,heads', [(37, 300, 2), (128, 64, 1), (300, 900, 16), (300, 4500, 16), (130, 1000, 4), (1, 70, 3)])
+def test_selsa_attention_tc_vs_oracle(N, M, heads):
+    g = torch.Generator().manual_seed(N + M)
+    D = heads * 64
+    q, k, v = (torch.randn(n, D, generator=g) for n in (N, M, M))
+    ref = O.selsa_attention(q, k, v, heads)
+    out = ops.selsa_attention(q.to('cuda'), k.to('cuda'), v.to('cuda'), heads, impl=ops.IMPL_TC)
+    print('selsa tf32', (N, M, heads), 'rel err %.3e' % rel_err(out, ref))
+    assert rel_err(out, ref) < SELSA_TF32_TOL, rel_err(out, ref)
+    # V handed over pre-transposed (what SelsaAggregator does), padded leading dimension
+    ld = (M + 7) // 8 * 8
+    vt = torch.zeros(D, ld)
+    vt[:, :M] = v.t()
+    out_t = ops.selsa_attention(q.to('cuda'), k.to('cuda'), vt.to('cuda'), heads, v_transposed=True, impl=ops.IMPL_TC)
+    assert rel_err(out_t, ref) < SELSA_TF32_TOL
+    # SIMT kernel cross-check on the same inputs (exact fp32)
+    out_s = ops.selsa_attention(q.to('cuda'), k.to('cuda'), v.to('cuda'), heads, impl=ops.IMPL_SIMT)
+    assert rel_err(out_s, ref) < 2e-5
+    # bf16 operands
+    out_b = ops.selsa_attention(q.to('cuda').bfloat16(), k.to('cuda').bfloat16(), v.to('cuda').bfloat16(), heads, impl=ops.IMPL_TC)
+    ref_b = O.selsa_attention(q.bfloat16().float(), k.bfloat16().float(), v.bfloat16().float(), heads)
+    assert rel_err(out_b, ref_b) < SELSA_BF16_TOL, rel_err(out_b, ref_b)
+
+
+def test_selsa_attention_tc_large_logits():
+    """rows whose maximum moves between chunks exercise the running-max correction."""
+    g = torch.Generator().manual_seed(3)
+    N, M, heads = 200, 2000, 2
+    q = torch.randn(N, 128, generator=g) * 3
+    k = torch.randn(M, 128, generator=g) * 3
+    k[M // 2:] *= 2.0
+    v = torch.randn(M, 128, generator=g)
+    ref = O.selsa_attention(q.double(), k.double(), v.double(), heads).float()
+    out = ops.selsa_attention(q.to('cuda'), k.to('cuda'), v.to('cuda'), heads, impl=ops.IMPL_TC)
+    assert rel_err(out, ref) < 2e-2   # tf32 logits of magnitude ~100: softmax amplifies operand rounding
+    out_s = ops.selsa_attention(q.to('cuda'), k.to('cuda'), v.to('cuda'), heads, impl=ops.IMPL_SIMT)
+    assert rel_err(out_s, ref) < 1e-3
+
+
+def test_selsa_aggregator_golden_tc(golden):
+    m = vod.build_aggregator(dict(type='SelsaAggregator', in_channels=128, num_attention_blocks=2))
+    m.load_state_dict(params(golden, 'selsa64_p.'))
+    m = m.to('cuda')
+    torch.backends.cuda.matmul.allow_tf32 = False
+    out = m(golden['selsa64_x'].to('cuda'), golden['selsa64_ref_x'].to('cuda'))   # auto -> tcgen05 (d = 64)
+    assert rel_err(out, golden['selsa64_out']) < SELSA_TF32_TOL
+
+
+# ------------------------------------------------------------------------------------------ (4) most-similar on tcgen05
+def _msra_compare(N, C, T, H, W, seed):
+    g = torch.Generator().manual_seed(seed)
+    roi = torch.relu(torch.randn(N, C, 7, 7, generator=g))
+    ref = torch.relu(torch.randn(T, C, H, W, generator=g))
+    out0, idx0, sim0 = O.most_similar_roi_align(roi, ref, 2, return_indices=True)
+    ref_nhwc, norm, unit = ops.to_nhwc(ref.to('cuda'), want_norm=True, want_unit_bf16=True)
+    rows = roi.permute(0, 2, 3, 1).reshape(N * 49, C).to('cuda')
+    out1, idx1, val1 = ops.msra_topk_sample(rows, ref_nhwc, 2, ref_norm=norm, ref_unit=unit, impl=ops.IMPL_TC,
+                                            return_indices=True)
+    idx1 = idx1.cpu().long()
+    same = (idx1.sort(dim=2).values == idx0.sort(dim=2).values).all(dim=2)
+    for r, t in (~same).nonzero().tolist():
+        # tie tolerance: a differing location must have the same fp32 similarity up to 1e-6
+        v_ours = sim0[r, t, idx1[r, t]].sort().values
+        v_ref = sim0[r, t, idx0[r, t]].sort().values
+        assert (v_ours - v_ref).abs().max() <= 1e-6, (r, t, v_ours, v_ref)
+    got = out1.view(T, N, 7, 7, C).permute(0, 1, 4, 2, 3)
+    assert rel_err(got, out0) < 1e-3
+    return float(same.float().mean())
+
+
+@pytest.mark.parametrize('N,C,T,H,W', [(6, 64, 3, 12, 20), (20, 512, 3, 38, 63), (3, 128, 2, 9, 15)])
+def test_msra_tc_vs_oracle(N, C, T, H, W):
+    frac = _msra_compare(N, C, T, H, W, N + C)
+    assert frac > 0.999
+
+
+def test_temporal_roi_align_golden_tc(golden):
+    torch.backends.cudnn.allow_tf32 = False
+    m = vod.build_roi_extractor(dict(type='TemporalRoIAlign', num_most_similar_points=2, num_temporal_attention_blocks=4,
+                                     roi_layer=dict(type='RoIAlign', output_size=7, sampling_ratio=2),
+                                     out_channels=64, featmap_strides=[16]))
+    m.load_state_dict(params(golden, 'troi_p.'))
+    m = m.to('cuda')
+    out = m((golden['troi_feat'].to('cuda'),), golden['troi_rois'].to('cuda'), ref_feats=(golden['troi_ref'].to('cuda'),))
+    assert rel_err(out, golden['troi_out']) < 1e-4

@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py -- VID frames/s through the SELSA + TemporalRoIAlign aggregation path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg3|cfg1]
+
+A "step" = one key frame through SelsaRoIHead.simple_test at the shapes of configs[2]
+("SELSA + TemporalRoIAlign R-50-DC5, 14 ref frames, 300 proposals/frame"): TemporalRoIAlign(key) over
+T=15 reference maps, RoIAlign of the 4500 reference RoIs, the 3 shared FCs each followed by a
+SelsaAggregator, get_bboxes and multiclass NMS.  Inputs are synthetic: relu(N(0,1))
+stride-16 feature maps [*,512,38,63] of a 600x1000 frame, RPN-like proposals, random-init weights.
+
+value   whole-job frames/s with the inputs resident in HBM (device time, CUDA events, max over ranks)
+e2e     the same through the public API with HOST (pinned) inputs: H2D of the step's feature maps and
+        proposals and D2H of the detections inside the timed region
+roofline  the dominant hand-written kernel timed alone with CUDA events (L2 flushed between launches),
+        algorithmic FLOPs/bytes from BASELINE.md section 3 over that time vs MEASURED_PEAKS.json
+cpu_baseline  the CPU oracle (port of the reference's Python path) on the host cores, one key frame
+--impl reference  times that CPU port on all host threads (the reference is Python + un-vendored mmcv:
+        nothing compiles into oracle/_ref), rank 0 only.
+
+Multi-GPU (torchrun): clips are sharded by rank (one independent clip stream per rank, weak scaling,
+no data-path collective); the only exchange is one NCCL all_gather of the per-frame detections.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (N proposals, T frames in the reference set incl. key, shared fcs, TRoIA)
+    'cfg3': dict(N=300, T=15, fcs=3, troi=True,
+                 workload='SELSA+TemporalRoIAlign R-50-DC5, 14 ref frames (+key), 300 proposals/frame, 600x1000'),
+    'cfg1': dict(N=300, T=3, fcs=2, troi=False,
+                 workload='SELSA R-50-DC5, 2 ref frames (+key), 300 proposals/frame, 600x1000'),
+}
+C, H, W, D, CLASSES = 512, 38, 63, 1024, 30
+IMG_SHAPE = (600, 1000, 3)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p['hbm_gbs'], tf_burst=p['bf16_tflops'], tf_sust=p.get('bf16_tflops_sustained', p['bf16_tflops']),
+                    src='measured')
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src='fallback')
+
+
+# --------------------------------------------------------------------------------------------- inputs
+def make_inputs(cfg, seed, pinned=False):
+    """One clip position: feature maps of the T reference frames (the last one is the key frame, as
+    SELSA.extract_feats builds ref_x = cat(memo, key), selsa.py:220-223) + proposals."""
+    g = torch.Generator().manual_seed(1234 + seed)
+    N, T = cfg['N'], cfg['T']
+    ref_x = torch.relu(torch.randn(T, C, H, W, generator=g))
+
+    def props(n):
+        c = torch.rand(n, 2, generator=g) * torch.tensor([1000., 600.])
+        lw = torch.rand(n, generator=g) * (torch.log(torch.tensor(600. / 16))) + torch.log(torch.tensor(16.))
+        lh = torch.rand(n, generator=g) * (torch.log(torch.tensor(400. / 16))) + torch.log(torch.tensor(16.))
+        w, h = torch.exp(lw), torch.exp(lh)
+        b = torch.stack([c[:, 0] - w / 2, c[:, 1] - h / 2, c[:, 0] + w / 2, c[:, 1] + h / 2], 1)
+        b[:, 0::2] = b[:, 0::2].clamp(0, 1000.)
+        b[:, 1::2] = b[:, 1::2].clamp(0, 600.)
+        return b
+    props_all = torch.stack([props(N) for _ in range(T + 1)], 0)   # [T+1, N, 4]: refs..., key last
+    if pinned:
+        ref_x, props_all = ref_x.pin_memory(), props_all.pin_memory()
+    return ref_x, props_all
+
+
+def build_head(cfg, device):
+    import lowlightenvironmentvideoobjectdetection_b200 as vod
+    torch.manual_seed(0)
+    if cfg['troi']:
+        ext = dict(type='TemporalRoIAlign', num_most_similar_points=2, num_temporal_attention_blocks=4,
+                   roi_layer=dict(type='RoIAlign', output_size=7, sampling_ratio=2), out_channels=C, featmap_strides=[16])
+    else:
+        ext = dict(type='SingleRoIExtractor', roi_layer=dict(type='RoIAlign', output_size=7, sampling_ratio=2),
+                   out_channels=C, featmap_strides=[16])
+    head = vod.SelsaRoIHead(
+        bbox_roi_extractor=ext,
+        bbox_head=dict(type='SelsaBBoxHead', num_shared_fcs=cfg['fcs'], in_channels=C, fc_out_channels=D,
+                       roi_feat_size=7, num_classes=CLASSES,
+                       aggregator=dict(type='SelsaAggregator', in_channels=D, num_attention_blocks=16)),
+        test_cfg=dict(score_thr=0.0001, nms=dict(type='nms', iou_threshold=0.5), max_per_img=100))
+    return head.to(device).eval()
+
+
+def run_step(head, ref_x, props_all, metas):
+    """SELSA.simple_test's RoI-head part (mmtracking/mmtrack/models/vid/selsa.py:319-335)."""
+    T = ref_x.shape[0]
+    x = ref_x[T - 1:T]
+    proposals = [props_all[T]]
+    ref_proposals = [props_all[t] for t in range(T)]
+    dets, labels = head.simple_test((x,), (ref_x,), proposals, ref_proposals, metas, rescale=False)
+    return dets[0], labels[0]
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonSwPowerCap: 'sw_power_cap', nv.nvmlClocksThrottleReasonHwSlowdown: 'hw_slowdown',
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: 'sw_thermal_slowdown',
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: 'hw_thermal_slowdown',
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: 'hw_power_brake'}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return dict(sm_mhz=(s[len(s) // 2] if s else None), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons))
+
+
+# --------------------------------------------------------------------------------------------- roofline of the dominant kernel
+def kernel_rooflines(cfg, device, peaks):
+    """Times each hand-written kernel of the step alone (CUDA events on the launching stream, L2 flushed by
+    writing a 256 MB buffer between launches) and converts BASELINE.md's algorithmic work into achieved rates."""
+    from lowlightenvironmentvideoobjectdetection_b200 import ops
+    N, T = cfg['N'], cfg['T']
+    M = N * T
+    P = 49
+    g = torch.Generator(device=device).manual_seed(7)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+
+    def timeit(fn, iters=5):
+        fn(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        return sum(ts) / len(ts)
+
+    ref_x, props_all = make_inputs(cfg, 99)
+    ref_x = ref_x.to(device)
+    rois = torch.cat([torch.cat([torch.full((N, 1), float(t)), props_all[t]], 1) for t in range(T)], 0).to(device)
+    key_rois = torch.cat([torch.zeros(N, 1), props_all[T]], 1).to(device)
+    out = {}
+    ref_nhwc, norm, unit = ops.to_nhwc(ref_x, want_norm=True, want_unit_bf16=True)
+    ref_nhwc = ref_nhwc.contiguous()
+    # (1) RoIAlign of the reference RoIs: bytes = T*C*HW*4 + M*C*P*4
+    t = timeit(lambda: ops.roi_align_nhwc(ref_nhwc, rois, 7, 1 / 16, 2, True))
+    b = (T * C * H * W + M * C * P) * 4
+    out['roi_align_refs'] = dict(bound='hbm', seconds=t, achieved=b / t / 1e9, peak=peaks['hbm'], unit='GB/s', bytes=b)
+    if cfg['troi']:
+        key_rows = ops.roi_align_nhwc(ref_nhwc[T - 1:T].contiguous(), key_rois, 7, 1 / 16, 2, True, out_nhwc=True).view(N * P, C)
+        # (4) most-similar sampling: flops = 2*N*P*C*T*HW
+        fl = 2.0 * N * P * C * T * H * W
+        t = timeit(lambda: ops.msra_topk_sample(key_rows, ref_nhwc, 2, ref_norm=norm, ref_unit=unit), iters=3)
+        out['msra_topk_sample'] = dict(bound='tensor', seconds=t, achieved=fl / t / 1e12, peak=peaks['tf_burst'], unit='TFLOP/s', flops=fl)
+        # (4') TAFA weighting: bytes = (2*(T+1)+1)*N*C*P*4
+        x_all = torch.randn(T + 1, N, P, C, device=device, generator=g)
+        emb = torch.randn(T + 1, N, P, C, device=device, generator=g)
+        t = timeit(lambda: ops.tafa_weighted_sum(x_all, emb, 4))
+        b = (2 * (T + 1) + 1) * N * C * P * 4
+        out['tafa_weighted_sum'] = dict(bound='hbm', seconds=t, achieved=b / t / 1e9, peak=peaks['hbm'], unit='GB/s', bytes=b)
+        del x_all, emb
+    # (3) SELSA core per layer: flops = 4*N*M*D ; bytes = (2N+2M)*D*4
+    q = torch.randn(N, D, device=device, generator=g)
+    k = torch.randn(M, D, device=device, generator=g)
+    vt = torch.randn(D, (M + 7) // 8 * 8, device=device, generator=g)
+    t = timeit(lambda: ops.selsa_attention(q, k, vt, 16, v_transposed=True))
+    fl = 4.0 * N * M * D
+    by = (2 * N + 2 * M) * D * 4
+    out['selsa_attention'] = dict(bound='tensor', seconds=t, achieved=fl / t / 1e12, peak=peaks['tf_burst'] / 2, unit='TFLOP/s',
+                                  flops=fl, bytes=by, hbm_gbs=by / t / 1e9, note='peak = tf32 dense ~ bf16/2')
+    # (5) RCNN NMS: n = 30*N candidates
+    n = CLASSES * N
+    base = props_all[T].to(device)
+    boxes = (base[:, None, :] + torch.randn(N, CLASSES, 4, device=device, generator=g) * 4).reshape(-1, 4)
+    scores = torch.rand(n, device=device, generator=g)
+    labels = torch.arange(CLASSES, device=device).repeat(N)
+    t = timeit(lambda: ops.nms_device(boxes, scores, labels, 0.5, ops.NMS_MODE_OFFSET, max_keep=100))
+    b = n * 20 + n * ((n + 63) // 64) * 8
+    out['batched_nms_rcnn'] = dict(bound='hbm', seconds=t, achieved=b / t / 1e9, peak=peaks['hbm'], unit='GB/s', bytes=b)
+    for v in out.values():
+        v['frac'] = v['achieved'] / v['peak']
+    return out
+
+
+# --------------------------------------------------------------------------------------------- CPU port (oracle)
+def cpu_step(cfg, head_sd, ref_x, props_all):
+    from oracle import vod_oracle as O
+    N, T = cfg['N'], cfg['T']
+    rois = torch.cat([torch.zeros(N, 1), props_all[T]], 1)
+    ref_rois = torch.cat([torch.cat([torch.full((N, 1), float(t)), props_all[t]], 1) for t in range(T)], 0)
+    x = ref_x[T - 1:T]
+    if cfg['troi']:
+        bbox_feats = O.temporal_roi_align(x, rois, ref_x, head_sd['bbox_roi_extractor.embed_network.conv.weight'],
+                                          head_sd['bbox_roi_extractor.embed_network.conv.bias'], 2, 4)
+    else:
+        bbox_feats = O.roi_align(x, rois, 7, 1 / 16, 2, True)
+    ref_feats = O.roi_align(ref_x, ref_rois, 7, 1 / 16, 2, True)
+    hp = {k[len('bbox_head.'):]: v for k, v in head_sd.items() if k.startswith('bbox_head.')}
+    cls, reg = O.selsa_bbox_head(bbox_feats, ref_feats, hp, cfg['fcs'], 16)
+    return O.get_bboxes(rois, cls, reg, IMG_SHAPE, (1., 1., 1., 1.), False, 0.0001, dict(type='nms', iou_threshold=0.5), 100)
+
+
+def cpu_head_state(cfg):
+    """Random-init weights of the same architecture, built without touching CUDA."""
+    import lowlightenvironmentvideoobjectdetection_b200 as vod  # module definitions only (nn.Module on CPU)
+    head = build_head(cfg, torch.device('cpu'))
+    return {k: v.detach() for k, v in head.state_dict().items()}
+
+
+def time_cpu(cfg, steps, warmup, budget_s=150.0):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    os.environ.setdefault('OMP_NUM_THREADS', str(cores))
+    sd = cpu_head_state(cfg)
+    times = []
+    with torch.no_grad():
+        t_start = time.perf_counter()
+        for i in range(warmup + steps):
+            ref_x, props_all = make_inputs(cfg, i)
+            t0 = time.perf_counter()
+            cpu_step(cfg, sd, ref_x, props_all)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+            # bounded sample: stop early when the wall-clock budget is used up (at least one timed step)
+            if times and time.perf_counter() - t_start > budget_s:
+                break
+            if not times and i + 1 >= warmup and time.perf_counter() - t_start > budget_s:
+                warmup = i + 1
+    return times, cores
+
+
+# --------------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--config', default='cfg3', choices=sorted(CONFIGS))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-roofline', action='store_true')
+    ap.add_argument('--kernels-only', action='store_true', help='run only the per-kernel roofline pass (ncu target)')
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    metric, unit = 'VID frames/sec (SELSA+TRoIA path)', 'frames/s'
+    config = dict(workload=cfg['workload'], proposals=cfg['N'], ref_frames=cfg['T'] - 1, shared_fcs=cfg['fcs'],
+                  feature='[T,512,38,63] fp32', l2_policy='per-step working set (>1.4 GB at cfg3) exceeds the 126 MB L2; '
+                  'inputs rotate over 4 clip positions', parallelism='clip-sharded x%d' % world)
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        warm = min(args.warmup, 1)
+        times, cores = time_cpu(cfg, args.steps, warm)
+        ms = 1e3 * sum(times) / len(times)
+        val = 1e3 / ms
+        print(json.dumps({
+            'impl': 'reference', 'metric': metric, 'value': val, 'unit': unit, 'n_gpus': args.gpus, 'steps': len(times),
+            'warmup': warm, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic', 'config': config,
+            'cpu_baseline': {'value': val, 'unit': unit, 'cores': cores, 'kind': 'port',
+                             'sample': '%d key frame(s) of the same workload on the host cores (torch CPU + C/OpenMP oracle); '
+                                       'steps bounded by a 150 s wall-clock budget' % len(times)},
+            'e2e': {'value': val, 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        return
+
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback exists for the product path)'
+    import lowlightenvironmentvideoobjectdetection_b200 as vod
+    device = torch.device('cuda', local_rank)
+    torch.cuda.set_device(device)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=device)
+    # library GEMMs/convs around the path (shared FCs, embed conv) run tf32 like our own tensor-core kernels
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    peaks = load_peaks()
+    if args.kernels_only:
+        with torch.no_grad():
+            kr = kernel_rooflines(cfg, device, peaks)
+        print(json.dumps({k: {kk: (round(vv, 6) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in kr.items()}))
+        return
+    head = build_head(cfg, device)
+    metas = [dict(img_shape=IMG_SHAPE, scale_factor=(1., 1., 1., 1.))]
+    lib = vod._lib.load()
+
+    n_sets = 4
+    host_sets = [make_inputs(cfg, rank * 1000 + i, pinned=True) for i in range(n_sets)]
+    dev_sets = [(a.to(device), b.to(device)) for a, b in host_sets]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(seconds):
+        if world == 1:
+            return seconds
+        t = torch.tensor([seconds], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    det_buf = torch.zeros(args.steps, 100, 6, device=device)
+
+    def gather_detections():
+        if world > 1:
+            outs = [torch.empty_like(det_buf) for _ in range(world)]
+            dist.all_gather(outs, det_buf)
+
+    # ------------------------------------------------ device-resident throughput
+    with torch.no_grad():
+        for i in range(args.warmup):
+            run_step(head, *dev_sets[i % n_sets], metas)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        l0 = lib.vod_kernel_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            d, l = run_step(head, *dev_sets[i % n_sets], metas)
+            det_buf[i, :d.shape[0], :5] = d
+            det_buf[i, :d.shape[0], 5] = l.float()
+        gather_detections()
+        e1.record()
+        barrier()
+        sampler.stop_flag = True
+        launches = lib.vod_kernel_launch_count() - l0
+        t_dev = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+
+        # ------------------------------------------------ end to end: pinned host inputs in, detections out
+        h2d = host_sets[0][0].numel() * 4 + host_sets[0][1].numel() * 4
+        d2h = 100 * 6 * 4
+        out_host = torch.empty(100, 6).pin_memory()
+        for i in range(2):
+            a, b = host_sets[i % n_sets]
+            run_step(head, a.to(device, non_blocking=True), b.to(device, non_blocking=True), metas)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            a, b = host_sets[i % n_sets]
+            d, l = run_step(head, a.to(device, non_blocking=True), b.to(device, non_blocking=True), metas)
+            det_buf[i].zero_()
+            det_buf[i, :d.shape[0], :5] = d
+            det_buf[i, :d.shape[0], 5] = l.float()
+            out_host.copy_(det_buf[i], non_blocking=True)
+        gather_detections()
+        e1.record()
+        barrier()
+        t_e2e = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+
+    frames = args.steps * world
+    result = {
+        'metric': metric, 'value': frames / t_dev, 'unit': unit, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * t_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'tf32', 'data': 'synthetic', 'config': config,
+        'e2e': {'value': frames / t_e2e, 'unit': unit, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+        'gpu_launches': int(launches), 'clocks': sampler.summary(),
+    }
+    if rank == 0 and not args.no_roofline:
+        with torch.no_grad():
+            kr = kernel_rooflines(cfg, device, peaks)
+        dom = max(kr, key=lambda k: kr[k]['seconds'])
+        r = kr[dom]
+        result['roofline'] = {'kernel': dom, 'bound': r['bound'], 'achieved': r['achieved'], 'peak': r['peak'], 'unit': r['unit'],
+                              'frac': r['frac'], 'traffic': None, 'peak_source': peaks['src'] + ' (burst: kernel timed alone)'}
+        result['kernels'] = {k: {kk: (round(vv, 6) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in kr.items()}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        times, cores = time_cpu(cfg, 1, 0)
+        result['cpu_baseline'] = {'value': 1.0 / times[0], 'unit': unit, 'cores': cores, 'kind': 'port',
+                                  'sample': '1 key frame of the same workload (%.1f s) on the host cores: torch CPU + C/OpenMP oracle' % times[0]}
+    if world > 1:
+        barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(result))
+
+
+if __name__ == '__main__':
+    main()

@@ -43,6 +43,8 @@ int vod_version(void);
 const char *vod_last_error(void);
 /* 1 when the visible device is compute capability 10.x (tcgen05 / TMEM / TMA paths usable). */
 int vod_device_is_sm100(void);
+/* Total number of CUDA kernels this library has launched in the process (monotonic; for benchmarks). */
+long long vod_kernel_launch_count(void);
 
 /* ------------------------------------------------------------------ layout
  * NCHW fp32 -> NHWC fp32 (+ optional per-pixel ||x||_2 over C and optional
@@ -130,6 +132,8 @@ int vod_msra_topk_sample(const float *roi_feats, const float *ref_nhwc, const fl
 
 /* ------------------------- (4') TemporalRoIAlign: temporal attention weighting
  * x_all, emb_all [T1, N, P, C] fp32 (frame 0 = the key's own RoI features);
+ * emb_bias [C] (nullable) is added to every embedding vector on load, so the caller's embed conv
+ * can run without its bias and no separate bias-add pass touches emb_all;
  * per (n, bin, head) dot(emb[t], emb[0]) over C/heads channels / sqrt(C/heads),
  * softmax over t, out = sum_t w * x_all[t].
  *   out_layout 0: out [N, C, P] (== [N,C,ph,pw]); 1: out [N, P, C].
@@ -137,8 +141,8 @@ int vod_msra_topk_sample(const float *roi_feats, const float *ref_nhwc, const fl
  * replaces: the weighting half of temporal_attentional_feature_aggregation,
  *   mmtracking/mmtrack/models/roi_heads/roi_extractors/temporal_roi_align.py:77-97
  */
-int vod_tafa_weighted_sum(const float *x_all, const float *emb_all, float *out, int T1, int N, int P,
-                          int C, int heads, int out_layout, vod_stream_t stream);
+int vod_tafa_weighted_sum(const float *x_all, const float *emb_all, const float *emb_bias, float *out,
+                          int T1, int N, int P, int C, int heads, int out_layout, vod_stream_t stream);
 
 /* -------------------------------------------------------- (5) batched NMS
  * Bitmask NMS with the sort, mask and the greedy sweep all on the device (no

@@ -26,6 +26,7 @@ SIGNATURES = {
     'vod_version': (_I, []),
     'vod_last_error': (_c.c_char_p, []),
     'vod_device_is_sm100': (_I, []),
+    'vod_kernel_launch_count': (_c.c_longlong, []),
     'vod_nchw_to_nhwc': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     'vod_rows_l2norm': (_I, [_P, _P, _P, _I, _I, _P]),
     'vod_roi_align_fwd': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _I, _P]),
@@ -36,7 +37,7 @@ SIGNATURES = {
     'vod_selsa_attn': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _I, _I, _I, _P, _SZ, _P]),
     'vod_msra_workspace_bytes': (_SZ, [_I, _I, _I, _I, _I]),
     'vod_msra_topk_sample': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _SZ, _P]),
-    'vod_tafa_weighted_sum': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    'vod_tafa_weighted_sum': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     'vod_nms_workspace_bytes': (_SZ, [_I, _I]),
     'vod_batched_nms': (_I, [_P, _P, _P, _I, _c.POINTER(_I), _I, _F, _I, _I, _P, _P, _P, _SZ, _P]),
     'vod_test_gemm_nt': (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
@@ -100,7 +101,8 @@ def require_cuda(*tensors):
 
 
 class Workspace:
-    """Grow-only per-device scratch buffer (1024-byte aligned, as torch's allocator returns)."""
+    """Grow-only per-device scratch buffer, 1024-byte aligned (TMA-swizzled tiles need it; torch's caching
+    allocator only guarantees 512)."""
 
     def __init__(self):
         self._buf = {}
@@ -109,6 +111,8 @@ class Workspace:
         key = (device.type, device.index)
         buf = self._buf.get(key)
         if buf is None or buf.numel() < nbytes:
-            buf = torch.empty(max(int(nbytes), 1024), dtype=torch.uint8, device=device)
+            raw = torch.empty(max(int(nbytes), 1024) + 1024, dtype=torch.uint8, device=device)
+            off = (-raw.data_ptr()) % 1024
+            buf = raw[off:off + max(int(nbytes), 1024)]
             self._buf[key] = buf
         return buf

@@ -1,6 +1,8 @@
 // common.cu -- error reporting + version for libvodagg.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace vod {
@@ -18,7 +20,13 @@ int fail(int code, const char *fmt, ...) {
     return code;
 }
 
+static std::atomic<long long> g_launches{0};
+void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launches_total() { return g_launches.load(std::memory_order_relaxed); }
+
 }  // namespace vod
+
+extern "C" long long vod_kernel_launch_count(void) { return vod::launches_total(); }
 
 extern "C" int vod_version(void) { return 100; }
 

@@ -13,6 +13,10 @@ namespace vod {
 char *last_error_buf();
 int fail(int code, const char *fmt, ...);
 
+// Every kernel launch site calls note_launch(); vod_kernel_launch_count() exposes the total so that
+// the benchmark can report how many of OUR kernels ran inside its timed region.
+void note_launch(int n = 1);
+
 static inline int check_launch(const char *what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(VOD_E_LAUNCH, "%s: %s", what, cudaGetErrorString(e));

@@ -153,10 +153,10 @@ extern "C" int vod_test_gemm_nt(const void *a, const void *b, float *d, int M, i
     dim3 grid(ceil_div(N, 128), ceil_div(M, 128));
     if (dtype == VOD_DTYPE_BF16) {
         cudaFuncSetAttribute(gemm_nt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        gemm_nt_kernel<true><<<grid, kGtThreads, smem, as_stream(stream)>>>(ta, tb, d, M, N, K);
+        gemm_nt_kernel<true><<<grid, kGtThreads, smem, as_stream(stream)>>>(ta, tb, d, M, N, K); note_launch();
     } else {
         cudaFuncSetAttribute(gemm_nt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        gemm_nt_kernel<false><<<grid, kGtThreads, smem, as_stream(stream)>>>(ta, tb, d, M, N, K);
+        gemm_nt_kernel<false><<<grid, kGtThreads, smem, as_stream(stream)>>>(ta, tb, d, M, N, K); note_launch();
     }
     return check_launch("vod_test_gemm_nt");
 }

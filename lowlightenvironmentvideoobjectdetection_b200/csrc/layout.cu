@@ -95,7 +95,7 @@ extern "C" int vod_nchw_to_nhwc(const float *in_nchw, float *out_nhwc, float *no
         cudaFuncSetAttribute(nchw_to_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(ceil_div(H * W, kTrPix), B);
     nchw_to_nhwc_kernel<<<grid, kTrThreads, smem, as_stream(stream)>>>(
-        in_nchw, out_nhwc, norm_out, reinterpret_cast<__nv_bfloat16 *>(out_unit_bf16), C, H * W);
+        in_nchw, out_nhwc, norm_out, reinterpret_cast<__nv_bfloat16 *>(out_unit_bf16), C, H * W); note_launch();
     return check_launch("vod_nchw_to_nhwc");
 }
 
@@ -104,6 +104,6 @@ extern "C" int vod_rows_l2norm(const float *rows, float *norm_out, void *out_uni
     if (R == 0) return VOD_OK;
     VOD_REQUIRE(rows && (norm_out || out_unit_bf16) && R > 0 && C > 0, "vod_rows_l2norm: bad args");
     rows_l2norm_kernel<<<ceil_div(R, 8), 256, 0, as_stream(stream)>>>(
-        rows, norm_out, reinterpret_cast<__nv_bfloat16 *>(out_unit_bf16), R, C);
+        rows, norm_out, reinterpret_cast<__nv_bfloat16 *>(out_unit_bf16), R, C); note_launch();
     return check_launch("vod_rows_l2norm");
 }

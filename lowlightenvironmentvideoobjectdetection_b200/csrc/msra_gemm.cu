@@ -8,13 +8,16 @@
 // candidates are then re-scored in exact fp32 (msra_rescore_kernel, tafa.cu) so that the selected
 // locations match the fp32 reference; the bf16 GEMM is only a pre-filter.
 //
-// Persistent kernel, one CTA per SM, 192 threads; a work unit = (128-row tile, frame t):
-//   warp 4   TMA producer: the A tile (128 rows x C, K-major bf16, 128B swizzle) stays resident in shared
+// Persistent kernel, one CTA per SM, 320 threads; a work unit = (128-row tile, frame t):
+//   warp 8   TMA producer: the A tile (128 rows x C, K-major bf16, 128B swizzle) stays resident in shared
 //            memory while the unit's B tiles (128 locations x 64 channels per stage) stream through a ring
-//   warp 5   MMA issuer: tcgen05.mma kind::f16 (bf16 in, fp32 accumulate), 128x128 accumulator,
+//   warp 9   MMA issuer: tcgen05.mma kind::f16 (bf16 in, fp32 accumulate), 128x128 accumulator,
 //            double buffered in TMEM (2 x 128 columns)
-//   warps 0-3 epilogue: thread = row; tcgen05.ld 32 columns at a time, threshold-filtered insertion
-//            into a sorted top-8 held in registers; one 32-byte store per (row, frame) at the end
+//   warps 0-7 epilogue: thread = row (two warps per TMEM lane quarter, each owning 64 of the tile's 128
+//            columns); every similarity is packed with its location into one order-preserving 32-bit key
+//            (20 value bits | 12 location bits) and pushed through a branch-free min/max insertion network
+//            that keeps the 4 largest keys in registers -- no divergence although the 32 lanes of a warp
+//            follow 32 different rows; one 16-byte store per (row, frame, column half) at the end
 // Units are assigned to CTAs in contiguous ranges so the A tile is reloaded only when the row tile changes.
 #include <cuda_bf16.h>
 
@@ -30,11 +33,12 @@ constexpr int kMgSlice = 64;         // bf16 elements per 128-byte K slice
 constexpr int kMgMaxSlices = 8;      // C <= 512
 constexpr int kMgStages = 5;
 constexpr int kMgTile = 128 * 128;   // bytes of one [128 x 128 B] slice tile
-constexpr int kMgThreads = 192;
+constexpr int kMgThreads = 320;
+constexpr int kMgEpiWarps = 8;
 constexpr int kMgSmem = kMgMaxSlices * kMgTile + kMgStages * kMgTile + 1024;
 
 struct MgParams {
-    int *cand;      // [NP, T, kMsraCand]
+    uint32_t *cand; // [NP, T, kMsraCand] packed keys: (ordered value & 0xFFFFF000) | location
     int NP, T, HW, nslices, row_tiles, ntiles;  // ntiles = ceil(HW / 128)
     int units;      // row_tiles * T
 };
@@ -59,16 +63,16 @@ msra_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         tc::mbar_init(&a_full, 1);
         tc::mbar_init(&a_empty, 1);
         for (int i = 0; i < kMgStages; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], kMgEpiWarps * 32); }
         tc::fence_barrier_init();
     }
-    if (warp == 5) tc::tmem_alloc(&tmem_slot, 256);
+    if (warp == 9) tc::tmem_alloc(&tmem_slot, 256);
     tc::tcgen05_fence_before();
     __syncthreads();
     tc::tcgen05_fence_after();
     const uint32_t tmem = tmem_slot;
 
-    if (warp == 4) {
+    if (warp == 8) {
         // ------------------------------------------------------------------ TMA producer
         if (tc::elect_one()) {
             tc::tma_prefetch_desc(&tm_a); tc::tma_prefetch_desc(&tm_b);
@@ -96,7 +100,7 @@ msra_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         // ------------------------------------------------------------------ MMA issuer
         constexpr uint32_t idesc = tc::umma_idesc(tc::kFmtBF16, kMgBM, kMgBN);
         int cur_rt = -1, a_loads = 0;
@@ -134,63 +138,63 @@ msra_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue: running top-8 per row
-        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+        // ------------------------------------------------------------------ epilogue: running top-4 keys per row
+        const int quarter = warp & 3, half = warp >> 2;
+        const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16) + half * 64;
         long tile_it = 0;
         for (int u = u0; u < u1; ++u) {
             const int rt = u / p.T, t = u % p.T;
-            float val[kMsraCand];
-            int loc[kMsraCand];
-#pragma unroll
-            for (int i = 0; i < kMsraCand; ++i) { val[i] = -INFINITY; loc[i] = -1; }
+            uint32_t k0 = 0, k1 = 0, k2 = 0, k3 = 0;   // descending; 0 = "nothing yet" (below every real key)
             for (int nt = 0; nt < p.ntiles; ++nt, ++tile_it) {
                 const int buf = (int)(tile_it & 1);
                 tc::mbar_wait(&acc_full[buf], (uint32_t)((tile_it >> 1) & 1));
                 tc::tcgen05_fence_after();
-#pragma unroll 1
-                for (int c = 0; c < kMgBN / 32; ++c) {
-                    uint32_t r[32];
-                    tc::tmem_ld_32x32(tl + buf * kMgBN + c * 32, r);
-                    tc::tmem_ld_wait();
-                    const int base = nt * kMgBN + c * 32;
-                    const int nvalid = p.HW - base;  // columns of this frame that exist
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float v = __uint_as_float(r[j]);
-                        if (j < nvalid && v > val[kMsraCand - 1]) {
-                            // sorted insertion (descending); strict '>' keeps the earlier location on ties
-                            float cv = v; int cl = base + j;
-#pragma unroll
-                            for (int q = 0; q < kMsraCand; ++q) {
-                                if (cv > val[q]) {
-                                    const float tv = val[q]; const int tl2 = loc[q];
-                                    val[q] = cv; loc[q] = cl; cv = tv; cl = tl2;
-                                }
-                            }
-                        }
-                    }
-                }
+                uint32_t ra[32], rb[32];
+                tc::tmem_ld_32x32(tl + buf * kMgBN, ra);
+                tc::tmem_ld_32x32(tl + buf * kMgBN + 32, rb);
+                tc::tmem_ld_wait();
                 tc::tcgen05_fence_before();
-                tc::mbar_arrive(&acc_empty[buf]);
+                tc::mbar_arrive(&acc_empty[buf]);       // values are in registers: the MMA may overwrite the buffer
+                const uint32_t base = (uint32_t)(nt * kMgBN + half * 64);
+                const int nvalid = p.HW - (int)base;    // columns of this frame that exist (tail tile only)
+                auto push = [&](uint32_t bits, uint32_t loc, bool ok) {
+                    // order-preserving float -> uint, top 20 bits kept, location in the low 12 bits
+                    const uint32_t ord = bits ^ ((uint32_t)((int32_t)bits >> 31) | 0x80000000u);
+                    uint32_t key = ok ? ((ord & 0xFFFFF000u) | loc) : 0u;
+                    uint32_t hi;
+                    hi = max(k0, key); key = min(k0, key); k0 = hi;
+                    hi = max(k1, key); key = min(k1, key); k1 = hi;
+                    hi = max(k2, key); key = min(k2, key); k2 = hi;
+                    k3 = max(k3, key);
+                };
+                if (nvalid >= 64) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) push(ra[j], base + j, true);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) push(rb[j], base + 32 + j, true);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) push(ra[j], base + j, j < nvalid);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) push(rb[j], base + 32 + j, 32 + j < nvalid);
+                }
             }
-            const int row = rt * kMgBM + warp * 32 + lane;
-            if (row < p.NP) {
-                int4 *dst = reinterpret_cast<int4 *>(p.cand + ((size_t)row * p.T + t) * kMsraCand);
-                dst[0] = make_int4(loc[0], loc[1], loc[2], loc[3]);
-                dst[1] = make_int4(loc[4], loc[5], loc[6], loc[7]);
-            }
+            const int row = rt * kMgBM + quarter * 32 + lane;
+            if (row < p.NP)
+                *reinterpret_cast<uint4 *>(p.cand + ((size_t)row * p.T + t) * kMsraCand + half * 4) = make_uint4(k0, k1, k2, k3);
         }
     }
     tc::tcgen05_fence_before();
     __syncthreads();
-    if (warp == 5) tc::tmem_dealloc(tmem, 256);
+    if (warp == 9) tc::tmem_dealloc(tmem, 256);
 }
 
 bool msra_gemm_supported(int NP, int C, int T, int HW) {
-    return NP > 0 && T > 0 && HW > 0 && C % kMgSlice == 0 && C / kMgSlice <= kMgMaxSlices;
+    // HW <= 4096: the location shares a 32-bit key with the similarity (12 bits)
+    return NP > 0 && T > 0 && HW > 0 && HW <= 4096 && C % kMgSlice == 0 && C / kMgSlice <= kMgMaxSlices;
 }
 
-int msra_launch_gemm_topk(const void *roi_unit_bf16, const void *ref_unit_bf16, int *cand, int NP, int NP_pad, int C,
+int msra_launch_gemm_topk(const void *roi_unit_bf16, const void *ref_unit_bf16, uint32_t *cand, int NP, int NP_pad, int C,
                           int T, int HW, cudaStream_t st) {
     (void)NP_pad;
     CUtensorMap ta, tb;
@@ -205,7 +209,7 @@ int msra_launch_gemm_topk(const void *roi_unit_bf16, const void *ref_unit_bf16, 
     p.units = p.row_tiles * T;
     cudaFuncSetAttribute(msra_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMgSmem);
     const int grid = min(kNumSMs, p.units);
-    msra_gemm_topk_kernel<<<grid, kMgThreads, kMgSmem, st>>>(ta, tb, p);
+    msra_gemm_topk_kernel<<<grid, kMgThreads, kMgSmem, st>>>(ta, tb, p); note_launch();
     return check_launch("msra_gemm_topk");
 }
 
@@ -268,7 +272,7 @@ extern "C" int vod_msra_topk_sample(const float *roi_feats, const float *ref_nhw
     }
     cudaStream_t st = as_stream(stream);
     if (!use_tc) return msra_launch_scan(roi_feats, ref_nhwc, roi_norm, rn, out, idx_out, val_out, NP, C, T, HW, k, st);
-    int *cand = reinterpret_cast<int *>(wsb + w.cand);
+    uint32_t *cand = reinterpret_cast<uint32_t *>(wsb + w.cand);
     rc = msra_launch_gemm_topk(roi_unit, ru, cand, NP, NP, C, T, HW, st);
     if (rc) return rc;
     return msra_launch_rescore(roi_feats, ref_nhwc, roi_norm, rn, cand, kMsraCand, out, idx_out, val_out, NP, C, T, HW, k, st);

@@ -279,15 +279,15 @@ extern "C" int vod_batched_nms(const float *boxes, const float *scores, const in
     // enough j-splits to fill the machine (~4 CTAs/SM), each split at least 256 candidates
     int jsplits = max(1, min(ceil_div(max_seg, 256), ceil_div(4 * kNumSMs, iblocks * n_images)));
     nms_rank_kernel<<<dim3(iblocks, jsplits, n_images), kRankThreads, 0, st>>>(
-        boxes, scores, seg, w.rank, w.segmax, mode == 1);
+        boxes, scores, seg, w.rank, w.segmax, mode == 1); note_launch();
     nms_scatter_kernel<<<dim3(ceil_div(max_seg, 256), n_images), 256, 0, st>>>(
-        boxes, labels, seg, w.rank, w.segmax, mode, w.sboxes, w.sidx, w.slab);
+        boxes, labels, seg, w.rank, w.segmax, mode, w.sboxes, w.sidx, w.slab); note_launch();
     nms_mask_kernel<<<dim3(words, words, n_images), 64, 0, st>>>(w.sboxes, w.slab, seg, iou_thr, mode,
-                                                                 words, w.mask);
+                                                                 words, w.mask); note_launch();
     size_t smem = sizeof(unsigned long long) * words;
     if (smem > 40 * 1024)
         cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     nms_sweep_kernel<<<n_images, kSweepThreads, smem, st>>>(w.mask, w.sidx, seg, words, max_keep,
-                                                            keep_out, num_keep_out);
+                                                            keep_out, num_keep_out); note_launch();
     return check_launch("vod_batched_nms");
 }

@@ -188,7 +188,7 @@ static int launch_roi(const float *feat, const float *rois, float *out, int B, i
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
     dim3 grid(K, ceil_div(C, CS));
     kern<<<grid, kRoiWarps * 32, smem, st>>>(feat, rois, out, B, C, H, W, K, ph, pw, scale, sr, aligned,
-                                             out_layout);
+                                             out_layout); note_launch();
     return check_launch("vod_roi_align_fwd");
 }
 

@@ -66,10 +66,11 @@ static int launch_simt(const T *q, const T *k, const T *v, float *out, int N, in
                        int v_layout, int ldv, cudaStream_t st) {
     const long tasks = (long)N * heads;
     const unsigned grid = (unsigned)ceil_div(tasks, (long)kSimtWarps);
+    if (d > 128) return fail(VOD_E_UNSUPPORTED, "vod_selsa_attn: head dim %d > 128 unsupported", d);
     if (d <= 16) selsa_simt_kernel<T, 16><<<grid, kSimtWarps * 32, 0, st>>>(q, k, v, out, N, M, heads, d, scale, v_layout, ldv);
     else if (d <= 64) selsa_simt_kernel<T, 64><<<grid, kSimtWarps * 32, 0, st>>>(q, k, v, out, N, M, heads, d, scale, v_layout, ldv);
-    else if (d <= 128) selsa_simt_kernel<T, 128><<<grid, kSimtWarps * 32, 0, st>>>(q, k, v, out, N, M, heads, d, scale, v_layout, ldv);
-    else return fail(VOD_E_UNSUPPORTED, "vod_selsa_attn: head dim %d > 128 unsupported", d);
+    else selsa_simt_kernel<T, 128><<<grid, kSimtWarps * 32, 0, st>>>(q, k, v, out, N, M, heads, d, scale, v_layout, ldv);
+    note_launch();
     return check_launch("vod_selsa_attn(simt)");
 }
 

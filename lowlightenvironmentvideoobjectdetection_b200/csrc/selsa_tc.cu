@@ -387,10 +387,10 @@ static int launch_tc(const void *q, const void *k, const void *vt, int ldv, floa
     auto kern = selsa_tc_kernel<BF16>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
     dim3 grid(ceil_div(N, kBM), heads, p.splits);
-    kern<<<grid, kSelsaThreads, Cfg::kSmem, st>>>(tq, tk, tv, p);
+    kern<<<grid, kSelsaThreads, Cfg::kSmem, st>>>(tq, tk, tv, p); note_launch();
     if (p.splits > 1) {
         const long total = (long)N * heads * (kHD / 4);
-        selsa_merge_kernel<<<(unsigned)ceil_div(total, 256L), 256, 0, st>>>(p);
+        selsa_merge_kernel<<<(unsigned)ceil_div(total, 256L), 256, 0, st>>>(p); note_launch();
     }
     return check_launch("vod_selsa_attn(tcgen05)");
 }
@@ -408,7 +408,7 @@ int selsa_tc_launch(const void *q, const void *k, const void *v, float *out, int
     if (v_layout == 0) {
         const int D = heads * kHD;
         dim3 grid(ceil_div(w.ldv, 32), ceil_div(D, 32));
-        transpose_rows_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t *>(v), wsb + w.vt_off, M, D, w.ldv, eb);
+        transpose_rows_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t *>(v), wsb + w.vt_off, M, D, w.ldv, eb); note_launch();
         vt = wsb + w.vt_off;
         ld = w.ldv;
     }

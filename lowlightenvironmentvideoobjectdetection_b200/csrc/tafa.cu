@@ -18,8 +18,8 @@ constexpr int kTafaMaxT = 64;
 // CTA = (n, head).  VEC=4: lanes own 4 consecutive channels, chunks of 128 channels.
 template <int VEC>
 __global__ void __launch_bounds__(kTafaWarps * 32)
-tafa_kernel(const float *__restrict__ x_all, const float *__restrict__ emb_all, float *__restrict__ out, int T1,
-            int N, int P, int C, int hs, float scale, int use_attn, int out_layout) {
+tafa_kernel(const float *__restrict__ x_all, const float *__restrict__ emb_all, const float *__restrict__ emb_bias,
+            float *__restrict__ out, int T1, int N, int P, int C, int hs, float scale, int use_attn, int out_layout) {
     extern __shared__ __align__(16) float tile[];          // [hs][P] (layout 0)
     __shared__ float s_w[kTafaWarps][kTafaMaxT];
     constexpr int CH = 32 * VEC;
@@ -34,7 +34,8 @@ tafa_kernel(const float *__restrict__ x_all, const float *__restrict__ emb_all, 
         const size_t base = ((size_t)n * P + p) * C + c_head + lane * VEC;
         float *w = s_w[warp];
         if (use_attn) {
-            // logits_t = <emb[t], emb[0]>_head * scale
+            // logits_t = <emb[t] + b, emb[0] + b>_head * scale   (b = the embed conv's bias, folded in here so
+            // the conv can run bias-free and the [T1,N,P,C] embedding is not rewritten by a bias-add pass)
             for (int t = 0; t < T1; ++t) {
                 float d = 0.f;
                 for (int ch = 0; ch < nch; ++ch) {
@@ -42,9 +43,16 @@ tafa_kernel(const float *__restrict__ x_all, const float *__restrict__ emb_all, 
                         if (VEC == 4) {
                             float4 a = ldg_f4(emb_all + base + ch * CH);
                             float4 b = ldg_f4(emb_all + (size_t)t * frame_stride + base + ch * CH);
+                            if (emb_bias) {
+                                const float4 bb = ldg_f4(emb_bias + c_head + lane * VEC + ch * CH);
+                                a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+                                b.x += bb.x; b.y += bb.y; b.z += bb.z; b.w += bb.w;
+                            }
                             d = fmaf(a.x, b.x, d); d = fmaf(a.y, b.y, d); d = fmaf(a.z, b.z, d); d = fmaf(a.w, b.w, d);
                         } else {
-                            d = fmaf(__ldg(emb_all + base + ch * CH), __ldg(emb_all + (size_t)t * frame_stride + base + ch * CH), d);
+                            float a = __ldg(emb_all + base + ch * CH), b = __ldg(emb_all + (size_t)t * frame_stride + base + ch * CH);
+                            if (emb_bias) { const float bb = __ldg(emb_bias + c_head + lane + ch * CH); a += bb; b += bb; }
+                            d = fmaf(a, b, d);
                         }
                     }
                 }
@@ -231,46 +239,76 @@ msra_scan_kernel(const float *__restrict__ roi, const float *__restrict__ ref, c
                          val_out ? val_out + ((size_t)row * T + t) * k : nullptr, val, loc, k, C, lane);
 }
 
-// warp = (row, t) task; candidates cand[(row*T + t)*KC + j] (location or -1) from the tensor-core pass.
+// Tail of the tensor-core path.  warp = one RoI row (all T frames): the row is normalised once; for every
+// frame the 8 packed candidate keys of msra_gemm_topk_kernel are decoded, candidates whose bf16-GEMM
+// similarity lies within kMsraMargin of the 2nd best are re-scored in exact fp32
+//   sim = sum_c (roi[c] / |roi|) * (ref[c] / |ref|)      (temporal_roi_align.py:127-142)
+// and the exact top-k feeds the softmax + gather.  Typically 2-3 of the 8 candidates are re-scored.
 __global__ void __launch_bounds__(kScanWarps * 32)
 msra_rescore_kernel(const float *__restrict__ roi, const float *__restrict__ ref, const float *__restrict__ roi_norm,
-                    const float *__restrict__ ref_norm, const int *__restrict__ cand, int KC,
+                    const float *__restrict__ ref_norm, const uint32_t *__restrict__ cand, int KC,
                     float *__restrict__ out, int *__restrict__ idx_out, float *__restrict__ val_out, int NP, int C,
                     int T, int HW, int k) {
     extern __shared__ float s_roi[];  // [kScanWarps][C]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long task = (long)blockIdx.x * kScanWarps + warp;
-    if (task >= (long)NP * T) return;
-    const int row = (int)(task / T), t = (int)(task % T);
+    const int row = blockIdx.x * kScanWarps + warp;
+    if (row >= NP) return;
     float *q = s_roi + (size_t)warp * C;
     const float qn = roi_norm[row];
     for (int c = lane; c < C; c += 32) q[c] = __fdiv_rn(__ldg(roi + (size_t)row * C + c), qn);
     __syncwarp();
-    const float *ref_t = ref + (size_t)t * HW * C;
-    float val[kMsraMaxK]; int loc[kMsraMaxK];
-#pragma unroll
-    for (int i = 0; i < kMsraMaxK; ++i) { val[i] = -INFINITY; loc[i] = 0x7fffffff; }
-    const int *cd = cand + (size_t)task * KC;
-    for (int j = 0; j < KC; ++j) {
-        const int l = cd[j];
-        if (l < 0 || l >= HW) continue;  // warp-uniform
-        const float rn = ref_norm[(size_t)t * HW + l];
-        const float *r = ref_t + (size_t)l * C;
-        float s = 0.f;
-        if ((C & 3) == 0) {
-            for (int c = lane * 4; c < C; c += 128) {
-                float4 v = ldg_f4(r + c);
-                s = fmaf(q[c], __fdiv_rn(v.x, rn), s); s = fmaf(q[c + 1], __fdiv_rn(v.y, rn), s);
-                s = fmaf(q[c + 2], __fdiv_rn(v.z, rn), s); s = fmaf(q[c + 3], __fdiv_rn(v.w, rn), s);
+    for (int t = 0; t < T; ++t) {
+        const float *ref_t = ref + (size_t)t * HW * C;
+        // decode this frame's candidate keys (lane j < KC holds candidate j)
+        uint32_t key = lane < KC ? cand[((size_t)row * T + t) * KC + lane] : 0u;
+        const uint32_t ord = key & 0xFFFFF000u;
+        const float approx = key ? __uint_as_float((ord & 0x80000000u) ? (ord ^ 0x80000000u) : ~ord) : -INFINITY;
+        // k-th largest approximate similarity (k <= 4): repeatedly remove the maximum
+        float kth = approx;
+        {
+            float mine = approx;
+            bool removed = false;
+            for (int r = 0; r < k; ++r) {
+                float cur = removed ? -INFINITY : mine;
+                float m = warp_max(cur);
+                kth = m;
+                // remove exactly one holder of the maximum (lowest lane)
+                unsigned holders = __ballot_sync(0xffffffffu, !removed && cur == m);
+                if (holders && lane == __ffs(holders) - 1) removed = true;
             }
-        } else {
-            for (int c = lane; c < C; c += 32) s = fmaf(q[c], __fdiv_rn(__ldg(r + c), rn), s);
         }
-        s = warp_sum(s);
-        topk_insert<kMsraMaxK>(val, loc, s, l);  // identical on all lanes
+        // NaN approximations (zero-norm vectors) compare false: keep them as candidates so the NaN propagates
+        const bool want = key != 0u && !(approx < kth - kMsraMargin);
+        unsigned todo = __ballot_sync(0xffffffffu, want);
+        float val[kMsraMaxK]; int loc[kMsraMaxK];
+#pragma unroll
+        for (int i = 0; i < kMsraMaxK; ++i) { val[i] = -INFINITY; loc[i] = 0x7fffffff; }
+        bool any_nan = false;
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int l = (int)(__shfl_sync(0xffffffffu, key, j) & 0xFFFu);
+            if (l >= HW) continue;
+            const float rn = ref_norm[(size_t)t * HW + l];
+            const float *r = ref_t + (size_t)l * C;
+            float s = 0.f;
+            if ((C & 3) == 0) {
+                for (int c = lane * 4; c < C; c += 128) {
+                    float4 v = ldg_f4(r + c);
+                    s = fmaf(q[c], __fdiv_rn(v.x, rn), s); s = fmaf(q[c + 1], __fdiv_rn(v.y, rn), s);
+                    s = fmaf(q[c + 2], __fdiv_rn(v.z, rn), s); s = fmaf(q[c + 3], __fdiv_rn(v.w, rn), s);
+                }
+            } else {
+                for (int c = lane; c < C; c += 32) s = fmaf(q[c], __fdiv_rn(__ldg(r + c), rn), s);
+            }
+            s = warp_sum(s);
+            if (s != s) any_nan = true;            // torch.topk ranks NaN first: the reference row becomes NaN
+            topk_insert<kMsraMaxK>(val, loc, s, l);  // identical on all lanes
+        }
+        if (any_nan) loc[0] = 0x7fffffff;          // msra_emit writes a NaN row
+        msra_emit<kMsraMaxK>(ref_t, out + ((size_t)t * NP + row) * C, idx_out ? idx_out + ((size_t)row * T + t) * k : nullptr,
+                             val_out ? val_out + ((size_t)row * T + t) * k : nullptr, val, loc, k, C, lane);
     }
-    msra_emit<kMsraMaxK>(ref_t, out + ((size_t)t * NP + row) * C, idx_out ? idx_out + ((size_t)row * T + t) * k : nullptr,
-                         val_out ? val_out + ((size_t)row * T + t) * k : nullptr, val, loc, k, C, lane);
 }
 
 int msra_launch_scan(const float *roi, const float *ref, const float *roi_norm, const float *ref_norm, float *out,
@@ -279,18 +317,17 @@ int msra_launch_scan(const float *roi, const float *ref, const float *roi_norm, 
     if (smem > 40 * 1024) cudaFuncSetAttribute(msra_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     long tasks = (long)NP * T;
     msra_scan_kernel<<<(unsigned)ceil_div(tasks, (long)kScanWarps), kScanWarps * 32, smem, st>>>(
-        roi, ref, roi_norm, ref_norm, out, idx_out, val_out, NP, C, T, HW, k);
+        roi, ref, roi_norm, ref_norm, out, idx_out, val_out, NP, C, T, HW, k); note_launch();
     return check_launch("msra_scan");
 }
 
 int msra_launch_rescore(const float *roi, const float *ref, const float *roi_norm, const float *ref_norm,
-                        const int *cand, int KC, float *out, int *idx_out, float *val_out, int NP, int C, int T,
+                        const uint32_t *cand, int KC, float *out, int *idx_out, float *val_out, int NP, int C, int T,
                         int HW, int k, cudaStream_t st) {
     size_t smem = sizeof(float) * kScanWarps * C;
     if (smem > 40 * 1024) cudaFuncSetAttribute(msra_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    long tasks = (long)NP * T;
-    msra_rescore_kernel<<<(unsigned)ceil_div(tasks, (long)kScanWarps), kScanWarps * 32, smem, st>>>(
-        roi, ref, roi_norm, ref_norm, cand, KC, out, idx_out, val_out, NP, C, T, HW, k);
+    msra_rescore_kernel<<<(unsigned)ceil_div(NP, kScanWarps), kScanWarps * 32, smem, st>>>(
+        roi, ref, roi_norm, ref_norm, cand, KC, out, idx_out, val_out, NP, C, T, HW, k); note_launch();
     return check_launch("msra_rescore");
 }
 
@@ -298,8 +335,8 @@ int msra_launch_rescore(const float *roi, const float *ref, const float *roi_nor
 
 using namespace vod;
 
-extern "C" int vod_tafa_weighted_sum(const float *x_all, const float *emb_all, float *out, int T1, int N, int P,
-                                     int C, int heads, int out_layout, vod_stream_t stream) {
+extern "C" int vod_tafa_weighted_sum(const float *x_all, const float *emb_all, const float *emb_bias, float *out, int T1,
+                                     int N, int P, int C, int heads, int out_layout, vod_stream_t stream) {
     if (N == 0) return VOD_OK;
     VOD_REQUIRE(x_all && out, "vod_tafa_weighted_sum: null pointer");
     VOD_REQUIRE(T1 > 0 && T1 <= kTafaMaxT, "vod_tafa_weighted_sum: T1=%d not in [1,%d]", T1, kTafaMaxT);
@@ -316,16 +353,17 @@ extern "C" int vod_tafa_weighted_sum(const float *x_all, const float *emb_all, f
     VOD_REQUIRE(smem <= 200 * 1024, "vod_tafa_weighted_sum: head size %d x %d bins too large", hs, P);
     const bool vec4 = (hs % 4 == 0) && (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(x_all) & 15) == 0) &&
                       (!emb_all || (reinterpret_cast<uintptr_t>(emb_all) & 15) == 0) &&
+                      (!emb_bias || (reinterpret_cast<uintptr_t>(emb_bias) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     dim3 grid(N, groups);
     if (vec4) {
         if (smem > 40 * 1024) cudaFuncSetAttribute(tafa_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        tafa_kernel<4><<<grid, kTafaWarps * 32, smem, as_stream(stream)>>>(x_all, emb_all, out, T1, N, P, C, hs, scale,
-                                                                         use_attn, out_layout);
+        tafa_kernel<4><<<grid, kTafaWarps * 32, smem, as_stream(stream)>>>(x_all, emb_all, emb_bias, out, T1, N, P, C, hs, scale,
+                                                                         use_attn, out_layout); note_launch();
     } else {
         if (smem > 40 * 1024) cudaFuncSetAttribute(tafa_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        tafa_kernel<1><<<grid, kTafaWarps * 32, smem, as_stream(stream)>>>(x_all, emb_all, out, T1, N, P, C, hs, scale,
-                                                                         use_attn, out_layout);
+        tafa_kernel<1><<<grid, kTafaWarps * 32, smem, as_stream(stream)>>>(x_all, emb_all, emb_bias, out, T1, N, P, C, hs, scale,
+                                                                         use_attn, out_layout); note_launch();
     }
     return check_launch("vod_tafa_weighted_sum");
 }

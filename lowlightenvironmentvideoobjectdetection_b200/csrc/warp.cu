@@ -220,7 +220,7 @@ extern "C" int vod_flow_warp(const float *x, const float *flow, float *out, int 
     float s, inv_s;
     flow_scale(W, Wf, s, inv_s);
     dim3 grid(ceil_div(H * W, kWarpPix), ceil_div(C, kWarpCh), N);
-    flow_warp_kernel<<<grid, kWarpPix, 0, as_stream(stream)>>>(x, flow, out, C, H, W, Hf, Wf, s, inv_s);
+    flow_warp_kernel<<<grid, kWarpPix, 0, as_stream(stream)>>>(x, flow, out, C, H, W, Hf, Wf, s, inv_s); note_launch();
     return check_launch("vod_flow_warp");
 }
 
@@ -238,12 +238,12 @@ static int launch_embed(bool fused, const float *key_emb, const float *ref_emb, 
         if (smem > 40 * 1024)
             cudaFuncSetAttribute(embed_weighted_sum_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         embed_weighted_sum_kernel<true><<<grid, kEwPix * kEwLanes, smem, as_stream(stream)>>>(
-            key_emb, ref_emb, ref_x, flow, key_x, key_slot, out, T, C, Cx, H, W, Hf, Wf, s, inv_s);
+            key_emb, ref_emb, ref_x, flow, key_x, key_slot, out, T, C, Cx, H, W, Hf, Wf, s, inv_s); note_launch();
     } else {
         if (smem > 40 * 1024)
             cudaFuncSetAttribute(embed_weighted_sum_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         embed_weighted_sum_kernel<false><<<grid, kEwPix * kEwLanes, smem, as_stream(stream)>>>(
-            key_emb, ref_emb, ref_x, nullptr, nullptr, -1, out, T, C, Cx, H, W, 1, 1, s, inv_s);
+            key_emb, ref_emb, ref_x, nullptr, nullptr, -1, out, T, C, Cx, H, W, 1, 1, s, inv_s); note_launch();
     }
     return check_launch("vod_embed_weighted_sum");
 }

@@ -34,7 +34,23 @@ def _f32c(t):
 
 
 # ----------------------------------------------------------------------------- layout
+# One-entry memo: SelsaRoIHead._bbox_forward hands the SAME reference feature tensor to the extractor twice
+# (key call with ref_feats=, then the reference-RoI call); the second NHWC transposition is skipped.  The
+# entry keeps the source tensor alive and is validated by identity + in-place version counter.
+_nhwc_memo = {}
+
+
 def to_nhwc(x, want_norm=False, want_unit_bf16=False):
+    m = _nhwc_memo.get('e')
+    if m is not None and m[0] is x and m[1] == x._version and (m[3] is not None or not want_norm) \
+            and (m[4] is not None or not want_unit_bf16):
+        return m[2], m[3], m[4]
+    res = _to_nhwc(x, want_norm, want_unit_bf16)
+    _nhwc_memo['e'] = (x, x._version, res[0], res[1], res[2])
+    return res
+
+
+def _to_nhwc(x, want_norm=False, want_unit_bf16=False):
     """[B,C,H,W] fp32 -> ([B,H,W,C] fp32 contiguous, norm [B*H*W] | None, unit bf16 [B*H*W, C] | None).
 
     A channels_last input is consumed in place (zero copy) unless norms are requested."""
@@ -291,16 +307,19 @@ def msra_topk_sample(roi_rows, ref_nhwc, k=2, ref_norm=None, ref_unit=None, impl
     return out
 
 
-def tafa_weighted_sum(x_all, emb_all, num_heads, out_nhwc=False):
-    """x_all, emb_all [T1, N, P, C] fp32 -> [N, C, P] (or [N, P, C])."""
-    _lib.require_cuda(x_all, emb_all)
+def tafa_weighted_sum(x_all, emb_all, num_heads, out_nhwc=False, emb_bias=None):
+    """x_all, emb_all [T1, N, P, C] fp32 -> [N, C, P] (or [N, P, C]).  ``emb_bias`` [C] is added to the
+    embeddings on load (lets the embed conv run bias-free)."""
+    _lib.require_cuda(x_all, emb_all, emb_bias)
+    if emb_bias is not None:
+        emb_bias = _f32c(emb_bias)
     assert x_all.is_contiguous() and x_all.dtype == torch.float32
     T1, N, P, C = x_all.shape
     if emb_all is not None:
         assert emb_all.is_contiguous() and emb_all.shape == x_all.shape and emb_all.dtype == torch.float32
     out = torch.empty((N, P, C) if out_nhwc else (N, C, P), dtype=torch.float32, device=x_all.device)
     if N:
-        _lib.call('vod_tafa_weighted_sum', _lib.ptr(x_all), _lib.ptr(emb_all), _lib.ptr(out), T1, N, P, C,
+        _lib.call('vod_tafa_weighted_sum', _lib.ptr(x_all), _lib.ptr(emb_all), _lib.ptr(emb_bias), _lib.ptr(out), T1, N, P, C,
                   int(num_heads), int(bool(out_nhwc)), _lib.stream_ptr(x_all.device))
     return out
 

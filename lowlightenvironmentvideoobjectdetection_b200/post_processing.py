@@ -90,6 +90,12 @@ def delta2bbox(rois, deltas, means=(0., 0., 0., 0.), stds=(1., 1., 1., 1.), max_
 
 def bbox2roi(bbox_list):
     """transforms.py:58-77: list of [n,4(+)] per image -> [sum n, 5] with the image index in column 0."""
+    if len(bbox_list) > 1 and all(b.shape == bbox_list[0].shape and b.shape[0] > 0 for b in bbox_list):
+        # equal-sized proposal sets (the test-time case: max_num per frame): one stack instead of 2 kernels per image
+        n = bbox_list[0].shape[0]
+        boxes = torch.stack([b[:, :4] for b in bbox_list], 0)
+        ids = torch.arange(len(bbox_list), device=boxes.device, dtype=boxes.dtype).view(-1, 1, 1).expand(-1, n, 1)
+        return torch.cat([ids, boxes], dim=-1).view(-1, 5)
     rois_list = []
     for img_id, bboxes in enumerate(bbox_list):
         if bboxes.size(0) > 0:

@@ -87,11 +87,11 @@ class SingleRoIExtractor(BaseRoIExtractor):
     def _extract(self, feats, rois, roi_scale_factor=None):
         out_size = self.roi_layers[0].output_size
         num_levels = len(feats)
-        roi_feats = feats[0].new_zeros(rois.size(0), self.out_channels, *out_size)
         if num_levels == 1:
             if len(rois) == 0:
-                return roi_feats
+                return feats[0].new_zeros(0, self.out_channels, *out_size)
             return self.roi_layers[0](feats[0], rois)
+        roi_feats = feats[0].new_zeros(rois.size(0), self.out_channels, *out_size)
         target_lvls = self.map_roi_levels(rois, num_levels)
         if roi_scale_factor is not None:
             rois = self.roi_rescale(rois, roi_scale_factor)
@@ -182,9 +182,12 @@ class TemporalRoIAlign(SingleRoIExtractor):
         if self.num_temporal_attention_blocks > 0:
             # embed conv on the channels_last view: logical [(T+1)*N, C, 7, 7], memory [(T+1)*N, 7, 7, C]
             patches = x_all.view(T1 * N, rh, rw, C).permute(0, 3, 1, 2)
-            emb = self.embed_network(patches)                              # temporal_roi_align.py:74
-            emb = emb.permute(0, 2, 3, 1).contiguous().view(T1, N, P, C)  # no copy when cuDNN kept channels_last
-            out = ops.tafa_weighted_sum(x_all, emb, self.num_temporal_attention_blocks)
+            conv = self.embed_network.conv
+            # temporal_roi_align.py:74 -- the conv runs without its bias; the bias is added on load inside
+            # the weighting kernel (saves a full read+write pass over the [T+1,N,49,C] embedding)
+            emb = torch.nn.functional.conv2d(patches, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+            emb = emb.permute(0, 2, 3, 1).contiguous().view(T1, N, P, C)  # no copy: cuDNN keeps channels_last
+            out = ops.tafa_weighted_sum(x_all, emb, self.num_temporal_attention_blocks, emb_bias=conv.bias)
         else:
             out = ops.tafa_weighted_sum(x_all, None, 0)                    # plain mean, :203-206
         return out.view(N, C, rh, rw)

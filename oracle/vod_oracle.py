@@ -287,7 +287,7 @@ def temporal_roi_align(feat, rois, ref_feat, conv_w, conv_b, k=2, num_blocks=4,
 
 
 # --------------------------------------------------------------------- a10 (callers)
-def delta2bbox(rois, deltas, means=(0., 0., 0., 0.), stds=(0.1, 0.1, 0.2, 0.2),
+def delta2bbox(rois, deltas, means=(0., 0., 0., 0.), stds=(1., 1., 1., 1.),
                max_shape=None, wh_ratio_clip=16 / 1000):
     """mmdetection/mmdet/core/bbox/coder/delta_xywh_bbox_coder.py:134-237."""
     means = deltas.new_tensor(means).view(1, -1).repeat(1, deltas.size(1) // 4)
@@ -330,11 +330,12 @@ def selsa_bbox_head(x, ref_x, p, num_shared_fcs, num_heads=16):
 
 
 def get_bboxes(rois, cls_score, bbox_pred, img_shape, scale_factor, rescale, score_thr,
-               nms_cfg, max_per_img, return_inds=False):
+               nms_cfg, max_per_img, return_inds=False, target_means=(0., 0., 0., 0.),
+               target_stds=(0.2, 0.2, 0.2, 0.2)):
     """BBoxHead.get_bboxes, mmdetection/mmdet/models/roi_heads/bbox_heads/
     bbox_head.py:269-373 (softmax scores, class-specific regression)."""
     scores = torch.softmax(cls_score, dim=1)
-    bboxes = delta2bbox(rois[:, 1:], bbox_pred, max_shape=img_shape)
+    bboxes = delta2bbox(rois[:, 1:], bbox_pred, target_means, target_stds, max_shape=img_shape)
     if rescale and bboxes.size(0) > 0:
         sf = bboxes.new_tensor(scale_factor)
         bboxes = (bboxes.view(bboxes.size(0), -1, 4) / sf).view(bboxes.size()[0], -1)

@@ -154,6 +154,8 @@ def kernel_rooflines(cfg, device, peaks):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
 
     def timeit(fn, iters=5):
+        if os.environ.get('VOD_PROFILE'):
+            iters = 1
         fn(); torch.cuda.synchronize()
         ts = []
         for _ in range(iters):

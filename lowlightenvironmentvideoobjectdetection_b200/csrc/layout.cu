@@ -46,16 +46,15 @@ nchw_to_nhwc_kernel(const float *__restrict__ in, float *__restrict__ out, float
         if (dst)
             for (int c = lane; c < C; c += 32) dst[c] = slab[p * ld + c];
         if (unit) {
-            const float nrm = s_nrm[p];  // x / ||x|| (true division, as the reference)
+            const float rinv = 1.0f / s_nrm[p];  // x * (1/||x||): per-element IEEE division is slow on exact zeros
             __nv_bfloat16 *u = unit + ((size_t)b * HW + p0 + p) * C;
             if ((C & 1) == 0) {
                 for (int c = 2 * lane; c < C; c += 64) {
-                    __nv_bfloat162 h = __floats2bfloat162_rn(__fdiv_rn(slab[p * ld + c], nrm),
-                                                             __fdiv_rn(slab[p * ld + c + 1], nrm));
+                    __nv_bfloat162 h = __floats2bfloat162_rn(slab[p * ld + c] * rinv, slab[p * ld + c + 1] * rinv);
                     *reinterpret_cast<__nv_bfloat162 *>(u + c) = h;
                 }
             } else {
-                for (int c = lane; c < C; c += 32) u[c] = __float2bfloat16_rn(__fdiv_rn(slab[p * ld + c], nrm));
+                for (int c = lane; c < C; c += 32) u[c] = __float2bfloat16_rn(slab[p * ld + c] * rinv);
             }
         }
     }
@@ -76,7 +75,8 @@ rows_l2norm_kernel(const float *__restrict__ rows, float *__restrict__ norm_out,
     if (lane == 0 && norm_out) norm_out[r] = nrm;
     if (unit) {
         __nv_bfloat16 *u = unit + (size_t)r * C;
-        for (int c = lane; c < C; c += 32) u[c] = __float2bfloat16_rn(__fdiv_rn(__ldg(src + c), nrm));
+        const float rinv = 1.0f / nrm;
+        for (int c = lane; c < C; c += 32) u[c] = __float2bfloat16_rn(__ldg(src + c) * rinv);
     }
 }
 

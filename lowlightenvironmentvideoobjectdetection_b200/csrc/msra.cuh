@@ -5,7 +5,7 @@
 namespace vod {
 
 constexpr int kMsraMaxK = 4;      // num_most_similar_points <= 4 (reference default 2)
-constexpr int kMsraCand = 8;      // candidates per (row, frame) kept by the tensor-core pass (2 column halves x top-4)
+constexpr int kMsraCand = 16;     // candidates per (row, frame) kept by the tensor-core pass (4 column groups x top-4)
 // A candidate is re-scored in fp32 when its bf16-GEMM similarity is within this margin of the 2nd best one.
 // bf16 operand rounding gives an error of ~1e-4 (sigma) on unit vectors, the 20-bit key truncation < 3.5e-4.
 constexpr float kMsraMargin = 2.5e-3f;

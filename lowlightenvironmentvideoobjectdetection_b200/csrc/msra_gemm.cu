@@ -8,16 +8,16 @@
 // candidates are then re-scored in exact fp32 (msra_rescore_kernel, tafa.cu) so that the selected
 // locations match the fp32 reference; the bf16 GEMM is only a pre-filter.
 //
-// Persistent kernel, one CTA per SM, 320 threads; a work unit = (128-row tile, frame t):
-//   warp 8   TMA producer: the A tile (128 rows x C, K-major bf16, 128B swizzle) stays resident in shared
+// Persistent kernel, one CTA per SM, 576 threads; a work unit = (128-row tile, frame t):
+//   warp 16  TMA producer: the A tile (128 rows x C, K-major bf16, 128B swizzle) stays resident in shared
 //            memory while the unit's B tiles (128 locations x 64 channels per stage) stream through a ring
-//   warp 9   MMA issuer: tcgen05.mma kind::f16 (bf16 in, fp32 accumulate), 128x128 accumulator,
+//   warp 17  MMA issuer: tcgen05.mma kind::f16 (bf16 in, fp32 accumulate), 128x128 accumulator,
 //            double buffered in TMEM (2 x 128 columns)
-//   warps 0-7 epilogue: thread = row (two warps per TMEM lane quarter, each owning 64 of the tile's 128
-//            columns); every similarity is packed with its location into one order-preserving 32-bit key
+//   warps 0-15 epilogue: thread = row (four warps per TMEM lane quarter, each owning 32 of the tile's 128
+//            columns, so every SM sub-partition always has 4 epilogue warps to interleave); every similarity is packed with its location into one order-preserving 32-bit key
 //            (20 value bits | 12 location bits) and pushed through a branch-free min/max insertion network
 //            that keeps the 4 largest keys in registers -- no divergence although the 32 lanes of a warp
-//            follow 32 different rows; one 16-byte store per (row, frame, column half) at the end
+//            follow 32 different rows; one 16-byte store per (row, frame, column group) at the end
 // Units are assigned to CTAs in contiguous ranges so the A tile is reloaded only when the row tile changes.
 #include <cuda_bf16.h>
 
@@ -33,8 +33,8 @@ constexpr int kMgSlice = 64;         // bf16 elements per 128-byte K slice
 constexpr int kMgMaxSlices = 8;      // C <= 512
 constexpr int kMgStages = 5;
 constexpr int kMgTile = 128 * 128;   // bytes of one [128 x 128 B] slice tile
-constexpr int kMgThreads = 320;
-constexpr int kMgEpiWarps = 8;
+constexpr int kMgEpiWarps = 16;
+constexpr int kMgThreads = (kMgEpiWarps + 2) * 32;
 constexpr int kMgSmem = kMgMaxSlices * kMgTile + kMgStages * kMgTile + 1024;
 
 struct MgParams {
@@ -66,13 +66,13 @@ msra_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], kMgEpiWarps * 32); }
         tc::fence_barrier_init();
     }
-    if (warp == 9) tc::tmem_alloc(&tmem_slot, 256);
+    if (warp == kMgEpiWarps + 1) tc::tmem_alloc(&tmem_slot, 256);
     tc::tcgen05_fence_before();
     __syncthreads();
     tc::tcgen05_fence_after();
     const uint32_t tmem = tmem_slot;
 
-    if (warp == 8) {
+    if (warp == kMgEpiWarps) {
         // ------------------------------------------------------------------ TMA producer
         if (tc::elect_one()) {
             tc::tma_prefetch_desc(&tm_a); tc::tma_prefetch_desc(&tm_b);
@@ -100,7 +100,7 @@ msra_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
                 }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == kMgEpiWarps + 1) {
         // ------------------------------------------------------------------ MMA issuer
         constexpr uint32_t idesc = tc::umma_idesc(tc::kFmtBF16, kMgBM, kMgBN);
         int cur_rt = -1, a_loads = 0;
@@ -139,8 +139,8 @@ msra_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         }
     } else {
         // ------------------------------------------------------------------ epilogue: running top-4 keys per row
-        const int quarter = warp & 3, half = warp >> 2;
-        const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16) + half * 64;
+        const int quarter = warp & 3, grp = warp >> 2;   // TMEM lane quarter, 32-column group of the tile
+        const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16) + grp * 32;
         long tile_it = 0;
         for (int u = u0; u < u1; ++u) {
             const int rt = u / p.T, t = u % p.T;
@@ -149,13 +149,12 @@ msra_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
                 const int buf = (int)(tile_it & 1);
                 tc::mbar_wait(&acc_full[buf], (uint32_t)((tile_it >> 1) & 1));
                 tc::tcgen05_fence_after();
-                uint32_t ra[32], rb[32];
+                uint32_t ra[32];
                 tc::tmem_ld_32x32(tl + buf * kMgBN, ra);
-                tc::tmem_ld_32x32(tl + buf * kMgBN + 32, rb);
                 tc::tmem_ld_wait();
                 tc::tcgen05_fence_before();
                 tc::mbar_arrive(&acc_empty[buf]);       // values are in registers: the MMA may overwrite the buffer
-                const uint32_t base = (uint32_t)(nt * kMgBN + half * 64);
+                const uint32_t base = (uint32_t)(nt * kMgBN + grp * 32);
                 const int nvalid = p.HW - (int)base;    // columns of this frame that exist (tail tile only)
                 auto push = [&](uint32_t bits, uint32_t loc, bool ok) {
                     // order-preserving float -> uint, top 20 bits kept, location in the low 12 bits
@@ -167,26 +166,22 @@ msra_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
                     hi = max(k2, key); key = min(k2, key); k2 = hi;
                     k3 = max(k3, key);
                 };
-                if (nvalid >= 64) {
+                if (nvalid >= 32) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) push(ra[j], base + j, true);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) push(rb[j], base + 32 + j, true);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) push(ra[j], base + j, j < nvalid);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) push(rb[j], base + 32 + j, 32 + j < nvalid);
                 }
             }
             const int row = rt * kMgBM + quarter * 32 + lane;
             if (row < p.NP)
-                *reinterpret_cast<uint4 *>(p.cand + ((size_t)row * p.T + t) * kMsraCand + half * 4) = make_uint4(k0, k1, k2, k3);
+                *reinterpret_cast<uint4 *>(p.cand + ((size_t)row * p.T + t) * kMsraCand + grp * 4) = make_uint4(k0, k1, k2, k3);
         }
     }
     tc::tcgen05_fence_before();
     __syncthreads();
-    if (warp == 9) tc::tmem_dealloc(tmem, 256);
+    if (warp == kMgEpiWarps + 1) tc::tmem_dealloc(tmem, 256);
 }
 
 bool msra_gemm_supported(int NP, int C, int T, int HW) {

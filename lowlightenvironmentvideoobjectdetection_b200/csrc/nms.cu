@@ -67,19 +67,33 @@ nms_rank_kernel(const float *__restrict__ boxes, const float *__restrict__ score
     if (blockIdx.x * kRankThreads >= n) return;
     const float si = i < n ? scores[beg + i] : 0.f;
 
-    __shared__ float sj[kRankThreads];
+    __shared__ __align__(16) float sj[kRankThreads];
     const int per = ceil_div(n, (int)gridDim.y);
     const int j0 = blockIdx.y * per, j1 = min(n, j0 + per);
     int cnt = 0;
+    const int i_lo = blockIdx.x * kRankThreads, i_hi = i_lo + kRankThreads - 1;
     for (int base = j0; base < j1; base += kRankThreads) {
         int j = base + threadIdx.x;
-        sj[threadIdx.x] = j < j1 ? scores[beg + j] : 0.f;
+        sj[threadIdx.x] = j < j1 ? scores[beg + j] : -INFINITY;
         __syncthreads();
-        int lim = min(kRankThreads, j1 - base);
-#pragma unroll 8
-        for (int t = 0; t < lim; ++t) {
-            float s = sj[t];
-            cnt += (s > si) || (s == si && (base + t) < i);
+        const int lim = min(kRankThreads, j1 - base);
+        // rank = #{s_j > s_i} + #{s_j == s_i, j < i}: for a tile entirely before (after) this block's rows the
+        // tie term is constant, so the inner loop is a single compare
+        if (base + lim - 1 < i_lo) {
+            for (int t = 0; t < lim; t += 4) {
+                const float4 s4 = *reinterpret_cast<const float4 *>(&sj[t]);   // padded with -inf
+                cnt += (s4.x >= si) + (s4.y >= si) + (s4.z >= si) + (s4.w >= si);
+            }
+        } else if (base > i_hi) {
+            for (int t = 0; t < lim; t += 4) {
+                const float4 s4 = *reinterpret_cast<const float4 *>(&sj[t]);
+                cnt += (s4.x > si) + (s4.y > si) + (s4.z > si) + (s4.w > si);
+            }
+        } else {
+            for (int t = 0; t < lim; ++t) {
+                const float s = sj[t];
+                cnt += (s > si) || (s == si && (base + t) < i);
+            }
         }
         __syncthreads();
     }
@@ -125,6 +139,9 @@ __device__ __forceinline__ bool iou_gt(const float4 &a, float area_a, const floa
     float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
     float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
     float inter = __fmul_rn(w, h);
+    // disjoint boxes: inter == 0 -> IoU is 0 (or 0/0 = NaN), never > thr; skipping the IEEE division here
+    // avoids its slow path (zero numerator) for the vast majority of pairs without changing any result
+    if (!(inter > 0.f)) return false;
     float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
     return ovr > thr;
 }

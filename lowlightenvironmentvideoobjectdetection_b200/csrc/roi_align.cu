@@ -79,7 +79,7 @@ template <> struct Vec<1> {
 
 // JC = bin-columns accumulated in registers at once.
 template <int VEC, int JC>
-__global__ void __launch_bounds__(kRoiWarps * 32)
+__global__ void __launch_bounds__(kRoiWarps * 32, 5)
 roi_align_kernel(const float *__restrict__ feat, const float *__restrict__ rois, float *__restrict__ out,
                  int B, int C, int H, int W, int K, int ph, int pw, float spatial_scale,
                  int sampling_ratio, int aligned, int out_layout) {
@@ -119,47 +119,41 @@ roi_align_kernel(const float *__restrict__ feat, const float *__restrict__ rois,
 
     for (int i = warp; i < ph; i += kRoiWarps) {
         const int ny = ty.cnt[i];
-        for (int j0 = 0; j0 < pw; j0 += JC) {
-            Vec<VEC> acc[JC];
-#pragma unroll
-            for (int j = 0; j < JC; ++j) acc[j].zero();
+        for (int j = 0; j < pw; ++j) {
+            Vec<VEC> acc;
+            acc.zero();
+            const int nx = tx.cnt[j];
             if (active) {
-                for (int e = 0; e < ny; ++e) {
-                    const float wy = ty.w[i][e];
-                    const float *rowp = fb + (size_t)ty.idx[i][e] * W * C;
+                for (int x0 = 0; x0 < nx; x0 += 4) {
+                    // this bin-column's (column offset, weight) entries live in registers across the row loop
+                    const int nq = min(4, nx - x0);   // warp-uniform
+                    int xo[4];
+                    float xw[4];
 #pragma unroll
-                    for (int j = 0; j < JC; ++j) {
-                        if (j0 + j < pw) {
-                            const int nx = tx.cnt[j0 + j];
-                            for (int x0 = 0; x0 < nx; x0 += 4) {
-                                Vec<VEC> v[4];
-                                float wx[4];
+                    for (int q = 0; q < 4; ++q) {
+                        xo[q] = q < nq ? tx.idx[j][x0 + q] * C : 0;
+                        xw[q] = q < nq ? tx.w[j][x0 + q] : 0.f;
+                    }
+#pragma unroll 2
+                    for (int e = 0; e < ny; ++e) {
+                        const float wy = ty.w[i][e];
+                        const float *rowp = fb + (size_t)ty.idx[i][e] * W * C;
+                        Vec<VEC> v[4];
 #pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    const bool on = x0 + q < nx;  // warp-uniform
-                                    wx[q] = on ? tx.w[j0 + j][x0 + q] * wy : 0.f;
-                                    if (on) v[q].load(rowp + (size_t)tx.idx[j0 + j][x0 + q] * C);
-                                    else v[q].zero();
-                                }
+                        for (int q = 0; q < 4; ++q)
+                            if (q < nq) v[q].load(rowp + xo[q]);
 #pragma unroll
-                                for (int q = 0; q < 4; ++q) acc[j].fma(wx[q], v[q]);
-                            }
-                        }
+                        for (int q = 0; q < 4; ++q)
+                            if (q < nq) acc.fma(xw[q] * wy, v[q]);
                     }
                 }
             }
-            // emit
+            const int bin = i * pw + j;
+            if (out_layout == 0) {
 #pragma unroll
-            for (int j = 0; j < JC; ++j) {
-                if (j0 + j < pw) {
-                    const int bin = i * pw + j0 + j;
-                    if (out_layout == 0) {
-#pragma unroll
-                        for (int q = 0; q < VEC; ++q) tile[(cl + q) * P + bin] = acc[j].get(q);
-                    } else if (active) {
-                        acc[j].store(out + ((size_t)k * P + bin) * C + c0 + cl);
-                    }
-                }
+                for (int q = 0; q < VEC; ++q) tile[(cl + q) * P + bin] = acc.get(q);
+            } else if (active) {
+                acc.store(out + ((size_t)k * P + bin) * C + c0 + cl);
             }
         }
     }
@@ -184,8 +178,9 @@ static int launch_roi(const float *feat, const float *rois, float *out, int B, i
     size_t smem = out_layout == 0 ? sizeof(float) * CS * ph * pw : 0;
     auto kern = roi_align_kernel<VEC, JC>;
     if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    // keep roughly half of the 228 KB for L1: adjacent bins of a small RoI re-touch the same pixels
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+    // occupancy (6 CTAs = 42 warps per SM) matters more than L1 capacity here: the per-axis weight merge
+    // already removed most duplicate taps, the rest is served by the 126 MB L2
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     dim3 grid(K, ceil_div(C, CS));
     kern<<<grid, kRoiWarps * 32, smem, st>>>(feat, rois, out, B, C, H, W, K, ph, pw, scale, sr, aligned,
                                              out_layout); note_launch();

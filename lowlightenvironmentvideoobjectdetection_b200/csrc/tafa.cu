@@ -35,29 +35,47 @@ tafa_kernel(const float *__restrict__ x_all, const float *__restrict__ emb_all, 
         float *w = s_w[warp];
         if (use_attn) {
             // logits_t = <emb[t] + b, emb[0] + b>_head * scale   (b = the embed conv's bias, folded in here so
-            // the conv can run bias-free and the [T1,N,P,C] embedding is not rewritten by a bias-add pass)
-            for (int t = 0; t < T1; ++t) {
-                float d = 0.f;
+            // the conv can run bias-free and the [T1,N,P,C] embedding is not rewritten by a bias-add pass).
+            // Frames are processed 8 at a time: all loads of a batch are issued before the first reduction.
+            constexpr int TB = 8;
+            for (int t0 = 0; t0 < T1; t0 += TB) {
+                float d[TB];
+#pragma unroll
+                for (int u = 0; u < TB; ++u) d[u] = 0.f;
                 for (int ch = 0; ch < nch; ++ch) {
                     if (ch * CH + lane * VEC < hs_eff) {
                         if (VEC == 4) {
                             float4 a = ldg_f4(emb_all + base + ch * CH);
-                            float4 b = ldg_f4(emb_all + (size_t)t * frame_stride + base + ch * CH);
-                            if (emb_bias) {
-                                const float4 bb = ldg_f4(emb_bias + c_head + lane * VEC + ch * CH);
-                                a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
-                                b.x += bb.x; b.y += bb.y; b.z += bb.z; b.w += bb.w;
+                            float4 b[TB];
+#pragma unroll
+                            for (int u = 0; u < TB; ++u)
+                                b[u] = (t0 + u < T1) ? ldg_f4(emb_all + (size_t)(t0 + u) * frame_stride + base + ch * CH)
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (emb_bias) bb = ldg_f4(emb_bias + c_head + lane * VEC + ch * CH);
+                            a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+#pragma unroll
+                            for (int u = 0; u < TB; ++u) {
+                                d[u] = fmaf(a.x, b[u].x + bb.x, d[u]); d[u] = fmaf(a.y, b[u].y + bb.y, d[u]);
+                                d[u] = fmaf(a.z, b[u].z + bb.z, d[u]); d[u] = fmaf(a.w, b[u].w + bb.w, d[u]);
                             }
-                            d = fmaf(a.x, b.x, d); d = fmaf(a.y, b.y, d); d = fmaf(a.z, b.z, d); d = fmaf(a.w, b.w, d);
                         } else {
-                            float a = __ldg(emb_all + base + ch * CH), b = __ldg(emb_all + (size_t)t * frame_stride + base + ch * CH);
-                            if (emb_bias) { const float bb = __ldg(emb_bias + c_head + lane + ch * CH); a += bb; b += bb; }
-                            d = fmaf(a, b, d);
+                            float a = __ldg(emb_all + base + ch * CH);
+                            const float bb = emb_bias ? __ldg(emb_bias + c_head + lane + ch * CH) : 0.f;
+                            a += bb;
+#pragma unroll
+                            for (int u = 0; u < TB; ++u)
+                                if (t0 + u < T1)
+                                    d[u] = fmaf(a, __ldg(emb_all + (size_t)(t0 + u) * frame_stride + base + ch * CH) + bb, d[u]);
                         }
                     }
                 }
-                d = warp_sum(d);
-                if (lane == 0) w[t] = d * scale;
+#pragma unroll
+                for (int u = 0; u < TB; ++u) d[u] = warp_sum(d[u]);
+                if (lane == 0) {
+#pragma unroll
+                    for (int u = 0; u < TB; ++u) if (t0 + u < T1) w[t0 + u] = d[u] * scale;
+                }
             }
             __syncwarp();
             float m = -INFINITY;
@@ -76,15 +94,26 @@ tafa_kernel(const float *__restrict__ x_all, const float *__restrict__ emb_all, 
 #pragma unroll
             for (int q = 0; q < VEC; ++q) acc[q] = 0.f;
             if (on) {
-#pragma unroll 4
-                for (int t = 0; t < T1; ++t) {
-                    const float wt = use_attn ? w[t] : uniform;
+                constexpr int TB2 = 8;
+                for (int t0 = 0; t0 < T1; t0 += TB2) {
                     if (VEC == 4) {
-                        float4 v = ldg_f4(x_all + (size_t)t * frame_stride + base + ch * CH);
-                        acc[0] = fmaf(wt, v.x, acc[0]); acc[1 % VEC] = fmaf(wt, v.y, acc[1 % VEC]);
-                        acc[2 % VEC] = fmaf(wt, v.z, acc[2 % VEC]); acc[3 % VEC] = fmaf(wt, v.w, acc[3 % VEC]);
+                        float4 v[TB2];
+#pragma unroll
+                        for (int u = 0; u < TB2; ++u)
+                            v[u] = (t0 + u < T1) ? ldg_f4(x_all + (size_t)(t0 + u) * frame_stride + base + ch * CH)
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int u = 0; u < TB2; ++u) {
+                            const float wt = (t0 + u < T1) ? (use_attn ? w[t0 + u] : uniform) : 0.f;
+                            acc[0] = fmaf(wt, v[u].x, acc[0]); acc[1 % VEC] = fmaf(wt, v[u].y, acc[1 % VEC]);
+                            acc[2 % VEC] = fmaf(wt, v[u].z, acc[2 % VEC]); acc[3 % VEC] = fmaf(wt, v[u].w, acc[3 % VEC]);
+                        }
                     } else {
-                        acc[0] = fmaf(wt, __ldg(x_all + (size_t)t * frame_stride + base + ch * CH), acc[0]);
+#pragma unroll
+                        for (int u = 0; u < TB2; ++u)
+                            if (t0 + u < T1)
+                                acc[0] = fmaf(use_attn ? w[t0 + u] : uniform,
+                                              __ldg(x_all + (size_t)(t0 + u) * frame_stride + base + ch * CH), acc[0]);
                     }
                 }
                 if (out_layout == 0) {
@@ -240,10 +269,10 @@ msra_scan_kernel(const float *__restrict__ roi, const float *__restrict__ ref, c
 }
 
 // Tail of the tensor-core path.  warp = one RoI row (all T frames): the row is normalised once; for every
-// frame the 8 packed candidate keys of msra_gemm_topk_kernel are decoded, candidates whose bf16-GEMM
+// frame the 16 packed candidate keys of msra_gemm_topk_kernel are decoded, candidates whose bf16-GEMM
 // similarity lies within kMsraMargin of the 2nd best are re-scored in exact fp32
 //   sim = sum_c (roi[c] / |roi|) * (ref[c] / |ref|)      (temporal_roi_align.py:127-142)
-// and the exact top-k feeds the softmax + gather.  Typically 2-3 of the 8 candidates are re-scored.
+// and the exact top-k feeds the softmax + gather.  Typically 2-3 of the 16 candidates are re-scored.
 __global__ void __launch_bounds__(kScanWarps * 32)
 msra_rescore_kernel(const float *__restrict__ roi, const float *__restrict__ ref, const float *__restrict__ roi_norm,
                     const float *__restrict__ ref_norm, const uint32_t *__restrict__ cand, int KC,
@@ -254,8 +283,11 @@ msra_rescore_kernel(const float *__restrict__ roi, const float *__restrict__ ref
     const int row = blockIdx.x * kScanWarps + warp;
     if (row >= NP) return;
     float *q = s_roi + (size_t)warp * C;
-    const float qn = roi_norm[row];
-    for (int c = lane; c < C; c += 32) q[c] = __fdiv_rn(__ldg(roi + (size_t)row * C + c), qn);
+    // x * (1/|x|) instead of x / |x|: an IEEE division per element takes the slow path whenever a lane holds an
+    // exact zero (half of all post-ReLU features); the two differ by <= 1 ulp per element, far below the
+    // spacing of neighbouring similarities.
+    const float qinv = 1.0f / roi_norm[row];
+    for (int c = lane; c < C; c += 32) q[c] = __ldg(roi + (size_t)row * C + c) * qinv;
     __syncwarp();
     for (int t = 0; t < T; ++t) {
         const float *ref_t = ref + (size_t)t * HW * C;
@@ -289,17 +321,18 @@ msra_rescore_kernel(const float *__restrict__ roi, const float *__restrict__ ref
             todo &= todo - 1;
             const int l = (int)(__shfl_sync(0xffffffffu, key, j) & 0xFFFu);
             if (l >= HW) continue;
-            const float rn = ref_norm[(size_t)t * HW + l];
+            const float rinv = 1.0f / ref_norm[(size_t)t * HW + l];
             const float *r = ref_t + (size_t)l * C;
             float s = 0.f;
             if ((C & 3) == 0) {
                 for (int c = lane * 4; c < C; c += 128) {
-                    float4 v = ldg_f4(r + c);
-                    s = fmaf(q[c], __fdiv_rn(v.x, rn), s); s = fmaf(q[c + 1], __fdiv_rn(v.y, rn), s);
-                    s = fmaf(q[c + 2], __fdiv_rn(v.z, rn), s); s = fmaf(q[c + 3], __fdiv_rn(v.w, rn), s);
+                    const float4 v = ldg_f4(r + c);
+                    const float4 qq = *reinterpret_cast<const float4 *>(q + c);
+                    s = fmaf(qq.x, v.x * rinv, s); s = fmaf(qq.y, v.y * rinv, s);
+                    s = fmaf(qq.z, v.z * rinv, s); s = fmaf(qq.w, v.w * rinv, s);
                 }
             } else {
-                for (int c = lane; c < C; c += 32) s = fmaf(q[c], __fdiv_rn(__ldg(r + c), rn), s);
+                for (int c = lane; c < C; c += 32) s = fmaf(q[c], __ldg(r + c) * rinv, s);
             }
             s = warp_sum(s);
             if (s != s) any_nan = true;            // torch.topk ranks NaN first: the reference row becomes NaN

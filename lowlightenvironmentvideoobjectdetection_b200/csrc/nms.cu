@@ -12,7 +12,7 @@
 //   4. nms_sweep_kernel    greedy sweep: one CTA per image, 64-box blocks resolved by a warp in
 //                          registers, kept rows OR-ed into a shared-memory "removed" bitmap
 // IoU arithmetic uses __fmul_rn/__fadd_rn/__fdiv_rn so nothing is contracted into an FMA: kept
-// indices are bit-exact against an un-contracted CPU evaluation (oracle/vod_oracle.c).
+// indices are bit-exact against an un-contracted CPU evaluation of the same formula.
 #include "common.cuh"
 
 namespace vod {

@@ -1,0 +1,135 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every symbol include/vodagg.h
+declares, the registries / module signatures / parameter names mirror the reference, the reference's own
+assertion behaviour is kept, the product path refuses to run without CUDA (no fallback) and never imports
+the oracle."""
+import ctypes
+import inspect
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import lowlightenvironmentvideoobjectdetection_b200 as vod
+from lowlightenvironmentvideoobjectdetection_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, 'include', 'vodagg.h')).read()
+    declared = set(re.findall(r'\b(vod_[a-z0-9_]+)\s*\(', header))
+    declared.discard('vod_stream_t')
+    assert len(declared) >= 17
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), 'libvodagg.so does not export %s' % name
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    assert _lib.load().vod_version() >= 100
+    assert _lib.load().vod_device_is_sm100() in (0, 1)   # no compute call without a GPU
+
+
+def test_sass_is_blackwell_native():
+    """The shipped cubin carries tcgen05 MMAs (UTC*MMA), TMEM loads (LDTM) and TMA loads (UTMALDG)."""
+    r = subprocess.run(['cuobjdump', '-sass', _lib.LIB_PATH], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip('cuobjdump unavailable')
+    assert 'sm_100a' in r.stdout
+    for mnemonic in ('UTCHMMA', 'LDTM', 'UTMALDG'):
+        assert mnemonic in r.stdout, mnemonic
+
+
+def test_registries_and_signatures():
+    assert set(vod.AGGREGATORS.module_dict) >= {'SelsaAggregator', 'EmbedAggregator'}
+    assert set(vod.ROI_EXTRACTORS.module_dict) >= {'SingleRoIExtractor', 'TemporalRoIAlign'}
+    m = vod.build_aggregator(dict(type='SelsaAggregator', in_channels=32, num_attention_blocks=4))
+    assert list(m.state_dict()) == ['fc_embed.weight', 'fc_embed.bias', 'ref_fc_embed.weight', 'ref_fc_embed.bias',
+                                    'fc.weight', 'fc.bias', 'ref_fc.weight', 'ref_fc.bias']
+    assert list(inspect.signature(vod.SelsaAggregator.__init__).parameters) == ['self', 'in_channels', 'num_attention_blocks']
+    e = vod.build_aggregator(dict(type='EmbedAggregator', num_convs=2, channels=8, kernel_size=3))
+    assert list(e.state_dict()) == ['embed_convs.0.conv.weight', 'embed_convs.0.conv.bias',
+                                    'embed_convs.1.conv.weight', 'embed_convs.1.conv.bias']
+    assert list(inspect.signature(vod.EmbedAggregator.__init__).parameters) == \
+        ['self', 'num_convs', 'channels', 'kernel_size', 'norm_cfg', 'act_cfg']
+    t = vod.build_roi_extractor(dict(type='TemporalRoIAlign', num_most_similar_points=2, num_temporal_attention_blocks=4,
+                                     roi_layer=dict(type='RoIAlign', output_size=7, sampling_ratio=2),
+                                     out_channels=16, featmap_strides=[16]))
+    assert list(t.state_dict()) == ['embed_network.conv.weight', 'embed_network.conv.bias']
+    assert t.roi_layers[0].output_size == (7, 7) and abs(t.roi_layers[0].spatial_scale - 1 / 16) < 1e-12
+    assert t.num_inputs == 1
+    assert list(inspect.signature(vod.TemporalRoIAlign.forward).parameters) == ['self', 'feats', 'rois', 'roi_scale_factor', 'ref_feats']
+    assert list(inspect.signature(vod.flow_warp_feats).parameters) == ['x', 'flow']
+    assert list(inspect.signature(vod.batched_nms).parameters) == ['boxes', 'scores', 'idxs', 'nms_cfg', 'class_agnostic']
+    assert list(inspect.signature(vod.RoIAlign.__init__).parameters) == \
+        ['self', 'output_size', 'spatial_scale', 'sampling_ratio', 'pool_mode', 'aligned', 'use_torchvision']
+    with pytest.raises(KeyError):
+        vod.build_aggregator(dict(type='NoSuchAggregator'))
+    with pytest.raises(KeyError):
+        vod.AGGREGATORS.register_module()(vod.SelsaAggregator)     # duplicate without force
+    vod.AGGREGATORS.register_module(force=True)(vod.SelsaAggregator)
+
+
+def test_reference_assertions_are_kept():
+    """mmtracking/tests/test_models/test_aggregators.py:9-20 and tests/test_core/test_motion_utils.py:13-29."""
+    with pytest.raises(AssertionError):
+        vod.EmbedAggregator(num_convs=0, channels=32, kernel_size=3)
+    model = vod.EmbedAggregator(num_convs=3, channels=32, kernel_size=3)
+    with pytest.raises(AssertionError):
+        model(torch.randn(2, 32, 8, 8), torch.randn(4, 32, 8, 8))
+    with pytest.raises(AssertionError):
+        vod.flow_warp_feats(torch.randn(2, 8, 32, 32, 32), torch.randn(2, 2, 10, 10))
+    with pytest.raises(AssertionError):
+        vod.flow_warp_feats(torch.randn(2, 8, 32, 32), torch.randn(2, 2, 10, 10, 10))
+    with pytest.raises(AssertionError):
+        vod.flow_warp_feats(torch.randn(2, 8, 32, 32), torch.randn(2, 3, 10, 10))
+
+
+def test_no_cpu_fallback():
+    """The product path fails loudly on CPU tensors instead of silently computing somewhere else."""
+    with pytest.raises(_lib.VodError):
+        vod.flow_warp_feats(torch.randn(2, 8, 32, 32), torch.randn(2, 2, 10, 10))
+    with pytest.raises(_lib.VodError):
+        vod.SelsaAggregator(16, 4)(torch.randn(2, 16), torch.randn(4, 16))
+    with pytest.raises(_lib.VodError):
+        vod.batched_nms(torch.rand(4, 4), torch.rand(4), torch.zeros(4, dtype=torch.long), dict(type='nms', iou_threshold=0.5))
+    with pytest.raises(_lib.VodError):
+        vod.RoIAlign(7, 1 / 16, 2)(torch.randn(1, 4, 8, 8), torch.tensor([[0, 0., 0., 32., 32.]]))
+
+
+def test_missing_library_is_loud(tmp_path, monkeypatch):
+    monkeypatch.setattr(_lib, '_lib', None)
+    monkeypatch.setattr(_lib, 'LIB_PATH', str(tmp_path / 'libvodagg.so'))
+    with pytest.raises(_lib.VodError, match='no CPU / PyTorch fallback'):
+        _lib.load()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'lowlightenvironmentvideoobjectdetection_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', src, re.M), f
+                assert 'vod_oracle' not in src and 'ref_shim' not in src, f
+    code = 'import sys; import lowlightenvironmentvideoobjectdetection_b200; assert not any(m.startswith("oracle") for m in sys.modules)'
+    subprocess.run([sys.executable, '-c', code], check=True, cwd=ROOT)
+
+
+def test_host_glue_matches_oracle_on_cpu():
+    """delta2bbox / bbox2roi are plain torch (callers of the hot path): check them against the oracle's restatement."""
+    from oracle import vod_oracle as O
+    g = torch.Generator().manual_seed(1)
+    rois = torch.rand(50, 4, generator=g) * 300
+    rois[:, 2:] += rois[:, :2]
+    deltas = torch.randn(50, 120, generator=g)
+    a = vod.delta2bbox(rois, deltas, (0., 0., 0., 0.), (0.2, 0.2, 0.2, 0.2), max_shape=(600, 1000, 3))
+    b = O.delta2bbox(rois, deltas, (0., 0., 0., 0.), (0.2, 0.2, 0.2, 0.2), max_shape=(600, 1000, 3))
+    assert torch.equal(a, b)
+    lst = [torch.rand(7, 4, generator=g) for _ in range(3)]
+    r = vod.bbox2roi(lst)
+    assert r.shape == (21, 5) and torch.equal(r[:, 0], torch.arange(3.).repeat_interleave(7))
+    assert torch.equal(r[:, 1:], torch.cat(lst, 0))
+    r2 = vod.bbox2roi([torch.rand(3, 4), torch.zeros(0, 4), torch.rand(2, 4)])
+    assert r2.shape == (5, 5) and r2[:, 0].tolist() == [0, 0, 0, 2, 2]

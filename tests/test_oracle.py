@@ -1,0 +1,103 @@
+"""CPU tests of the oracle itself: pinned against the golden vectors produced by the reference's own
+unmodified files (tests/golden/make_golden.py), against torchvision (the executable stand-in for
+mmcv-full's ops) and, when /root/reference is present (build container), against the reference live."""
+import pytest
+import torch
+
+from oracle import ref_shim
+from oracle import vod_oracle as O
+
+from conftest import params, rel_err
+from helpers import clustered_boxes, rpn_like_rois
+
+
+def test_selsa_matches_golden(golden):
+    for pre, heads in (('selsa', 16), ('selsa64', 2)):
+        out = O.selsa_aggregate(golden[pre + '_x'], golden[pre + '_ref_x'], params(golden, pre + '_p.'), heads)
+        assert rel_err(out, golden[pre + '_out']) < 1e-5
+
+
+def test_flow_warp_matches_golden(golden):
+    for p in ('warp', 'warp2'):
+        out = O.flow_warp_feats(golden[p + '_x'], golden[p + '_flow'])
+        # closed form vs ATen's normalise/un-normalise round trip: ~1e-5 abs on N(0,1) features
+        assert (out - golden[p + '_out']).abs().max() < 1e-4
+
+
+def test_embed_aggregator_matches_golden(golden):
+    p = params(golden, 'embed_p.')
+    convs = [(p['embed_convs.0.conv.weight'], p['embed_convs.0.conv.bias'], True),
+             (p['embed_convs.1.conv.weight'], p['embed_convs.1.conv.bias'], False)]
+    out = O.embed_aggregate(golden['embed_x'], golden['embed_ref_x'], convs)
+    assert rel_err(out, golden['embed_out']) < 1e-5
+
+
+def test_roi_align_and_troi_match_golden(golden):
+    ra = O.roi_align(golden['troi_feat'], golden['troi_rois'], 7, 1 / 16, 2, True)
+    assert rel_err(ra, golden['roialign_out']) < 1e-6
+    msra = O.most_similar_roi_align(ra, golden['troi_ref'], 2)
+    assert rel_err(msra, golden['msra_out']) < 1e-5
+    p = params(golden, 'troi_p.')
+    out = O.temporal_roi_align(golden['troi_feat'], golden['troi_rois'], golden['troi_ref'],
+                               p['embed_network.conv.weight'], p['embed_network.conv.bias'], 2, 4)
+    assert rel_err(out, golden['troi_out']) < 1e-5
+    out0 = O.temporal_roi_align(golden['troi_feat'], golden['troi_rois'], golden['troi_ref'], None, None, 2, 0)
+    assert rel_err(out0, golden['troi_mean_out']) < 1e-5
+    assert rel_err(O.roi_align(golden['troi_ref'], golden['troi_ref_rois'], 7, 1 / 16, 2, True), golden['troi_ref_out']) < 1e-6
+
+
+def test_nms_matches_golden(golden):
+    b, s = golden['rpnnms_boxes'], golden['rpnnms_scores']
+    d, k = O.batched_nms(b, s, torch.zeros(len(b), dtype=torch.long), dict(type='nms', iou_threshold=0.7))
+    assert torch.equal(k, golden['rpnnms_keep']) and torch.equal(d, golden['rpnnms_dets'])
+    d, k = O.batched_nms(b, s, golden['bnms_ids'], dict(type='nms', iou_threshold=0.5))
+    assert torch.equal(k, golden['bnms_keep']) and torch.equal(d, golden['bnms_dets'])
+    d, k = O.batched_nms(b, s, golden['bnms_ids'], dict(type='nms', iou_threshold=0.5, split_thr=1000))
+    assert torch.equal(k, golden['bnms_split_keep']) and torch.equal(d, golden['bnms_split_dets'])
+    d, l, k = O.multiclass_nms(golden['mcnms_bboxes'], golden['mcnms_scores'], 0.05, dict(type='nms', iou_threshold=0.5),
+                               100, return_inds=True)
+    assert torch.equal(k, golden['mcnms_keep']) and torch.equal(l, golden['mcnms_labels'])
+    assert torch.equal(d, golden['mcnms_dets'])
+
+
+def test_c_oracle_vs_torchvision():
+    """mmcv-full's RoIAlign / nms are un-vendored; torchvision is the executable truth."""
+    tv = pytest.importorskip('torchvision')
+    g = torch.Generator().manual_seed(3)
+    feat = torch.randn(2, 24, 19, 31, generator=g)
+    rois = rpn_like_rois(g, 40, 2, 31 * 16., 19 * 16.)
+    rois[0, 1:] = torch.tensor([-50., -30., 20., 10.])
+    for aligned, sr, osz in ((True, 2, (7, 7)), (False, 2, (7, 7)), (True, 0, (5, 6))):
+        ref = tv.ops.roi_align(feat, rois, osz, 1 / 16, sr, aligned)
+        assert rel_err(O.roi_align(feat, rois, osz, 1 / 16, sr, aligned), ref) < 1e-6
+    boxes = clustered_boxes(g, 4000, 60)
+    scores = torch.rand(4000, generator=g)
+    for thr in (0.3, 0.5, 0.7):
+        assert torch.equal(O.nms(boxes, scores, thr)[1], tv.ops.nms(boxes, scores, thr))
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason='reference tree not present (GPU box)')
+def test_oracle_vs_live_reference():
+    R = ref_shim.load()
+    torch.manual_seed(0)
+    g = torch.Generator().manual_seed(9)
+    with torch.no_grad():
+        m = R.SelsaAggregator(256, 4)
+        x, r = torch.randn(33, 256, generator=g), torch.randn(120, 256, generator=g)
+        assert rel_err(O.selsa_aggregate(x, r, dict(m.state_dict()), 4), m(x, r)) < 1e-6
+        x, f = torch.randn(3, 16, 38, 63, generator=g), torch.randn(3, 2, 608, 1008, generator=g) * 8
+        assert (O.flow_warp_feats(x, f) - R.flow_warp_feats(x, f)).abs().max() < 1e-4
+        m = R.TemporalRoIAlign(2, 4, roi_layer=dict(type='RoIAlign', output_size=7, sampling_ratio=2), out_channels=32,
+                               featmap_strides=[16])
+        feat, ref = torch.relu(torch.randn(1, 32, 20, 30, generator=g)), torch.relu(torch.randn(4, 32, 20, 30, generator=g))
+        rois = rpn_like_rois(g, 12, 1, 480., 320.)
+        a = m((feat,), rois, ref_feats=(ref,))
+        b = O.temporal_roi_align(feat, rois, ref, m.embed_network.conv.weight, m.embed_network.conv.bias, 2, 4)
+        assert rel_err(b, a) < 1e-5
+        n = 5000
+        boxes, scores = clustered_boxes(g, n, 80), torch.rand(n, generator=g)
+        ids = torch.randint(0, 30, (n,), generator=g)
+        for cfg in (dict(type='nms', iou_threshold=0.5), dict(type='nms', iou_threshold=0.5, split_thr=3000)):
+            da, ka = R.batched_nms(boxes, scores, ids, cfg)
+            db, kb = O.batched_nms(boxes, scores, ids, cfg)
+            assert torch.equal(ka, kb) and torch.equal(da, db)

@@ -10,9 +10,10 @@
 //     per-axis sparse weight lists (<= 2g entries, duplicates merged) are built once per RoI in
 //     shared memory; a small RoI whose 14x14 sample points fall on a handful of pixels then loads
 //     each (row, col) once per bin-row instead of 16 taps per bin.
-//   * one CTA = (RoI, 128-channel slab); warp w owns bin-row w.  The [C_slab][P] output tile is
-//     staged in shared memory and written back as one contiguous, coalesced 128-bit stream in the
-//     reference's [K,C,ph,pw] layout (or written directly for the [K,P,C] layout).
+//   * one CTA = one RoI x up to 512 channels; warp w owns bin-row w and each lane accumulates 4 x 128-bit
+//     channel groups per tap, so the per-tap bookkeeping is paid once per 2 KB of features.  For the
+//     reference's [K,C,ph,pw] layout the [C][P] tile is staged in shared memory and written back as one
+//     contiguous, coalesced 128-bit stream; the [K,P,C] layout is written directly (no tile, no barrier).
 #include "common.cuh"
 
 namespace vod {
@@ -30,7 +31,7 @@ struct AxisTable {
 // Build the sparse weight list of one bin along one axis (start = roi start on this axis in
 // feature px, bin = bin size, g samples, size = H or W).  Arithmetic order follows the reference:
 //   y = start + i*bin + (iy + 0.5) * bin / g
-__device__ void build_axis(AxisTable &tab, int i, float start, float bin, int g, int size) {
+__device__ void build_axis(AxisTable &tab, int i, float start, float bin, int g, int size, int stride) {
     int cnt = 0;
     const float inv_g = 1.0f / (float)g;
     for (int s = 0; s < g; ++s) {
@@ -53,8 +54,11 @@ __device__ void build_axis(AxisTable &tab, int i, float start, float bin, int g,
             tab.w[i][e] += wv[q];
         }
     }
+    for (int e = 0; e < cnt; ++e) tab.idx[i][e] *= stride;   // pixel index -> element offset
     tab.cnt[i] = cnt;
 }
+
+__device__ __forceinline__ void prefetch_l1(const float *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 template <int VEC> struct Vec;
 template <> struct Vec<4> {
@@ -67,6 +71,7 @@ template <> struct Vec<4> {
     }
     __device__ __forceinline__ float get(int q) const { return q == 0 ? v.x : q == 1 ? v.y : q == 2 ? v.z : v.w; }
     __device__ __forceinline__ void store(float *p) const { *reinterpret_cast<float4 *>(p) = v; }
+    __device__ __forceinline__ void store_cs(float *p) const { stg_cs_f4(p, v); }
 };
 template <> struct Vec<1> {
     float v;
@@ -75,16 +80,20 @@ template <> struct Vec<1> {
     __device__ __forceinline__ void fma(float w, const Vec &o) { v = fmaf(w, o.v, v); }
     __device__ __forceinline__ float get(int) const { return v; }
     __device__ __forceinline__ void store(float *p) const { *p = v; }
+    __device__ __forceinline__ void store_cs(float *p) const { __stcs(p, v); }
 };
 
-// JC = bin-columns accumulated in registers at once.
-template <int VEC, int JC>
-__global__ void __launch_bounds__(kRoiWarps * 32, 5)
+// One CTA = one RoI x (NCH * 32 * VEC) channels (all 512 channels of the R-50-DC5 neck for VEC=4, NCH=4), so the
+// per-RoI work (RoI decode, weight lists, loop control, address arithmetic) is paid once per tap for 2 KB of
+// features instead of once per 512 B.  Warp w owns bin-row w.
+template <int VEC, int NCH>
+__global__ void __launch_bounds__(kRoiWarps * 32)
 roi_align_kernel(const float *__restrict__ feat, const float *__restrict__ rois, float *__restrict__ out,
                  int B, int C, int H, int W, int K, int ph, int pw, float spatial_scale,
                  int sampling_ratio, int aligned, int out_layout) {
-    constexpr int CS = 32 * VEC;  // channels per slab
-    extern __shared__ __align__(16) float tile[];  // [CS][P] (layout 0 only)
+    constexpr int CH = 32 * VEC;        // channels per warp-wide load
+    constexpr int CS = CH * NCH;        // channels per CTA
+    extern __shared__ __align__(16) float tile[];  // [cs_eff][P] (layout 0 only)
     __shared__ AxisTable ty, tx;
     __shared__ int s_batch;
 
@@ -107,53 +116,51 @@ roi_align_kernel(const float *__restrict__ feat, const float *__restrict__ rois,
         int gw = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(__fdiv_rn(rw, (float)pw));
         gh = min(max(gh, 0), kMaxEntries / 2);
         gw = min(max(gw, 0), kMaxEntries / 2);
-        if (tid < ph) build_axis(ty, tid, rsh, bh, gh, H);
-        else if (tid >= 32 && tid < 32 + pw) build_axis(tx, tid - 32, rsw, bw, gw, W);
+        if (tid < ph) build_axis(ty, tid, rsh, bh, gh, H, W * C);
+        else if (tid >= 32 && tid < 32 + pw) build_axis(tx, tid - 32, rsw, bw, gw, W, C);
         if (tid == 0) s_batch = min(max((int)r[0], 0), B - 1);
     }
     __syncthreads();
 
-    const int cl = lane * VEC;           // channel within slab
-    const bool active = (c0 + cl) < C;   // C % VEC == 0 guaranteed by the launcher
+    const int cl = lane * VEC;   // channel within a 32*VEC chunk
     const float *fb = feat + (size_t)s_batch * H * W * C + c0 + cl;
+    asm volatile("" : "+l"(fb));  // keep the base pointer materialised (ptxas otherwise re-derives it per load)
+    bool on[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) on[c] = c0 + c * CH + cl < C;   // C % VEC == 0 guaranteed by the launcher
 
     for (int i = warp; i < ph; i += kRoiWarps) {
         const int ny = ty.cnt[i];
         for (int j = 0; j < pw; ++j) {
-            Vec<VEC> acc;
-            acc.zero();
+            Vec<VEC> acc[NCH];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) acc[c].zero();
             const int nx = tx.cnt[j];
-            if (active) {
-                for (int x0 = 0; x0 < nx; x0 += 4) {
-                    // this bin-column's (column offset, weight) entries live in registers across the row loop
-                    const int nq = min(4, nx - x0);   // warp-uniform
-                    int xo[4];
-                    float xw[4];
+            for (int e = 0; e < ny; ++e) {
+                const float wy = ty.w[i][e];
+                const float *rowp = fb + ty.idx[i][e];
+                for (int q = 0; q < nx; ++q) {
+                    const float *p = rowp + tx.idx[j][q];
+                    const float w = tx.w[j][q] * wy;
+                    Vec<VEC> v[NCH];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        xo[q] = q < nq ? tx.idx[j][x0 + q] * C : 0;
-                        xw[q] = q < nq ? tx.w[j][x0 + q] : 0.f;
-                    }
-#pragma unroll 2
-                    for (int e = 0; e < ny; ++e) {
-                        const float wy = ty.w[i][e];
-                        const float *rowp = fb + (size_t)ty.idx[i][e] * W * C;
-                        Vec<VEC> v[4];
+                    for (int c = 0; c < NCH; ++c)
+                        if (on[c]) v[c].load(p + c * CH); else v[c].zero();
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            if (q < nq) v[q].load(rowp + xo[q]);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            if (q < nq) acc.fma(xw[q] * wy, v[q]);
-                    }
+                    for (int c = 0; c < NCH; ++c) acc[c].fma(w, v[c]);
                 }
             }
             const int bin = i * pw + j;
-            if (out_layout == 0) {
 #pragma unroll
-                for (int q = 0; q < VEC; ++q) tile[(cl + q) * P + bin] = acc.get(q);
-            } else if (active) {
-                acc.store(out + ((size_t)k * P + bin) * C + c0 + cl);
+            for (int c = 0; c < NCH; ++c) {
+                if (out_layout == 0) {
+                    if (on[c]) {
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) tile[(c * CH + cl + q) * P + bin] = acc[c].get(q);
+                    }
+                } else if (on[c]) {
+                    acc[c].store_cs(out + ((size_t)k * P + bin) * C + c0 + c * CH + cl);
+                }
             }
         }
     }
@@ -171,16 +178,14 @@ roi_align_kernel(const float *__restrict__ feat, const float *__restrict__ rois,
     }
 }
 
-template <int VEC, int JC>
+template <int VEC, int NCH>
 static int launch_roi(const float *feat, const float *rois, float *out, int B, int C, int H, int W, int K,
                       int ph, int pw, float scale, int sr, int aligned, int out_layout, cudaStream_t st) {
-    constexpr int CS = 32 * VEC;
-    size_t smem = out_layout == 0 ? sizeof(float) * CS * ph * pw : 0;
-    auto kern = roi_align_kernel<VEC, JC>;
+    constexpr int CS = 32 * VEC * NCH;
+    size_t smem = out_layout == 0 ? sizeof(float) * (size_t)min(C, CS) * ph * pw : 0;
+    if (smem > 200 * 1024) return fail(VOD_E_UNSUPPORTED, "vod_roi_align_fwd: output tile %zu B too large", smem);
+    auto kern = roi_align_kernel<VEC, NCH>;
     if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    // occupancy (6 CTAs = 42 warps per SM) matters more than L1 capacity here: the per-axis weight merge
-    // already removed most duplicate taps, the rest is served by the 126 MB L2
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     dim3 grid(K, ceil_div(C, CS));
     kern<<<grid, kRoiWarps * 32, smem, st>>>(feat, rois, out, B, C, H, W, K, ph, pw, scale, sr, aligned,
                                              out_layout); note_launch();
@@ -206,10 +211,13 @@ extern "C" int vod_roi_align_fwd(const float *feat_nhwc, const float *rois, floa
     cudaStream_t st = as_stream(stream);
     const bool vec4 = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(feat_nhwc) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+#define VOD_ROI_ARGS feat_nhwc, rois, out, B, C, H, W, K, ph, pw, spatial_scale, sampling_ratio, aligned, out_layout, st
     if (vec4) {
-        if (pw % 7 == 0) return launch_roi<4, 7>(feat_nhwc, rois, out, B, C, H, W, K, ph, pw, spatial_scale, sampling_ratio, aligned, out_layout, st);
-        return launch_roi<4, 4>(feat_nhwc, rois, out, B, C, H, W, K, ph, pw, spatial_scale, sampling_ratio, aligned, out_layout, st);
+        if (C > 256) return launch_roi<4, 4>(VOD_ROI_ARGS);
+        if (C > 128) return launch_roi<4, 2>(VOD_ROI_ARGS);
+        return launch_roi<4, 1>(VOD_ROI_ARGS);
     }
-    if (pw % 7 == 0) return launch_roi<1, 7>(feat_nhwc, rois, out, B, C, H, W, K, ph, pw, spatial_scale, sampling_ratio, aligned, out_layout, st);
-    return launch_roi<1, 4>(feat_nhwc, rois, out, B, C, H, W, K, ph, pw, spatial_scale, sampling_ratio, aligned, out_layout, st);
+    if (C > 64) return launch_roi<1, 4>(VOD_ROI_ARGS);
+    return launch_roi<1, 1>(VOD_ROI_ARGS);
+#undef VOD_ROI_ARGS
 }

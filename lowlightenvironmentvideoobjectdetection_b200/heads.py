@@ -27,6 +27,7 @@ class SelsaBBoxHead(nn.Module):
                  target_stds=(0.2, 0.2, 0.2, 0.2), **kwargs):
         super().__init__()
         self.num_shared_fcs = num_shared_fcs
+        self._in_channels = in_channels
         self.num_classes = num_classes
         self.reg_class_agnostic = reg_class_agnostic
         self.target_means, self.target_stds = tuple(target_means), tuple(target_stds)
@@ -38,6 +39,7 @@ class SelsaBBoxHead(nn.Module):
         self.fc_cls = nn.Linear(last, num_classes + 1)
         self.fc_reg = nn.Linear(last, 4 if reg_class_agnostic else 4 * num_classes)
         self.aggregator = nn.ModuleList([build_aggregator(aggregator) for _ in range(num_shared_fcs)])
+        self._fc0_cl = None   # (weight version, weight columns re-ordered for channels_last RoI features)
         self.init_weights()
 
     def init_weights(self):
@@ -54,15 +56,40 @@ class SelsaBBoxHead(nn.Module):
     def forward(self, x, ref_x):
         """x [N, C, 7, 7] key RoI features, ref_x [M, C, 7, 7] reference RoI features
         -> (cls_score [N, classes+1], bbox_pred [N, 4*classes])   (selsa_bbox_head.py:25-84)."""
-        x = x.flatten(1)
-        ref_x = ref_x.flatten(1)
+        x, x_cl = self._flatten(x)
+        ref_x, ref_cl = self._flatten(ref_x)
         for i, fc in enumerate(self.shared_fcs):
-            x = fc(x)
-            ref_x = fc(ref_x)
+            if i == 0:
+                x = F.linear(x, self._fc0_weight(x_cl), fc.bias)
+                ref_x = F.linear(ref_x, self._fc0_weight(ref_cl), fc.bias)
+            else:
+                x = fc(x)
+                ref_x = fc(ref_x)
             x = x + self.aggregator[i](x, ref_x)   # aggregator sees the PRE-ReLU features (:56)
             ref_x = F.relu(ref_x)
             x = F.relu(x)
         return self.fc_cls(x), self.fc_reg(x)
+
+    @staticmethod
+    def _flatten(t):
+        """x.flatten(1) (selsa_bbox_head.py:50-51).  RoI features that arrive with channels_last strides
+        (memory [K,7,7,C], what the RoIAlign / TAFA kernels write without a transposition tile) are flattened
+        in (7,7,C) order for free; fc_0 then uses its column-permuted weight, so the product is unchanged."""
+        if t.dim() == 4 and not t.is_contiguous() and t.permute(0, 2, 3, 1).is_contiguous():
+            return t.permute(0, 2, 3, 1).reshape(t.shape[0], -1), True
+        return t.flatten(1), False
+
+    def _fc0_weight(self, channels_last):
+        w = self.shared_fcs[0].weight
+        if not channels_last:
+            return w
+        key = (w._version, w.data_ptr())
+        if self._fc0_cl is None or self._fc0_cl[0] != key:
+            out_f, in_f = w.shape
+            p = in_f // self._in_channels
+            w_cl = w.detach().view(out_f, self._in_channels, p).permute(0, 2, 1).reshape(out_f, in_f).contiguous()
+            self._fc0_cl = (key, w_cl)
+        return self._fc0_cl[1]
 
     @torch.no_grad()
     def get_bboxes(self, rois, cls_score, bbox_pred, img_shape, scale_factor, rescale=False, cfg=None):
@@ -91,6 +118,10 @@ class SelsaRoIHead(nn.Module):
             head_cfg.setdefault('target_means', coder.get('target_means', (0., 0., 0., 0.)))
             head_cfg.setdefault('target_stds', coder.get('target_stds', (0.2, 0.2, 0.2, 0.2)))
         self.bbox_head = HEADS.build(head_cfg)
+        # our bbox head consumes channels_last RoI features directly (fc_0 weight columns permuted once), so the
+        # extractor kernels can skip the [C][49] shared-memory transposition
+        for layer in self.bbox_roi_extractor.roi_layers:
+            layer.channels_last_out = True
         self.test_cfg = test_cfg or dict(score_thr=0.0001, nms=dict(type='nms', iou_threshold=0.5), max_per_img=100)
 
     @torch.no_grad()

@@ -100,11 +100,19 @@ def roi_align_nhwc(feat_nhwc, rois, output_size, spatial_scale=1.0, sampling_rat
     return out
 
 
-def roi_align(input, rois, output_size, spatial_scale=1.0, sampling_ratio=0, pool_mode='avg', aligned=True):
-    """Functional mmcv.ops.roi_align (NCHW in, [K,C,ph,pw] out)."""
+def roi_align(input, rois, output_size, spatial_scale=1.0, sampling_ratio=0, pool_mode='avg', aligned=True,
+              channels_last_out=False):
+    """Functional mmcv.ops.roi_align (NCHW in, [K,C,ph,pw] out).
+
+    ``channels_last_out``: the result has the same logical shape [K,C,ph,pw] and values but channels_last
+    strides (memory [K,ph,pw,C]); the kernel then writes straight from registers, without the shared-memory
+    transposition tile.  Consumers that flatten in (C,ph,pw) order still get correct values (torch copies)."""
     if pool_mode != 'avg':
         raise NotImplementedError("vodagg RoIAlign implements pool_mode='avg' only (the reference's configs)")
     nhwc, _, _ = to_nhwc(input)
+    if channels_last_out:
+        return roi_align_nhwc(nhwc.contiguous(), rois, output_size, spatial_scale, sampling_ratio, aligned,
+                              out_nhwc=True).permute(0, 3, 1, 2)
     return roi_align_nhwc(nhwc.contiguous(), rois, output_size, spatial_scale, sampling_ratio, aligned)
 
 
@@ -120,10 +128,11 @@ class RoIAlign(nn.Module):
         self.pool_mode = pool_mode
         self.aligned = aligned
         self.use_torchvision = use_torchvision  # accepted for signature parity; the CUDA kernel is always used
+        self.channels_last_out = False          # set by SelsaRoIHead: emit channels_last strides (same values)
 
     def forward(self, input, rois):
         return roi_align(input, rois, self.output_size, self.spatial_scale, self.sampling_ratio, self.pool_mode,
-                         self.aligned)
+                         self.aligned, channels_last_out=self.channels_last_out)
 
     def __repr__(self):
         return ('%s(output_size=%s, spatial_scale=%s, sampling_ratio=%s, pool_mode=%s, aligned=%s)' %

@@ -179,6 +179,7 @@ class TemporalRoIAlign(SingleRoIExtractor):
 
     def _tafa(self, x_all, rh, rw):
         T1, N, P, C = x_all.shape
+        cl_out = self.roi_layers[0].channels_last_out
         if self.num_temporal_attention_blocks > 0:
             # embed conv on the channels_last view: logical [(T+1)*N, C, 7, 7], memory [(T+1)*N, 7, 7, C]
             patches = x_all.view(T1 * N, rh, rw, C).permute(0, 3, 1, 2)
@@ -187,9 +188,12 @@ class TemporalRoIAlign(SingleRoIExtractor):
             # the weighting kernel (saves a full read+write pass over the [T+1,N,49,C] embedding)
             emb = torch.nn.functional.conv2d(patches, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
             emb = emb.permute(0, 2, 3, 1).contiguous().view(T1, N, P, C)  # no copy: cuDNN keeps channels_last
-            out = ops.tafa_weighted_sum(x_all, emb, self.num_temporal_attention_blocks, emb_bias=conv.bias)
+            out = ops.tafa_weighted_sum(x_all, emb, self.num_temporal_attention_blocks, emb_bias=conv.bias,
+                                        out_nhwc=cl_out)
         else:
-            out = ops.tafa_weighted_sum(x_all, None, 0)                    # plain mean, :203-206
+            out = ops.tafa_weighted_sum(x_all, None, 0, out_nhwc=cl_out)   # plain mean, :203-206
+        if cl_out:
+            return out.view(N, rh, rw, C).permute(0, 3, 1, 2)              # logical [N,C,7,7], channels_last strides
         return out.view(N, C, rh, rw)
 
     @force_fp32(apply_to=('feats', 'ref_feats'), out_fp16=True)

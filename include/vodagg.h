@@ -166,6 +166,35 @@ int vod_batched_nms(const float *boxes, const float *scores, const int64_t *labe
                     int64_t *keep_out, int *num_keep_out, void *ws, size_t ws_bytes,
                     vod_stream_t stream);
 
+/* Superset of vod_batched_nms for the fixed-shape, sync-free multiclass path:
+ *   n_valid_dev [n_images] (device, nullable): boxes whose score is -inf are invalid, the image's effective
+ *               candidate count is n_valid_dev[img] (they sort last and are never visited)
+ *   mode 3:     decided on the device per image: coordinate-offset trick when n_valid < split_thr, per-class
+ *               raw-coordinate NMS otherwise (what mmcv's batched_nms does on the host)
+ *   dets_out [n_images][max_keep][5], labels_out [n_images][max_keep] (nullable): survivors' (box, score) and
+ *               label gathered by the sweep itself; keep_out may then be null.
+ */
+int vod_batched_nms_ex(const float *boxes, const float *scores, const int64_t *labels, int n_total,
+                       const int *seg_offsets_host, int n_images, float iou_thr, int mode, int max_keep,
+                       const int *n_valid_dev, int split_thr, int64_t *keep_out, int *num_keep_out,
+                       float *dets_out, int64_t *labels_out, void *ws, size_t ws_bytes,
+                       vod_stream_t stream);
+
+/* ---------------------------------------------- get_bboxes front half (caller of (5))
+ * softmax(cls_score) + delta2bbox (+ clip to img_h/img_w when >= 0, + division by scale_factor_host when
+ * non-null) + the multiclass candidate expansion, in one launch: candidate id = proposal * ncls + class,
+ * score = -inf when score <= score_thr, *n_valid_dev = number of valid candidates.
+ * replaces: the elementwise half of BBoxHead.get_bboxes (mmdet/models/roi_heads/bbox_heads/bbox_head.py:319-353),
+ *   delta2bbox (mmdet/core/bbox/coder/delta_xywh_bbox_coder.py:134-237) and the candidate filtering of
+ *   multiclass_nms (mmdet/core/post_processing/bbox_nms.py:34-73)
+ */
+int vod_bbox_decode_candidates(const float *rois, const float *cls_score, const float *bbox_pred, int N,
+                               int ncls, int reg_class_agnostic, const float *means_host,
+                               const float *stds_host, float max_ratio, float img_h, float img_w,
+                               const float *scale_factor_host, float score_thr, float *cand_boxes,
+                               float *cand_scores, int64_t *cand_labels, int *n_valid_dev,
+                               vod_stream_t stream);
+
 /* ------------------------------------------------------------ diagnostics
  * Plain tcgen05 GEMM used by the unit tests to validate descriptors/pipeline:
  * D[M,N] (fp32) = A[M,K] * B[N,K]^T, A/B row-major (K contiguous), dtype bf16 or fp32(tf32).

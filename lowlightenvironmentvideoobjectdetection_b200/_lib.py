@@ -40,6 +40,9 @@ SIGNATURES = {
     'vod_tafa_weighted_sum': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     'vod_nms_workspace_bytes': (_SZ, [_I, _I]),
     'vod_batched_nms': (_I, [_P, _P, _P, _I, _c.POINTER(_I), _I, _F, _I, _I, _P, _P, _P, _SZ, _P]),
+    'vod_batched_nms_ex': (_I, [_P, _P, _P, _I, _c.POINTER(_I), _I, _F, _I, _I, _P, _I, _P, _P, _P, _P, _P, _SZ, _P]),
+    'vod_bbox_decode_candidates': (_I, [_P, _P, _P, _I, _I, _I, _c.POINTER(_F), _c.POINTER(_F), _F, _F, _F,
+                                        _c.POINTER(_F), _F, _P, _P, _P, _P, _P]),
     'vod_test_gemm_nt': (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
 }
 

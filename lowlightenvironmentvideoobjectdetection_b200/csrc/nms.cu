@@ -23,6 +23,22 @@ struct SegTable {
     int off[kMaxImages + 1];
 };
 
+// Optional extensions used by the fixed-shape (sync-free, graph-capturable) multiclass path.
+struct NmsOpt {
+    const int *n_valid;      // [n_images] device or null: candidates whose score is -inf are invalid and the
+                             // image's effective box count is n_valid[img] (they sort last)
+    int split_thr;           // mode 3 (auto): coordinate-offset trick below split_thr valid boxes, per-class at/above
+    float *dets_out;         // [n_images][keep_stride][5] or null: (x1,y1,x2,y2,score) of the survivors
+    int64_t *labels_out;     // [n_images][keep_stride] or null
+    const float *boxes, *scores;
+    const int64_t *labels;
+    int keep_stride;
+};
+__device__ __forceinline__ int eff_n(const NmsOpt &o, int img, int n) { return o.n_valid ? min(n, o.n_valid[img]) : n; }
+__device__ __forceinline__ int eff_mode(const NmsOpt &o, int mode, int n_eff) {
+    return mode == 3 ? (n_eff < o.split_thr ? 1 : 2) : mode;
+}
+
 struct NmsWorkspace {
     int *rank;            // [n_total]
     unsigned *segmax;     // [kMaxImages] order-preserving encoding of the max coordinate
@@ -60,7 +76,7 @@ __device__ __forceinline__ float dec_ordered(unsigned u) {
 constexpr int kRankThreads = 256;
 __global__ void __launch_bounds__(kRankThreads)
 nms_rank_kernel(const float *__restrict__ boxes, const float *__restrict__ scores, SegTable seg,
-                int *__restrict__ rank, unsigned *__restrict__ segmax, int want_max) {
+                int *__restrict__ rank, unsigned *__restrict__ segmax, int want_max, int skip_invalid) {
     const int img = blockIdx.z;
     const int beg = seg.off[img], n = seg.off[img + 1] - beg;
     const int i = blockIdx.x * kRankThreads + threadIdx.x;
@@ -80,15 +96,19 @@ nms_rank_kernel(const float *__restrict__ boxes, const float *__restrict__ score
         // rank = #{s_j > s_i} + #{s_j == s_i, j < i}: for a tile entirely before (after) this block's rows the
         // tie term is constant, so the inner loop is a single compare
         if (base + lim - 1 < i_lo) {
-            for (int t = 0; t < lim; t += 4) {
-                const float4 s4 = *reinterpret_cast<const float4 *>(&sj[t]);   // padded with -inf
+            int t = 0;
+            for (; t + 4 <= lim; t += 4) {
+                const float4 s4 = *reinterpret_cast<const float4 *>(&sj[t]);
                 cnt += (s4.x >= si) + (s4.y >= si) + (s4.z >= si) + (s4.w >= si);
             }
+            for (; t < lim; ++t) cnt += sj[t] >= si;
         } else if (base > i_hi) {
-            for (int t = 0; t < lim; t += 4) {
+            int t = 0;
+            for (; t + 4 <= lim; t += 4) {
                 const float4 s4 = *reinterpret_cast<const float4 *>(&sj[t]);
                 cnt += (s4.x > si) + (s4.y > si) + (s4.z > si) + (s4.w > si);
             }
+            for (; t < lim; ++t) cnt += sj[t] > si;
         } else {
             for (int t = 0; t < lim; ++t) {
                 const float s = sj[t];
@@ -101,7 +121,7 @@ nms_rank_kernel(const float *__restrict__ boxes, const float *__restrict__ score
 
     if (want_max && blockIdx.y == 0) {
         float m = -INFINITY;
-        if (i < n) {
+        if (i < n && !(skip_invalid && si == -INFINITY)) {   // boxes.max() is taken over the valid boxes only
             float4 b = reinterpret_cast<const float4 *>(boxes)[beg + i];
             m = fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w));
         }
@@ -113,10 +133,11 @@ nms_rank_kernel(const float *__restrict__ boxes, const float *__restrict__ score
 // grid (i-blocks, images)
 __global__ void __launch_bounds__(256)
 nms_scatter_kernel(const float *__restrict__ boxes, const int64_t *__restrict__ labels, SegTable seg,
-                   const int *__restrict__ rank, const unsigned *__restrict__ segmax, int mode,
+                   const int *__restrict__ rank, const unsigned *__restrict__ segmax, int mode_in, NmsOpt opt,
                    float4 *__restrict__ sboxes, int *__restrict__ sidx, int *__restrict__ slab) {
     const int img = blockIdx.y;
     const int beg = seg.off[img], n = seg.off[img + 1] - beg;
+    const int mode = eff_mode(opt, mode_in, eff_n(opt, img, n));
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 b = reinterpret_cast<const float4 *>(boxes)[beg + i];
@@ -149,9 +170,11 @@ __device__ __forceinline__ bool iou_gt(const float4 &a, float area_a, const floa
 // grid (col-blocks, row-blocks, images), 64 threads; thread = one row of the tile
 __global__ void __launch_bounds__(64)
 nms_mask_kernel(const float4 *__restrict__ sboxes, const int *__restrict__ slab, SegTable seg,
-                float thr, int mode, int words, unsigned long long *__restrict__ mask) {
+                float thr, int mode_in, NmsOpt opt, int words, unsigned long long *__restrict__ mask) {
     const int img = blockIdx.z;
-    const int beg = seg.off[img], n = seg.off[img + 1] - beg;
+    const int beg = seg.off[img];
+    const int n = eff_n(opt, img, seg.off[img + 1] - beg);
+    const int mode = eff_mode(opt, mode_in, n);
     const int rb = blockIdx.y, cb = blockIdx.x;
     if (cb < rb || rb * 64 >= n || cb * 64 >= n) return;
     __shared__ float4 cbox[64];
@@ -182,13 +205,14 @@ nms_mask_kernel(const float4 *__restrict__ sboxes, const int *__restrict__ slab,
 constexpr int kSweepThreads = 1024;
 __global__ void __launch_bounds__(kSweepThreads)
 nms_sweep_kernel(const unsigned long long *__restrict__ mask, const int *__restrict__ sidx,
-                 SegTable seg, int words, int max_keep, int64_t *__restrict__ keep_out,
+                 SegTable seg, int words, int max_keep, NmsOpt opt, int64_t *__restrict__ keep_out,
                  int *__restrict__ num_keep_out) {
     extern __shared__ unsigned long long remv[];  // [words]
     __shared__ unsigned long long s_keepbits;
     __shared__ int s_count;
     const int img = blockIdx.x;
-    const int beg = seg.off[img], n = seg.off[img + 1] - beg;
+    const int beg = seg.off[img];
+    const int n = eff_n(opt, img, seg.off[img + 1] - beg);
     const int nblk = ceil_div(n, 64);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int w = tid; w < words; w += kSweepThreads) remv[w] = 0ull;
@@ -217,7 +241,17 @@ nms_sweep_kernel(const unsigned long long *__restrict__ mask, const int *__restr
                 int t = lane + 32 * h;
                 if ((kb >> t) & 1ull) {
                     int pos = before + __popcll(kb & ((1ull << t) - 1ull));
-                    if (pos < limit) keep_out[beg + pos] = (int64_t)sidx[beg + blk * 64 + t];
+                    if (pos < limit) {
+                        const int orig = sidx[beg + blk * 64 + t];
+                        if (keep_out) keep_out[beg + pos] = (int64_t)orig;
+                        if (opt.dets_out) {
+                            const float4 b = reinterpret_cast<const float4 *>(opt.boxes)[beg + orig];
+                            float *d = opt.dets_out + ((size_t)img * opt.keep_stride + pos) * 5;
+                            d[0] = b.x; d[1] = b.y; d[2] = b.z; d[3] = b.w; d[4] = opt.scores[beg + orig];
+                        }
+                        if (opt.labels_out)
+                            opt.labels_out[(size_t)img * opt.keep_stride + pos] = opt.labels ? opt.labels[beg + orig] : 0;
+                    }
                 }
             }
             __syncwarp();
@@ -259,14 +293,16 @@ extern "C" size_t vod_nms_workspace_bytes(int n_total, int max_seg) {
     return carve(nullptr, n_total, ceil_div(max_seg, 64)).bytes;
 }
 
-extern "C" int vod_batched_nms(const float *boxes, const float *scores, const int64_t *labels,
-                               int n_total, const int *seg_offsets_host, int n_images, float iou_thr,
-                               int mode, int max_keep, int64_t *keep_out, int *num_keep_out, void *ws,
-                               size_t ws_bytes, vod_stream_t stream) {
+extern "C" int vod_batched_nms_ex(const float *boxes, const float *scores, const int64_t *labels,
+                                  int n_total, const int *seg_offsets_host, int n_images, float iou_thr,
+                                  int mode, int max_keep, const int *n_valid_dev, int split_thr,
+                                  int64_t *keep_out, int *num_keep_out, float *dets_out, int64_t *labels_out,
+                                  void *ws, size_t ws_bytes, vod_stream_t stream) {
     VOD_REQUIRE(n_images >= 1 && n_images <= kMaxImages, "vod_batched_nms: n_images=%d not in [1,%d]",
                 n_images, kMaxImages);
     VOD_REQUIRE(seg_offsets_host && num_keep_out, "vod_batched_nms: null seg_offsets/num_keep_out");
-    VOD_REQUIRE(mode >= 0 && mode <= 2, "vod_batched_nms: mode=%d", mode);
+    VOD_REQUIRE(mode >= 0 && mode <= 3, "vod_batched_nms: mode=%d", mode);
+    VOD_REQUIRE(!(dets_out || labels_out) || max_keep > 0, "vod_batched_nms: dets_out/labels_out need max_keep > 0");
     VOD_REQUIRE(mode == 0 || labels, "vod_batched_nms: labels required for mode %d", mode);
     SegTable seg;
     seg.n_images = n_images;
@@ -282,7 +318,10 @@ extern "C" int vod_batched_nms(const float *boxes, const float *scores, const in
         cudaMemsetAsync(num_keep_out, 0, sizeof(int) * n_images, st);
         return check_launch("vod_batched_nms(memset)");
     }
-    VOD_REQUIRE(boxes && scores && keep_out && ws, "vod_batched_nms: null pointer");
+    VOD_REQUIRE(boxes && scores && (keep_out || dets_out) && ws, "vod_batched_nms: null pointer");
+    NmsOpt opt;
+    opt.n_valid = n_valid_dev; opt.split_thr = split_thr; opt.dets_out = dets_out; opt.labels_out = labels_out;
+    opt.boxes = boxes; opt.scores = scores; opt.labels = labels; opt.keep_stride = max_keep;
     const int words = ceil_div(max_seg, 64);
     VOD_REQUIRE(words * 8 <= 200 * 1024, "vod_batched_nms: image with %d boxes too large", max_seg);
     NmsWorkspace w = carve(ws, n_total, words);
@@ -296,15 +335,23 @@ extern "C" int vod_batched_nms(const float *boxes, const float *scores, const in
     // enough j-splits to fill the machine (~4 CTAs/SM), each split at least 256 candidates
     int jsplits = max(1, min(ceil_div(max_seg, 256), ceil_div(4 * kNumSMs, iblocks * n_images)));
     nms_rank_kernel<<<dim3(iblocks, jsplits, n_images), kRankThreads, 0, st>>>(
-        boxes, scores, seg, w.rank, w.segmax, mode == 1); note_launch();
+        boxes, scores, seg, w.rank, w.segmax, mode == 1 || mode == 3, n_valid_dev != nullptr); note_launch();
     nms_scatter_kernel<<<dim3(ceil_div(max_seg, 256), n_images), 256, 0, st>>>(
-        boxes, labels, seg, w.rank, w.segmax, mode, w.sboxes, w.sidx, w.slab); note_launch();
-    nms_mask_kernel<<<dim3(words, words, n_images), 64, 0, st>>>(w.sboxes, w.slab, seg, iou_thr, mode,
+        boxes, labels, seg, w.rank, w.segmax, mode, opt, w.sboxes, w.sidx, w.slab); note_launch();
+    nms_mask_kernel<<<dim3(words, words, n_images), 64, 0, st>>>(w.sboxes, w.slab, seg, iou_thr, mode, opt,
                                                                  words, w.mask); note_launch();
     size_t smem = sizeof(unsigned long long) * words;
     if (smem > 40 * 1024)
         cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    nms_sweep_kernel<<<n_images, kSweepThreads, smem, st>>>(w.mask, w.sidx, seg, words, max_keep,
+    nms_sweep_kernel<<<n_images, kSweepThreads, smem, st>>>(w.mask, w.sidx, seg, words, max_keep, opt,
                                                             keep_out, num_keep_out); note_launch();
     return check_launch("vod_batched_nms");
+}
+
+extern "C" int vod_batched_nms(const float *boxes, const float *scores, const int64_t *labels, int n_total,
+                               const int *seg_offsets_host, int n_images, float iou_thr, int mode, int max_keep,
+                               int64_t *keep_out, int *num_keep_out, void *ws, size_t ws_bytes, vod_stream_t stream) {
+    VOD_REQUIRE(mode >= 0 && mode <= 2, "vod_batched_nms: mode=%d", mode);
+    return vod_batched_nms_ex(boxes, scores, labels, n_total, seg_offsets_host, n_images, iou_thr, mode, max_keep,
+                              nullptr, 0, keep_out, num_keep_out, nullptr, nullptr, ws, ws_bytes, stream);
 }

@@ -103,6 +103,21 @@ class SelsaBBoxHead(nn.Module):
             return bboxes, scores
         return multiclass_nms(bboxes, scores, cfg['score_thr'], cfg['nms'], cfg['max_per_img'])
 
+    @torch.no_grad()
+    def get_bboxes_device(self, rois, cls_score, bbox_pred, img_shape, scale_factor, rescale=False, cfg=None):
+        """Same result as ``get_bboxes`` but sync-free and fixed-shape: softmax + delta2bbox + clip + rescale +
+        candidate expansion run as one kernel, the NMS (sort, mask, sweep, gather) stays on the device.
+        Returns (dets [max_per_img,5] zero-padded, labels [max_per_img], count [1] int32 device tensor)."""
+        from . import ops
+        nms_cfg = dict(cfg['nms'])
+        assert nms_cfg.pop('type', 'nms') == 'nms'
+        thr = nms_cfg.pop('iou_threshold', nms_cfg.pop('iou_thr', None))
+        cand = ops.bbox_decode_candidates(rois, cls_score, bbox_pred, self.num_classes, self.target_means,
+                                          self.target_stds, img_shape, scale_factor if rescale else None,
+                                          cfg['score_thr'], reg_class_agnostic=self.reg_class_agnostic)
+        return ops.multiclass_nms_device(*cand, thr, cfg['max_per_img'], split_thr=nms_cfg.pop('split_thr', 10000),
+                                         class_agnostic=nms_cfg.pop('class_agnostic', False))
+
 
 @HEADS.register_module()
 class SelsaRoIHead(nn.Module):
@@ -153,6 +168,32 @@ class SelsaRoIHead(nn.Module):
             det_bboxes.append(det_bbox)
             det_labels.append(det_label)
         return det_bboxes, det_labels
+
+    @torch.no_grad()
+    def simple_test_device(self, x, ref_x, rois, ref_rois, img_shape, scale_factor, rescale=False):
+        """One key frame, fixed shapes, no host synchronisation (the form CUDA graphs capture):
+        x / ref_x feature tuples, rois [N,5] of the key frame, ref_rois [M,5] -> (dets [max,5], labels [max], count [1])."""
+        res = self._bbox_forward(x, ref_x, rois, ref_rois)
+        return self.bbox_head.get_bboxes_device(rois, res['cls_score'], res['bbox_pred'], img_shape, scale_factor,
+                                                rescale=rescale, cfg=self.test_cfg)
+
+    def capture_graph(self, x, ref_x, rois, ref_rois, img_shape, scale_factor, rescale=False, warmup=2):
+        """Captures ``simple_test_device`` for these (static) input tensors into a CUDA graph.  The caller refills
+        the same input tensors in place and calls ``graph.replay()``; outputs are the returned static tensors."""
+        from . import ops
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):          # allocates workspaces, loads modules, sets kernel attributes
+                self.simple_test_device(x, ref_x, rois, ref_rois, img_shape, scale_factor, rescale)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        ops._nhwc_memo.clear()               # every layout pass must be recorded inside the graph
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            outs = self.simple_test_device(x, ref_x, rois, ref_rois, img_shape, scale_factor, rescale)
+        ops._nhwc_memo.clear()
+        return graph, outs
 
     @torch.no_grad()
     def simple_test(self, x, ref_x, proposals_list, ref_proposals_list, img_metas, proposals=None, rescale=False):

@@ -219,6 +219,52 @@ def batched_nms(boxes, scores, idxs, nms_cfg, class_agnostic=False):
     return dets, keep
 
 
+def bbox_decode_candidates(rois, cls_score, bbox_pred, num_classes, means, stds, img_shape=None, scale_factor=None,
+                           score_thr=0.0, wh_ratio_clip=16 / 1000, reg_class_agnostic=False):
+    """softmax + delta2bbox + clip (+ rescale) + multiclass candidate expansion in one launch (fixed shapes).
+    Returns (cand_boxes [N*ncls,4], cand_scores [N*ncls] (-inf where score <= thr), cand_labels [N*ncls] int64,
+    n_valid [1] int32 on the device)."""
+    _lib.require_cuda(rois, cls_score, bbox_pred)
+    rois, cls_score, bbox_pred = _f32c(rois), _f32c(cls_score), _f32c(bbox_pred)
+    N = rois.shape[0]
+    dev = rois.device
+    n = N * num_classes
+    boxes = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    scores = torch.empty((n,), dtype=torch.float32, device=dev)
+    labels = torch.empty((n,), dtype=torch.int64, device=dev)
+    n_valid = torch.empty((1,), dtype=torch.int32, device=dev)
+    f4 = ctypes.c_float * 4
+    sf = f4(*[float(v) for v in scale_factor]) if scale_factor is not None else None
+    h, w = (float(img_shape[0]), float(img_shape[1])) if img_shape is not None else (-1.0, -1.0)
+    _lib.call('vod_bbox_decode_candidates', _lib.ptr(rois), _lib.ptr(cls_score), _lib.ptr(bbox_pred), N,
+              int(num_classes), int(bool(reg_class_agnostic)), f4(*[float(v) for v in means]),
+              f4(*[float(v) for v in stds]), float(abs(math.log(wh_ratio_clip))), h, w, sf, float(score_thr),
+              _lib.ptr(boxes), _lib.ptr(scores), _lib.ptr(labels), _lib.ptr(n_valid), _lib.stream_ptr(dev))
+    return boxes, scores, labels, n_valid
+
+
+def multiclass_nms_device(cand_boxes, cand_scores, cand_labels, n_valid, iou_threshold, max_num, split_thr=10000,
+                          class_agnostic=False):
+    """Fixed-shape multiclass NMS without any host synchronisation (CUDA-graph capturable):
+    returns (dets [max_num,5] zero-padded, labels [max_num] int64, count [1] int32), all on the device."""
+    _lib.require_cuda(cand_boxes, cand_scores, cand_labels, n_valid)
+    n = cand_boxes.shape[0]
+    dev = cand_boxes.device
+    dets = torch.zeros((max_num, 5), dtype=torch.float32, device=dev)
+    labels = torch.zeros((max_num,), dtype=torch.int64, device=dev)
+    count = torch.zeros((1,), dtype=torch.int32, device=dev)
+    if n == 0:
+        return dets, labels, count
+    lib = _lib.load()
+    ws = _ws.get(lib.vod_nms_workspace_bytes(n, n), dev)
+    offs = (ctypes.c_int * 2)(0, n)
+    _lib.call('vod_batched_nms_ex', _lib.ptr(cand_boxes), _lib.ptr(cand_scores), _lib.ptr(cand_labels), n, offs, 1,
+              float(iou_threshold), NMS_MODE_AGNOSTIC if class_agnostic else 3, int(max_num), _lib.ptr(n_valid),
+              int(split_thr), None, _lib.ptr(count), _lib.ptr(dets), _lib.ptr(labels), _lib.ptr(ws), ws.numel(),
+              _lib.stream_ptr(dev))
+    return dets, labels, count
+
+
 # ----------------------------------------------------------------------------- (2) warp / FGFA weighting
 def flow_warp(x, flow):
     _lib.require_cuda(x, flow)

@@ -294,3 +294,85 @@ def test_layout_kernel():
     assert rel_err(norm, ref_norm) < 1e-6
     ref_unit = (x.permute(0, 2, 3, 1).reshape(-1, 512) / ref_norm[:, None]).bfloat16()
     assert (unit.float() - ref_unit.float()).abs().max() <= 2 ** -8
+
+
+# ------------------------------------------------------------------------------------------ fixed-shape get_bboxes / graph
+def _head(C=64, D=128, classes=6, fcs=2, troi=True):
+    torch.manual_seed(0)
+    ext = dict(type='TemporalRoIAlign' if troi else 'SingleRoIExtractor',
+               roi_layer=dict(type='RoIAlign', output_size=7, sampling_ratio=2), out_channels=C, featmap_strides=[16])
+    if troi:
+        ext.update(num_most_similar_points=2, num_temporal_attention_blocks=4)
+    head = vod.SelsaRoIHead(bbox_roi_extractor=ext,
+                            bbox_head=dict(type='SelsaBBoxHead', num_shared_fcs=fcs, in_channels=C, fc_out_channels=D,
+                                           num_classes=classes, aggregator=dict(type='SelsaAggregator', in_channels=D,
+                                                                                num_attention_blocks=2))).to(DEV)
+    torch.nn.init.normal_(head.bbox_head.fc_cls.weight, 0, 0.3)
+    torch.nn.init.normal_(head.bbox_head.fc_reg.weight, 0, 0.05)
+    return head
+
+
+def test_get_bboxes_device_matches_oracle_and_sync_path():
+    g = torch.Generator().manual_seed(31)
+    head = _head()
+    N, classes = 200, 6
+    rois = rpn_like_rois(g, N, 1, 320., 192.)
+    cls = torch.randn(N, classes + 1, generator=g) * 2
+    reg = torch.randn(N, classes * 4, generator=g) * 0.5
+    cfg = dict(score_thr=0.05, nms=dict(type='nms', iou_threshold=0.5), max_per_img=100)
+    for rescale, sf in ((False, (1., 1., 1., 1.)), (True, (1.6, 1.5, 1.6, 1.5))):
+        d0, l0 = O.get_bboxes(rois, cls, reg, (192, 320, 3), sf, rescale, 0.05, cfg['nms'], 100)
+        d1, l1, cnt = head.bbox_head.get_bboxes_device(rois.to(DEV), cls.to(DEV), reg.to(DEV), (192, 320, 3), sf,
+                                                       rescale=rescale, cfg=cfg)
+        k = int(cnt.item())
+        assert k == len(d0)
+        assert torch.equal(l1[:k].cpu(), l0)
+        assert (d1[:k].cpu() - d0).abs().max() < 1e-4          # boxes px / scores (expf, softmax order)
+        assert float(d1[k:].abs().sum()) == 0.0
+        d2, l2 = head.bbox_head.get_bboxes(rois.to(DEV), cls.to(DEV), reg.to(DEV), (192, 320, 3), sf, rescale=rescale, cfg=cfg)
+        assert torch.equal(l2.cpu(), l0) and (d2.cpu() - d0).abs().max() < 1e-4
+    # nothing above the score threshold -> count 0
+    d1, l1, cnt = head.bbox_head.get_bboxes_device(rois.to(DEV), torch.zeros(N, classes + 1, device=DEV), reg.to(DEV),
+                                                   (192, 320, 3), (1., 1., 1., 1.), cfg=dict(cfg, score_thr=0.9))
+    assert int(cnt.item()) == 0
+
+
+def test_device_multiclass_split_path():
+    """n_valid >= split_thr switches to the per-class raw-coordinate NMS on the device (mode decided in-kernel)."""
+    g = torch.Generator().manual_seed(32)
+    n, ncls = 600, 5
+    boxes = (clustered_boxes(g, n, 12)[:, None, :] + torch.randn(n, ncls, 4, generator=g) * 3).reshape(n, ncls * 4)
+    scores = torch.softmax(torch.randn(n, ncls + 1, generator=g) * 2, 1)
+    for split in (10000, 500):
+        cfg = dict(type='nms', iou_threshold=0.5, split_thr=split)
+        d0, l0 = O.multiclass_nms(boxes, scores, 0.05, cfg, 100)
+        flat_b = boxes.view(n, ncls, 4).reshape(-1, 4).to(DEV)
+        flat_s = scores[:, :-1].reshape(-1)
+        valid = flat_s > 0.05
+        cs = torch.where(valid, flat_s, torch.full_like(flat_s, float('-inf'))).to(DEV)
+        lab = torch.arange(ncls).repeat(n).to(DEV)
+        nv = torch.tensor([int(valid.sum())], dtype=torch.int32, device=DEV)
+        d1, l1, cnt = ops.multiclass_nms_device(flat_b, cs, lab, nv, 0.5, 100, split_thr=split)
+        k = int(cnt.item())
+        assert k == len(d0) and torch.equal(l1[:k].cpu(), l0) and torch.equal(d1[:k].cpu(), d0)
+
+
+def test_cuda_graph_replay_matches_eager():
+    g = torch.Generator().manual_seed(33)
+    head = _head()
+    C, H, W, N, T = 64, 12, 20, 24, 3
+    ref_x = torch.relu(torch.randn(T, C, H, W, generator=g)).to(DEV)
+    x = ref_x[T - 1:T].clone()
+    rois = rpn_like_rois(g, N, 1, W * 16., H * 16.).to(DEV)
+    ref_rois = rpn_like_rois(g, N, T, W * 16., H * 16.).to(DEV)
+    graph, (d, l, c) = head.capture_graph((x,), (ref_x,), rois, ref_rois, (H * 16, W * 16, 3), (1., 1., 1., 1.))
+    for seed in (34, 35):
+        g2 = torch.Generator().manual_seed(seed)
+        new_ref = torch.relu(torch.randn(T, C, H, W, generator=g2)).to(DEV)
+        ref_x.copy_(new_ref); x.copy_(new_ref[T - 1:T])
+        rois.copy_(rpn_like_rois(g2, N, 1, W * 16., H * 16.).to(DEV))
+        graph.replay()
+        torch.cuda.synchronize()
+        de, le, ce = head.simple_test_device((x,), (ref_x,), rois, ref_rois, (H * 16, W * 16, 3), (1., 1., 1., 1.))
+        assert int(c.item()) == int(ce.item())
+        assert torch.equal(l, le) and torch.equal(d, de)

@@ -308,6 +308,7 @@ def main():
     torch.cuda.set_device(device)
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault('NCCL_DEBUG', 'WARN')   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group('nccl', device_id=device)
     # library GEMMs/convs around the path (shared FCs, embed conv) run tf32 like our own tensor-core kernels
     torch.backends.cuda.matmul.allow_tf32 = True

@@ -9,10 +9,14 @@
 // locations match the fp32 reference; the bf16 GEMM is only a pre-filter.
 //
 // Persistent kernel, one CTA per SM, 576 threads; a work unit = (128-row tile, frame t):
-//   warp 16  TMA producer: the A tile (128 rows x C, K-major bf16, 128B swizzle) stays resident in shared
-//            memory while the unit's B tiles (128 locations x 64 channels per stage) stream through a ring
+//   A tile   (128 RoI rows x C bf16) lives in TENSOR MEMORY, not shared memory: row r in TMEM lane r, two bf16
+//            per 32-bit column (256 columns for C = 512), written with tcgen05.st by epilogue warps 0-3 whenever
+//            the row tile changes and consumed by the TS form of tcgen05.mma.  That frees all 208 KB of shared
+//            memory for the B ring: 13 stages in flight instead of 5 (the 5-stage version was TMA-latency bound,
+//            tensor pipe 40 % active).
+//   warp 16  TMA producer: the unit's B tiles (128 locations x 64 channels per stage, SWIZZLE_128B)
 //   warp 17  MMA issuer: tcgen05.mma kind::f16 (bf16 in, fp32 accumulate), 128x128 accumulator,
-//            double buffered in TMEM (2 x 128 columns)
+//            double buffered in TMEM (2 x 128 columns; TMEM total: 256 accumulator + 256 A = 512 columns)
 //   warps 0-15 epilogue: thread = row (four warps per TMEM lane quarter, each owning 32 of the tile's 128
 //            columns, so every SM sub-partition always has 4 epilogue warps to interleave); every similarity is packed with its location into one order-preserving 32-bit key
 //            (20 value bits | 12 location bits) and pushed through a branch-free min/max insertion network
@@ -31,26 +35,26 @@ constexpr int kMgBM = 128;           // rows per tile
 constexpr int kMgBN = 128;           // locations per accumulator tile
 constexpr int kMgSlice = 64;         // bf16 elements per 128-byte K slice
 constexpr int kMgMaxSlices = 8;      // C <= 512
-constexpr int kMgStages = 5;
+constexpr int kMgStages = 13;
 constexpr int kMgTile = 128 * 128;   // bytes of one [128 x 128 B] slice tile
 constexpr int kMgEpiWarps = 16;
 constexpr int kMgThreads = (kMgEpiWarps + 2) * 32;
-constexpr int kMgSmem = kMgMaxSlices * kMgTile + kMgStages * kMgTile + 1024;
+constexpr int kMgSmem = kMgStages * kMgTile + 1024;
+constexpr uint32_t kMgACol = 256;    // first TMEM column of the A tile
 
 struct MgParams {
     uint32_t *cand; // [NP, T, kMsraCand] packed keys: (ordered value & 0xFFFFF000) | location
+    const __nv_bfloat16 *a_rows;  // [NP, C] unit-norm RoI rows
     int NP, T, HW, nslices, row_tiles, ntiles;  // ntiles = ceil(HW / 128)
     int units;      // row_tiles * T
 };
 
 __global__ void __launch_bounds__(kMgThreads, 1)
-msra_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                      const MgParams p) {
+msra_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_b, const MgParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t *sA = smem;                               // [nslices][16 KB]
-    uint8_t *sB = smem + kMgMaxSlices * kMgTile;      // [stages][16 KB]
-    __shared__ uint64_t a_full, a_empty, b_full[kMgStages], b_empty[kMgStages], acc_full[2], acc_empty[2];
+    uint8_t *sB = smem;                               // [stages][16 KB]
+    __shared__ uint64_t a_full, b_full[kMgStages], b_empty[kMgStages], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -60,13 +64,12 @@ msra_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
     const int u1 = u0 + per + ((int)blockIdx.x < rem ? 1 : 0);
 
     if (threadIdx.x == 0) {
-        tc::mbar_init(&a_full, 1);
-        tc::mbar_init(&a_empty, 1);
+        tc::mbar_init(&a_full, 128);
         for (int i = 0; i < kMgStages; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], kMgEpiWarps * 32); }
         tc::fence_barrier_init();
     }
-    if (warp == kMgEpiWarps + 1) tc::tmem_alloc(&tmem_slot, 256);
+    if (warp == kMgEpiWarps + 1) tc::tmem_alloc(&tmem_slot, 512);
     tc::tcgen05_fence_before();
     __syncthreads();
     tc::tcgen05_fence_after();
@@ -75,20 +78,10 @@ msra_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
     if (warp == kMgEpiWarps) {
         // ------------------------------------------------------------------ TMA producer
         if (tc::elect_one()) {
-            tc::tma_prefetch_desc(&tm_a); tc::tma_prefetch_desc(&tm_b);
-            int cur_rt = -1, a_loads = 0;
+            tc::tma_prefetch_desc(&tm_b);
             long it = 0;  // global B-stage counter
             for (int u = u0; u < u1; ++u) {
-                const int rt = u / p.T, t = u % p.T;
-                if (rt != cur_rt) {
-                    // the MMA warp signals a_empty when the last MMA reading the old A tile has completed
-                    tc::mbar_wait(&a_empty, (a_loads & 1) ^ 1);
-                    tc::mbar_arrive_expect_tx(&a_full, p.nslices * kMgTile);
-                    for (int s = 0; s < p.nslices; ++s)
-                        tc::tma_load_2d(sA + s * kMgTile, &tm_a, &a_full, s * kMgSlice, rt * kMgBM);
-                    cur_rt = rt;
-                    ++a_loads;
-                }
+                const int t = u % p.T;
                 for (int nt = 0; nt < p.ntiles; ++nt) {
                     for (int s = 0; s < p.nslices; ++s, ++it) {
                         const int st = (int)(it % kMgStages);
@@ -107,9 +100,9 @@ msra_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         long it = 0, tile_it = 0;
         for (int u = u0; u < u1; ++u) {
             const int rt = u / p.T;
-            const bool last_of_rt = (u + 1 == u1) || ((u + 1) / p.T != rt);
             if (rt != cur_rt) {
-                tc::mbar_wait(&a_full, a_loads & 1);
+                tc::mbar_wait(&a_full, a_loads & 1);   // epilogue warps 0-3 have written this row tile's A into TMEM
+                tc::tcgen05_fence_after();
                 cur_rt = rt;
                 ++a_loads;
             }
@@ -122,16 +115,13 @@ msra_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
                     tc::mbar_wait(&b_full[st], (uint32_t)((it / kMgStages) & 1));
                     tc::tcgen05_fence_after();
                     if (tc::elect_one()) {
-                        const uint32_t a0 = tc::smem_u32(sA + s * kMgTile), b0 = tc::smem_u32(sB + st * kMgTile);
+                        const uint32_t b0 = tc::smem_u32(sB + st * kMgTile);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            tc::umma_f16(tmem + buf * kMgBN, tc::umma_desc_k_sw128(a0 + k * 32),
-                                         tc::umma_desc_k_sw128(b0 + k * 32), idesc, (s | k) != 0);
+                        for (int k = 0; k < 4; ++k)   // 16 bf16 of K per MMA: 8 TMEM columns of A, 32 bytes of the B slice
+                            tc::umma_f16_ts(tmem + buf * kMgBN, tmem + kMgACol + s * 32 + k * 8,
+                                            tc::umma_desc_k_sw128(b0 + k * 32), idesc, (s | k) != 0);
                         tc::umma_commit(&b_empty[st]);
-                        if (s == p.nslices - 1) {
-                            tc::umma_commit(&acc_full[buf]);
-                            if (last_of_rt && nt == p.ntiles - 1) tc::umma_commit(&a_empty);
-                        }
+                        if (s == p.nslices - 1) tc::umma_commit(&acc_full[buf]);
                     }
                     __syncwarp();
                 }
@@ -142,8 +132,37 @@ msra_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         const int quarter = warp & 3, grp = warp >> 2;   // TMEM lane quarter, 32-column group of the tile
         const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16) + grp * 32;
         long tile_it = 0;
+        int cur_rt = -1;
         for (int u = u0; u < u1; ++u) {
             const int rt = u / p.T, t = u % p.T;
+            if (rt != cur_rt) {
+                cur_rt = rt;
+                if (warp < 4) {
+                    // New row tile: this thread's RoI row -> TMEM lane, two bf16 per column.  Every MMA that read the
+                    // previous A tile has completed (this warp consumed that tile's last accumulator already).
+                    const int arow = rt * kMgBM + warp * 32 + lane;
+                    const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + kMgACol;
+                    const int C = p.nslices * kMgSlice;
+                    for (int c = 0; c < C / 2; c += 16) {
+                        uint32_t v[16];
+                        if (arow < p.NP) {
+                            const uint4 *src = reinterpret_cast<const uint4 *>(p.a_rows + (size_t)arow * C + 2 * c);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint4 w4 = __ldg(src + q);
+                                v[4 * q] = w4.x; v[4 * q + 1] = w4.y; v[4 * q + 2] = w4.z; v[4 * q + 3] = w4.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) v[q] = 0u;
+                        }
+                        tc::tmem_st_32x16(ta + c, v);
+                    }
+                    tc::tmem_st_wait();
+                    tc::tcgen05_fence_before();
+                    tc::mbar_arrive(&a_full);
+                }
+            }
             uint32_t k0 = 0, k1 = 0, k2 = 0, k3 = 0;   // descending; 0 = "nothing yet" (below every real key)
             for (int nt = 0; nt < p.ntiles; ++nt, ++tile_it) {
                 const int buf = (int)(tile_it & 1);
@@ -181,7 +200,7 @@ msra_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
     }
     tc::tcgen05_fence_before();
     __syncthreads();
-    if (warp == kMgEpiWarps + 1) tc::tmem_dealloc(tmem, 256);
+    if (warp == kMgEpiWarps + 1) tc::tmem_dealloc(tmem, 512);
 }
 
 bool msra_gemm_supported(int NP, int C, int T, int HW) {
@@ -192,19 +211,20 @@ bool msra_gemm_supported(int NP, int C, int T, int HW) {
 int msra_launch_gemm_topk(const void *roi_unit_bf16, const void *ref_unit_bf16, uint32_t *cand, int NP, int NP_pad, int C,
                           int T, int HW, cudaStream_t st) {
     (void)NP_pad;
-    CUtensorMap ta, tb;
+    CUtensorMap tb;
     int rc;
-    if ((rc = make_tmap_2d_sw128(&ta, roi_unit_bf16, 2, NP, C, (uint64_t)C * 2, kMgBM))) return rc;
+    if ((reinterpret_cast<uintptr_t>(roi_unit_bf16) & 15) != 0) return fail(VOD_E_BADARG, "msra_gemm: A rows must be 16-byte aligned");
     if ((rc = make_tmap_2d_sw128(&tb, ref_unit_bf16, 2, (uint64_t)T * HW, C, (uint64_t)C * 2, kMgBN))) return rc;
     MgParams p;
     p.cand = cand; p.NP = NP; p.T = T; p.HW = HW;
+    p.a_rows = reinterpret_cast<const __nv_bfloat16 *>(roi_unit_bf16);
     p.nslices = C / kMgSlice;
     p.row_tiles = ceil_div(NP, kMgBM);
     p.ntiles = ceil_div(HW, kMgBN);
     p.units = p.row_tiles * T;
     cudaFuncSetAttribute(msra_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMgSmem);
     const int grid = min(kNumSMs, p.units);
-    msra_gemm_topk_kernel<<<grid, kMgThreads, kMgSmem, st>>>(ta, tb, p); note_launch();
+    msra_gemm_topk_kernel<<<grid, kMgThreads, kMgSmem, st>>>(tb, p); note_launch();
     return check_launch("msra_gemm_topk");
 }
 

@@ -17,7 +17,7 @@ constexpr int kTafaMaxT = 64;
 
 // CTA = (n, head).  VEC=4: lanes own 4 consecutive channels, chunks of 128 channels.
 template <int VEC>
-__global__ void __launch_bounds__(kTafaWarps * 32)
+__global__ void __launch_bounds__(kTafaWarps * 32, 4)
 tafa_kernel(const float *__restrict__ x_all, const float *__restrict__ emb_all, const float *__restrict__ emb_bias,
             float *__restrict__ out, int T1, int N, int P, int C, int hs, float scale, int use_attn, int out_layout) {
     extern __shared__ __align__(16) float tile[];          // [hs][P] (layout 0)
@@ -273,6 +273,7 @@ msra_scan_kernel(const float *__restrict__ roi, const float *__restrict__ ref, c
 // similarity lies within kMsraMargin of the 2nd best are re-scored in exact fp32
 //   sim = sum_c (roi[c] / |roi|) * (ref[c] / |ref|)      (temporal_roi_align.py:127-142)
 // and the exact top-k feeds the softmax + gather.  Typically 2-3 of the 16 candidates are re-scored.
+template <int KM>
 __global__ void __launch_bounds__(kScanWarps * 32)
 msra_rescore_kernel(const float *__restrict__ roi, const float *__restrict__ ref, const float *__restrict__ roi_norm,
                     const float *__restrict__ ref_norm, const uint32_t *__restrict__ cand, int KC,
@@ -312,9 +313,9 @@ msra_rescore_kernel(const float *__restrict__ roi, const float *__restrict__ ref
         // NaN approximations (zero-norm vectors) compare false: keep them as candidates so the NaN propagates
         const bool want = key != 0u && !(approx < kth - kMsraMargin);
         unsigned todo = __ballot_sync(0xffffffffu, want);
-        float val[kMsraMaxK]; int loc[kMsraMaxK];
+        float val[KM]; int loc[KM];
 #pragma unroll
-        for (int i = 0; i < kMsraMaxK; ++i) { val[i] = -INFINITY; loc[i] = 0x7fffffff; }
+        for (int i = 0; i < KM; ++i) { val[i] = -INFINITY; loc[i] = 0x7fffffff; }
         bool any_nan = false;
         while (todo) {
             const int j = __ffs(todo) - 1;
@@ -336,10 +337,10 @@ msra_rescore_kernel(const float *__restrict__ roi, const float *__restrict__ ref
             }
             s = warp_sum(s);
             if (s != s) any_nan = true;            // torch.topk ranks NaN first: the reference row becomes NaN
-            topk_insert<kMsraMaxK>(val, loc, s, l);  // identical on all lanes
+            topk_insert<KM>(val, loc, s, l);  // identical on all lanes
         }
         if (any_nan) loc[0] = 0x7fffffff;          // msra_emit writes a NaN row
-        msra_emit<kMsraMaxK>(ref_t, out + ((size_t)t * NP + row) * C, idx_out ? idx_out + ((size_t)row * T + t) * k : nullptr,
+        msra_emit<KM>(ref_t, out + ((size_t)t * NP + row) * C, idx_out ? idx_out + ((size_t)row * T + t) * k : nullptr,
                              val_out ? val_out + ((size_t)row * T + t) * k : nullptr, val, loc, k, C, lane);
     }
 }
@@ -358,9 +359,17 @@ int msra_launch_rescore(const float *roi, const float *ref, const float *roi_nor
                         const uint32_t *cand, int KC, float *out, int *idx_out, float *val_out, int NP, int C, int T,
                         int HW, int k, cudaStream_t st) {
     size_t smem = sizeof(float) * kScanWarps * C;
-    if (smem > 40 * 1024) cudaFuncSetAttribute(msra_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    msra_rescore_kernel<<<(unsigned)ceil_div(NP, kScanWarps), kScanWarps * 32, smem, st>>>(
-        roi, ref, roi_norm, ref_norm, cand, KC, out, idx_out, val_out, NP, C, T, HW, k); note_launch();
+    const unsigned grid = (unsigned)ceil_div(NP, kScanWarps);
+    if (k <= 2) {   // the reference's num_most_similar_points = 2: a 2-entry insertion network
+        if (smem > 40 * 1024) cudaFuncSetAttribute(msra_rescore_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        msra_rescore_kernel<2><<<grid, kScanWarps * 32, smem, st>>>(roi, ref, roi_norm, ref_norm, cand, KC, out, idx_out,
+                                                                  val_out, NP, C, T, HW, k);
+    } else {
+        if (smem > 40 * 1024) cudaFuncSetAttribute(msra_rescore_kernel<kMsraMaxK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        msra_rescore_kernel<kMsraMaxK><<<grid, kScanWarps * 32, smem, st>>>(roi, ref, roi_norm, ref_norm, cand, KC, out,
+                                                                          idx_out, val_out, NP, C, T, HW, k);
+    }
+    note_launch();
     return check_launch("msra_rescore");
 }
 

@@ -20,6 +20,19 @@ def test_gemm_bf16(shape):
     assert err < 1e-5, err   # bf16 products are exact in fp32; only accumulation order differs
 
 
+@pytest.mark.parametrize('shape', [(128, 128, 64), (256, 384, 512), (300, 200, 128), (77, 130, 192)])
+def test_gemm_bf16_a_in_tmem(shape):
+    """TS-form MMA: A rows written to TMEM (lane = row, two bf16 per column) with tcgen05.st."""
+    M, N, K = shape
+    g = torch.Generator(device='cuda').manual_seed(4)
+    a = torch.randn(M, K, device='cuda', generator=g).bfloat16()
+    b = torch.randn(N, K, device='cuda', generator=g).bfloat16()
+    d = ops.test_gemm_nt(a, b, a_in_tmem=True)
+    ref = a.float() @ b.float().t()
+    err = (d - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-5, err
+
+
 @pytest.mark.parametrize('shape', [(128, 128, 32), (256, 256, 64), (300, 200, 100)])
 def test_gemm_tf32(shape):
     M, N, K = shape

@@ -130,6 +130,15 @@ int vod_msra_topk_sample(const float *roi_feats, const float *ref_nhwc, const fl
                          int C, int T, int HW, int k, int impl, void *ws, size_t ws_bytes,
                          vod_stream_t stream);
 
+/* The tensor-core half of (4) alone (what vod_msra_topk_sample runs before its fp32 re-score): unit-norm bf16
+ * rows roi_unit [NP, C] x ref_unit [T*HW, C] -> cand_out [NP, T, 16] packed keys
+ * (order-preserving bits of the similarity & 0xFFFFF000) | location: the 4 best of each of the four 32-column
+ * groups of the 128-location tiles; 0 = empty slot.  Exposed so the GEMM can be profiled / roofline-timed on
+ * its own and its candidate recall tested.
+ */
+int vod_msra_gemm_candidates(const void *roi_unit_bf16, const void *ref_unit_bf16, uint32_t *cand_out,
+                             int NP, int C, int T, int HW, vod_stream_t stream);
+
 /* ------------------------- (4') TemporalRoIAlign: temporal attention weighting
  * x_all, emb_all [T1, N, P, C] fp32 (frame 0 = the key's own RoI features);
  * emb_bias [C] (nullable) is added to every embedding vector on load, so the caller's embed conv

@@ -292,3 +292,11 @@ extern "C" int vod_msra_topk_sample(const float *roi_feats, const float *ref_nhw
     if (rc) return rc;
     return msra_launch_rescore(roi_feats, ref_nhwc, roi_norm, rn, cand, kMsraCand, out, idx_out, val_out, NP, C, T, HW, k, st);
 }
+
+extern "C" int vod_msra_gemm_candidates(const void *roi_unit_bf16, const void *ref_unit_bf16, uint32_t *cand_out, int NP,
+                                        int C, int T, int HW, vod_stream_t stream) {
+    VOD_REQUIRE(roi_unit_bf16 && ref_unit_bf16 && cand_out, "vod_msra_gemm_candidates: null pointer");
+    if (!msra_gemm_supported(NP, C, T, HW) || !vod_device_is_sm100())
+        return fail(VOD_E_UNSUPPORTED, "vod_msra_gemm_candidates: needs C %% 64 == 0, C <= 512, HW <= 4096, sm_100");
+    return msra_launch_gemm_topk(roi_unit_bf16, ref_unit_bf16, cand_out, NP, NP, C, T, HW, as_stream(stream));
+}

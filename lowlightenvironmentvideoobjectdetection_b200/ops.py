@@ -362,6 +362,20 @@ def msra_topk_sample(roi_rows, ref_nhwc, k=2, ref_norm=None, ref_unit=None, impl
     return out
 
 
+def msra_gemm_candidates(roi_unit, ref_unit, T):
+    """bf16 unit rows roi_unit [NP, C], ref_unit [T*HW, C] -> packed candidate keys [NP, T, 16]
+    (uint32 bit patterns in an int32 tensor; location = key & 0xFFF, 0 = empty slot)."""
+    _lib.require_cuda(roi_unit, ref_unit)
+    assert roi_unit.dtype == torch.bfloat16 and ref_unit.dtype == torch.bfloat16
+    roi_unit, ref_unit = roi_unit.contiguous(), ref_unit.contiguous()
+    NP, C = roi_unit.shape
+    HW = ref_unit.shape[0] // T
+    cand = torch.empty((NP, T, 16), dtype=torch.int32, device=roi_unit.device)
+    _lib.call('vod_msra_gemm_candidates', _lib.ptr(roi_unit), _lib.ptr(ref_unit), _lib.ptr(cand), NP, C, T, HW,
+              _lib.stream_ptr(roi_unit.device))
+    return cand
+
+
 def tafa_weighted_sum(x_all, emb_all, num_heads, out_nhwc=False, emb_bias=None):
     """x_all, emb_all [T1, N, P, C] fp32 -> [N, C, P] (or [N, P, C]).  ``emb_bias`` [C] is added to the
     embeddings on load (lets the embed conv run bias-free)."""

@@ -141,3 +141,34 @@ def test_temporal_roi_align_golden_tc(golden):
     m = m.to('cuda')
     out = m((golden['troi_feat'].to('cuda'),), golden['troi_rois'].to('cuda'), ref_feats=(golden['troi_ref'].to('cuda'),))
     assert rel_err(out, golden['troi_out']) < 1e-4
+
+
+def test_msra_candidate_recall_full_scale():
+    """cfg-3 scale (N=300 RoIs x 49 bins, T=15 frames of 38x63): the true fp32 top-2 of every (row, frame) must be
+    among the 16 candidates the bf16 tensor-core pass keeps, and the end result must pick exactly them."""
+    g = torch.Generator().manual_seed(77)
+    N, C, T, H, W = 300, 512, 15, 38, 63
+    ref = torch.relu(torch.randn(T, C, H, W, generator=g))
+    roi = torch.relu(torch.randn(N, C, 7, 7, generator=g)) + 0.3 * ref[T - 1, :, :7, :7]   # correlated with the key frame
+    out0, idx0, sim0 = O.most_similar_roi_align(roi, ref, 2, return_indices=True)
+    ref_nhwc, norm, unit = ops.to_nhwc(ref.to('cuda'), want_norm=True, want_unit_bf16=True)
+    rows = roi.permute(0, 2, 3, 1).reshape(N * 49, C).to('cuda')
+    roi_unit = torch.nn.functional.normalize(rows, dim=1).bfloat16()
+    cand = ops.msra_gemm_candidates(roi_unit, unit, T).cpu()
+    locs = (cand & 0xFFF).long()                                  # [NP, T, 16]
+    valid = cand != 0
+    hit = ((locs.unsqueeze(-1) == idx0.unsqueeze(2)) & valid.unsqueeze(-1)).any(dim=2)   # [NP, T, 2]
+    assert bool(hit.all()), 'recall %.6f' % hit.float().mean()
+    out1, idx1, _ = ops.msra_topk_sample(rows, ref_nhwc, 2, ref_norm=norm, ref_unit=unit, impl=ops.IMPL_TC, return_indices=True)
+    idx1 = idx1.cpu().long()
+    same = (idx1.sort(dim=2).values == idx0.sort(dim=2).values).all(dim=2)
+    for r, t in (~same).nonzero().tolist():
+        v_ours = sim0[r, t, idx1[r, t]].sort().values
+        v_ref = sim0[r, t, idx0[r, t]].sort().values
+        assert (v_ours - v_ref).abs().max() <= 1e-6, (r, t)
+    assert same.float().mean() > 0.9999
+    # sampled features: compared where the location sets agree (an fp32 tie that flips picks a different pixel)
+    got = out1.view(T, N * 49, C).cpu()
+    want = out0.permute(0, 1, 3, 4, 2).reshape(T, N * 49, C)
+    ok = same.t().unsqueeze(-1)                                  # [T, NP, 1]
+    assert rel_err(torch.where(ok, got, want), want) < 1e-4

@@ -215,6 +215,30 @@ def kernel_rooflines(cfg, device, peaks):
     t = timeit(lambda: ops.nms_device(boxes, scores, labels, 0.5, ops.NMS_MODE_OFFSET, max_keep=100))
     b = n * 20 + n * ((n + 63) // 64) * 8
     out['batched_nms_rcnn'] = dict(bound='hbm', seconds=t, achieved=b / t / 1e9, peak=peaks['hbm'], unit='GB/s', bytes=b)
+    # (2) FGFA / DFF feature-level path at its own shapes (31 frames): flow warp, cosine weighting, fused variant
+    TF = 31
+    xf = torch.randn(TF, C, H, W, device=device, generator=g)
+    flow = torch.randn(TF, 2, H * 16, W * 16, device=device, generator=g) * 8
+    t = timeit(lambda: ops.flow_warp(xf, flow))
+    b = 2 * TF * C * H * W * 4 + 16 * TF * H * W * 4
+    out['flow_warp_T31'] = dict(bound='hbm', seconds=t, achieved=b / t / 1e9, peak=peaks['hbm'], unit='GB/s', bytes=b)
+    key_e = torch.randn(1, C, H, W, device=device, generator=g)
+    ref_e = torch.randn(TF, C, H, W, device=device, generator=g)
+    t = timeit(lambda: ops.embed_weighted_sum(key_e, ref_e, xf))
+    b = (2 * TF + 2) * C * H * W * 4
+    out['embed_weighted_sum_T31'] = dict(bound='hbm', seconds=t, achieved=b / t / 1e9, peak=peaks['hbm'], unit='GB/s', bytes=b)
+    t = timeit(lambda: ops.fgfa_warp_weighted_sum(key_e, ref_e, xf, flow, key_e, 15))
+    out['fgfa_warp_weighted_sum_T31'] = dict(bound='hbm', seconds=t, achieved=b / t / 1e9, peak=peaks['hbm'], unit='GB/s', bytes=b)
+    del xf, flow, ref_e
+    # (5) RPN NMS: 6000 proposals x (T+1) images in one launch set, 300 kept per image
+    nimg = T + 1
+    pb = torch.cat([props_all[i % (T + 1)].to(device).repeat(20, 1) + torch.randn(6000, 4, device=device, generator=g) * 6
+                    for i in range(nimg)], 0)
+    ps = torch.rand(6000 * nimg, device=device, generator=g)
+    offs = [6000 * i for i in range(nimg + 1)]
+    t = timeit(lambda: ops.nms_device(pb, ps, None, 0.7, ops.NMS_MODE_AGNOSTIC, seg_offsets=offs, max_keep=300))
+    b = nimg * (6000 * 20 + 6000 * 94 * 8)
+    out['batched_nms_rpn_x%d' % nimg] = dict(bound='hbm', seconds=t, achieved=b / t / 1e9, peak=peaks['hbm'], unit='GB/s', bytes=b)
     for v in out.values():
         v['frac'] = v['achieved'] / v['peak']
     return out

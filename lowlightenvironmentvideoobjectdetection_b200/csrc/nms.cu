@@ -284,6 +284,120 @@ nms_sweep_kernel(const unsigned long long *__restrict__ mask, const int *__restr
     if (tid == 0) num_keep_out[img] = min(s_count, limit);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Bounded-survivor path (0 < max_keep <= kLazyMaxKeep, what multiclass_nms (100) and the RPN (300) ask for): the greedy
+// sweep only ever needs IoUs against the boxes ALREADY KEPT, so the n^2/2 bitmask is never built.  One CTA per image
+// walks the score-sorted candidates 64 at a time:
+//   (a) 16 threads per candidate test it against the kept list (shared memory),
+//   (b) the 64x64 intra-block mask is computed by the same 1024 threads,
+//   (c) warp 0 resolves the block serially in registers (identical recurrence to nms_sweep_kernel) and appends.
+// It stops as soon as max_keep boxes survived.  Same IoU arithmetic, same order => bit-identical survivors.
+constexpr int kLazyMaxKeep = 1024;
+__global__ void __launch_bounds__(1024)
+nms_lazy_kernel(const float4 *__restrict__ sboxes, const int *__restrict__ slab, const int *__restrict__ sidx,
+                SegTable seg, float thr, int mode_in, int max_keep, NmsOpt opt, int64_t *__restrict__ keep_out,
+                int *__restrict__ num_keep_out) {
+    extern __shared__ float4 kept_box[];                 // [max_keep]
+    int *kept_lab = reinterpret_cast<int *>(kept_box + max_keep);   // [max_keep]
+    __shared__ float4 cbox[64];
+    __shared__ int clab[64];
+    __shared__ unsigned long long s_dead, s_d[64], s_keepbits;
+    __shared__ int s_count;
+    const int img = blockIdx.x;
+    const int beg = seg.off[img];
+    const int n = eff_n(opt, img, seg.off[img + 1] - beg);
+    const int mode = eff_mode(opt, mode_in, n);
+    const int nblk = ceil_div(n, 64);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+
+    for (int blk = 0; blk < nblk; ++blk) {
+        const int nc = min(64, n - blk * 64);
+        if (tid < 64) {
+            if (tid < nc) { cbox[tid] = sboxes[beg + blk * 64 + tid]; clab[tid] = slab[beg + blk * 64 + tid]; }
+            s_d[tid] = 0ull;
+        }
+        if (tid == 0) s_dead = nc < 64 ? (~0ull << nc) : 0ull;
+        __syncthreads();
+        const int count = s_count;
+        const int c = tid >> 4, h = tid & 15;           // candidate, helper lane
+        // (a) candidate c against the kept list
+        if (c < nc) {
+            const float4 b = cbox[c];
+            const int lb = clab[c];
+            bool sup = false;
+            for (int k = h; k < count && !sup; k += 16) {
+                const float4 a = kept_box[k];
+                const float area_a = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+                sup = iou_gt(a, area_a, b, thr) && (mode != 2 || kept_lab[k] == lb);
+            }
+            const unsigned grp = __ballot_sync(0xffffffffu, sup) >> (lane & 16) & 0xffffu;
+            if (h == 0 && grp) atomicOr(&s_dead, 1ull << c);
+        } else {
+            __ballot_sync(0xffffffffu, false);
+        }
+        // (b) intra-block mask: row r = c (higher score), columns 4h..4h+3
+        {
+            unsigned long long bits = 0ull;
+            if (c < nc) {
+                const float4 a = cbox[c];
+                const int la = clab[c];
+                const float area_a = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int cc = 4 * h + q;
+                    if (cc > c && cc < nc) {
+                        bool sup = iou_gt(a, area_a, cbox[cc], thr);
+                        if (mode == 2) sup = sup && (clab[cc] == la);
+                        if (sup) bits |= 1ull << cc;
+                    }
+                }
+            }
+            // OR-reduce over the 16 helper lanes of this candidate
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, o);
+            if (h == 0 && c < nc) s_d[c] = bits;
+        }
+        __syncthreads();
+        // (c) serial resolve of the block by warp 0
+        if (warp == 0) {
+            const unsigned long long d_lo = s_d[lane], d_hi = s_d[lane + 32];
+            unsigned long long cur = s_dead, kb = 0ull;
+#pragma unroll
+            for (int t = 0; t < 64; ++t) {
+                const unsigned long long dt = __shfl_sync(0xffffffffu, t < 32 ? d_lo : d_hi, t & 31);
+                if (!((cur >> t) & 1ull)) { kb |= 1ull << t; cur |= dt; }
+            }
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int t = lane + 32 * hh;
+                if ((kb >> t) & 1ull) {
+                    const int pos = count + __popcll(kb & ((1ull << t) - 1ull));
+                    if (pos < max_keep) {
+                        kept_box[pos] = cbox[t];
+                        kept_lab[pos] = clab[t];
+                        const int orig = sidx[beg + blk * 64 + t];
+                        if (keep_out) keep_out[beg + pos] = (int64_t)orig;
+                        if (opt.dets_out) {
+                            const float4 b = reinterpret_cast<const float4 *>(opt.boxes)[beg + orig];
+                            float *d = opt.dets_out + ((size_t)img * opt.keep_stride + pos) * 5;
+                            d[0] = b.x; d[1] = b.y; d[2] = b.z; d[3] = b.w; d[4] = opt.scores[beg + orig];
+                        }
+                        if (opt.labels_out)
+                            opt.labels_out[(size_t)img * opt.keep_stride + pos] = opt.labels ? opt.labels[beg + orig] : 0;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) { s_keepbits = kb; s_count = count + __popcll(kb); }
+        }
+        __syncthreads();
+        if (s_count >= max_keep) break;
+    }
+    if (tid == 0) num_keep_out[img] = min(s_count, max_keep);
+}
+
 }  // namespace vod
 
 using namespace vod;
@@ -338,6 +452,12 @@ extern "C" int vod_batched_nms_ex(const float *boxes, const float *scores, const
         boxes, scores, seg, w.rank, w.segmax, mode == 1 || mode == 3, n_valid_dev != nullptr); note_launch();
     nms_scatter_kernel<<<dim3(ceil_div(max_seg, 256), n_images), 256, 0, st>>>(
         boxes, labels, seg, w.rank, w.segmax, mode, opt, w.sboxes, w.sidx, w.slab); note_launch();
+    if (max_keep > 0 && max_keep <= kLazyMaxKeep) {
+        const size_t lsmem = (sizeof(float4) + sizeof(int)) * (size_t)max_keep;
+        nms_lazy_kernel<<<n_images, 1024, lsmem, st>>>(w.sboxes, w.slab, w.sidx, seg, iou_thr, mode, max_keep, opt,
+                                                       keep_out, num_keep_out); note_launch();
+        return check_launch("vod_batched_nms(lazy)");
+    }
     nms_mask_kernel<<<dim3(words, words, n_images), 64, 0, st>>>(w.sboxes, w.slab, seg, iou_thr, mode, opt,
                                                                  words, w.mask); note_launch();
     size_t smem = sizeof(unsigned long long) * words;

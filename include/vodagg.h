@@ -82,9 +82,13 @@ int vod_flow_warp(const float *x, const float *flow, float *out, int N, int C, i
  * cosine(key_emb, ref_emb[t]) over C, softmax over t, weighted sum of ref_x.
  * replaces: the weighting half of EmbedAggregator.forward,
  *   mmtracking/mmtrack/models/aggregators/embed_aggregator.py:71-81
+ * ws (nullable): >= T*HW*4 bytes of scratch for the per-pixel cosines; with it the op runs as two
+ *   machine-filling kernels (cosine per (frame, pixel), then softmax + weighted sum), without it as one
+ *   smaller-grid kernel.
  */
 int vod_embed_weighted_sum(const float *key_emb, const float *ref_emb, const float *ref_x,
-                           float *out, int T, int C, int Cx, int HW, vod_stream_t stream);
+                           float *out, int T, int C, int Cx, int HW, void *ws, size_t ws_bytes,
+                           vod_stream_t stream);
 /* Same weighting, but the weighted operand is re-warped on the fly from the raw
  * feature memory + flows (the warped tensor is never re-read); slot `key_slot`
  * (or -1) uses key_x un-warped, as FGFA does at mmtracking/mmtrack/models/vid/fgfa.py:277-282.

@@ -201,6 +201,78 @@ embed_weighted_sum_kernel(const float *__restrict__ key_emb, const float *__rest
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Two-kernel form of the (un-fused) embed weighting, used when the shape is large enough to fill the machine:
+//   embed_cos_kernel   grid (pixel blocks, T): cos(e_t, e_k) per pixel; thread = pixel (coalesced plane rows),
+//                      4 channel groups per CTA reduced through shared memory
+//   embed_apply_kernel grid (pixel blocks, channel chunks): softmax over t recomputed per CTA from the T cosines of
+//                      its pixels (cheap), then out[c] = sum_t w_t * ref_x[t][c]
+// Every input element is read once from HBM (the key embedding is re-read per frame, from L2).
+constexpr int kEcPix = 128, kEcGroups = 4;
+
+__global__ void __launch_bounds__(kEcPix *kEcGroups)
+embed_cos_kernel(const float *__restrict__ key_emb, const float *__restrict__ ref_emb, float *__restrict__ cosv, int C,
+                 int HW) {
+    __shared__ float red[3][kEcGroups][kEcPix];
+    const int t = blockIdx.y;
+    const int pl = threadIdx.x % kEcPix, g = threadIdx.x / kEcPix;
+    const int p = blockIdx.x * kEcPix + pl;
+    const int pc = min(p, HW - 1);
+    const float *kp = key_emb + pc, *rp = ref_emb + (size_t)t * C * HW + pc;
+    float dot = 0.f, nn = 0.f, kk = 0.f;
+    const int c0 = g * (C / kEcGroups), c1 = (g == kEcGroups - 1) ? C : c0 + C / kEcGroups;
+    int c = c0;
+    for (; c + 8 <= c1; c += 8) {
+        float kv[8], rv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { kv[q] = __ldg(kp + (size_t)(c + q) * HW); rv[q] = __ldg(rp + (size_t)(c + q) * HW); }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { dot = fmaf(rv[q], kv[q], dot); nn = fmaf(rv[q], rv[q], nn); kk = fmaf(kv[q], kv[q], kk); }
+    }
+    for (; c < c1; ++c) {
+        const float kv = __ldg(kp + (size_t)c * HW), rv = __ldg(rp + (size_t)c * HW);
+        dot = fmaf(rv, kv, dot); nn = fmaf(rv, rv, nn); kk = fmaf(kv, kv, kk);
+    }
+    red[0][g][pl] = dot; red[1][g][pl] = nn; red[2][g][pl] = kk;
+    __syncthreads();
+    if (g == 0 && p < HW) {
+        float d = 0.f, n2 = 0.f, k2 = 0.f;
+#pragma unroll
+        for (int q = 0; q < kEcGroups; ++q) { d += red[0][q][pl]; n2 += red[1][q][pl]; k2 += red[2][q][pl]; }
+        cosv[(size_t)t * HW + p] = d / (sqrtf(n2) * sqrtf(k2));   // no epsilon, as the reference
+    }
+}
+
+constexpr int kEaPix = 128, kEaCh = 16;
+__global__ void __launch_bounds__(kEaPix)
+embed_apply_kernel(const float *__restrict__ cosv, const float *__restrict__ ref_x, float *__restrict__ out, int T, int Cx,
+                   int HW) {
+    extern __shared__ float wts[];   // [T][kEaPix]
+    const int pl = threadIdx.x;
+    const int p = blockIdx.x * kEaPix + pl;
+    const int pc = min(p, HW - 1);
+    float m = -INFINITY;
+    for (int t = 0; t < T; ++t) { const float v = __ldg(cosv + (size_t)t * HW + pc); wts[t * kEaPix + pl] = v; m = fmaxf(m, v); }
+    float sum = 0.f;
+    for (int t = 0; t < T; ++t) { const float e = expf(wts[t * kEaPix + pl] - m); wts[t * kEaPix + pl] = e; sum += e; }
+    for (int t = 0; t < T; ++t) wts[t * kEaPix + pl] = wts[t * kEaPix + pl] / sum;
+    if (p >= HW) return;
+    const int c0 = blockIdx.y * kEaCh, c1 = min(Cx, c0 + kEaCh);
+    for (int c = c0; c < c1; c += 2) {
+        float a0 = 0.f, a1 = 0.f;
+        const bool two = c + 1 < c1;
+        const float *x0 = ref_x + (size_t)c * HW + p;
+#pragma unroll 4
+        for (int t = 0; t < T; ++t) {
+            const float w = wts[t * kEaPix + pl];
+            a0 = fmaf(__ldg(x0 + (size_t)t * Cx * HW), w, a0);
+            if (two) a1 = fmaf(__ldg(x0 + (size_t)t * Cx * HW + HW), w, a1);
+        }
+        __stcs(out + (size_t)c * HW + p, a0);
+        if (two) __stcs(out + (size_t)(c + 1) * HW + p, a1);
+    }
+}
+
 static void flow_scale(int W, int Wf, float &s, float &inv_s) {
     double sd = (double)W / (double)Wf;  // python float scale_factor, flow.py:17
     s = (float)sd;
@@ -226,7 +298,7 @@ extern "C" int vod_flow_warp(const float *x, const float *flow, float *out, int 
 
 static int launch_embed(bool fused, const float *key_emb, const float *ref_emb, const float *ref_x,
                         const float *flow, const float *key_x, int key_slot, float *out, int T, int C, int Cx,
-                        int H, int W, int Hf, int Wf, vod_stream_t stream) {
+                        int H, int W, int Hf, int Wf, void *ws, size_t ws_bytes, vod_stream_t stream) {
     VOD_REQUIRE(key_emb && ref_emb && ref_x && out, "vod_embed_weighted_sum: null pointer");
     VOD_REQUIRE(T > 0 && C > 0 && Cx > 0 && H > 0 && W > 0, "vod_embed_weighted_sum: bad dims");
     size_t smem = sizeof(float) * ((size_t)T * kEwPix + 3 * kEwLanes * kEwPix) + (fused ? sizeof(Taps) * (size_t)T * kEwPix : 0);
@@ -234,6 +306,17 @@ static int launch_embed(bool fused, const float *key_emb, const float *ref_emb, 
     float s = 1.f, inv_s = 1.f;
     if (fused) flow_scale(W, Wf, s, inv_s);
     dim3 grid(ceil_div(H * W, kEwPix));
+    if (!fused && ws && ws_bytes >= sizeof(float) * (size_t)T * H * W && (size_t)T * kEaPix * sizeof(float) <= 200 * 1024) {
+        const int HW = H * W;
+        float *cosv = reinterpret_cast<float *>(ws);   // [T, HW] per-pixel cosines
+        embed_cos_kernel<<<dim3(ceil_div(HW, kEcPix), T), kEcPix * kEcGroups, 0, as_stream(stream)>>>(key_emb, ref_emb, cosv, C, HW);
+        note_launch();
+        const size_t sm = sizeof(float) * (size_t)T * kEaPix;
+        if (sm > 40 * 1024) cudaFuncSetAttribute(embed_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        embed_apply_kernel<<<dim3(ceil_div(HW, kEaPix), ceil_div(Cx, kEaCh)), kEaPix, sm, as_stream(stream)>>>(cosv, ref_x, out, T, Cx, HW);
+        note_launch();
+        return check_launch("vod_embed_weighted_sum(2-kernel)");
+    }
     if (fused) {
         if (smem > 40 * 1024)
             cudaFuncSetAttribute(embed_weighted_sum_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -249,8 +332,8 @@ static int launch_embed(bool fused, const float *key_emb, const float *ref_emb, 
 }
 
 extern "C" int vod_embed_weighted_sum(const float *key_emb, const float *ref_emb, const float *ref_x, float *out,
-                                      int T, int C, int Cx, int HW, vod_stream_t stream) {
-    return launch_embed(false, key_emb, ref_emb, ref_x, nullptr, nullptr, -1, out, T, C, Cx, 1, HW, 1, 1, stream);
+                                      int T, int C, int Cx, int HW, void *ws, size_t ws_bytes, vod_stream_t stream) {
+    return launch_embed(false, key_emb, ref_emb, ref_x, nullptr, nullptr, -1, out, T, C, Cx, 1, HW, 1, 1, ws, ws_bytes, stream);
 }
 
 extern "C" int vod_fgfa_warp_weighted_sum(const float *key_emb, const float *ref_emb, const float *raw_x,
@@ -258,5 +341,5 @@ extern "C" int vod_fgfa_warp_weighted_sum(const float *key_emb, const float *ref
                                           int C, int Cx, int H, int W, int Hf, int Wf, vod_stream_t stream) {
     VOD_REQUIRE(flow, "vod_fgfa_warp_weighted_sum: null flow");
     VOD_REQUIRE(key_slot < 0 || key_x, "vod_fgfa_warp_weighted_sum: key_x required with key_slot");
-    return launch_embed(true, key_emb, ref_emb, raw_x, flow, key_x, key_slot, out, T, C, Cx, H, W, Hf, Wf, stream);
+    return launch_embed(true, key_emb, ref_emb, raw_x, flow, key_x, key_slot, out, T, C, Cx, H, W, Hf, Wf, nullptr, 0, stream);
 }

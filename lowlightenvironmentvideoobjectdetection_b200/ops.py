@@ -284,8 +284,9 @@ def embed_weighted_sum(key_emb, ref_emb, ref_x):
     T, C, H, W = ref_emb.shape
     Cx = ref_x.shape[1]
     out = torch.empty((1, Cx, H, W), dtype=torch.float32, device=ref_x.device)
+    ws = _ws.get(T * H * W * 4, ref_x.device)
     _lib.call('vod_embed_weighted_sum', _lib.ptr(key_emb), _lib.ptr(ref_emb), _lib.ptr(ref_x), _lib.ptr(out), T, C,
-              Cx, H * W, _lib.stream_ptr(ref_x.device))
+              Cx, H * W, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(ref_x.device))
     return out
 
 

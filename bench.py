@@ -337,7 +337,7 @@ def main():
     torch.cuda.set_device(device)
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault('NCCL_DEBUG', 'WARN')   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # keep NCCL's banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group('nccl', device_id=device)
     # library GEMMs/convs around the path (shared FCs, embed conv) run tf32 like our own tensor-core kernels
     torch.backends.cuda.matmul.allow_tf32 = True
@@ -408,6 +408,7 @@ def main():
         # ------------------------------------------------ device-resident throughput (graph replay)
         for i in range(args.warmup):
             graph_step(0, dev_sets[i % n_sets])
+        gather_detections()   # warm the collective (communicator / channel setup is not part of a steady-state step)
         barrier()
         sampler = ClockSampler(local_rank)
         sampler.start()

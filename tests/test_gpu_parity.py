@@ -376,3 +376,61 @@ def test_cuda_graph_replay_matches_eager():
         de, le, ce = head.simple_test_device((x,), (ref_x,), rois, ref_rois, (H * 16, W * 16, 3), (1., 1., 1., 1.))
         assert int(c.item()) == int(ce.item())
         assert torch.equal(l, le) and torch.equal(d, de)
+
+
+# ------------------------------------------------------------------------------------------ full BASELINE sizes: properties
+def test_nms_sweep_sizes_exact():
+    """cfg-5 sweep extreme: 1000 proposals x 30 classes = 30000 candidates (>= mmcv's split_thr: per-class path)."""
+    g = torch.Generator().manual_seed(41)
+    n = 30000
+    boxes = clustered_boxes(g, n, 300)
+    scores = torch.rand(n, generator=g) + 1e-7 * torch.arange(n)
+    ids = torch.arange(30).repeat(1000)
+    _check_nms(boxes, scores, ids, dict(type='nms', iou_threshold=0.5))                 # split path (mode 2), mask + sweep
+    _check_nms(boxes, scores, ids, dict(type='nms', iou_threshold=0.5, split_thr=40000))  # offset trick at n = 30000
+    d0, k0 = O.batched_nms(boxes, scores, ids, dict(type='nms', iou_threshold=0.5))
+    d1, k1 = vod.batched_nms(boxes.to(DEV), scores.to(DEV), ids.to(DEV), dict(type='nms', iou_threshold=0.5, max_num=100))
+    assert torch.equal(k1.cpu(), k0[:100])                                               # bounded-survivor kernel
+
+
+def test_selsa_sweep_size_tc_vs_simt():
+    """N=1000, T=31 (M=31000), 16 heads: the tensor-core kernel (8 row tiles, no M split) against the exact SIMT kernel."""
+    g = torch.Generator(device=DEV).manual_seed(42)
+    N, M, heads = 1000, 31000, 16
+    q = torch.randn(N, 1024, device=DEV, generator=g)
+    k = torch.randn(M, 1024, device=DEV, generator=g)
+    v = torch.randn(M, 1024, device=DEV, generator=g)
+    a = ops.selsa_attention(q, k, v, heads, impl=ops.IMPL_TC)
+    b = ops.selsa_attention(q, k, v, heads, impl=ops.IMPL_SIMT)
+    assert rel_err(a, b) < FEAT_TOL
+    # linearity in V (a property that holds at any size): attention(q, k, 2v + w) == 2 attention(q,k,v) + attention(q,k,w)
+    w = torch.randn(M, 1024, device=DEV, generator=g)
+    lhs = ops.selsa_attention(q, k, 2 * v + w, heads, impl=ops.IMPL_TC)
+    rhs = 2 * a + ops.selsa_attention(q, k, w, heads, impl=ops.IMPL_TC)
+    assert rel_err(lhs, rhs) < 2e-3
+
+
+def test_temporal_roi_align_sweep_size_properties():
+    """N=1000 proposals, T=31 frames: finite, deterministic, and RoI-separable (a subset of RoIs gives the same rows)."""
+    torch.manual_seed(0)
+    g = torch.Generator().manual_seed(43)
+    m = vod.build_roi_extractor(dict(type='TemporalRoIAlign', num_most_similar_points=2, num_temporal_attention_blocks=4,
+                                     roi_layer=dict(type='RoIAlign', output_size=7, sampling_ratio=2),
+                                     out_channels=512, featmap_strides=[16])).to(DEV)
+    T, N = 31, 1000
+    ref = torch.relu(torch.randn(T, 512, 38, 63, generator=g)).to(DEV)
+    x = ref[T - 1:T]
+    rois = rpn_like_rois(g, N, 1).to(DEV)
+    out = m((x,), rois, ref_feats=(ref,))
+    assert out.shape == (N, 512, 7, 7) and bool(torch.isfinite(out).all())
+    out2 = m((x,), rois, ref_feats=(ref,))
+    assert torch.equal(out, out2)
+    sub = m((x,), rois[100:228], ref_feats=(ref,))
+    assert rel_err(sub, out[100:228]) < 1e-4     # embed conv may pick another algorithm for the smaller batch
+    # reference RoIs of all 31 frames in one launch
+    ref_rois = rpn_like_rois(g, N, T).to(DEV)
+    rf = m((ref,), ref_rois)
+    assert rf.shape == (T * N, 512, 7, 7) and bool(torch.isfinite(rf).all())
+    pick = torch.tensor([0, 999, 15000, 30999])
+    want = O.roi_align(ref.cpu(), ref_rois[pick].cpu(), 7, 1 / 16, 2, True)
+    assert rel_err(rf[pick], want) < TIGHT

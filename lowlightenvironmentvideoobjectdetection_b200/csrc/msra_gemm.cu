@@ -8,21 +8,24 @@
 // candidates are then re-scored in exact fp32 (msra_rescore_kernel, tafa.cu) so that the selected
 // locations match the fp32 reference; the bf16 GEMM is only a pre-filter.
 //
-// Persistent kernel, one CTA per SM, 576 threads; a work unit = (128-row tile, frame t):
-//   A tile   (128 RoI rows x C bf16) lives in TENSOR MEMORY, not shared memory: row r in TMEM lane r, two bf16
-//            per 32-bit column (256 columns for C = 512), written with tcgen05.st by epilogue warps 0-3 whenever
-//            the row tile changes and consumed by the TS form of tcgen05.mma.  That frees all 208 KB of shared
-//            memory for the B ring: 13 stages in flight instead of 5 (the 5-stage version was TMA-latency bound,
-//            tensor pipe 40 % active).
-//   warp 16  TMA producer: the unit's B tiles (128 locations x 64 channels per stage, SWIZZLE_128B)
-//   warp 17  MMA issuer: tcgen05.mma kind::f16 (bf16 in, fp32 accumulate), 128x128 accumulator,
-//            double buffered in TMEM (2 x 128 columns; TMEM total: 256 accumulator + 256 A = 512 columns)
-//   warps 0-15 epilogue: thread = row (four warps per TMEM lane quarter, each owning 32 of the tile's 128
-//            columns, so every SM sub-partition always has 4 epilogue warps to interleave); every similarity is packed with its location into one order-preserving 32-bit key
-//            (20 value bits | 12 location bits) and pushed through a branch-free min/max insertion network
-//            that keeps the 4 largest keys in registers -- no divergence although the 32 lanes of a warp
-//            follow 32 different rows; one 16-byte store per (row, frame, column group) at the end
-// Units are assigned to CTAs in contiguous ranges so the A tile is reloaded only when the row tile changes.
+// Persistent kernel, one CTA per SM, CTAs paired into clusters of 2 (tcgen05 cta_group::2), 576 threads per CTA;
+// a work unit = (PAIR of adjacent 128-row tiles, frame t), i.e. a 256-row x HW similarity slab:
+//   A tile   (128 RoI rows x C bf16 per CTA) lives in TENSOR MEMORY, not shared memory: row r in TMEM lane r, two
+//            bf16 per 32-bit column (256 columns for C = 512), written with tcgen05.st by epilogue warps 0-3
+//            whenever the row tile changes and consumed by the TS form of tcgen05.mma.  That frees all 208 KB of
+//            shared memory for the B ring.
+//   warp 16  TMA producer (both CTAs): each CTA loads HALF of every B stage (64 of the 128 locations x 64 channels,
+//            SWIZZLE_128B) and signals the leader's mbarrier; 26 stages x 8 KB in flight per CTA
+//   warp 17  MMA issuer (leader CTA only): tcgen05.mma.cta_group::2 kind::f16 (bf16 in, fp32 accumulate), M = 256
+//            over the pair, N = 128; accumulator double buffered in each CTA's TMEM (2 x 128 columns; TMEM total:
+//            256 accumulator + 256 A = 512 columns); commits are multicast to both CTAs' barriers
+//   warps 0-15 epilogue (both CTAs, own 128 rows): thread = row (four warps per TMEM lane quarter, each owning 32 of
+//            the tile's 128 columns); every similarity is packed with its location into one order-preserving 32-bit
+//            key (20 value bits | 12 location bits) and pushed through a branch-free min/max insertion network that
+//            keeps the 4 largest keys in registers -- no divergence although the 32 lanes of a warp follow 32
+//            different rows; one 16-byte store per (row, frame, column group) at the end
+// Units are assigned to clusters in contiguous ranges so the A tile is reloaded only when the row-tile pair changes.
+// History (profiles/r01_bench_history.md): 5-stage smem-A 1-CTA 1108 us -> TMEM-A 13-stage 1-CTA 641 us -> CTA pair 555 us.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -31,99 +34,109 @@
 
 namespace vod {
 
-constexpr int kMgBM = 128;           // rows per tile
+constexpr int kMgBM = 128;           // rows per CTA (a CTA pair covers 256)
 constexpr int kMgBN = 128;           // locations per accumulator tile
 constexpr int kMgSlice = 64;         // bf16 elements per 128-byte K slice
 constexpr int kMgMaxSlices = 8;      // C <= 512
-constexpr int kMgStages = 13;
-constexpr int kMgTile = 128 * 128;   // bytes of one [128 x 128 B] slice tile
+constexpr int kMgHalf = 64 * 128;    // bytes of one CTA's half of a B stage: 64 locations x 128 B
+constexpr int kMgStages = 26;        // 26 x 8 KB = 208 KB of B in flight per CTA
 constexpr int kMgEpiWarps = 16;
 constexpr int kMgThreads = (kMgEpiWarps + 2) * 32;
-constexpr int kMgSmem = kMgStages * kMgTile + 1024;
+constexpr int kMgSmem = kMgStages * kMgHalf + 1024;
 constexpr uint32_t kMgACol = 256;    // first TMEM column of the A tile
 
 struct MgParams {
     uint32_t *cand; // [NP, T, kMsraCand] packed keys: (ordered value & 0xFFFFF000) | location
     const __nv_bfloat16 *a_rows;  // [NP, C] unit-norm RoI rows
     int NP, T, HW, nslices, row_tiles, ntiles;  // ntiles = ceil(HW / 128)
-    int units;      // row_tiles * T
+    int units;      // ceil(row_tiles / 2) * T  (a unit = a PAIR of row tiles x one frame)
 };
 
-__global__ void __launch_bounds__(kMgThreads, 1)
+// CTA pair (cluster of 2, cta_group::2): the two CTAs own two adjacent 128-row tiles, i.e. one 256 x 128 MMA tile.
+// Each CTA keeps its own A rows in its own TMEM and TMA-loads only HALF of every B stage (64 of the 128 locations);
+// the leader CTA (rank 0) issues tcgen05.mma.cta_group::2 for both.  A single-CTA tcgen05.mma runs at half the
+// tensor-core rate of a CTA pair (measured: 1.09 PFLOP/s ceiling for the 1-CTA version of this kernel), and the pair
+// also halves the L2 -> shared-memory operand traffic.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMgThreads, 1)
 msra_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_b, const MgParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t *sB = smem;                               // [stages][16 KB]
+    uint8_t *sB = smem;                               // [stages][8 KB]
     __shared__ uint64_t a_full, b_full[kMgStages], b_empty[kMgStages], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // contiguous unit range of this CTA
-    const int per = p.units / gridDim.x, rem = p.units % gridDim.x;
-    const int u0 = blockIdx.x * per + min((int)blockIdx.x, rem);
-    const int u1 = u0 + per + ((int)blockIdx.x < rem ? 1 : 0);
+    const uint32_t crank = tc::cluster_ctarank();
+    // contiguous unit range of this CLUSTER (both CTAs walk the same units; the CTA rank picks the row tile)
+    const int ncl = gridDim.x >> 1, cl = blockIdx.x >> 1;
+    const int per = p.units / ncl, rem = p.units % ncl;
+    const int u0 = cl * per + min(cl, rem);
+    const int u1 = u0 + per + (cl < rem ? 1 : 0);
 
     if (threadIdx.x == 0) {
-        tc::mbar_init(&a_full, 128);
+        // leader-side barriers are also initialised in the peer (unused there) to keep the code symmetric
+        tc::mbar_init(&a_full, 8);                      // 4 A-writer warps in each CTA of the pair
         for (int i = 0; i < kMgStages; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], kMgEpiWarps * 32); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 2 * kMgEpiWarps); }
         tc::fence_barrier_init();
     }
-    if (warp == kMgEpiWarps + 1) tc::tmem_alloc(&tmem_slot, 512);
+    if (warp == kMgEpiWarps + 1) tc::tmem_alloc_2sm(&tmem_slot, 512);
     tc::tcgen05_fence_before();
     __syncthreads();
+    tc::cluster_sync_all();   // both CTAs' barriers and TMEM exist before anything crosses the pair
     tc::tcgen05_fence_after();
     const uint32_t tmem = tmem_slot;
 
     if (warp == kMgEpiWarps) {
-        // ------------------------------------------------------------------ TMA producer
+        // ------------------------------------------------------------------ TMA producer (both CTAs: own half of B)
         if (tc::elect_one()) {
             tc::tma_prefetch_desc(&tm_b);
-            long it = 0;  // global B-stage counter
+            uint32_t st = 0, ph = 0;
             for (int u = u0; u < u1; ++u) {
-                const int t = u % p.T;
+                const int row0 = (u % p.T) * p.HW + (int)crank * (kMgBN / 2);
                 for (int nt = 0; nt < p.ntiles; ++nt) {
-                    for (int s = 0; s < p.nslices; ++s, ++it) {
-                        const int st = (int)(it % kMgStages);
-                        const uint32_t ph = (uint32_t)((it / kMgStages) & 1);
-                        tc::mbar_wait(&b_empty[st], ph ^ 1);
-                        tc::mbar_arrive_expect_tx(&b_full[st], kMgTile);
-                        tc::tma_load_2d(sB + st * kMgTile, &tm_b, &b_full[st], s * kMgSlice, t * p.HW + nt * kMgBN);
+                    for (int s = 0; s < p.nslices; ++s) {
+                        tc::mbar_wait(&b_empty[st], ph ^ 1);   // the pair's MMAs have consumed this stage (multicast commit)
+                        if (crank == 0) tc::mbar_arrive_expect_tx(&b_full[st], 2 * kMgHalf);   // both halves land on the leader's barrier
+                        tc::tma_load_2d_2sm(sB + st * kMgHalf, &tm_b, &b_full[st], s * kMgSlice, row0 + nt * kMgBN);
+                        if (++st == kMgStages) { st = 0; ph ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == kMgEpiWarps + 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc = tc::umma_idesc(tc::kFmtBF16, kMgBM, kMgBN);
-        int cur_rt = -1, a_loads = 0;
-        long it = 0, tile_it = 0;
-        for (int u = u0; u < u1; ++u) {
-            const int rt = u / p.T;
-            if (rt != cur_rt) {
-                tc::mbar_wait(&a_full, a_loads & 1);   // epilogue warps 0-3 have written this row tile's A into TMEM
-                tc::tcgen05_fence_after();
-                cur_rt = rt;
-                ++a_loads;
-            }
-            for (int nt = 0; nt < p.ntiles; ++nt, ++tile_it) {
-                const int buf = (int)(tile_it & 1);
-                tc::mbar_wait(&acc_empty[buf], (uint32_t)(((tile_it >> 1) & 1) ^ 1));
-                tc::tcgen05_fence_after();
-                for (int s = 0; s < p.nslices; ++s, ++it) {
-                    const int st = (int)(it % kMgStages);
-                    tc::mbar_wait(&b_full[st], (uint32_t)((it / kMgStages) & 1));
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (crank == 0) {
+            constexpr uint32_t idesc = tc::umma_idesc(tc::kFmtBF16, 2 * kMgBM, kMgBN);   // M = 256 over the pair
+            int cur_pr = -1;
+            uint32_t a_loads = 0, st = 0, ph = 0, tile = 0;
+            for (int u = u0; u < u1; ++u) {
+                const int pr = u / p.T;
+                if (pr != cur_pr) {
+                    tc::mbar_wait(&a_full, a_loads & 1);   // both CTAs have written their A rows into their TMEM
                     tc::tcgen05_fence_after();
-                    if (tc::elect_one()) {
-                        const uint32_t b0 = tc::smem_u32(sB + st * kMgTile);
+                    cur_pr = pr;
+                    ++a_loads;
+                }
+                for (int nt = 0; nt < p.ntiles; ++nt, ++tile) {
+                    const uint32_t buf = tile & 1;
+                    tc::mbar_wait(&acc_empty[buf], ((tile >> 1) & 1) ^ 1);   // drained by the epilogue warps of BOTH CTAs
+                    tc::tcgen05_fence_after();
+                    for (int s = 0; s < p.nslices; ++s) {
+                        tc::mbar_wait(&b_full[st], ph);
+                        tc::tcgen05_fence_after();
+                        if (tc::elect_one()) {
+                            const uint32_t b0 = tc::smem_u32(sB + st * kMgHalf);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)   // 16 bf16 of K per MMA: 8 TMEM columns of A, 32 bytes of the B slice
-                            tc::umma_f16_ts(tmem + buf * kMgBN, tmem + kMgACol + s * 32 + k * 8,
-                                            tc::umma_desc_k_sw128(b0 + k * 32), idesc, (s | k) != 0);
-                        tc::umma_commit(&b_empty[st]);
-                        if (s == p.nslices - 1) tc::umma_commit(&acc_full[buf]);
+                            for (int k = 0; k < 4; ++k)   // 16 bf16 of K per MMA: 8 TMEM columns of A, 32 bytes of the B slice
+                                tc::umma_f16_ts_2sm(tmem + buf * kMgBN, tmem + kMgACol + s * 32 + k * 8,
+                                                    tc::umma_desc_k_sw128(b0 + k * 32), idesc, (s | k) != 0);
+                            tc::umma_commit_2sm(&b_empty[st], (uint16_t)0x3);                       // frees the stage in both CTAs
+                            if (s == p.nslices - 1) tc::umma_commit_2sm(&acc_full[buf], (uint16_t)0x3);   // wakes both epilogues
+                        }
+                        __syncwarp();
+                        if (++st == kMgStages) { st = 0; ph ^= 1; }
                     }
-                    __syncwarp();
                 }
             }
         }
@@ -131,10 +144,10 @@ msra_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_b, const MgParams p
         // ------------------------------------------------------------------ epilogue: running top-4 keys per row
         const int quarter = warp & 3, grp = warp >> 2;   // TMEM lane quarter, 32-column group of the tile
         const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16) + grp * 32;
-        long tile_it = 0;
+        uint32_t tile_it = 0;
         int cur_rt = -1;
         for (int u = u0; u < u1; ++u) {
-            const int rt = u / p.T, t = u % p.T;
+            const int rt = (u / p.T) * 2 + (int)crank, t = u % p.T;
             if (rt != cur_rt) {
                 cur_rt = rt;
                 if (warp < 4) {
@@ -160,24 +173,29 @@ msra_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_b, const MgParams p
                     }
                     tc::tmem_st_wait();
                     tc::tcgen05_fence_before();
-                    tc::mbar_arrive(&a_full);
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive_cluster(&a_full, 0);   // leader's barrier
                 }
             }
             uint32_t k0 = 0, k1 = 0, k2 = 0, k3 = 0;   // descending; 0 = "nothing yet" (below every real key)
             for (int nt = 0; nt < p.ntiles; ++nt, ++tile_it) {
-                const int buf = (int)(tile_it & 1);
-                tc::mbar_wait(&acc_full[buf], (uint32_t)((tile_it >> 1) & 1));
+                const uint32_t buf = tile_it & 1;
+                tc::mbar_wait(&acc_full[buf], (tile_it >> 1) & 1);
                 tc::tcgen05_fence_after();
                 uint32_t ra[32];
                 tc::tmem_ld_32x32(tl + buf * kMgBN, ra);
                 tc::tmem_ld_wait();
                 tc::tcgen05_fence_before();
-                tc::mbar_arrive(&acc_empty[buf]);       // values are in registers: the MMA may overwrite the buffer
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive_cluster(&acc_empty[buf], 0);   // values are in registers: the pair's MMA may overwrite
                 const uint32_t base = (uint32_t)(nt * kMgBN + grp * 32);
                 const int nvalid = p.HW - (int)base;    // columns of this frame that exist (tail tile only)
                 auto push = [&](uint32_t bits, uint32_t loc, bool ok) {
-                    // order-preserving float -> uint, top 20 bits kept, location in the low 12 bits
-                    const uint32_t ord = bits ^ ((uint32_t)((int32_t)bits >> 31) | 0x80000000u);
+                    // |cos| <= 1, so sim + 2 lies in [1, 3]: a positive float whose bit pattern orders like an unsigned
+                    // integer (one FADD instead of a sign-dependent transform).  Top 20 bits of the word kept (11
+                    // mantissa bits: the value resolution of ~1e-3 is covered by the re-score margin), location in the
+                    // low 12 bits; 4-deep branch-free insertion = 9 instructions per similarity.
+                    const uint32_t ord = __float_as_uint(__uint_as_float(bits) + 2.0f);
                     uint32_t key = ok ? ((ord & 0xFFFFF000u) | loc) : 0u;
                     uint32_t hi;
                     hi = max(k0, key); key = min(k0, key); k0 = hi;
@@ -200,7 +218,8 @@ msra_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_b, const MgParams p
     }
     tc::tcgen05_fence_before();
     __syncthreads();
-    if (warp == kMgEpiWarps + 1) tc::tmem_dealloc(tmem, 512);
+    tc::cluster_sync_all();   // neither CTA may free TMEM / exit while the pair's MMAs or remote arrivals are pending
+    if (warp == kMgEpiWarps + 1) tc::tmem_dealloc_2sm(tmem, 512);
 }
 
 bool msra_gemm_supported(int NP, int C, int T, int HW) {
@@ -214,16 +233,16 @@ int msra_launch_gemm_topk(const void *roi_unit_bf16, const void *ref_unit_bf16, 
     CUtensorMap tb;
     int rc;
     if ((reinterpret_cast<uintptr_t>(roi_unit_bf16) & 15) != 0) return fail(VOD_E_BADARG, "msra_gemm: A rows must be 16-byte aligned");
-    if ((rc = make_tmap_2d_sw128(&tb, ref_unit_bf16, 2, (uint64_t)T * HW, C, (uint64_t)C * 2, kMgBN))) return rc;
+    if ((rc = make_tmap_2d_sw128(&tb, ref_unit_bf16, 2, (uint64_t)T * HW, C, (uint64_t)C * 2, kMgBN / 2))) return rc;   // each CTA of a pair loads 64 locations
     MgParams p;
     p.cand = cand; p.NP = NP; p.T = T; p.HW = HW;
     p.a_rows = reinterpret_cast<const __nv_bfloat16 *>(roi_unit_bf16);
     p.nslices = C / kMgSlice;
     p.row_tiles = ceil_div(NP, kMgBM);
     p.ntiles = ceil_div(HW, kMgBN);
-    p.units = p.row_tiles * T;
+    p.units = ceil_div(p.row_tiles, 2) * T;
     cudaFuncSetAttribute(msra_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMgSmem);
-    const int grid = min(kNumSMs, p.units);
+    const int grid = 2 * min(kNumSMs / 2, p.units);   // clusters of 2 CTAs
     msra_gemm_topk_kernel<<<grid, kMgThreads, kMgSmem, st>>>(tb, p); note_launch();
     return check_launch("msra_gemm_topk");
 }

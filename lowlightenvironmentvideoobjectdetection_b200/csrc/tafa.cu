@@ -294,8 +294,8 @@ msra_rescore_kernel(const float *__restrict__ roi, const float *__restrict__ ref
         const float *ref_t = ref + (size_t)t * HW * C;
         // decode this frame's candidate keys (lane j < KC holds candidate j)
         uint32_t key = lane < KC ? cand[((size_t)row * T + t) * KC + lane] : 0u;
-        const uint32_t ord = key & 0xFFFFF000u;
-        const float approx = key ? __uint_as_float((ord & 0x80000000u) ? (ord ^ 0x80000000u) : ~ord) : -INFINITY;
+        // key = bits(sim + 2.0f) & 0xFFFFF000 | location (msra_gemm.cu); a NaN similarity keeps a NaN pattern
+        const float approx = key ? __uint_as_float(key & 0xFFFFF000u) - 2.0f : -INFINITY;
         // k-th largest approximate similarity (k <= 4): repeatedly remove the maximum
         float kth = approx;
         {

@@ -78,6 +78,56 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m
         : "memory");
 }
 
+// ------------------------------------------------------------------------------ clusters / CTA pairs
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar, uint32_t cta) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// cta_group::2 TMA load: issued by BOTH CTAs of a pair, each into its own shared memory; the transaction bytes of
+// both are credited to the mbarrier of the pair's even ("leader") CTA (peer bit of the barrier address cleared).
+__device__ __forceinline__ void tma_load_2d_2sm(void *smem_dst, const CUtensorMap *m, uint64_t *leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(leader_bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+// TMEM allocation for a CTA pair (executed by one full warp in EACH CTA of the pair)
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t *smem_slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// 2-CTA MMA (M = 256: 128 rows per CTA, each CTA supplies its half of A (TMEM) and half of B's N (shared memory));
+// issued by ONE thread of the leader CTA only.
+__device__ __forceinline__ void umma_f16_ts_2sm(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// commit of the pair's MMAs: arrives on the mbarrier at the same offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_2sm(uint64_t *bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask)
+                 : "memory");
+}
+
 // ------------------------------------------------------------------------------ TMEM
 // Executed by ONE full warp. ncols: power of two in [32, 512]. The base address lands in *smem_slot.
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_slot, uint32_t ncols) {

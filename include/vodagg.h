@@ -136,7 +136,7 @@ int vod_msra_topk_sample(const float *roi_feats, const float *ref_nhwc, const fl
 
 /* The tensor-core half of (4) alone (what vod_msra_topk_sample runs before its fp32 re-score): unit-norm bf16
  * rows roi_unit [NP, C] x ref_unit [T*HW, C] -> cand_out [NP, T, 16] packed keys
- * (bits(similarity + 2.0f) & 0xFFFFF000) | location: the 4 best of each of the four 32-column
+ * round((1.5 + similarity) * 2^11) << 12 | location: the 4 best of each of the four 32-column
  * groups of the 128-location tiles; 0 = empty slot.  Exposed so the GEMM can be profiled / roofline-timed on
  * its own and its candidate recall tested.
  */

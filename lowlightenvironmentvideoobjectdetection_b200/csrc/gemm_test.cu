@@ -49,6 +49,25 @@ int make_tmap_2d_sw128(CUtensorMap *map, const void *base, int elem_bytes, uint6
     return VOD_OK;
 }
 
+// bf16 [rows, C] matrix seen as (64 channels, rows, C/64 K-slices): one box = box_rows x 128 B x box_slices, landing in
+// shared memory as box_slices consecutive K-major SWIZZLE_128B tiles (slice stride 128 B < row stride: dimensions may be
+// listed in any order, only the innermost one must be contiguous).
+int make_tmap_kslices_sw128(CUtensorMap *map, const void *base, uint64_t rows, uint64_t C, uint32_t box_rows, uint32_t box_slices) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return fail(VOD_E_LAUNCH, "cuTensorMapEncodeTiled entry point unavailable");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || C % 64 != 0)
+        return fail(VOD_E_BADARG, "TMA operand needs a 16-byte aligned base and C %% 64 == 0");
+    cuuint64_t dims[3] = {64, rows, C / 64};
+    cuuint64_t strides[2] = {C * 2, 128};
+    cuuint32_t box[3] = {64, box_rows, box_slices};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(VOD_E_LAUNCH, "cuTensorMapEncodeTiled (k-slices) failed (%d)", (int)r);
+    return VOD_OK;
+}
+
 constexpr int kGtStages = 4;
 constexpr int kGtTileBytes = 128 * 128;  // 128 rows x 128 B
 constexpr int kGtThreads = 192;

@@ -21,7 +21,7 @@
 //            256 accumulator + 256 A = 512 columns); commits are multicast to both CTAs' barriers
 //   warps 0-15 epilogue (both CTAs, own 128 rows): thread = row (four warps per TMEM lane quarter, each owning 32 of
 //            the tile's 128 columns); every similarity is packed with its location into one order-preserving 32-bit
-//            key (20 value bits | 12 location bits) and pushed through a branch-free min/max insertion network that
+//            key (20 value bits | 12 location bits, built on the FMA pipe) and pushed through a branch-free min/max insertion network that
 //            keeps the 4 largest keys in registers -- no divergence although the 32 lanes of a warp follow 32
 //            different rows; one 16-byte store per (row, frame, column group) at the end
 // Units are assigned to clusters in contiguous ranges so the A tile is reloaded only when the row-tile pair changes.
@@ -38,18 +38,22 @@ constexpr int kMgBM = 128;           // rows per CTA (a CTA pair covers 256)
 constexpr int kMgBN = 128;           // locations per accumulator tile
 constexpr int kMgSlice = 64;         // bf16 elements per 128-byte K slice
 constexpr int kMgMaxSlices = 8;      // C <= 512
-constexpr int kMgHalf = 64 * 128;    // bytes of one CTA's half of a B stage: 64 locations x 128 B
-constexpr int kMgStages = 26;        // 26 x 8 KB = 208 KB of B in flight per CTA
+constexpr int kMgHalf = 64 * 128;    // bytes of one K slice of a CTA's half of B: 64 locations x 128 B
+constexpr int kMgSPS = 8;            // K slices per stage = per TMA instruction (3-D box): few, large bulk copies --
+                                     // with one 8 KB copy per instruction the TMA unit, not the tensor pipe, set the pace
+constexpr int kMgStageBytes = kMgSPS * kMgHalf;
+constexpr int kMgStages = 3;         // 6 x 32 KB = 192 KB of B in flight per CTA
 constexpr int kMgEpiWarps = 16;
 constexpr int kMgThreads = (kMgEpiWarps + 2) * 32;
-constexpr int kMgSmem = kMgStages * kMgHalf + 1024;
+constexpr int kMgSmem = kMgStages * kMgStageBytes + 1024;
 constexpr uint32_t kMgACol = 256;    // first TMEM column of the A tile
 
 struct MgParams {
-    uint32_t *cand; // [NP, T, kMsraCand] packed keys: (ordered value & 0xFFFFF000) | location
+    uint32_t *cand; // [NP, T, kMsraCand] packed keys: round((1.5 + sim) * 2^11) << 12 | location
     const __nv_bfloat16 *a_rows;  // [NP, C] unit-norm RoI rows
-    int NP, T, HW, nslices, row_tiles, ntiles;  // ntiles = ceil(HW / 128)
+    int NP, T, HW, nslices, nstg, row_tiles, ntiles;  // ntiles = ceil(HW / 128), nstg = ceil(nslices / kMgSPS)
     int units;      // ceil(row_tiles / 2) * T  (a unit = a PAIR of row tiles x one frame)
+    int k4096, kone;   // the constants 4096 and 1, opaque to the compiler (see the epilogue's key packing)
 };
 
 // CTA pair (cluster of 2, cta_group::2): the two CTAs own two adjacent 128-row tiles, i.e. one 256 x 128 MMA tile.
@@ -61,7 +65,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMgThreads, 1)
 msra_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_b, const MgParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t *sB = smem;                               // [stages][8 KB]
+    uint8_t *sB = smem;                               // [stages][slices per stage][8 KB]
     __shared__ uint64_t a_full, b_full[kMgStages], b_empty[kMgStages], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_slot;
 
@@ -95,10 +99,11 @@ msra_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_b, const MgParams p
             for (int u = u0; u < u1; ++u) {
                 const int row0 = (u % p.T) * p.HW + (int)crank * (kMgBN / 2);
                 for (int nt = 0; nt < p.ntiles; ++nt) {
-                    for (int s = 0; s < p.nslices; ++s) {
+                    for (int g = 0; g < p.nstg; ++g) {
                         tc::mbar_wait(&b_empty[st], ph ^ 1);   // the pair's MMAs have consumed this stage (multicast commit)
-                        if (crank == 0) tc::mbar_arrive_expect_tx(&b_full[st], 2 * kMgHalf);   // both halves land on the leader's barrier
-                        tc::tma_load_2d_2sm(sB + st * kMgHalf, &tm_b, &b_full[st], s * kMgSlice, row0 + nt * kMgBN);
+                        if (crank == 0) tc::mbar_arrive_expect_tx(&b_full[st], 2 * kMgStageBytes);   // both halves land on the leader's barrier
+                        // box = 64 channels x 64 locations x kMgSPS slices (slices past C are zero-filled, never read)
+                        tc::tma_load_3d_2sm(sB + st * kMgStageBytes, &tm_b, &b_full[st], 0, row0 + nt * kMgBN, g * kMgSPS);
                         if (++st == kMgStages) { st = 0; ph ^= 1; }
                     }
                 }
@@ -122,17 +127,21 @@ msra_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_b, const MgParams p
                     const uint32_t buf = tile & 1;
                     tc::mbar_wait(&acc_empty[buf], ((tile >> 1) & 1) ^ 1);   // drained by the epilogue warps of BOTH CTAs
                     tc::tcgen05_fence_after();
-                    for (int s = 0; s < p.nslices; ++s) {
+                    for (int g = 0; g < p.nstg; ++g) {
                         tc::mbar_wait(&b_full[st], ph);
                         tc::tcgen05_fence_after();
                         if (tc::elect_one()) {
-                            const uint32_t b0 = tc::smem_u32(sB + st * kMgHalf);
+                            const int ns = min(kMgSPS, p.nslices - g * kMgSPS);
+                            for (int j = 0; j < ns; ++j) {
+                                const int s = g * kMgSPS + j;
+                                const uint32_t b0 = tc::smem_u32(sB + st * kMgStageBytes + j * kMgHalf);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)   // 16 bf16 of K per MMA: 8 TMEM columns of A, 32 bytes of the B slice
-                                tc::umma_f16_ts_2sm(tmem + buf * kMgBN, tmem + kMgACol + s * 32 + k * 8,
-                                                    tc::umma_desc_k_sw128(b0 + k * 32), idesc, (s | k) != 0);
+                                for (int k = 0; k < 4; ++k)   // 16 bf16 of K per MMA: 8 TMEM columns of A, 32 bytes of the B slice
+                                    tc::umma_f16_ts_2sm(tmem + buf * kMgBN, tmem + kMgACol + s * 32 + k * 8,
+                                                        tc::umma_desc_k_sw128(b0 + k * 32), idesc, (s | k) != 0);
+                            }
                             tc::umma_commit_2sm(&b_empty[st], (uint16_t)0x3);                       // frees the stage in both CTAs
-                            if (s == p.nslices - 1) tc::umma_commit_2sm(&acc_full[buf], (uint16_t)0x3);   // wakes both epilogues
+                            if (g == p.nstg - 1) tc::umma_commit_2sm(&acc_full[buf], (uint16_t)0x3);   // wakes both epilogues
                         }
                         __syncwarp();
                         if (++st == kMgStages) { st = 0; ph ^= 1; }
@@ -190,13 +199,17 @@ msra_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_b, const MgParams p
                 if (lane == 0) tc::mbar_arrive_cluster(&acc_empty[buf], 0);   // values are in registers: the pair's MMA may overwrite
                 const uint32_t base = (uint32_t)(nt * kMgBN + grp * 32);
                 const int nvalid = p.HW - (int)base;    // columns of this frame that exist (tail tile only)
-                auto push = [&](uint32_t bits, uint32_t loc, bool ok) {
-                    // |cos| <= 1, so sim + 2 lies in [1, 3]: a positive float whose bit pattern orders like an unsigned
-                    // integer (one FADD instead of a sign-dependent transform).  Top 20 bits of the word kept (11
-                    // mantissa bits: the value resolution of ~1e-3 is covered by the re-score margin), location in the
-                    // low 12 bits; 4-deep branch-free insertion = 9 instructions per similarity.
-                    const uint32_t ord = __float_as_uint(__uint_as_float(bits) + 2.0f);
-                    uint32_t key = ok ? ((ord & 0xFFFFF000u) | loc) : 0u;
+                auto push = [&](uint32_t bits, uint32_t j, bool ok) {
+                    // |cos| <= 1 (+ bf16 noise): t = sim + 6145.5 lies in [4096, 8192), where one ulp is 2^-11, so the FADD
+                    // itself rounds the similarity to 11 fractional bits and bits(t) = 0x45800000 + (2049.5 + sim) * 2^11.
+                    // Multiplying the word by 4096 (mod 2^32) drops the constant part and leaves (1.5 + sim) * 2^23, a
+                    // positive, order-preserving 20-bit value field above 12 free location bits.  FADD and both IMADs run
+                    // on the FMA pipe; the ALU pipe -- the busy one -- only sees the 7 min/max of the insertion network.
+                    // (The multipliers 4096 and 1 are kernel parameters so that ptxas cannot turn the IMADs into ALU ops.)
+                    // A NaN similarity gives the canonical 0x7FFFFFFF -> value field 0xFFFFF: ranked first, like torch.topk.
+                    const uint32_t w = __float_as_uint(__uint_as_float(bits) + 6145.5f);
+                    uint32_t key = tc::mad_lo(tc::mad_lo(w, (uint32_t)p.k4096, base), (uint32_t)p.kone, j);
+                    if (!ok) key = 0u;
                     uint32_t hi;
                     hi = max(k0, key); key = min(k0, key); k0 = hi;
                     hi = max(k1, key); key = min(k1, key); k1 = hi;
@@ -205,10 +218,10 @@ msra_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_b, const MgParams p
                 };
                 if (nvalid >= 32) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) push(ra[j], base + j, true);
+                    for (int j = 0; j < 32; ++j) push(ra[j], j, true);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) push(ra[j], base + j, j < nvalid);
+                    for (int j = 0; j < 32; ++j) push(ra[j], j, j < nvalid);
                 }
             }
             const int row = rt * kMgBM + quarter * 32 + lane;
@@ -233,14 +246,17 @@ int msra_launch_gemm_topk(const void *roi_unit_bf16, const void *ref_unit_bf16, 
     CUtensorMap tb;
     int rc;
     if ((reinterpret_cast<uintptr_t>(roi_unit_bf16) & 15) != 0) return fail(VOD_E_BADARG, "msra_gemm: A rows must be 16-byte aligned");
-    if ((rc = make_tmap_2d_sw128(&tb, ref_unit_bf16, 2, (uint64_t)T * HW, C, (uint64_t)C * 2, kMgBN / 2))) return rc;   // each CTA of a pair loads 64 locations
+    // each CTA of a pair loads 64 locations x kMgSPS K slices per instruction
+    if ((rc = make_tmap_kslices_sw128(&tb, ref_unit_bf16, (uint64_t)T * HW, C, kMgBN / 2, kMgSPS))) return rc;
     MgParams p;
     p.cand = cand; p.NP = NP; p.T = T; p.HW = HW;
     p.a_rows = reinterpret_cast<const __nv_bfloat16 *>(roi_unit_bf16);
     p.nslices = C / kMgSlice;
+    p.nstg = ceil_div(p.nslices, kMgSPS);
     p.row_tiles = ceil_div(NP, kMgBM);
     p.ntiles = ceil_div(HW, kMgBN);
     p.units = ceil_div(p.row_tiles, 2) * T;
+    p.k4096 = 4096; p.kone = 1;
     cudaFuncSetAttribute(msra_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMgSmem);
     const int grid = 2 * min(kNumSMs / 2, p.units);   // clusters of 2 CTAs
     msra_gemm_topk_kernel<<<grid, kMgThreads, kMgSmem, st>>>(tb, p); note_launch();

@@ -294,8 +294,9 @@ msra_rescore_kernel(const float *__restrict__ roi, const float *__restrict__ ref
         const float *ref_t = ref + (size_t)t * HW * C;
         // decode this frame's candidate keys (lane j < KC holds candidate j)
         uint32_t key = lane < KC ? cand[((size_t)row * T + t) * KC + lane] : 0u;
-        // key = bits(sim + 2.0f) & 0xFFFFF000 | location (msra_gemm.cu); a NaN similarity keeps a NaN pattern
-        const float approx = key ? __uint_as_float(key & 0xFFFFF000u) - 2.0f : -INFINITY;
+        // key = round((1.5 + sim) * 2^11) << 12 | location (msra_gemm.cu); a NaN similarity has the value field 0xFFFFF
+        const float approx = !key ? -INFINITY : key >= 0xFFFFF000u ? __int_as_float(0x7fc00000)
+                                              : (float)(key >> 12) * (1.0f / 2048.0f) - 1.5f;
         // k-th largest approximate similarity (k <= 4): repeatedly remove the maximum
         float kth = approx;
         {

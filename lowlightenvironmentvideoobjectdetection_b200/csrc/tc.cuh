@@ -102,6 +102,18 @@ __device__ __forceinline__ void tma_load_2d_2sm(void *smem_dst, const CUtensorMa
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(leader_bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_2sm(void *smem_dst, const CUtensorMap *m, uint64_t *leader_bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(leader_bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// 32-bit multiply-add kept as an IMAD (FMA pipe) -- use with a multiplier the compiler cannot see through
+__device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 // TMEM allocation for a CTA pair (executed by one full warp in EACH CTA of the pair)
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t *smem_slot, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
@@ -235,5 +247,6 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
 // 128-byte swizzle.  Out-of-bounds box elements are zero-filled (tile tails need no special casing).
 int make_tmap_2d_sw128(CUtensorMap *map, const void *base, int elem_bytes, uint64_t rows, uint64_t cols,
                        uint64_t row_stride_bytes, uint32_t box_rows);
+int make_tmap_kslices_sw128(CUtensorMap *map, const void *base, uint64_t rows, uint64_t C, uint32_t box_rows, uint32_t box_slices);
 
 }  // namespace vod

@@ -491,7 +491,10 @@ def main():
     if rank == 0 and not args.no_roofline:
         with torch.no_grad():
             kr = kernel_rooflines(cfg, device, peaks)
-        single = {k: v for k, v in kr.items() if k not in ('msra_topk_sample', 'roi_align_refs_nchw_out')}   # composites / alternates
+        # the dominant kernel of THE TIMED STEP: composites (msra_topk_sample), alternates (NCHW-output RoIAlign) and the
+        # kernels of the other detectors' shapes (FGFA/DFF T=31, RPN NMS), which the table also lists, do not qualify
+        in_step = ('roi_align_refs', 'msra_gemm_topk_kernel', 'tafa_weighted_sum', 'selsa_attention', 'batched_nms_rcnn')
+        single = {k: v for k, v in kr.items() if k in in_step}
         dom = max(single, key=lambda k: single[k]['seconds'])
         r = kr[dom]
         result['roofline'] = {'kernel': dom, 'bound': r['bound'], 'achieved': r['achieved'], 'peak': r['peak'], 'unit': r['unit'],

@@ -1,21 +1,25 @@
-import os, sys, torch
+"""Times the msra similarity GEMM alone and the whole msra_topk_sample op (GEMM + 2 norms + re-score) at cfg-3 size."""
+import sys, torch
 sys.path.insert(0, '.')
 from lowlightenvironmentvideoobjectdetection_b200 import ops
-N, T, C, HW = 300, 15, 512, 38 * 63
+N, T, C, H, W = 300, 15, 512, 38, 63
+HW = H * W
 g = torch.Generator(device='cuda').manual_seed(0)
-ru = torch.nn.functional.normalize(torch.rand(N * 49, C, device='cuda', generator=g), dim=1).bfloat16()
-unit = torch.nn.functional.normalize(torch.rand(T * HW, C, device='cuda', generator=g), dim=1).bfloat16()
-def t(probe):
-    os.environ['VOD_MG_PROBE'] = str(probe & ~8)
-    for _ in range(3): ops.msra_gemm_candidates(ru, unit, T)
-    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-    torch.cuda.synchronize(); e0.record()
-    for _ in range(10): ops.msra_gemm_candidates(ru, unit, T)
-    e1.record(); torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) * 100
-    print('probe', probe, '%.1f us  %.0f TFLOP/s  (%.0f clk @1.965GHz)' % (us, 2.0 * N * 49 * T * HW * C / us / 1e6, us * 1965), flush=True)
-    if probe & 8:
-        os.environ['VOD_MG_PROBE'] = str(probe)
-        ops.msra_gemm_candidates(ru, unit, T); torch.cuda.synchronize()
-for pr in sys.argv[1:] or ['0', '1']:
-    t(int(pr))
+ref = torch.relu(torch.randn(T, C, H, W, device='cuda', generator=g))
+rows = torch.relu(torch.randn(N * 49, C, device='cuda', generator=g))
+ref_nhwc, norm, unit = ops.to_nhwc(ref, want_norm=True, want_unit_bf16=True)
+ru = torch.nn.functional.normalize(rows, dim=1).bfloat16()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+def timeit(fn, iters=10):
+    for _ in range(3): fn()
+    tot = 0.0
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / iters * 1e3
+tg = timeit(lambda: ops.msra_gemm_candidates(ru, unit, T))
+out = torch.empty(T, N * 49, C, device='cuda')
+tf = timeit(lambda: ops.msra_topk_sample(rows, ref_nhwc, 2, ref_norm=norm, ref_unit=unit, out=out))
+print('gemm %.1f us (%.0f TFLOP/s)   msra_topk_sample %.1f us   norms+rescore %.1f us' % (tg, 2.0 * N * 49 * T * HW * C / tg / 1e6, tf, tf - tg))

@@ -421,10 +421,19 @@ def test_temporal_roi_align_sweep_size_properties():
     ref = torch.relu(torch.randn(T, 512, 38, 63, generator=g)).to(DEV)
     x = ref[T - 1:T]
     rois = rpn_like_rois(g, N, 1).to(DEV)
+    stacks = []
+    tafa = m._tafa
+    m._tafa = lambda x_all, rh, rw: (stacks.append(x_all), tafa(x_all, rh, rw))[1]
     out = m((x,), rois, ref_feats=(ref,))
     assert out.shape == (N, 512, 7, 7) and bool(torch.isfinite(out).all())
     out2 = m((x,), rois, ref_feats=(ref,))
-    assert torch.equal(out, out2)
+    m._tafa = tafa
+    # our kernels (RoIAlign, similarity GEMM + re-score, sampling) are bit-deterministic ...
+    assert torch.equal(stacks[0], stacks[1])
+    del stacks
+    # ... the embed conv is cuDNN's: its first call in a process with a fragmented allocator may fall back to another
+    # plan (seen: 2.6e-6 absolute on every element, later calls identical), so the end result is compared with a tolerance
+    assert rel_err(out, out2) < 1e-5
     sub = m((x,), rois[100:228], ref_feats=(ref,))
     assert rel_err(sub, out[100:228]) < 1e-4     # embed conv may pick another algorithm for the smaller batch
     # reference RoIs of all 31 frames in one launch

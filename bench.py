@@ -193,7 +193,7 @@ def kernel_rooflines(cfg, device, peaks):
         # (4') TAFA weighting: bytes = (2*(T+1)+1)*N*C*P*4
         x_all = torch.randn(T + 1, N, P, C, device=device, generator=g)
         emb = torch.randn(T + 1, N, P, C, device=device, generator=g)
-        t = timeit(lambda: ops.tafa_weighted_sum(x_all, emb, 4))
+        t = timeit(lambda: ops.tafa_weighted_sum(x_all, emb, 4, out_nhwc=True))   # channels_last output, as in the step
         b = (2 * (T + 1) + 1) * N * C * P * 4
         out['tafa_weighted_sum'] = dict(bound='hbm', seconds=t, achieved=b / t / 1e9, peak=peaks['hbm'], unit='GB/s', bytes=b)
         del x_all, emb

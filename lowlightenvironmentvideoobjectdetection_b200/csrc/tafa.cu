@@ -16,21 +16,35 @@ constexpr int kTafaWarps = 8;
 constexpr int kTafaMaxT = 64;
 
 // CTA = (n, head).  VEC=4: lanes own 4 consecutive channels, chunks of 128 channels.
-template <int VEC>
+template <int VEC, bool FLAT>
 __global__ void __launch_bounds__(kTafaWarps * 32, 4)
 tafa_kernel(const float *__restrict__ x_all, const float *__restrict__ emb_all, const float *__restrict__ emb_bias,
             float *__restrict__ out, int T1, int N, int P, int C, int hs, float scale, int use_attn, int out_layout) {
     extern __shared__ __align__(16) float tile[];          // [hs][P] (layout 0)
     __shared__ float s_w[kTafaWarps][kTafaMaxT];
     constexpr int CH = 32 * VEC;
-    const int n = blockIdx.x, head = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // layout 0 (NCHW output, transposed through shared memory): CTA = (n, head), its warps stride over the P positions.
+    // layout 1 (channels_last output): nothing ties a CTA to one RoI, so the grid is flat over (n, p, head) warp tasks
+    // -- consecutive warps read consecutive 512-byte head slices, and 7350 small CTAs leave no wave tail (the
+    // (300, 4) grid ran 2.03 waves of 592 resident CTAs: a third wave for 16 CTAs).
+    int n, head, p0, p1, pstep;
+    if (FLAT) {
+        const int groups = ceil_div(C, hs);
+        const long task = (long)blockIdx.x * kTafaWarps + warp;
+        if (task >= (long)N * P * groups) return;
+        head = (int)(task % groups);
+        const long np = task / groups;
+        n = (int)(np / P); p0 = (int)(np % P); p1 = p0 + 1; pstep = 1;
+    } else {
+        n = blockIdx.x; head = blockIdx.y; p0 = warp; p1 = P; pstep = kTafaWarps;
+    }
     const int c_head = head * hs;
     const int hs_eff = min(hs, C - c_head);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t frame_stride = (size_t)N * P * C;
     const int nch = ceil_div(hs_eff, CH);
 
-    for (int p = warp; p < P; p += kTafaWarps) {
+    for (int p = p0; p < p1; p += pstep) {
         const size_t base = ((size_t)n * P + p) * C + c_head + lane * VEC;
         float *w = s_w[warp];
         if (use_attn) {
@@ -116,7 +130,7 @@ tafa_kernel(const float *__restrict__ x_all, const float *__restrict__ emb_all, 
                                               __ldg(x_all + (size_t)(t0 + u) * frame_stride + base + ch * CH), acc[0]);
                     }
                 }
-                if (out_layout == 0) {
+                if (!FLAT) {
 #pragma unroll
                     for (int q = 0; q < VEC; ++q) tile[(ch * CH + lane * VEC + q) * P + p] = acc[q];
                 } else {
@@ -128,7 +142,7 @@ tafa_kernel(const float *__restrict__ x_all, const float *__restrict__ emb_all, 
         }
         __syncwarp();
     }
-    if (out_layout != 0) return;
+    if (FLAT) return;
     __syncthreads();
     const int total = hs_eff * P;
     float *dst = out + ((size_t)n * C + c_head) * P;
@@ -399,14 +413,13 @@ extern "C" int vod_tafa_weighted_sum(const float *x_all, const float *emb_all, c
                       (!emb_bias || (reinterpret_cast<uintptr_t>(emb_bias) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     dim3 grid(N, groups);
-    if (vec4) {
-        if (smem > 40 * 1024) cudaFuncSetAttribute(tafa_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        tafa_kernel<4><<<grid, kTafaWarps * 32, smem, as_stream(stream)>>>(x_all, emb_all, emb_bias, out, T1, N, P, C, hs, scale,
-                                                                         use_attn, out_layout); note_launch();
-    } else {
-        if (smem > 40 * 1024) cudaFuncSetAttribute(tafa_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        tafa_kernel<1><<<grid, kTafaWarps * 32, smem, as_stream(stream)>>>(x_all, emb_all, emb_bias, out, T1, N, P, C, hs, scale,
-                                                                         use_attn, out_layout); note_launch();
-    }
+    if (out_layout != 0) grid = dim3((unsigned)ceil_div((long)N * P * groups, (long)kTafaWarps), 1);
+    auto launch = [&](auto kern) {
+        if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<grid, kTafaWarps * 32, smem, as_stream(stream)>>>(x_all, emb_all, emb_bias, out, T1, N, P, C, hs, scale, use_attn, out_layout);
+        note_launch();
+    };
+    if (out_layout != 0) { if (vec4) launch(tafa_kernel<4, true>); else launch(tafa_kernel<1, true>); }
+    else { if (vec4) launch(tafa_kernel<4, false>); else launch(tafa_kernel<1, false>); }
     return check_launch("vod_tafa_weighted_sum");
 }

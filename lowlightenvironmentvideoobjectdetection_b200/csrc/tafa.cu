@@ -360,6 +360,104 @@ msra_rescore_kernel(const float *__restrict__ roi, const float *__restrict__ ref
     }
 }
 
+// Lean form of the re-score for the reference's configuration (k <= 2, C = 128 * NQ <= 512, 16 candidates):
+//   * warp task = (RoI row, chunk of kRfFrames frames): 3x more, shorter tasks than warp-per-row -> no wave tail;
+//   * the normalised RoI row lives in registers (lane owns channels lane*4 + 128*i), no shared memory;
+//   * the k-th best approximate similarity is found on the integer value field of the keys with two warp REDUX
+//     (the field is monotone in the similarity), the margin is 6 quanta of 2^-11 (>= kMsraMargin);
+//   * same arithmetic as the generic kernel for the exact similarity, the softmax and the weighted sum.
+// The generic kernel above needed ~1300 warp instructions per (row, frame); this one ~300.
+constexpr int kRfFrames = 5;
+constexpr int kRfWarps = 4;
+template <int NQ>
+__global__ void __launch_bounds__(kRfWarps * 32)
+msra_rescore_fast_kernel(const float *__restrict__ roi, const float *__restrict__ ref, const float *__restrict__ roi_norm,
+                         const float *__restrict__ ref_norm, const uint32_t *__restrict__ cand,
+                         float *__restrict__ out, int *__restrict__ idx_out, float *__restrict__ val_out, int NP,
+                         int T, int HW, int k, int nchunks) {
+    constexpr int C = 128 * NQ;
+    const int lane = threadIdx.x & 31;
+    const long task = (long)blockIdx.x * kRfWarps + (threadIdx.x >> 5);
+    if (task >= (long)NP * nchunks) return;
+    const int row = (int)(task / nchunks), t_begin = (int)(task % nchunks) * kRfFrames, t_end = min(T, t_begin + kRfFrames);
+    const float qinv = 1.0f / roi_norm[row];
+    float4 q[NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+        q[i] = ldg_f4(roi + (size_t)row * C + lane * 4 + 128 * i);
+        q[i].x *= qinv; q[i].y *= qinv; q[i].z *= qinv; q[i].w *= qinv;
+    }
+    constexpr uint32_t kMarginQ = 6;   // ceil(kMsraMargin * 2048) = 6 quanta
+    static_assert(kMsraMargin * 2048.0f <= 6.0f, "margin quanta");
+    uint32_t key = lane < kMsraCand ? __ldg(cand + ((size_t)row * T + t_begin) * kMsraCand + lane) : 0u;
+    for (int t = t_begin; t < t_end; ++t) {
+        const uint32_t next = (t + 1 < t_end && lane < kMsraCand) ? __ldg(cand + ((size_t)row * T + t + 1) * kMsraCand + lane) : 0u;
+        const float *ref_t = ref + (size_t)t * HW * C;
+        // k-th largest value field (k <= 2); a NaN similarity has the largest field and is always re-scored
+        const uint32_t vf = key >> 12;
+        uint32_t kth = __reduce_max_sync(0xffffffffu, vf);
+        if (k > 1) {
+            const unsigned holders = __ballot_sync(0xffffffffu, vf == kth);
+            const uint32_t rest = (lane == __ffs(holders) - 1) ? 0u : vf;
+            kth = __reduce_max_sync(0xffffffffu, rest);
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, key != 0u && vf + kMarginQ >= kth);
+        float v0 = -INFINITY, v1 = -INFINITY; int l0 = 0x7fffffff, l1 = 0x7fffffff;
+        bool any_nan = false;
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int l = min((int)(__shfl_sync(0xffffffffu, key, j) & 0xFFFu), HW - 1);
+            const float rinv = 1.0f / __ldg(ref_norm + (size_t)t * HW + l);
+            const float *r = ref_t + (size_t)l * C + lane * 4;
+            float4 v[NQ];
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) v[i] = ldg_f4(r + 128 * i);
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) {
+                s = fmaf(q[i].x, v[i].x * rinv, s); s = fmaf(q[i].y, v[i].y * rinv, s);
+                s = fmaf(q[i].z, v[i].z * rinv, s); s = fmaf(q[i].w, v[i].w * rinv, s);
+            }
+            s = warp_sum(s);
+            if (s != s) any_nan = true;               // torch.topk ranks NaN first: the reference row becomes NaN
+            if (s > v0 || (s == v0 && l < l0)) { v1 = v0; l1 = l0; v0 = s; l0 = l; }
+            else if (s > v1 || (s == v1 && l < l1)) { v1 = s; l1 = l; }
+        }
+        float *out_row = out + ((size_t)t * NP + row) * C + lane * 4;
+        const bool bad = any_nan || l0 == 0x7fffffff || (k > 1 && l1 == 0x7fffffff);
+        float w0 = 1.f, w1 = 0.f;
+        if (k > 1) {
+            const float e1 = expf(v1 - v0), sum = 1.0f + e1;   // softmax over the k values (temporal_roi_align.py:155)
+            w0 = 1.0f / sum; w1 = e1 / sum;
+        }
+        if (lane < k) {
+            const float qnan = __int_as_float(0x7fc00000);
+            if (idx_out) idx_out[((size_t)row * T + t) * k + lane] = bad ? 0 : (lane ? l1 : l0);
+            if (val_out) val_out[((size_t)row * T + t) * k + lane] = bad ? qnan : (lane ? v1 : v0);
+        }
+        if (bad) {
+            const float qnan = __int_as_float(0x7fc00000);
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) stg_cs_f4(out_row + 128 * i, make_float4(qnan, qnan, qnan, qnan));
+        } else {
+            const float *r0 = ref_t + (size_t)l0 * C + lane * 4, *r1 = ref_t + (size_t)(k > 1 ? l1 : l0) * C + lane * 4;
+            float4 a[NQ], b[NQ];
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) { a[i] = ldg_f4(r0 + 128 * i); b[i] = ldg_f4(r1 + 128 * i); }
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) {
+                // topk_feats * topk_weights summed over k (temporal_roi_align.py:170-172), same order as msra_emit
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                acc.x += a[i].x * w0; acc.y += a[i].y * w0; acc.z += a[i].z * w0; acc.w += a[i].w * w0;
+                if (k > 1) { acc.x += b[i].x * w1; acc.y += b[i].y * w1; acc.z += b[i].z * w1; acc.w += b[i].w * w1; }
+                stg_cs_f4(out_row + 128 * i, acc);
+            }
+        }
+        key = next;
+    }
+}
+
 int msra_launch_scan(const float *roi, const float *ref, const float *roi_norm, const float *ref_norm, float *out,
                      int *idx_out, float *val_out, int NP, int C, int T, int HW, int k, cudaStream_t st) {
     size_t smem = sizeof(float) * kScanWarps * C;
@@ -373,6 +471,21 @@ int msra_launch_scan(const float *roi, const float *ref, const float *roi_norm, 
 int msra_launch_rescore(const float *roi, const float *ref, const float *roi_norm, const float *ref_norm,
                         const uint32_t *cand, int KC, float *out, int *idx_out, float *val_out, int NP, int C, int T,
                         int HW, int k, cudaStream_t st) {
+    if (k <= 2 && KC == kMsraCand && (C & 127) == 0 && C <= 512 && HW <= 4096) {
+        const int nchunks = ceil_div(T, kRfFrames);
+        const unsigned g = (unsigned)ceil_div((long)NP * nchunks, (long)kRfWarps);
+        auto go = [&](auto kern) {
+            kern<<<g, kRfWarps * 32, 0, st>>>(roi, ref, roi_norm, ref_norm, cand, out, idx_out, val_out, NP, T, HW, k, nchunks);
+        };
+        switch (C >> 7) {
+            case 1: go(msra_rescore_fast_kernel<1>); break;
+            case 2: go(msra_rescore_fast_kernel<2>); break;
+            case 3: go(msra_rescore_fast_kernel<3>); break;
+            default: go(msra_rescore_fast_kernel<4>); break;
+        }
+        note_launch();
+        return check_launch("msra_rescore_fast");
+    }
     size_t smem = sizeof(float) * kScanWarps * C;
     const unsigned grid = (unsigned)ceil_div(NP, kScanWarps);
     if (k <= 2) {   // the reference's num_most_similar_points = 2: a 2-entry insertion network

@@ -243,30 +243,45 @@ embed_cos_kernel(const float *__restrict__ key_emb, const float *__restrict__ re
     }
 }
 
-constexpr int kEaPix = 128, kEaCh = 16;
-__global__ void __launch_bounds__(kEaPix)
+constexpr int kEaPix = 128, kEaGroups = 4, kEaChPerGroup = 4, kEaCh = kEaGroups * kEaChPerGroup;
+// CTA = 128 pixels x 4 channel groups (512 threads, 16 channels).  The softmax over t is computed once per CTA (group 0)
+// and shared; every thread then streams T frames of 4 channels with 8 independent loads in flight per channel pair
+// (the 128-thread version kept 16 warps per SM busy at 22 % of DRAM bandwidth: too few bytes in flight).
+__global__ void __launch_bounds__(kEaPix *kEaGroups)
 embed_apply_kernel(const float *__restrict__ cosv, const float *__restrict__ ref_x, float *__restrict__ out, int T, int Cx,
                    int HW) {
     extern __shared__ float wts[];   // [T][kEaPix]
-    const int pl = threadIdx.x;
+    const int pl = threadIdx.x % kEaPix, g = threadIdx.x / kEaPix;
     const int p = blockIdx.x * kEaPix + pl;
     const int pc = min(p, HW - 1);
-    float m = -INFINITY;
-    for (int t = 0; t < T; ++t) { const float v = __ldg(cosv + (size_t)t * HW + pc); wts[t * kEaPix + pl] = v; m = fmaxf(m, v); }
-    float sum = 0.f;
-    for (int t = 0; t < T; ++t) { const float e = expf(wts[t * kEaPix + pl] - m); wts[t * kEaPix + pl] = e; sum += e; }
-    for (int t = 0; t < T; ++t) wts[t * kEaPix + pl] = wts[t * kEaPix + pl] / sum;
+    if (g == 0) {
+        float m = -INFINITY;
+        for (int t = 0; t < T; ++t) { const float v = __ldg(cosv + (size_t)t * HW + pc); wts[t * kEaPix + pl] = v; m = fmaxf(m, v); }
+        float sum = 0.f;
+        for (int t = 0; t < T; ++t) { const float e = expf(wts[t * kEaPix + pl] - m); wts[t * kEaPix + pl] = e; sum += e; }
+        for (int t = 0; t < T; ++t) wts[t * kEaPix + pl] = wts[t * kEaPix + pl] / sum;
+    }
+    __syncthreads();
     if (p >= HW) return;
-    const int c0 = blockIdx.y * kEaCh, c1 = min(Cx, c0 + kEaCh);
+    const int c0 = blockIdx.y * kEaCh + g * kEaChPerGroup, c1 = min(Cx, c0 + kEaChPerGroup);
+    const size_t fs = (size_t)Cx * HW;   // frame stride
     for (int c = c0; c < c1; c += 2) {
         float a0 = 0.f, a1 = 0.f;
         const bool two = c + 1 < c1;
         const float *x0 = ref_x + (size_t)c * HW + p;
-#pragma unroll 4
-        for (int t = 0; t < T; ++t) {
+        const float *x1 = two ? x0 + HW : x0;
+        int t = 0;
+        for (; t + 8 <= T; t += 8) {
+            float u[8], v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { u[q] = __ldg(x0 + (size_t)(t + q) * fs); v[q] = __ldg(x1 + (size_t)(t + q) * fs); }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { const float w = wts[(t + q) * kEaPix + pl]; a0 = fmaf(u[q], w, a0); a1 = fmaf(v[q], w, a1); }
+        }
+        for (; t < T; ++t) {
             const float w = wts[t * kEaPix + pl];
-            a0 = fmaf(__ldg(x0 + (size_t)t * Cx * HW), w, a0);
-            if (two) a1 = fmaf(__ldg(x0 + (size_t)t * Cx * HW + HW), w, a1);
+            a0 = fmaf(__ldg(x0 + (size_t)t * fs), w, a0);
+            a1 = fmaf(__ldg(x1 + (size_t)t * fs), w, a1);
         }
         __stcs(out + (size_t)c * HW + p, a0);
         if (two) __stcs(out + (size_t)(c + 1) * HW + p, a1);
@@ -313,7 +328,7 @@ static int launch_embed(bool fused, const float *key_emb, const float *ref_emb, 
         note_launch();
         const size_t sm = sizeof(float) * (size_t)T * kEaPix;
         if (sm > 40 * 1024) cudaFuncSetAttribute(embed_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        embed_apply_kernel<<<dim3(ceil_div(HW, kEaPix), ceil_div(Cx, kEaCh)), kEaPix, sm, as_stream(stream)>>>(cosv, ref_x, out, T, Cx, HW);
+        embed_apply_kernel<<<dim3(ceil_div(HW, kEaPix), ceil_div(Cx, kEaCh)), kEaPix * kEaGroups, sm, as_stream(stream)>>>(cosv, ref_x, out, T, Cx, HW);
         note_launch();
         return check_launch("vod_embed_weighted_sum(2-kernel)");
     }

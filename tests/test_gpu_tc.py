@@ -105,30 +105,53 @@ def test_selsa_aggregator_golden_tc(golden):
 
 
 # ------------------------------------------------------------------------------------------ (4) most-similar on tcgen05
-def _msra_compare(N, C, T, H, W, seed):
+def _msra_compare(N, C, T, H, W, seed, k=2, zero_rows=(), zero_pixels=()):
     g = torch.Generator().manual_seed(seed)
     roi = torch.relu(torch.randn(N, C, 7, 7, generator=g))
     ref = torch.relu(torch.randn(T, C, H, W, generator=g))
-    out0, idx0, sim0 = O.most_similar_roi_align(roi, ref, 2, return_indices=True)
+    for n, p in zero_rows:                  # an all-zero RoI vector: the reference divides by its zero norm -> NaN row
+        roi[n, :, p // 7, p % 7] = 0
+    for t, y, x in zero_pixels:             # an all-zero reference pixel: NaN similarity for every RoI row of frame t
+        ref[t, :, y, x] = 0
+    out0, idx0, sim0 = O.most_similar_roi_align(roi, ref, k, return_indices=True)
     ref_nhwc, norm, unit = ops.to_nhwc(ref.to('cuda'), want_norm=True, want_unit_bf16=True)
     rows = roi.permute(0, 2, 3, 1).reshape(N * 49, C).to('cuda')
-    out1, idx1, val1 = ops.msra_topk_sample(rows, ref_nhwc, 2, ref_norm=norm, ref_unit=unit, impl=ops.IMPL_TC,
+    out1, idx1, val1 = ops.msra_topk_sample(rows, ref_nhwc, k, ref_norm=norm, ref_unit=unit, impl=ops.IMPL_TC,
                                             return_indices=True)
     idx1 = idx1.cpu().long()
-    same = (idx1.sort(dim=2).values == idx0.sort(dim=2).values).all(dim=2)
+    got = out1.view(T, N, 7, 7, C).permute(0, 1, 4, 2, 3)
+    nan_rows = torch.isnan(out0).any(dim=2).permute(1, 2, 3, 0).reshape(N * 49, T)      # [NP, T]
+    same = (idx1.sort(dim=2).values == idx0.sort(dim=2).values).all(dim=2) | nan_rows
     for r, t in (~same).nonzero().tolist():
         # tie tolerance: a differing location must have the same fp32 similarity up to 1e-6
         v_ours = sim0[r, t, idx1[r, t]].sort().values
         v_ref = sim0[r, t, idx0[r, t]].sort().values
         assert (v_ours - v_ref).abs().max() <= 1e-6, (r, t, v_ours, v_ref)
-    got = out1.view(T, N, 7, 7, C).permute(0, 1, 4, 2, 3)
-    assert rel_err(got, out0) < 1e-3
+    assert rel_err(got, out0) < 1e-3        # also asserts that the NaN patterns are identical
     return float(same.float().mean())
 
 
-@pytest.mark.parametrize('N,C,T,H,W', [(6, 64, 3, 12, 20), (20, 512, 3, 38, 63), (3, 128, 2, 9, 15)])
+# C = 64 -> generic re-score (C % 128 != 0); C = 128/256/384/512 -> the four instantiations of the lean re-score kernel;
+# 294, 980, 147, 245, 196 rows -> odd and even numbers of 128-row tiles for the CTA pairs
+@pytest.mark.parametrize('N,C,T,H,W', [(6, 64, 3, 12, 20), (20, 512, 3, 38, 63), (3, 128, 2, 9, 15), (5, 256, 2, 10, 17),
+                                       (4, 384, 3, 11, 13)])
 def test_msra_tc_vs_oracle(N, C, T, H, W):
     frac = _msra_compare(N, C, T, H, W, N + C)
+    assert frac > 0.999
+
+
+@pytest.mark.parametrize('k,C', [(1, 512), (1, 128), (3, 512), (4, 256), (4, 64)])
+def test_msra_tc_other_k(k, C):
+    """num_most_similar_points != 2: k = 1 runs the lean kernel, k > 2 the generic re-score of the 16 candidates."""
+    frac = _msra_compare(4, C, 3, 13, 21, 100 * k + C, k=k)
+    assert frac > 0.999
+
+
+@pytest.mark.parametrize('C', [512, 64])
+def test_msra_tc_zero_norm_vectors(C):
+    """The reference has no epsilon: a zero RoI vector gives a NaN row in every frame, a zero reference pixel makes the
+    similarity NaN for every RoI row of that frame (torch.topk ranks NaN first).  Same NaN pattern, same finite rows."""
+    frac = _msra_compare(3, C, 3, 12, 19, 5 + C, zero_rows=((0, 0), (2, 30)), zero_pixels=((1, 4, 7),))
     assert frac > 0.999
 
 

@@ -128,7 +128,9 @@ int vod_selsa_attn(const void *q, const void *k, const void *v, float *out, int 
  */
 size_t vod_msra_workspace_bytes(int NP, int C, int T, int HW, int k);
 /* ref_norm [T*HW] fp32 and ref_unit_bf16 [T*HW, C] may be passed when the caller already has them
- * from vod_nchw_to_nhwc (nullable: recomputed into the workspace). */
+ * from vod_nchw_to_nhwc (nullable: recomputed into the workspace).  When HW % 4 != 0 the ref_unit_bf16 buffer
+ * must be readable for 3 rows (3*C*2 bytes) past row T*HW (contents ignored): the tensor-core pass fetches
+ * locations in groups of 4. */
 int vod_msra_topk_sample(const float *roi_feats, const float *ref_nhwc, const float *ref_norm,
                          const void *ref_unit_bf16, float *out, int *idx_out, float *val_out, int NP,
                          int C, int T, int HW, int k, int impl, void *ws, size_t ws_bytes,
@@ -139,6 +141,7 @@ int vod_msra_topk_sample(const float *roi_feats, const float *ref_nhwc, const fl
  * round((1.5 + similarity) * 2^11) << 12 | location: the 4 best of each of the four 32-column
  * groups of the 128-location tiles; 0 = empty slot.  Exposed so the GEMM can be profiled / roofline-timed on
  * its own and its candidate recall tested.
+  * ref_unit: same 3-row readable padding as above when HW % 4 != 0.
  */
 int vod_msra_gemm_candidates(const void *roi_unit_bf16, const void *ref_unit_bf16, uint32_t *cand_out,
                              int NP, int C, int T, int HW, vod_stream_t stream);

@@ -4,6 +4,7 @@ signatures.  Host code is Python/PyTorch (device memory + streams only); every o
 kernels from libvodagg.so through a C ABI (include/vodagg.h).  No Triton, no backend dispatch, no CPU fallback.
 """
 from . import _lib, ops  # noqa: F401
+from ._lib import VodError  # noqa: F401
 from .aggregators import EmbedAggregator, SelsaAggregator  # noqa: F401
 from .heads import SelsaBBoxHead, SelsaRoIHead  # noqa: F401
 from .motion import flow_warp_feats  # noqa: F401

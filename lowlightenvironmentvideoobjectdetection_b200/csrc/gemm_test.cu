@@ -68,6 +68,28 @@ int make_tmap_kslices_sw128(CUtensorMap *map, const void *base, uint64_t rows, u
     return VOD_OK;
 }
 
+// B operand of the msra similarity GEMM: bf16 unit rows [T*HW, C], seen as a 5-D tensor
+//   (64 channels | A = location / 4 | g = location % 4 | frame t | K slice of 64 channels)
+// so that one box (64, 32, 2, 1, slices) lands in shared memory as `slices` K-major SWIZZLE_128B tiles of 64 rows ordered
+// r = g_local * 32 + a, i.e. location = 128 * tile + 4 * a + g: neighbouring locations fall into different 32-row groups.
+// When HW % 4 != 0 the last A of a frame touches up to 3 rows of the next frame (masked by the consumer); for the last
+// frame these lie past T*HW, hence the 3 rows of readable padding the C ABI asks for.
+int make_tmap_msra_b(CUtensorMap *map, const void *base, uint64_t T, uint64_t HW, uint64_t C, uint32_t box_slices) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return fail(VOD_E_LAUNCH, "cuTensorMapEncodeTiled entry point unavailable");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || C % 64 != 0)
+        return fail(VOD_E_BADARG, "TMA operand needs a 16-byte aligned base and C %% 64 == 0");
+    cuuint64_t dims[5] = {64, (HW + 3) / 4, 4, T, C / 64};
+    cuuint64_t strides[4] = {4 * C * 2, C * 2, HW * C * 2, 128};
+    cuuint32_t box[5] = {64, 32, 2, 1, box_slices};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(VOD_E_LAUNCH, "cuTensorMapEncodeTiled (msra B) failed (%d)", (int)r);
+    return VOD_OK;
+}
+
 constexpr int kGtStages = 4;
 constexpr int kGtTileBytes = 128 * 128;  // 128 rows x 128 B
 constexpr int kGtThreads = 192;

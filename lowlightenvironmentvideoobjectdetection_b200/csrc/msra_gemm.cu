@@ -20,7 +20,7 @@
 //            over the pair, N = 128; accumulator double buffered in each CTA's TMEM (2 x 128 columns; TMEM total:
 //            256 accumulator + 256 A = 512 columns); commits are multicast to both CTAs' barriers
 //   warps 0-15 epilogue (both CTAs, own 128 rows): thread = row (four warps per TMEM lane quarter, each owning 32 of
-//            the tile's 128 columns); every similarity is packed with its location into one order-preserving 32-bit
+//            the tile's 128 columns = every 4th location of the tile); every similarity is packed with its location into one order-preserving 32-bit
 //            key (20 value bits | 12 location bits, built on the FMA pipe) and pushed through a branch-free min/max insertion network that
 //            keeps the 4 largest keys in registers -- no divergence although the 32 lanes of a warp follow 32
 //            different rows; one 16-byte store per (row, frame, column group) at the end
@@ -97,13 +97,15 @@ msra_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_b, const MgParams p
             tc::tma_prefetch_desc(&tm_b);
             uint32_t st = 0, ph = 0;
             for (int u = u0; u < u1; ++u) {
-                const int row0 = (u % p.T) * p.HW + (int)crank * (kMgBN / 2);
+                const int t = u % p.T;
                 for (int nt = 0; nt < p.ntiles; ++nt) {
                     for (int g = 0; g < p.nstg; ++g) {
                         tc::mbar_wait(&b_empty[st], ph ^ 1);   // the pair's MMAs have consumed this stage (multicast commit)
                         if (crank == 0) tc::mbar_arrive_expect_tx(&b_full[st], 2 * kMgStageBytes);   // both halves land on the leader's barrier
-                        // box = 64 channels x 64 locations x kMgSPS slices (slices past C are zero-filled, never read)
-                        tc::tma_load_3d_2sm(sB + st * kMgStageBytes, &tm_b, &b_full[st], 0, row0 + nt * kMgBN, g * kMgSPS);
+                        // box = 64 channels x (32 a x 2 g) locations x kMgSPS slices of frame t; this CTA's 64 B rows are the
+                        // locations 128*nt + 4*a + g with g in {2*rank, 2*rank + 1} (slices past C / locations past the
+                        // frame are zero-filled or masked in the epilogue)
+                        tc::tma_load_5d_2sm(sB + st * kMgStageBytes, &tm_b, &b_full[st], 0, nt * (kMgBN / 4), 2 * (int)crank, t, g * kMgSPS);
                         if (++st == kMgStages) { st = 0; ph ^= 1; }
                     }
                 }
@@ -197,8 +199,10 @@ msra_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_b, const MgParams p
                 tc::tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive_cluster(&acc_empty[buf], 0);   // values are in registers: the pair's MMA may overwrite
-                const uint32_t base = (uint32_t)(nt * kMgBN + grp * 32);
-                const int nvalid = p.HW - (int)base;    // columns of this frame that exist (tail tile only)
+                // accumulator column 32*grp + j holds location 128*nt + 4*j + grp (see the producer): the four column groups
+                // interleave the locations, so a run of near-tied NEIGHBOURING pixels is spread over all four top-4 lists
+                const uint32_t base = (uint32_t)(nt * kMgBN + grp);
+                const int nvalid = (p.HW - (int)base + 3) >> 2;    // j < nvalid <=> location < HW (tail tile only)
                 auto push = [&](uint32_t bits, uint32_t j, bool ok) {
                     // |cos| <= 1 (+ bf16 noise): t = sim + 6145.5 lies in [4096, 8192), where one ulp is 2^-11, so the FADD
                     // itself rounds the similarity to 11 fractional bits and bits(t) = 0x45800000 + (2049.5 + sim) * 2^11.
@@ -208,7 +212,7 @@ msra_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_b, const MgParams p
                     // (The multipliers 4096 and 1 are kernel parameters so that ptxas cannot turn the IMADs into ALU ops.)
                     // A NaN similarity gives the canonical 0x7FFFFFFF -> value field 0xFFFFF: ranked first, like torch.topk.
                     const uint32_t w = __float_as_uint(__uint_as_float(bits) + 6145.5f);
-                    uint32_t key = tc::mad_lo(tc::mad_lo(w, (uint32_t)p.k4096, base), (uint32_t)p.kone, j);
+                    uint32_t key = tc::mad_lo(tc::mad_lo(w, (uint32_t)p.k4096, base), (uint32_t)p.kone, 4u * j);
                     if (!ok) key = 0u;
                     uint32_t hi;
                     hi = max(k0, key); key = min(k0, key); k0 = hi;
@@ -246,8 +250,8 @@ int msra_launch_gemm_topk(const void *roi_unit_bf16, const void *ref_unit_bf16, 
     CUtensorMap tb;
     int rc;
     if ((reinterpret_cast<uintptr_t>(roi_unit_bf16) & 15) != 0) return fail(VOD_E_BADARG, "msra_gemm: A rows must be 16-byte aligned");
-    // each CTA of a pair loads 64 locations x kMgSPS K slices per instruction
-    if ((rc = make_tmap_kslices_sw128(&tb, ref_unit_bf16, (uint64_t)T * HW, C, kMgBN / 2, kMgSPS))) return rc;
+    // each CTA of a pair loads 64 (interleaved) locations x kMgSPS K slices per instruction
+    if ((rc = make_tmap_msra_b(&tb, ref_unit_bf16, T, HW, C, kMgSPS))) return rc;
     MgParams p;
     p.cand = cand; p.NP = NP; p.T = T; p.HW = HW;
     p.a_rows = reinterpret_cast<const __nv_bfloat16 *>(roi_unit_bf16);
@@ -277,7 +281,7 @@ MsraWs msra_ws(int NP, int C, int T, int HW) {
     w.roi_norm = o; o = align_up(o + sizeof(float) * (size_t)NP, 256);
     w.ref_norm = o; o = align_up(o + sizeof(float) * (size_t)T * HW, 256);
     w.roi_unit = o; o = align_up(o + 2 * (size_t)NP * C, 1024);
-    w.ref_unit = o; o = align_up(o + 2 * (size_t)T * HW * C, 1024);
+    w.ref_unit = o; o = align_up(o + 2 * ((size_t)T * HW + 4) * C, 1024);   // + the padding rows the TMA box may touch
     w.cand = o;     o = align_up(o + sizeof(int) * (size_t)NP * T * kMsraCand, 256);
     w.bytes = o;
     return w;
@@ -302,8 +306,11 @@ extern "C" int vod_msra_topk_sample(const float *roi_feats, const float *ref_nhw
     const MsraWs w = msra_ws(NP, C, T, HW);
     if (ws_bytes < w.bytes) return fail(VOD_E_WORKSPACE, "vod_msra_topk_sample: workspace %zu < %zu", ws_bytes, w.bytes);
     uint8_t *wsb = reinterpret_cast<uint8_t *>(ws);
-    const bool tc_ok = msra_gemm_supported(NP, C, T, HW) && HW >= kMsraCand && vod_device_is_sm100();
-    if (impl == 2 && !tc_ok) return fail(VOD_E_UNSUPPORTED, "vod_msra_topk_sample: tcgen05 path needs C %% 64 == 0, C <= 512, sm_100");
+    // The candidate pass keeps the 4 best of four interleaved location groups: sized for the reference's k = 2 (and k = 1).
+    // Larger k runs the exact scan (a true top-4 with three members in one group would leave no slack in that group).
+    const bool tc_ok = msra_gemm_supported(NP, C, T, HW) && HW >= kMsraCand && k <= 2 && vod_device_is_sm100();
+    if (impl == 2 && !tc_ok)
+        return fail(VOD_E_UNSUPPORTED, "vod_msra_topk_sample: tcgen05 path needs C %% 64 == 0, C <= 512, k <= 2, sm_100");
     const bool use_tc = impl == 2 || (impl == 0 && tc_ok);
 
     float *roi_norm = reinterpret_cast<float *>(wsb + w.roi_norm);

@@ -486,17 +486,13 @@ int msra_launch_rescore(const float *roi, const float *ref, const float *roi_nor
         note_launch();
         return check_launch("msra_rescore_fast");
     }
+    // generic shapes (C % 128 != 0): still k <= 2, the only k the candidate pass is used for (msra_gemm.cu)
+    if (k > 2) return fail(VOD_E_UNSUPPORTED, "msra_rescore: k=%d > 2", k);
     size_t smem = sizeof(float) * kScanWarps * C;
     const unsigned grid = (unsigned)ceil_div(NP, kScanWarps);
-    if (k <= 2) {   // the reference's num_most_similar_points = 2: a 2-entry insertion network
-        if (smem > 40 * 1024) cudaFuncSetAttribute(msra_rescore_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        msra_rescore_kernel<2><<<grid, kScanWarps * 32, smem, st>>>(roi, ref, roi_norm, ref_norm, cand, KC, out, idx_out,
-                                                                  val_out, NP, C, T, HW, k);
-    } else {
-        if (smem > 40 * 1024) cudaFuncSetAttribute(msra_rescore_kernel<kMsraMaxK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        msra_rescore_kernel<kMsraMaxK><<<grid, kScanWarps * 32, smem, st>>>(roi, ref, roi_norm, ref_norm, cand, KC, out,
-                                                                          idx_out, val_out, NP, C, T, HW, k);
-    }
+    if (smem > 40 * 1024) cudaFuncSetAttribute(msra_rescore_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    msra_rescore_kernel<2><<<grid, kScanWarps * 32, smem, st>>>(roi, ref, roi_norm, ref_norm, cand, KC, out, idx_out, val_out, NP, C,
+                                                              T, HW, k);
     note_launch();
     return check_launch("msra_rescore");
 }

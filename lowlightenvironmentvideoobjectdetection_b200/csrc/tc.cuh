@@ -108,6 +108,14 @@ __device__ __forceinline__ void tma_load_3d_2sm(void *smem_dst, const CUtensorMa
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(leader_bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_5d_2sm(void *smem_dst, const CUtensorMap *m, uint64_t *leader_bar, int c0, int c1, int c2,
+                                                int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(leader_bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2),
+          "r"(c3), "r"(c4)
+        : "memory");
+}
 // 32-bit multiply-add kept as an IMAD (FMA pipe) -- use with a multiplier the compiler cannot see through
 __device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t d;
@@ -248,5 +256,6 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
 int make_tmap_2d_sw128(CUtensorMap *map, const void *base, int elem_bytes, uint64_t rows, uint64_t cols,
                        uint64_t row_stride_bytes, uint32_t box_rows);
 int make_tmap_kslices_sw128(CUtensorMap *map, const void *base, uint64_t rows, uint64_t C, uint32_t box_rows, uint32_t box_slices);
+int make_tmap_msra_b(CUtensorMap *map, const void *base, uint64_t T, uint64_t HW, uint64_t C, uint32_t box_slices);
 
 }  // namespace vod

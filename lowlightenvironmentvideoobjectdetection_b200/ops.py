@@ -62,7 +62,8 @@ def _to_nhwc(x, want_norm=False, want_unit_bf16=False):
         return x.permute(0, 2, 3, 1), None, None
     nhwc = torch.empty((B, H, W, C), dtype=torch.float32, device=x.device)
     norm = torch.empty((B * H * W,), dtype=torch.float32, device=x.device) if (want_norm or want_unit_bf16) else None
-    unit = torch.empty((B * H * W, C), dtype=torch.bfloat16, device=x.device) if want_unit_bf16 else None
+    # 4 spare rows behind the unit copy: the msra GEMM's TMA box fetches locations in groups of 4 (vodagg.h)
+    unit = torch.empty((B * H * W + 4, C), dtype=torch.bfloat16, device=x.device)[:B * H * W] if want_unit_bf16 else None
     if x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous():
         # already NHWC in memory: only the norms / unit copy are missing
         nhwc = x.permute(0, 2, 3, 1)
@@ -338,6 +339,21 @@ def selsa_attention(q, k, v, num_heads, v_transposed=False, impl=IMPL_AUTO):
 
 
 # ----------------------------------------------------------------------------- (4) TemporalRoIAlign pieces
+def _padded_unit(ref_unit, rows):
+    """The tensor-core pass may read up to 3 rows past the last reference row (vodagg.h): copy into a padded buffer
+    unless the tensor's storage already extends that far (the copies made by ``to_nhwc`` do)."""
+    if ref_unit is None:
+        return None
+    ref_unit = ref_unit.contiguous()
+    C = ref_unit.shape[-1]
+    have = ref_unit.untyped_storage().nbytes() - ref_unit.storage_offset() * ref_unit.element_size()
+    if have >= (rows + 3) * C * ref_unit.element_size():
+        return ref_unit
+    buf = torch.empty((rows + 4, C), dtype=ref_unit.dtype, device=ref_unit.device)
+    buf[:rows].copy_(ref_unit.reshape(rows, C))
+    return buf[:rows]
+
+
 def msra_topk_sample(roi_rows, ref_nhwc, k=2, ref_norm=None, ref_unit=None, impl=IMPL_AUTO, return_indices=False,
                      out=None):
     """roi_rows [NP, C] fp32, ref_nhwc [T, H, W, C] fp32 -> out [T, NP, C] (+ idx [NP,T,k] int32, val fp32)."""
@@ -354,6 +370,7 @@ def msra_topk_sample(roi_rows, ref_nhwc, k=2, ref_norm=None, ref_unit=None, impl
     val = torch.empty((NP, T, k), dtype=torch.float32, device=dev) if return_indices else None
     if NP and T:
         lib = _lib.load()
+        ref_unit = _padded_unit(ref_unit, T * H * W)
         ws = _ws.get(lib.vod_msra_workspace_bytes(NP, C, T, H * W, k), dev)
         _lib.call('vod_msra_topk_sample', _lib.ptr(roi_rows), _lib.ptr(ref_nhwc), _lib.ptr(ref_norm),
                   _lib.ptr(ref_unit), _lib.ptr(out), _lib.ptr(idx), _lib.ptr(val), NP, C, T, H * W, int(k), int(impl),
@@ -368,9 +385,10 @@ def msra_gemm_candidates(roi_unit, ref_unit, T):
     (uint32 bit patterns in an int32 tensor; location = key & 0xFFF, 0 = empty slot)."""
     _lib.require_cuda(roi_unit, ref_unit)
     assert roi_unit.dtype == torch.bfloat16 and ref_unit.dtype == torch.bfloat16
-    roi_unit, ref_unit = roi_unit.contiguous(), ref_unit.contiguous()
+    roi_unit = roi_unit.contiguous()
     NP, C = roi_unit.shape
     HW = ref_unit.shape[0] // T
+    ref_unit = _padded_unit(ref_unit, T * HW)
     cand = torch.empty((NP, T, 16), dtype=torch.int32, device=roi_unit.device)
     _lib.call('vod_msra_gemm_candidates', _lib.ptr(roi_unit), _lib.ptr(ref_unit), _lib.ptr(cand), NP, C, T, HW,
               _lib.stream_ptr(roi_unit.device))

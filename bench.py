@@ -486,7 +486,7 @@ def main():
         'e2e': {'value': frames / t_e2e, 'unit': unit, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
         'gpu_launches': int(launches), 'clocks': sampler.summary(),
         'eager_api': {'value': frames / t_eager, 'unit': unit,
-                      'note': 'SelsaRoIHead.simple_test called eagerly (variable-length outputs, 2 host syncs per frame)'},
+                      'note': 'SelsaRoIHead.simple_test called eagerly (variable-length outputs, one host read of the detection count per frame)'},
     }
     if rank == 0 and not args.no_roofline:
         with torch.no_grad():

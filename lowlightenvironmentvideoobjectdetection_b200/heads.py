@@ -94,6 +94,13 @@ class SelsaBBoxHead(nn.Module):
     @torch.no_grad()
     def get_bboxes(self, rois, cls_score, bbox_pred, img_shape, scale_factor, rescale=False, cfg=None):
         """bbox_head.py:269-373 (non-batch mode)."""
+        if (cfg is not None and cls_score.is_cuda and cfg['nms'].get('type', 'nms') == 'nms' and cls_score.size(0) > 0
+                and cfg.get('max_per_img', 0) > 0):
+            # same result through the fused decode kernel + device NMS; one host read (the detection count) trims the
+            # fixed-size buffers to the reference's variable-length return
+            dets, labels, count = self.get_bboxes_device(rois, cls_score, bbox_pred, img_shape, scale_factor, rescale, cfg)
+            n = int(count)
+            return dets[:n], labels[:n]
         scores = F.softmax(cls_score, dim=-1)
         bboxes = delta2bbox(rois[:, 1:], bbox_pred, self.target_means, self.target_stds, max_shape=img_shape)
         if rescale and bboxes.size(0) > 0:

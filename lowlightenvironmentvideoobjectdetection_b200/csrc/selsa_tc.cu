@@ -164,12 +164,16 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         // ------------------------------------------------------------------ softmax / accumulate (warps 0-3)
         const int r = warp * 32 + lane;                       // row within the tile == TMEM lane
         const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
-        float acc[kHD];
+        // Instruction diet of the softmax warps (one warp per SM sub-partition walks 32 rows serially, so the loop is
+        // issue-bound): packed fp32x2 FMA/ADD (FFMA2/FADD2), ex2.approx on the raw MUFU, the scale folded into the
+        // exponent's FMA, masking only in the tail chunk.  ~1100 -> ~400 instructions per 64-key chunk and thread.
+        float2 acc[kHD / 2];
 #pragma unroll
-        for (int i = 0; i < kHD; ++i) acc[i] = 0.f;
+        for (int i = 0; i < kHD / 2; ++i) acc[i] = make_float2(0.f, 0.f);
         float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
         const uint32_t prow = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
         const uint32_t rx = (uint32_t)(r & 7);
+        auto ex2 = [](float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; };
 
         auto consume_o = [&](int j) {
             tc::mbar_wait(&o_full, j & 1);
@@ -180,10 +184,11 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             tc::tmem_ld_wait();
             tc::tcgen05_fence_before();
             tc::mbar_arrive(&o_empty);
+            const float2 c2 = make_float2(corr_prev, corr_prev);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                acc[i] = fmaf(acc[i], corr_prev, __uint_as_float(o0[i]));
-                acc[32 + i] = fmaf(acc[32 + i], corr_prev, __uint_as_float(o1[i]));
+            for (int i = 0; i < 16; ++i) {
+                acc[i] = __ffma2_rn(acc[i], c2, make_float2(__uint_as_float(o0[2 * i]), __uint_as_float(o0[2 * i + 1])));
+                acc[16 + i] = __ffma2_rn(acc[16 + i], c2, make_float2(__uint_as_float(o1[2 * i]), __uint_as_float(o1[2 * i + 1])));
             }
         };
 
@@ -200,19 +205,26 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
             const int valid = min(kBN, p.M - (c0 + j) * kBN);  // reference rows of this chunk that exist
             float s[kBN];
-            float mx = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                s[i] = i < valid ? __uint_as_float(s0[i]) * p.scale_log2 : -INFINITY;
-                s[32 + i] = 32 + i < valid ? __uint_as_float(s1[i]) * p.scale_log2 : -INFINITY;
-                mx = fmaxf(mx, fmaxf(s[i], s[32 + i]));
+            for (int i = 0; i < 32; ++i) { s[i] = __uint_as_float(s0[i]); s[32 + i] = __uint_as_float(s1[i]); }
+            if (valid < kBN) {   // tail chunk only (warp-uniform)
+#pragma unroll
+                for (int i = 0; i < kBN; ++i) s[i] = i < valid ? s[i] : -INFINITY;
             }
-            const float m_new = fmaxf(m_run, mx);
-            const float corr = exp2f(m_run - m_new);  // m_run = -inf on the first chunk -> 0
-            float rowsum = 0.f;
+            float mx = s[0];
 #pragma unroll
-            for (int i = 0; i < kBN; ++i) { s[i] = exp2f(s[i] - m_new); rowsum += s[i]; }
-            l_run = fmaf(l_run, corr, rowsum);
+            for (int i = 1; i < kBN; ++i) mx = fmaxf(mx, s[i]);
+            const float m_new = fmaxf(m_run, mx * p.scale_log2);   // scale > 0: max commutes with the scaling
+            const float corr = ex2(m_run - m_new);                 // m_run = -inf on the first chunk -> 0
+            const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_new, -m_new);
+            float2 sum2 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < kBN; i += 2) {
+                const float2 t = __ffma2_rn(make_float2(s[i], s[i + 1]), sc2, nm2);   // raw * scale - m  (-inf stays -inf)
+                s[i] = ex2(t.x); s[i + 1] = ex2(t.y);
+                sum2 = __fadd2_rn(sum2, make_float2(s[i], s[i + 1]));
+            }
+            l_run = fmaf(l_run, corr, sum2.x + sum2.y);
 
             tc::mbar_wait(&p_empty[buf], ((j >> 1) & 1) ^ 1);
             uint8_t *pb = sP + buf * Cfg::kPBytes + prow;
@@ -234,8 +246,9 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
                     for (uint32_t c16 = 0; c16 < 8; ++c16) {
                         uint4 v;
-                        v.x = f32_to_tf32(s[sl * 32 + c16 * 4 + 0]); v.y = f32_to_tf32(s[sl * 32 + c16 * 4 + 1]);
-                        v.z = f32_to_tf32(s[sl * 32 + c16 * 4 + 2]); v.w = f32_to_tf32(s[sl * 32 + c16 * 4 + 3]);
+                        // + half a tf32 ulp: the MMA truncates the low 13 bits, together = cvt.rna.tf32 (one IADD instead of two ops)
+                        v.x = __float_as_uint(s[sl * 32 + c16 * 4 + 0]) + 0x1000u; v.y = __float_as_uint(s[sl * 32 + c16 * 4 + 1]) + 0x1000u;
+                        v.z = __float_as_uint(s[sl * 32 + c16 * 4 + 2]) + 0x1000u; v.w = __float_as_uint(s[sl * 32 + c16 * 4 + 3]) + 0x1000u;
                         *reinterpret_cast<uint4 *>(pb + sl * kBM * 128 + ((c16 ^ rx) << 4)) = v;
                     }
             }
@@ -256,13 +269,13 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < kHD; i += 4)
                     *reinterpret_cast<float4 *>(dst + i) =
-                        make_float4(acc[i] * inv, acc[i + 1] * inv, acc[i + 2] * inv, acc[i + 3] * inv);
+                        make_float4(acc[i / 2].x * inv, acc[i / 2].y * inv, acc[i / 2 + 1].x * inv, acc[i / 2 + 1].y * inv);
             } else {
                 const size_t pr = ((size_t)split * p.heads + h) * p.Npad + row;
                 float *dst = p.part_acc + pr * kHD;
 #pragma unroll
                 for (int i = 0; i < kHD; i += 4)
-                    *reinterpret_cast<float4 *>(dst + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+                    *reinterpret_cast<float4 *>(dst + i) = make_float4(acc[i / 2].x, acc[i / 2].y, acc[i / 2 + 1].x, acc[i / 2 + 1].y);
                 p.part_m[pr] = m_run;
                 p.part_l[pr] = l_run;
             }

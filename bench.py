@@ -239,6 +239,20 @@ def kernel_rooflines(cfg, device, peaks):
     t = timeit(lambda: ops.nms_device(pb, ps, None, 0.7, ops.NMS_MODE_AGNOSTIC, seg_offsets=offs, max_keep=300))
     b = nimg * (6000 * 20 + 6000 * 94 * 8)
     out['batched_nms_rpn_x%d' % nimg] = dict(bound='hbm', seconds=t, achieved=b / t / 1e9, peak=peaks['hbm'], unit='GB/s', bytes=b)
+    # (N3) the whole RPN proposal stage for the T+1 frames of a step: sigmoid, top-6000, decode, segmented NMS, top-300
+    import lowlightenvironmentvideoobjectdetection_b200 as vod
+    A_per = 12
+    ys, xs = torch.meshgrid(torch.arange(H, device=device) * 16., torch.arange(W, device=device) * 16., indexing='ij')
+    shift = torch.stack([xs, ys, xs, ys], -1).reshape(-1, 1, 4)
+    base = torch.tensor([[-16. * sc / r ** 0.5 / 2, -16. * sc * r ** 0.5 / 2, 16. * sc / r ** 0.5 / 2, 16. * sc * r ** 0.5 / 2]
+                         for r in (0.5, 1., 2.) for sc in (4, 8, 16, 32)], device=device)
+    anchors = (shift + base[None]).reshape(-1, 4)
+    rc = torch.randn(nimg, A_per, H, W, device=device, generator=g) * 3
+    rr = torch.randn(nimg, A_per * 4, H, W, device=device, generator=g) * 0.3
+    t = timeit(lambda: vod.rpn_get_bboxes_device(rc, rr, anchors, IMG_SHAPE, 6000, 0.7, 300))
+    b = nimg * (H * W * A_per * 20 + 6000 * 20 + 6000 * 94 * 8)
+    out['rpn_proposal_stage_x%d' % nimg] = dict(bound='hbm', seconds=t, achieved=b / t / 1e9, peak=peaks['hbm'], unit='GB/s', bytes=b,
+                                                note='row N3: logits+deltas in, 300 proposals per image out; latency-bound')
     for v in out.values():
         v['frac'] = v['achieved'] / v['peak']
     return out

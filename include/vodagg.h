@@ -211,6 +211,13 @@ int vod_bbox_decode_candidates(const float *rois, const float *cls_score, const 
                                float *cand_scores, int64_t *cand_labels, int *n_valid_dev,
                                vod_stream_t stream);
 
+/* RPN proposal decode, RPNHead._get_bboxes (mmdetection/mmdet/models/dense_heads/rpn_head.py:163-188, one feature
+ * level): topk_idx [B,K] int64 = positions of the K best-scoring anchors of each image (from the score sort),
+ * deltas [B,A,4], anchors [A,4] -> boxes [B*K,4] = delta2bbox(anchors[idx], deltas[idx], means 0, stds 1) clipped to
+ * the image (img_w < 0: no clipping).  Feeds vod_batched_nms with B segments of K boxes. */
+int vod_rpn_decode_topk(const int64_t *topk_idx, const float *deltas, const float *anchors, float *boxes, int B, int K,
+                        int A, float max_ratio, float img_h, float img_w, vod_stream_t stream);
+
 /* ------------------------------------------------------------ diagnostics
  * Plain tcgen05 GEMM used by the unit tests to validate descriptors/pipeline:
  * D[M,N] (fp32) = A[M,K] * B[N,K]^T, A/B row-major (K contiguous), dtype bf16 or fp32(tf32).

@@ -9,7 +9,8 @@ from .aggregators import EmbedAggregator, SelsaAggregator  # noqa: F401
 from .heads import SelsaBBoxHead, SelsaRoIHead  # noqa: F401
 from .motion import flow_warp_feats  # noqa: F401
 from .ops import RoIAlign, batched_nms, nms, roi_align  # noqa: F401
-from .post_processing import bbox2roi, delta2bbox, multiclass_nms, rpn_batched_nms  # noqa: F401
+from .post_processing import (bbox2roi, delta2bbox, multiclass_nms, rpn_batched_nms, rpn_get_bboxes,  # noqa: F401
+                              rpn_get_bboxes_device)
 from .registry import (AGGREGATORS, HEADS, ROI_EXTRACTORS, ConvModule, Registry, build_aggregator,  # noqa: F401
                        build_from_cfg, build_head, build_roi_extractor, force_fp32, register_into_openmmlab)
 from .roi_extractors import BaseRoIExtractor, SingleRoIExtractor, TemporalRoIAlign  # noqa: F401

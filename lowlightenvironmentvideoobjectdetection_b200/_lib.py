@@ -44,6 +44,7 @@ SIGNATURES = {
     'vod_batched_nms_ex': (_I, [_P, _P, _P, _I, _c.POINTER(_I), _I, _F, _I, _I, _P, _I, _P, _P, _P, _P, _P, _SZ, _P]),
     'vod_bbox_decode_candidates': (_I, [_P, _P, _P, _I, _I, _I, _c.POINTER(_F), _c.POINTER(_F), _F, _F, _F,
                                         _c.POINTER(_F), _F, _P, _P, _P, _P, _P]),
+    'vod_rpn_decode_topk': (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _F, _F, _P]),
     'vod_test_gemm_nt': (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
 }
 

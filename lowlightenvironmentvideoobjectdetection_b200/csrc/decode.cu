@@ -82,6 +82,34 @@ bbox_decode_kernel(const DecodeParams p) {
     if (lane == 0 && valid) atomicAdd(p.n_valid, valid);
 }
 
+// RPN proposal decode (RPNHead._get_bboxes, mmdet/models/dense_heads/rpn_head.py:163-188 for one level): the anchors and
+// deltas of the nms_pre best-scoring positions (indices from the score sort) -> clipped proposal boxes, one launch for
+// all images.  Same separately-rounded arithmetic as delta2bbox with means 0 / stds 1.
+__global__ void __launch_bounds__(256)
+rpn_decode_kernel(const int64_t *__restrict__ topk_idx /*[B,K]*/, const float *__restrict__ deltas /*[B,A,4]*/,
+                  const float *__restrict__ anchors /*[A,4]*/, float *__restrict__ boxes /*[B*K,4]*/, int B, int K, int A,
+                  float max_ratio, float img_h, float img_w) {
+    const long i = (long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (long)B * K) return;
+    const int b = (int)(i / K);
+    const long a = topk_idx[i];
+    const float4 an = reinterpret_cast<const float4 *>(anchors)[a];
+    const float4 d = reinterpret_cast<const float4 *>(deltas)[(size_t)b * A + a];
+    const float px = __fmul_rn(__fadd_rn(an.x, an.z), 0.5f), py = __fmul_rn(__fadd_rn(an.y, an.w), 0.5f);
+    const float pw = __fsub_rn(an.z, an.x), ph = __fsub_rn(an.w, an.y);
+    // deltas * stds + means with stds = 1, means = 0: x * 1 + 0 is exact, nothing to round
+    const float dw = fminf(fmaxf(d.z, -max_ratio), max_ratio), dh = fminf(fmaxf(d.w, -max_ratio), max_ratio);
+    const float gw = __fmul_rn(pw, expf(dw)), gh = __fmul_rn(ph, expf(dh));
+    const float gx = __fadd_rn(px, __fmul_rn(pw, d.x)), gy = __fadd_rn(py, __fmul_rn(ph, d.y));
+    float x1 = __fsub_rn(gx, __fmul_rn(gw, 0.5f)), y1 = __fsub_rn(gy, __fmul_rn(gh, 0.5f));
+    float x2 = __fadd_rn(gx, __fmul_rn(gw, 0.5f)), y2 = __fadd_rn(gy, __fmul_rn(gh, 0.5f));
+    if (img_w >= 0.f) {
+        x1 = fminf(fmaxf(x1, 0.f), img_w); x2 = fminf(fmaxf(x2, 0.f), img_w);
+        y1 = fminf(fmaxf(y1, 0.f), img_h); y2 = fminf(fmaxf(y2, 0.f), img_h);
+    }
+    reinterpret_cast<float4 *>(boxes)[i] = make_float4(x1, y1, x2, y2);
+}
+
 }  // namespace vod
 
 using namespace vod;
@@ -112,4 +140,17 @@ extern "C" int vod_bbox_decode_candidates(const float *rois, const float *cls_sc
     p.max_ratio = max_ratio; p.img_h = img_h; p.img_w = img_w; p.score_thr = score_thr;
     bbox_decode_kernel<<<ceil_div(N, kDecWarps), kDecWarps * 32, 0, st>>>(p); note_launch();
     return check_launch("vod_bbox_decode_candidates");
+}
+
+extern "C" int vod_rpn_decode_topk(const int64_t *topk_idx, const float *deltas, const float *anchors, float *boxes, int B,
+                                   int K, int A, float max_ratio, float img_h, float img_w, vod_stream_t stream) {
+    if (B == 0 || K == 0) return VOD_OK;
+    VOD_REQUIRE(topk_idx && deltas && anchors && boxes, "vod_rpn_decode_topk: null pointer");
+    VOD_REQUIRE(B > 0 && K > 0 && A >= K, "vod_rpn_decode_topk: bad dims (B=%d K=%d A=%d)", B, K, A);
+    VOD_REQUIRE(((reinterpret_cast<uintptr_t>(deltas) | reinterpret_cast<uintptr_t>(anchors) | reinterpret_cast<uintptr_t>(boxes)) & 15) == 0,
+                "vod_rpn_decode_topk: deltas / anchors / boxes must be 16-byte aligned");
+    rpn_decode_kernel<<<(unsigned)ceil_div((long)B * K, 256L), 256, 0, as_stream(stream)>>>(topk_idx, deltas, anchors, boxes, B, K, A,
+                                                                                           max_ratio, img_h, img_w);
+    note_launch();
+    return check_launch("vod_rpn_decode_topk");
 }

@@ -266,6 +266,24 @@ def multiclass_nms_device(cand_boxes, cand_scores, cand_labels, n_valid, iou_thr
     return dets, labels, count
 
 
+def rpn_decode_topk(topk_idx, deltas, anchors, img_shape=None, wh_ratio_clip=16 / 1000):
+    """topk_idx [B,K] int64, deltas [B,A,4], anchors [A,4] -> proposal boxes [B*K,4] (delta2bbox with means 0 / stds 1,
+    clipped to img_shape = (h, w[, c]) when given)."""
+    _lib.require_cuda(topk_idx, deltas, anchors)
+    topk_idx = topk_idx.to(torch.int64).contiguous()
+    deltas, anchors = _f32c(deltas), _f32c(anchors)
+    B, K = topk_idx.shape
+    A = anchors.shape[0]
+    assert deltas.shape == (B, A, 4)
+    boxes = torch.empty((B * K, 4), dtype=torch.float32, device=deltas.device)
+    if B * K:
+        import math
+        h, w = (float(img_shape[0]), float(img_shape[1])) if img_shape is not None else (-1.0, -1.0)
+        _lib.call('vod_rpn_decode_topk', _lib.ptr(topk_idx), _lib.ptr(deltas), _lib.ptr(anchors), _lib.ptr(boxes), B, K, A,
+                  float(abs(math.log(wh_ratio_clip))), h, w, _lib.stream_ptr(deltas.device))
+    return boxes
+
+
 # ----------------------------------------------------------------------------- (2) warp / FGFA weighting
 def flow_warp(x, flow):
     _lib.require_cuda(x, flow)

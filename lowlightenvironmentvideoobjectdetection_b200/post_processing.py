@@ -128,3 +128,42 @@ def rpn_batched_nms(proposals_list, scores_list, iou_threshold=0.7, max_num=300)
         k = keep[offs[i]:offs[i] + nums[i]]
         out.append(torch.cat([proposals_list[i][k].float(), scores_list[i][k].float()[:, None]], dim=1))
     return out
+
+
+def rpn_get_bboxes_device(cls_scores, bbox_preds, anchors, img_shape, nms_pre=6000, nms_thr=0.7, max_per_img=300):
+    """The proposal stage of RPNHead._get_bboxes (rpn_head.py:126-236) for ONE feature level (the R-50-DC5 configs),
+    all images of the batch at once, fixed shapes, no host synchronisation (CUDA-graph capturable):
+
+    cls_scores [B, A_per, H, W] logits (sigmoid scores), bbox_preds [B, A_per*4, H, W], anchors [H*W*A_per, 4]
+    -> (proposals [B, max_per_img, 5] zero-padded (x1, y1, x2, y2, score), counts [B] int32).
+
+    sigmoid -> best nms_pre positions by score (sorted) -> delta2bbox + clip (one kernel for all images) -> segmented NMS
+    with the bounded-survivor sweep.  ``min_bbox_size`` is 0 in every config of the reference (faster_rcnn_r50_dc5.py:104-110)."""
+    B = cls_scores.shape[0]
+    scores = cls_scores.permute(0, 2, 3, 1).reshape(B, -1).sigmoid()              # :131-135
+    deltas = bbox_preds.permute(0, 2, 3, 1).reshape(B, -1, 4)                      # :143-144
+    A = scores.shape[1]
+    K = min(int(nms_pre), A) if nms_pre > 0 else A
+    ranked, order = scores.sort(dim=1, descending=True)                           # :163-170 (a full sort beats topk here, as the reference notes)
+    top_scores, top_idx = ranked[:, :K].contiguous(), order[:, :K].contiguous()
+    boxes = ops.rpn_decode_topk(top_idx, deltas, anchors, img_shape)              # :187-188
+    offs = [K * i for i in range(B + 1)]
+    keep, num = ops.nms_device(boxes, top_scores.reshape(-1), None, nms_thr, ops.NMS_MODE_AGNOSTIC, seg_offsets=offs,
+                               max_keep=max_per_img)                              # :233-236 (level ids all 0)
+    # keep[b*K : b*K + num[b]] are the kept positions of image b in descending-score order
+    k_idx = keep.view(B, K)[:, :max_per_img]
+    if k_idx.shape[1] < max_per_img:
+        k_idx = torch.nn.functional.pad(k_idx, (0, max_per_img - k_idx.shape[1]))
+    valid = torch.arange(max_per_img, device=keep.device)[None, :] < num[:, None]
+    k_idx = torch.where(valid, k_idx, torch.zeros_like(k_idx))
+    gb = boxes.view(B, K, 4).gather(1, k_idx[:, :, None].expand(-1, -1, 4))
+    gs = top_scores.gather(1, k_idx)
+    props = torch.cat([gb, gs[:, :, None]], dim=2) * valid[:, :, None]
+    return props, num
+
+
+def rpn_get_bboxes(cls_scores, bbox_preds, anchors, img_shape, nms_pre=6000, nms_thr=0.7, max_per_img=300):
+    """List-of-tensors form of ``rpn_get_bboxes_device`` (the reference's result_list, rpn_head.py:219-236): one host
+    read of the per-image counts trims the padded proposals."""
+    props, num = rpn_get_bboxes_device(cls_scores, bbox_preds, anchors, img_shape, nms_pre, nms_thr, max_per_img)
+    return [props[i, :n] for i, n in enumerate(num.tolist())]

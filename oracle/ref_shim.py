@@ -221,3 +221,47 @@ def load():
     )
     _LOADED = ns
     return ns
+
+
+_RPN = None
+
+
+def load_rpn():
+    """The reference's own ``RPNHead._get_bboxes`` and ``DeltaXYWHBBoxCoder`` (files loaded unmodified), for the golden
+    vectors of the RPN proposal stage.  Extra stand-ins: mmcv.ConfigDict (attribute dict),
+    mmcv.jit / mmcv.cnn.normal_init (no-ops), AnchorHead / RPNTestMixin (empty bases: ``_get_bboxes`` only reads
+    ``self.use_sigmoid_cls``, ``self.bbox_coder`` and ``self.test_cfg``)."""
+    global _RPN
+    if _RPN is not None:
+        return _RPN
+    load()
+    mmcv = sys.modules['mmcv']
+
+    class ConfigDict(dict):
+        def __getattr__(self, k):
+            try:
+                return self[k]
+            except KeyError:
+                raise AttributeError(k)
+
+        def __setattr__(self, k, v):
+            self[k] = v
+
+    mmcv.ConfigDict = ConfigDict
+    mmcv.jit = lambda *a, **kw: (lambda fn: fn)
+    sys.modules['mmcv.cnn'].normal_init = lambda *a, **kw: None
+    HEADS = _Registry('head')
+    BBOX_CODERS = _Registry('bbox_coder')
+    sys.modules['mmdet.models.builder'].HEADS = HEADS
+    _mod('mmdet.core.bbox.builder', BBOX_CODERS=BBOX_CODERS)
+    _mod('mmdet.core.bbox.coder')
+    _mod('mmdet.models.dense_heads')
+    _mod('mmdet.models.dense_heads.anchor_head', AnchorHead=type('AnchorHead', (nn.Module,), {}))
+    _mod('mmdet.models.dense_heads.rpn_test_mixin', RPNTestMixin=type('RPNTestMixin', (object,), {}))
+    d = 'mmdetection/mmdet/'
+    _load('mmdet.core.bbox.coder.base_bbox_coder', d + 'core/bbox/coder/base_bbox_coder.py')
+    coder = _load('mmdet.core.bbox.coder.delta_xywh_bbox_coder', d + 'core/bbox/coder/delta_xywh_bbox_coder.py')
+    rpn = _load('mmdet.models.dense_heads.rpn_head', d + 'models/dense_heads/rpn_head.py')
+    _RPN = types.SimpleNamespace(RPNHead=rpn.RPNHead, DeltaXYWHBBoxCoder=coder.DeltaXYWHBBoxCoder,
+                                 delta2bbox=coder.delta2bbox, ConfigDict=ConfigDict)
+    return _RPN

@@ -340,3 +340,24 @@ def get_bboxes(rois, cls_score, bbox_pred, img_shape, scale_factor, rescale, sco
         sf = bboxes.new_tensor(scale_factor)
         bboxes = (bboxes.view(bboxes.size(0), -1, 4) / sf).view(bboxes.size()[0], -1)
     return multiclass_nms(bboxes, scores, score_thr, nms_cfg, max_per_img, return_inds=return_inds)
+
+
+def rpn_get_bboxes(cls_score, bbox_pred, anchors, img_shape, nms_pre=6000, nms_thr=0.7, max_per_img=300,
+                   min_bbox_size=0):
+    """RPNHead._get_bboxes for one image and one feature level (sigmoid scores),
+    mmdetection/mmdet/models/dense_heads/rpn_head.py:126-236:
+    cls_score [A_per, H, W] logits, bbox_pred [A_per*4, H, W], anchors [H*W*A_per, 4] -> dets [<=max_per_img, 5]."""
+    scores = cls_score.permute(1, 2, 0).reshape(-1).sigmoid()                     # :131-135
+    deltas = bbox_pred.permute(1, 2, 0).reshape(-1, 4)                            # :143-144
+    if nms_pre > 0 and scores.shape[0] > nms_pre:                                 # :163-170
+        ranked, rank_inds = scores.sort(descending=True)
+        topk = rank_inds[:nms_pre]
+        scores, deltas, anchors = ranked[:nms_pre], deltas[topk], anchors[topk]
+    proposals = delta2bbox(anchors, deltas, (0., 0., 0., 0.), (1., 1., 1., 1.), max_shape=img_shape)   # :187-188
+    if min_bbox_size > 0:                                                         # :222-231
+        w, h = proposals[:, 2] - proposals[:, 0], proposals[:, 3] - proposals[:, 1]
+        ok = (w >= min_bbox_size) & (h >= min_bbox_size)
+        proposals, scores = proposals[ok], scores[ok]
+    ids = torch.zeros(len(scores), dtype=torch.long)                              # single level -> level id 0
+    dets, _ = batched_nms(proposals, scores, ids, dict(type='nms', iou_threshold=nms_thr))   # :233-235
+    return dets[:max_per_img]

@@ -44,3 +44,12 @@ def rel_err(a, b):
     assert torch.equal(torch.isnan(a), torch.isnan(b)), 'NaN pattern differs'
     a, b = torch.nan_to_num(a, nan=0.0), torch.nan_to_num(b, nan=0.0)
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.fixture(scope='session')
+def rpn_golden():
+    """RPN proposal-stage vectors made by the reference's RPNHead._get_bboxes (tests/golden/make_rpn_golden.py)."""
+    import numpy as np
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'rpn_golden.npz')
+    z = np.load(path)
+    return {k: torch.from_numpy(z[k]) for k in z.files}

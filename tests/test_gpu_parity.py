@@ -443,3 +443,66 @@ def test_temporal_roi_align_sweep_size_properties():
     pick = torch.tensor([0, 999, 15000, 30999])
     want = O.roi_align(ref.cpu(), ref_rois[pick].cpu(), 7, 1 / 16, 2, True)
     assert rel_err(rf[pick], want) < TIGHT
+
+
+# ------------------------------------------------------------------------------------------ RPN proposal stage (row N3)
+def _rpn_compare(props, num, want_list):
+    num = num.tolist()
+    for b, want in enumerate(want_list):
+        assert num[b] == len(want), (b, num[b], len(want))
+        got = props[b, :num[b]].cpu()
+        assert (got - want).abs().max() < 1e-4          # expf on the device vs torch CPU exp: <= 1 ulp of a pixel coordinate
+        assert float(props[b, num[b]:].abs().sum()) == 0.0
+
+
+def test_rpn_get_bboxes_golden(rpn_golden):
+    G = rpn_golden
+    img_shape = tuple(int(v) for v in G['img_shape'])
+    B = G['cls'].shape[0]
+    for tag in ('a', 'b'):
+        nms_pre, thr, mx = G['cfg_' + tag].tolist()
+        props, num = vod.rpn_get_bboxes_device(G['cls'].to(DEV), G['reg'].to(DEV), G['anchors'].to(DEV), img_shape,
+                                               int(nms_pre), thr, int(mx))
+        _rpn_compare(props, num, [G['dets_%s_%d' % (tag, b)] for b in range(B)])
+    lst = vod.rpn_get_bboxes(G['cls'].to(DEV), G['reg'].to(DEV), G['anchors'].to(DEV), img_shape, 600, 0.7, 100)
+    assert [len(x) for x in lst] == [len(G['dets_a_%d' % b]) for b in range(B)]
+
+
+def test_rpn_get_bboxes_full_size_vs_oracle():
+    """R-50-DC5 test shapes: 38 x 63 x 12 = 28 728 anchors per image, nms_pre 6000, IoU 0.7, 300 kept, 4 images."""
+    g = torch.Generator().manual_seed(61)
+    B, H, W, Ap = 4, 38, 63, 12
+    ys, xs = torch.meshgrid(torch.arange(H) * 16., torch.arange(W) * 16., indexing='ij')
+    shift = torch.stack([xs, ys, xs, ys], -1).reshape(-1, 1, 4)
+    base = []
+    for r in (0.5, 1.0, 2.0):
+        for sc in (4, 8, 16, 32):
+            w, h = 16 * sc / r ** 0.5, 16 * sc * r ** 0.5
+            base.append([-w / 2, -h / 2, w / 2, h / 2])
+    anchors = (shift + torch.tensor(base)[None]).reshape(-1, 4)
+    # distinct scores by construction: among equal fp32 sigmoid values the order of the reference's sort (and hence the
+    # greedy NMS) is unspecified; 28 728 random logits would collide a few times per image
+    A = Ap * H * W
+    cls = torch.stack([torch.linspace(-4, 4, A)[torch.randperm(A, generator=g)] for _ in range(B)]).view(B, H, W, Ap).permute(0, 3, 1, 2)
+    reg = torch.randn(B, Ap * 4, H, W, generator=g) * 0.3
+    props, num = vod.rpn_get_bboxes_device(cls.to(DEV), reg.to(DEV), anchors.to(DEV), (600, 1000, 3), 6000, 0.7, 300)
+    # 18 M box pairs per image: a 1-ulp difference between the device expf and torch's CPU exp flips an IoU that sits on the
+    # 0.7 threshold now and then, and greedy NMS then diverges.  So the stage is checked in two exact halves:
+    # (i) selection + decode against the oracle's delta2bbox, (ii) NMS of the device-decoded boxes, bit-exact.
+    scores = cls.permute(0, 2, 3, 1).reshape(B, -1).sigmoid()
+    deltas = reg.permute(0, 2, 3, 1).reshape(B, -1, 4)
+    ranked, order = scores.sort(dim=1, descending=True)
+    top = order[:, :6000]
+    boxes_dev = ops.rpn_decode_topk(top.to(DEV), deltas.to(DEV), anchors.to(DEV), (600, 1000, 3)).cpu().view(B, 6000, 4)
+    num = num.tolist()
+    for b in range(B):
+        want_boxes = O.delta2bbox(anchors[top[b]], deltas[b][top[b]], max_shape=(600, 1000, 3))
+        # 1 ulp of exp() on the pre-clip width (anchor side x up to 62.5, i.e. up to ~32 000 px) is ~4e-3 px
+        diff = (boxes_dev[b] - want_boxes).abs()
+        assert diff.max() < 1e-2 and (diff < 1e-4).float().mean() > 0.999
+        dets, _ = O.batched_nms(boxes_dev[b], ranked[b, :6000], torch.zeros(6000, dtype=torch.long), dict(type='nms', iou_threshold=0.7))
+        dets = dets[:300]
+        assert num[b] == len(dets)
+        got = props[b, :num[b]].cpu()
+        assert torch.equal(got[:, :4], dets[:, :4]) and (got[:, 4] - dets[:, 4]).abs().max() < 1e-6   # sigmoid: device vs CPU
+        assert float(props[b, num[b]:].abs().sum()) == 0.0

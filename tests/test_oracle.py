@@ -101,3 +101,14 @@ def test_oracle_vs_live_reference():
             da, ka = R.batched_nms(boxes, scores, ids, cfg)
             db, kb = O.batched_nms(boxes, scores, ids, cfg)
             assert torch.equal(ka, kb) and torch.equal(da, db)
+
+
+def test_rpn_get_bboxes_matches_reference_golden(rpn_golden):
+    """oracle restatement of RPNHead._get_bboxes == the reference's own method (unmodified file) on the committed vectors."""
+    G = rpn_golden
+    img_shape = tuple(int(v) for v in G['img_shape'])
+    for tag in ('a', 'b'):
+        nms_pre, thr, mx = G['cfg_' + tag].tolist()
+        for b in range(G['cls'].shape[0]):
+            d = O.rpn_get_bboxes(G['cls'][b], G['reg'][b], G['anchors'], img_shape, int(nms_pre), thr, int(mx))
+            assert torch.equal(d, G['dets_%s_%d' % (tag, b)])

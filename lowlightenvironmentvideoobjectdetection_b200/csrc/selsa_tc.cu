@@ -6,15 +6,16 @@
 // One CTA = (128 query rows, head, split of the reference axis).  192 threads:
 //   warps 0-3  softmax: thread = query row; S chunk read from TMEM with tcgen05.ld, online softmax held
 //              entirely in registers (row max / row sum are thread-local, no shuffles), probabilities
-//              written to shared memory in the 128B-swizzled K-major operand layout, partial O read
-//              back from TMEM and accumulated in registers with the running-max correction.
+//              written to shared memory in the 128B-swizzled K-major operand layout.  O is NOT read back per
+//              chunk: it stays in TMEM, exponentials are taken against a per-row reference maximum that is
+//              raised (with a rescale of the row's O and row sum) only when a score outgrows it by 2^64.
 //   warp 4     TMA producer: Q once, then a 3-stage ring of (K chunk, V^T chunk) tiles.
 //   warp 5     MMA issuer: S = Q K^T (kind::tf32 or kind::f16/bf16) into a double-buffered TMEM
-//              accumulator, O_chunk = P V into a third TMEM accumulator; completion via tcgen05.commit.
+//              accumulator, O += P V into a third TMEM accumulator (over all chunks); completion via tcgen05.commit.
 // Reference rows are processed in chunks of 64.  When N*heads/128 CTAs cannot fill 148 SMs the reference
 // axis is split across CTAs and the partial (acc, max, sum) triples are merged by selsa_merge_kernel.
 //
-// TMEM columns: [0,64) S buffer 0, [64,128) S buffer 1, [128,192) O chunk.
+// TMEM columns: [0,64) S buffer 0, [64,128) S buffer 1, [128,192) O.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -69,7 +70,7 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     uint8_t *sV = sK + kKvStages * Cfg::kKBytes;
     uint8_t *sP = sV + kKvStages * Cfg::kVBytes;
     __shared__ uint64_t q_full, kv_full[kKvStages], kv_empty[kKvStages], s_full[2], s_empty[2], p_full[2], p_empty[2],
-        o_full, o_empty;
+        o_full;
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -85,7 +86,6 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             tc::mbar_init(&p_full[i], 128); tc::mbar_init(&p_empty[i], 1);
         }
         tc::mbar_init(&o_full, 1);
-        tc::mbar_init(&o_empty, 128);
         tc::fence_barrier_init();
     }
     if (warp == 5) tc::tmem_alloc(&tmem_slot, kSelsaTmemCols);
@@ -143,8 +143,7 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         for (int j = 0; j < n; ++j) {
             if (j + 1 < n) issue_s(j + 1);
             const int st = j % kKvStages, buf = j & 1;
-            tc::mbar_wait(&p_full[buf], (j >> 1) & 1);
-            tc::mbar_wait(&o_empty, (j & 1) ^ 1);
+            tc::mbar_wait(&p_full[buf], (j >> 1) & 1);   // also orders any rescale of O (done before the P store) before this PV
             tc::tcgen05_fence_after();
             if (tc::elect_one()) {
                 const uint32_t pa = tc::smem_u32(sP + buf * Cfg::kPBytes), va = tc::smem_u32(sV + st * Cfg::kVBytes);
@@ -153,7 +152,7 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         mma(tmem + 2 * kBN, tc::umma_desc_k_sw128(pa + sl * kBM * 128 + k * 32),
-                            tc::umma_desc_k_sw128(va + sl * kHD * 128 + k * 32), (sl | k) != 0);
+                            tc::umma_desc_k_sw128(va + sl * kHD * 128 + k * 32), (j | sl | k) != 0);   // O accumulates over all chunks
                 tc::umma_commit(&o_full);
                 tc::umma_commit(&kv_empty[st]);
                 tc::umma_commit(&p_empty[buf]);
@@ -164,33 +163,19 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         // ------------------------------------------------------------------ softmax / accumulate (warps 0-3)
         const int r = warp * 32 + lane;                       // row within the tile == TMEM lane
         const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
-        // Instruction diet of the softmax warps (one warp per SM sub-partition walks 32 rows serially, so the loop is
-        // issue-bound): packed fp32x2 FMA/ADD (FFMA2/FADD2), ex2.approx on the raw MUFU, the scale folded into the
-        // exponent's FMA, masking only in the tail chunk.  ~1100 -> ~400 instructions per 64-key chunk and thread.
-        float2 acc[kHD / 2];
-#pragma unroll
-        for (int i = 0; i < kHD / 2; ++i) acc[i] = make_float2(0.f, 0.f);
-        float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
+        // O stays in TENSOR MEMORY for the whole pass (the PV MMAs accumulate over all chunks) and the exponentials are
+        // taken against a per-row reference maximum m_ref that is only raised -- with a rescale of the row's O and l -- when
+        // a new score exceeds it by more than 2^kLazy (FlashAttention-4 style lazy rescaling).  With that the softmax
+        // warps never wait for a PV product in the steady state: the first version read every chunk's product back
+        // (acc = acc * corr + O_chunk), a commit -> mbarrier -> tcgen05.ld round trip per 64 reference rows that made
+        // the kernel latency-bound (1970 clk per chunk with the tensor pipe 19 % busy; removing 7/8 of the MMAs,
+        // halving the instructions or doubling the softmax warps did not change its time).
+        // Instruction diet as before: packed fp32x2 FMA/ADD, ex2.approx on the raw MUFU, scale folded into the FMA.
+        constexpr float kLazy = 64.f;   // P <= 2^64: no overflow in fp32 / tf32 / bf16, same relative precision
+        float m_ref = -INFINITY, l_run = 0.f;
         const uint32_t prow = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
         const uint32_t rx = (uint32_t)(r & 7);
         auto ex2 = [](float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; };
-
-        auto consume_o = [&](int j) {
-            tc::mbar_wait(&o_full, j & 1);
-            tc::tcgen05_fence_after();
-            uint32_t o0[32], o1[32];
-            tc::tmem_ld_32x32(tl + 2 * kBN, o0);
-            tc::tmem_ld_32x32(tl + 2 * kBN + 32, o1);
-            tc::tmem_ld_wait();
-            tc::tcgen05_fence_before();
-            tc::mbar_arrive(&o_empty);
-            const float2 c2 = make_float2(corr_prev, corr_prev);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                acc[i] = __ffma2_rn(acc[i], c2, make_float2(__uint_as_float(o0[2 * i]), __uint_as_float(o0[2 * i + 1])));
-                acc[16 + i] = __ffma2_rn(acc[16 + i], c2, make_float2(__uint_as_float(o1[2 * i]), __uint_as_float(o1[2 * i + 1])));
-            }
-        };
 
         for (int j = 0; j < n; ++j) {
             const int buf = j & 1;
@@ -214,17 +199,45 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             float mx = s[0];
 #pragma unroll
             for (int i = 1; i < kBN; ++i) mx = fmaxf(mx, s[i]);
-            const float m_new = fmaxf(m_run, mx * p.scale_log2);   // scale > 0: max commutes with the scaling
-            const float corr = ex2(m_run - m_new);                 // m_run = -inf on the first chunk -> 0
-            const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_new, -m_new);
+            const float m_new = mx * p.scale_log2;                 // scale > 0: max commutes with the scaling
+            if (j == 0) {
+                m_ref = m_new;                                     // O is still empty (PV(0) overwrites it)
+            } else if (__any_sync(0xffffffffu, m_new > m_ref + kLazy)) {
+                // rare: some row of this warp outgrew its reference maximum.  All PV products issued so far (chunks < j) must
+                // have landed; PV(j) cannot start before this thread's p_full arrival below.  tcgen05.ld/st are warp-wide,
+                // rows that do not need it rescale by 1.
+                tc::mbar_wait(&o_full, (j - 1) & 1);
+                tc::tcgen05_fence_after();
+                const bool need = m_new > m_ref + kLazy;
+                const float f = need ? ex2(m_ref - m_new) : 1.0f;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t o[32];
+                    tc::tmem_ld_32x32(tl + 2 * kBN + half * 32, o);
+                    tc::tmem_ld_wait();
+                    uint32_t lo[16], hi[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        lo[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+                        hi[i] = __float_as_uint(__uint_as_float(o[16 + i]) * f);
+                    }
+                    tc::tmem_st_32x16(tl + 2 * kBN + half * 32, lo);
+                    tc::tmem_st_32x16(tl + 2 * kBN + half * 32 + 16, hi);
+                }
+                tc::tmem_st_wait();
+                tc::tcgen05_fence_before();
+                l_run *= f;
+                if (need) m_ref = m_new;
+            }
+            const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_ref, -m_ref);
             float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll
             for (int i = 0; i < kBN; i += 2) {
-                const float2 t = __ffma2_rn(make_float2(s[i], s[i + 1]), sc2, nm2);   // raw * scale - m  (-inf stays -inf)
+                const float2 t = __ffma2_rn(make_float2(s[i], s[i + 1]), sc2, nm2);   // raw * scale - m_ref  (-inf stays -inf)
                 s[i] = ex2(t.x); s[i + 1] = ex2(t.y);
                 sum2 = __fadd2_rn(sum2, make_float2(s[i], s[i + 1]));
             }
-            l_run = fmaf(l_run, corr, sum2.x + sum2.y);
+            l_run += sum2.x + sum2.y;
 
             tc::mbar_wait(&p_empty[buf], ((j >> 1) & 1) ^ 1);
             uint8_t *pb = sP + buf * Cfg::kPBytes + prow;
@@ -254,12 +267,21 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
             tc::fence_proxy_async();
             tc::mbar_arrive(&p_full[buf]);
-
-            if (j > 0) consume_o(j - 1);
-            corr_prev = corr;
-            m_run = m_new;
         }
-        consume_o(n - 1);
+        // the finished accumulator: all PV products have landed once the last commit fires
+        tc::mbar_wait(&o_full, (n - 1) & 1);
+        tc::tcgen05_fence_after();
+        float acc[kHD];
+        {
+            uint32_t o0[32], o1[32];
+            tc::tmem_ld_32x32(tl + 2 * kBN, o0);
+            tc::tmem_ld_32x32(tl + 2 * kBN + 32, o1);
+            tc::tmem_ld_wait();
+            tc::tcgen05_fence_before();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { acc[i] = __uint_as_float(o0[i]); acc[32 + i] = __uint_as_float(o1[i]); }
+        }
+        const float m_run = m_ref;
 
         const int row = rt * kBM + r;
         if (row < p.N) {
@@ -269,13 +291,13 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < kHD; i += 4)
                     *reinterpret_cast<float4 *>(dst + i) =
-                        make_float4(acc[i / 2].x * inv, acc[i / 2].y * inv, acc[i / 2 + 1].x * inv, acc[i / 2 + 1].y * inv);
+                        make_float4(acc[i] * inv, acc[i + 1] * inv, acc[i + 2] * inv, acc[i + 3] * inv);
             } else {
                 const size_t pr = ((size_t)split * p.heads + h) * p.Npad + row;
                 float *dst = p.part_acc + pr * kHD;
 #pragma unroll
                 for (int i = 0; i < kHD; i += 4)
-                    *reinterpret_cast<float4 *>(dst + i) = make_float4(acc[i / 2].x, acc[i / 2].y, acc[i / 2 + 1].x, acc[i / 2 + 1].y);
+                    *reinterpret_cast<float4 *>(dst + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
                 p.part_m[pr] = m_run;
                 p.part_l[pr] = l_run;
             }

@@ -189,7 +189,7 @@ def kernel_rooflines(cfg, device, peaks):
         roi_unit = torch.nn.functional.normalize(key_rows, dim=1).bfloat16()
         t = timeit(lambda: ops.msra_gemm_candidates(roi_unit, unit, T), iters=3)
         out['msra_gemm_topk_kernel'] = dict(bound='tensor', seconds=t, achieved=fl / t / 1e12, peak=peaks['tf_burst'], unit='TFLOP/s', flops=fl,
-                                            traffic=55.8e6, note='traffic = dram read+write per launch from ncu --set full (profiles/)')
+                                            traffic=54.8e6, note='traffic = dram read+write per launch from ncu --set full (profiles/r01g_ncu_full_summary.csv)')
         # (4') TAFA weighting: bytes = (2*(T+1)+1)*N*C*P*4
         x_all = torch.randn(T + 1, N, P, C, device=device, generator=g)
         emb = torch.randn(T + 1, N, P, C, device=device, generator=g)

@@ -106,18 +106,27 @@ def require_cuda(*tensors):
 
 
 class Workspace:
-    """Grow-only per-device scratch buffer, 1024-byte aligned (TMA-swizzled tiles need it; torch's caching
-    allocator only guarantees 512)."""
+    """Scratch memory for the kernels, 1024-byte aligned (TMA-swizzled tiles need it; torch's caching allocator only
+    guarantees 512).  One grow-only buffer per (device, stream): callers on different streams never share scratch
+    (SURVEY 8b threading contract).  While a CUDA graph is being captured nothing is cached: every request is a fresh
+    allocation from the graph's private pool, so a replay can never touch a buffer that was later outgrown and freed."""
 
     def __init__(self):
         self._buf = {}
 
+    @staticmethod
+    def _aligned(nbytes, device):
+        raw = torch.empty(max(int(nbytes), 1024) + 1024, dtype=torch.uint8, device=device)
+        off = (-raw.data_ptr()) % 1024
+        return raw[off:off + max(int(nbytes), 1024)]
+
     def get(self, nbytes, device):
-        key = (device.type, device.index)
+        if device.type == 'cuda' and torch.cuda.is_current_stream_capturing():
+            return self._aligned(nbytes, device)
+        stream = torch.cuda.current_stream(device).cuda_stream if device.type == 'cuda' else 0
+        key = (device.type, device.index, stream)
         buf = self._buf.get(key)
         if buf is None or buf.numel() < nbytes:
-            raw = torch.empty(max(int(nbytes), 1024) + 1024, dtype=torch.uint8, device=device)
-            off = (-raw.data_ptr()) % 1024
-            buf = raw[off:off + max(int(nbytes), 1024)]
+            buf = self._aligned(nbytes, device)
             self._buf[key] = buf
         return buf

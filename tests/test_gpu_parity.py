@@ -506,3 +506,46 @@ def test_rpn_get_bboxes_full_size_vs_oracle():
         got = props[b, :num[b]].cpu()
         assert torch.equal(got[:, :4], dets[:, :4]) and (got[:, 4] - dets[:, 4]).abs().max() < 1e-6   # sigmoid: device vs CPU
         assert float(props[b, num[b]:].abs().sum()) == 0.0
+
+
+def test_workspace_is_private_to_graphs_and_streams():
+    """Scratch memory: (i) a captured graph keeps its own scratch -- growing the eager workspace afterwards (bigger problem)
+    and churning the allocator must not disturb replays; (ii) two streams running different problems concurrently do not
+    share a scratch buffer."""
+    g = torch.Generator(device=DEV).manual_seed(70)
+    q = torch.randn(130, 256, device=DEV, generator=g)
+    k = torch.randn(700, 256, device=DEV, generator=g)
+    v = torch.randn(700, 256, device=DEV, generator=g)
+    want = ops.selsa_attention(q, k, v, 4).clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ops.selsa_attention(q, k, v, 4)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = ops.selsa_attention(q, k, v, 4)
+    # outgrow the eager workspace, then fill freed memory with garbage
+    big = ops.selsa_attention(torch.randn(600, 1024, device=DEV, generator=g), torch.randn(9000, 1024, device=DEV, generator=g),
+                              torch.randn(9000, 1024, device=DEV, generator=g), 16)
+    junk = [torch.full((1 << 22,), float('nan'), device=DEV) for _ in range(8)]
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, want)
+    del junk, big
+    # two streams, two problems, interleaved launches
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    rows = torch.relu(torch.randn(6 * 49, 128, device=DEV, generator=g))
+    ref = torch.relu(torch.randn(3, 128, 12, 20, device=DEV, generator=g))
+    nh, norm, unit = ops.to_nhwc(ref, want_norm=True, want_unit_bf16=True)
+    want2 = ops.msra_topk_sample(rows, nh, 2, ref_norm=norm, ref_unit=unit).clone()
+    torch.cuda.synchronize()
+    outs1, outs2 = [], []
+    for _ in range(10):
+        with torch.cuda.stream(s1):
+            outs1.append(ops.selsa_attention(q, k, v, 4))
+        with torch.cuda.stream(s2):
+            outs2.append(ops.msra_topk_sample(rows, nh, 2, ref_norm=norm, ref_unit=unit))
+    torch.cuda.synchronize()
+    assert all(torch.equal(o, want) for o in outs1) and all(torch.equal(o, want2) for o in outs2)

@@ -108,7 +108,7 @@ def run_step(head, ref_x, props_all, metas):
 class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz, self.first = index, [], set(), False, None, 0
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -138,7 +138,7 @@ class ClockSampler(threading.Thread):
             time.sleep(0.05)
 
     def summary(self):
-        s = sorted(self.samples)
+        s = sorted(self.samples[self.first:] or self.samples)
         return dict(sm_mhz=(s[len(s) // 2] if s else None), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons))
 
 
@@ -420,12 +420,15 @@ def main():
             det_cnt[i:i + 1] = g_count
 
         # ------------------------------------------------ device-resident throughput (graph replay)
+        # the clock sampler starts before the warm-up: NVML's first queries take tens of ms and serialise with the CUDA
+        # driver (seen as a 30 ms stall of the first timed replays at 8 ranks); only samples taken after e0 are reported
+        sampler = ClockSampler(local_rank)
+        sampler.start()
         for i in range(args.warmup):
             graph_step(0, dev_sets[i % n_sets])
         gather_detections()   # warm the collective (communicator / channel setup is not part of a steady-state step)
         barrier()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
+        sampler.first, sampler.reasons = len(sampler.samples), set()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(args.steps):

@@ -219,3 +219,22 @@ def test_msra_candidate_recall_full_scale():
     want = out0.permute(0, 1, 3, 4, 2).reshape(T, N * 49, C)
     ok = same.t().unsqueeze(-1)                                  # [T, NP, 1]
     assert rel_err(torch.where(ok, got, want), want) < 1e-4
+
+
+def test_msra_unit_operand_without_padding_is_copied():
+    """HW % 4 != 0: the tensor-core pass may touch 3 rows past the unit-norm copy (include/vodagg.h).  ``to_nhwc`` allocates
+    them; a caller-made tensor without slack (clone) is copied into a padded buffer by the Python layer."""
+    g = torch.Generator().manual_seed(5)
+    C, T, H, W = 128, 2, 9, 15                       # HW = 135
+    ref = torch.relu(torch.randn(T, C, H, W, generator=g)).to('cuda')
+    rows = torch.relu(torch.randn(3 * 49, C, generator=g)).to('cuda')
+    nh, norm, unit = ops.to_nhwc(ref, want_norm=True, want_unit_bf16=True)
+    assert unit.untyped_storage().nbytes() >= (T * H * W + 3) * C * 2
+    tight = unit.clone()
+    assert ops._padded_unit(unit, T * H * W).data_ptr() == unit.data_ptr()
+    assert ops._padded_unit(tight, T * H * W).data_ptr() != tight.data_ptr()
+    a = ops.msra_topk_sample(rows, nh, 2, ref_norm=norm, ref_unit=unit, impl=ops.IMPL_TC, return_indices=True)
+    b = ops.msra_topk_sample(rows, nh, 2, ref_norm=norm, ref_unit=tight, impl=ops.IMPL_TC, return_indices=True)
+    c = ops.msra_topk_sample(rows, nh, 2, impl=ops.IMPL_TC, return_indices=True)     # norms / unit copy made by the library
+    for x, y in ((a, b), (a, c)):
+        assert torch.equal(x[0], y[0]) and torch.equal(x[1], y[1])

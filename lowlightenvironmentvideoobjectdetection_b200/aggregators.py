@@ -116,8 +116,10 @@ class EmbedAggregator(nn.Module):
             Tensor: The aggregated feature map with shape [1, C, H, W].
         """
         assert len(x.shape) == 4 and len(x) == 1, "Only support 'batch_size == 1' for x"
-        x_embed = self._embed(x.float())                        # embed_aggregator.py:68-70
-        ref_x_embed = self._embed(ref_x.float())                # :73-75
+        # the embed convs run in the module's own dtype, as in the reference (a bf16 / fp16 model keeps its convs there);
+        # the weighting kernel up-converts the embeddings and computes in fp32
+        x_embed = self._embed(x)                                # embed_aggregator.py:68-70
+        ref_x_embed = self._embed(ref_x)                        # :73-75
         # :71-81 fused: cosine over C, softmax over frames, weighted sum of the raw ref features
         return ops.embed_weighted_sum(x_embed, ref_x_embed, ref_x).to(x.dtype)
 
@@ -132,6 +134,6 @@ class EmbedAggregator(nn.Module):
         warped = flow_warp_feats(raw_ref_x, flows)
         if key_slot >= 0:
             warped[key_slot] = x[0]
-        x_embed = self._embed(x.float())
-        ref_x_embed = self._embed(warped.float())
+        x_embed = self._embed(x)
+        ref_x_embed = self._embed(warped)
         return ops.fgfa_warp_weighted_sum(x_embed, ref_x_embed, raw_ref_x, flows, key_x=x, key_slot=key_slot).to(x.dtype)

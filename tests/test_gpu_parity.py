@@ -549,3 +549,58 @@ def test_workspace_is_private_to_graphs_and_streams():
             outs2.append(ops.msra_topk_sample(rows, nh, 2, ref_norm=norm, ref_unit=unit))
     torch.cuda.synchronize()
     assert all(torch.equal(o, want) for o in outs1) and all(torch.equal(o, want2) for o in outs2)
+
+
+def test_fgfa_path_cfg2_bf16_io():
+    """BASELINE config 2 (FGFA, 2 reference frames + key, C=512, 38x63, flow 608x1008) with bf16 feature maps and a bf16
+    module, as the config states.  The kernels compute in fp32 on the up-converted maps and hand back bf16; the embed conv
+    runs in bf16.  Stated bf16 tolerance: 2e-2 relative for the aggregated map (bf16 conv inputs + bf16 output rounding),
+    4e-3 (one bf16 rounding of the result) for the warp alone -- against the fp32 oracle on the same bf16-rounded inputs."""
+    g = torch.Generator().manual_seed(71)
+    T, C, H, W = 3, 512, 38, 63
+    x = torch.randn(1, C, H, W, generator=g).bfloat16()
+    mem = torch.randn(T, C, H, W, generator=g).bfloat16()
+    flow = torch.randn(T, 2, H * 16, W * 16, generator=g) * 8
+    warped = vod.flow_warp_feats(mem.to(DEV), flow.to(DEV))
+    assert warped.dtype == torch.bfloat16
+    want_w = O.flow_warp_feats(mem.float(), flow)
+    assert rel_err(warped.float(), want_w) < 4e-3
+    torch.manual_seed(0)
+    m = vod.build_aggregator(dict(type='EmbedAggregator', num_convs=1, channels=C, kernel_size=3, act_cfg=None))
+    convs = [(m.embed_convs[0].conv.weight.detach().bfloat16().float(), m.embed_convs[0].conv.bias.detach().bfloat16().float(), False)]
+    m = m.to(DEV).bfloat16()
+    out = m(x.to(DEV), warped)
+    assert out.dtype == torch.bfloat16 and out.shape == (1, C, H, W)
+    want = O.embed_aggregate(x.float(), warped.float().cpu(), convs)
+    assert rel_err(out.float(), want) < 2e-2
+
+
+@pytest.mark.parametrize('troi,fcs', [(False, 2), (True, 3)])
+def test_selsa_roi_head_step_vs_oracle(troi, fcs):
+    """One key-frame step through SelsaRoIHead.simple_test against the same step on the CPU oracle: BASELINE config 1
+    (plain SingleRoIExtractor, 2 aggregator layers, 2 refs + key) and config 3 (TemporalRoIAlign, 3 layers), small shapes."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator().manual_seed(80 + fcs)
+    C, H, W, N, T, D, classes = 64, 12, 20, 30, 3, 128, 6
+    head = _head(C, D, classes, fcs, troi)
+    ref_x = torch.relu(torch.randn(T, C, H, W, generator=g))
+    x = ref_x[T - 1:T].clone()
+    props = [rpn_like_rois(g, N, 1, W * 16., H * 16.)[:, 1:]]
+    ref_props = [rpn_like_rois(g, N, 1, W * 16., H * 16.)[:, 1:] for _ in range(T)]
+    metas = [dict(img_shape=(H * 16, W * 16, 3), scale_factor=(1., 1., 1., 1.))]
+    dets, labels = head.simple_test((x.to(DEV),), (ref_x.to(DEV),), [p.to(DEV) for p in props], [p.to(DEV) for p in ref_props], metas)
+    sd = {k: v.detach().cpu() for k, v in head.state_dict().items()}
+    rois, ref_rois = vod.bbox2roi(props), vod.bbox2roi(ref_props)
+    if troi:
+        feats = O.temporal_roi_align(x, rois, ref_x, sd['bbox_roi_extractor.embed_network.conv.weight'],
+                                     sd['bbox_roi_extractor.embed_network.conv.bias'], 2, 4)
+    else:
+        feats = O.roi_align(x, rois, 7, 1 / 16, 2, True)
+    ref_feats = O.roi_align(ref_x, ref_rois, 7, 1 / 16, 2, True)
+    hp = {k[len('bbox_head.'):]: v for k, v in sd.items() if k.startswith('bbox_head.')}
+    cls, reg = O.selsa_bbox_head(feats, ref_feats, hp, fcs, 2)
+    d0, l0 = O.get_bboxes(rois, cls, reg, (H * 16, W * 16, 3), (1., 1., 1., 1.), False, 0.0001, dict(type='nms', iou_threshold=0.5), 100)
+    d1, l1 = dets[0].cpu(), labels[0].cpu()
+    assert d1.shape == d0.shape and torch.equal(l1, l0)
+    assert (d1 - d0).abs().max() < 1e-2      # boxes in px and scores after 2-3 tf32 SELSA layers

@@ -57,17 +57,25 @@ class SelsaAggregator(nn.Module):
         if use_vt:
             # ref_fc (:64) emitted directly as V^T [C, M] (same GEMM, no transposition pass): the
             # tensor-core kernel wants the reference axis contiguous for the P.V product.
-            ldv = (ref_roi_n + 7) // 8 * 8
+            # row stride of V^T: a multiple of 16 bytes (TMA).  fp32: 4 elements -- M = 4500 then needs no padding and the
+            # GEMM writes straight into a contiguous buffer (a strided `out=` costs a temporary + a copy pass per layer)
+            align = 8 if self.compute_dtype == torch.bfloat16 else 4
+            ldv = (ref_roi_n + align - 1) // align * align
             vt = torch.empty((q.shape[1], ldv), dtype=torch.float32, device=x.device)
             if ldv != ref_roi_n:
                 vt[:, ref_roi_n:].zero_()
-            torch.addmm(self.ref_fc.bias.float()[:, None], self.ref_fc.weight.float(), ref_x.t(), out=vt[:, :ref_roi_n])
+            # softmax rows sum to one, so the bias of ref_fc passes through the attention unchanged: P (V0 + 1 b^T) = P V0 + b.
+            # It is added to the [N, C] result below instead of being broadcast into the [C, M] operand first (which costs
+            # a full copy pass: torch materialises the broadcast bias in the output before the GEMM).
+            torch.mm(self.ref_fc.weight.float(), ref_x.t(), out=vt[:, :ref_roi_n])
             v = vt
         else:
             v = self.ref_fc(ref_x)
         if self.compute_dtype == torch.bfloat16:
             q, k, v = q.bfloat16(), k.bfloat16(), v.bfloat16()
         o = ops.selsa_attention(q, k, v, self.num_attention_blocks, v_transposed=use_vt, impl=self.impl)  # :61-70
+        if use_vt:
+            o += self.ref_fc.bias.float()
         x_new = self.fc(o.view(roi_n, -1))                     # :72
         return x_new.to(in_dtype)
 

@@ -186,7 +186,11 @@ class TemporalRoIAlign(SingleRoIExtractor):
             conv = self.embed_network.conv
             # temporal_roi_align.py:74 -- the conv runs without its bias; the bias is added on load inside
             # the weighting kernel (saves a full read+write pass over the [T+1,N,49,C] embedding)
-            emb = torch.nn.functional.conv2d(patches, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+            # the weight in channels_last too (cached): otherwise cuDNN re-lays it out on every call (a 2.4 M element copy)
+            key = (conv.weight._version, conv.weight.data_ptr())
+            if getattr(self, '_w_cl', None) is None or self._w_cl[0] != key:
+                self._w_cl = (key, conv.weight.detach().contiguous(memory_format=torch.channels_last))
+            emb = torch.nn.functional.conv2d(patches, self._w_cl[1], None, conv.stride, conv.padding, conv.dilation, conv.groups)
             emb = emb.permute(0, 2, 3, 1).contiguous().view(T1, N, P, C)  # no copy: cuDNN keeps channels_last
             out = ops.tafa_weighted_sum(x_all, emb, self.num_temporal_attention_blocks, emb_bias=conv.bias,
                                         out_nhwc=cl_out)

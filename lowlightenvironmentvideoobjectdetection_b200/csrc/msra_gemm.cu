@@ -4,7 +4,7 @@
 // mmtracking/mmtrack/models/roi_heads/roi_extractors/temporal_roi_align.py:99-181:
 //   sim[row, t, loc] = <roi_unit[row, :], ref_unit[t, loc, :]>,  top-k over loc per (row, t).
 // The [N*49, T*HW] similarity matrix (2.1 GB fp32 at N=300, T=15) is never written: the epilogue keeps a
-// running top-8 per (row, frame) in registers while the accumulator tile is read out of TMEM.  The
+// running top-4 per (row, frame, interleaved location group) in registers while the accumulator tile is read out of TMEM.  The
 // candidates are then re-scored in exact fp32 (msra_rescore_kernel, tafa.cu) so that the selected
 // locations match the fp32 reference; the bf16 GEMM is only a pre-filter.
 //
@@ -12,10 +12,12 @@
 // a work unit = (PAIR of adjacent 128-row tiles, frame t), i.e. a 256-row x HW similarity slab:
 //   A tile   (128 RoI rows x C bf16 per CTA) lives in TENSOR MEMORY, not shared memory: row r in TMEM lane r, two
 //            bf16 per 32-bit column (256 columns for C = 512), written with tcgen05.st by epilogue warps 0-3
-//            whenever the row tile changes and consumed by the TS form of tcgen05.mma.  That frees all 208 KB of
+//            whenever the row tile changes and consumed by the TS form of tcgen05.mma.  That frees all of the
 //            shared memory for the B ring.
-//   warp 16  TMA producer (both CTAs): each CTA loads HALF of every B stage (64 of the 128 locations x 64 channels,
-//            SWIZZLE_128B) and signals the leader's mbarrier; 26 stages x 8 KB in flight per CTA
+//   warp 16  TMA producer (both CTAs): each CTA loads HALF of every B stage (64 of the tile's 128 locations, all C
+//            channels) with ONE 5-D TMA box (64 channels | 32 x 2 interleaved locations | frame | 8 K slices ->
+//            eight SWIZZLE_128B sub-tiles, 64 KB) and signals the leader's mbarrier; 3 stages per CTA.  One copy
+//            per 8 KB had left the TMA unit, not the tensor pipe, in charge of the pace (26 stages, 535 us).
 //   warp 17  MMA issuer (leader CTA only): tcgen05.mma.cta_group::2 kind::f16 (bf16 in, fp32 accumulate), M = 256
 //            over the pair, N = 128; accumulator double buffered in each CTA's TMEM (2 x 128 columns; TMEM total:
 //            256 accumulator + 256 A = 512 columns); commits are multicast to both CTAs' barriers
@@ -25,7 +27,8 @@
 //            keeps the 4 largest keys in registers -- no divergence although the 32 lanes of a warp follow 32
 //            different rows; one 16-byte store per (row, frame, column group) at the end
 // Units are assigned to clusters in contiguous ranges so the A tile is reloaded only when the row-tile pair changes.
-// History (profiles/r01_bench_history.md): 5-stage smem-A 1-CTA 1108 us -> TMEM-A 13-stage 1-CTA 641 us -> CTA pair 555 us.
+// History (profiles/r01_bench_history.md): 5-stage smem-A 1-CTA 1108 us -> TMEM-A 13-stage 1-CTA 641 us -> CTA pair 555 us ->
+// whole-tile 64 KB TMA stages 395 us -> FMA-pipe key packing 380 us (+ interleaved 5-D boxes, same speed).
 #include <cuda_bf16.h>
 
 #include "common.cuh"

@@ -39,8 +39,7 @@ struct SelsaCfg {
     static constexpr int kQBytes = kSlices * kBM * 128;
     static constexpr int kKBytes = kSlices * kBN * 128;
     static constexpr int kVBytes = kSlices * kHD * 128;
-    static constexpr int kPBytes = kSlices * kBM * 128;
-    static constexpr int kSmem = kQBytes + kKvStages * (kKBytes + kVBytes) + 2 * kPBytes + 1024;
+    static constexpr int kSmem = kQBytes + kKvStages * (kKBytes + kVBytes) + 1024;   // P never touches shared memory
 };
 
 struct SelsaParams {
@@ -68,9 +67,7 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     uint8_t *sQ = smem;
     uint8_t *sK = sQ + Cfg::kQBytes;
     uint8_t *sV = sK + kKvStages * Cfg::kKBytes;
-    uint8_t *sP = sV + kKvStages * Cfg::kVBytes;
-    __shared__ uint64_t q_full, kv_full[kKvStages], kv_empty[kKvStages], s_full[2], s_empty[2], p_full[2], p_empty[2],
-        o_full;
+    __shared__ uint64_t q_full, kv_full[kKvStages], kv_empty[kKvStages], s_full[2], s_empty[2], p_full[2], o_full;
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -82,8 +79,8 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tc::mbar_init(&q_full, 1);
         for (int i = 0; i < kKvStages; ++i) { tc::mbar_init(&kv_full[i], 1); tc::mbar_init(&kv_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
-            tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 128);
-            tc::mbar_init(&p_full[i], 128); tc::mbar_init(&p_empty[i], 1);
+            tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 1);
+            tc::mbar_init(&p_full[i], 128);
         }
         tc::mbar_init(&o_full, 1);
         tc::fence_barrier_init();
@@ -146,16 +143,20 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             tc::mbar_wait(&p_full[buf], (j >> 1) & 1);   // also orders any rescale of O (done before the P store) before this PV
             tc::tcgen05_fence_after();
             if (tc::elect_one()) {
-                const uint32_t pa = tc::smem_u32(sP + buf * Cfg::kPBytes), va = tc::smem_u32(sV + st * Cfg::kVBytes);
+                // O += P V with P read from TENSOR MEMORY (TS form): the softmax warps wrote it over the S tile in place, so
+                // the probabilities never pass through shared memory (that round trip was 64 KB of the 160 KB of
+                // shared-memory traffic per 64-row chunk which bounded the first versions of this kernel)
+                const uint32_t va = tc::smem_u32(sV + st * Cfg::kVBytes);
+                constexpr int kSteps = 4 * Cfg::kSlices;   // MMAs of 32 bytes of K: 8 tf32 or 16 bf16 reference rows = 8 TMEM columns
 #pragma unroll
-                for (int sl = 0; sl < Cfg::kSlices; ++sl)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        mma(tmem + 2 * kBN, tc::umma_desc_k_sw128(pa + sl * kBM * 128 + k * 32),
-                            tc::umma_desc_k_sw128(va + sl * kHD * 128 + k * 32), (j | sl | k) != 0);   // O accumulates over all chunks
+                for (int i = 0; i < kSteps; ++i) {
+                    const uint64_t vb = tc::umma_desc_k_sw128(va + (i >> 2) * kHD * 128 + (i & 3) * 32);
+                    if (BF16) tc::umma_f16_ts(tmem + 2 * kBN, tmem + buf * kBN + i * 8, vb, idesc, (j | i) != 0);
+                    else tc::umma_tf32_ts(tmem + 2 * kBN, tmem + buf * kBN + i * 8, vb, idesc, (j | i) != 0);   // O accumulates over all chunks
+                }
                 tc::umma_commit(&o_full);
                 tc::umma_commit(&kv_empty[st]);
-                tc::umma_commit(&p_empty[buf]);
+                tc::umma_commit(&s_empty[buf]);   // the S/P tile may be overwritten by S(j + 2)
             }
             __syncwarp();
         }
@@ -173,8 +174,6 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         // Instruction diet as before: packed fp32x2 FMA/ADD, ex2.approx on the raw MUFU, scale folded into the FMA.
         constexpr float kLazy = 64.f;   // P <= 2^64: no overflow in fp32 / tf32 / bf16, same relative precision
         float m_ref = -INFINITY, l_run = 0.f;
-        const uint32_t prow = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
-        const uint32_t rx = (uint32_t)(r & 7);
         auto ex2 = [](float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; };
 
         for (int j = 0; j < n; ++j) {
@@ -185,8 +184,6 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             tc::tmem_ld_32x32(tl + buf * kBN, s0);
             tc::tmem_ld_32x32(tl + buf * kBN + 32, s1);
             tc::tmem_ld_wait();
-            tc::tcgen05_fence_before();
-            tc::mbar_arrive(&s_empty[buf]);
 
             const int valid = min(kBN, p.M - (c0 + j) * kBN);  // reference rows of this chunk that exist
             float s[kBN];
@@ -239,33 +236,31 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
             l_run += sum2.x + sum2.y;
 
-            tc::mbar_wait(&p_empty[buf], ((j >> 1) & 1) ^ 1);
-            uint8_t *pb = sP + buf * Cfg::kPBytes + prow;
+            // P overwrites this row's S values in place (thread = row = TMEM lane): tf32 one value per column, bf16 two
             if (BF16) {
+                uint32_t pk[32];
 #pragma unroll
-                for (uint32_t c16 = 0; c16 < 8; ++c16) {
-                    __nv_bfloat162 h0 = __floats2bfloat162_rn(s[c16 * 8 + 0], s[c16 * 8 + 1]);
-                    __nv_bfloat162 h1 = __floats2bfloat162_rn(s[c16 * 8 + 2], s[c16 * 8 + 3]);
-                    __nv_bfloat162 h2 = __floats2bfloat162_rn(s[c16 * 8 + 4], s[c16 * 8 + 5]);
-                    __nv_bfloat162 h3 = __floats2bfloat162_rn(s[c16 * 8 + 6], s[c16 * 8 + 7]);
-                    uint4 v;
-                    v.x = *reinterpret_cast<uint32_t *>(&h0); v.y = *reinterpret_cast<uint32_t *>(&h1);
-                    v.z = *reinterpret_cast<uint32_t *>(&h2); v.w = *reinterpret_cast<uint32_t *>(&h3);
-                    *reinterpret_cast<uint4 *>(pb + ((c16 ^ rx) << 4)) = v;
+                for (int i = 0; i < 32; ++i) {
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(s[2 * i], s[2 * i + 1]);   // .x (even reference row) in the low half
+                    pk[i] = *reinterpret_cast<uint32_t *>(&h2);
                 }
+                uint32_t a16[16], b16[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { a16[i] = pk[i]; b16[i] = pk[16 + i]; }
+                tc::tmem_st_32x16(tl + buf * kBN, a16);
+                tc::tmem_st_32x16(tl + buf * kBN + 16, b16);
             } else {
 #pragma unroll
-                for (int sl = 0; sl < 2; ++sl)
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t c16[16];
+                    // + half a tf32 ulp: the MMA truncates the low 13 bits, together = cvt.rna.tf32 (one IADD instead of two ops)
 #pragma unroll
-                    for (uint32_t c16 = 0; c16 < 8; ++c16) {
-                        uint4 v;
-                        // + half a tf32 ulp: the MMA truncates the low 13 bits, together = cvt.rna.tf32 (one IADD instead of two ops)
-                        v.x = __float_as_uint(s[sl * 32 + c16 * 4 + 0]) + 0x1000u; v.y = __float_as_uint(s[sl * 32 + c16 * 4 + 1]) + 0x1000u;
-                        v.z = __float_as_uint(s[sl * 32 + c16 * 4 + 2]) + 0x1000u; v.w = __float_as_uint(s[sl * 32 + c16 * 4 + 3]) + 0x1000u;
-                        *reinterpret_cast<uint4 *>(pb + sl * kBM * 128 + ((c16 ^ rx) << 4)) = v;
-                    }
+                    for (int i = 0; i < 16; ++i) c16[i] = __float_as_uint(s[q * 16 + i]) + 0x1000u;
+                    tc::tmem_st_32x16(tl + buf * kBN + q * 16, c16);
+                }
             }
-            tc::fence_proxy_async();
+            tc::tmem_st_wait();
+            tc::tcgen05_fence_before();
             tc::mbar_arrive(&p_full[buf]);
         }
         // the finished accumulator: all PV products have landed once the last commit fires

@@ -56,7 +56,9 @@ SELSA_TF32_TOL = 1e-3    # north_star bar: aggregated features within 1e-3 relat
 SELSA_BF16_TOL = 2e-2    # bf16 operands (8-bit mantissa): stated separately
 
 
-@pytest.mark.parametrize('N,M,heads', [(37, 300, 2), (128, 64, 1), (300, 900, 16), (300, 4500, 16), (130, 1000, 4), (1, 70, 3)])
+# M = 20 / 33: the second softmax group of the kernel sees no (or one) reference row; M = 70: a 6-row tail chunk
+@pytest.mark.parametrize('N,M,heads', [(37, 300, 2), (128, 64, 1), (300, 900, 16), (300, 4500, 16), (130, 1000, 4), (1, 70, 3),
+                                       (40, 20, 2), (129, 33, 1)])
 def test_selsa_attention_tc_vs_oracle(N, M, heads):
     g = torch.Generator().manual_seed(N + M)
     D = heads * 64

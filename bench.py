@@ -196,7 +196,19 @@ def kernel_rooflines(cfg, device, peaks):
         t = timeit(lambda: ops.tafa_weighted_sum(x_all, emb, 4, out_nhwc=True))   # channels_last output, as in the step
         b = (2 * (T + 1) + 1) * N * C * P * 4
         out['tafa_weighted_sum'] = dict(bound='hbm', seconds=t, achieved=b / t / 1e9, peak=peaks['hbm'], unit='GB/s', bytes=b)
-        del x_all, emb
+        # (4'') key-projected attention logits (the embed conv is applied to the key slot only; tafa_keyproj.cu) and the weighting
+        # that consumes them: bytes = G (heads*N*P*9*C*4) + x_all read once each; then x_all again + the [N,P,C] output
+        cc = ops.tafa_keyproj_chunk(T + 1, P, C, 4)
+        G = torch.randn(4, N * P, 9 * C, device=device, generator=g)
+        t = timeit(lambda: ops.tafa_keyproj_logits(x_all, G, 7, 4, cc))
+        b = (G.numel() + x_all.numel()) * 4
+        out['tafa_keyproj_logits'] = dict(bound='hbm', seconds=t, achieved=b / t / 1e9, peak=peaks['hbm'], unit='GB/s', bytes=b,
+                                          traffic=1627.1e6, note='traffic = dram read+write per launch from ncu --set full (profiles/r01h_ncu_keyproj.csv)')
+        parts = ops.tafa_keyproj_logits(x_all, G, 7, 4, cc)
+        t = timeit(lambda: ops.tafa_weighted_sum_logits(x_all, parts, 4, out_nhwc=True))
+        b = (x_all.numel() + N * P * C + parts.numel()) * 4
+        out['tafa_weighted_sum_logits'] = dict(bound='hbm', seconds=t, achieved=b / t / 1e9, peak=peaks['hbm'], unit='GB/s', bytes=b)
+        del x_all, emb, G, parts
     # (3) SELSA core per layer: flops = 4*N*M*D ; bytes = (2N+2M)*D*4
     q = torch.randn(N, D, device=device, generator=g)
     k = torch.randn(M, D, device=device, generator=g)
@@ -510,7 +522,8 @@ def main():
             kr = kernel_rooflines(cfg, device, peaks)
         # the dominant kernel of THE TIMED STEP: composites (msra_topk_sample), alternates (NCHW-output RoIAlign) and the
         # kernels of the other detectors' shapes (FGFA/DFF T=31, RPN NMS), which the table also lists, do not qualify
-        in_step = ('roi_align_refs', 'msra_gemm_topk_kernel', 'tafa_weighted_sum', 'selsa_attention', 'batched_nms_rcnn')
+        in_step = ('roi_align_refs', 'msra_gemm_topk_kernel', 'tafa_keyproj_logits', 'tafa_weighted_sum_logits', 'selsa_attention',
+                   'batched_nms_rcnn')
         single = {k: v for k, v in kr.items() if k in in_step}
         dom = max(single, key=lambda k: single[k]['seconds'])
         r = kr[dom]

@@ -160,6 +160,25 @@ int vod_msra_gemm_candidates(const void *roi_unit_bf16, const void *ref_unit_bf1
 int vod_tafa_weighted_sum(const float *x_all, const float *emb_all, const float *emb_bias, float *out,
                           int T1, int N, int P, int C, int heads, int out_layout, vod_stream_t stream);
 
+/* Key-projected attention logits: the same weighting WITHOUT embedding the T reference slots.
+ * The embed conv is linear, so <conv(x_t), ek>_head = sum_{tap,c} x_t[p+tap,c] * G[h,(n,p),tap,c] with
+ * G = ek_head . W_head (one batched library GEMM of the KEY embedding ek = conv(x_0)+b against the conv
+ * weight); the bias term is constant over t and cancels in the softmax.  Only the N key patches go
+ * through the conv instead of (T+1)*N.
+ *   vod_tafa_keyproj_chunk: channel-chunk width CC the kernel wants G laid out with, 0 = unsupported
+ *     shape (heads != 4, C % 32 != 0, or the [T1,P,CC] tile exceeds shared memory) -> use
+ *     vod_tafa_weighted_sum with full embeddings instead.
+ *   x_all [T1, N, P, C] fp32;  G [heads, N*P, C/CC, 9, CC] fp32 (tap = ky*3+kx of the 3x3, pad-1 conv);
+ *   parts [C/CC, N, P, heads, T1] fp32 out: per-chunk partial logits (unscaled).
+ *   vod_tafa_weighted_sum_logits: sums the chunks, scales by 1/sqrt(C/heads), softmax over t, weighted sum.
+ * replaces: temporal_roi_align.py:72-97 (embed_network over img_n*roi_n patches + multi-head weighting)
+ */
+int vod_tafa_keyproj_chunk(int T1, int P, int C, int heads);
+int vod_tafa_keyproj_logits(const float *x_all, const float *G, float *parts, int T1, int N, int ph, int pw,
+                            int C, int heads, int cc, vod_stream_t stream);
+int vod_tafa_weighted_sum_logits(const float *x_all, const float *logit_parts, int nparts, float *out,
+                                 int T1, int N, int P, int C, int heads, int out_layout, vod_stream_t stream);
+
 /* -------------------------------------------------------- (5) batched NMS
  * Bitmask NMS with the sort, mask and the greedy sweep all on the device (no
  * host round trip).  Boxes of `n_images` independent images are concatenated;

@@ -90,6 +90,26 @@ int make_tmap_msra_b(CUtensorMap *map, const void *base, uint64_t T, uint64_t HW
     return VOD_OK;
 }
 
+// fp32 [d2][d1][d0] tensor (d0 contiguous), dense un-swizzled box (b0, b1, b2): lands in shared memory as [b2][b1][b0].
+// Out-of-range coordinates are zero-filled.  Used for the frame tiles of the key-projected TAFA logits kernel.
+int make_tmap_f32_3d(CUtensorMap *map, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                     uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return fail(VOD_E_LAUNCH, "cuTensorMapEncodeTiled entry point unavailable");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (stride1_bytes & 15) || (stride2_bytes & 15) || (b0 * 4) % 16 != 0 ||
+        b0 > 256 || b1 > 256 || b2 > 256)
+        return fail(VOD_E_BADARG, "TMA operand needs 16-byte aligned base/strides and box dims <= 256");
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+    cuuint32_t box[3] = {b0, b1, b2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(VOD_E_LAUNCH, "cuTensorMapEncodeTiled (f32 3d) failed (%d)", (int)r);
+    return VOD_OK;
+}
+
 constexpr int kGtStages = 4;
 constexpr int kGtTileBytes = 128 * 128;  // 128 rows x 128 B
 constexpr int kGtThreads = 192;

@@ -19,7 +19,8 @@ constexpr int kTafaMaxT = 64;
 template <int VEC, bool FLAT>
 __global__ void __launch_bounds__(kTafaWarps * 32, 4)
 tafa_kernel(const float *__restrict__ x_all, const float *__restrict__ emb_all, const float *__restrict__ emb_bias,
-            float *__restrict__ out, int T1, int N, int P, int C, int hs, float scale, int use_attn, int out_layout) {
+            float *__restrict__ out, int T1, int N, int P, int C, int hs, float scale, int use_attn, int out_layout,
+            const float *__restrict__ logit_parts, int nparts) {
     extern __shared__ __align__(16) float tile[];          // [hs][P] (layout 0)
     __shared__ float s_w[kTafaWarps][kTafaMaxT];
     constexpr int CH = 32 * VEC;
@@ -47,7 +48,19 @@ tafa_kernel(const float *__restrict__ x_all, const float *__restrict__ emb_all, 
     for (int p = p0; p < p1; p += pstep) {
         const size_t base = ((size_t)n * P + p) * C + c_head + lane * VEC;
         float *w = s_w[warp];
-        if (use_attn) {
+        if (use_attn && logit_parts) {
+            // logits come from the key-projected contraction (tafa_keyproj.cu) as per-channel-chunk partial sums
+            // [nparts][N][P][groups][T1]; sum the chunks in a fixed order
+            const int groups = ceil_div(C, hs);
+            const size_t part_stride = (size_t)N * P * groups * T1;
+            const float *src = logit_parts + (((size_t)n * P + p) * groups + head) * T1;
+            for (int t = lane; t < T1; t += 32) {
+                float s = 0.f;
+                for (int k = 0; k < nparts; ++k) s += __ldg(src + (size_t)k * part_stride + t);
+                w[t] = s * scale;
+            }
+            __syncwarp();
+        } else if (use_attn) {
             // logits_t = <emb[t] + b, emb[0] + b>_head * scale   (b = the embed conv's bias, folded in here so
             // the conv can run bias-free and the [T1,N,P,C] embedding is not rewritten by a bias-add pass).
             // Frames are processed 8 at a time: all loads of a batch are issued before the first reduction.
@@ -91,6 +104,8 @@ tafa_kernel(const float *__restrict__ x_all, const float *__restrict__ emb_all, 
                     for (int u = 0; u < TB; ++u) if (t0 + u < T1) w[t0 + u] = d[u] * scale;
                 }
             }
+        }
+        if (use_attn) {
             __syncwarp();
             float m = -INFINITY;
             for (int t = 0; t < T1; ++t) m = fmaxf(m, w[t]);
@@ -501,15 +516,29 @@ int msra_launch_rescore(const float *roi, const float *ref, const float *roi_nor
 
 using namespace vod;
 
+static int tafa_launch(const float *x_all, const float *emb_all, const float *emb_bias, const float *logit_parts, int nparts,
+                       float *out, int T1, int N, int P, int C, int heads, int out_layout, vod_stream_t stream);
+
 extern "C" int vod_tafa_weighted_sum(const float *x_all, const float *emb_all, const float *emb_bias, float *out, int T1,
                                      int N, int P, int C, int heads, int out_layout, vod_stream_t stream) {
+    return tafa_launch(x_all, emb_all, emb_bias, nullptr, 0, out, T1, N, P, C, heads, out_layout, stream);
+}
+
+extern "C" int vod_tafa_weighted_sum_logits(const float *x_all, const float *logit_parts, int nparts, float *out, int T1,
+                                            int N, int P, int C, int heads, int out_layout, vod_stream_t stream) {
+    VOD_REQUIRE(heads > 0 && nparts > 0 && (logit_parts || N == 0), "vod_tafa_weighted_sum_logits: heads, nparts, logit_parts required");
+    return tafa_launch(x_all, nullptr, nullptr, logit_parts, nparts, out, T1, N, P, C, heads, out_layout, stream);
+}
+
+static int tafa_launch(const float *x_all, const float *emb_all, const float *emb_bias, const float *logit_parts, int nparts,
+                       float *out, int T1, int N, int P, int C, int heads, int out_layout, vod_stream_t stream) {
     if (N == 0) return VOD_OK;
     VOD_REQUIRE(x_all && out, "vod_tafa_weighted_sum: null pointer");
     VOD_REQUIRE(T1 > 0 && T1 <= kTafaMaxT, "vod_tafa_weighted_sum: T1=%d not in [1,%d]", T1, kTafaMaxT);
     VOD_REQUIRE(N > 0 && P > 0 && C > 0, "vod_tafa_weighted_sum: bad dims");
     VOD_REQUIRE(out_layout == 0 || out_layout == 1, "vod_tafa_weighted_sum: out_layout");
     const int use_attn = heads > 0;
-    VOD_REQUIRE(!use_attn || emb_all, "vod_tafa_weighted_sum: emb_all required when heads > 0");
+    VOD_REQUIRE(!use_attn || emb_all || logit_parts, "vod_tafa_weighted_sum: emb_all required when heads > 0");
     VOD_REQUIRE(!use_attn || C % heads == 0, "vod_tafa_weighted_sum: C=%d not divisible by heads=%d", C, heads);
     int hs = use_attn ? C / heads : min(C, 128);
     int groups = use_attn ? heads : ceil_div(C, hs);
@@ -525,7 +554,8 @@ extern "C" int vod_tafa_weighted_sum(const float *x_all, const float *emb_all, c
     if (out_layout != 0) grid = dim3((unsigned)ceil_div((long)N * P * groups, (long)kTafaWarps), 1);
     auto launch = [&](auto kern) {
         if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<grid, kTafaWarps * 32, smem, as_stream(stream)>>>(x_all, emb_all, emb_bias, out, T1, N, P, C, hs, scale, use_attn, out_layout);
+        kern<<<grid, kTafaWarps * 32, smem, as_stream(stream)>>>(x_all, emb_all, emb_bias, out, T1, N, P, C, hs, scale, use_attn, out_layout,
+                                                                       logit_parts, nparts);
         note_launch();
     };
     if (out_layout != 0) { if (vec4) launch(tafa_kernel<4, true>); else launch(tafa_kernel<1, true>); }

@@ -1,0 +1,391 @@
+// tafa_keyproj.cu -- TemporalRoIAlign's attention logits WITHOUT the reference-frame embeddings.
+//
+// The reference (mmtracking/mmtrack/models/roi_heads/roi_extractors/temporal_roi_align.py:72-93) runs its 3x3 embed conv over
+// all (T+1)*N RoI patches (1.11 TFLOP at N=300, T=15) and then only ever uses the result through the per-head dot product with
+// the KEY patch's embedding.  The conv is linear, so that dot product can be taken on the weight side first:
+//
+//   logit[t,n,p,h] = sum_{o in head h} ek[n,p,o] * (conv(x_t)[n,p,o] + b[o])
+//                  = sum_{tap, c} x_t[n, p+tap, c] * G[h, (n,p), tap, c]  +  (a term constant in t, cancelled by the softmax)
+//   G[h, (n,p), tap, c] = sum_{o in head h} ek[n,p,o] * W[o, c, tap]          (one batched library GEMM, 69 GFLOP)
+//
+// Only the key patches go through the conv (1/(T+1) of the work); this kernel contracts the raw RoI features x_all with G:
+// 3.6 G fp32 FMA on the CUDA cores and one streaming read of G (1.08 GB) and x_all (0.48 GB) -- HBM-bound, not a GEMM.
+//
+//   Work unit ("tile") = (RoI n, chunk of 32 input channels, block of 8 frames): its x_all slice [8][P][32] (50 KB) arrives in
+//   shared memory as ONE 3-D TMA box and every element is reused by up to 9 taps of the neighbouring output positions.
+//   warp = output position p; lane = (tg, cg): tg owns 2 frames, cg owns 4 consecutive channels (128-bit accesses).
+//   G has no reuse but is 70 % of the bytes: each consumer warp streams the four head rows (9 taps x 32 channels, 1152
+//   contiguous bytes each) of its NEXT positions into a private shared-memory ring with cp.async.bulk + mbarrier.
+//   Per (tap, 32 channels): 4 G vectors x 2 frame vectors from shared memory -> 16 packed FFMA2 per lane.
+//   The (frame, head) partial sums are reduced over the 8 cg lanes by a transposing butterfly (7 shuffles) and written as
+//   per-chunk partial logits [C/32][N][P][H][T1]; the weighting kernel (tafa.cu) sums the chunks -- deterministic, no atomics.
+//
+//   Persistent kernel: one CTA per SM walks a contiguous range of tiles; a producer warp keeps TWO frame tiles in flight
+//   (double buffer, full/empty mbarriers) and the consumer warps' position stream runs on across tile boundaries, so neither
+//   the tile load nor the first ring fill is ever exposed.  Probes on the one-CTA-per-tile version of this kernel (kept below for
+//   frame blocks of 16, VOD_KP_PERSIST=0) showed why: memory alone 255 us, FMAs alone 160 us, but 175 us of per-CTA start-up
+//   (launch + first ring fill + tile load) that overlapped with neither -- 383 us in total.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace vod {
+
+constexpr int kKpHeads = 4;
+constexpr int kKpCC = 32;                         // channels per tile
+constexpr int kKpRowFloats = 9 * kKpCC;           // one (head, position) row of G for this chunk
+constexpr int kKpStageFloats = kKpHeads * kKpRowFloats;
+constexpr int kKpMaxWarps = 16;
+constexpr int kKpTile = 8;                        // frames per tile of the persistent kernel
+
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
+}
+
+// 3x3 window, pad 1: bit (ky*3 + kx) of the mask is set when the tap of output position p falls inside the ph x pw patch
+__device__ __forceinline__ unsigned kp_tap_mask(int p, int ph, int pw) {
+    const int py = p / pw, px = p - py * pw;
+    const unsigned rows_ok = (py > 0 ? 1u : 0u) | 2u | (py < ph - 1 ? 4u : 0u);
+    const unsigned cols_ok = (px > 0 ? 1u : 0u) | 2u | (px < pw - 1 ? 4u : 0u);
+    unsigned m = 0;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) m |= ((rows_ok >> (tap / 3)) & (cols_ok >> (tap % 3)) & 1u) << tap;
+    return m;
+}
+
+// One output position: contract the 3x3 neighbourhood of p in the frame tile (xlane = tile + this lane's (tg, cg) offset) with
+// the four G rows in `gs`; returns the NV/8 sums this lane owns after the butterfly: v = cg*NV/8 + k, frame = v / H, head = v % H.
+template <int FR>
+__device__ __forceinline__ void kp_position(const float *__restrict__ xlane, const float *__restrict__ gs, int p, int P, int pw,
+                                            unsigned taps, int cg, float (&vc)[FR * kKpHeads / 8]) {
+    constexpr int H = kKpHeads, CC = kKpCC, NV = FR * H;
+    const int frame_floats = P * CC, row_floats = pw * CC;
+    const float *xp = xlane + p * CC;
+
+    // packed fp32x2 FMAs (FFMA2: the full-rate fp32 path of sm_100): even / odd channels accumulate separately
+    float2 acc2[FR][H];
+#pragma unroll
+    for (int u = 0; u < FR; ++u)
+#pragma unroll
+        for (int h = 0; h < H; ++h) acc2[u][h] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        if (!((taps >> tap) & 1u)) continue;                // warp-uniform
+        const float *xq = xp + (tap / 3 - 1) * row_floats + (tap % 3 - 1) * CC;
+        float4 g[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) g[h] = *reinterpret_cast<const float4 *>(gs + h * kKpRowFloats + tap * CC);
+#pragma unroll
+        for (int u = 0; u < FR; ++u) {
+            const float4 xv = *reinterpret_cast<const float4 *>(xq + u * frame_floats);
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                acc2[u][h] = __ffma2_rn(make_float2(xv.x, xv.y), make_float2(g[h].x, g[h].y), acc2[u][h]);
+                acc2[u][h] = __ffma2_rn(make_float2(xv.z, xv.w), make_float2(g[h].z, g[h].w), acc2[u][h]);
+            }
+        }
+    }
+    float acc[FR][H];
+#pragma unroll
+    for (int u = 0; u < FR; ++u)
+#pragma unroll
+        for (int h = 0; h < H; ++h) acc[u][h] = acc2[u][h].x + acc2[u][h].y;
+
+    // transposing butterfly over the 8 cg lanes: NV sums -> NV/8 per lane
+    float va[NV / 2], vb[NV / 4];
+    {
+        const bool up = cg & 4;
+#pragma unroll
+        for (int k = 0; k < NV / 2; ++k) {
+            const float lo = acc[k / H][k % H], hi = acc[(k + NV / 2) / H][(k + NV / 2) % H];
+            const float send = up ? lo : hi, keep = up ? hi : lo;
+            va[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    {
+        const bool up = cg & 2;
+#pragma unroll
+        for (int k = 0; k < NV / 4; ++k) {
+            const float send = up ? va[k] : va[k + NV / 4], keep = up ? va[k + NV / 4] : va[k];
+            vb[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+    }
+    {
+        const bool up = cg & 1;
+#pragma unroll
+        for (int k = 0; k < NV / 8; ++k) {
+            const float send = up ? vb[k] : vb[k + NV / 8], keep = up ? vb[k + NV / 8] : vb[k];
+            vc[k] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ persistent kernel
+// blockDim = (nwc + 1) warps: warps 0..nwc-1 consume, warp nwc produces the frame tiles.  Requires nwc <= P.
+__global__ void __launch_bounds__(kKpMaxWarps * 32, 1)
+tafa_keyproj_persist_kernel(const __grid_constant__ CUtensorMap tm_x, const float *__restrict__ G, float *__restrict__ parts,
+                            int T1, int N, int ph, int pw, int C, int depth, int tiles_per_cta, int dbg) {
+    constexpr int H = kKpHeads, CC = kKpCC, TB = kKpTile, FR = TB / 4, NV = FR * H;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int nch = C / CC, ntb = ceil_div(T1, TB), P = ph * pw;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwc = (blockDim.x >> 5) - 1;
+    const int tg = lane >> 3, cg = lane & 7;
+    const int total_tiles = N * nch * ntb;                              // tile id = (n*nch + chunk)*ntb + tb (host checks < 2^31)
+    const int tile0 = blockIdx.x * tiles_per_cta;
+    const int my_tiles = max(0, min(tiles_per_cta, total_tiles - tile0));
+    const int tile_floats = TB * P * CC;
+    float *xs = reinterpret_cast<float *>(smem_raw);                                    // [2][TB][P][CC]
+    float *ring = xs + 2 * (size_t)tile_floats;                                         // [nwc][depth][H][9][CC]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ring + (size_t)nwc * depth * kKpStageFloats);   // [nwc][depth], xfull[2], xempty[2]
+    uint64_t *xfull = bars + nwc * depth, *xempty = xfull + 2;
+    unsigned *tap_mask = reinterpret_cast<unsigned *>(xempty + 2);                      // [P]
+    const size_t NP = (size_t)N * P;
+    const size_t head_stride = NP * 9 * (size_t)C;        // floats between the heads of G
+
+    if (tid == 0) {
+        for (int b = 0; b < 2; ++b) { tc::mbar_init(xfull + b, 1); tc::mbar_init(xempty + b, nwc); }
+        for (int s = 0; s < nwc * depth; ++s) tc::mbar_init(bars + s, 1);
+        tc::fence_barrier_init();
+    }
+    for (int q = tid; q < P; q += blockDim.x) tap_mask[q] = (dbg & 1) ? 0u : kp_tap_mask(q, ph, pw);
+    __syncthreads();
+    if (my_tiles == 0) return;
+
+    if (warp == nwc) {
+        // ---- producer: frame tile j of this CTA -> buffer j & 1 as one 3-D TMA box (frames past T1 arrive as zeros)
+        if (lane == 0) {
+            for (int j = 0; j < my_tiles; ++j) {
+                const int b = j & 1;
+                if (j >= 2) tc::mbar_wait(xempty + b, (uint32_t)(((j >> 1) - 1) & 1));   // consumers are done with tile j-2
+                const unsigned tile = tile0 + j, nc = tile / ntb;
+                if (!(dbg & 4)) {
+                    tc::mbar_arrive_expect_tx(xfull + b, (uint32_t)(tile_floats * sizeof(float)));
+                    tc::tma_load_3d(xs + (size_t)b * tile_floats, &tm_x, xfull + b, (int)(nc % nch) * CC, (int)(nc / nch) * P,
+                                    (int)(tile % ntb) * TB);
+                } else {
+                    tc::mbar_arrive(xfull + b);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---- consumers: warp w owns positions w, w + nwc, ... of the CTA's concatenated (tile, position) stream (nwc <= P)
+    float *my_ring = ring + (size_t)warp * depth * kKpStageFloats;
+    uint64_t *my_bars = bars + warp * depth;
+    // lane 0 feeds the warp's own ring, `depth` positions ahead of the consumer: (ji, pi) = tile and position of the next
+    // stage to request, si = its ring stage; gi_row = G row of (tile ji, position 0) for this chunk
+    int ji = 0, pi = warp, si = 0, ji_cur = -1;
+    const float *gi_row = nullptr;
+    auto issue = [&]() {
+        if (ji >= my_tiles) return;
+        if (ji != ji_cur) {
+            ji_cur = ji;
+            const unsigned nc = (unsigned)(tile0 + ji) / ntb;            // n*nch + chunk
+            gi_row = G + ((size_t)(nc / nch) * P * nch + (size_t)(nc % nch)) * kKpRowFloats;
+        }
+        tc::mbar_arrive_expect_tx(my_bars + si, kKpStageFloats * 4);
+        const float *row = gi_row + (size_t)pi * nch * kKpRowFloats;
+#pragma unroll
+        for (int h = 0; h < H; ++h)
+            bulk_g2s(my_ring + (size_t)si * kKpStageFloats + h * kKpRowFloats, row + (size_t)h * head_stride, kKpRowFloats * 4,
+                     my_bars + si);
+        if (++si == depth) si = 0;
+        pi += nwc;
+        if (pi >= P) { pi -= P; ++ji; }
+    };
+    if (lane == 0)
+        for (int i = 0; i < depth; ++i) issue();
+
+    int j = 0, p = warp, s = 0;                           // current tile (local index), position, ring stage
+    uint32_t phase = 0;
+    int cur = -1, t0 = 0, nt = 0;
+    int refills = (dbg & 2) ? 0 : 0x7fffffff;
+    float *out_tile = nullptr;
+    const float *xlane = nullptr;
+    while (j < my_tiles) {
+        if (j != cur) {
+            cur = j;
+            const unsigned tile = tile0 + j, nc = tile / ntb;
+            t0 = (int)(tile % ntb) * TB; nt = min(TB, T1 - t0);
+            out_tile = parts + ((size_t)(nc % nch) * N + nc / nch) * P * H * T1 + t0;    // [chunk][n] + frame block
+            tc::mbar_wait(xfull + (j & 1), (uint32_t)((j >> 1) & 1));
+            xlane = xs + (size_t)(j & 1) * tile_floats + (size_t)tg * FR * P * CC + cg * 4;
+        }
+        tc::mbar_wait(my_bars + s, phase);
+        float vc[NV / 8];
+        kp_position<FR>(xlane, my_ring + (size_t)s * kKpStageFloats + cg * 4, p, P, pw, tap_mask[p], cg, vc);
+        // every lane's sums (hence its reads of stage s and of the frame tile) are complete once it has taken part in the
+        // butterfly shuffles: lane 0 may hand the stage back to the copy engine
+        if (lane == 0) {
+            if (refills > 0) issue();
+            else tc::mbar_arrive(my_bars + s);             // probe mode: keep the phases moving without a copy
+        }
+#pragma unroll
+        for (int k = 0; k < NV / 8; ++k) {
+            const int v = cg * (NV / 8) + k;
+            const int t = tg * FR + v / H;
+            if (t < nt) out_tile[((size_t)p * H + v % H) * T1 + t] = vc[k];
+        }
+        if (++s == depth) { s = 0; phase ^= 1; }
+        p += nwc;
+        if (p >= P) {                                      // this warp's last position in tile j: release the frame buffer
+            p -= P;
+            if (lane == 0) tc::mbar_arrive(xempty + (j & 1));
+            ++j;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ one CTA per tile
+// TB = frames per CTA: 8 -> [8][P][32] tile + 7 x 2 G stages = 112 KB, two CTAs per SM; 16 -> one CTA per SM, G read once.
+template <int TB, int MAXW, int MINB>
+__global__ void __launch_bounds__(MAXW * 32, MINB)
+tafa_keyproj_logits_kernel(const __grid_constant__ CUtensorMap tm_x, const float *__restrict__ G, float *__restrict__ parts,
+                           int T1, int N, int ph, int pw, int C, int depth, int dbg) {
+    constexpr int H = kKpHeads, CC = kKpCC, FR = TB / 4, NV = FR * H;   // FR frames per lane group, NV sums per lane
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tb = blockIdx.x, chunk = blockIdx.y, n = blockIdx.z, nch = C / CC;
+    const int P = ph * pw;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int tg = lane >> 3, cg = lane & 7;
+    const int t0 = tb * TB, nt = min(TB, T1 - t0);
+    float *xs = reinterpret_cast<float *>(smem_raw);                                   // [TB][P][CC]
+    float *ring = xs + (size_t)TB * P * CC;                                            // [nwarps][depth][H][9][CC]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ring + (size_t)nwarps * depth * kKpStageFloats);   // [nwarps][depth] + 1
+    uint64_t *xbar = bars + nwarps * depth;
+    const size_t NP = (size_t)N * P;
+    const size_t head_stride = NP * 9 * (size_t)C;        // floats between the heads of G
+    const float *g_roi = G + ((size_t)n * P * nch + chunk) * kKpRowFloats;   // + p * nch*9*CC + h * head_stride
+
+    float *my_ring = ring + (size_t)warp * depth * kKpStageFloats;
+    uint64_t *my_bars = bars + warp * depth;
+    auto issue = [&](int i) {
+        const int p = warp + i * nwarps;
+        if (p >= P) return;
+        if ((dbg & 2) && i >= depth) return;
+        const int s = i % depth;
+        tc::mbar_arrive_expect_tx(my_bars + s, kKpStageFloats * 4);
+        const float *row = g_roi + (size_t)p * nch * kKpRowFloats;
+#pragma unroll
+        for (int h = 0; h < H; ++h)
+            bulk_g2s(my_ring + (size_t)s * kKpStageFloats + h * kKpRowFloats, row + (size_t)h * head_stride, kKpRowFloats * 4,
+                     my_bars + s);
+    };
+    if (lane == 0) {
+        if (warp == 0) {
+            tc::mbar_init(xbar, 1);
+            tc::fence_barrier_init();
+            if (!(dbg & 4)) {
+                tc::mbar_arrive_expect_tx(xbar, (uint32_t)(TB * P * CC * sizeof(float)));
+                tc::tma_load_3d(xs, &tm_x, xbar, chunk * CC, n * P, t0);
+            }
+        }
+        for (int s = 0; s < depth; ++s) tc::mbar_init(my_bars + s, 1);
+        tc::fence_barrier_init();
+        for (int i = 0; i < depth; ++i) issue(i);
+    }
+    __syncthreads();                 // barrier initialisations visible to every waiter
+    if (!(dbg & 4)) tc::mbar_wait(xbar, 0);
+
+    const float *xlane = xs + (size_t)tg * FR * P * CC + cg * 4;   // + u * P*CC + q * CC
+    int i = 0;
+    for (int p = warp; p < P; p += nwarps, ++i) {
+        const int s = i % depth;
+        if (!((dbg & 2) && i >= depth)) tc::mbar_wait(my_bars + s, (uint32_t)((i / depth) & 1));
+        float vc[NV / 8];
+        kp_position<FR>(xlane, my_ring + (size_t)s * kKpStageFloats + cg * 4, p, P, pw, (dbg & 1) ? 0u : kp_tap_mask(p, ph, pw), cg, vc);
+        if (lane == 0) issue(i + depth);
+#pragma unroll
+        for (int k = 0; k < NV / 8; ++k) {
+            const int v = cg * (NV / 8) + k;
+            const int t = tg * FR + v / H;
+            if (t < nt) parts[((((size_t)chunk * N + n) * P + p) * H + v % H) * T1 + t0 + t] = vc[k];
+        }
+    }
+}
+
+}  // namespace vod
+
+using namespace vod;
+
+static size_t kp_smem_bytes(int tile_frames, int P, int warps, int depth) {
+    return (size_t)tile_frames * P * kKpCC * sizeof(float) + (size_t)warps * depth * (kKpStageFloats * sizeof(float) + 8) + 64 + (size_t)P * 4;
+}
+constexpr size_t kKpSmemLimit = 227 * 1024;
+
+// Channel-chunk width the logits kernel uses for these dims (the caller lays G out with it); 0 = shape not supported
+// (the caller then takes the full-embedding path, vod_tafa_weighted_sum).
+extern "C" int vod_tafa_keyproj_chunk(int T1, int P, int C, int heads) {
+    if (heads != kKpHeads || T1 <= 0 || P <= 0 || C <= 0) return 0;
+    if (C % kKpCC != 0) return 0;
+    if (P > 256 || kp_smem_bytes(8, P, 4, 2) > kKpSmemLimit) return 0;   // TMA box dims <= 256
+    return kKpCC;
+}
+
+extern "C" int vod_tafa_keyproj_logits(const float *x_all, const float *G, float *parts, int T1, int N, int ph, int pw,
+                                       int C, int heads, int cc, vod_stream_t stream) {
+    if (N == 0) return VOD_OK;
+    VOD_REQUIRE(x_all && G && parts, "vod_tafa_keyproj_logits: null pointer");
+    VOD_REQUIRE(T1 > 0 && N > 0 && ph > 0 && pw > 0 && C > 0, "vod_tafa_keyproj_logits: bad dims");
+    VOD_REQUIRE(cc != 0 && cc == vod_tafa_keyproj_chunk(T1, ph * pw, C, heads),
+                "vod_tafa_keyproj_logits: unsupported shape (T1=%d P=%d C=%d heads=%d cc=%d)", T1, ph * pw, C, heads, cc);
+    VOD_REQUIRE(((reinterpret_cast<uintptr_t>(x_all) | reinterpret_cast<uintptr_t>(G)) & 15) == 0,
+                "vod_tafa_keyproj_logits: x_all and G must be 16-byte aligned");
+    VOD_REQUIRE(N <= 65535 && C / cc <= 65535 && (long)N * (C / cc) * ceil_div(T1, 8) < (1L << 30),
+                "vod_tafa_keyproj_logits: grid too large");
+    const int P = ph * pw;
+    // Measured at N=300, C=512 (B200): 16 stacked frames -- one CTA per 16-frame tile 383 us, persistent 8-frame tiles 432 us,
+    // one CTA per 8-frame tile (two per SM) 458 us; 8 frames -- one CTA per 8-frame tile 241 us (5.6 TB/s).
+    int persist = 0, tb = T1 > 8 ? 16 : 8, warps = min(T1 > 8 ? 14 : 7, P), depth = 2, dbg = 0;
+    // tuning / probe hooks (dbg: 1 = no FMAs, 2 = no G refills after the first ring fill, 4 = no frame tile loads)
+    if (const char *e = getenv("VOD_KP_PERSIST")) persist = atoi(e) != 0;
+    if (const char *e = getenv("VOD_KP_TB")) tb = atoi(e) == 16 ? 16 : 8;
+    if (const char *e = getenv("VOD_KP_WARPS")) warps = max(1, min(atoi(e), min(kKpMaxWarps, P)));
+    if (const char *e = getenv("VOD_KP_DEPTH")) depth = max(1, min(atoi(e), 8));
+    if (const char *e = getenv("VOD_KP_DBG")) dbg = atoi(e);
+    if (persist) { tb = kKpTile; warps = min(warps, kKpMaxWarps - 1); }   // + the producer warp
+    const int tile_frames = persist ? 2 * kKpTile : tb;     // the persistent kernel double-buffers its frame tile
+    while (warps > 4 && kp_smem_bytes(tile_frames, P, warps, depth) > kKpSmemLimit) --warps;
+    while (depth > 2 && kp_smem_bytes(tile_frames, P, warps, depth) > kKpSmemLimit) --depth;
+    if (persist && kp_smem_bytes(tile_frames, P, warps, depth) > kKpSmemLimit) {   // large patches: one tile per CTA
+        persist = 0;
+        tb = 8;
+    }
+    const size_t smem = kp_smem_bytes(persist ? 2 * kKpTile : tb, P, warps, depth);
+    VOD_REQUIRE(smem <= kKpSmemLimit, "vod_tafa_keyproj_logits: tile does not fit shared memory");
+    static bool attr_set = false;   // immutable function attributes, set once
+    if (!attr_set) {
+        cudaFuncSetAttribute(tafa_keyproj_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKpSmemLimit);
+        cudaFuncSetAttribute(tafa_keyproj_logits_kernel<8, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKpSmemLimit);
+        cudaFuncSetAttribute(tafa_keyproj_logits_kernel<8, kKpMaxWarps, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKpSmemLimit);
+        cudaFuncSetAttribute(tafa_keyproj_logits_kernel<16, kKpMaxWarps, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKpSmemLimit);
+        attr_set = true;
+    }
+    // x_all [T1][N*P][C] as a 3-D tensor, box = (32 channels, P positions, tb frames)
+    CUtensorMap tm_x;
+    if (int rc = make_tmap_f32_3d(&tm_x, x_all, (uint64_t)C, (uint64_t)N * P, (uint64_t)T1, (uint64_t)C * 4,
+                                  (uint64_t)N * P * C * 4, kKpCC, (uint32_t)P, (uint32_t)tb))
+        return rc;
+    cudaStream_t st = as_stream(stream);
+    if (persist) {
+        const long total_tiles = (long)N * (C / cc) * ceil_div(T1, kKpTile);
+        int sms = kNumSMs;
+        if (const char *e = getenv("VOD_KP_CTAS")) sms = max(1, atoi(e));
+        const int tiles_per_cta = (int)ceil_div(total_tiles, (long)sms);
+        const int grid = (int)ceil_div(total_tiles, (long)tiles_per_cta);
+        tafa_keyproj_persist_kernel<<<grid, (warps + 1) * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, tiles_per_cta, dbg);
+    } else {
+        dim3 grid(ceil_div(T1, tb), C / cc, N);
+        if (tb == 16)
+            tafa_keyproj_logits_kernel<16, kKpMaxWarps, 1><<<grid, warps * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, dbg);
+        else if (warps <= 8 && kp_smem_bytes(tb, P, warps, depth) <= 113 * 1024)
+            tafa_keyproj_logits_kernel<8, 8, 2><<<grid, warps * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, dbg);
+        else
+            tafa_keyproj_logits_kernel<8, kKpMaxWarps, 1><<<grid, warps * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, dbg);
+    }
+    note_launch();
+    return check_launch("vod_tafa_keyproj_logits");
+}

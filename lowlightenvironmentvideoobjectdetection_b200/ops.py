@@ -430,6 +430,39 @@ def tafa_weighted_sum(x_all, emb_all, num_heads, out_nhwc=False, emb_bias=None):
     return out
 
 
+def tafa_keyproj_chunk(T1, P, C, num_heads):
+    """Channel-chunk width the key-projected logits kernel wants G laid out with; 0 = shape unsupported."""
+    return int(_lib.load().vod_tafa_keyproj_chunk(int(T1), int(P), int(C), int(num_heads)))
+
+
+def tafa_keyproj_logits(x_all, G, output_size, num_heads, cc):
+    """x_all [T1, N, P, C], G [heads, N*P, C/cc, 9, cc] (key embedding x conv weight, see include/vodagg.h)
+    -> per-chunk partial logits [C/cc, N, P, heads, T1] (unscaled)."""
+    _lib.require_cuda(x_all, G)
+    ph, pw = _pair(output_size)
+    T1, N, P, C = x_all.shape
+    assert P == ph * pw and x_all.is_contiguous() and x_all.dtype == torch.float32
+    assert G.is_contiguous() and G.dtype == torch.float32 and G.numel() == num_heads * N * P * 9 * C
+    parts = torch.empty((C // cc, N, P, num_heads, T1), dtype=torch.float32, device=x_all.device)
+    if N:
+        _lib.call('vod_tafa_keyproj_logits', _lib.ptr(x_all), _lib.ptr(G), _lib.ptr(parts), T1, N, ph, pw, C,
+                  int(num_heads), int(cc), _lib.stream_ptr(x_all.device))
+    return parts
+
+
+def tafa_weighted_sum_logits(x_all, parts, num_heads, out_nhwc=False):
+    """x_all [T1, N, P, C], partial logits [nparts, N, P, heads, T1] -> [N, C, P] (or [N, P, C])."""
+    _lib.require_cuda(x_all, parts)
+    assert x_all.is_contiguous() and x_all.dtype == torch.float32
+    T1, N, P, C = x_all.shape
+    assert parts.is_contiguous() and parts.dtype == torch.float32 and parts.shape[1:] == (N, P, num_heads, T1)
+    out = torch.empty((N, P, C) if out_nhwc else (N, C, P), dtype=torch.float32, device=x_all.device)
+    if N:
+        _lib.call('vod_tafa_weighted_sum_logits', _lib.ptr(x_all), _lib.ptr(parts), int(parts.shape[0]), _lib.ptr(out),
+                  T1, N, P, C, int(num_heads), int(bool(out_nhwc)), _lib.stream_ptr(x_all.device))
+    return out
+
+
 def test_gemm_nt(a, b, a_in_tmem=False):
     """D = A @ B^T on the tcgen05 path (unit-test hook for the descriptor/pipeline building blocks).
     ``a_in_tmem``: bf16 only; the A tile is written to TMEM with tcgen05.st and consumed by the TS-form MMA."""

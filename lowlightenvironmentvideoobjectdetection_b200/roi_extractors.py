@@ -125,9 +125,11 @@ class TemporalRoIAlign(SingleRoIExtractor):
       3. vod_msra_topk_sample  bf16 tcgen05 GEMM with a register top-8 epilogue (the 2.1 GB similarity
                             tensor is never written) + exact fp32 re-score/top-k/softmax/gather into
                             slots 1..T of x_all
-      4. embed_network      3x3 conv over the [(T+1)*N, C, 7, 7] channels_last view of x_all (cuDNN)
-      5. vod_tafa_weighted_sum  per-head dot with the key embedding, softmax over frames, weighted sum,
-                            written as [N, C, 7, 7]
+      4. embed_network      3x3 conv (cuDNN) over the KEY slot of x_all only; G = ek_head . W_head (one batched
+                            cuBLAS GEMM); vod_tafa_keyproj_logits contracts x_all with G -- the reference-slot
+                            embeddings (15/16 of the conv's 1.11 TFLOP at cfg 3) are never computed
+      5. vod_tafa_weighted_sum_logits  softmax over frames, weighted sum, written as [N, C, 7, 7]
+      (few stacked frames / unsupported shapes: conv over all (T+1)*N patches + vod_tafa_weighted_sum)
     """
 
     def __init__(self, num_most_similar_points=2, num_temporal_attention_blocks=4, *args, **kwargs):
@@ -138,6 +140,10 @@ class TemporalRoIAlign(SingleRoIExtractor):
             self.embed_network = ConvModule(self.out_channels, self.out_channels, 3, padding=1, conv_cfg=None,
                                             norm_cfg=None, act_cfg=None)
         self.impl = ops.IMPL_AUTO  # test hook: force the exact SIMT scan or the tcgen05 candidate GEMM
+        # key-projected attention logits (embed conv on the key slot only): None = when it pays (>= keyproj_min_frames
+        # stacked frames), True / False = forced on (where the shape is supported) / off
+        self.keyproj = None
+        self.keyproj_min_frames = 8
 
     def _stack_key_and_refs(self, feat, rois, ref_feat, return_indices=False):
         """RoIAlign(key) + most-similar RoI features, stacked as x_all [T+1, N, P, C] (NHWC rows)."""
@@ -177,23 +183,61 @@ class TemporalRoIAlign(SingleRoIExtractor):
         rows = x_all.permute(0, 1, 3, 4, 2).contiguous().view(img_n, roi_n, rh * rw, C)
         return self._tafa(rows, rh, rw)
 
+    def _conv_weight_cl(self, conv):
+        # the weight in channels_last too (cached): otherwise cuDNN re-lays it out on every call (a 2.4 M element copy)
+        key = (conv.weight._version, conv.weight.data_ptr())
+        if getattr(self, '_w_cl', None) is None or self._w_cl[0] != key:
+            self._w_cl = (key, conv.weight.detach().contiguous(memory_format=torch.channels_last))
+        return self._w_cl[1]
+
+    def _keyproj_weight(self, conv, heads, cc):
+        """conv weight [C, C, 3, 3] -> [heads, C/heads, 9*C] with columns ordered (channel chunk, tap, channel in chunk):
+        the right-hand side of the G GEMM, laid out so that each (RoI, chunk) CTA of the logits kernel reads contiguous rows."""
+        key = (conv.weight._version, conv.weight.data_ptr(), heads, cc)
+        if getattr(self, '_w_kp', None) is None or self._w_kp[0] != key:
+            w = conv.weight.detach().float()
+            C = w.shape[0]
+            wr = w.view(heads, C // heads, C // cc, cc, 9).permute(0, 1, 2, 4, 3).reshape(heads, C // heads, 9 * C)
+            self._w_kp = (key, wr.contiguous())
+        return self._w_kp[1]
+
+    def _keyproj_chunk(self, T1, P, C):
+        """Channel-chunk width for the key-projected path, 0 when the full-embedding path must be taken."""
+        heads = self.num_temporal_attention_blocks
+        conv = self.embed_network.conv
+        if self.keyproj is False or (self.keyproj is None and T1 < self.keyproj_min_frames):
+            return 0
+        if (tuple(conv.kernel_size), tuple(conv.padding), tuple(conv.stride), tuple(conv.dilation), conv.groups) != \
+                ((3, 3), (1, 1), (1, 1), (1, 1), 1) or C % heads != 0:
+            return 0
+        return ops.tafa_keyproj_chunk(T1, P, C, heads)
+
     def _tafa(self, x_all, rh, rw):
         T1, N, P, C = x_all.shape
         cl_out = self.roi_layers[0].channels_last_out
-        if self.num_temporal_attention_blocks > 0:
-            # embed conv on the channels_last view: logical [(T+1)*N, C, 7, 7], memory [(T+1)*N, 7, 7, C]
-            patches = x_all.view(T1 * N, rh, rw, C).permute(0, 3, 1, 2)
+        heads = self.num_temporal_attention_blocks
+        if heads > 0:
             conv = self.embed_network.conv
-            # temporal_roi_align.py:74 -- the conv runs without its bias; the bias is added on load inside
-            # the weighting kernel (saves a full read+write pass over the [T+1,N,49,C] embedding)
-            # the weight in channels_last too (cached): otherwise cuDNN re-lays it out on every call (a 2.4 M element copy)
-            key = (conv.weight._version, conv.weight.data_ptr())
-            if getattr(self, '_w_cl', None) is None or self._w_cl[0] != key:
-                self._w_cl = (key, conv.weight.detach().contiguous(memory_format=torch.channels_last))
-            emb = torch.nn.functional.conv2d(patches, self._w_cl[1], None, conv.stride, conv.padding, conv.dilation, conv.groups)
-            emb = emb.permute(0, 2, 3, 1).contiguous().view(T1, N, P, C)  # no copy: cuDNN keeps channels_last
-            out = ops.tafa_weighted_sum(x_all, emb, self.num_temporal_attention_blocks, emb_bias=conv.bias,
-                                        out_nhwc=cl_out)
+            cc = self._keyproj_chunk(T1, P, C)
+            if cc:
+                # temporal_roi_align.py:72-93 with the embed conv applied to the KEY slot only: the conv is linear, so
+                # <conv(x_t), ek>_head = <x_t, ek_head . W_head>; G = ek_head . W_head is one batched GEMM with the FLOPs of
+                # one slot's conv, the contraction of x_t with G runs in vod_tafa_keyproj_logits
+                key_patches = x_all[0].view(N, rh, rw, C).permute(0, 3, 1, 2)
+                ek = torch.nn.functional.conv2d(key_patches, self._conv_weight_cl(conv), conv.bias, 1, 1)
+                ek = ek.permute(0, 2, 3, 1).contiguous().view(N * P, heads, C // heads)   # no copy (channels_last)
+                G = torch.bmm(ek.transpose(0, 1), self._keyproj_weight(conv, heads, cc))  # [heads, N*P, 9*C]
+                parts = ops.tafa_keyproj_logits(x_all, G, (rh, rw), heads, cc)
+                out = ops.tafa_weighted_sum_logits(x_all, parts, heads, out_nhwc=cl_out)
+            else:
+                # embed conv on the channels_last view: logical [(T+1)*N, C, 7, 7], memory [(T+1)*N, 7, 7, C]
+                patches = x_all.view(T1 * N, rh, rw, C).permute(0, 3, 1, 2)
+                # temporal_roi_align.py:74 -- the conv runs without its bias; the bias is added on load inside
+                # the weighting kernel (saves a full read+write pass over the [T+1,N,49,C] embedding)
+                emb = torch.nn.functional.conv2d(patches, self._conv_weight_cl(conv), None, conv.stride, conv.padding,
+                                                 conv.dilation, conv.groups)
+                emb = emb.permute(0, 2, 3, 1).contiguous().view(T1, N, P, C)  # no copy: cuDNN keeps channels_last
+                out = ops.tafa_weighted_sum(x_all, emb, heads, emb_bias=conv.bias, out_nhwc=cl_out)
         else:
             out = ops.tafa_weighted_sum(x_all, None, 0, out_nhwc=cl_out)   # plain mean, :203-206
         if cl_out:

@@ -237,6 +237,10 @@ def test_temporal_roi_align_golden_simt(golden):
     out = m((feat,), rois, ref_feats=(ref,))
     assert out.shape == golden['troi_out'].shape
     assert rel_err(out, golden['troi_out']) < 1e-4
+    m.keyproj = True     # embed conv on the key slot only + key-projected logits (the default from 8 stacked frames on)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    assert rel_err(m((feat,), rois, ref_feats=(ref,)), golden['troi_out']) < 1e-4
+    m.keyproj = None
     # reference-frame call: plain RoIAlign
     assert rel_err(m((ref,), golden['troi_ref_rois'].to(DEV)), golden['troi_ref_out']) < TIGHT
     # num_temporal_attention_blocks <= 0: mean over key + refs
@@ -283,6 +287,75 @@ def test_tafa_vs_oracle():
     assert rel_err(out_nhwc, ref) < TIGHT
     mean = ops.tafa_weighted_sum(xr, None, 0).view(N, C, 7, 7)
     assert rel_err(mean, x_all.mean(0)) < TIGHT
+
+
+def _keyproj_G(ek_rows, w, heads, cc):
+    """G = ek_head . W_head laid out [heads, N*P, C/cc, 9, cc] (what TemporalRoIAlign._tafa feeds the logits kernel)."""
+    C = w.shape[0]
+    wr = w.view(heads, C // heads, C // cc, cc, 9).permute(0, 1, 2, 4, 3).reshape(heads, C // heads, 9 * C).contiguous()
+    return torch.bmm(ek_rows.view(-1, heads, C // heads).transpose(0, 1), wr)
+
+
+@pytest.mark.parametrize('T1,N,C', [(6, 3, 64), (16, 9, 512), (32, 4, 128), (1, 2, 64), (19, 2, 64), (40, 2, 64)])
+def test_tafa_keyproj_vs_oracle(T1, N, C):
+    """Key-projected attention logits (embed conv on the key slot only) == the reference's TAFA with the conv on every slot
+    (temporal_roi_align.py:44-97); fp32 library GEMM here, so the bar is the tight one."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator().manual_seed(220 + T1)
+    x = torch.randn(1, N, C, 7, 7, generator=g)
+    ref_x = torch.randn(T1 - 1, N, C, 7, 7, generator=g)
+    w = torch.randn(C, C, 3, 3, generator=g) * (1.5 / (9 * C) ** 0.5)
+    b = torch.randn(C, generator=g) * 0.2
+    want = O.tafa(x, ref_x, w, b, 4)
+    x_all = torch.cat((x, ref_x), 0).permute(0, 1, 3, 4, 2).reshape(T1, N, 49, C).contiguous().to(DEV)
+    cc = ops.tafa_keyproj_chunk(T1, 49, C, 4)
+    assert cc == 32
+    ek = torch.nn.functional.conv2d(x[0].to(DEV), w.to(DEV), b.to(DEV), padding=1)       # [N, C, 7, 7]
+    ek_rows = ek.permute(0, 2, 3, 1).reshape(N * 49, C).contiguous()
+    parts = ops.tafa_keyproj_logits(x_all, _keyproj_G(ek_rows, w.to(DEV), 4, cc), 7, 4, cc)
+    assert parts.shape == (C // cc, N, 49, 4, T1)
+    # the logits themselves (up to the per-(n,p,head) constant that the softmax removes)
+    emb = torch.nn.functional.conv2d(torch.cat((x, ref_x), 0).view(T1 * N, C, 7, 7), w, None, padding=1).view(T1, N, 4, C // 4, 49)
+    ekc = ek.cpu().view(N, 4, C // 4, 49)
+    want_logits = (emb * ekc[None]).sum(3).permute(1, 3, 2, 0)                            # [N, 49, 4, T1]
+    assert rel_err(parts.sum(0), want_logits) < TIGHT
+    for nhwc in (False, True):
+        out = ops.tafa_weighted_sum_logits(x_all, parts, 4, out_nhwc=nhwc)
+        out = out.view(N, 7, 7, C).permute(0, 3, 1, 2) if nhwc else out.view(N, C, 7, 7)
+        assert rel_err(out, want) < TIGHT
+
+
+def test_tafa_keyproj_unsupported_shapes_take_the_embedding_path():
+    assert ops.tafa_keyproj_chunk(16, 49, 512, 4) == 32 and ops.tafa_keyproj_chunk(32, 49, 512, 4) == 32
+    assert ops.tafa_keyproj_chunk(64, 49, 512, 4) == 32     # frames are tiled 16 per CTA
+    assert ops.tafa_keyproj_chunk(16, 256, 512, 4) == 0     # [16, P, 32] tile beyond shared memory
+    assert ops.tafa_keyproj_chunk(16, 49, 512, 8) == 0      # heads != 4
+    assert ops.tafa_keyproj_chunk(16, 49, 48, 4) == 0       # C % 32
+    x_all = torch.zeros(4, 2, 49, 48, device=DEV)
+    with pytest.raises(vod.VodError):
+        ops.tafa_keyproj_logits(x_all, torch.zeros(4, 98, 9 * 48, device=DEV), 7, 4, 16)
+
+
+def test_temporal_roi_align_keyproj_matches_embedding_path_full_size():
+    """cfg 3 (N=300, 15 reference maps): the key-projected path against the full-embedding path, both with fp32 library math."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(0)
+    g = torch.Generator().manual_seed(44)
+    m = vod.build_roi_extractor(dict(type='TemporalRoIAlign', num_most_similar_points=2, num_temporal_attention_blocks=4,
+                                     roi_layer=dict(type='RoIAlign', output_size=7, sampling_ratio=2),
+                                     out_channels=512, featmap_strides=[16])).to(DEV)
+    T, N = 15, 300
+    ref = torch.relu(torch.randn(T, 512, 38, 63, generator=g)).to(DEV)
+    rois = rpn_like_rois(g, N, 1).to(DEV)
+    m.keyproj = False
+    a = m((ref[-1:],), rois, ref_feats=(ref,))
+    m.keyproj = True
+    b = m((ref[-1:],), rois, ref_feats=(ref,))
+    assert rel_err(b, a) < TIGHT
+    m.keyproj = None
+    assert torch.equal(m((ref[-1:],), rois, ref_feats=(ref,)), b)   # 16 stacked frames: the default takes the key-projected path
 
 
 def test_layout_kernel():

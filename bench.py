@@ -203,7 +203,7 @@ def kernel_rooflines(cfg, device, peaks):
         t = timeit(lambda: ops.tafa_keyproj_logits(x_all, G, 7, 4, cc))
         b = (G.numel() + x_all.numel()) * 4
         out['tafa_keyproj_logits'] = dict(bound='hbm', seconds=t, achieved=b / t / 1e9, peak=peaks['hbm'], unit='GB/s', bytes=b,
-                                          traffic=1627.1e6, note='traffic = dram read+write per launch from ncu --set full (profiles/r01h_ncu_keyproj.csv)')
+                                          traffic=1626.1e6, note='traffic = dram read+write per launch from ncu --set full (profiles/r01h_ncu_full_summary.csv)')
         parts = ops.tafa_keyproj_logits(x_all, G, 7, 4, cc)
         t = timeit(lambda: ops.tafa_weighted_sum_logits(x_all, parts, 4, out_nhwc=True))
         b = (x_all.numel() + N * P * C + parts.numel()) * 4

@@ -133,3 +133,47 @@ def test_host_glue_matches_oracle_on_cpu():
     assert torch.equal(r[:, 1:], torch.cat(lst, 0))
     r2 = vod.bbox2roi([torch.rand(3, 4), torch.zeros(0, 4), torch.rand(2, 4)])
     assert r2.shape == (5, 5) and r2[:, 0].tolist() == [0, 0, 0, 2, 2]
+
+
+def test_keyproj_weight_layout_and_identity_cpu(golden):
+    """Host side of the key-projected TAFA logits (roi_extractors.TemporalRoIAlign._keyproj_weight): with the weight laid out as
+    the C ABI documents (G [heads, N*P, C/cc, 9, cc]), contracting the raw RoI features with G = ek_head . W_head reproduces
+    the reference's temporal_attentional_feature_aggregation (temporal_roi_align.py:44-97) on the golden TemporalRoIAlign
+    parameters -- the identity the CUDA kernel relies on, checked here in plain torch (no kernel call)."""
+    import torch
+    import lowlightenvironmentvideoobjectdetection_b200 as vod
+    from conftest import params, rel_err
+    from oracle import vod_oracle as O
+    m = vod.build_roi_extractor(dict(type='TemporalRoIAlign', num_most_similar_points=2, num_temporal_attention_blocks=4,
+                                     roi_layer=dict(type='RoIAlign', output_size=7, sampling_ratio=2),
+                                     out_channels=64, featmap_strides=[16]))
+    m.load_state_dict(params(golden, 'troi_p.'))
+    conv = m.embed_network.conv
+    H, C, cc, P = 4, 64, 32, 49
+    wr = m._keyproj_weight(conv, H, cc)
+    assert wr.shape == (H, C // H, 9 * C)
+    g = torch.Generator().manual_seed(5)
+    T1, N = 5, 3
+    x = torch.randn(1, N, C, 7, 7, generator=g)
+    ref_x = torch.randn(T1 - 1, N, C, 7, 7, generator=g)
+    want = O.tafa(x, ref_x, conv.weight.detach(), conv.bias.detach(), H)
+    x_all = torch.cat((x, ref_x), 0)
+    ek = torch.nn.functional.conv2d(x_all[0], conv.weight, conv.bias, padding=1).detach()
+    ek_rows = ek.permute(0, 2, 3, 1).reshape(N * P, H, C // H)
+    G = torch.bmm(ek_rows.transpose(0, 1), wr).view(H, N, P, C // cc, 9, cc)
+    xr = x_all.permute(0, 1, 3, 4, 2)                                   # [T1, N, 7, 7, C]
+    logits = torch.zeros(N, P, H, T1)
+    for p in range(P):
+        py, px = divmod(p, 7)
+        for tap in range(9):
+            qy, qx = py + tap // 3 - 1, px + tap % 3 - 1
+            if 0 <= qy < 7 and 0 <= qx < 7:
+                xv = xr[:, :, qy, qx, :].reshape(T1, N, C // cc, cc)
+                logits[:, p] += torch.einsum('tnkc,hnkc->nht', xv, G[:, :, p, :, tap, :])
+    w = torch.softmax(logits / (C // H) ** 0.5, dim=-1).repeat_interleave(C // H, dim=2)   # [N, P, C, T1]
+    out = torch.einsum('tnpc,npct->npc', xr.reshape(T1, N, P, C), w).view(N, 7, 7, C).permute(0, 3, 1, 2)
+    assert rel_err(out, want) < 1e-5
+    # path selection: few stacked frames / unsupported convs take the full-embedding path
+    assert m._keyproj_chunk(4, P, C) == 0                # below keyproj_min_frames
+    m.keyproj = False
+    assert m._keyproj_chunk(16, P, C) == 0

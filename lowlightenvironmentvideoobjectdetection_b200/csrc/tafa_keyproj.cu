@@ -11,20 +11,24 @@
 // Only the key patches go through the conv (1/(T+1) of the work); this kernel contracts the raw RoI features x_all with G:
 // 3.6 G fp32 FMA on the CUDA cores and one streaming read of G (1.08 GB) and x_all (0.48 GB) -- HBM-bound, not a GEMM.
 //
-//   Work unit ("tile") = (RoI n, chunk of 32 input channels, block of 8 frames): its x_all slice [8][P][32] (50 KB) arrives in
-//   shared memory as ONE 3-D TMA box and every element is reused by up to 9 taps of the neighbouring output positions.
-//   warp = output position p; lane = (tg, cg): tg owns 2 frames, cg owns 4 consecutive channels (128-bit accesses).
+//   Work unit ("tile") = (RoI n, chunk of 32 input channels, block of 16 frames): its x_all slice [16][P][32] (98 KB) arrives
+//   in shared memory as ONE 3-D TMA box and every element is reused by up to 9 taps of the neighbouring output positions.
+//   warp = output position p; lane = (tg, cg): tg owns 4 frames, cg owns 4 consecutive channels (128-bit accesses).
 //   G has no reuse but is 70 % of the bytes: each consumer warp streams the four head rows (9 taps x 32 channels, 1152
-//   contiguous bytes each) of its NEXT positions into a private shared-memory ring with cp.async.bulk + mbarrier.
-//   Per (tap, 32 channels): 4 G vectors x 2 frame vectors from shared memory -> 16 packed FFMA2 per lane.
-//   The (frame, head) partial sums are reduced over the 8 cg lanes by a transposing butterfly (7 shuffles) and written as
+//   contiguous bytes each) of its NEXT positions into a private shared-memory ring with cp.async.bulk + mbarrier (no
+//   registers held while in flight, 129 KB of ring per SM).
+//   Per (tap, 32 channels): 4 G vectors x 4 frame vectors from shared memory -> 32 packed FFMA2 per lane.
+//   The (frame, head) partial sums are reduced over the 8 cg lanes by a transposing butterfly (14 shuffles) and written as
 //   per-chunk partial logits [C/32][N][P][H][T1]; the weighting kernel (tafa.cu) sums the chunks -- deterministic, no atomics.
 //
-//   Persistent kernel: one CTA per SM walks a contiguous range of tiles; a producer warp keeps TWO frame tiles in flight
-//   (double buffer, full/empty mbarriers) and the consumer warps' position stream runs on across tile boundaries, so neither
-//   the tile load nor the first ring fill is ever exposed.  Probes on the one-CTA-per-tile version of this kernel (kept below for
-//   frame blocks of 16, VOD_KP_PERSIST=0) showed why: memory alone 255 us, FMAs alone 160 us, but 175 us of per-CTA start-up
-//   (launch + first ring fill + tile load) that overlapped with neither -- 383 us in total.
+//   Shipped for more than 8 frames: the persistent kernel <16, 1> -- one CTA per SM walks a contiguous range of tiles, a
+//   producer warp requests the next frame tile as soon as every consumer warp has left the current one, and the consumer warps'
+//   position stream (and with it the G rings) runs on across tile boundaries, so the first ring fill is paid once per SM instead
+//   of once per tile.  Up to 8 frames: one CTA per 8-frame tile, two CTAs per SM (HBM-bound at 5.6 TB/s).  The other variants
+//   (one CTA per 16-frame tile, persistent double-buffered 8-frame tiles) stay selectable through VOD_KP_* for the record of the
+//   measurements in DESIGN.md section 4.  Probes (VOD_KP_DBG) on the one-CTA-per-tile version: memory alone 255 us, FMAs alone
+//   160 us, per-CTA start-up 175 us; the ncu source page puts ~500 of the ~750 warp instructions per position outside the
+//   FFMA2 / LDS core (bulk-copy issue, mbarrier waits, butterfly, tap control) -- the next thing to cut.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -37,7 +41,6 @@ constexpr int kKpCC = 32;                         // channels per tile
 constexpr int kKpRowFloats = 9 * kKpCC;           // one (head, position) row of G for this chunk
 constexpr int kKpStageFloats = kKpHeads * kKpRowFloats;
 constexpr int kKpMaxWarps = 16;
-constexpr int kKpTile = 8;                        // frames per tile of the persistent kernel
 
 __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -124,10 +127,14 @@ __device__ __forceinline__ void kp_position(const float *__restrict__ xlane, con
 
 // ------------------------------------------------------------------------------------------------ persistent kernel
 // blockDim = (nwc + 1) warps: warps 0..nwc-1 consume, warp nwc produces the frame tiles.  Requires nwc <= P.
+// <TB = 8, NBUF = 2>: 8-frame tiles, double-buffered (a warp may run one tile ahead of the slowest).
+// <TB = 16, NBUF = 1>: 16-frame tiles (twice the FMAs per shared-memory load and per G byte), one buffer: the next tile is
+//   requested when every warp has left the current one; the G rings keep streaming across that gap.
+template <int TB, int NBUF>
 __global__ void __launch_bounds__(kKpMaxWarps * 32, 1)
 tafa_keyproj_persist_kernel(const __grid_constant__ CUtensorMap tm_x, const float *__restrict__ G, float *__restrict__ parts,
                             int T1, int N, int ph, int pw, int C, int depth, int tiles_per_cta, int dbg) {
-    constexpr int H = kKpHeads, CC = kKpCC, TB = kKpTile, FR = TB / 4, NV = FR * H;
+    constexpr int H = kKpHeads, CC = kKpCC, FR = TB / 4, NV = FR * H;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int nch = C / CC, ntb = ceil_div(T1, TB), P = ph * pw;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwc = (blockDim.x >> 5) - 1;
@@ -136,8 +143,8 @@ tafa_keyproj_persist_kernel(const __grid_constant__ CUtensorMap tm_x, const floa
     const int tile0 = blockIdx.x * tiles_per_cta;
     const int my_tiles = max(0, min(tiles_per_cta, total_tiles - tile0));
     const int tile_floats = TB * P * CC;
-    float *xs = reinterpret_cast<float *>(smem_raw);                                    // [2][TB][P][CC]
-    float *ring = xs + 2 * (size_t)tile_floats;                                         // [nwc][depth][H][9][CC]
+    float *xs = reinterpret_cast<float *>(smem_raw);                                    // [NBUF][TB][P][CC]
+    float *ring = xs + NBUF * (size_t)tile_floats;                                      // [nwc][depth][H][9][CC]
     uint64_t *bars = reinterpret_cast<uint64_t *>(ring + (size_t)nwc * depth * kKpStageFloats);   // [nwc][depth], xfull[2], xempty[2]
     uint64_t *xfull = bars + nwc * depth, *xempty = xfull + 2;
     unsigned *tap_mask = reinterpret_cast<unsigned *>(xempty + 2);                      // [P]
@@ -145,7 +152,7 @@ tafa_keyproj_persist_kernel(const __grid_constant__ CUtensorMap tm_x, const floa
     const size_t head_stride = NP * 9 * (size_t)C;        // floats between the heads of G
 
     if (tid == 0) {
-        for (int b = 0; b < 2; ++b) { tc::mbar_init(xfull + b, 1); tc::mbar_init(xempty + b, nwc); }
+        for (int b = 0; b < NBUF; ++b) { tc::mbar_init(xfull + b, 1); tc::mbar_init(xempty + b, nwc); }
         for (int s = 0; s < nwc * depth; ++s) tc::mbar_init(bars + s, 1);
         tc::fence_barrier_init();
     }
@@ -157,8 +164,8 @@ tafa_keyproj_persist_kernel(const __grid_constant__ CUtensorMap tm_x, const floa
         // ---- producer: frame tile j of this CTA -> buffer j & 1 as one 3-D TMA box (frames past T1 arrive as zeros)
         if (lane == 0) {
             for (int j = 0; j < my_tiles; ++j) {
-                const int b = j & 1;
-                if (j >= 2) tc::mbar_wait(xempty + b, (uint32_t)(((j >> 1) - 1) & 1));   // consumers are done with tile j-2
+                const int b = j % NBUF;
+                if (j >= NBUF) tc::mbar_wait(xempty + b, (uint32_t)((j / NBUF - 1) & 1));   // consumers are done with tile j-NBUF
                 const unsigned tile = tile0 + j, nc = tile / ntb;
                 if (!(dbg & 4)) {
                     tc::mbar_arrive_expect_tx(xfull + b, (uint32_t)(tile_floats * sizeof(float)));
@@ -211,8 +218,8 @@ tafa_keyproj_persist_kernel(const __grid_constant__ CUtensorMap tm_x, const floa
             const unsigned tile = tile0 + j, nc = tile / ntb;
             t0 = (int)(tile % ntb) * TB; nt = min(TB, T1 - t0);
             out_tile = parts + ((size_t)(nc % nch) * N + nc / nch) * P * H * T1 + t0;    // [chunk][n] + frame block
-            tc::mbar_wait(xfull + (j & 1), (uint32_t)((j >> 1) & 1));
-            xlane = xs + (size_t)(j & 1) * tile_floats + (size_t)tg * FR * P * CC + cg * 4;
+            tc::mbar_wait(xfull + j % NBUF, (uint32_t)((j / NBUF) & 1));
+            xlane = xs + (size_t)(j % NBUF) * tile_floats + (size_t)tg * FR * P * CC + cg * 4;
         }
         tc::mbar_wait(my_bars + s, phase);
         float vc[NV / 8];
@@ -233,7 +240,7 @@ tafa_keyproj_persist_kernel(const __grid_constant__ CUtensorMap tm_x, const floa
         p += nwc;
         if (p >= P) {                                      // this warp's last position in tile j: release the frame buffer
             p -= P;
-            if (lane == 0) tc::mbar_arrive(xempty + (j & 1));
+            if (lane == 0) tc::mbar_arrive(xempty + j % NBUF);
             ++j;
         }
     }
@@ -337,28 +344,30 @@ extern "C" int vod_tafa_keyproj_logits(const float *x_all, const float *G, float
     VOD_REQUIRE(N <= 65535 && C / cc <= 65535 && (long)N * (C / cc) * ceil_div(T1, 8) < (1L << 30),
                 "vod_tafa_keyproj_logits: grid too large");
     const int P = ph * pw;
-    // Measured at N=300, C=512 (B200): 16 stacked frames -- one CTA per 16-frame tile 383 us, persistent 8-frame tiles 432 us,
-    // one CTA per 8-frame tile (two per SM) 458 us; 8 frames -- one CTA per 8-frame tile 241 us (5.6 TB/s).
-    int persist = 0, tb = T1 > 8 ? 16 : 8, warps = min(T1 > 8 ? 14 : 7, P), depth = 2, dbg = 0;
+    // Measured at N=300, C=512 (B200).  16 stacked frames: persistent 16-frame tiles 381 us, one CTA per 16-frame tile 391 us,
+    // persistent double-buffered 8-frame tiles 432 us, one CTA per 8-frame tile (two per SM) 458 us.  32 frames: persistent
+    // 16-frame tiles 723 us, one CTA per tile 893 us.  8 frames: one CTA per 8-frame tile 241 us (5.6 TB/s).
+    int persist = T1 > 8, tb = T1 > 8 ? 16 : 8, warps = min(T1 > 8 ? 14 : 7, P), depth = 2, dbg = 0;
     // tuning / probe hooks (dbg: 1 = no FMAs, 2 = no G refills after the first ring fill, 4 = no frame tile loads)
     if (const char *e = getenv("VOD_KP_PERSIST")) persist = atoi(e) != 0;
     if (const char *e = getenv("VOD_KP_TB")) tb = atoi(e) == 16 ? 16 : 8;
     if (const char *e = getenv("VOD_KP_WARPS")) warps = max(1, min(atoi(e), min(kKpMaxWarps, P)));
     if (const char *e = getenv("VOD_KP_DEPTH")) depth = max(1, min(atoi(e), 8));
     if (const char *e = getenv("VOD_KP_DBG")) dbg = atoi(e);
-    if (persist) { tb = kKpTile; warps = min(warps, kKpMaxWarps - 1); }   // + the producer warp
-    const int tile_frames = persist ? 2 * kKpTile : tb;     // the persistent kernel double-buffers its frame tile
+    if (persist) warps = min(warps, kKpMaxWarps - 1);      // + the producer warp
+    const int tile_frames = persist ? 16 : tb;              // persistent: 2 x 8 frames (double buffer) or 1 x 16
     while (warps > 4 && kp_smem_bytes(tile_frames, P, warps, depth) > kKpSmemLimit) --warps;
     while (depth > 2 && kp_smem_bytes(tile_frames, P, warps, depth) > kKpSmemLimit) --depth;
     if (persist && kp_smem_bytes(tile_frames, P, warps, depth) > kKpSmemLimit) {   // large patches: one tile per CTA
         persist = 0;
         tb = 8;
     }
-    const size_t smem = kp_smem_bytes(persist ? 2 * kKpTile : tb, P, warps, depth);
+    const size_t smem = kp_smem_bytes(persist ? 16 : tb, P, warps, depth);
     VOD_REQUIRE(smem <= kKpSmemLimit, "vod_tafa_keyproj_logits: tile does not fit shared memory");
     static bool attr_set = false;   // immutable function attributes, set once
     if (!attr_set) {
-        cudaFuncSetAttribute(tafa_keyproj_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKpSmemLimit);
+        cudaFuncSetAttribute(tafa_keyproj_persist_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKpSmemLimit);
+        cudaFuncSetAttribute(tafa_keyproj_persist_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKpSmemLimit);
         cudaFuncSetAttribute(tafa_keyproj_logits_kernel<8, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKpSmemLimit);
         cudaFuncSetAttribute(tafa_keyproj_logits_kernel<8, kKpMaxWarps, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKpSmemLimit);
         cudaFuncSetAttribute(tafa_keyproj_logits_kernel<16, kKpMaxWarps, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKpSmemLimit);
@@ -371,12 +380,15 @@ extern "C" int vod_tafa_keyproj_logits(const float *x_all, const float *G, float
         return rc;
     cudaStream_t st = as_stream(stream);
     if (persist) {
-        const long total_tiles = (long)N * (C / cc) * ceil_div(T1, kKpTile);
+        const long total_tiles = (long)N * (C / cc) * ceil_div(T1, tb);
         int sms = kNumSMs;
         if (const char *e = getenv("VOD_KP_CTAS")) sms = max(1, atoi(e));
         const int tiles_per_cta = (int)ceil_div(total_tiles, (long)sms);
         const int grid = (int)ceil_div(total_tiles, (long)tiles_per_cta);
-        tafa_keyproj_persist_kernel<<<grid, (warps + 1) * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, tiles_per_cta, dbg);
+        if (tb == 16)
+            tafa_keyproj_persist_kernel<16, 1><<<grid, (warps + 1) * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, tiles_per_cta, dbg);
+        else
+            tafa_keyproj_persist_kernel<8, 2><<<grid, (warps + 1) * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, tiles_per_cta, dbg);
     } else {
         dim3 grid(ceil_div(T1, tb), C / cc, N);
         if (tb == 16)

@@ -648,6 +648,29 @@ def test_fgfa_path_cfg2_bf16_io():
     assert rel_err(out.float(), want) < 2e-2
 
 
+def test_dff_path_cfg4_low_light_clip():
+    """BASELINE config 4 (DFF, key-frame interval 10, low-light clip): mmtracking/mmtrack/models/vid/dff.py:200-217 -- every
+    non-key frame is the key frame's feature map warped by that frame's flow (flow_warp_feats with one map).  One key
+    interval of a synthetic low-light clip (features scaled by 0.25 as SeqBrighten(m=0.25) darkens the frames), R-50-DC5
+    shapes; also the batched form (the 9 non-key frames of an interval share one key map: one launch, same rows)."""
+    g = torch.Generator().manual_seed(72)
+    C, H, W, interval = 512, 38, 63, 10
+    key_feat = torch.relu(torch.randn(1, C, H, W, generator=g)) * 0.25
+    flows = torch.randn(interval - 1, 2, H * 16, W * 16, generator=g) * 6
+    key_dev = key_feat.to(DEV)
+    per_frame = []
+    for f in range(interval - 1):                       # frame_id % key_frame_interval != 0
+        got = vod.flow_warp_feats(key_dev, flows[f:f + 1].to(DEV))
+        assert got.shape == (1, C, H, W) and got.is_contiguous()
+        assert rel_err(got, O.flow_warp_feats(key_feat, flows[f:f + 1])) < TIGHT
+        per_frame.append(got)
+    batched = vod.flow_warp_feats(key_dev.expand(interval - 1, C, H, W), flows.to(DEV))
+    assert torch.equal(batched, torch.cat(per_frame, 0))
+    # zero flow on a non-key frame reproduces the key map's bilinear self-sampling (grid scaled by (W-1)/W, flow.py:30-36)
+    zero = vod.flow_warp_feats(key_dev, torch.zeros(1, 2, H * 16, W * 16, device=DEV))
+    assert rel_err(zero, O.flow_warp_feats(key_feat, torch.zeros(1, 2, H * 16, W * 16))) < TIGHT
+
+
 @pytest.mark.parametrize('troi,fcs', [(False, 2), (True, 3)])
 def test_selsa_roi_head_step_vs_oracle(troi, fcs):
     """One key-frame step through SelsaRoIHead.simple_test against the same step on the CPU oracle: BASELINE config 1

@@ -364,21 +364,15 @@ extern "C" int vod_tafa_keyproj_logits(const float *x_all, const float *G, float
     }
     const size_t smem = kp_smem_bytes(persist ? 16 : tb, P, warps, depth);
     VOD_REQUIRE(smem <= kKpSmemLimit, "vod_tafa_keyproj_logits: tile does not fit shared memory");
-    static bool attr_set = false;   // immutable function attributes, set once
-    if (!attr_set) {
-        cudaFuncSetAttribute(tafa_keyproj_persist_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKpSmemLimit);
-        cudaFuncSetAttribute(tafa_keyproj_persist_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKpSmemLimit);
-        cudaFuncSetAttribute(tafa_keyproj_logits_kernel<8, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKpSmemLimit);
-        cudaFuncSetAttribute(tafa_keyproj_logits_kernel<8, kKpMaxWarps, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKpSmemLimit);
-        cudaFuncSetAttribute(tafa_keyproj_logits_kernel<16, kKpMaxWarps, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKpSmemLimit);
-        attr_set = true;
-    }
     // x_all [T1][N*P][C] as a 3-D tensor, box = (32 channels, P positions, tb frames)
     CUtensorMap tm_x;
     if (int rc = make_tmap_f32_3d(&tm_x, x_all, (uint64_t)C, (uint64_t)N * P, (uint64_t)T1, (uint64_t)C * 4,
                                   (uint64_t)N * P * C * 4, kKpCC, (uint32_t)P, (uint32_t)tb))
         return rc;
     cudaStream_t st = as_stream(stream);
+    // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute: set it on every call (cheap,
+    // idempotent) rather than once per process, so a second device in the same process works too
+    auto allow = [&](auto kern) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); return kern; };
     if (persist) {
         const long total_tiles = (long)N * (C / cc) * ceil_div(T1, tb);
         int sms = kNumSMs;
@@ -386,17 +380,17 @@ extern "C" int vod_tafa_keyproj_logits(const float *x_all, const float *G, float
         const int tiles_per_cta = (int)ceil_div(total_tiles, (long)sms);
         const int grid = (int)ceil_div(total_tiles, (long)tiles_per_cta);
         if (tb == 16)
-            tafa_keyproj_persist_kernel<16, 1><<<grid, (warps + 1) * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, tiles_per_cta, dbg);
+            allow(tafa_keyproj_persist_kernel<16, 1>)<<<grid, (warps + 1) * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, tiles_per_cta, dbg);
         else
-            tafa_keyproj_persist_kernel<8, 2><<<grid, (warps + 1) * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, tiles_per_cta, dbg);
+            allow(tafa_keyproj_persist_kernel<8, 2>)<<<grid, (warps + 1) * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, tiles_per_cta, dbg);
     } else {
         dim3 grid(ceil_div(T1, tb), C / cc, N);
         if (tb == 16)
-            tafa_keyproj_logits_kernel<16, kKpMaxWarps, 1><<<grid, warps * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, dbg);
+            allow(tafa_keyproj_logits_kernel<16, kKpMaxWarps, 1>)<<<grid, warps * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, dbg);
         else if (warps <= 8 && kp_smem_bytes(tb, P, warps, depth) <= 113 * 1024)
-            tafa_keyproj_logits_kernel<8, 8, 2><<<grid, warps * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, dbg);
+            allow(tafa_keyproj_logits_kernel<8, 8, 2>)<<<grid, warps * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, dbg);
         else
-            tafa_keyproj_logits_kernel<8, kKpMaxWarps, 1><<<grid, warps * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, dbg);
+            allow(tafa_keyproj_logits_kernel<8, kKpMaxWarps, 1>)<<<grid, warps * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, dbg);
     }
     note_launch();
     return check_launch("vod_tafa_keyproj_logits");

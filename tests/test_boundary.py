@@ -177,3 +177,16 @@ def test_keyproj_weight_layout_and_identity_cpu(golden):
     assert m._keyproj_chunk(4, P, C) == 0                # below keyproj_min_frames
     m.keyproj = False
     assert m._keyproj_chunk(16, P, C) == 0
+
+
+def test_keyproj_shape_gate_is_host_only():
+    """vod_tafa_keyproj_chunk is pure host logic (no device call): which shapes the key-projected logits kernel accepts.
+    Everything else must take the full-embedding path (vod_tafa_weighted_sum), never a silent partial result."""
+    from lowlightenvironmentvideoobjectdetection_b200 import ops
+    assert ops.tafa_keyproj_chunk(16, 49, 512, 4) == 32          # cfg 3
+    assert ops.tafa_keyproj_chunk(32, 49, 512, 4) == 32          # sweep maximum (frames are tiled, any count works)
+    assert ops.tafa_keyproj_chunk(1, 49, 64, 4) == 32
+    assert ops.tafa_keyproj_chunk(16, 49, 512, 8) == 0           # heads != 4
+    assert ops.tafa_keyproj_chunk(16, 49, 48, 4) == 0            # channels not a multiple of the 32-channel chunk
+    assert ops.tafa_keyproj_chunk(16, 16 * 16, 512, 4) == 0      # 16x16 bins: the frame tile exceeds shared memory
+    assert ops.tafa_keyproj_chunk(0, 49, 512, 4) == 0

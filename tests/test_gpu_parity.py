@@ -370,6 +370,21 @@ def test_layout_kernel():
 
 
 # ------------------------------------------------------------------------------------------ fixed-shape get_bboxes / graph
+def _dets_match(d1, l1, d0, l0, tol=1e-2):
+    """Detections are ordered by score: two boxes whose scores differ by less than the numerical noise of the step may swap
+    places, so rows are matched to the nearest row of the same label instead of by rank (returns the worst distance)."""
+    d1, l1, d0, l0 = d1.cpu(), l1.cpu(), d0.cpu(), l0.cpu()
+    assert d1.shape == d0.shape, (d1.shape, d0.shape)
+    assert torch.equal(l1.sort().values, l0.sort().values), 'detected labels differ'
+    if d1.numel() == 0:
+        return 0.0
+    cost = (d1[:, None, :] - d0[None, :, :]).abs().amax(dim=2)
+    cost = cost.masked_fill(l1[:, None] != l0[None, :], float('inf'))
+    err = max(cost.min(dim=1).values.max().item(), cost.min(dim=0).values.max().item())
+    assert err < tol, err
+    return err
+
+
 def _head(C=64, D=128, classes=6, fcs=2, troi=True):
     torch.manual_seed(0)
     ext = dict(type='TemporalRoIAlign' if troi else 'SingleRoIExtractor',
@@ -430,10 +445,13 @@ def test_device_multiclass_split_path():
         assert k == len(d0) and torch.equal(l1[:k].cpu(), l0) and torch.equal(d1[:k].cpu(), d0)
 
 
-def test_cuda_graph_replay_matches_eager():
+@pytest.mark.parametrize('T', [3, 9])
+def test_cuda_graph_replay_matches_eager(T):
+    """T = 9 stacks 10 frames: TemporalRoIAlign takes the key-projected path (key-slot conv, G GEMM, TMA logits kernel with a
+    tensor map built at capture time) inside the captured graph."""
     g = torch.Generator().manual_seed(33)
     head = _head()
-    C, H, W, N, T = 64, 12, 20, 24, 3
+    C, H, W, N = 64, 12, 20, 24
     ref_x = torch.relu(torch.randn(T, C, H, W, generator=g)).to(DEV)
     x = ref_x[T - 1:T].clone()
     rois = rpn_like_rois(g, N, 1, W * 16., H * 16.).to(DEV)
@@ -448,7 +466,11 @@ def test_cuda_graph_replay_matches_eager():
         torch.cuda.synchronize()
         de, le, ce = head.simple_test_device((x,), (ref_x,), rois, ref_rois, (H * 16, W * 16, 3), (1., 1., 1., 1.))
         assert int(c.item()) == int(ce.item())
-        assert torch.equal(l, le) and torch.equal(d, de)
+        if T == 3:
+            assert torch.equal(l, le) and torch.equal(d, de)
+        else:   # library GEMM / conv plans may differ between capture and eager execution: compare numerically
+            n = int(c.item())
+            _dets_match(d[:n], l[:n], de[:n], le[:n], tol=1e-3)
 
 
 # ------------------------------------------------------------------------------------------ full BASELINE sizes: properties
@@ -671,14 +693,15 @@ def test_dff_path_cfg4_low_light_clip():
     assert rel_err(zero, O.flow_warp_feats(key_feat, torch.zeros(1, 2, H * 16, W * 16))) < TIGHT
 
 
-@pytest.mark.parametrize('troi,fcs', [(False, 2), (True, 3)])
-def test_selsa_roi_head_step_vs_oracle(troi, fcs):
+@pytest.mark.parametrize('troi,fcs,T', [(False, 2, 3), (True, 3, 3), (True, 3, 9)])
+def test_selsa_roi_head_step_vs_oracle(troi, fcs, T):
     """One key-frame step through SelsaRoIHead.simple_test against the same step on the CPU oracle: BASELINE config 1
-    (plain SingleRoIExtractor, 2 aggregator layers, 2 refs + key) and config 3 (TemporalRoIAlign, 3 layers), small shapes."""
+    (plain SingleRoIExtractor, 2 aggregator layers, 2 refs + key) and config 3 (TemporalRoIAlign, 3 layers), small shapes;
+    with 9 reference maps TemporalRoIAlign stacks 10 frames and takes the key-projected attention-logits path."""
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
-    g = torch.Generator().manual_seed(80 + fcs)
-    C, H, W, N, T, D, classes = 64, 12, 20, 30, 3, 128, 6
+    g = torch.Generator().manual_seed(80 + fcs + T)
+    C, H, W, N, D, classes = 64, 12, 20, 30, 128, 6
     head = _head(C, D, classes, fcs, troi)
     ref_x = torch.relu(torch.randn(T, C, H, W, generator=g))
     x = ref_x[T - 1:T].clone()
@@ -697,6 +720,4 @@ def test_selsa_roi_head_step_vs_oracle(troi, fcs):
     hp = {k[len('bbox_head.'):]: v for k, v in sd.items() if k.startswith('bbox_head.')}
     cls, reg = O.selsa_bbox_head(feats, ref_feats, hp, fcs, 2)
     d0, l0 = O.get_bboxes(rois, cls, reg, (H * 16, W * 16, 3), (1., 1., 1., 1.), False, 0.0001, dict(type='nms', iou_threshold=0.5), 100)
-    d1, l1 = dets[0].cpu(), labels[0].cpu()
-    assert d1.shape == d0.shape and torch.equal(l1, l0)
-    assert (d1 - d0).abs().max() < 1e-2      # boxes in px and scores after 2-3 tf32 SELSA layers
+    _dets_match(dets[0], labels[0], d0, l0, tol=1e-2)      # boxes in px and scores after 2-3 tf32 SELSA layers

@@ -270,8 +270,102 @@ def kernel_rooflines(cfg, device, peaks):
     return out
 
 
+# --------------------------------------------------------------------------------------------- parity of the benchmarked step
+class library_math:
+    """Scoped switch of the math mode of the LIBRARY GEMMs / convs around the path (cuBLAS shared FCs and projections, the
+    cuDNN key-slot embed conv): tf32 (what the headline number runs with) or fp32.  Our own kernels do not read these flags.
+    Restores the previous global flags on exit."""
+
+    def __init__(self, tf32):
+        self.tf32 = bool(tf32)
+
+    def __enter__(self):
+        self.prev = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        torch.backends.cuda.matmul.allow_tf32 = self.tf32
+        torch.backends.cudnn.allow_tf32 = self.tf32
+        return self
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = self.prev
+        return False
+
+
+def step_rois(cfg, props_all, device=None):
+    N, T = cfg['N'], cfg['T']
+    props_all = props_all.to(device) if device is not None else props_all
+    rois = torch.cat([props_all.new_zeros(N, 1), props_all[T]], 1)
+    ids = torch.arange(T, dtype=props_all.dtype, device=props_all.device).repeat_interleave(N)[:, None]
+    ref_rois = torch.cat([ids, props_all[:T].reshape(T * N, 4)], 1)
+    return rois, ref_rois
+
+
+def gpu_step_outputs(head, cfg, ref_x, props_all):
+    """One key-frame step on the device exactly as the timed loop runs it (``SelsaRoIHead.simple_test_device``: fixed-shape
+    detections + count), plus the intermediates the parity report compares."""
+    T = cfg['T']
+    rois, ref_rois = step_rois(cfg, props_all)
+    x = ref_x[T - 1:T]
+    with torch.no_grad():
+        res = head._bbox_forward((x,), (ref_x,), rois, ref_rois)
+        dets, labels, count = head.bbox_head.get_bboxes_device(rois, res['cls_score'], res['bbox_pred'], IMG_SHAPE, (1., 1., 1., 1.),
+                                                               rescale=False, cfg=head.test_cfg)
+    n = int(count.item())
+    return dict(bbox_feats=res['bbox_feats'].float().cpu(), cls_score=res['cls_score'].float().cpu(),
+                bbox_pred=res['bbox_pred'].float().cpu(), dets=dets[:n].cpu(), labels=labels[:n].cpu())
+
+
+def _rel_err(a, b):
+    a, b = a.double(), b.double()
+    nan_same = bool(torch.equal(torch.isnan(a), torch.isnan(b)))
+    a, b = torch.nan_to_num(a), torch.nan_to_num(b)
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)), nan_same
+
+
+def match_detections(d1, l1, d0, l0, box_tol=1.0, score_tol=1e-3):
+    """Fraction of detections that have a counterpart of the same label within ``box_tol`` px and ``score_tol`` in the other
+    set (the smaller of the two directions).  Detections are a top-100 by score: candidates whose scores differ by less than
+    the step's numerical noise can swap in and out at the cut, so this is a fraction, not an equality."""
+    if len(d0) == 0 or len(d1) == 0:
+        return 1.0 if len(d0) == len(d1) else 0.0
+    box = (d1[:, None, :4] - d0[None, :, :4]).abs().amax(dim=2)
+    sc = (d1[:, None, 4] - d0[None, :, 4]).abs()
+    ok = (box <= box_tol) & (sc <= score_tol) & (l1[:, None] == l0[None, :])
+    return float(min(ok.any(dim=1).float().mean(), ok.any(dim=0).float().mean()))
+
+
+def parity_report(ours, want, exclude_rois=None):
+    """max|a-b| / max|b| of the step's tensors against the CPU oracle (overall and per RoI), and the matched fraction of the
+    final detections.  An exact fp32 TIE between two reference locations (similarities closer than the fp32 rounding of a
+    512-term dot product) may be broken differently by the two implementations: that RoI then samples another pixel and its
+    row differs visibly while every other RoI agrees to ~1e-6, which is why the per-RoI distribution is reported next to the
+    maximum.  ``exclude_rois``: RoIs whose differing pick was verified to be such a tie (tests only)."""
+    rep = {}
+    n = want['bbox_feats'].shape[0]
+    keep = torch.ones(n, dtype=torch.bool)
+    if exclude_rois is not None and len(exclude_rois):
+        keep[torch.as_tensor(sorted(exclude_rois))] = False
+        rep['rois_excluded_as_fp32_ties'] = int((~keep).sum())
+    for k in ('bbox_feats', 'cls_score', 'bbox_pred'):
+        a, b = ours[k].reshape(want[k].shape).double(), want[k].double()
+        if not torch.equal(torch.isnan(a), torch.isnan(b)):
+            rep[k + '_nan_mismatch'] = True
+        a, b = torch.nan_to_num(a), torch.nan_to_num(b)
+        scale = float(b.abs().max().clamp_min(1e-30))
+        per_roi = (a - b).abs().reshape(n, -1).amax(dim=1) / scale
+        rep[k + '_rel_err'] = float(per_roi[keep].max())
+        if exclude_rois is None:
+            rep[k + '_rois_within_1e-3'] = float((per_roi < 1e-3).float().mean())
+            rep[k + '_rel_err_median_roi'] = float(per_roi.median())
+    rep['n_dets'] = [int(len(ours['dets'])), int(len(want['dets']))]
+    rep['det_match'] = match_detections(ours['dets'], ours['labels'], want['dets'], want['labels'])
+    # scores of the detections, rank by rank (robust to swaps of equal-score boxes): how far the score profile moved
+    k = min(len(ours['dets']), len(want['dets']))
+    rep['det_score_max_abs_diff'] = float((ours['dets'][:k, 4] - want['dets'][:k, 4]).abs().max()) if k else 0.0
+    return rep
+
+
 # --------------------------------------------------------------------------------------------- CPU port (oracle)
-def cpu_step(cfg, head_sd, ref_x, props_all):
+def cpu_step(cfg, head_sd, ref_x, props_all, return_all=False):
     from oracle import vod_oracle as O
     N, T = cfg['N'], cfg['T']
     rois = torch.cat([torch.zeros(N, 1), props_all[T]], 1)
@@ -285,7 +379,10 @@ def cpu_step(cfg, head_sd, ref_x, props_all):
     ref_feats = O.roi_align(ref_x, ref_rois, 7, 1 / 16, 2, True)
     hp = {k[len('bbox_head.'):]: v for k, v in head_sd.items() if k.startswith('bbox_head.')}
     cls, reg = O.selsa_bbox_head(bbox_feats, ref_feats, hp, cfg['fcs'], 16)
-    return O.get_bboxes(rois, cls, reg, IMG_SHAPE, (1., 1., 1., 1.), False, 0.0001, dict(type='nms', iou_threshold=0.5), 100)
+    dets, labels = O.get_bboxes(rois, cls, reg, IMG_SHAPE, (1., 1., 1., 1.), False, 0.0001, dict(type='nms', iou_threshold=0.5), 100)
+    if return_all:
+        return dict(bbox_feats=bbox_feats, cls_score=cls, bbox_pred=reg, dets=dets, labels=labels)
+    return dets, labels
 
 
 def cpu_head_state(cfg):

@@ -122,7 +122,9 @@ int vod_selsa_attn(const void *q, const void *k, const void *v, float *out, int 
  *   out     [T, N*P, C] fp32  (row-major; the host views it as [T,N,ph,pw,C])
  *   idx_out [N*P, T, k] int32 flat h*W+w locations, descending similarity (nullable)
  *   val_out [N*P, T, k] fp32 similarities (nullable)
- * impl: 0 auto, 1 exact fp32 SIMT scan, 2 bf16 tcgen05 candidate GEMM + exact fp32 re-score.
+ * impl: 0 auto, 1 exact fp32 SIMT scan, 2 bf16 tcgen05 candidate GEMM + exact fp32 re-score; a (row, frame) whose
+ *       candidate lists could have dropped a member of the exact top-k (more than 4 near-tied locations congruent mod 4) is
+ *       detected and re-scanned in exact fp32, so the selected locations are the exact top-k for every input.
  * replaces: TemporalRoIAlign.most_similar_roi_align,
  *   mmtracking/mmtrack/models/roi_heads/roi_extractors/temporal_roi_align.py:99-181
  */
@@ -135,6 +137,11 @@ int vod_msra_topk_sample(const float *roi_feats, const float *ref_nhwc, const fl
                          const void *ref_unit_bf16, float *out, int *idx_out, float *val_out, int NP,
                          int C, int T, int HW, int k, int impl, void *ws, size_t ws_bytes,
                          vod_stream_t stream);
+
+/* Byte offset, inside the workspace of vod_msra_topk_sample, of an int32 counter block: [0] = number of (row, frame) pairs of
+ * the last tensor-core call whose candidate lists may have lost a member of the exact top-k and were therefore re-scanned in
+ * exact fp32 (the result is exact either way; the counter is a diagnostic for tests and benchmarks). */
+size_t vod_msra_overflow_counter_offset(int NP, int C, int T, int HW);
 
 /* The tensor-core half of (4) alone (what vod_msra_topk_sample runs before its fp32 re-score): unit-norm bf16
  * rows roi_unit [NP, C] x ref_unit [T*HW, C] -> cand_out [NP, T, 16] packed keys

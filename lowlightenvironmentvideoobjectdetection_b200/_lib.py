@@ -37,6 +37,7 @@ SIGNATURES = {
     'vod_selsa_attn': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _I, _I, _I, _P, _SZ, _P]),
     'vod_msra_workspace_bytes': (_SZ, [_I, _I, _I, _I, _I]),
     'vod_msra_topk_sample': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _SZ, _P]),
+    'vod_msra_overflow_counter_offset': (_SZ, [_I, _I, _I, _I]),
     'vod_msra_gemm_candidates': (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     'vod_tafa_weighted_sum': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     'vod_tafa_keyproj_chunk': (_I, [_I, _I, _I, _I]),

@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .registry import AGGREGATORS, ConvModule
+from .registry import AGGREGATORS, ConvModule, inference_only
 
 
 @AGGREGATORS.register_module()
@@ -36,7 +36,7 @@ class SelsaAggregator(nn.Module):
         self.impl = ops.IMPL_AUTO          # test hook: force the SIMT or tcgen05 kernel
         self.compute_dtype = torch.float32  # torch.bfloat16 selects bf16 tensor-core math (stated tolerance)
 
-    @torch.no_grad()
+    @inference_only
     def forward(self, x, ref_x):
         """Aggregate the features `ref_x` of reference proposals.
 
@@ -50,34 +50,66 @@ class SelsaAggregator(nn.Module):
         roi_n, ref_roi_n = x.shape[0], ref_x.shape[0]
         in_dtype = x.dtype
         x, ref_x = x.float(), ref_x.float()
-        q = self.fc_embed(x)                                   # selsa_aggregator.py:50
-        k = self.ref_fc_embed(ref_x)                           # :55
-        d = q.shape[1] // self.num_attention_blocks
-        use_vt = (d == 64 and ref_roi_n > 0)
-        if use_vt:
-            # ref_fc (:64) emitted directly as V^T [C, M] (same GEMM, no transposition pass): the
-            # tensor-core kernel wants the reference axis contiguous for the P.V product.
-            # row stride of V^T: a multiple of 16 bytes (TMA).  fp32: 4 elements -- M = 4500 then needs no padding and the
-            # GEMM writes straight into a contiguous buffer (a strided `out=` costs a temporary + a copy pass per layer)
-            align = 8 if self.compute_dtype == torch.bfloat16 else 4
-            ldv = (ref_roi_n + align - 1) // align * align
-            vt = torch.empty((q.shape[1], ldv), dtype=torch.float32, device=x.device)
-            if ldv != ref_roi_n:
-                vt[:, ref_roi_n:].zero_()
-            # softmax rows sum to one, so the bias of ref_fc passes through the attention unchanged: P (V0 + 1 b^T) = P V0 + b.
-            # It is added to the [N, C] result below instead of being broadcast into the [C, M] operand first (which costs
-            # a full copy pass: torch materialises the broadcast bias in the output before the GEMM).
-            torch.mm(self.ref_fc.weight.float(), ref_x.t(), out=vt[:, :ref_roi_n])
-            v = vt
+        if ref_roi_n == 0:
+            # no reference proposals: the reference's softmax over an empty axis and bmm with a [.., 0, d] operand give zeros,
+            # so the result is fc(0) = the output bias in every row (selsa_aggregator.py:61-72)
+            return self.fc(x.new_zeros(roi_n, x.shape[1])).to(in_dtype)
+        k, v, use_vt = self.project_ref(ref_x)
+        return self.attend(x, k, v, ref_roi_n, use_vt).to(in_dtype)
+
+    def v_layout(self):
+        """(V is kept transposed, row alignment in elements): the tensor-core kernel wants the reference axis contiguous for
+        the P.V product, with a row stride that is a multiple of 16 bytes (TMA)."""
+        d = self.fc_embed.out_features // self.num_attention_blocks
+        return d == 64, (8 if self.compute_dtype == torch.bfloat16 else 4)
+
+    def project_ref(self, ref_x, k_out=None, vt_out=None):
+        """The reference-side projections of one aggregator layer: K = ref_fc_embed(ref_x) (selsa_aggregator.py:55) and
+        V = ref_fc(ref_x) (:64), the latter emitted directly as V^T [C, M] WITHOUT its bias when d == 64 (softmax rows sum to
+        one, so the bias passes through the attention unchanged, P (V0 + 1 b^T) = P V0 + b, and is added to the [N, C] result in
+        ``attend`` instead of being broadcast into the [C, M] operand first).  They depend on the reference proposals only,
+        which is what lets SelsaRoIHead cache them per reference frame.
+
+        ``k_out`` [M, C] / ``vt_out`` [C, M(+pad)] (views into a cache) receive the results when given.
+        Returns (k, v or V^T, v_is_transposed)."""
+        ref_x = ref_x.float()
+        M = ref_x.shape[0]
+        use_vt, align = self.v_layout()
+        use_vt = use_vt and M > 0
+        if k_out is not None:
+            torch.addmm(self.ref_fc_embed.bias, ref_x, self.ref_fc_embed.weight.t(), out=k_out)
+            k = k_out
         else:
-            v = self.ref_fc(ref_x)
+            k = self.ref_fc_embed(ref_x)                       # :55
+        if not use_vt:
+            assert vt_out is None
+            return k, self.ref_fc(ref_x), False
+        if vt_out is None:
+            # row stride of V^T: a multiple of 16 bytes.  fp32: 4 elements -- M = 4500 then needs no padding and the GEMM
+            # writes straight into a contiguous buffer (a strided `out=` costs a temporary + a copy pass per layer)
+            ldv = (M + align - 1) // align * align
+            vt = torch.empty((self.ref_fc.out_features, ldv), dtype=torch.float32, device=ref_x.device)
+            if ldv != M:
+                vt[:, M:].zero_()
+            torch.mm(self.ref_fc.weight.float(), ref_x.t(), out=vt[:, :M])
+            return k, vt, True
+        torch.mm(self.ref_fc.weight.float(), ref_x.t(), out=vt_out)
+        return k, vt_out, True
+
+    def attend(self, x, k, v, M, v_transposed):
+        """fc(softmax(fc_embed(x) K^T / sqrt(d)) V) for the first ``M`` reference rows of k / columns of V^T
+        (selsa_aggregator.py:50,57-72)."""
+        roi_n = x.shape[0]
+        q = self.fc_embed(x.float())                           # :50
+        k = k[:M]
+        if not v_transposed:
+            v = v[:M]
         if self.compute_dtype == torch.bfloat16:
             q, k, v = q.bfloat16(), k.bfloat16(), v.bfloat16()
-        o = ops.selsa_attention(q, k, v, self.num_attention_blocks, v_transposed=use_vt, impl=self.impl)  # :61-70
-        if use_vt:
+        o = ops.selsa_attention(q, k, v, self.num_attention_blocks, v_transposed=v_transposed, impl=self.impl)  # :61-70
+        if v_transposed:
             o += self.ref_fc.bias.float()
-        x_new = self.fc(o.view(roi_n, -1))                     # :72
-        return x_new.to(in_dtype)
+        return self.fc(o.view(roi_n, -1))                      # :72
 
 
 @AGGREGATORS.register_module()
@@ -112,7 +144,7 @@ class EmbedAggregator(nn.Module):
             t = embed_conv(t)
         return t
 
-    @torch.no_grad()
+    @inference_only
     def forward(self, x, ref_x):
         """Aggregate reference feature maps `ref_x`.
 

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, 'libvodagg.so')
 _OBJ_DIR = os.path.join(_HERE, '_build', 'obj')
 
 SOURCES = ['common.cu', 'nms.cu', 'roi_align.cu', 'layout.cu', 'warp.cu', 'tafa.cu', 'tafa_keyproj.cu', 'selsa.cu',
-           'selsa_tc.cu', 'msra_gemm.cu', 'gemm_test.cu', 'decode.cu']
+           'selsa_tc.cu', 'msra_gemm.cu', 'msra_overflow.cu', 'gemm_test.cu', 'decode.cu']
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']

@@ -30,7 +30,9 @@ __host__ __device__ static inline T ceil_div(T a, T b) { return (a + b - 1) / b;
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-constexpr int kNumSMs = 148;  // B200
+// SM count of the current device (cudaDevAttrMultiProcessorCount, cached per device; 148 on a B200): grids of the
+// persistent kernels are sized from it, never from a constant.
+int num_sms();
 
 // 128-bit streaming loads/stores (read-only path, do not pollute L1 for write-once data)
 __device__ __forceinline__ float4 ldg_f4(const float *p) {

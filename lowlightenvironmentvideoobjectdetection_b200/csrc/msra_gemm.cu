@@ -265,7 +265,7 @@ int msra_launch_gemm_topk(const void *roi_unit_bf16, const void *ref_unit_bf16, 
     p.units = ceil_div(p.row_tiles, 2) * T;
     p.k4096 = 4096; p.kone = 1;
     cudaFuncSetAttribute(msra_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMgSmem);
-    const int grid = 2 * min(kNumSMs / 2, p.units);   // clusters of 2 CTAs
+    const int grid = 2 * min(num_sms() / 2, p.units);   // clusters of 2 CTAs
     msra_gemm_topk_kernel<<<grid, kMgThreads, kMgSmem, st>>>(tb, p); note_launch();
     return check_launch("msra_gemm_topk");
 }
@@ -276,7 +276,7 @@ using namespace vod;
 
 namespace {
 struct MsraWs {
-    size_t roi_norm, ref_norm, roi_unit, ref_unit, cand, bytes;
+    size_t roi_norm, ref_norm, roi_unit, ref_unit, cand, ovf_ctrl, ovf_pairs, ovf_top2, ovf_bins, ovf_scan, bytes;
 };
 MsraWs msra_ws(int NP, int C, int T, int HW) {
     MsraWs w;
@@ -286,6 +286,13 @@ MsraWs msra_ws(int NP, int C, int T, int HW) {
     w.roi_unit = o; o = align_up(o + 2 * (size_t)NP * C, 1024);
     w.ref_unit = o; o = align_up(o + 2 * ((size_t)T * HW + 4) * C, 1024);   // + the padding rows the TMA box may touch
     w.cand = o;     o = align_up(o + sizeof(int) * (size_t)NP * T * kMsraCand, 256);
+    // overflow work lists of the exact-by-construction top-k (msra.cuh): sized for the worst case, every pair flagged
+    const size_t pairs = (size_t)NP * T;
+    w.ovf_ctrl = o;  o = align_up(o + sizeof(int) * (1 + 4 * (size_t)T), 256);
+    w.ovf_pairs = o; o = align_up(o + sizeof(int4) * pairs, 256);
+    w.ovf_top2 = o;  o = align_up(o + sizeof(float4) * pairs, 256);
+    w.ovf_bins = o;  o = align_up(o + sizeof(int2) * 4 * pairs, 256);
+    w.ovf_scan = o;  o = align_up(o + sizeof(float4) * 4 * pairs, 256);
     w.bytes = o;
     return w;
 }
@@ -311,7 +318,7 @@ extern "C" int vod_msra_topk_sample(const float *roi_feats, const float *ref_nhw
     uint8_t *wsb = reinterpret_cast<uint8_t *>(ws);
     // The candidate pass keeps the 4 best of four interleaved location groups: sized for the reference's k = 2 (and k = 1).
     // Larger k runs the exact scan (a true top-4 with three members in one group would leave no slack in that group).
-    const bool tc_ok = msra_gemm_supported(NP, C, T, HW) && HW >= kMsraCand && k <= 2 && vod_device_is_sm100();
+    const bool tc_ok = msra_gemm_supported(NP, C, T, HW) && HW >= kMsraCand && k <= 2 && T <= 256 && vod_device_is_sm100();
     if (impl == 2 && !tc_ok)
         return fail(VOD_E_UNSUPPORTED, "vod_msra_topk_sample: tcgen05 path needs C %% 64 == 0, C <= 512, k <= 2, sm_100");
     const bool use_tc = impl == 2 || (impl == 0 && tc_ok);
@@ -335,7 +342,27 @@ extern "C" int vod_msra_topk_sample(const float *roi_feats, const float *ref_nhw
     uint32_t *cand = reinterpret_cast<uint32_t *>(wsb + w.cand);
     rc = msra_launch_gemm_topk(roi_unit, ru, cand, NP, NP, C, T, HW, st);
     if (rc) return rc;
-    return msra_launch_rescore(roi_feats, ref_nhwc, roi_norm, rn, cand, kMsraCand, out, idx_out, val_out, NP, C, T, HW, k, st);
+    // exact-by-construction top-k: the re-score flags every (row, frame, group) whose candidate list may have lost a member of
+    // the exact top-k; msra_overflow_fix re-scans those groups in fp32 (usually none: two empty launches)
+    MsraOvf ovf;
+    ovf.ctrl = reinterpret_cast<int *>(wsb + w.ovf_ctrl);
+    ovf.pair_list = reinterpret_cast<int4 *>(wsb + w.ovf_pairs);
+    ovf.pair_top = reinterpret_cast<float4 *>(wsb + w.ovf_top2);
+    ovf.bin_list = reinterpret_cast<int2 *>(wsb + w.ovf_bins);
+    ovf.ovf_top = reinterpret_cast<float4 *>(wsb + w.ovf_scan);
+    const bool fix = 4 * T <= 1024;    // (more frames than the fix-up kernels index: T > 256 never reaches here in practice)
+    if (fix) {
+        cudaError_t e = cudaMemsetAsync(ovf.ctrl, 0, sizeof(int) * (1 + 4 * (size_t)T), st);
+        if (e != cudaSuccess) return fail(VOD_E_LAUNCH, "vod_msra_topk_sample: memset: %s", cudaGetErrorString(e));
+    }
+    rc = msra_launch_rescore(roi_feats, ref_nhwc, roi_norm, rn, cand, kMsraCand, out, idx_out, val_out, NP, C, T, HW, k,
+                             fix ? &ovf : nullptr, st);
+    if (rc || !fix) return rc;
+    return msra_overflow_fix(roi_feats, ref_nhwc, roi_norm, rn, ovf, out, idx_out, val_out, NP, C, T, HW, k, st);
+}
+
+extern "C" size_t vod_msra_overflow_counter_offset(int NP, int C, int T, int HW) {
+    return msra_ws(NP, C, T, HW).ovf_ctrl;
 }
 
 extern "C" int vod_msra_gemm_candidates(const void *roi_unit_bf16, const void *ref_unit_bf16, uint32_t *cand_out, int NP,

@@ -72,6 +72,12 @@ __device__ __forceinline__ float dec_ordered(unsigned u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
+// total order on scores: -inf < finite < +inf < NaN; +0 and -0 compare equal, as they do as floats
+__device__ __forceinline__ unsigned score_key(float f) {
+    if (f != f) return 0xFFFFFFFFu;
+    return enc_ordered(f + 0.0f);      // -0 + 0 = +0
+}
+
 // grid (i-blocks, j-splits, images), 256 threads
 constexpr int kRankThreads = 256;
 __global__ void __launch_bounds__(kRankThreads)
@@ -81,16 +87,20 @@ nms_rank_kernel(const float *__restrict__ boxes, const float *__restrict__ score
     const int beg = seg.off[img], n = seg.off[img + 1] - beg;
     const int i = blockIdx.x * kRankThreads + threadIdx.x;
     if (blockIdx.x * kRankThreads >= n) return;
-    const float si = i < n ? scores[beg + i] : 0.f;
+    // Scores are compared through an order-preserving unsigned key with NaN mapped to the largest key (torch.sort(descending)
+    // ranks NaN first): the order is total, so the ranks are a permutation for ANY input -- with float compares a NaN score
+    // compares false everywhere, every NaN box would get rank 0 and the scatter would leave sorted slots unwritten.
+    const float si_f = i < n ? scores[beg + i] : 0.f;
+    const unsigned si = score_key(si_f);
 
-    __shared__ __align__(16) float sj[kRankThreads];
+    __shared__ __align__(16) unsigned sj[kRankThreads];
     const int per = ceil_div(n, (int)gridDim.y);
     const int j0 = blockIdx.y * per, j1 = min(n, j0 + per);
     int cnt = 0;
     const int i_lo = blockIdx.x * kRankThreads, i_hi = i_lo + kRankThreads - 1;
     for (int base = j0; base < j1; base += kRankThreads) {
         int j = base + threadIdx.x;
-        sj[threadIdx.x] = j < j1 ? scores[beg + j] : -INFINITY;
+        sj[threadIdx.x] = j < j1 ? score_key(scores[beg + j]) : 0u;
         __syncthreads();
         const int lim = min(kRankThreads, j1 - base);
         // rank = #{s_j > s_i} + #{s_j == s_i, j < i}: for a tile entirely before (after) this block's rows the
@@ -98,20 +108,20 @@ nms_rank_kernel(const float *__restrict__ boxes, const float *__restrict__ score
         if (base + lim - 1 < i_lo) {
             int t = 0;
             for (; t + 4 <= lim; t += 4) {
-                const float4 s4 = *reinterpret_cast<const float4 *>(&sj[t]);
+                const uint4 s4 = *reinterpret_cast<const uint4 *>(&sj[t]);
                 cnt += (s4.x >= si) + (s4.y >= si) + (s4.z >= si) + (s4.w >= si);
             }
             for (; t < lim; ++t) cnt += sj[t] >= si;
         } else if (base > i_hi) {
             int t = 0;
             for (; t + 4 <= lim; t += 4) {
-                const float4 s4 = *reinterpret_cast<const float4 *>(&sj[t]);
+                const uint4 s4 = *reinterpret_cast<const uint4 *>(&sj[t]);
                 cnt += (s4.x > si) + (s4.y > si) + (s4.z > si) + (s4.w > si);
             }
             for (; t < lim; ++t) cnt += sj[t] > si;
         } else {
             for (int t = 0; t < lim; ++t) {
-                const float s = sj[t];
+                const unsigned s = sj[t];
                 cnt += (s > si) || (s == si && (base + t) < i);
             }
         }
@@ -121,7 +131,7 @@ nms_rank_kernel(const float *__restrict__ boxes, const float *__restrict__ score
 
     if (want_max && blockIdx.y == 0) {
         float m = -INFINITY;
-        if (i < n && !(skip_invalid && si == -INFINITY)) {   // boxes.max() is taken over the valid boxes only
+        if (i < n && !(skip_invalid && si_f == -INFINITY)) {   // boxes.max() is taken over the valid boxes only
             float4 b = reinterpret_cast<const float4 *>(boxes)[beg + i];
             m = fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w));
         }
@@ -447,7 +457,7 @@ extern "C" int vod_batched_nms_ex(const float *boxes, const float *scores, const
 
     const int iblocks = ceil_div(max_seg, kRankThreads);
     // enough j-splits to fill the machine (~4 CTAs/SM), each split at least 256 candidates
-    int jsplits = max(1, min(ceil_div(max_seg, 256), ceil_div(4 * kNumSMs, iblocks * n_images)));
+    int jsplits = max(1, min(ceil_div(max_seg, 256), ceil_div(4 * num_sms(), iblocks * n_images)));
     nms_rank_kernel<<<dim3(iblocks, jsplits, n_images), kRankThreads, 0, st>>>(
         boxes, scores, seg, w.rank, w.segmax, mode == 1 || mode == 3, n_valid_dev != nullptr); note_launch();
     nms_scatter_kernel<<<dim3(ceil_div(max_seg, 256), n_images), 256, 0, st>>>(

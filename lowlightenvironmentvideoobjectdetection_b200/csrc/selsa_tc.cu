@@ -354,7 +354,7 @@ transpose_rows_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
 static int pick_splits(int N, int M, int heads) {
     const int units = ceil_div(N, kBM) * heads;
     const int nchunks = ceil_div(M, kBN);
-    int s = max(1, kNumSMs / units);
+    int s = max(1, num_sms() / units);
     s = min(s, max(1, nchunks / 4));  // at least 4 chunks per split
     return min(s, 16);
 }

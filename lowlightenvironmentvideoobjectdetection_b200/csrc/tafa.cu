@@ -170,100 +170,6 @@ tafa_kernel(const float *__restrict__ x_all, const float *__restrict__ emb_all, 
 }
 
 // ------------------------------------------------------------------------------------ MSRA
-// Shared tail: given this warp's k best (value, location) pairs (sorted descending, warp-uniform),
-// softmax over the k values (temporal_roi_align.py:155) and weighted gather of the raw reference
-// features (temporal_roi_align.py:165-176).
-template <int KMAX>
-__device__ __forceinline__ void msra_emit(const float *__restrict__ ref_t /*[HW,C]*/, float *__restrict__ out_row,
-                                          int *__restrict__ idx_out, float *__restrict__ val_out, const float *val,
-                                          const int *loc, int k, int C, int lane) {
-    // No comparable candidate (an all-zero RoI row or reference pixel makes every similarity NaN, the
-    // reference divides by a zero norm without an epsilon): the reference's output row is NaN too.
-    if (!(loc[0] >= 0 && loc[0] != 0x7fffffff) || (k > 1 && !(loc[k - 1] >= 0 && loc[k - 1] != 0x7fffffff))) {
-        const float qnan = __int_as_float(0x7fc00000);
-        for (int c = lane; c < C; c += 32) out_row[c] = qnan;
-        if (lane < k) {
-            if (idx_out) idx_out[lane] = 0;
-            if (val_out) val_out[lane] = qnan;
-        }
-        return;
-    }
-    float w[KMAX];
-    float m = val[0], sum = 0.f;
-#pragma unroll
-    for (int q = 0; q < KMAX; ++q) if (q < k) { w[q] = expf(val[q] - m); sum += w[q]; }
-#pragma unroll
-    for (int q = 0; q < KMAX; ++q) if (q < k) w[q] = w[q] / sum;
-    if (lane < k) {
-        // pick element `lane` without dynamic register indexing
-        float v = val[0]; int l = loc[0];
-#pragma unroll
-        for (int q = 1; q < KMAX; ++q) if (lane == q) { v = val[q]; l = loc[q]; }
-        if (idx_out) idx_out[lane] = l;
-        if (val_out) val_out[lane] = v;
-    }
-    if ((C & 3) == 0) {
-        for (int c = lane * 4; c < C; c += 128) {
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int q = 0; q < KMAX; ++q) if (q < k) {
-                float4 v = ldg_f4(ref_t + (size_t)loc[q] * C + c);
-                // topk_feats * topk_weights summed over k (temporal_roi_align.py:170-172)
-                acc.x += v.x * w[q]; acc.y += v.y * w[q]; acc.z += v.z * w[q]; acc.w += v.w * w[q];
-            }
-            stg_cs_f4(out_row + c, acc);
-        }
-    } else {
-        for (int c = lane; c < C; c += 32) {
-            float acc = 0.f;
-#pragma unroll
-            for (int q = 0; q < KMAX; ++q) if (q < k) acc += __ldg(ref_t + (size_t)loc[q] * C + c) * w[q];
-            out_row[c] = acc;
-        }
-    }
-}
-
-// insert (v, l) into a descending sorted list of length KMAX (ties: smaller location first)
-template <int KMAX>
-__device__ __forceinline__ void topk_insert(float (&val)[KMAX], int (&loc)[KMAX], float v, int l) {
-#pragma unroll
-    for (int q = 0; q < KMAX; ++q) {
-        bool better = (v > val[q]) || (v == val[q] && l < loc[q]);
-        if (better) {
-            float tv = val[q]; int tl = loc[q];
-            val[q] = v; loc[q] = l; v = tv; l = tl;
-        }
-    }
-}
-
-// warp-wide merge of per-lane sorted lists into the warp's top-k (result warp-uniform)
-template <int KMAX>
-__device__ __forceinline__ void topk_warp_merge(float (&val)[KMAX], int (&loc)[KMAX], int k, int lane) {
-    float rv[KMAX]; int rl[KMAX];
-#pragma unroll
-    for (int q = 0; q < KMAX; ++q) { rv[q] = -INFINITY; rl[q] = 0x7fffffff; }
-#pragma unroll
-    for (int r = 0; r < KMAX; ++r) {
-        if (r < k) {
-            float bv = val[0]; int bl = loc[0];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                int ol = __shfl_xor_sync(0xffffffffu, bl, o);
-                if (ov > bv || (ov == bv && ol < bl)) { bv = ov; bl = ol; }
-            }
-            rv[r] = bv; rl[r] = bl;
-            if (val[0] == bv && loc[0] == bl) {  // the owning lane pops its head
-#pragma unroll
-                for (int q = 0; q + 1 < KMAX; ++q) { val[q] = val[q + 1]; loc[q] = loc[q + 1]; }
-                val[KMAX - 1] = -INFINITY; loc[KMAX - 1] = 0x7fffffff;
-            }
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < KMAX; ++q) { val[q] = rv[q]; loc[q] = rl[q]; }
-}
-
 constexpr int kScanWarps = 8;
 
 // warp = (row, t) task; lane scans locations lane, lane+32, ...; exact fp32:
@@ -297,6 +203,27 @@ msra_scan_kernel(const float *__restrict__ roi, const float *__restrict__ ref, c
                          val_out ? val_out + ((size_t)row * T + t) * k : nullptr, val, loc, k, C, lane);
 }
 
+// Appends the (row, frame) to the overflow work lists (msra.cuh): `mask` bit g = the candidate list of location group g was
+// full AND its 4th key lies within the re-score margin of the k-th best key, so a location that fell off that list could still
+// belong to the exact top-k.  Called by one lane; (v0, l0, v1, l1) is the exact top-2 of the re-scored candidates.
+__device__ __forceinline__ void msra_flag_overflow(const MsraOvf &o, int NP, int row, int t, unsigned mask, float v0, int l0,
+                                                   float v1, int l1) {
+    const int pos = atomicAdd(o.ctrl, 1);
+    o.pair_list[pos] = make_int4(row, t, (int)mask, 0);
+    o.pair_top[pos] = make_float4(v0, __int_as_float(l0), v1, __int_as_float(l1));
+    for (int g = 0; g < 4; ++g)
+        if (mask >> g & 1u) {
+            const int bin = 4 * t + g;
+            const int j = atomicAdd(o.ctrl + 1 + bin, 1);
+            o.bin_list[(size_t)bin * NP + j] = make_int2(row, pos);
+        }
+}
+
+// lanes 3, 7, 11, 15 of a ballot (the 4th key of each group's list) -> 4-bit group mask
+__device__ __forceinline__ unsigned msra_group_mask(unsigned ballot) {
+    return (ballot >> 3 & 1u) | (ballot >> 6 & 2u) | (ballot >> 9 & 4u) | (ballot >> 12 & 8u);
+}
+
 // Tail of the tensor-core path.  warp = one RoI row (all T frames): the row is normalised once; for every
 // frame the 16 packed candidate keys of msra_gemm_topk_kernel are decoded, candidates whose bf16-GEMM
 // similarity lies within kMsraMargin of the 2nd best are re-scored in exact fp32
@@ -307,7 +234,7 @@ __global__ void __launch_bounds__(kScanWarps * 32)
 msra_rescore_kernel(const float *__restrict__ roi, const float *__restrict__ ref, const float *__restrict__ roi_norm,
                     const float *__restrict__ ref_norm, const uint32_t *__restrict__ cand, int KC,
                     float *__restrict__ out, int *__restrict__ idx_out, float *__restrict__ val_out, int NP, int C,
-                    int T, int HW, int k) {
+                    int T, int HW, int k, const MsraOvf ovf) {
     extern __shared__ float s_roi[];  // [kScanWarps][C]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int row = blockIdx.x * kScanWarps + warp;
@@ -343,6 +270,8 @@ msra_rescore_kernel(const float *__restrict__ roi, const float *__restrict__ ref
         // NaN approximations (zero-norm vectors) compare false: keep them as candidates so the NaN propagates
         const bool want = key != 0u && !(approx < kth - kMsraMargin);
         unsigned todo = __ballot_sync(0xffffffffu, want);
+        // a full list (KC == 16: 4 groups x 4 keys, the 4th key in lanes 3, 7, 11, 15) whose last key is within the margin
+        const unsigned ovf_mask = (ovf.ctrl && KC == kMsraCand) ? msra_group_mask(__ballot_sync(0xffffffffu, want && (lane & 3) == 3)) : 0u;
         float val[KM]; int loc[KM];
 #pragma unroll
         for (int i = 0; i < KM; ++i) { val[i] = -INFINITY; loc[i] = 0x7fffffff; }
@@ -370,6 +299,8 @@ msra_rescore_kernel(const float *__restrict__ roi, const float *__restrict__ ref
             topk_insert<KM>(val, loc, s, l);  // identical on all lanes
         }
         if (any_nan) loc[0] = 0x7fffffff;          // msra_emit writes a NaN row
+        if (ovf_mask && !any_nan && lane == 0)       // (a NaN row stays NaN whatever a re-scan would find)
+            msra_flag_overflow(ovf, NP, row, t, ovf_mask, val[0], loc[0], KM > 1 ? val[1] : -INFINITY, KM > 1 ? loc[1] : 0x7fffffff);
         msra_emit<KM>(ref_t, out + ((size_t)t * NP + row) * C, idx_out ? idx_out + ((size_t)row * T + t) * k : nullptr,
                              val_out ? val_out + ((size_t)row * T + t) * k : nullptr, val, loc, k, C, lane);
     }
@@ -389,7 +320,7 @@ __global__ void __launch_bounds__(kRfWarps * 32)
 msra_rescore_fast_kernel(const float *__restrict__ roi, const float *__restrict__ ref, const float *__restrict__ roi_norm,
                          const float *__restrict__ ref_norm, const uint32_t *__restrict__ cand,
                          float *__restrict__ out, int *__restrict__ idx_out, float *__restrict__ val_out, int NP,
-                         int T, int HW, int k, int nchunks) {
+                         int T, int HW, int k, int nchunks, const MsraOvf ovf) {
     constexpr int C = 128 * NQ;
     const int lane = threadIdx.x & 31;
     const long task = (long)blockIdx.x * kRfWarps + (threadIdx.x >> 5);
@@ -416,7 +347,10 @@ msra_rescore_fast_kernel(const float *__restrict__ roi, const float *__restrict_
             const uint32_t rest = (lane == __ffs(holders) - 1) ? 0u : vf;
             kth = __reduce_max_sync(0xffffffffu, rest);
         }
-        unsigned todo = __ballot_sync(0xffffffffu, key != 0u && vf + kMarginQ >= kth);
+        const bool want = key != 0u && vf + kMarginQ >= kth;
+        unsigned todo = __ballot_sync(0xffffffffu, want);
+        // overflow test per location group: its list is full (4th key, lanes 3/7/11/15, non-empty) and that key is within the margin
+        const unsigned ovf_mask = ovf.ctrl ? msra_group_mask(todo & 0x8888u) : 0u;
         float v0 = -INFINITY, v1 = -INFINITY; int l0 = 0x7fffffff, l1 = 0x7fffffff;
         bool any_nan = false;
         while (todo) {
@@ -441,6 +375,7 @@ msra_rescore_fast_kernel(const float *__restrict__ roi, const float *__restrict_
         }
         float *out_row = out + ((size_t)t * NP + row) * C + lane * 4;
         const bool bad = any_nan || l0 == 0x7fffffff || (k > 1 && l1 == 0x7fffffff);
+        if (ovf_mask && !any_nan && lane == 0) msra_flag_overflow(ovf, NP, row, t, ovf_mask, v0, l0, v1, l1);
         float w0 = 1.f, w1 = 0.f;
         if (k > 1) {
             const float e1 = expf(v1 - v0), sum = 1.0f + e1;   // softmax over the k values (temporal_roi_align.py:155)
@@ -485,12 +420,15 @@ int msra_launch_scan(const float *roi, const float *ref, const float *roi_norm, 
 
 int msra_launch_rescore(const float *roi, const float *ref, const float *roi_norm, const float *ref_norm,
                         const uint32_t *cand, int KC, float *out, int *idx_out, float *val_out, int NP, int C, int T,
-                        int HW, int k, cudaStream_t st) {
+                        int HW, int k, const MsraOvf *ovf_in, cudaStream_t st) {
+    MsraOvf ovf;
+    memset(&ovf, 0, sizeof(ovf));
+    if (ovf_in) ovf = *ovf_in;
     if (k <= 2 && KC == kMsraCand && (C & 127) == 0 && C <= 512 && HW <= 4096) {
         const int nchunks = ceil_div(T, kRfFrames);
         const unsigned g = (unsigned)ceil_div((long)NP * nchunks, (long)kRfWarps);
         auto go = [&](auto kern) {
-            kern<<<g, kRfWarps * 32, 0, st>>>(roi, ref, roi_norm, ref_norm, cand, out, idx_out, val_out, NP, T, HW, k, nchunks);
+            kern<<<g, kRfWarps * 32, 0, st>>>(roi, ref, roi_norm, ref_norm, cand, out, idx_out, val_out, NP, T, HW, k, nchunks, ovf);
         };
         switch (C >> 7) {
             case 1: go(msra_rescore_fast_kernel<1>); break;
@@ -507,7 +445,7 @@ int msra_launch_rescore(const float *roi, const float *ref, const float *roi_nor
     const unsigned grid = (unsigned)ceil_div(NP, kScanWarps);
     if (smem > 40 * 1024) cudaFuncSetAttribute(msra_rescore_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     msra_rescore_kernel<2><<<grid, kScanWarps * 32, smem, st>>>(roi, ref, roi_norm, ref_norm, cand, KC, out, idx_out, val_out, NP, C,
-                                                              T, HW, k);
+                                                              T, HW, k, ovf);
     note_launch();
     return check_launch("msra_rescore");
 }

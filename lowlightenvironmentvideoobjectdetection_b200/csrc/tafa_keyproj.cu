@@ -348,12 +348,16 @@ extern "C" int vod_tafa_keyproj_logits(const float *x_all, const float *G, float
     // persistent double-buffered 8-frame tiles 432 us, one CTA per 8-frame tile (two per SM) 458 us.  32 frames: persistent
     // 16-frame tiles 723 us, one CTA per tile 893 us.  8 frames: one CTA per 8-frame tile 241 us (5.6 TB/s).
     int persist = T1 > 8, tb = T1 > 8 ? 16 : 8, warps = min(T1 > 8 ? 14 : 7, P), depth = 2, dbg = 0;
-    // tuning / probe hooks (dbg: 1 = no FMAs, 2 = no G refills after the first ring fill, 4 = no frame tile loads)
+    // Tuning / probe hooks (dbg: 1 = no FMAs, 2 = no G refills after the first ring fill, 4 = no frame tile loads) exist only
+    // in a -DVOD_PROBES build: the production library ignores the environment, so a stray variable can never switch
+    // parts of the computation off.
+#ifdef VOD_PROBES
     if (const char *e = getenv("VOD_KP_PERSIST")) persist = atoi(e) != 0;
     if (const char *e = getenv("VOD_KP_TB")) tb = atoi(e) == 16 ? 16 : 8;
     if (const char *e = getenv("VOD_KP_WARPS")) warps = max(1, min(atoi(e), min(kKpMaxWarps, P)));
     if (const char *e = getenv("VOD_KP_DEPTH")) depth = max(1, min(atoi(e), 8));
     if (const char *e = getenv("VOD_KP_DBG")) dbg = atoi(e);
+#endif
     if (persist) warps = min(warps, kKpMaxWarps - 1);      // + the producer warp
     const int tile_frames = persist ? 16 : tb;              // persistent: 2 x 8 frames (double buffer) or 1 x 16
     while (warps > 4 && kp_smem_bytes(tile_frames, P, warps, depth) > kKpSmemLimit) --warps;
@@ -375,8 +379,10 @@ extern "C" int vod_tafa_keyproj_logits(const float *x_all, const float *G, float
     auto allow = [&](auto kern) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); return kern; };
     if (persist) {
         const long total_tiles = (long)N * (C / cc) * ceil_div(T1, tb);
-        int sms = kNumSMs;
+        int sms = num_sms();
+#ifdef VOD_PROBES
         if (const char *e = getenv("VOD_KP_CTAS")) sms = max(1, atoi(e));
+#endif
         const int tiles_per_cta = (int)ceil_div(total_tiles, (long)sms);
         const int grid = (int)ceil_div(total_tiles, (long)tiles_per_cta);
         if (tb == 16)

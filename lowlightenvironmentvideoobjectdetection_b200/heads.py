@@ -8,6 +8,14 @@ the FC layers remain nn.Linear / cuBLAS).  Inference only.
 
 Parameter names follow the reference state_dict: shared_fcs.{i}, aggregator.{i}.{fc_embed,ref_fc_embed,fc,ref_fc},
 fc_cls, fc_reg, bbox_roi_extractor.embed_network.conv.
+
+Reference-frame cache.  SELSA.extract_feats keeps a per-video memory of reference feature maps that does not
+change between key frames (adaptive stride: the 14 memory frames are fixed for the whole video, only the key frame's own slot
+changes; fixed stride: a FIFO that advances every ``frame_stride`` frames -- mmtracking/mmtrack/models/vid/selsa.py:207-249), yet
+the reference re-extracts the 4500 reference RoIs (selsa_roi_head.py:88-89) and re-runs every shared FC and every K/V
+projection on them (selsa_bbox_head.py:53-58, selsa_aggregator.py:55,64) for every key frame.  ``RefFrameCache`` keeps, per
+reference frame, exactly what those calls produce -- the NHWC map with its norms and unit-norm bf16 copy (TemporalRoIAlign's
+search space) and each layer's K rows and V^T columns -- so a key-frame step only computes them for the frames that are new.
 """
 import torch
 import torch.nn as nn
@@ -68,6 +76,43 @@ class SelsaBBoxHead(nn.Module):
             x = x + self.aggregator[i](x, ref_x)   # aggregator sees the PRE-ReLU features (:56)
             ref_x = F.relu(ref_x)
             x = F.relu(x)
+        return self.fc_cls(x), self.fc_reg(x)
+
+    @torch.no_grad()
+    def forward_cached(self, rows, n_key, cache, slots, channels_last=True):
+        """SelsaBBoxHead.forward (selsa_bbox_head.py:25-84) with the reference side taken from ``cache``.
+
+        rows [n_key + F*N, in_channels*49]: the flattened RoI features of the key-frame proposals (first ``n_key`` rows; may be
+        0 when only the cache is being filled) followed by those of the F reference frames that go into ``slots`` (N each,
+        in slot order).  Each layer: one FC over all rows, the new frames' K / V^T written into their cache slots, then the key
+        rows attend over the cache's T*N reference proposals.  ``rows`` is consumed (activations are updated in place).
+        Returns (cls_score, bbox_pred) of the key rows, or None when n_key == 0."""
+        N, T = cache.N, cache.T
+        F_new = len(slots)
+        assert rows.shape[0] == n_key + F_new * N
+        runs = _slot_runs(slots)
+        y = rows
+        for i, fc in enumerate(self.shared_fcs):
+            w = self._fc0_weight(channels_last) if i == 0 else fc.weight
+            y = F.linear(y, w, fc.bias)                                   # :53-55, key and new reference rows in one GEMM
+            agg = self.aggregator[i]
+            for j0, s0, n_run in runs:                                    # :55,64 of selsa_aggregator.py, new frames only
+                r = y[n_key + j0 * N:n_key + (j0 + n_run) * N]
+                lo, hi = s0 * N, (s0 + n_run) * N
+                if cache.v_transposed:
+                    agg.project_ref(r, k_out=cache.K[i][lo:hi], vt_out=cache.V[i][:, lo:hi])
+                else:
+                    k, v, _ = agg.project_ref(r)
+                    cache.K[i][lo:hi].copy_(k)
+                    cache.V[i][lo:hi].copy_(v)
+            if n_key:
+                x = y[:n_key]
+                x += agg.attend(x, cache.K[i], cache.V[i], T * N, cache.v_transposed)   # :56, pre-ReLU features on both sides
+            if i + 1 < len(self.shared_fcs) or n_key:
+                torch.relu_(y)                                             # :57-58
+        if not n_key:
+            return None
+        x = y[:n_key]
         return self.fc_cls(x), self.fc_reg(x)
 
     @staticmethod
@@ -145,6 +190,8 @@ class SelsaRoIHead(nn.Module):
         for layer in self.bbox_roi_extractor.roi_layers:
             layer.channels_last_out = True
         self.test_cfg = test_cfg or dict(score_thr=0.0001, nms=dict(type='nms', iou_threshold=0.5), max_per_img=100)
+        self.use_ref_cache = True     # simple_test(..., ref_img_metas=...) goes through the reference-frame cache
+        self._clip_cache = None
 
     @torch.no_grad()
     def _bbox_forward(self, x, ref_x, rois, ref_rois):
@@ -184,6 +231,25 @@ class SelsaRoIHead(nn.Module):
         return self.bbox_head.get_bboxes_device(rois, res['cls_score'], res['bbox_pred'], img_shape, scale_factor,
                                                 rescale=rescale, cfg=self.test_cfg)
 
+    @staticmethod
+    def capture_callable(fn, warmup=2):
+        """Captures ``fn()`` (any of the sync-free, fixed-shape entry points of this head over static tensors) into a CUDA graph:
+        warm-up calls on a side stream first (workspaces, module loading, kernel attributes).  Returns (graph, fn's outputs)."""
+        from . import ops
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                fn()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        ops._nhwc_memo.clear()               # every layout pass must be recorded inside the graph
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            outs = fn()
+        ops._nhwc_memo.clear()
+        return graph, outs
+
     def capture_graph(self, x, ref_x, rois, ref_rois, img_shape, scale_factor, rescale=False, warmup=2):
         """Captures ``simple_test_device`` for these (static) input tensors into a CUDA graph.  The caller refills
         the same input tensors in place and calls ``graph.replay()``; outputs are the returned static tensors."""
@@ -202,9 +268,253 @@ class SelsaRoIHead(nn.Module):
         ops._nhwc_memo.clear()
         return graph, outs
 
+    # ------------------------------------------------------------------ reference-frame cache
+    def new_ref_cache(self, num_frames, num_proposals, feat_shape, device=None):
+        """A cache for clips whose reference set holds ``num_frames`` maps of ``feat_shape`` = (C, H, W) with
+        ``num_proposals`` proposals each."""
+        device = device if device is not None else next(self.parameters()).device
+        return RefFrameCache(self, num_frames, num_proposals, feat_shape, device)
+
+    def _ref_rows_into(self, cache, slots, feats, ref_rois, rows_out):
+        """Layout pass + RoIAlign of the reference frames ``feats`` [F,C,H,W] that go into ``slots``; their RoI features are
+        written into rows_out [F*N, 49*C] (channels_last rows).  ref_rois[:, 0] indexes ``feats``."""
+        ext = self.bbox_roi_extractor
+        layer = ext.roi_layers[0]
+        from . import ops
+        if cache.maps is not None:
+            runs = _slot_runs(slots)
+            for j0, s0, n_run in runs:
+                hw = cache.H * cache.W
+                ops._to_nhwc(feats[j0:j0 + n_run], out=(cache.maps[s0:s0 + n_run], cache.norm[s0 * hw:(s0 + n_run) * hw],
+                                                        cache.unit[s0 * hw:(s0 + n_run) * hw] if cache.unit is not None else None))
+            rois2 = ref_rois.clone()
+            if len(runs) == 1:
+                rois2[:, 0] += float(slots[0])            # one run of consecutive slots (sync-free: graph capturable)
+            else:
+                slot_of = torch.as_tensor(slots, dtype=ref_rois.dtype, device=ref_rois.device)
+                rois2[:, 0] = slot_of[ref_rois[:, 0].long()]
+            ops.roi_align_nhwc(cache.maps, rois2, layer.output_size, layer.spatial_scale, layer.sampling_ratio, layer.aligned,
+                               out_nhwc=True, out=rows_out)
+        else:
+            nhwc, _, _ = ops.to_nhwc(feats)
+            ops.roi_align_nhwc(nhwc.contiguous(), ref_rois, layer.output_size, layer.spatial_scale, layer.sampling_ratio,
+                               layer.aligned, out_nhwc=True, out=rows_out)
+
     @torch.no_grad()
-    def simple_test(self, x, ref_x, proposals_list, ref_proposals_list, img_metas, proposals=None, rescale=False):
+    def update_ref_cache(self, cache, slots, feats, ref_rois, keys=None):
+        """Computes everything the head needs from the reference frames ``feats`` [F,C,H,W] (their ``ref_rois`` [F*N,5],
+        column 0 = index into ``feats``) and stores it in ``slots`` of the cache: what selsa_roi_head.py:88-89 and the
+        reference side of selsa_bbox_head.py:53-58 recompute on every key frame.  Fixed shapes, no host synchronisation."""
+        if not len(slots):
+            return
+        N = cache.N
+        assert feats.shape[0] == len(slots) and ref_rois.shape[0] == len(slots) * N
+        rows = torch.empty((len(slots) * N, cache.row_len), dtype=torch.float32, device=feats.device)
+        self._ref_rows_into(cache, slots, feats, ref_rois, rows)
+        self.bbox_head.forward_cached(rows, 0, cache, slots)
+        cache.mark(slots, keys)
+
+    @torch.no_grad()
+    def simple_test_cached_device(self, x, rois, key_ref_rois, cache, key_slot, img_shape, scale_factor, rescale=False,
+                                  return_feats=False):
+        """One key frame against a filled cache; fixed shapes, no host synchronisation (CUDA-graph capturable).
+
+        x: the key frame's feature tuple ([1,C,H,W]); rois [N,5] its proposals; the key frame is itself a member of the reference
+        set (selsa.py:220-223): it occupies ``key_slot`` with the reference proposals ``key_ref_rois`` [N,5] (column 0 ignored;
+        in the reference's pipeline these equal ``rois``).  Same outputs as ``simple_test_device`` on the full reference set."""
+        from . import ops
+        ext = self.bbox_roi_extractor
+        layer = ext.roi_layers[0]
+        N = cache.N
+        assert rois.shape[0] > 0 and key_ref_rois.shape[0] == N
+        n_key = rois.shape[0]
+        feat = x[0]
+        rows = torch.empty((n_key + N, cache.row_len), dtype=torch.float32, device=feat.device)
+        zero_rois = key_ref_rois.clone()
+        zero_rois[:, 0] = 0
+        if cache.maps is not None:
+            hw = cache.H * cache.W
+            s = key_slot
+            ops._to_nhwc(feat, out=(cache.maps[s:s + 1], cache.norm[s * hw:(s + 1) * hw],
+                                    cache.unit[s * hw:(s + 1) * hw] if cache.unit is not None else None))
+            key_nhwc = cache.maps[s:s + 1]
+            ext.forward_from_layout(key_nhwc, rois, cache.maps, cache.norm, cache.unit, out=rows[:n_key])
+        else:
+            key_nhwc = ops.to_nhwc(feat)[0].contiguous()
+            ops.roi_align_nhwc(key_nhwc, rois, layer.output_size, layer.spatial_scale, layer.sampling_ratio, layer.aligned,
+                               out_nhwc=True, out=rows[:n_key])
+        ops.roi_align_nhwc(key_nhwc, zero_rois, layer.output_size, layer.spatial_scale, layer.sampling_ratio, layer.aligned,
+                           out_nhwc=True, out=rows[n_key:])
+        feats_out = rows[:n_key].clone() if return_feats else None
+        cache.mark([key_slot], None)
+        assert cache.filled(), 'reference-frame cache has unfilled slots'
+        cls_score, bbox_pred = self.bbox_head.forward_cached(rows, n_key, cache, [key_slot])
+        out = self.bbox_head.get_bboxes_device(rois, cls_score, bbox_pred, img_shape, scale_factor, rescale=rescale, cfg=self.test_cfg)
+        if return_feats:
+            return out + (dict(cls_score=cls_score, bbox_pred=bbox_pred, bbox_feats=feats_out),)
+        return out
+
+    def _simple_test_with_cache(self, x, ref_x, proposals_list, ref_proposals_list, img_metas, ref_img_metas, rescale):
+        """simple_test through the reference-frame cache: frames are identified by their img_metas, the cache is brought into the
+        order of ``ref_img_metas`` (a FIFO advance is a shift), and only frames it does not hold are computed.  Returns None
+        when the situation is outside the cache's fixed-shape contract (the caller then runs the uncached path)."""
+        ext = self.bbox_roi_extractor
+        if len(x) != 1 or len(ref_x) != 1 or len(proposals_list) != 1 or len(ext.featmap_strides) != 1:
+            return None
+        T = ref_x[0].shape[0]
+        N = ref_proposals_list[0].shape[0] if len(ref_proposals_list) else 0
+        if N == 0 or len(ref_proposals_list) != T or len(ref_img_metas) != T or proposals_list[0].shape[0] == 0 or \
+                any(p.shape[0] != N for p in ref_proposals_list):
+            return None
+        keys = [_frame_key(m) for m in ref_img_metas]
+        key_key = _frame_key(img_metas[0])
+        if len(set(keys)) != T or key_key not in keys:
+            return None
+        key_slot = keys.index(key_key)
+        C, H, W = ref_x[0].shape[1:]
+        cache = getattr(self, '_clip_cache', None)
+        if cache is None or not cache.compatible(self, T, N, (C, H, W), ref_x[0].device):
+            cache = self._clip_cache = self.new_ref_cache(T, N, (C, H, W), ref_x[0].device)
+        cache.align(keys)
+        todo = [t for t in range(T) if t != key_slot and cache.keys[t] != keys[t]]
+        if todo:
+            idx = torch.as_tensor(todo, device=ref_x[0].device)
+            rr = bbox2roi([ref_proposals_list[t] for t in todo])
+            self.update_ref_cache(cache, todo, ref_x[0].index_select(0, idx), rr, keys=[keys[t] for t in todo])
+        rois = bbox2roi(proposals_list)
+        dets, labels, count = self.simple_test_cached_device(
+            x, rois, bbox2roi([ref_proposals_list[key_slot]]), cache, key_slot, img_metas[0]['img_shape'],
+            img_metas[0]['scale_factor'], rescale=rescale)
+        cache.keys[key_slot] = key_key
+        n = int(count)
+        return [dets[:n]], [labels[:n]]
+
+    @torch.no_grad()
+    def simple_test(self, x, ref_x, proposals_list, ref_proposals_list, img_metas, proposals=None, rescale=False,
+                    ref_img_metas=None):
         """selsa_roi_head.py:115-145; returns (det_bboxes, det_labels) lists (device tensors; the
-        per-class numpy split of bbox2result is left to the caller)."""
+        per-class numpy split of bbox2result is left to the caller).
+
+        ``ref_img_metas`` (optional, what SELSA.simple_test already holds, selsa.py:309-312): identifies the reference frames so
+        that everything that depends only on a reference frame is taken from the per-clip cache instead of being recomputed."""
+        if ref_img_metas is not None and self.use_ref_cache:
+            out = self._simple_test_with_cache(x, ref_x, proposals_list, ref_proposals_list, img_metas, ref_img_metas, rescale)
+            if out is not None:
+                return out
         return self.simple_test_bboxes(x, ref_x, proposals_list, ref_proposals_list, img_metas, self.test_cfg,
                                        rescale=rescale)
+
+
+def _slot_runs(slots):
+    """[(first position in ``slots``, first slot, run length)] of maximal runs of consecutive slots."""
+    runs, j = [], 0
+    while j < len(slots):
+        n = 1
+        while j + n < len(slots) and slots[j + n] == slots[j] + n:
+            n += 1
+        runs.append((j, slots[j], n))
+        j += n
+    return runs
+
+
+def _frame_key(meta):
+    """Identity of a frame from its img_meta (mmtrack's VideoCollect keys): the file when known, else (video, frame id)."""
+    ident = meta.get('filename', None)
+    if ident is None:
+        ident = (meta.get('video_id', None), meta.get('frame_id', None))
+    return (ident, tuple(meta.get('img_shape', ())), bool(meta.get('flip', False)))
+
+
+class RefFrameCache:
+    """Per-clip cache of everything that depends only on a reference frame (see the module docstring), in the ORDER of the
+    reference set, so that every reduction over frames / reference proposals runs in the same order as in the uncached step.
+
+      maps [T,H,W,C] fp32, norm [T*H*W], unit [T*H*W, C] bf16   TemporalRoIAlign's search space (only with that extractor)
+      K[i] [T*N, D], V[i] = V^T [D, ld] (or V [T*N, D])          aggregator layer i's reference-side projections
+    A FIFO advance of the reference set (selsa.py:237-243) is ``shift``: slots move down, in place."""
+
+    def __init__(self, head, T, N, feat_shape, device):
+        from .roi_extractors import TemporalRoIAlign
+        C, H, W = feat_shape
+        ext, bh = head.bbox_roi_extractor, head.bbox_head
+        self.T, self.N, self.C, self.H, self.W = T, N, C, H, W
+        self.device = torch.device(device)
+        ph, pw = ext.roi_layers[0].output_size
+        self.row_len = C * ph * pw
+        self.keys = [None] * T
+        self._filled = [False] * T
+        self.maps = self.norm = self.unit = None
+        if isinstance(ext, TemporalRoIAlign):
+            self.maps = torch.empty((T, H, W, C), dtype=torch.float32, device=device)
+            self.norm = torch.empty((T * H * W,), dtype=torch.float32, device=device)
+            if C % 64 == 0 and C <= 512:
+                self.unit = torch.empty((T * H * W + 4, C), dtype=torch.bfloat16, device=device)[:T * H * W]
+        D = bh.shared_fcs[0].out_features
+        self.v_transposed, align = bh.aggregator[0].v_layout()
+        L = len(bh.shared_fcs)
+        self.K = [torch.empty((T * N, D), dtype=torch.float32, device=device) for _ in range(L)]
+        if self.v_transposed:
+            ld = (T * N + align - 1) // align * align
+            self.V = [torch.zeros((D, ld), dtype=torch.float32, device=device) for _ in range(L)]
+        else:
+            self.V = [torch.empty((T * N, D), dtype=torch.float32, device=device) for _ in range(L)]
+        self._tag = self._weights_tag(head)
+
+    @staticmethod
+    def _weights_tag(head):
+        return tuple((p.data_ptr(), p._version) for p in head.parameters())
+
+    def compatible(self, head, T, N, feat_shape, device):
+        return (self.T, self.N, (self.C, self.H, self.W)) == (T, N, tuple(feat_shape)) and self.device == torch.device(device) \
+            and self._tag == self._weights_tag(head)
+
+    def filled(self):
+        return all(self._filled)
+
+    def mark(self, slots, keys):
+        for j, s in enumerate(slots):
+            self._filled[s] = True
+            self.keys[s] = keys[j] if keys is not None else self.keys[s]
+
+    def reset(self):
+        self.keys = [None] * self.T
+        self._filled = [False] * self.T
+
+    def shift(self, s):
+        """Slots s..T-1 move to 0..T-1-s (the oldest ``s`` frames leave); the last ``s`` slots become unfilled."""
+        if s <= 0:
+            return
+        T, N = self.T, self.N
+        if s < T:
+            hw = self.H * self.W
+
+            def move(buf, unit, dim=0):
+                src = buf.narrow(dim, s * unit, (T - s) * unit).clone()
+                buf.narrow(dim, 0, (T - s) * unit).copy_(src)
+            if self.maps is not None:
+                move(self.maps, 1)
+                move(self.norm, hw)
+                if self.unit is not None:
+                    move(self.unit, hw)
+            for i in range(len(self.K)):
+                move(self.K[i], N)
+                move(self.V[i], N, dim=1 if self.v_transposed else 0)
+        self.keys = self.keys[s:] + [None] * min(s, T)
+        self._filled = self._filled[s:] + [False] * min(s, T)
+        self.keys, self._filled = self.keys[:T], self._filled[:T]
+
+    def align(self, keys):
+        """Brings the cache into the order of ``keys``: the shift that preserves the most frames (0 = none); slots whose frame
+        is not the wanted one are left for the caller to recompute."""
+        best, best_s = -1, 0
+        for s in range(self.T + 1):
+            hits = sum(1 for t in range(self.T - s) if self.keys[t + s] is not None and self.keys[t + s] == keys[t])
+            if hits > best:
+                best, best_s = hits, s
+        if best <= 0:
+            self.reset()
+            return
+        self.shift(best_s)
+        for t in range(self.T):
+            if self.keys[t] != keys[t]:
+                self._filled[t] = False

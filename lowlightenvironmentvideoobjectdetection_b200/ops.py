@@ -50,14 +50,30 @@ def to_nhwc(x, want_norm=False, want_unit_bf16=False):
     return res
 
 
-def _to_nhwc(x, want_norm=False, want_unit_bf16=False):
+def _to_nhwc(x, want_norm=False, want_unit_bf16=False, out=None):
     """[B,C,H,W] fp32 -> ([B,H,W,C] fp32 contiguous, norm [B*H*W] | None, unit bf16 [B*H*W, C] | None).
 
-    A channels_last input is consumed in place (zero copy) unless norms are requested."""
+    A channels_last input is consumed in place (zero copy) unless norms are requested.
+    ``out`` = (nhwc, norm, unit) preallocated contiguous destinations (e.g. the slots of a reference-frame cache); the unit
+    buffer must stay readable for 3 rows past its end when H*W % 4 != 0 (include/vodagg.h)."""
     _lib.require_cuda(x)
     assert x.dim() == 4
     x = x.float() if x.dtype != torch.float32 else x
     B, C, H, W = x.shape
+    if out is not None:
+        nhwc, norm, unit = out
+        assert nhwc.is_contiguous() and nhwc.numel() == x.numel() and nhwc.dtype == torch.float32
+        assert norm is None or (norm.is_contiguous() and norm.numel() == B * H * W)
+        assert unit is None or (unit.is_contiguous() and unit.numel() == B * H * W * C and unit.dtype == torch.bfloat16)
+        if B * H * W:
+            if x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous():
+                nhwc.view(B, H, W, C).copy_(x.permute(0, 2, 3, 1))
+                _lib.call('vod_rows_l2norm', _lib.ptr(nhwc), _lib.ptr(norm), _lib.ptr(unit), B * H * W, C,
+                          _lib.stream_ptr(x.device))
+            else:
+                _lib.call('vod_nchw_to_nhwc', _lib.ptr(x.contiguous()), _lib.ptr(nhwc), _lib.ptr(norm), _lib.ptr(unit), B, C, H, W,
+                          _lib.stream_ptr(x.device))
+        return nhwc.view(B, H, W, C), norm, unit
     if not (want_norm or want_unit_bf16) and x.is_contiguous(memory_format=torch.channels_last) and B * C * H * W > 0:
         return x.permute(0, 2, 3, 1), None, None
     nhwc = torch.empty((B, H, W, C), dtype=torch.float32, device=x.device)
@@ -398,6 +414,16 @@ def msra_topk_sample(roi_rows, ref_nhwc, k=2, ref_norm=None, ref_unit=None, impl
     return out
 
 
+def msra_overflow_count(NP, C, T, HW, device):
+    """Diagnostic: number of (row, frame) pairs of the LAST tensor-core ``msra_topk_sample`` call of these dimensions (on the
+    current stream) whose candidate lists might have lost a member of the exact top-k and were re-scanned in exact fp32.
+    Reads the counter the library keeps in the caller's workspace (one host sync)."""
+    lib = _lib.load()
+    ws = _ws.get(lib.vod_msra_workspace_bytes(NP, C, T, HW, 2), torch.device(device))
+    off = int(lib.vod_msra_overflow_counter_offset(NP, C, T, HW))
+    return int(ws[off:off + 4].view(torch.int32).item())
+
+
 def msra_gemm_candidates(roi_unit, ref_unit, T):
     """bf16 unit rows roi_unit [NP, C], ref_unit [T*HW, C] -> packed candidate keys [NP, T, 16]
     (uint32 bit patterns in an int32 tensor; location = key & 0xFFF, 0 = empty slot)."""
@@ -413,7 +439,14 @@ def msra_gemm_candidates(roi_unit, ref_unit, T):
     return cand
 
 
-def tafa_weighted_sum(x_all, emb_all, num_heads, out_nhwc=False, emb_bias=None):
+def _tafa_out(out, N, P, C, out_nhwc, device):
+    if out is None:
+        return torch.empty((N, P, C) if out_nhwc else (N, C, P), dtype=torch.float32, device=device)
+    assert out.is_contiguous() and out.dtype == torch.float32 and out.numel() == N * P * C
+    return out
+
+
+def tafa_weighted_sum(x_all, emb_all, num_heads, out_nhwc=False, emb_bias=None, out=None):
     """x_all, emb_all [T1, N, P, C] fp32 -> [N, C, P] (or [N, P, C]).  ``emb_bias`` [C] is added to the
     embeddings on load (lets the embed conv run bias-free)."""
     _lib.require_cuda(x_all, emb_all, emb_bias)
@@ -423,7 +456,7 @@ def tafa_weighted_sum(x_all, emb_all, num_heads, out_nhwc=False, emb_bias=None):
     T1, N, P, C = x_all.shape
     if emb_all is not None:
         assert emb_all.is_contiguous() and emb_all.shape == x_all.shape and emb_all.dtype == torch.float32
-    out = torch.empty((N, P, C) if out_nhwc else (N, C, P), dtype=torch.float32, device=x_all.device)
+    out = _tafa_out(out, N, P, C, out_nhwc, x_all.device)
     if N:
         _lib.call('vod_tafa_weighted_sum', _lib.ptr(x_all), _lib.ptr(emb_all), _lib.ptr(emb_bias), _lib.ptr(out), T1, N, P, C,
                   int(num_heads), int(bool(out_nhwc)), _lib.stream_ptr(x_all.device))
@@ -450,13 +483,13 @@ def tafa_keyproj_logits(x_all, G, output_size, num_heads, cc):
     return parts
 
 
-def tafa_weighted_sum_logits(x_all, parts, num_heads, out_nhwc=False):
+def tafa_weighted_sum_logits(x_all, parts, num_heads, out_nhwc=False, out=None):
     """x_all [T1, N, P, C], partial logits [nparts, N, P, heads, T1] -> [N, C, P] (or [N, P, C])."""
     _lib.require_cuda(x_all, parts)
     assert x_all.is_contiguous() and x_all.dtype == torch.float32
     T1, N, P, C = x_all.shape
     assert parts.is_contiguous() and parts.dtype == torch.float32 and parts.shape[1:] == (N, P, num_heads, T1)
-    out = torch.empty((N, P, C) if out_nhwc else (N, C, P), dtype=torch.float32, device=x_all.device)
+    out = _tafa_out(out, N, P, C, out_nhwc, x_all.device)
     if N:
         _lib.call('vod_tafa_weighted_sum_logits', _lib.ptr(x_all), _lib.ptr(parts), int(parts.shape[0]), _lib.ptr(out),
                   T1, N, P, C, int(num_heads), int(bool(out_nhwc)), _lib.stream_ptr(x_all.device))

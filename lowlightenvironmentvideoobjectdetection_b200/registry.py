@@ -163,23 +163,70 @@ def force_fp32(apply_to=None, out_fp16=False):
     return deco
 
 
-def register_into_openmmlab():
+def register_into_openmmlab(strict=False):
     """If the real mmtrack / mmdet packages are importable, register the B200 modules into their
-    registries (same names, force=True) and return the list of registries touched."""
-    touched = []
+    registries (same names, force=True).
+
+    Returns ``(touched, failed)``: the registries that now hold the B200 modules, and a dict
+    ``registry name -> reason`` for every registry that does not (package absent -> ``'not installed'``; anything else is
+    the exception's text, and is also logged as a warning -- a caller can tell that the reference modules are still in
+    use).  ``strict=True`` raises on any failure other than the package being absent.
+
+    The B200 modules are inference-only (no backward): their ``forward`` raises while autograd is recording in training
+    mode instead of silently returning tensors without a graph."""
+    import warnings
+    touched, failed = [], {}
     from . import aggregators, roi_extractors
-    try:
-        from mmtrack.models.builder import AGGREGATORS as MM_AGG
-        MM_AGG.register_module(name='SelsaAggregator', force=True, module=aggregators.SelsaAggregator)
-        MM_AGG.register_module(name='EmbedAggregator', force=True, module=aggregators.EmbedAggregator)
-        touched.append('mmtrack.AGGREGATORS')
-    except Exception:
-        pass
-    try:
-        from mmdet.models.builder import ROI_EXTRACTORS as MM_ROI
-        MM_ROI.register_module(name='SingleRoIExtractor', force=True, module=roi_extractors.SingleRoIExtractor)
-        MM_ROI.register_module(name='TemporalRoIAlign', force=True, module=roi_extractors.TemporalRoIAlign)
-        touched.append('mmdet.ROI_EXTRACTORS')
-    except Exception:
-        pass
-    return touched
+
+    def attempt(name, importer, entries):
+        try:
+            reg = importer()
+        except ImportError:
+            failed[name] = 'not installed'
+            return
+        try:
+            for mod_name, mod in entries:
+                reg.register_module(name=mod_name, force=True, module=mod)
+            touched.append(name)
+        except Exception as e:   # registration itself failed: report, do not hide
+            failed[name] = '%s: %s' % (type(e).__name__, e)
+            warnings.warn('vodagg: could not register into %s (%s); the reference modules stay in use' % (name, failed[name]))
+            if strict:
+                raise
+
+    def mm_agg():
+        from mmtrack.models.builder import AGGREGATORS as reg
+        return reg
+
+    def mm_roi():
+        from mmdet.models.builder import ROI_EXTRACTORS as reg
+        return reg
+
+    attempt('mmtrack.AGGREGATORS', mm_agg, [('SelsaAggregator', aggregators.SelsaAggregator),
+                                             ('EmbedAggregator', aggregators.EmbedAggregator)])
+    attempt('mmdet.ROI_EXTRACTORS', mm_roi, [('SingleRoIExtractor', roi_extractors.SingleRoIExtractor),
+                                             ('TemporalRoIAlign', roi_extractors.TemporalRoIAlign)])
+    return touched, failed
+
+
+def inference_only(fn):
+    """Decorator for the ``forward`` of the B200 drop-ins: the kernels have no backward, so a call that the reference
+    would have differentiated through (module in training mode, autograd recording, an input that requires grad -- i.e. a
+    real training step, where the inputs come from the backbone) raises instead of silently cutting the graph.  Everything
+    else runs under ``torch.no_grad()``."""
+
+    def needs_grad(v):
+        if torch.is_tensor(v):
+            return v.requires_grad
+        if isinstance(v, (list, tuple)):
+            return any(needs_grad(u) for u in v)
+        return False
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        if self.training and torch.is_grad_enabled() and (needs_grad(args) or needs_grad(tuple(kwargs.values()))):
+            raise RuntimeError('%s (vodagg B200 drop-in) is inference-only: call model.eval() or run under torch.no_grad(); '
+                               'a training run must keep the reference module' % type(self).__name__)
+        with torch.no_grad():
+            return fn(self, *args, **kwargs)
+    return wrapper

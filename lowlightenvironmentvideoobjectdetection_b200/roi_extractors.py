@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .registry import ROI_EXTRACTORS, ConvModule, force_fp32
+from .registry import ROI_EXTRACTORS, ConvModule, force_fp32, inference_only
 
 
 class BaseRoIExtractor(nn.Module):
@@ -102,7 +102,7 @@ class SingleRoIExtractor(BaseRoIExtractor):
         return roi_feats
 
     @force_fp32(apply_to=('feats', ), out_fp16=True)
-    @torch.no_grad()
+    @inference_only
     def forward(self, feats, rois, roi_scale_factor=None, **kwargs):
         """Forward function (``**kwargs`` swallows ``ref_feats=`` as the mmtrack override does)."""
         return self._extract(feats, rois, roi_scale_factor)
@@ -147,22 +147,38 @@ class TemporalRoIAlign(SingleRoIExtractor):
 
     def _stack_key_and_refs(self, feat, rois, ref_feat, return_indices=False):
         """RoIAlign(key) + most-similar RoI features, stacked as x_all [T+1, N, P, C] (NHWC rows)."""
-        layer = self.roi_layers[0]
-        ph, pw = layer.output_size
-        N = rois.shape[0]
-        T, C = ref_feat.shape[0], ref_feat.shape[1]
+        C = ref_feat.shape[1]
         key_nhwc, _, _ = ops.to_nhwc(feat)
         want_tc = ref_feat.is_cuda and C % 64 == 0 and C <= 512 and self.impl != ops.IMPL_SIMT
         ref_nhwc, ref_norm, ref_unit = ops.to_nhwc(ref_feat, want_norm=True, want_unit_bf16=want_tc)
-        x_all = torch.empty((T + 1, N, ph * pw, C), dtype=torch.float32, device=feat.device)
+        return self._stack_from_layout(key_nhwc.contiguous(), rois, ref_nhwc.contiguous(), ref_norm, ref_unit, return_indices)
+
+    def _stack_from_layout(self, key_nhwc, rois, ref_nhwc, ref_norm, ref_unit, return_indices=False):
+        """Same, from maps that are already laid out: key_nhwc [1,H,W,C], ref_nhwc [T,H,W,C] fp32 contiguous, ref_norm [T*H*W],
+        ref_unit [T*H*W, C] bf16 (or None) -- the form a reference-frame cache holds (heads.RefFrameCache)."""
+        layer = self.roi_layers[0]
+        ph, pw = layer.output_size
+        N = rois.shape[0]
+        T, C = ref_nhwc.shape[0], ref_nhwc.shape[3]
+        x_all = torch.empty((T + 1, N, ph * pw, C), dtype=torch.float32, device=key_nhwc.device)
         # temporal_roi_align.py:186 -- key RoI features, emitted as [N, 49, C] rows into slot 0
-        ops.roi_align_nhwc(key_nhwc.contiguous(), rois, (ph, pw), layer.spatial_scale, layer.sampling_ratio,
+        ops.roi_align_nhwc(key_nhwc, rois, (ph, pw), layer.spatial_scale, layer.sampling_ratio,
                            layer.aligned, out_nhwc=True, out=x_all[0])
         # temporal_roi_align.py:99-181
-        res = ops.msra_topk_sample(x_all[0].view(N * ph * pw, C), ref_nhwc.contiguous(),
+        res = ops.msra_topk_sample(x_all[0].view(N * ph * pw, C), ref_nhwc,
                                    k=self.num_most_similar_points, ref_norm=ref_norm, ref_unit=ref_unit,
                                    impl=self.impl, return_indices=return_indices, out=x_all[1:])
         return (x_all, res[1], res[2]) if return_indices else x_all
+
+    def forward_from_layout(self, key_nhwc, rois, ref_nhwc, ref_norm, ref_unit, out=None):
+        """``forward(feats, rois, ref_feats=...)`` for maps already held in NHWC with their norms / unit-norm bf16 copy
+        (reference-frame cache): skips the per-call layout pass over the T reference maps.  ``out``: optional preallocated
+        destination of N*49*C floats (the layout follows ``roi_layers[0].channels_last_out``)."""
+        out_size = self.roi_layers[0].output_size
+        if len(rois) == 0:
+            return key_nhwc.new_zeros(0, self.out_channels, *out_size)
+        x_all = self._stack_from_layout(key_nhwc, rois, ref_nhwc, ref_norm, ref_unit)
+        return self._tafa(x_all, out_size[0], out_size[1], out=out)
 
     @torch.no_grad()
     def most_similar_roi_align(self, roi_feats, ref_feats):
@@ -212,7 +228,7 @@ class TemporalRoIAlign(SingleRoIExtractor):
             return 0
         return ops.tafa_keyproj_chunk(T1, P, C, heads)
 
-    def _tafa(self, x_all, rh, rw):
+    def _tafa(self, x_all, rh, rw, out=None):
         T1, N, P, C = x_all.shape
         cl_out = self.roi_layers[0].channels_last_out
         heads = self.num_temporal_attention_blocks
@@ -228,7 +244,7 @@ class TemporalRoIAlign(SingleRoIExtractor):
                 ek = ek.permute(0, 2, 3, 1).contiguous().view(N * P, heads, C // heads)   # no copy (channels_last)
                 G = torch.bmm(ek.transpose(0, 1), self._keyproj_weight(conv, heads, cc))  # [heads, N*P, 9*C]
                 parts = ops.tafa_keyproj_logits(x_all, G, (rh, rw), heads, cc)
-                out = ops.tafa_weighted_sum_logits(x_all, parts, heads, out_nhwc=cl_out)
+                out = ops.tafa_weighted_sum_logits(x_all, parts, heads, out_nhwc=cl_out, out=out)
             else:
                 # embed conv on the channels_last view: logical [(T+1)*N, C, 7, 7], memory [(T+1)*N, 7, 7, C]
                 patches = x_all.view(T1 * N, rh, rw, C).permute(0, 3, 1, 2)
@@ -237,15 +253,15 @@ class TemporalRoIAlign(SingleRoIExtractor):
                 emb = torch.nn.functional.conv2d(patches, self._conv_weight_cl(conv), None, conv.stride, conv.padding,
                                                  conv.dilation, conv.groups)
                 emb = emb.permute(0, 2, 3, 1).contiguous().view(T1, N, P, C)  # no copy: cuDNN keeps channels_last
-                out = ops.tafa_weighted_sum(x_all, emb, heads, emb_bias=conv.bias, out_nhwc=cl_out)
+                out = ops.tafa_weighted_sum(x_all, emb, heads, emb_bias=conv.bias, out_nhwc=cl_out, out=out)
         else:
-            out = ops.tafa_weighted_sum(x_all, None, 0, out_nhwc=cl_out)   # plain mean, :203-206
+            out = ops.tafa_weighted_sum(x_all, None, 0, out_nhwc=cl_out, out=out)   # plain mean, :203-206
         if cl_out:
             return out.view(N, rh, rw, C).permute(0, 3, 1, 2)              # logical [N,C,7,7], channels_last strides
         return out.view(N, C, rh, rw)
 
     @force_fp32(apply_to=('feats', 'ref_feats'), out_fp16=True)
-    @torch.no_grad()
+    @inference_only
     def forward(self, feats, rois, roi_scale_factor=None, ref_feats=None):
         """Forward function."""
         if ref_feats is None:

@@ -1,11 +1,13 @@
-"""oracle/ref_shim.py -- TEST INFRASTRUCTURE ONLY (build container only).
+"""oracle/ref_shim.py -- TEST INFRASTRUCTURE ONLY.
 
-Loads the reference's own hot-path Python files UNMODIFIED from
-``/root/reference`` under small stand-ins for the absent mmcv / mmdet packages
+Loads the reference's own hot-path Python files UNMODIFIED -- from
+``/root/reference`` in the build container, from the byte-identical staged copy
+``oracle/_ref/`` (``oracle/make_ref.py``; git-ignored, travels with gpurun) on the
+GPU box -- under small stand-ins for the absent mmcv / mmdet packages
 (SURVEY.md Appendix C).  Used to (i) validate the restatement in
-``oracle/vod_oracle.py`` and (ii) generate the golden vectors committed under
-``tests/golden/`` (``tests/golden/make_golden.py``).  ``/root/reference`` does
-not exist on the GPU box: nothing that runs there imports this module.
+``oracle/vod_oracle.py``, (ii) generate the golden vectors committed under
+``tests/golden/`` (``tests/golden/make_golden.py``) and (iii) run the reference's
+own step as the benchmark comparator (``oracle/ref_step.py``).
 
 Stand-ins (the only arithmetic they carry is the un-vendored mmcv-full ops):
   mmcv.ops.RoIAlign        -> torchvision.ops.roi_align(aligned=True)   (Appendix A.1)
@@ -22,7 +24,15 @@ import types
 import torch
 import torch.nn as nn
 
-REF_ROOT = os.environ.get('VOD_REFERENCE_ROOT', '/root/reference')
+def _default_root():
+    if 'VOD_REFERENCE_ROOT' in os.environ:
+        return os.environ['VOD_REFERENCE_ROOT']
+    if os.path.isdir('/root/reference/mmtracking/mmtrack'):
+        return '/root/reference'
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')
+
+
+REF_ROOT = _default_root()
 _LOADED = None
 
 

@@ -23,6 +23,14 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+@pytest.fixture(autouse=True)
+def _restore_library_math_flags():
+    """Tests switch torch's global tf32 flags (cuBLAS / cuDNN library math around the path); none may leak into the next."""
+    prev = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    yield
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+
+
 @pytest.fixture(scope='session')
 def golden():
     """Fixtures generated from the reference's own unmodified files (tests/golden/make_golden.py)."""

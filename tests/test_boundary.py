@@ -190,3 +190,121 @@ def test_keyproj_shape_gate_is_host_only():
     assert ops.tafa_keyproj_chunk(16, 49, 48, 4) == 0            # channels not a multiple of the 32-channel chunk
     assert ops.tafa_keyproj_chunk(16, 16 * 16, 512, 4) == 0      # 16x16 bins: the frame tile exceeds shared memory
     assert ops.tafa_keyproj_chunk(0, 49, 512, 4) == 0
+
+
+# ------------------------------------------------------------------------------------------ round 2
+def test_register_into_openmmlab_reports_what_failed(monkeypatch):
+    """registration failures must not be swallowed.  Absent packages are reported as such; a registry that raises
+    is reported with the exception text (and raised under strict=True)."""
+    import types
+    import warnings
+    touched, failed = vod.register_into_openmmlab()
+    assert touched == [] and failed == {'mmtrack.AGGREGATORS': 'not installed', 'mmdet.ROI_EXTRACTORS': 'not installed'}
+
+    class BadRegistry:
+        def register_module(self, name=None, force=False, module=None):
+            raise TypeError('boom')
+
+    class GoodRegistry:
+        def __init__(self):
+            self.got = {}
+
+        def register_module(self, name=None, force=False, module=None):
+            assert force
+            self.got[name] = module
+
+    good = GoodRegistry()
+    for name in ('mmtrack', 'mmtrack.models'):
+        monkeypatch.setitem(sys.modules, name, types.ModuleType(name))
+    monkeypatch.setitem(sys.modules, 'mmtrack.models.builder', types.SimpleNamespace(AGGREGATORS=BadRegistry()))
+    for name in ('mmdet', 'mmdet.models'):
+        monkeypatch.setitem(sys.modules, name, types.ModuleType(name))
+    monkeypatch.setitem(sys.modules, 'mmdet.models.builder', types.SimpleNamespace(ROI_EXTRACTORS=good))
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter('always')
+        touched, failed = vod.register_into_openmmlab()
+    assert touched == ['mmdet.ROI_EXTRACTORS'] and set(good.got) == {'SingleRoIExtractor', 'TemporalRoIAlign'}
+    assert failed == {'mmtrack.AGGREGATORS': 'TypeError: boom'} and any('boom' in str(x.message) for x in w)
+    with pytest.raises(TypeError):
+        vod.register_into_openmmlab(strict=True)
+
+
+def test_drop_ins_refuse_to_cut_a_training_graph():
+    """The kernels have no backward: a forward the reference would differentiate through (training mode, autograd on, an input
+    that requires grad) raises instead of silently returning a graph-less tensor; eval / no_grad / plain inputs go through
+    (here: down to the 'no CPU fallback' error)."""
+    agg = vod.SelsaAggregator(16, 4)
+    x = torch.randn(2, 16, requires_grad=True)
+    with pytest.raises(RuntimeError, match='inference-only'):
+        agg(x, torch.randn(4, 16))
+    with pytest.raises(_lib.VodError):
+        agg.eval()(x, torch.randn(4, 16))
+    agg.train()
+    with torch.no_grad(), pytest.raises(_lib.VodError):
+        agg(x, torch.randn(4, 16))
+    t = vod.build_roi_extractor(dict(type='SingleRoIExtractor', roi_layer=dict(type='RoIAlign', output_size=7, sampling_ratio=2),
+                                     out_channels=4, featmap_strides=[16]))
+    with pytest.raises(RuntimeError, match='inference-only'):
+        t((torch.randn(1, 4, 8, 8, requires_grad=True),), torch.tensor([[0, 0., 0., 32., 32.]]))
+
+
+def test_selsa_aggregator_without_reference_proposals():
+    """ref_x with zero rows: the reference's softmax over an empty axis and bmm with an empty operand give zeros, i.e. fc(0)
+    (selsa_aggregator.py:61-72); the drop-in returns the same instead of failing on a null pointer."""
+    agg = vod.SelsaAggregator(16, 4)
+    out = agg(torch.randn(3, 16), torch.zeros(0, 16))
+    assert out.shape == (3, 16) and torch.allclose(out, agg.fc.bias.detach().expand(3, 16))
+
+
+def test_production_library_ignores_probe_environment():
+    """the probe hooks of the key-projected logits kernel (VOD_KP_DBG ...) exist only in a -DVOD_PROBES build."""
+    src = open(os.path.join(ROOT, 'lowlightenvironmentvideoobjectdetection_b200', 'csrc', 'tafa_keyproj.cu')).read()
+    body = re.sub(r'#ifdef VOD_PROBES.*?#endif', '', src, flags=re.S)
+    assert 'getenv' not in body
+    from lowlightenvironmentvideoobjectdetection_b200 import build
+    assert not any('VOD_PROBES' in f for f in build.NVCC_FLAGS)
+    blob = open(_lib.LIB_PATH, 'rb').read()
+    assert b'VOD_KP_DBG' not in blob
+
+
+def test_ref_frame_cache_bookkeeping_cpu():
+    """Host logic of the reference-frame cache (heads.RefFrameCache): a FIFO advance is found as the shift that preserves the
+    most frames, the buffers move with it (in reference order, so reductions keep their order), and only frames the cache does
+    not hold are left to recompute.  No kernel runs here."""
+    from lowlightenvironmentvideoobjectdetection_b200.heads import RefFrameCache, _frame_key, _slot_runs
+    head = vod.SelsaRoIHead(
+        bbox_roi_extractor=dict(type='TemporalRoIAlign', roi_layer=dict(type='RoIAlign', output_size=7, sampling_ratio=2),
+                                out_channels=64, featmap_strides=[16]),
+        bbox_head=dict(type='SelsaBBoxHead', num_shared_fcs=2, in_channels=64, fc_out_channels=128, num_classes=3,
+                       aggregator=dict(type='SelsaAggregator', in_channels=128, num_attention_blocks=2)))
+    T, N = 5, 4
+    c = head.new_ref_cache(T, N, (64, 3, 4), 'cpu')
+    assert c.maps.shape == (T, 3, 4, 64) and c.unit.shape == (T * 12, 64) and c.v_transposed and c.V[0].shape == (128, T * N)
+    assert not c.filled()
+    for t in range(T):                       # recognisable contents: slot t holds the value t
+        c.maps[t] = t; c.norm[t * 12:(t + 1) * 12] = t; c.unit[t * 12:(t + 1) * 12] = t
+        for i in range(2):
+            c.K[i][t * N:(t + 1) * N] = t; c.V[i][:, t * N:(t + 1) * N] = t
+    keys = [_frame_key(dict(video_id=1, frame_id=f, img_shape=(48, 64, 3))) for f in range(10)]
+    c.mark(list(range(T)), keys[0:T])
+    assert c.filled()
+    c.align(keys[0:T])                       # same reference set: nothing to do
+    assert c.filled() and c.keys == keys[0:T]
+    c.align(keys[2:T + 2])                   # the set advanced by two frames
+    assert c.keys[:3] == keys[2:5] and c._filled == [True, True, True, False, False]
+    for t in range(3):
+        assert float(c.maps[t].min()) == float(c.maps[t].max()) == t + 2
+        assert float(c.norm[t * 12]) == t + 2 and float(c.unit[t * 12, 0]) == t + 2
+        assert float(c.K[1][t * N, 0]) == t + 2 and float(c.V[0][5, t * N + 1]) == t + 2
+    c.mark([3, 4], keys[5:7])
+    want = list(keys[2:T + 2]); want[1] = keys[9]        # one slot replaced in place (the key frame's slot)
+    c.align(want)
+    assert c._filled == [True, False, True, True, True]
+    c.align(keys[7:10] + keys[0:2])          # an unrelated set: everything is recomputed
+    assert not any(c._filled)
+    assert _slot_runs([3, 4, 0, 1, 2, 9]) == [(0, 3, 2), (2, 0, 3), (5, 9, 1)]
+    # a cache is tied to the weights it was computed with
+    assert c.compatible(head, T, N, (64, 3, 4), 'cpu')
+    with torch.no_grad():
+        head.bbox_head.shared_fcs[0].weight.mul_(2.0)
+    assert not c.compatible(head, T, N, (64, 3, 4), 'cpu')

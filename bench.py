@@ -1,25 +1,33 @@
 #!/usr/bin/env python
-"""bench.py -- VID frames/s through the SELSA + TemporalRoIAlign aggregation path (BASELINE.json metric).
+"""bench.py -- VID frames/s through the multi-frame feature-aggregation hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg3|cfg1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg3|cfg1|cfg2|cfg4|sweep]
 
-A "step" = one key frame through SelsaRoIHead.simple_test at the shapes of configs[2]
-("SELSA + TemporalRoIAlign R-50-DC5, 14 ref frames, 300 proposals/frame"): TemporalRoIAlign(key) over
-T=15 reference maps, RoIAlign of the 4500 reference RoIs, the 3 shared FCs each followed by a
-SelsaAggregator, get_bboxes and multiclass NMS.  Inputs are synthetic: relu(N(0,1))
-stride-16 feature maps [*,512,38,63] of a 600x1000 frame, RPN-like proposals, random-init weights.
+Default (cfg3, the configuration the metric is quoted on): a "step" = one key frame through SelsaRoIHead at the shapes of
+configs[2] ("SELSA + TemporalRoIAlign R-50-DC5, 14 ref frames, 300 proposals/frame"): TemporalRoIAlign(key) over T=15
+reference maps, RoIAlign of the 4500 reference RoIs, the 3 shared FCs each followed by a SelsaAggregator, get_bboxes and
+multiclass NMS.  Inputs are synthetic: relu(N(0,1)) stride-16 feature maps [*,512,38,63] of a 600x1000 frame,
+RPN-like proposals, random-init weights.
 
-value   whole-job frames/s with the inputs resident in HBM (device time, CUDA events, max over ranks)
-e2e     the same through the public API with HOST (pinned) inputs: H2D of the step's feature maps and
-        proposals and D2H of the detections inside the timed region
-roofline  the dominant hand-written kernel timed alone with CUDA events (L2 flushed between launches),
-        algorithmic FLOPs/bytes from BASELINE.md section 3 over that time vs MEASURED_PEAKS.json
-cpu_baseline  the CPU oracle (port of the reference's Python path) on the host cores, one key frame
---impl reference  times that CPU port on all host threads (the reference is Python + un-vendored mmcv:
-        nothing compiles into oracle/_ref), rank 0 only.
+value     whole-job frames/s of the UNCACHED step (every reference frame recomputed, as the reference does) with the inputs
+          resident in HBM (device time, CUDA events, max over ranks); library GEMMs/convs around the path in tf32
+e2e       the same through the public API with HOST (pinned) inputs: H2D of the step's maps/proposals, D2H of the detections
+fp32_library_math   the same step with cuBLAS/cuDNN in fp32 (what the tf32 switch buys; parity is reported for both)
+cached / cached_e2e the step through the reference-frame cache: a clip's 14 memory frames are processed once
+          per clip, a key-frame step computes only the key frame's own slot; end to end only the new frame's map crosses PCIe
+parity    the timed step's outputs against the CPU comparator on the same input, for both library math modes and the cache
+roofline  the dominant hand-written kernel timed alone (CUDA events, L2 flushed), algorithmic FLOPs/bytes from BASELINE.md
+          section 3 over that time vs MEASURED_PEAKS.json; `kernels` lists every kernel the same way
+cpu_baseline   the reference's OWN files (oracle/_ref, staged by oracle/make_ref.py; kind "reference") on the host cores,
+          one key frame; kind "port" (oracle/vod_oracle.py) only if the staged files are absent
+eager_cuda_reference  the same reference files on the B200 in torch eager + torchvision CUDA ops (what a user of the
+          reference gets on this GPU)
+--impl reference  times the reference's own CPU implementation on all host threads, rank 0 only.
+--config cfg1 | cfg2 (FGFA step, bf16 maps) | cfg4 (DFF per-frame loop, key interval 10) | sweep (300-1000 proposals x 2-30
+          reference frames): the other BASELINE.json configs, same JSON contract, one line each.
 
-Multi-GPU (torchrun): clips are sharded by rank (one independent clip stream per rank, weak scaling,
-no data-path collective); the only exchange is one NCCL all_gather of the per-frame detections.
+Multi-GPU (torchrun): clips are sharded by rank (one independent clip stream per rank, weak scaling, no data-path
+collective); the only exchange is one NCCL all_gather of the per-frame detections.
 """
 import argparse
 import json
@@ -34,11 +42,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CONFIGS = {
-    # name: (N proposals, T frames in the reference set incl. key, shared fcs, TRoIA)
-    'cfg3': dict(N=300, T=15, fcs=3, troi=True,
+    # SELSA family: N proposals, T frames in the reference set incl. key, shared fcs, TRoIA
+    'cfg3': dict(family='selsa', N=300, T=15, fcs=3, troi=True,
                  workload='SELSA+TemporalRoIAlign R-50-DC5, 14 ref frames (+key), 300 proposals/frame, 600x1000'),
-    'cfg1': dict(N=300, T=3, fcs=2, troi=False,
+    'cfg1': dict(family='selsa', N=300, T=3, fcs=2, troi=False,
                  workload='SELSA R-50-DC5, 2 ref frames (+key), 300 proposals/frame, 600x1000'),
+    'cfg2': dict(family='fgfa', N=300, T=3, num_left=1,
+                 workload='FGFA R-50-DC5 feature path, 2 ref frames (+key slot), flow 608x1008, bf16 maps, 300 proposals, 600x1000'),
+    'cfg4': dict(family='dff', N=300, interval=10, clip=300,
+                 workload='DFF R-50-DC5 feature propagation, key-frame interval 10, low-light clip of 300 frames, 300 proposals'),
+    'sweep': dict(family='sweep', Ns=(300, 500, 1000), refs=(2, 6, 14, 30), fcs=3, troi=True,
+                  workload='SELSA+TemporalRoIAlign aggregation sweep: 300-1000 proposals x 2-30 ref frames (+key), 600x1000'),
 }
 C, H, W, D, CLASSES = 512, 38, 63, 1024, 30
 IMG_SHAPE = (600, 1000, 3)
@@ -51,6 +65,23 @@ def load_peaks():
         return dict(hbm=p['hbm_gbs'], tf_burst=p['bf16_tflops'], tf_sust=p.get('bf16_tflops_sustained', p['bf16_tflops']),
                     src='measured')
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src='fallback')
+
+
+def measure_tf32_peak(device):
+    """Dense tf32 tensor-core peak measured the way MEASURED_PEAKS.json measures bf16: torch.matmul of 8192^3 fp32 operands
+    with tf32 allowed, best of 10, CUDA events."""
+    n = 8192
+    with library_math(True):
+        a = torch.randn(n, n, device=device)
+        b = torch.randn(n, n, device=device)
+        best = float('inf')
+        for i in range(12):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+            if i >= 2:
+                best = min(best, e0.elapsed_time(e1) * 1e-3)
+    del a, b
+    return 2.0 * n ** 3 / best / 1e12
 
 
 # --------------------------------------------------------------------------------------------- inputs
@@ -189,7 +220,7 @@ def kernel_rooflines(cfg, device, peaks):
         roi_unit = torch.nn.functional.normalize(key_rows, dim=1).bfloat16()
         t = timeit(lambda: ops.msra_gemm_candidates(roi_unit, unit, T), iters=3)
         out['msra_gemm_topk_kernel'] = dict(bound='tensor', seconds=t, achieved=fl / t / 1e12, peak=peaks['tf_burst'], unit='TFLOP/s', flops=fl,
-                                            traffic=54.8e6, note='traffic = dram read+write per launch from ncu --set full (profiles/r01g_ncu_full_summary.csv)')
+                                            traffic=54.8e6, note='traffic: NOT measured in this run -- dram read+write per launch copied from the ncu --set full capture profiles/r01g_ncu_full_summary.csv')
         # (4') TAFA weighting: bytes = (2*(T+1)+1)*N*C*P*4
         x_all = torch.randn(T + 1, N, P, C, device=device, generator=g)
         emb = torch.randn(T + 1, N, P, C, device=device, generator=g)
@@ -203,7 +234,7 @@ def kernel_rooflines(cfg, device, peaks):
         t = timeit(lambda: ops.tafa_keyproj_logits(x_all, G, 7, 4, cc))
         b = (G.numel() + x_all.numel()) * 4
         out['tafa_keyproj_logits'] = dict(bound='hbm', seconds=t, achieved=b / t / 1e9, peak=peaks['hbm'], unit='GB/s', bytes=b,
-                                          traffic=1626.1e6, note='traffic = dram read+write per launch from ncu --set full (profiles/r01h_ncu_full_summary.csv)')
+                                          traffic=1626.1e6, note='traffic: NOT measured in this run -- dram read+write per launch copied from the ncu --set full capture profiles/r01h_ncu_full_summary.csv')
         parts = ops.tafa_keyproj_logits(x_all, G, 7, 4, cc)
         t = timeit(lambda: ops.tafa_weighted_sum_logits(x_all, parts, 4, out_nhwc=True))
         b = (x_all.numel() + N * P * C + parts.numel()) * 4
@@ -216,8 +247,21 @@ def kernel_rooflines(cfg, device, peaks):
     t = timeit(lambda: ops.selsa_attention(q, k, vt, 16, v_transposed=True))
     fl = 4.0 * N * M * D
     by = (2 * N + 2 * M) * D * 4
-    out['selsa_attention'] = dict(bound='tensor', seconds=t, achieved=fl / t / 1e12, peak=peaks['tf_burst'] / 2, unit='TFLOP/s',
-                                  flops=fl, bytes=by, hbm_gbs=by / t / 1e9, note='peak = tf32 dense ~ bf16/2')
+    tf32_peak = peaks.get('tf32') or peaks['tf_burst'] / 2
+    tf32_note = 'peak = dense tf32 measured in this run (torch.matmul 8192^3)' if peaks.get('tf32') else 'peak = tf32 dense ~ bf16/2'
+    out['selsa_attention'] = dict(bound='tensor', seconds=t, achieved=fl / t / 1e12, peak=tf32_peak, unit='TFLOP/s',
+                                  flops=fl, bytes=by, hbm_gbs=by / t / 1e9, note=tf32_note)
+    # the same kernel at the sweep maximum (N=1000 proposals, 31 frames): 127 GFLOP, where it is tensor-bound
+    Ns, Ms = 1000, 31000
+    qs = torch.randn(Ns, D, device=device, generator=g)
+    ks = torch.randn(Ms, D, device=device, generator=g)
+    vts = torch.randn(D, Ms, device=device, generator=g)
+    t = timeit(lambda: ops.selsa_attention(qs, ks, vts, 16, v_transposed=True), iters=3)
+    fl = 4.0 * Ns * Ms * D
+    by = (2 * Ns + 2 * Ms) * D * 4
+    out['selsa_attention_sweep_max'] = dict(bound='tensor', seconds=t, achieved=fl / t / 1e12, peak=tf32_peak, unit='TFLOP/s',
+                                            flops=fl, bytes=by, hbm_gbs=by / t / 1e9, note='N=1000, M=31000; ' + tf32_note)
+    del qs, ks, vts
     # (5) RCNN NMS: n = 30*N candidates
     n = CLASSES * N
     base = props_all[T].to(device)
@@ -385,6 +429,28 @@ def cpu_step(cfg, head_sd, ref_x, props_all, return_all=False):
     return dets, labels
 
 
+def reference_available():
+    try:
+        from oracle import ref_step
+        return ref_step.available()
+    except Exception:
+        return False
+
+
+def reference_head(cfg, head_sd, device):
+    """The reference's own RoI head (oracle/ref_step.py: its unmodified classes) with the benchmark's random-init weights."""
+    from oracle import ref_step
+    m = ref_step.ReferenceSelsaRoIHead(in_channels=C, fc_out_channels=D, num_shared_fcs=cfg['fcs'], num_classes=CLASSES,
+                                       temporal_roi_align=cfg['troi'])
+    m.load_state_dict(head_sd, strict=True)
+    return m.to(device).eval()
+
+
+def reference_step(ref_head, cfg, ref_x, props_all, return_all=False):
+    rois, ref_rois = step_rois(cfg, props_all)
+    return ref_head.step(ref_x[cfg['T'] - 1:], ref_x, rois, ref_rois, IMG_SHAPE, return_all=return_all)
+
+
 def cpu_head_state(cfg):
     """Random-init weights of the same architecture, built without touching CUDA."""
     import lowlightenvironmentvideoobjectdetection_b200 as vod  # module definitions only (nn.Module on CPU)
@@ -392,19 +458,28 @@ def cpu_head_state(cfg):
     return {k: v.detach() for k, v in head.state_dict().items()}
 
 
-def time_cpu(cfg, steps, warmup, budget_s=150.0):
+def time_cpu(cfg, steps, warmup, budget_s=150.0, keep_outputs=False):
+    """Times the CPU comparator on the host cores: the reference's own files when staged (kind 'reference'), else the oracle
+    port (kind 'port').  Returns (times, cores, kind, outputs of the first step | None)."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     os.environ.setdefault('OMP_NUM_THREADS', str(cores))
     sd = cpu_head_state(cfg)
-    times = []
+    kind = 'reference' if reference_available() else 'port'
+    ref_head = reference_head(cfg, sd, 'cpu') if kind == 'reference' else None
+    times, first = [], None
     with torch.no_grad():
         t_start = time.perf_counter()
         for i in range(warmup + steps):
             ref_x, props_all = make_inputs(cfg, i)
             t0 = time.perf_counter()
-            cpu_step(cfg, sd, ref_x, props_all)
+            if ref_head is not None:
+                res = reference_step(ref_head, cfg, ref_x, props_all, return_all=keep_outputs and i == 0)
+            else:
+                res = cpu_step(cfg, sd, ref_x, props_all, return_all=keep_outputs and i == 0)
             dt = time.perf_counter() - t0
+            if keep_outputs and i == 0:
+                first = res
             if i >= warmup:
                 times.append(dt)
             # bounded sample: stop early when the wall-clock budget is used up (at least one timed step)
@@ -412,7 +487,729 @@ def time_cpu(cfg, steps, warmup, budget_s=150.0):
                 break
             if not times and i + 1 >= warmup and time.perf_counter() - t_start > budget_s:
                 warmup = i + 1
-    return times, cores
+    return times, cores, kind, first
+
+
+# --------------------------------------------------------------------------------------------- run context
+class Ctx:
+    """Rank / device bookkeeping + the timing protocol: barrier + synchronize on both sides, CUDA events on the launching
+    stream, max over ranks."""
+
+    def __init__(self, args):
+        self.args = args
+        self.rank = int(os.environ.get('RANK', 0))
+        self.world = int(os.environ.get('WORLD_SIZE', 1))
+        self.local_rank = int(os.environ.get('LOCAL_RANK', 0))
+        self.device = torch.device('cuda', self.local_rank)
+        torch.cuda.set_device(self.device)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # keep NCCL's banner off stdout: rank 0 prints ONE JSON line
+            dist.init_process_group('nccl', device_id=self.device)
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, seconds):
+        if self.dist is None:
+            return seconds
+        t = torch.tensor([seconds], device=self.device, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, loop):
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loop()
+        e1.record()
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+
+    def close(self):
+        if self.dist is not None:
+            self.barrier()
+            self.dist.destroy_process_group()
+
+
+def base_result(ctx, cfg, metric, unit, value, t_step, dtype, config):
+    a = ctx.args
+    return {'metric': metric, 'value': value, 'unit': unit, 'n_gpus': ctx.world, 'steps': a.steps, 'warmup': a.warmup,
+            'ms_per_step': 1e3 * t_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': dtype,
+            'data': 'synthetic', 'config': config}
+
+
+METRIC, UNIT = 'VID frames/sec (SELSA+TRoIA path)', 'frames/s'
+
+
+class DetectionSink:
+    """Per-frame fixed-shape detections of this rank + the path's only exchange: one all_gather at the end (NCCL/NVLink)."""
+
+    def __init__(self, ctx, frames):
+        self.ctx, self.frames = ctx, frames
+        self.buf = torch.zeros(frames, 100, 6, device=ctx.device)
+        self.cnt = torch.zeros(frames, dtype=torch.int32, device=ctx.device)
+
+    def put(self, i, dets, labels, count):
+        i = i % self.frames
+        self.buf[i, :, :5] = dets
+        self.buf[i, :, 5] = labels.float()
+        self.cnt[i:i + 1] = count
+
+    def gather(self):
+        from lowlightenvironmentvideoobjectdetection_b200 import parallel
+        parallel.gather_detections(self.buf, self.cnt, frames_per_rank=[self.frames] * self.ctx.world)
+
+
+class Prefetcher:
+    """Double-buffered host->device copies on a copy stream: frame i+1's inputs cross PCIe while frame i computes; every
+    frame's inputs are still copied inside the timed region."""
+
+    def __init__(self, like):
+        self.stream = torch.cuda.Stream()
+        self.stage = [[torch.empty_like(t, device='cuda') for t in like] for _ in range(2)]
+        self.staged = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def begin(self):
+        for ev in self.consumed:
+            ev.record()
+
+    def prefetch(self, i, host_tensors):
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self.consumed[i % 2])
+            for dst, src in zip(self.stage[i % 2], host_tensors):
+                dst.copy_(src, non_blocking=True)
+            self.staged[i % 2].record(self.stream)
+
+    def wait(self, i):
+        torch.cuda.current_stream().wait_event(self.staged[i % 2])
+        return self.stage[i % 2]
+
+    def done(self, i):
+        self.consumed[i % 2].record()
+
+
+# --------------------------------------------------------------------------------------------- SELSA family (cfg1, cfg3, sweep cells)
+class SelsaRunner:
+    """Static buffers + CUDA graphs of one key-frame step of SelsaRoIHead at the shapes of ``cfg``."""
+
+    def __init__(self, ctx, cfg, n_sets=4, pinned=True):
+        import lowlightenvironmentvideoobjectdetection_b200 as vod
+        self.vod, self.ctx, self.cfg = vod, ctx, cfg
+        dev = ctx.device
+        self.head = build_head(cfg, dev)
+        self.lib = vod._lib.load()
+        self.n_sets = n_sets
+        self.host_sets = [make_inputs(cfg, ctx.rank * 1000 + i, pinned=pinned) for i in range(n_sets)]
+        self.dev_sets = [(a.to(dev), b.to(dev)) for a, b in self.host_sets]
+        T, N = cfg['T'], cfg['N']
+        self.st_ref = torch.empty_like(self.dev_sets[0][0])           # [T,512,38,63] reference maps (last = key frame)
+        self.st_props = torch.empty_like(self.dev_sets[0][1])         # [T+1,N,4]
+        self.st_rois = torch.zeros(N, 5, device=dev)                  # key-frame rois (batch index 0)
+        self.st_ref_rois = torch.zeros(T * N, 5, device=dev)
+        self.st_ref_rois[:, 0] = torch.arange(T, device=dev, dtype=torch.float32).repeat_interleave(N)
+        self.graphs = {}
+
+    def load_inputs(self, ref_x, props_all, non_blocking=False):
+        T, N = self.cfg['T'], self.cfg['N']
+        self.st_ref.copy_(ref_x, non_blocking=non_blocking)
+        self.st_props.copy_(props_all, non_blocking=non_blocking)
+        self.st_rois[:, 1:] = self.st_props[T]
+        self.st_ref_rois[:, 1:] = self.st_props[:T].reshape(T * N, 4)
+
+    def capture(self, name, tf32=True):
+        """The uncached step (SelsaRoIHead.capture_graph) under the given library math mode."""
+        T = self.cfg['T']
+        with torch.no_grad(), library_math(tf32):
+            self.load_inputs(*self.dev_sets[0])
+            l0 = self.lib.vod_kernel_launch_count()
+            graph, outs = self.head.capture_graph((self.st_ref[T - 1:T],), (self.st_ref,), self.st_rois, self.st_ref_rois, IMG_SHAPE,
+                                                  (1., 1., 1., 1.), rescale=False, warmup=2)
+            launches = (self.lib.vod_kernel_launch_count() - l0) // 3   # 2 warm-ups + 1 capture
+        self.graphs[name] = (graph, outs, launches)
+        return launches
+
+    def step(self, name, i, src, sink, non_blocking=False):
+        graph, (d, l, c), _ = self.graphs[name]
+        self.load_inputs(*src, non_blocking=non_blocking)
+        graph.replay()
+        sink.put(i, d, l, c)
+
+    # ---- reference-frame cache (row N2)
+    def capture_cached(self, tf32=True):
+        cfg, dev, head = self.cfg, self.ctx.device, self.head
+        T, N = cfg['T'], cfg['N']
+        self.cache = head.new_ref_cache(T, N, (C, H, W), dev)
+        self.st_memo = torch.empty((T - 1, C, H, W), device=dev)
+        self.st_memo_rois = torch.zeros((T - 1) * N, 5, device=dev)
+        self.st_memo_rois[:, 0] = torch.arange(T - 1, device=dev, dtype=torch.float32).repeat_interleave(N)
+        self.st_key = torch.empty((1, C, H, W), device=dev)
+        self.st_key_rois = torch.zeros(N, 5, device=dev)
+        self.st_key_ref_rois = torch.zeros(N, 5, device=dev)
+        slots = list(range(T - 1))
+        with torch.no_grad(), library_math(tf32):
+            self.load_memo(*self.dev_sets[0])
+            self.load_key(*self.dev_sets[0])
+            l0 = self.lib.vod_kernel_launch_count()
+            g_fill, _ = head.capture_callable(lambda: head.update_ref_cache(self.cache, slots, self.st_memo, self.st_memo_rois))
+            l1 = self.lib.vod_kernel_launch_count()
+            g_step, outs = head.capture_callable(lambda: head.simple_test_cached_device(
+                (self.st_key,), self.st_key_rois, self.st_key_ref_rois, self.cache, T - 1, IMG_SHAPE, (1., 1., 1., 1.)))
+            l2 = self.lib.vod_kernel_launch_count()
+        self.graphs['fill'] = (g_fill, None, (l1 - l0) // 3)
+        self.graphs['cached'] = (g_step, outs, (l2 - l1) // 3)
+
+    def load_memo(self, ref_x, props_all, non_blocking=False):
+        T, N = self.cfg['T'], self.cfg['N']
+        self.st_memo.copy_(ref_x[:T - 1], non_blocking=non_blocking)
+        self.st_memo_rois[:, 1:].copy_(props_all[:T - 1].reshape((T - 1) * N, 4), non_blocking=non_blocking)
+
+    def load_key(self, ref_x, props_all, non_blocking=False):
+        T = self.cfg['T']
+        self.st_key.copy_(ref_x[T - 1:T], non_blocking=non_blocking)
+        self.st_key_rois[:, 1:].copy_(props_all[T], non_blocking=non_blocking)
+        self.st_key_ref_rois[:, 1:].copy_(props_all[T - 1], non_blocking=non_blocking)
+
+
+def bench_selsa(ctx, cfg, cfg_name):
+    args = ctx.args
+    world, rank, device = ctx.world, ctx.rank, ctx.device
+    peaks = load_peaks()
+    T, N = cfg['T'], cfg['N']
+    config = dict(workload=cfg['workload'], proposals=N, ref_frames=T - 1, shared_fcs=cfg['fcs'],
+                  execution='one CUDA graph per key-frame step (SelsaRoIHead.capture_graph), inputs copied into its static buffers',
+                  library_math='cuBLAS shared FCs / projections and the cuDNN key-slot conv in tf32 (fp32_library_math: the same in fp32)',
+                  feature='[T,512,38,63] fp32', l2_policy='per-step working set (>1.4 GB at cfg3) exceeds the 126 MB L2; '
+                  'inputs rotate over 4 clip positions', parallelism='clip-sharded x%d' % world)
+    run = SelsaRunner(ctx, cfg)
+    n_sets = run.n_sets
+    sink = DetectionSink(ctx, args.steps)
+    launches_per_step = run.capture('tf32', tf32=True)
+
+    with torch.no_grad():
+        # ------------------------------------------------ device-resident throughput (graph replay)
+        # the clock sampler starts before the warm-up: NVML's first queries take tens of ms and serialise with the CUDA
+        # driver (seen as a 30 ms stall of the first timed replays at 8 ranks); only samples taken after e0 are reported
+        sampler = ClockSampler(ctx.local_rank)
+        sampler.start()
+        for i in range(args.warmup):
+            run.step('tf32', 0, run.dev_sets[i % n_sets], sink)
+        sink.gather()   # warm the collective (communicator / channel setup is not part of a steady-state step)
+        ctx.barrier()
+        sampler.first, sampler.reasons = len(sampler.samples), set()
+
+        def dev_loop():
+            for i in range(args.steps):
+                run.step('tf32', i, run.dev_sets[i % n_sets], sink)
+            sink.gather()
+        t_dev = ctx.timed(dev_loop)
+        sampler.stop_flag = True
+
+        # ------------------------------------------------ end to end: pinned host inputs in, detections out
+        h2d = run.host_sets[0][0].numel() * 4 + run.host_sets[0][1].numel() * 4
+        d2h = 100 * 6 * 4 + 4
+        out_host = torch.empty(100, 6).pin_memory()
+        cnt_host = torch.empty(1, dtype=torch.int32).pin_memory()
+        pf = Prefetcher((run.st_ref, run.st_props))
+
+        def e2e_loop(steps):
+            pf.begin()
+            pf.prefetch(0, run.host_sets[0])
+            for i in range(steps):
+                if i + 1 < steps:
+                    pf.prefetch(i + 1, run.host_sets[(i + 1) % n_sets])
+                run.step('tf32', i, pf.wait(i), sink)
+                pf.done(i)
+                out_host.copy_(sink.buf[i % sink.frames], non_blocking=True)
+                cnt_host.copy_(sink.cnt[i % sink.frames:i % sink.frames + 1], non_blocking=True)
+        e2e_loop(2)
+        t_e2e = ctx.timed(lambda: (e2e_loop(args.steps), sink.gather()))
+
+        # ------------------------------------------------ the eager (un-graphed) module API, for reference
+        metas = [dict(img_shape=IMG_SHAPE, scale_factor=(1., 1., 1., 1.))]
+        with library_math(True):
+            for i in range(2):
+                run_step(run.head, *run.dev_sets[i % n_sets], metas)
+            t_eager = ctx.timed(lambda: [run_step(run.head, *run.dev_sets[i % n_sets], metas) for i in range(args.steps)])
+
+        # ------------------------------------------------ the same step with fp32 library GEMMs / convs
+        run.capture('fp32', tf32=False)
+        for i in range(min(args.warmup, 3)):
+            run.step('fp32', 0, run.dev_sets[i % n_sets], sink)
+        t_fp32 = ctx.timed(lambda: [run.step('fp32', i, run.dev_sets[i % n_sets], sink) for i in range(args.steps)])
+
+        # ------------------------------------------------ through the reference-frame cache (row N2)
+        # A clip = 14 fixed memory frames + clip_len key frames (SELSA's adaptive-stride test mode, selsa.py:207-225).  At a clip
+        # start the memory frames are laid out / RoIAligned / projected ONCE (graph `fill`); every key frame then computes only its
+        # own slot (graph `cached`).  Both are inside the timed region; end to end the memory maps cross PCIe once per clip and
+        # each key frame's map (4.9 MB) once.
+        clip_len = args.clip_len
+        run.capture_cached(tf32=True)
+
+        def cached_loop(steps, from_host=False, pfk=None):
+            for i in range(steps):
+                src = (run.host_sets if from_host else run.dev_sets)[(i // clip_len) % n_sets]
+                if i % clip_len == 0:
+                    run.load_memo(*src, non_blocking=from_host)
+                    run.graphs['fill'][0].replay()
+                key_src = (run.host_sets if from_host else run.dev_sets)[i % n_sets]
+                run.load_key(*key_src, non_blocking=from_host)
+                g, (d, l, c), _ = run.graphs['cached']
+                g.replay()
+                sink.put(i, d, l, c)
+                if from_host:
+                    out_host.copy_(sink.buf[i % sink.frames], non_blocking=True)
+                    cnt_host.copy_(sink.cnt[i % sink.frames:i % sink.frames + 1], non_blocking=True)
+        cached_loop(min(args.warmup, 3) + 1)
+        t_cached = ctx.timed(lambda: (cached_loop(args.steps), sink.gather()))
+        cached_loop(2, from_host=True)
+        t_cached_e2e = ctx.timed(lambda: (cached_loop(args.steps, from_host=True), sink.gather()))
+        clips = (args.steps + clip_len - 1) // clip_len
+        memo_bytes = (T - 1) * C * H * W * 4 + (T - 1) * N * 4 * 4
+        key_bytes = C * H * W * 4 + 2 * N * 4 * 4
+        cached_h2d = (clips * memo_bytes + args.steps * key_bytes) / args.steps
+
+    frames = args.steps * world
+    result = base_result(ctx, cfg, METRIC, UNIT, frames / t_dev, t_dev / args.steps, 'tf32', config)
+    result.update({
+        'e2e': {'value': frames / t_e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+        'gpu_launches': int(launches_per_step * args.steps), 'clocks': sampler.summary(),
+        'eager_api': {'value': frames / t_eager, 'unit': UNIT,
+                      'note': 'SelsaRoIHead.simple_test called eagerly (what an integrator gets without capture_graph: variable-length '
+                              'outputs, one host read of the detection count per frame)'},
+        'fp32_library_math': {'value': frames / t_fp32, 'unit': UNIT, 'ms_per_step': 1e3 * t_fp32 / args.steps,
+                              'note': 'same graph-replayed step with cuBLAS / cuDNN in fp32 instead of tf32'},
+        'cached': {'value': frames / t_cached, 'unit': UNIT, 'ms_per_step': 1e3 * t_cached / args.steps, 'clip_len': clip_len,
+                   'gpu_launches_per_key_frame': int(run.graphs['cached'][2]), 'gpu_launches_per_clip_start': int(run.graphs['fill'][2]),
+                   'note': 'reference-frame cache (SURVEY row N2): memory frames processed once per clip of clip_len key frames '
+                           '(clip starts are inside the timed region), a key-frame step computes only the key frame\'s own slot'},
+        'cached_e2e': {'value': frames / t_cached_e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(cached_h2d), 'd2h_bytes_per_step': d2h,
+                       'note': 'host inputs: %d memory maps once per clip + the key frame\'s map and proposals per step' % (T - 1)},
+    })
+
+    if rank == 0 and not args.no_roofline:
+        peaks['tf32'] = measure_tf32_peak(device)
+        with torch.no_grad(), library_math(True):
+            kr = kernel_rooflines(cfg, device, peaks)
+        # the dominant kernel of THE TIMED STEP: composites (msra_topk_sample), alternates (NCHW-output RoIAlign) and the
+        # kernels of the other detectors' shapes (FGFA/DFF T=31, RPN NMS), which the table also lists, do not qualify
+        in_step = ('roi_align_refs', 'msra_gemm_topk_kernel', 'tafa_keyproj_logits', 'tafa_weighted_sum_logits', 'selsa_attention',
+                   'batched_nms_rcnn')
+        single = {k: v for k, v in kr.items() if k in in_step}
+        dom = max(single, key=lambda k: single[k]['seconds'])
+        r = kr[dom]
+        result['roofline'] = {'kernel': dom, 'bound': r['bound'], 'achieved': r['achieved'], 'peak': r['peak'], 'unit': r['unit'],
+                              'frac': r['frac'], 'traffic': r.get('traffic'), 'traffic_source': 'ncu capture under profiles/ (not re-measured in this run)',
+                              'peak_source': peaks['src'] + ' (burst: kernel timed alone)'}
+        result['measured_tf32_tflops'] = peaks['tf32']
+        result['kernels'] = {k: {kk: (round(vv, 6) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in kr.items()}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # CPU comparator on the host cores (the reference's own files when staged) + parity of the timed configuration against it
+        times, cores, kind, want = time_cpu(cfg, 1, 0, keep_outputs=True)
+        result['cpu_baseline'] = {'value': 1.0 / times[0], 'unit': UNIT, 'cores': cores, 'kind': kind,
+                                  'sample': '1 key frame of the same workload (%.1f s) on the host cores: %s' % (
+                                      times[0], 'the reference\'s own files (oracle/_ref) under torch CPU + torchvision ops'
+                                      if kind == 'reference' else 'torch CPU + C/OpenMP oracle port')}
+        ref_x, props_all = make_inputs(cfg, 0)
+        want = {k: (v.float().cpu() if torch.is_tensor(v) else v) for k, v in want.items()}
+        parity = {'against': 'cpu_baseline (%s) on make_inputs(seed 0)' % kind,
+                  'note': 'max|a-b|/max|b|; an fp32 tie between two reference locations may be broken differently (that RoI then samples '
+                          'another pixel): see rois_within_1e-3 / median next to the maximum; tests/test_gpu_fullsize.py verifies every '
+                          'such RoI is a tie'}
+        for name, tf32 in (('tf32_library_math', True), ('fp32_library_math', False)):
+            with library_math(tf32):
+                ours = gpu_step_outputs(run.head, cfg, ref_x.to(device), props_all.to(device))
+            parity[name] = parity_report(ours, want)
+        with torch.no_grad(), library_math(True):
+            run.load_memo(ref_x.to(device), props_all.to(device))
+            run.graphs['fill'][0].replay()
+            run.load_key(ref_x.to(device), props_all.to(device))
+            d, l, c, mid = run.head.simple_test_cached_device((run.st_key,), run.st_key_rois, run.st_key_ref_rois, run.cache, T - 1,
+                                                              IMG_SHAPE, (1., 1., 1., 1.), return_feats=True)
+            n = int(c)
+            feats = mid['bbox_feats'].view(N, 7, 7, C).permute(0, 3, 1, 2) if cfg['troi'] else mid['bbox_feats'].view(N, 7, 7, C).permute(0, 3, 1, 2)
+            ours = dict(bbox_feats=feats.float().cpu(), cls_score=mid['cls_score'].cpu(), bbox_pred=mid['bbox_pred'].cpu(),
+                        dets=d[:n].cpu(), labels=l[:n].cpu())
+        parity['cached_tf32_library_math'] = parity_report(ours, want)
+        result['parity'] = parity
+
+    if rank == 0 and world == 1 and not args.no_eager_reference and reference_available():
+        # the reference's own files on this GPU: torch eager + torchvision CUDA ops (BASELINE.md section 4, second comparator)
+        try:
+            sd = {k: v.detach() for k, v in run.head.state_dict().items()}
+            ref_head = reference_head(cfg, sd, device)
+            rois_sets = [step_rois(cfg, b) for _, b in run.dev_sets]
+            with torch.no_grad(), library_math(True):
+                def ref_loop(k):
+                    for i in range(k):
+                        a = run.dev_sets[i % n_sets][0]
+                        ref_head.step(a[T - 1:], a, rois_sets[i % n_sets][0], rois_sets[i % n_sets][1], IMG_SHAPE)
+                ref_loop(2)
+                k_ref = max(3, min(args.steps, 10))
+                t_ref = ctx.timed(lambda: ref_loop(k_ref))
+                outs = ref_head.step(run.dev_sets[0][0][T - 1:], run.dev_sets[0][0], rois_sets[0][0], rois_sets[0][1], IMG_SHAPE, return_all=True)
+                ours = gpu_step_outputs(run.head, cfg, *run.dev_sets[0])
+            outs = {k: v.float().cpu() if v.is_floating_point() else v.cpu() for k, v in outs.items()}
+            result['eager_cuda_reference'] = {
+                'value': k_ref / t_ref, 'unit': UNIT, 'ms_per_step': 1e3 * t_ref / k_ref, 'steps': k_ref,
+                'note': 'the reference\'s own TemporalRoIAlign / SelsaAggregator / multiclass_nms files (oracle/_ref) in torch eager on this '
+                        'GPU, mmcv ops = torchvision CUDA ops, tf32 library math as in the headline; tools/benchmark.py:72-98 protocol',
+                'parity_of_ours_against_it': parity_report(ours, outs)}
+            del ref_head
+        except Exception as e:   # a comparator must never take the benchmark down
+            result['eager_cuda_reference'] = {'unavailable': '%s: %s' % (type(e).__name__, str(e)[:200])}
+    return result
+
+
+# --------------------------------------------------------------------------------------------- cfg 5: the aggregation sweep
+def bench_sweep(ctx, cfg):
+    """300-1000 proposals x 2-30 reference frames: per cell, frames/s of the graph-replayed SELSA+TRoIA step, the dominant
+    kernel (the tcgen05 similarity GEMM) timed alone with its fraction of the bf16 peak, and the CPU comparator's time."""
+    args = ctx.args
+    peaks = load_peaks()
+    cells = []
+    from lowlightenvironmentvideoobjectdetection_b200 import ops
+    steps = max(3, min(args.steps, 10))
+    for N in cfg['Ns']:
+        for refs in cfg['refs']:
+            cell_cfg = dict(family='selsa', N=N, T=refs + 1, fcs=cfg['fcs'], troi=True, workload='sweep cell')
+            run = SelsaRunner(ctx, cell_cfg, n_sets=2, pinned=False)
+            sink = DetectionSink(ctx, steps)
+            with torch.no_grad():
+                run.capture('tf32', tf32=True)
+                for i in range(3):
+                    run.step('tf32', i, run.dev_sets[i % 2], sink)
+                t = ctx.timed(lambda: [run.step('tf32', i, run.dev_sets[i % 2], sink) for i in range(steps)])
+                run.capture_cached(tf32=True)
+                run.load_memo(*run.dev_sets[0]); run.graphs['fill'][0].replay()
+
+                def cached(k):
+                    for i in range(k):
+                        run.load_key(*run.dev_sets[i % 2])
+                        g, (d, l, c), _ = run.graphs['cached']
+                        g.replay()
+                cached(2)
+                t_c = ctx.timed(lambda: cached(steps))
+                cell = dict(proposals=N, ref_frames=refs, value=steps * ctx.world / t, ms_per_step=1e3 * t / steps, unit=UNIT,
+                            cached_value=steps * ctx.world / t_c, cached_ms_per_step=1e3 * t_c / steps)
+                if ctx.rank == 0:
+                    T = refs + 1
+                    ref_nhwc, norm, unit = ops._to_nhwc(run.dev_sets[0][0], want_norm=True, want_unit_bf16=True)
+                    rows = torch.nn.functional.normalize(torch.relu(torch.randn(N * 49, C, device=ctx.device)), dim=1).bfloat16()
+                    ops.msra_gemm_candidates(rows, unit, T); torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); ops.msra_gemm_candidates(rows, unit, T); e1.record(); torch.cuda.synchronize()
+                    tk = e0.elapsed_time(e1) * 1e-3
+                    fl = 2.0 * N * 49 * C * T * H * W
+                    cell['dominant_kernel'] = dict(kernel='msra_gemm_topk_kernel', bound='tensor', seconds=tk, achieved=fl / tk / 1e12,
+                                                   peak=peaks['tf_burst'], unit='TFLOP/s', frac=fl / tk / 1e12 / peaks['tf_burst'],
+                                                   share_of_step=tk / (t / steps))
+                    del ref_nhwc, norm, unit, rows
+            if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline:
+                times, cores, kind, _ = time_cpu(cell_cfg, 1, 0, budget_s=120.0)
+                cell['cpu'] = dict(seconds_per_frame=times[0], value=1.0 / times[0], unit=UNIT, cores=cores, kind=kind)
+            cells.append(cell)
+            del run, sink
+            torch.cuda.empty_cache()
+    head_cell = next(c for c in cells if c['proposals'] == 300 and c['ref_frames'] == 14)
+    config = dict(workload=cfg['workload'], cells='proposals x ref_frames', steps_per_cell=steps,
+                  execution='one CUDA graph per key-frame step per cell', parallelism='clip-sharded x%d' % ctx.world,
+                  l2_policy='per-step working set exceeds L2 in every cell but the smallest; inputs rotate over 2 clip positions')
+    result = base_result(ctx, cfg, METRIC, UNIT, head_cell['value'], head_cell['ms_per_step'] * 1e-3, 'tf32', config)
+    result['steps'] = steps
+    result['sweep'] = cells
+    result['note'] = 'value = the (300 proposals, 14 ref frames) cell; every cell is listed under sweep'
+    return result
+
+
+# --------------------------------------------------------------------------------------------- cfg 2 / cfg 4: feature-level detectors
+def grid_anchors(device):
+    ys, xs = torch.meshgrid(torch.arange(H, device=device) * 16., torch.arange(W, device=device) * 16., indexing='ij')
+    shift = torch.stack([xs, ys, xs, ys], -1).reshape(-1, 1, 4)
+    base = torch.tensor([[-16. * sc / r ** 0.5 / 2, -16. * sc * r ** 0.5 / 2, 16. * sc / r ** 0.5 / 2, 16. * sc * r ** 0.5 / 2]
+                         for r in (0.5, 1., 2.) for sc in (4, 8, 16, 32)], device=device)
+    return (shift + base[None]).reshape(-1, 4)
+
+
+def feature_level_inputs(seed, n_flows, low_light=False, pinned=False):
+    """Synthetic inputs of the FGFA / DFF feature path: stride-16 maps (relu(N(0,1)); x0.25 for the low-light variant, mirroring
+    SeqBrighten(m=0.25)), flows ~ N(0, 8^2) px at 608x1008, RPN objectness / delta maps (the RPN convs are upstream)."""
+    g = torch.Generator().manual_seed(4321 + seed)
+    scale = 0.25 if low_light else 1.0
+    x = torch.relu(torch.randn(1, C, H, W, generator=g)) * scale
+    memo = torch.relu(torch.randn(n_flows, C, H, W, generator=g)) * scale
+    flows = torch.randn(n_flows, 2, H * 16, W * 16, generator=g) * 8
+    rpn_cls = torch.randn(1, 12, H, W, generator=g) * 3
+    rpn_reg = torch.randn(1, 48, H, W, generator=g) * 0.3
+    t = [x, memo, flows, rpn_cls, rpn_reg]
+    return [v.pin_memory() for v in t] if pinned else t
+
+
+def build_standard_head(device):
+    import lowlightenvironmentvideoobjectdetection_b200 as vod
+    torch.manual_seed(0)
+    head = vod.StandardRoIHead(
+        bbox_roi_extractor=dict(type='SingleRoIExtractor', roi_layer=dict(type='RoIAlign', output_size=7, sampling_ratio=2),
+                                out_channels=C, featmap_strides=[16]),
+        bbox_head=dict(type='Shared2FCBBoxHead', num_shared_fcs=2, in_channels=C, fc_out_channels=D, roi_feat_size=7,
+                       num_classes=CLASSES),
+        test_cfg=dict(score_thr=0.0001, nms=dict(type='nms', iou_threshold=0.5), max_per_img=100))
+    agg = vod.build_aggregator(dict(type='EmbedAggregator', num_convs=1, channels=C, kernel_size=3))
+    return head.to(device).eval(), agg.to(device).eval()
+
+
+def detect_on_map(vod, head, feat, rpn_cls, rpn_reg, anchors):
+    """RPN proposal stage (row N3, device) + StandardRoIHead on one feature map: what FGFA / DFF run after their feature step."""
+    props, num = vod.rpn_get_bboxes_device(rpn_cls, rpn_reg, anchors, IMG_SHAPE, 6000, 0.7, 300)
+    rois = torch.cat([props.new_zeros(props.shape[1], 1), props[0, :, :4]], 1)
+    return head.simple_test_device((feat,), rois, IMG_SHAPE, (1., 1., 1., 1.))
+
+
+def bench_fgfa(ctx, cfg):
+    import lowlightenvironmentvideoobjectdetection_b200 as vod
+    args, dev = ctx.args, ctx.device
+    T, num_left = cfg['T'], cfg['num_left']
+    head, agg = build_standard_head(dev)
+    agg = agg.bfloat16()                                        # the config states bf16: maps and the embed conv in bf16
+    anchors = grid_anchors(dev)
+    n_sets = 4
+    host = [feature_level_inputs(ctx.rank * 1000 + i, T, pinned=True) for i in range(n_sets)]
+    host = [[h[0].bfloat16().pin_memory(), h[1].bfloat16().pin_memory(), h[2], h[3], h[4]] for h in host]
+    devs = [[t.to(dev) for t in h] for h in host]
+    st = [torch.empty_like(t) for t in devs[0]]
+
+    def load(src, non_blocking=False):
+        for d, s_ in zip(st, src):
+            d.copy_(s_, non_blocking=non_blocking)
+
+    def step():
+        x, memo, flows, rpn_cls, rpn_reg = st
+        warped = vod.flow_warp_feats(memo, flows)               # fgfa.py:277
+        warped[num_left] = x[0]                                  # :281
+        feat = agg(x, warped)                                    # :282
+        return detect_on_map(vod, head, feat, rpn_cls, rpn_reg, anchors)
+
+    lib = vod._lib.load()
+    sink = DetectionSink(ctx, args.steps)
+    with torch.no_grad(), library_math(True):
+        load(devs[0])
+        l0 = lib.vod_kernel_launch_count()
+        graph, (d, l, c) = vod.SelsaRoIHead.capture_callable(step)
+        launches = (lib.vod_kernel_launch_count() - l0) // 3
+        sampler = ClockSampler(ctx.local_rank); sampler.start()
+
+        def dev_loop(k):
+            for i in range(k):
+                load(devs[i % n_sets]); graph.replay(); sink.put(i, d, l, c)
+        dev_loop(args.warmup)
+        sink.gather(); ctx.barrier()
+        sampler.first, sampler.reasons = len(sampler.samples), set()
+        t_dev = ctx.timed(lambda: (dev_loop(args.steps), sink.gather()))
+        sampler.stop_flag = True
+        # end to end: the key map, the flows and the RPN maps of every step come from pinned host memory; the feature memory
+        # is resident (FGFA keeps it on the device and advances it by one frame per stride, fgfa.py:256-265)
+        out_host = torch.empty(100, 6).pin_memory()
+        pf = Prefetcher((st[0], st[2], st[3], st[4]))
+
+        def e2e_loop(k):
+            pf.begin(); pf.prefetch(0, (host[0][0], host[0][2], host[0][3], host[0][4]))
+            for i in range(k):
+                if i + 1 < k:
+                    h = host[(i + 1) % n_sets]
+                    pf.prefetch(i + 1, (h[0], h[2], h[3], h[4]))
+                s0, s2, s3, s4 = pf.wait(i)
+                st[0].copy_(s0); st[2].copy_(s2); st[3].copy_(s3); st[4].copy_(s4)
+                pf.done(i)
+                graph.replay(); sink.put(i, d, l, c)
+                out_host.copy_(sink.buf[i % sink.frames], non_blocking=True)
+        e2e_loop(2)
+        t_e2e = ctx.timed(lambda: (e2e_loop(args.steps), sink.gather()))
+    frames = args.steps * ctx.world
+    h2d = sum(host[0][j].numel() * host[0][j].element_size() for j in (0, 2, 3, 4))
+    config = dict(workload=cfg['workload'], proposals=cfg['N'], ref_frames=T - 1, execution='one CUDA graph per frame',
+                  step='flow_warp_feats -> key slot -> EmbedAggregator (bf16 cuDNN embed conv + fp32 weighting kernels) -> RPN proposal '
+                       'stage (device) -> RoIAlign(300) -> Shared2FC head (cuBLAS tf32) -> decode + NMS',
+                  l2_policy='inputs rotate over 4 clip positions; per-step working set ~60 MB fits L2 (as it does in deployment)',
+                  parallelism='clip-sharded x%d' % ctx.world)
+    result = base_result(ctx, cfg, 'VID frames/sec (FGFA feature path)', UNIT, frames / t_dev, t_dev / args.steps, 'bf16', config)
+    result.update({'e2e': {'value': frames / t_e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 2400},
+                   'gpu_launches': int(launches * args.steps), 'clocks': sampler.summary()})
+    if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline and reference_available():
+        from oracle import ref_step
+        torch.set_num_threads(os.cpu_count() or 1)
+        ref = ref_step.ReferenceFeatureLevelDetector(in_channels=C, fc_out_channels=D, num_classes=CLASSES)
+        sd = {('bbox_head.' + k if not k.startswith('bbox_head.') else k): v for k, v in head.state_dict().items()}
+        ref.bbox_head.load_state_dict({k[len('bbox_head.'):]: v.float().cpu() for k, v in sd.items()})
+        ref.aggregator.load_state_dict({k: v.float().cpu() for k, v in agg.state_dict().items()})
+        h0 = [t.float() for t in host[0]]
+        t0 = time.perf_counter()
+        d0, l0_ = ref.fgfa_step(h0[0], h0[1], h0[2], num_left, h0[3], h0[4], anchors.cpu(), IMG_SHAPE)
+        dt = time.perf_counter() - t0
+        result['cpu_baseline'] = {'value': 1.0 / dt, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'reference',
+                                  'sample': '1 frame (%.2f s): the reference\'s flow_warp_feats + EmbedAggregator + RPNHead._get_bboxes + '
+                                            'multiclass_nms files on the host cores (fp32, bf16-rounded inputs)' % dt}
+        with torch.no_grad(), library_math(True):
+            load(devs[0]); graph.replay(); torch.cuda.synchronize()
+        n = int(c)
+        result['parity'] = {'against': 'cpu_baseline (reference) on the same input', 'n_dets': [n, int(len(d0))],
+                            'det_match': match_detections(d[:n].cpu(), l[:n].cpu(), d0, l0_, box_tol=2.0, score_tol=5e-3),
+                            'note': 'bf16 maps + bf16 embed conv against the fp32 reference: stated bf16 tolerance (2 px / 5e-3 score)'}
+    return result
+
+
+def bench_dff(ctx, cfg):
+    import lowlightenvironmentvideoobjectdetection_b200 as vod
+    args, dev = ctx.args, ctx.device
+    interval, clip = cfg['interval'], cfg['clip']
+    head, _ = build_standard_head(dev)
+    anchors = grid_anchors(dev)
+    n_sets = 4
+    host = [feature_level_inputs(ctx.rank * 1000 + i, 1, low_light=True, pinned=True) for i in range(n_sets)]
+    devs = [[t.to(dev) for t in h] for h in host]
+    key_map = torch.empty_like(devs[0][0])
+    st_flow, st_cls, st_reg = (torch.empty_like(devs[0][j]) for j in (2, 3, 4))
+    memo = vod.DFFFeatureMemo(interval)
+    memo.set_key((key_map,))
+    lib = vod._lib.load()
+    frames_total = clip
+    sink = DetectionSink(ctx, frames_total)
+    nb = interval - 1
+    st_flows = torch.empty((nb,) + tuple(devs[0][2].shape[1:]), device=dev)
+    st_cls_b = torch.empty((nb,) + tuple(devs[0][3].shape[1:]), device=dev)
+    st_reg_b = torch.empty((nb,) + tuple(devs[0][4].shape[1:]), device=dev)
+
+    def key_step():
+        return detect_on_map(vod, head, key_map, st_cls, st_reg, anchors)                  # dff.py:205-209 + detector head
+
+    def nonkey_step():
+        feat = memo.extract_feats(st_flow)[0]                                               # dff.py:211-216
+        return detect_on_map(vod, head, feat, st_cls, st_reg, anchors)
+
+    def interval_step():
+        feats = memo.extract_feats_interval(st_flows)[0]                                    # the 9 non-key frames, one warp launch
+        props, num = vod.rpn_get_bboxes_device(st_cls_b, st_reg_b, anchors, IMG_SHAPE, 6000, 0.7, 300)
+        outs = []
+        rois = torch.cat([torch.arange(nb, device=dev, dtype=torch.float32).repeat_interleave(300)[:, None], props[:, :, :4].reshape(-1, 4)], 1)
+        rf = head.bbox_roi_extractor((feats,), rois)
+        cls_score, bbox_pred = head.bbox_head(rf)
+        for b in range(nb):
+            sl = slice(b * 300, (b + 1) * 300)
+            outs.append(head.bbox_head.get_bboxes_device(rois[sl], cls_score[sl], bbox_pred[sl], IMG_SHAPE, (1., 1., 1., 1.), cfg=head.test_cfg))
+        return outs
+
+    with torch.no_grad(), library_math(True):
+        key_map.copy_(devs[0][0]); st_flow.copy_(devs[0][2]); st_cls.copy_(devs[0][3]); st_reg.copy_(devs[0][4])
+        for b in range(nb):
+            st_flows[b].copy_(devs[b % n_sets][2][0]); st_cls_b[b].copy_(devs[b % n_sets][3][0]); st_reg_b[b].copy_(devs[b % n_sets][4][0])
+        l0 = lib.vod_kernel_launch_count()
+        g_key, o_key = vod.SelsaRoIHead.capture_callable(key_step)
+        l1 = lib.vod_kernel_launch_count()
+        g_non, o_non = vod.SelsaRoIHead.capture_callable(nonkey_step)
+        l2 = lib.vod_kernel_launch_count()
+        g_int, o_int = vod.SelsaRoIHead.capture_callable(interval_step)
+        l3 = lib.vod_kernel_launch_count()
+        sampler = ClockSampler(ctx.local_rank); sampler.start()
+
+        def clip_loop(n_frames, from_host=False):
+            src = host if from_host else devs
+            for f in range(n_frames):
+                s_ = src[f % n_sets]
+                st_cls.copy_(s_[3], non_blocking=from_host); st_reg.copy_(s_[4], non_blocking=from_host)
+                if f % interval == 0:
+                    key_map.copy_(s_[0], non_blocking=from_host)                            # (the backbone's output for a key frame)
+                    g_key.replay(); sink.put(f, *o_key)
+                else:
+                    st_flow.copy_(s_[2], non_blocking=from_host)
+                    g_non.replay(); sink.put(f, *o_non)
+
+        def interval_loop(n_frames):
+            for f0 in range(0, n_frames, interval):
+                s_ = devs[(f0 // interval) % n_sets]
+                st_cls.copy_(s_[3]); st_reg.copy_(s_[4]); key_map.copy_(s_[0])
+                g_key.replay(); sink.put(f0, *o_key)
+                g_int.replay()
+                for b in range(nb):
+                    sink.put(f0 + 1 + b, *o_int[b])
+        clip_loop(2 * interval)
+        sink.gather(); ctx.barrier()
+        sampler.first, sampler.reasons = len(sampler.samples), set()
+        t_dev = ctx.timed(lambda: (clip_loop(frames_total), sink.gather()))
+        sampler.stop_flag = True
+        clip_loop(interval, from_host=True)
+        t_e2e = ctx.timed(lambda: (clip_loop(frames_total, from_host=True), sink.gather()))
+        interval_loop(2 * interval)
+        t_int = ctx.timed(lambda: (interval_loop(frames_total), sink.gather()))
+    frames = frames_total * ctx.world
+    launches = (l1 - l0) // 3 * (frames_total // interval) + (l2 - l1) // 3 * (frames_total - frames_total // interval)
+    map_b, flow_b, rpn_b = key_map.numel() * 4, st_flow.numel() * 4, (st_cls.numel() + st_reg.numel()) * 4
+    config = dict(workload=cfg['workload'], key_frame_interval=interval, frames=frames_total,
+                  execution='two CUDA graphs (key frame / non-key frame), one replay per frame', parallelism='clip-sharded x%d' % ctx.world,
+                  step='non-key frame: flow_warp_feats(key map, flow) -> RPN proposal stage (device) -> RoIAlign(300) -> Shared2FC head -> '
+                       'decode + NMS; key frame: the same on the key map (backbone / FlowNet / RPN convs are upstream, their outputs are inputs)',
+                  l2_policy='inputs rotate over 4 clip positions; the per-frame working set (~20 MB) is L2-resident, as in deployment')
+    result = base_result(ctx, cfg, 'VID frames/sec (DFF feature-propagation path)', UNIT, frames / t_dev, t_dev / frames_total, 'tf32', config)
+    result['steps'] = frames_total
+    result.update({'us_per_frame': 1e6 * t_dev / frames_total,
+                   'e2e': {'value': frames / t_e2e, 'unit': UNIT, 'd2h_bytes_per_step': 2400,
+                           'h2d_bytes_per_step': int(rpn_b + (map_b + (interval - 1) * flow_b) / interval)},
+                   'interval_batched': {'value': frames / t_int, 'unit': UNIT, 'us_per_frame': 1e6 * t_int / frames_total,
+                                        'note': 'the 9 non-key frames of an interval in ONE graph: one shared-map warp launch '
+                                                '(vod_flow_warp_shared), one RPN stage and one RoIAlign / FC pass over 9 frames (SURVEY row N4)'},
+                   'gpu_launches': int(launches), 'clocks': sampler.summary()})
+    if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline and reference_available():
+        from oracle import ref_step
+        torch.set_num_threads(os.cpu_count() or 1)
+        ref = ref_step.ReferenceFeatureLevelDetector(in_channels=C, fc_out_channels=D, num_classes=CLASSES, with_aggregator=False)
+        ref.bbox_head.load_state_dict({k[len('bbox_head.'):]: v.float().cpu() for k, v in head.state_dict().items() if k.startswith('bbox_head.')})
+        h0 = host[0]
+        t0 = time.perf_counter()
+        d0, l0_ = ref.dff_step(h0[0], h0[2], h0[3], h0[4], anchors.cpu(), IMG_SHAPE)
+        dt = time.perf_counter() - t0
+        result['cpu_baseline'] = {'value': 1.0 / dt, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'reference',
+                                  'sample': '1 non-key frame (%.2f s): the reference\'s flow_warp_feats + RPNHead._get_bboxes + multiclass_nms '
+                                            'files on the host cores' % dt}
+        with torch.no_grad(), library_math(True):
+            key_map.copy_(devs[0][0]); st_flow.copy_(devs[0][2]); st_cls.copy_(devs[0][3]); st_reg.copy_(devs[0][4])
+            g_non.replay(); torch.cuda.synchronize()
+        n = int(o_non[2])
+        result['parity'] = {'against': 'cpu_baseline (reference) on the same input', 'n_dets': [n, int(len(d0))],
+                            'det_match': match_detections(o_non[0][:n].cpu(), o_non[1][:n].cpu(), d0, l0_, box_tol=0.5, score_tol=1e-3)}
+    return result
+
+
+# --------------------------------------------------------------------------------------------- reference arm
+def reference_arm(args, cfg, cfg_name):
+    """``--impl reference``: the reference's OWN CPU implementation of the path on the host cores (rank 0 only)."""
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    if cfg['family'] == 'sweep':
+        cfg = dict(CONFIGS['cfg3'], workload=CONFIGS['sweep']['workload'] + ' -- reference arm: the (300, 14) cell')
+    if cfg['family'] != 'selsa':
+        print(json.dumps({'impl': 'reference', 'unavailable': 'the reference arm of %s is reported as cpu_baseline inside the GPU arm' % cfg_name}))
+        return
+    warm = min(args.warmup, 1)
+    times, cores, kind, _ = time_cpu(cfg, args.steps, warm)
+    ms = 1e3 * sum(times) / len(times)
+    val = 1e3 / ms
+    config = dict(workload=cfg['workload'], proposals=cfg['N'], ref_frames=cfg['T'] - 1, shared_fcs=cfg['fcs'],
+                  execution='torch CPU eager on all host threads: %s' % (
+                      'the reference\'s own unmodified files (oracle/_ref) under the mmcv stand-ins of oracle/ref_shim.py, mmcv ops = torchvision ops'
+                      if kind == 'reference' else 'oracle port (reference files not staged)'),
+                  feature='[T,512,38,63] fp32', parallelism='rank 0 only')
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': len(times),
+        'warmup': warm, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic', 'config': config,
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': kind,
+                         'sample': '%d key frame(s) of the same workload on the host cores; steps bounded by a 150 s wall-clock budget' % len(times)},
+        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
 
 # --------------------------------------------------------------------------------------------- main
@@ -423,219 +1220,42 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default='cfg3', choices=sorted(CONFIGS))
+    ap.add_argument('--clip-len', type=int, default=40, help='key frames per clip in the cached loop')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-roofline', action='store_true')
+    ap.add_argument('--no-eager-reference', action='store_true')
     ap.add_argument('--kernels-only', action='store_true', help='run only the per-kernel roofline pass (ncu target)')
+    ap.add_argument('--out', default=None, help='also write the JSON line to this file')
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
-    rank = int(os.environ.get('RANK', 0))
-    world = int(os.environ.get('WORLD_SIZE', 1))
-    local_rank = int(os.environ.get('LOCAL_RANK', 0))
-    metric, unit = 'VID frames/sec (SELSA+TRoIA path)', 'frames/s'
-    config = dict(workload=cfg['workload'], proposals=cfg['N'], ref_frames=cfg['T'] - 1, shared_fcs=cfg['fcs'],
-                  execution='one CUDA graph per key-frame step (SelsaRoIHead.capture_graph), inputs copied into its static buffers',
-                  feature='[T,512,38,63] fp32', l2_policy='per-step working set (>1.4 GB at cfg3) exceeds the 126 MB L2; '
-                  'inputs rotate over 4 clip positions', parallelism='clip-sharded x%d' % world)
-
     if args.impl == 'reference':
-        if rank != 0:
-            return
-        warm = min(args.warmup, 1)
-        times, cores = time_cpu(cfg, args.steps, warm)
-        ms = 1e3 * sum(times) / len(times)
-        val = 1e3 / ms
-        print(json.dumps({
-            'impl': 'reference', 'metric': metric, 'value': val, 'unit': unit, 'n_gpus': args.gpus, 'steps': len(times),
-            'warmup': warm, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32', 'data': 'synthetic', 'config': config,
-            'cpu_baseline': {'value': val, 'unit': unit, 'cores': cores, 'kind': 'port',
-                             'sample': '%d key frame(s) of the same workload on the host cores (torch CPU + C/OpenMP oracle); '
-                                       'steps bounded by a 150 s wall-clock budget' % len(times)},
-            'e2e': {'value': val, 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        reference_arm(args, cfg, args.config)
         return
-
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback exists for the product path)'
-    import lowlightenvironmentvideoobjectdetection_b200 as vod
-    device = torch.device('cuda', local_rank)
-    torch.cuda.set_device(device)
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # keep NCCL's banner off stdout: rank 0 prints ONE JSON line
-        dist.init_process_group('nccl', device_id=device)
-    # library GEMMs/convs around the path (shared FCs, embed conv) run tf32 like our own tensor-core kernels
-    torch.backends.cuda.matmul.allow_tf32 = True
-    torch.backends.cudnn.allow_tf32 = True
-    peaks = load_peaks()
+    ctx = Ctx(args)
     if args.kernels_only:
-        with torch.no_grad():
-            kr = kernel_rooflines(cfg, device, peaks)
+        peaks = load_peaks()
+        peaks['tf32'] = None if os.environ.get('VOD_PROFILE') else measure_tf32_peak(ctx.device)
+        with torch.no_grad(), library_math(True):
+            kr = kernel_rooflines(CONFIGS['cfg3'] if cfg['family'] != 'selsa' else cfg, ctx.device, peaks)
         print(json.dumps({k: {kk: (round(vv, 6) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in kr.items()}))
         return
-    head = build_head(cfg, device)
-    metas = [dict(img_shape=IMG_SHAPE, scale_factor=(1., 1., 1., 1.))]
-    lib = vod._lib.load()
-
-    n_sets = 4
-    host_sets = [make_inputs(cfg, rank * 1000 + i, pinned=True) for i in range(n_sets)]
-    dev_sets = [(a.to(device), b.to(device)) for a, b in host_sets]
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(seconds):
-        if world == 1:
-            return seconds
-        t = torch.tensor([seconds], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    from lowlightenvironmentvideoobjectdetection_b200 import parallel
-    det_buf = torch.zeros(args.steps, 100, 6, device=device)
-    det_cnt = torch.zeros(args.steps, dtype=torch.int32, device=device)
-
-    def gather_detections():
-        # the path's only exchange: one all_gather of the fixed-shape per-frame detections (NCCL over NVLink)
-        parallel.gather_detections(det_buf, det_cnt, frames_per_rank=[args.steps] * world)
-
-    # ------------------------------------------------ static buffers + CUDA graph of one key-frame step
-    T, N = cfg['T'], cfg['N']
-    st_ref = torch.empty_like(dev_sets[0][0])                    # [T,512,38,63] reference maps (last = key frame)
-    st_props = torch.empty_like(dev_sets[0][1])                  # [T+1,N,4]
-    st_rois = torch.zeros(N, 5, device=device)                   # key-frame rois (batch index 0)
-    st_ref_rois = torch.zeros(T * N, 5, device=device)
-    st_ref_rois[:, 0] = torch.arange(T, device=device, dtype=torch.float32).repeat_interleave(N)
-
-    def load_inputs(ref_x, props_all, non_blocking=False):
-        st_ref.copy_(ref_x, non_blocking=non_blocking)
-        st_props.copy_(props_all, non_blocking=non_blocking)
-        st_rois[:, 1:] = st_props[T]
-        st_ref_rois[:, 1:] = st_props[:T].reshape(T * N, 4)
-
-    with torch.no_grad():
-        load_inputs(*dev_sets[0])
-        x_key = st_ref[T - 1:T]
-        l0 = lib.vod_kernel_launch_count()
-        graph, (g_dets, g_labels, g_count) = head.capture_graph((x_key,), (st_ref,), st_rois, st_ref_rois, IMG_SHAPE,
-                                                                (1., 1., 1., 1.), rescale=False, warmup=2)
-        launches_per_step = (lib.vod_kernel_launch_count() - l0) // 3   # 2 warm-ups + 1 capture
-
-        def graph_step(i, src, non_blocking=False):
-            load_inputs(*src, non_blocking=non_blocking)
-            graph.replay()
-            det_buf[i, :, :5] = g_dets
-            det_buf[i, :, 5] = g_labels.float()
-            det_cnt[i:i + 1] = g_count
-
-        # ------------------------------------------------ device-resident throughput (graph replay)
-        # the clock sampler starts before the warm-up: NVML's first queries take tens of ms and serialise with the CUDA
-        # driver (seen as a 30 ms stall of the first timed replays at 8 ranks); only samples taken after e0 are reported
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        for i in range(args.warmup):
-            graph_step(0, dev_sets[i % n_sets])
-        gather_detections()   # warm the collective (communicator / channel setup is not part of a steady-state step)
-        barrier()
-        sampler.first, sampler.reasons = len(sampler.samples), set()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(args.steps):
-            graph_step(i, dev_sets[i % n_sets])
-        gather_detections()
-        e1.record()
-        barrier()
-        sampler.stop_flag = True
-        launches = launches_per_step * args.steps
-        t_dev = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
-
-        # ------------------------------------------------ end to end: pinned host inputs in, detections out
-        h2d = host_sets[0][0].numel() * 4 + host_sets[0][1].numel() * 4
-        d2h = 100 * 6 * 4 + 4
-        out_host = torch.empty(100, 6).pin_memory()
-        cnt_host = torch.empty(1, dtype=torch.int32).pin_memory()
-        # The next frame's host->device copy runs on a copy stream into a staging buffer while the current frame's
-        # graph executes (double-buffered); every frame's inputs still cross PCIe inside the timed region.
-        copy_stream = torch.cuda.Stream()
-        stage = [(torch.empty_like(st_ref), torch.empty_like(st_props)) for _ in range(2)]
-        staged = [torch.cuda.Event() for _ in range(2)]
-        consumed = [torch.cuda.Event() for _ in range(2)]
-
-        def prefetch(i):
-            a, b = host_sets[i % n_sets]
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(consumed[i % 2])
-                stage[i % 2][0].copy_(a, non_blocking=True)
-                stage[i % 2][1].copy_(b, non_blocking=True)
-                staged[i % 2].record(copy_stream)
-
-        def e2e_loop(steps):
-            for ev in consumed:
-                ev.record()
-            prefetch(0)
-            for i in range(steps):
-                if i + 1 < steps:
-                    prefetch(i + 1)
-                torch.cuda.current_stream().wait_event(staged[i % 2])
-                graph_step(i, stage[i % 2])
-                consumed[i % 2].record()
-                out_host.copy_(det_buf[i], non_blocking=True)
-                cnt_host.copy_(det_cnt[i:i + 1], non_blocking=True)
-
-        e2e_loop(2)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        e2e_loop(args.steps)
-        gather_detections()
-        e1.record()
-        barrier()
-        t_e2e = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
-
-        # ------------------------------------------------ the eager (un-graphed) module API, for reference
-        for i in range(2):
-            run_step(head, *dev_sets[i % n_sets], metas)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(args.steps):
-            run_step(head, *dev_sets[i % n_sets], metas)
-        e1.record()
-        barrier()
-        t_eager = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
-
-    frames = args.steps * world
-    result = {
-        'metric': metric, 'value': frames / t_dev, 'unit': unit, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': 1e3 * t_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'tf32', 'data': 'synthetic', 'config': config,
-        'e2e': {'value': frames / t_e2e, 'unit': unit, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
-        'gpu_launches': int(launches), 'clocks': sampler.summary(),
-        'eager_api': {'value': frames / t_eager, 'unit': unit,
-                      'note': 'SelsaRoIHead.simple_test called eagerly (variable-length outputs, one host read of the detection count per frame)'},
-    }
-    if rank == 0 and not args.no_roofline:
-        with torch.no_grad():
-            kr = kernel_rooflines(cfg, device, peaks)
-        # the dominant kernel of THE TIMED STEP: composites (msra_topk_sample), alternates (NCHW-output RoIAlign) and the
-        # kernels of the other detectors' shapes (FGFA/DFF T=31, RPN NMS), which the table also lists, do not qualify
-        in_step = ('roi_align_refs', 'msra_gemm_topk_kernel', 'tafa_keyproj_logits', 'tafa_weighted_sum_logits', 'selsa_attention',
-                   'batched_nms_rcnn')
-        single = {k: v for k, v in kr.items() if k in in_step}
-        dom = max(single, key=lambda k: single[k]['seconds'])
-        r = kr[dom]
-        result['roofline'] = {'kernel': dom, 'bound': r['bound'], 'achieved': r['achieved'], 'peak': r['peak'], 'unit': r['unit'],
-                              'frac': r['frac'], 'traffic': r.get('traffic'), 'peak_source': peaks['src'] + ' (burst: kernel timed alone)'}
-        result['kernels'] = {k: {kk: (round(vv, 6) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in kr.items()}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        times, cores = time_cpu(cfg, 1, 0)
-        result['cpu_baseline'] = {'value': 1.0 / times[0], 'unit': unit, 'cores': cores, 'kind': 'port',
-                                  'sample': '1 key frame of the same workload (%.1f s) on the host cores: torch CPU + C/OpenMP oracle' % times[0]}
-    if world > 1:
-        barrier()
-        dist.destroy_process_group()
-    if rank == 0:
-        print(json.dumps(result))
+    fam = cfg['family']
+    if fam == 'selsa':
+        result = bench_selsa(ctx, cfg, args.config)
+    elif fam == 'sweep':
+        result = bench_sweep(ctx, cfg)
+    elif fam == 'fgfa':
+        result = bench_fgfa(ctx, cfg)
+    else:
+        result = bench_dff(ctx, cfg)
+    ctx.close()
+    if ctx.rank == 0:
+        line = json.dumps(result)
+        print(line)
+        if args.out:
+            with open(args.out, 'w') as f:
+                f.write(line + '\n')
 
 
 if __name__ == '__main__':

@@ -78,6 +78,11 @@ int vod_roi_align_fwd(const float *feat_nhwc, const float *rois, float *out, int
  */
 int vod_flow_warp(const float *x, const float *flow, float *out, int N, int C, int H, int W, int Hf,
                   int Wf, vod_stream_t stream);
+/* Same with x [x_frames,C,H,W], x_frames = N or 1: with 1 every flow warps the SAME map in one launch -- the non-key frames
+ * of a DFF key interval all warp the key frame's features (mmtracking/mmtrack/models/vid/dff.py:210-216 runs them one frame
+ * at a time). */
+int vod_flow_warp_shared(const float *x, const float *flow, float *out, int N, int x_frames, int C, int H,
+                         int W, int Hf, int Wf, vod_stream_t stream);
 /* key_emb [1,C,H,W], ref_emb [T,C,H,W], ref_x [T,Cx,H,W] -> out [1,Cx,H,W]:
  * cosine(key_emb, ref_emb[t]) over C, softmax over t, weighted sum of ref_x.
  * replaces: the weighting half of EmbedAggregator.forward,

@@ -6,8 +6,8 @@ kernels from libvodagg.so through a C ABI (include/vodagg.h).  No Triton, no bac
 from . import _lib, ops  # noqa: F401
 from ._lib import VodError  # noqa: F401
 from .aggregators import EmbedAggregator, SelsaAggregator  # noqa: F401
-from .heads import SelsaBBoxHead, SelsaRoIHead  # noqa: F401
-from .motion import flow_warp_feats  # noqa: F401
+from .heads import RefFrameCache, SelsaBBoxHead, SelsaRoIHead, Shared2FCBBoxHead, StandardRoIHead  # noqa: F401
+from .motion import DFFFeatureMemo, flow_warp_feats, flow_warp_feats_shared  # noqa: F401
 from .ops import RoIAlign, batched_nms, nms, roi_align  # noqa: F401
 from .post_processing import (bbox2roi, delta2bbox, multiclass_nms, rpn_batched_nms, rpn_get_bboxes,  # noqa: F401
                               rpn_get_bboxes_device)

@@ -78,14 +78,15 @@ constexpr int kWarpCh = 64;     // channels per CTA
 // grid (pixel blocks, channel chunks, N)
 __global__ void __launch_bounds__(kWarpPix)
 flow_warp_kernel(const float *__restrict__ x, const float *__restrict__ flow, float *__restrict__ out, int C,
-                 int H, int W, int Hf, int Wf, float s, float inv_s) {
+                 int H, int W, int Hf, int Wf, float s, float inv_s, int x_frames) {
     const int n = blockIdx.z;
     const int p = blockIdx.x * kWarpPix + threadIdx.x;
     const int HW = H * W;
     if (p >= HW) return;
     const Taps t = make_taps(flow + (size_t)n * 2 * Hf * Wf, p / W, p % W, H, W, Hf, Wf, s, inv_s);
     const int c0 = blockIdx.y * kWarpCh, c1 = min(C, c0 + kWarpCh);
-    const float *xp = x + ((size_t)n * C + c0) * HW;
+    // x_frames == 1: every flow warps the SAME map (DFF: the non-key frames of an interval share the key frame's features)
+    const float *xp = x + ((size_t)(x_frames == 1 ? 0 : n) * C + c0) * HW;
     float *op = out + ((size_t)n * C + c0) * HW + p;
     int c = c0;
     for (; c + 4 <= c1; c += 4) {
@@ -298,17 +299,23 @@ static void flow_scale(int W, int Wf, float &s, float &inv_s) {
 
 using namespace vod;
 
-extern "C" int vod_flow_warp(const float *x, const float *flow, float *out, int N, int C, int H, int W, int Hf,
-                             int Wf, vod_stream_t stream) {
+extern "C" int vod_flow_warp_shared(const float *x, const float *flow, float *out, int N, int x_frames, int C, int H, int W,
+                                    int Hf, int Wf, vod_stream_t stream) {
     if (N == 0 || C == 0) return VOD_OK;
     VOD_REQUIRE(x && flow && out, "vod_flow_warp: null pointer");
     VOD_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && Hf > 0 && Wf > 0, "vod_flow_warp: bad dims");
     VOD_REQUIRE(N <= 65535, "vod_flow_warp: N too large");
+    VOD_REQUIRE(x_frames == 1 || x_frames == N, "vod_flow_warp: x must hold 1 (shared) or N=%d maps, got %d", N, x_frames);
     float s, inv_s;
     flow_scale(W, Wf, s, inv_s);
     dim3 grid(ceil_div(H * W, kWarpPix), ceil_div(C, kWarpCh), N);
-    flow_warp_kernel<<<grid, kWarpPix, 0, as_stream(stream)>>>(x, flow, out, C, H, W, Hf, Wf, s, inv_s); note_launch();
+    flow_warp_kernel<<<grid, kWarpPix, 0, as_stream(stream)>>>(x, flow, out, C, H, W, Hf, Wf, s, inv_s, x_frames); note_launch();
     return check_launch("vod_flow_warp");
+}
+
+extern "C" int vod_flow_warp(const float *x, const float *flow, float *out, int N, int C, int H, int W, int Hf,
+                             int Wf, vod_stream_t stream) {
+    return vod_flow_warp_shared(x, flow, out, N, N, C, H, W, Hf, Wf, stream);
 }
 
 static int launch_embed(bool fused, const float *key_emb, const float *ref_emb, const float *ref_x,

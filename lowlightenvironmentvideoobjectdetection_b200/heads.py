@@ -46,7 +46,8 @@ class SelsaBBoxHead(nn.Module):
             last = fc_out_channels
         self.fc_cls = nn.Linear(last, num_classes + 1)
         self.fc_reg = nn.Linear(last, 4 if reg_class_agnostic else 4 * num_classes)
-        self.aggregator = nn.ModuleList([build_aggregator(aggregator) for _ in range(num_shared_fcs)])
+        if aggregator is not None:
+            self.aggregator = nn.ModuleList([build_aggregator(aggregator) for _ in range(num_shared_fcs)])
         self._fc0_cl = None   # (weight version, weight columns re-ordered for channels_last RoI features)
         self.init_weights()
 
@@ -169,6 +170,70 @@ class SelsaBBoxHead(nn.Module):
                                           cfg['score_thr'], reg_class_agnostic=self.reg_class_agnostic)
         return ops.multiclass_nms_device(*cand, thr, cfg['max_per_img'], split_thr=nms_cfg.pop('split_thr', 10000),
                                          class_agnostic=nms_cfg.pop('class_agnostic', False))
+
+
+@HEADS.register_module()
+class Shared2FCBBoxHead(SelsaBBoxHead):
+    """mmdet's Shared2FCBBoxHead (mmdetection/mmdet/models/roi_heads/bbox_heads/convfc_bbox_head.py:85-124,172-182): the bbox
+    head of the FGFA / DFF detectors -- ``num_shared_fcs`` FC + ReLU layers, then fc_cls / fc_reg.  A caller
+    of the hot path like SelsaBBoxHead: FCs stay nn.Linear; ``get_bboxes`` / ``get_bboxes_device`` (fused decode + device NMS)
+    are inherited.  State-dict keys: shared_fcs.{i}, fc_cls, fc_reg."""
+
+    def __init__(self, num_shared_fcs=2, in_channels=512, fc_out_channels=1024, roi_feat_size=7, num_classes=30, **kwargs):
+        kwargs.pop('aggregator', None)
+        super().__init__(aggregator=None, num_shared_fcs=num_shared_fcs, in_channels=in_channels,
+                         fc_out_channels=fc_out_channels, roi_feat_size=roi_feat_size, num_classes=num_classes, **kwargs)
+
+    @torch.no_grad()
+    def forward(self, x):
+        x, cl = self._flatten(x)
+        for i, fc in enumerate(self.shared_fcs):
+            x = F.relu(F.linear(x, self._fc0_weight(cl) if i == 0 else fc.weight, fc.bias))
+        return self.fc_cls(x), self.fc_reg(x)
+
+
+@HEADS.register_module()
+class StandardRoIHead(nn.Module):
+    """mmdet StandardRoIHead, bbox branch, test path (mmdetection/mmdet/models/roi_heads/standard_roi_head.py:
+    simple_test -> test_mixins.py:simple_test_bboxes): RoIAlign of the proposals on the (aggregated / warped) feature map,
+    the bbox head, get_bboxes + multiclass NMS.  What FGFA and DFF run after their feature-level aggregation."""
+
+    def __init__(self, bbox_roi_extractor, bbox_head, test_cfg=None, **kwargs):
+        super().__init__()
+        self.bbox_roi_extractor = build_roi_extractor(bbox_roi_extractor)
+        head_cfg = dict(bbox_head)
+        head_cfg.setdefault('type', 'Shared2FCBBoxHead')
+        if 'bbox_coder' in head_cfg:
+            coder = head_cfg.pop('bbox_coder')
+            head_cfg.setdefault('target_means', coder.get('target_means', (0., 0., 0., 0.)))
+            head_cfg.setdefault('target_stds', coder.get('target_stds', (0.2, 0.2, 0.2, 0.2)))
+        self.bbox_head = HEADS.build(head_cfg)
+        for layer in self.bbox_roi_extractor.roi_layers:
+            layer.channels_last_out = True
+        self.test_cfg = test_cfg or dict(score_thr=0.0001, nms=dict(type='nms', iou_threshold=0.5), max_per_img=100)
+
+    @torch.no_grad()
+    def simple_test_device(self, x, rois, img_shape, scale_factor, rescale=False):
+        """One image, fixed shapes, sync-free: (dets [max,5], labels [max], count [1])."""
+        n_in = self.bbox_roi_extractor.num_inputs
+        feats = self.bbox_roi_extractor(x[:n_in], rois)
+        cls_score, bbox_pred = self.bbox_head(feats)
+        return self.bbox_head.get_bboxes_device(rois, cls_score, bbox_pred, img_shape, scale_factor, rescale=rescale,
+                                                cfg=self.test_cfg)
+
+    @torch.no_grad()
+    def simple_test(self, x, proposal_list, img_metas, proposals=None, rescale=False):
+        dets, labels = [], []
+        for i, props in enumerate(proposal_list):
+            rois = bbox2roi([props])
+            if rois.shape[0] == 0:
+                dets.append(rois.new_zeros((0, 5))); labels.append(rois.new_zeros((0,), dtype=torch.long))
+                continue
+            feat = tuple(f[i:i + 1] for f in x)
+            d, l, c = self.simple_test_device(feat, rois, img_metas[i]['img_shape'], img_metas[i]['scale_factor'], rescale)
+            n = int(c)
+            dets.append(d[:n]); labels.append(l[:n])
+        return dets, labels
 
 
 @HEADS.register_module()

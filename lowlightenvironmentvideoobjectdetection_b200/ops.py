@@ -302,12 +302,15 @@ def rpn_decode_topk(topk_idx, deltas, anchors, img_shape=None, wh_ratio_clip=16 
 
 # ----------------------------------------------------------------------------- (2) warp / FGFA weighting
 def flow_warp(x, flow):
+    """x [N,C,H,W] (or [1,C,H,W]: one map shared by all N flows), flow [N,2,Hf,Wf] -> [N,C,H,W]."""
     _lib.require_cuda(x, flow)
     x, flow = _f32c(x), _f32c(flow)
-    N, C, H, W = x.shape
-    out = torch.empty_like(x)
-    if x.numel():
-        _lib.call('vod_flow_warp', _lib.ptr(x), _lib.ptr(flow), _lib.ptr(out), N, C, H, W, flow.shape[2],
+    Nx, C, H, W = x.shape
+    N = flow.shape[0]
+    assert Nx in (1, N)
+    out = torch.empty((N, C, H, W), dtype=torch.float32, device=x.device)
+    if out.numel():
+        _lib.call('vod_flow_warp_shared', _lib.ptr(x), _lib.ptr(flow), _lib.ptr(out), N, Nx, C, H, W, flow.shape[2],
                   flow.shape[3], _lib.stream_ptr(x.device))
     return out
 

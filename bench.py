@@ -603,6 +603,9 @@ class SelsaRunner:
         self.vod, self.ctx, self.cfg = vod, ctx, cfg
         dev = ctx.device
         self.head = build_head(cfg, dev)
+        if ctx.args.no_overlap:
+            self.head.overlap = False
+            self.head.bbox_roi_extractor.overlap = False
         self.lib = vod._lib.load()
         self.n_sets = n_sets
         self.host_sets = [make_inputs(cfg, ctx.rank * 1000 + i, pinned=pinned) for i in range(n_sets)]
@@ -845,22 +848,32 @@ def bench_selsa(ctx, cfg, cfg_name):
             sd = {k: v.detach() for k, v in run.head.state_dict().items()}
             ref_head = reference_head(cfg, sd, device)
             rois_sets = [step_rois(cfg, b) for _, b in run.dev_sets]
-            with torch.no_grad(), library_math(True):
+            # (torch.device context: the reference's bbox_nms.py:44 creates its label tensor without a device and relies on mmcv's
+            # idxs.to(boxes); under torch 2.x indexing a CPU tensor with CUDA indices raises, so new tensors default to the GPU here)
+            with torch.no_grad(), torch.device(device):
                 def ref_loop(k):
                     for i in range(k):
                         a = run.dev_sets[i % n_sets][0]
                         ref_head.step(a[T - 1:], a, rois_sets[i % n_sets][0], rois_sets[i % n_sets][1], IMG_SHAPE)
-                ref_loop(2)
                 k_ref = max(3, min(args.steps, 10))
+                # PyTorch's default math flags (fp32 matmul, tf32 cuDNN convs): what a user of the reference gets out of the box
+                torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = False, True
+                ref_loop(2)
                 t_ref = ctx.timed(lambda: ref_loop(k_ref))
-                outs = ref_head.step(run.dev_sets[0][0][T - 1:], run.dev_sets[0][0], rois_sets[0][0], rois_sets[0][1], IMG_SHAPE, return_all=True)
-                ours = gpu_step_outputs(run.head, cfg, *run.dev_sets[0])
+                with library_math(True):       # and with tf32 matmuls switched on, the library math of our headline number
+                    ref_loop(2)
+                    t_ref_tf32 = ctx.timed(lambda: ref_loop(k_ref))
+                with library_math(False):      # parity in fp32 (tf32 similarities reshuffle the reference's own top-k picks)
+                    outs = ref_head.step(run.dev_sets[0][0][T - 1:], run.dev_sets[0][0], rois_sets[0][0], rois_sets[0][1], IMG_SHAPE, return_all=True)
+                    ours = gpu_step_outputs(run.head, cfg, *run.dev_sets[0])
             outs = {k: v.float().cpu() if v.is_floating_point() else v.cpu() for k, v in outs.items()}
             result['eager_cuda_reference'] = {
                 'value': k_ref / t_ref, 'unit': UNIT, 'ms_per_step': 1e3 * t_ref / k_ref, 'steps': k_ref,
+                'value_tf32_matmul': k_ref / t_ref_tf32, 'ms_per_step_tf32_matmul': 1e3 * t_ref_tf32 / k_ref,
                 'note': 'the reference\'s own TemporalRoIAlign / SelsaAggregator / multiclass_nms files (oracle/_ref) in torch eager on this '
-                        'GPU, mmcv ops = torchvision CUDA ops, tf32 library math as in the headline; tools/benchmark.py:72-98 protocol',
-                'parity_of_ours_against_it': parity_report(ours, outs)}
+                        'GPU, mmcv ops = torchvision CUDA ops; value: PyTorch default math flags (fp32 matmul, tf32 cuDNN), '
+                        'value_tf32_matmul: tf32 matmuls as in our headline; tools/benchmark.py:72-98 protocol',
+                'parity_of_ours_against_it_fp32': parity_report(ours, outs)}
             del ref_head
         except Exception as e:   # a comparator must never take the benchmark down
             result['eager_cuda_reference'] = {'unavailable': '%s: %s' % (type(e).__name__, str(e)[:200])}
@@ -1224,6 +1237,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-roofline', action='store_true')
     ap.add_argument('--no-eager-reference', action='store_true')
+    ap.add_argument('--no-overlap', action='store_true', help='single-stream execution (A/B of the two-stream overlap)')
     ap.add_argument('--kernels-only', action='store_true', help='run only the per-kernel roofline pass (ncu target)')
     ap.add_argument('--out', default=None, help='also write the JSON line to this file')
     args = ap.parse_args()

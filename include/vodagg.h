@@ -97,11 +97,13 @@ int vod_embed_weighted_sum(const float *key_emb, const float *ref_emb, const flo
 /* Same weighting, but the weighted operand is re-warped on the fly from the raw
  * feature memory + flows (the warped tensor is never re-read); slot `key_slot`
  * (or -1) uses key_x un-warped, as FGFA does at mmtracking/mmtrack/models/vid/fgfa.py:277-282.
+ * ws (nullable): >= T*H*W*4 bytes of scratch, as for vod_embed_weighted_sum: with it the op runs as two machine-filling
+ *   kernels (cosines, then softmax + weighted sum of the on-the-fly warp).
  */
 int vod_fgfa_warp_weighted_sum(const float *key_emb, const float *ref_emb, const float *raw_x,
                                const float *flow, const float *key_x, int key_slot, float *out,
-                               int T, int C, int Cx, int H, int W, int Hf, int Wf,
-                               vod_stream_t stream);
+                               int T, int C, int Cx, int H, int W, int Hf, int Wf, void *ws,
+                               size_t ws_bytes, vod_stream_t stream);
 
 /* ------------------------------------------------------ (3) SELSA aggregation
  * Per-head softmax(Q K^T * scale) V.  q [N, heads*d], k [M, heads*d] row-major

@@ -33,7 +33,7 @@ SIGNATURES = {
     'vod_flow_warp': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     'vod_flow_warp_shared': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     'vod_embed_weighted_sum': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _SZ, _P]),
-    'vod_fgfa_warp_weighted_sum': (_I, [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'vod_fgfa_warp_weighted_sum': (_I, [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _SZ, _P]),
     'vod_selsa_attn_workspace_bytes': (_SZ, [_I, _I, _I, _I]),
     'vod_selsa_attn': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _I, _I, _I, _P, _SZ, _P]),
     'vod_msra_workspace_bytes': (_SZ, [_I, _I, _I, _I, _I]),

@@ -50,8 +50,13 @@ def _digest():
     return h.hexdigest()
 
 
-def build_library(force=False, verbose=False):
-    """Compile every .cu for sm_100a and link libvodagg.so. Returns the library path."""
+def build_library(force=False, verbose=False, probes=False):
+    """Compile every .cu for sm_100a and link libvodagg.so. Returns the library path.
+
+    ``probes=True`` (``python -m ...build --probes``): an experiment build with -DVOD_PROBES (environment-selected kernel variants
+    and probe hooks) written to libvodagg_probes.so; the production library never reads the environment."""
+    if probes:
+        return _build_probes(verbose)
     stamp = os.path.join(_HERE, '_build', 'stamp')
     digest = _digest()
     if (not force and os.path.exists(LIB_PATH) and os.path.exists(stamp)
@@ -81,5 +86,27 @@ def build_library(force=False, verbose=False):
     return LIB_PATH
 
 
+def _build_probes(verbose=False):
+    nvcc, cxx = _nvcc(), _host_cxx()
+    obj_dir = os.path.join(_HERE, '_build', 'obj_probes')
+    os.makedirs(obj_dir, exist_ok=True)
+    out = os.path.join(_HERE, 'libvodagg_probes.so')
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, src.replace('.cu', '.o'))
+        r = subprocess.run([nvcc, '-ccbin', cxx] + NVCC_FLAGS + ['-DVOD_PROBES', '-c', os.path.join(CSRC, src), '-o', obj],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError('nvcc failed for %s:\n%s\n%s' % (src, r.stdout, r.stderr))
+        return obj
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    r = subprocess.run([nvcc, '-ccbin', cxx, '-shared', '-o', out] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a'],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))
+    return out
+
+
 if __name__ == '__main__':
-    print(build_library(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    print(build_library(force='--force' in sys.argv, verbose='-v' in sys.argv, probes='--probes' in sys.argv))

@@ -9,6 +9,9 @@ constexpr int kMsraCand = 16;     // candidates per (row, frame) kept by the ten
 // A candidate is re-scored in fp32 when its bf16-GEMM similarity is within this margin of the 2nd best one.
 // bf16 operand rounding gives an error of ~1e-4 (sigma) on unit vectors, the 20-bit key truncation < 3.5e-4.
 constexpr float kMsraMargin = 2.5e-3f;
+// Bound used on |bf16-GEMM key value - exact fp32 similarity| when a full candidate list is tested against the EXACT k-th best
+// similarity (overflow detection): half the re-score margin (3 key quanta: 2.4e-4 of key rounding + 12 sigma of bf16 noise).
+constexpr float kMsraKeyErr = 1.5e-3f;
 
 int msra_launch_scan(const float *roi, const float *ref, const float *roi_norm, const float *ref_norm, float *out,
                      int *idx_out, float *val_out, int NP, int C, int T, int HW, int k, cudaStream_t st);
@@ -34,7 +37,10 @@ struct MsraOvf {
     float4 *pair_top;   // [NP*T] the re-scored exact top-2 of the pair: (v0, bits(l0), v1, bits(l1))
     int2 *bin_list;     // [4*T][NP] (row, pair slot) of the pairs whose group g of frame t overflowed
     float4 *ovf_top;    // [NP*T][4] exact top-2 of group g of pair slot `pos`, written by the scan kernel
+    int *done;          // [kMsraOvfSplitChunks] arrival counters of the location-split scan (zeroed with ctrl)
+    float4 *split_top;  // [kMsraOvfSplitChunks][8 splits][8 rows] partial top-2 of a location slice
 };
+constexpr int kMsraOvfSplitChunks = 512;   // a short work list is scanned by up to 8 CTAs per item (latency); longer lists are not split
 int msra_overflow_fix(const float *roi, const float *ref, const float *roi_norm, const float *ref_norm, const MsraOvf &o,
                       float *out, int *idx_out, float *val_out, int NP, int C, int T, int HW, int k, cudaStream_t st);
 

@@ -276,7 +276,7 @@ using namespace vod;
 
 namespace {
 struct MsraWs {
-    size_t roi_norm, ref_norm, roi_unit, ref_unit, cand, ovf_ctrl, ovf_pairs, ovf_top2, ovf_bins, ovf_scan, bytes;
+    size_t roi_norm, ref_norm, roi_unit, ref_unit, cand, ovf_ctrl, ovf_ctrl_ints, ovf_pairs, ovf_top2, ovf_bins, ovf_scan, ovf_split, bytes;
 };
 MsraWs msra_ws(int NP, int C, int T, int HW) {
     MsraWs w;
@@ -288,7 +288,9 @@ MsraWs msra_ws(int NP, int C, int T, int HW) {
     w.cand = o;     o = align_up(o + sizeof(int) * (size_t)NP * T * kMsraCand, 256);
     // overflow work lists of the exact-by-construction top-k (msra.cuh): sized for the worst case, every pair flagged
     const size_t pairs = (size_t)NP * T;
-    w.ovf_ctrl = o;  o = align_up(o + sizeof(int) * (1 + 4 * (size_t)T), 256);
+    w.ovf_ctrl_ints = 1 + 4 * (size_t)T + kMsraOvfSplitChunks;      // counters + the split scan's arrival counters: one memset
+    w.ovf_ctrl = o;  o = align_up(o + sizeof(int) * w.ovf_ctrl_ints, 256);
+    w.ovf_split = o; o = align_up(o + sizeof(float4) * kMsraOvfSplitChunks * 8 * 8, 256);
     w.ovf_pairs = o; o = align_up(o + sizeof(int4) * pairs, 256);
     w.ovf_top2 = o;  o = align_up(o + sizeof(float4) * pairs, 256);
     w.ovf_bins = o;  o = align_up(o + sizeof(int2) * 4 * pairs, 256);
@@ -350,9 +352,11 @@ extern "C" int vod_msra_topk_sample(const float *roi_feats, const float *ref_nhw
     ovf.pair_top = reinterpret_cast<float4 *>(wsb + w.ovf_top2);
     ovf.bin_list = reinterpret_cast<int2 *>(wsb + w.ovf_bins);
     ovf.ovf_top = reinterpret_cast<float4 *>(wsb + w.ovf_scan);
+    ovf.done = ovf.ctrl + 1 + 4 * (size_t)T;
+    ovf.split_top = reinterpret_cast<float4 *>(wsb + w.ovf_split);
     const bool fix = 4 * T <= 1024;    // (more frames than the fix-up kernels index: T > 256 never reaches here in practice)
     if (fix) {
-        cudaError_t e = cudaMemsetAsync(ovf.ctrl, 0, sizeof(int) * (1 + 4 * (size_t)T), st);
+        cudaError_t e = cudaMemsetAsync(ovf.ctrl, 0, sizeof(int) * w.ovf_ctrl_ints, st);
         if (e != cudaSuccess) return fail(VOD_E_LAUNCH, "vod_msra_topk_sample: memset: %s", cudaGetErrorString(e));
     }
     rc = msra_launch_rescore(roi_feats, ref_nhwc, roi_norm, rn, cand, kMsraCand, out, idx_out, val_out, NP, C, T, HW, k,

@@ -8,9 +8,9 @@
 // resolve those flags on the same stream, with fixed grids (CUDA-graph capturable; an empty work list costs two ~2 us launches):
 //
 //   msra_overflow_scan_kernel      work item = (frame t, location group g, up to 8 flagged RoI rows): exact fp32 similarity of
-//                                  those rows against EVERY location of the group (thread = location, the 8 normalised rows
-//                                  broadcast from shared memory, so a reference row is read once for 8 RoI rows), exact top-2
-//                                  per row -> ovf_top[pair][g]
+//                                  those rows against EVERY location of the group (warp = 4 locations per pass, lanes split the
+//                                  channels exactly as the re-score kernel does; a reference row is read once for 8 RoI rows),
+//                                  exact top-2 per row -> ovf_top[pair][g]
 //   msra_overflow_finalize_kernel  warp = flagged pair: merges the re-scored top-2 with the scanned groups' top-2
 //                                  (de-duplicated by location) and, if the selection changed, re-emits softmax + gather.
 //
@@ -28,16 +28,27 @@ constexpr int kOvfMaxC = 512;      // the tensor-core pass supports C <= 512
 constexpr int kOvfMaxBins = 1024;  // 4 * T, T <= 256
 static_assert(kOvfWarps == kOvfRows, "the block-level merge assigns one warp per row");
 
-template <int R>
-__global__ void __launch_bounds__(kOvfThreads)
+// warp = kOvfLB locations at a time; lane owns channels lane*4 + 128*i (the re-score kernel's mapping and arithmetic, so a
+// location both kernels evaluate gets the bit-identical similarity); the R x kOvfLB = 32 partial dot products of a pass are
+// reduced with ONE transposing butterfly (31 shuffles; lane k ends up with the complete sum k = row*4 + location) instead of
+// 32 five-step reductions.  Reading every reference row once for 8 RoI rows and every RoI row once for 4 locations keeps the
+// kernel FMA-bound: the first version (thread = location, rows of 2 KB per thread) was bound by L1 wavefronts at 100 us per
+// work item; this one takes ~15 us per item and ~60 us for the ~3400 items of the iid-noise benchmark input.
+constexpr int kOvfLB = 4;
+static_assert(kOvfRows * kOvfLB == 32, "one butterfly reduces rows x locations = 32 values");
+
+template <int NQ>
+__global__ void __launch_bounds__(kOvfThreads, 2)
 msra_overflow_scan_kernel(const float *__restrict__ roi, const float *__restrict__ ref, const float *__restrict__ roi_norm,
                           const float *__restrict__ ref_norm, const MsraOvf o, int NP, int C, int T, int HW) {
-    __shared__ __align__(16) float s_q[R * kOvfMaxC];
+    constexpr int R = kOvfRows, LB = kOvfLB, CP = 128 * NQ;     // CP: padded channel count
+    __shared__ __align__(16) float s_q[R * CP];
     __shared__ int s_prefix[kOvfMaxBins + 1];
     __shared__ int s_warp_sum[kOvfWarps];
     __shared__ float s_mv[kOvfWarps][R][2];
     __shared__ int s_ml[kOvfWarps][R][2];
     __shared__ int s_row[R], s_pos[R];
+    __shared__ int s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nb = 4 * T;
 
@@ -68,8 +79,12 @@ msra_overflow_scan_kernel(const float *__restrict__ roi, const float *__restrict
     }
     __syncthreads();
     const int total = s_prefix[nb];
+    // A short work list (real video: a handful of flagged pairs) would leave one CTA scanning 600 locations on its own -- 60 us
+    // of latency in every step.  Its locations are then split over up to 8 CTAs per item; the last slice to arrive merges.
+    const int S = (total > 0 && total <= kMsraOvfSplitChunks) ? min(8, max(1, (int)gridDim.x / total)) : 1;
 
-    for (int chunk = blockIdx.x; chunk < total; chunk += gridDim.x) {
+    for (int item = blockIdx.x; item < total * S; item += gridDim.x) {
+        const int chunk = item / S, split = item - chunk * S;
         // bin of this chunk: largest b with s_prefix[b] <= chunk
         int lo = 0, hi = nb;
         while (hi - lo > 1) {
@@ -86,56 +101,92 @@ msra_overflow_scan_kernel(const float *__restrict__ roi, const float *__restrict
             s_row[tid] = e.x; s_pos[tid] = e.y;
         }
         __syncthreads();
-        // normalised RoI rows, same arithmetic as the re-score kernels: x * (1 / |x|)
-        const int c4n = C >> 2;
-        for (int i = tid; i < R * c4n; i += kOvfThreads) {
-            const int r = i / c4n, cq = i - r * c4n, row = s_row[r];
+        // normalised RoI rows, same arithmetic as the re-score kernels: x * (1 / |x|); zero beyond C and for absent rows
+        for (int i = tid; i < R * (CP / 4); i += kOvfThreads) {
+            const int r = i / (CP / 4), cq = i - r * (CP / 4), row = s_row[r];
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row >= 0) {
+            if (row >= 0 && 4 * cq < C) {
                 const float qinv = 1.0f / __ldg(roi_norm + row);
                 v = ldg_f4(roi + (size_t)row * C + 4 * cq);
                 v.x *= qinv; v.y *= qinv; v.z *= qinv; v.w *= qinv;
             }
-            *reinterpret_cast<float4 *>(s_q + r * C + 4 * cq) = v;
+            *reinterpret_cast<float4 *>(s_q + r * CP + 4 * cq) = v;
         }
         __syncthreads();
 
-        float tv0[R], tv1[R]; int tl0[R], tl1[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) { tv0[r] = tv1[r] = -INFINITY; tl0[r] = tl1[r] = 0x7fffffff; }
+        // lane k = 4*row + location-in-pass keeps the running top-2 of ITS row over ITS quarter of the locations
+        float tv0 = -INFINITY, tv1 = -INFINITY;
+        int tl0 = 0x7fffffff, tl1 = 0x7fffffff;
         const int nloc = (HW - g + 3) >> 2;                // locations 4*i + g < HW
-        for (int i = tid; i < nloc; i += kOvfThreads) {
-            const int l = 4 * i + g;
-            const float rinv = 1.0f / __ldg(ref_norm + (size_t)t * HW + l);
-            const float *rp = ref + ((size_t)t * HW + l) * C;
-            float s[R];
+        const float *ref_t = ref + (size_t)t * HW * C;
+        for (int i0 = (split * kOvfWarps + warp) * LB; i0 < nloc; i0 += S * kOvfWarps * LB) {
+            float4 v[LB][NQ];
 #pragma unroll
-            for (int r = 0; r < R; ++r) s[r] = 0.f;
-#pragma unroll 4
-            for (int c = 0; c < C; c += 4) {
-                float4 v = ldg_f4(rp + c);
-                v.x *= rinv; v.y *= rinv; v.z *= rinv; v.w *= rinv;
+            for (int j = 0; j < LB; ++j) {
+                const int l = 4 * (i0 + j) + g;
+                const bool ok = i0 + j < nloc;
+                const float rinv = ok ? 1.0f / __ldg(ref_norm + (size_t)t * HW + l) : 0.f;
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const float4 q = *reinterpret_cast<const float4 *>(s_q + r * C + c);
-                    s[r] = fmaf(q.x, v.x, s[r]); s[r] = fmaf(q.y, v.y, s[r]);
-                    s[r] = fmaf(q.z, v.z, s[r]); s[r] = fmaf(q.w, v.w, s[r]);
+                for (int i = 0; i < NQ; ++i) {
+                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok && lane * 4 + 128 * i < C) x = ldg_f4(ref_t + (size_t)l * C + lane * 4 + 128 * i);
+                    x.x *= rinv; x.y *= rinv; x.z *= rinv; x.w *= rinv;
+                    v[j][i] = x;
                 }
             }
+            float acc[R * LB];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                // a thread visits its locations in increasing order: on equal similarity the earlier (smaller) location stays ahead
-                if (s[r] > tv0[r]) { tv1[r] = tv0[r]; tl1[r] = tl0[r]; tv0[r] = s[r]; tl0[r] = l; }
-                else if (s[r] > tv1[r]) { tv1[r] = s[r]; tl1[r] = l; }
+                float4 q[NQ];
+#pragma unroll
+                for (int i = 0; i < NQ; ++i) q[i] = *reinterpret_cast<const float4 *>(s_q + r * CP + lane * 4 + 128 * i);
+#pragma unroll
+                for (int j = 0; j < LB; ++j) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int i = 0; i < NQ; ++i) {
+                        s = fmaf(q[i].x, v[j][i].x, s); s = fmaf(q[i].y, v[j][i].y, s);
+                        s = fmaf(q[i].z, v[j][i].z, s); s = fmaf(q[i].w, v[j][i].w, s);
+                    }
+                    acc[r * LB + j] = s;
+                }
+            }
+            // transposing butterfly: after the step with offset o, a lane keeps the half of its values selected by its bit o;
+            // the additions pair the same lanes in the same order as warp_sum (xor 16, 8, 4, 2, 1)
+#pragma unroll
+            for (int o = 16, n = 16; o >= 1; o >>= 1, n >>= 1) {
+                const bool up = (lane & o) != 0;
+#pragma unroll
+                for (int k = 0; k < n; ++k) {
+                    const float keep = up ? acc[k + n] : acc[k];
+                    const float send = up ? acc[k] : acc[k + n];
+                    acc[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                }
+            }
+            const int j = lane & (LB - 1);
+            const float sres = acc[0];
+            if (i0 + j < nloc) {
+                const int l = 4 * (i0 + j) + g;
+                // a lane visits its locations in increasing order: on equal similarity the earlier (smaller) location stays ahead
+                if (sres > tv0) { tv1 = tv0; tl1 = tl0; tv0 = sres; tl0 = l; }
+                else if (sres > tv1) { tv1 = sres; tl1 = l; }
             }
         }
-        // warp-level merge of the 32 per-thread top-2 lists of every row, then one warp per row merges the 8 warps' results
+        // merge the 4 lanes of a row (xor 1, 2), then the 8 warps through shared memory, one warp per row
+        {
+            float v2[2] = {tv0, tv1};
+            int l2[2] = {tl0, tl1};
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            float v[2] = {tv0[r], tv1[r]};
-            int l[2] = {tl0[r], tl1[r]};
-            topk_warp_merge<2>(v, l, 2, lane);
-            if (lane == 0) { s_mv[warp][r][0] = v[0]; s_mv[warp][r][1] = v[1]; s_ml[warp][r][0] = l[0]; s_ml[warp][r][1] = l[1]; }
+            for (int o = 1; o <= 2; o <<= 1) {
+                const float ov0 = __shfl_xor_sync(0xffffffffu, v2[0], o), ov1 = __shfl_xor_sync(0xffffffffu, v2[1], o);
+                const int ol0 = __shfl_xor_sync(0xffffffffu, l2[0], o), ol1 = __shfl_xor_sync(0xffffffffu, l2[1], o);
+                topk_insert<2>(v2, l2, ov0, ol0);
+                topk_insert<2>(v2, l2, ov1, ol1);
+            }
+            if ((lane & 3) == 0) {
+                const int r = lane >> 2;
+                s_mv[warp][r][0] = v2[0]; s_mv[warp][r][1] = v2[1]; s_ml[warp][r][0] = l2[0]; s_ml[warp][r][1] = l2[1];
+            }
         }
         __syncthreads();
         if (warp < R) {
@@ -144,8 +195,32 @@ msra_overflow_scan_kernel(const float *__restrict__ roi, const float *__restrict
             int l[2] = {0x7fffffff, 0x7fffffff};
             if (lane < 2 * kOvfWarps) { v[0] = s_mv[lane >> 1][r][lane & 1]; l[0] = s_ml[lane >> 1][r][lane & 1]; }
             topk_warp_merge<2>(v, l, 2, lane);
-            if (lane == 0 && s_pos[r] >= 0)
-                o.ovf_top[(size_t)s_pos[r] * 4 + g] = make_float4(v[0], __int_as_float(l[0]), v[1], __int_as_float(l[1]));
+            if (lane == 0) {
+                const float4 res = make_float4(v[0], __int_as_float(l[0]), v[1], __int_as_float(l[1]));
+                if (S == 1) { if (s_pos[r] >= 0) o.ovf_top[(size_t)s_pos[r] * 4 + g] = res; }
+                else o.split_top[((size_t)chunk * 8 + split) * R + r] = res;
+            }
+        }
+        if (S > 1) {
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) s_last = atomicAdd(o.done + chunk, 1) == S - 1;
+            __syncthreads();
+            if (s_last) {
+                __threadfence();
+                if (warp < R) {
+                    const int r = warp;
+                    float v[2] = {-INFINITY, -INFINITY};
+                    int l[2] = {0x7fffffff, 0x7fffffff};
+                    if (lane < S) {
+                        const float4 e = __ldcg(o.split_top + ((size_t)chunk * 8 + lane) * R + r);
+                        v[0] = e.x; l[0] = __float_as_int(e.y); v[1] = e.z; l[1] = __float_as_int(e.w);
+                    }
+                    topk_warp_merge<2>(v, l, 2, lane);
+                    if (lane == 0 && s_pos[r] >= 0)
+                        o.ovf_top[(size_t)s_pos[r] * 4 + g] = make_float4(v[0], __int_as_float(l[0]), v[1], __int_as_float(l[1]));
+                }
+            }
         }
     }
 }
@@ -186,7 +261,12 @@ int msra_overflow_fix(const float *roi, const float *ref, const float *roi_norm,
     if (C > kOvfMaxC || (C & 3) || 4 * T > kOvfMaxBins || k > 2)
         return fail(VOD_E_UNSUPPORTED, "msra_overflow_fix: C=%d T=%d k=%d outside the tensor-core path's range", C, T, k);
     const int sms = num_sms();
-    msra_overflow_scan_kernel<kOvfRows><<<2 * sms, kOvfThreads, 0, st>>>(roi, ref, roi_norm, ref_norm, o, NP, C, T, HW);
+    switch ((C + 127) >> 7) {
+        case 1: msra_overflow_scan_kernel<1><<<2 * sms, kOvfThreads, 0, st>>>(roi, ref, roi_norm, ref_norm, o, NP, C, T, HW); break;
+        case 2: msra_overflow_scan_kernel<2><<<2 * sms, kOvfThreads, 0, st>>>(roi, ref, roi_norm, ref_norm, o, NP, C, T, HW); break;
+        case 3: msra_overflow_scan_kernel<3><<<2 * sms, kOvfThreads, 0, st>>>(roi, ref, roi_norm, ref_norm, o, NP, C, T, HW); break;
+        default: msra_overflow_scan_kernel<4><<<2 * sms, kOvfThreads, 0, st>>>(roi, ref, roi_norm, ref_norm, o, NP, C, T, HW); break;
+    }
     note_launch();
     int rc = check_launch("msra_overflow_scan");
     if (rc) return rc;

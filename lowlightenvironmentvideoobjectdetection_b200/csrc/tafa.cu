@@ -315,14 +315,16 @@ msra_rescore_kernel(const float *__restrict__ roi, const float *__restrict__ ref
 // The generic kernel above needed ~1300 warp instructions per (row, frame); this one ~300.
 constexpr int kRfFrames = 5;
 constexpr int kRfWarps = 4;
-template <int NQ>
+template <int NQ, bool TWO>
 __global__ void __launch_bounds__(kRfWarps * 32)
 msra_rescore_fast_kernel(const float *__restrict__ roi, const float *__restrict__ ref, const float *__restrict__ roi_norm,
                          const float *__restrict__ ref_norm, const uint32_t *__restrict__ cand,
                          float *__restrict__ out, int *__restrict__ idx_out, float *__restrict__ val_out, int NP,
                          int T, int HW, int k, int nchunks, const MsraOvf ovf) {
     constexpr int C = 128 * NQ;
+    __shared__ float4 s_rows[kRfWarps][2 * NQ * 32];      // per warp: two parked rows, [slot][i][lane]
     const int lane = threadIdx.x & 31;
+    float4 *my_rows = s_rows[threadIdx.x >> 5];
     const long task = (long)blockIdx.x * kRfWarps + (threadIdx.x >> 5);
     if (task >= (long)NP * nchunks) return;
     const int row = (int)(task / nchunks), t_begin = (int)(task % nchunks) * kRfFrames, t_end = min(T, t_begin + kRfFrames);
@@ -352,30 +354,76 @@ msra_rescore_fast_kernel(const float *__restrict__ roi, const float *__restrict_
         // overflow test per location group: its list is full (4th key, lanes 3/7/11/15, non-empty) and that key is within the margin
         const unsigned ovf_mask = ovf.ctrl ? msra_group_mask(todo & 0x8888u) : 0u;
         float v0 = -INFINITY, v1 = -INFINITY; int l0 = 0x7fffffff, l1 = 0x7fffffff;
+        // The RAW reference rows of the best / second best location so far are parked in this warp's two shared-memory slots,
+        // so the gather below does not fetch the two rows a second time (the kernel is L2-bandwidth bound: ~2 GB of L2 -> SM
+        // traffic for 555 MB of algorithmic bytes with the second fetch).  Shared memory, not registers: parking them in
+        // registers cost 80 registers and, at 12 resident warps per SM, ran 1.6x SLOWER than re-fetching.
+        int best_slot = 0;            // slot holding the best row; the other one holds the second best
         bool any_nan = false;
-        while (todo) {
-            const int j = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int l = min((int)(__shfl_sync(0xffffffffu, key, j) & 0xFFFu), HW - 1);
-            const float rinv = 1.0f / __ldg(ref_norm + (size_t)t * HW + l);
-            const float *r = ref_t + (size_t)l * C + lane * 4;
-            float4 v[NQ];
+        auto insert = [&](float s, int l, const float4 (&row)[NQ]) {
+            if (s != s) any_nan = true;               // torch.topk ranks NaN first: the reference row becomes NaN
+            if (s > v0 || (s == v0 && l < l0)) {
+                v1 = v0; l1 = l0; v0 = s; l0 = l;
+                best_slot ^= 1;                       // the old best becomes the second best; its slot-mate is overwritten
 #pragma unroll
-            for (int i = 0; i < NQ; ++i) v[i] = ldg_f4(r + 128 * i);
-            float s = 0.f;
+                for (int i = 0; i < NQ; ++i) my_rows[(best_slot * NQ + i) * 32 + lane] = row[i];
+            } else if (s > v1 || (s == v1 && l < l1)) {
+                v1 = s; l1 = l;
+#pragma unroll
+                for (int i = 0; i < NQ; ++i) my_rows[((best_slot ^ 1) * NQ + i) * 32 + lane] = row[i];
+            }
+        };
+        // candidates are re-scored two at a time: both rows (and both norms) are in flight before the first reduction
+        while (todo) {
+            const int j0 = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const bool two = TWO && todo != 0u;
+            const int j1 = two ? __ffs(todo) - 1 : j0;
+            if (two) todo &= todo - 1;
+            const int la = min((int)(__shfl_sync(0xffffffffu, key, j0) & 0xFFFu), HW - 1);
+            const int lb = min((int)(__shfl_sync(0xffffffffu, key, j1) & 0xFFFu), HW - 1);
+            const float *pa = ref_t + (size_t)la * C + lane * 4, *pb = ref_t + (size_t)lb * C + lane * 4;
+            float4 xa[NQ], xb[NQ];
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) xa[i] = ldg_f4(pa + 128 * i);
+            if (two) {
+#pragma unroll
+                for (int i = 0; i < NQ; ++i) xb[i] = ldg_f4(pb + 128 * i);
+            }
+            const float rinv_a = 1.0f / __ldg(ref_norm + (size_t)t * HW + la);
+            const float rinv_b = 1.0f / __ldg(ref_norm + (size_t)t * HW + lb);
+            float sa = 0.f, sb = 0.f;
 #pragma unroll
             for (int i = 0; i < NQ; ++i) {
-                s = fmaf(q[i].x, v[i].x * rinv, s); s = fmaf(q[i].y, v[i].y * rinv, s);
-                s = fmaf(q[i].z, v[i].z * rinv, s); s = fmaf(q[i].w, v[i].w * rinv, s);
+                sa = fmaf(q[i].x, xa[i].x * rinv_a, sa); sa = fmaf(q[i].y, xa[i].y * rinv_a, sa);
+                sa = fmaf(q[i].z, xa[i].z * rinv_a, sa); sa = fmaf(q[i].w, xa[i].w * rinv_a, sa);
             }
-            s = warp_sum(s);
-            if (s != s) any_nan = true;               // torch.topk ranks NaN first: the reference row becomes NaN
-            if (s > v0 || (s == v0 && l < l0)) { v1 = v0; l1 = l0; v0 = s; l0 = l; }
-            else if (s > v1 || (s == v1 && l < l1)) { v1 = s; l1 = l; }
+            if (two) {
+#pragma unroll
+                for (int i = 0; i < NQ; ++i) {
+                    sb = fmaf(q[i].x, xb[i].x * rinv_b, sb); sb = fmaf(q[i].y, xb[i].y * rinv_b, sb);
+                    sb = fmaf(q[i].z, xb[i].z * rinv_b, sb); sb = fmaf(q[i].w, xb[i].w * rinv_b, sb);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {       // two warp sums, interleaved (same pairing order as warp_sum)
+                sa += __shfl_xor_sync(0xffffffffu, sa, o);
+                sb += __shfl_xor_sync(0xffffffffu, sb, o);
+            }
+            insert(sa, la, xa);
+            if (two) insert(sb, lb, xb);
         }
         float *out_row = out + ((size_t)t * NP + row) * C + lane * 4;
         const bool bad = any_nan || l0 == 0x7fffffff || (k > 1 && l1 == 0x7fffffff);
-        if (ovf_mask && !any_nan && lane == 0) msra_flag_overflow(ovf, NP, row, t, ovf_mask, v0, l0, v1, l1);
+        if (ovf_mask && !any_nan) {
+            // Second look with the EXACT k-th best similarity now known: a location that fell off group g's full list has a key
+            // value <= the list's 4th key, so its exact similarity is below value(4th key) + kMsraKeyErr; the group needs the
+            // exact re-scan only if that bound reaches the k-th best.  (Cuts the flags on iid noise by ~2-3x.)
+            const float vk = k > 1 ? v1 : v0;
+            const float key_val = (float)(key >> 12) * (1.0f / 2048.0f) - 1.5f;
+            const unsigned still = msra_group_mask(__ballot_sync(0xffffffffu, want && (lane & 3) == 3 && !(key_val + kMsraKeyErr < vk)));
+            if (still && lane == 0) msra_flag_overflow(ovf, NP, row, t, still & ovf_mask, v0, l0, v1, l1);
+        }
         float w0 = 1.f, w1 = 0.f;
         if (k > 1) {
             const float e1 = expf(v1 - v0), sum = 1.0f + e1;   // softmax over the k values (temporal_roi_align.py:155)
@@ -391,16 +439,16 @@ msra_rescore_fast_kernel(const float *__restrict__ roi, const float *__restrict_
 #pragma unroll
             for (int i = 0; i < NQ; ++i) stg_cs_f4(out_row + 128 * i, make_float4(qnan, qnan, qnan, qnan));
         } else {
-            const float *r0 = ref_t + (size_t)l0 * C + lane * 4, *r1 = ref_t + (size_t)(k > 1 ? l1 : l0) * C + lane * 4;
-            float4 a[NQ], b[NQ];
-#pragma unroll
-            for (int i = 0; i < NQ; ++i) { a[i] = ldg_f4(r0 + 128 * i); b[i] = ldg_f4(r1 + 128 * i); }
 #pragma unroll
             for (int i = 0; i < NQ; ++i) {
                 // topk_feats * topk_weights summed over k (temporal_roi_align.py:170-172), same order as msra_emit
+                const float4 ra = my_rows[(best_slot * NQ + i) * 32 + lane];
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                acc.x += a[i].x * w0; acc.y += a[i].y * w0; acc.z += a[i].z * w0; acc.w += a[i].w * w0;
-                if (k > 1) { acc.x += b[i].x * w1; acc.y += b[i].y * w1; acc.z += b[i].z * w1; acc.w += b[i].w * w1; }
+                acc.x += ra.x * w0; acc.y += ra.y * w0; acc.z += ra.z * w0; acc.w += ra.w * w0;
+                if (k > 1) {
+                    const float4 rb = my_rows[((best_slot ^ 1) * NQ + i) * 32 + lane];
+                    acc.x += rb.x * w1; acc.y += rb.y * w1; acc.z += rb.z * w1; acc.w += rb.w * w1;
+                }
                 stg_cs_f4(out_row + 128 * i, acc);
             }
         }
@@ -430,11 +478,13 @@ int msra_launch_rescore(const float *roi, const float *ref, const float *roi_nor
         auto go = [&](auto kern) {
             kern<<<g, kRfWarps * 32, 0, st>>>(roi, ref, roi_norm, ref_norm, cand, out, idx_out, val_out, NP, T, HW, k, nchunks, ovf);
         };
+        // (two candidates in flight per pass -- msra_rescore_fast_kernel<NQ, true> -- measured 206 us against 197 us: the extra
+        // 20 registers cost more resident warps than the second row in flight buys)
         switch (C >> 7) {
-            case 1: go(msra_rescore_fast_kernel<1>); break;
-            case 2: go(msra_rescore_fast_kernel<2>); break;
-            case 3: go(msra_rescore_fast_kernel<3>); break;
-            default: go(msra_rescore_fast_kernel<4>); break;
+            case 1: go(msra_rescore_fast_kernel<1, false>); break;
+            case 2: go(msra_rescore_fast_kernel<2, false>); break;
+            case 3: go(msra_rescore_fast_kernel<3, false>); break;
+            default: go(msra_rescore_fast_kernel<4, false>); break;
         }
         note_launch();
         return check_launch("msra_rescore_fast");

@@ -25,9 +25,14 @@ __device__ __forceinline__ void resize_src(int dst, float inv_scale, int in_size
     l1 = src - (float)a;
 }
 
-// Taps of pixel (h, w) of frame n: resized+scaled flow -> normalised grid -> border-clamped bilinear.
-__device__ __forceinline__ Taps make_taps(const float *__restrict__ flow_n, int h, int w, int H, int W, int Hf,
-                                          int Wf, float s, float inv_s) {
+// Sampling position of pixel (h, w) of frame n: resized+scaled flow -> normalised grid -> border-clamped bilinear, as the base
+// plane offset, the steps to the east / south neighbours (0 at a clamped border) and the two lerp fractions.
+struct TapF {
+    int i00, dx, dy;
+    float tx, ty;
+};
+__device__ __forceinline__ TapF make_tap_frac(const float *__restrict__ flow_n, int h, int w, int H, int W, int Hf,
+                                              int Wf, float s, float inv_s) {
     int y0, y1, x0, x1;
     float ly, lx;
     resize_src(h, inv_s, Hf, y0, y1, ly);
@@ -49,18 +54,26 @@ __device__ __forceinline__ Taps make_taps(const float *__restrict__ flow_n, int 
     float py = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.0f), 2.0f), (float)(H - 1));
     px = fminf(fmaxf(px, 0.f), (float)(W - 1));
     py = fminf(fmaxf(py, 0.f), (float)(H - 1));
-    int ix0 = (int)floorf(px), iy0 = (int)floorf(py);
-    float tx = px - (float)ix0, ty = py - (float)iy0;
-    int ix1 = ix0 + 1, iy1 = iy0 + 1;
-    bool vx = ix1 <= W - 1, vy = iy1 <= H - 1;
-    if (!vx) ix1 = W - 1;
-    if (!vy) iy1 = H - 1;
+    const int ix0 = (int)floorf(px), iy0 = (int)floorf(py);
+    TapF t;
+    t.tx = px - (float)ix0; t.ty = py - (float)iy0;
+    // at the east / south border the neighbour is the pixel itself and the fraction is exactly 0 (px == W - 1): the products
+    // below then give the +0 weights the reference's clamped grid_sample produces
+    t.dx = ix0 + 1 <= W - 1 ? 1 : 0;
+    t.dy = iy0 + 1 <= H - 1 ? W : 0;
+    t.i00 = iy0 * W + ix0;
+    return t;
+}
+
+__device__ __forceinline__ Taps make_taps(const float *__restrict__ flow_n, int h, int w, int H, int W, int Hf,
+                                          int Wf, float s, float inv_s) {
+    const TapF f = make_tap_frac(flow_n, h, w, H, W, Hf, Wf, s, inv_s);
     Taps t;
-    t.i00 = iy0 * W + ix0; t.i01 = iy0 * W + ix1; t.i10 = iy1 * W + ix0; t.i11 = iy1 * W + ix1;
-    t.w00 = (1.0f - tx) * (1.0f - ty);
-    t.w01 = vx ? tx * (1.0f - ty) : 0.f;
-    t.w10 = vy ? (1.0f - tx) * ty : 0.f;
-    t.w11 = (vx && vy) ? tx * ty : 0.f;
+    t.i00 = f.i00; t.i01 = f.i00 + f.dx; t.i10 = f.i00 + f.dy; t.i11 = f.i00 + f.dy + f.dx;
+    t.w00 = (1.0f - f.tx) * (1.0f - f.ty);
+    t.w01 = f.dx ? f.tx * (1.0f - f.ty) : 0.f;
+    t.w10 = f.dy ? (1.0f - f.tx) * f.ty : 0.f;
+    t.w11 = (f.dx && f.dy) ? f.tx * f.ty : 0.f;
     return t;
 }
 
@@ -76,7 +89,9 @@ constexpr int kWarpPix = 128;   // pixels per CTA
 constexpr int kWarpCh = 64;     // channels per CTA
 
 // grid (pixel blocks, channel chunks, N)
-__global__ void __launch_bounds__(kWarpPix)
+// (min 16 CTAs per SM = 32 registers: the kernel lives on its 2048 resident threads; at 48 registers -- 1280 threads -- the
+// same code ran 117 us instead of 90 us at T = 31)
+__global__ void __launch_bounds__(kWarpPix, 16)
 flow_warp_kernel(const float *__restrict__ x, const float *__restrict__ flow, float *__restrict__ out, int C,
                  int H, int W, int Hf, int Wf, float s, float inv_s, int x_frames) {
     const int n = blockIdx.z;
@@ -289,6 +304,80 @@ embed_apply_kernel(const float *__restrict__ cosv, const float *__restrict__ ref
     }
 }
 
+// Fused form of the weighting (north_star (2): the flow-guided warp fused with the cosine weighting): the weighted operand is
+// the bilinear warp of the RAW feature memory, recomputed on the fly -- the warped tensor is not re-read.  Same tiling as
+// embed_apply_kernel (128 pixels x 16 channels, 512 threads); the (frame, pixel) taps are computed once per CTA into shared
+// memory in a compact 16-byte form (base offset, +1 / +W steps, the two lerp fractions: at a clamped border the fraction is
+// exactly 0, so plain bilinear weights reproduce make_taps' zeroed weights bit for bit).  The first fused kernel ran one CTA
+// per 8 pixels x all channels (300 CTAs, 10 % of DRAM bandwidth, 426 us at T = 31); this one is a machine-filling grid.
+struct TapC {
+    int i00, step;      // step: bit 0 = step to the east neighbour (0 / 1), bits 1.. = step to the south neighbour (0 / W)
+    float tx, ty;
+};
+
+__global__ void __launch_bounds__(kEaPix *kEaGroups)
+embed_apply_warp_kernel(const float *__restrict__ cosv, const float *__restrict__ raw_x, const float *__restrict__ flow,
+                        const float *__restrict__ key_x, int key_slot, float *__restrict__ out, int T, int Cx, int H, int W,
+                        int Hf, int Wf, float s, float inv_s) {
+    extern __shared__ float sm_dyn[];
+    const int HW = H * W;
+    float *wts = sm_dyn;                                             // [T][kEaPix]
+    TapC *taps = reinterpret_cast<TapC *>(wts + (size_t)T * kEaPix);  // [T][kEaPix]
+    const int pl = threadIdx.x % kEaPix, g = threadIdx.x / kEaPix;
+    const int p = blockIdx.x * kEaPix + pl;
+    const int pc = min(p, HW - 1);
+    if (g == 0) {
+        float m = -INFINITY;
+        for (int t = 0; t < T; ++t) { const float v = __ldg(cosv + (size_t)t * HW + pc); wts[t * kEaPix + pl] = v; m = fmaxf(m, v); }
+        float sum = 0.f;
+        for (int t = 0; t < T; ++t) { const float e = expf(wts[t * kEaPix + pl] - m); wts[t * kEaPix + pl] = e; sum += e; }
+        for (int t = 0; t < T; ++t) wts[t * kEaPix + pl] = wts[t * kEaPix + pl] / sum;
+    }
+    for (int t = g; t < T; t += kEaGroups) {
+        TapC c;
+        if (t == key_slot) {
+            c.i00 = pc; c.step = 0; c.tx = 0.f; c.ty = 0.f;          // the key frame's own slot is taken un-warped (fgfa.py:281)
+        } else {
+            const TapF tp = make_tap_frac(flow + (size_t)t * 2 * Hf * Wf, pc / W, pc % W, H, W, Hf, Wf, s, inv_s);
+            c.i00 = tp.i00; c.step = tp.dx | (tp.dy << 1);
+            c.tx = tp.tx; c.ty = tp.ty;
+        }
+        taps[t * kEaPix + pl] = c;
+    }
+    __syncthreads();
+    if (p >= HW) return;
+    const int c0 = blockIdx.y * kEaCh + g * kEaChPerGroup;
+    const size_t fs = (size_t)Cx * HW;   // frame stride
+    // the tap of a (frame, pixel) is fetched and its four weights are formed ONCE for the thread's kEaChPerGroup channels:
+    // 16 independent loads in flight per frame
+    float acc[kEaChPerGroup];
+    bool on[kEaChPerGroup];
+#pragma unroll
+    for (int q = 0; q < kEaChPerGroup; ++q) { acc[q] = 0.f; on[q] = c0 + q < Cx; }
+    for (int t = 0; t < T; ++t) {
+        const TapC tc = taps[t * kEaPix + pl];
+        const float w = wts[t * kEaPix + pl];
+        const float *b = (t == key_slot ? key_x : raw_x + (size_t)t * fs) + (size_t)c0 * HW + tc.i00;
+        const int dx = tc.step & 1, dy = tc.step >> 1;
+        const float w00 = (1.0f - tc.tx) * (1.0f - tc.ty), w01 = tc.tx * (1.0f - tc.ty);
+        const float w10 = (1.0f - tc.tx) * tc.ty, w11 = tc.tx * tc.ty;
+        float u00[kEaChPerGroup], u01[kEaChPerGroup], u10[kEaChPerGroup], u11[kEaChPerGroup];
+#pragma unroll
+        for (int q = 0; q < kEaChPerGroup; ++q) {
+            const float *bq = on[q] ? b + (size_t)q * HW : b;
+            u00[q] = __ldg(bq); u01[q] = __ldg(bq + dx); u10[q] = __ldg(bq + dy); u11[q] = __ldg(bq + dy + dx);
+        }
+#pragma unroll
+        for (int q = 0; q < kEaChPerGroup; ++q) {
+            float u = u00[q] * w00; u = fmaf(u01[q], w01, u); u = fmaf(u10[q], w10, u); u = fmaf(u11[q], w11, u);
+            acc[q] = fmaf(u, w, acc[q]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < kEaChPerGroup; ++q)
+        if (on[q]) __stcs(out + (size_t)(c0 + q) * HW + p, acc[q]);
+}
+
 static void flow_scale(int W, int Wf, float &s, float &inv_s) {
     double sd = (double)W / (double)Wf;  // python float scale_factor, flow.py:17
     s = (float)sd;
@@ -339,6 +428,20 @@ static int launch_embed(bool fused, const float *key_emb, const float *ref_emb, 
         note_launch();
         return check_launch("vod_embed_weighted_sum(2-kernel)");
     }
+    if (fused && ws && ws_bytes >= sizeof(float) * (size_t)T * H * W &&
+        (size_t)T * kEaPix * (sizeof(float) + sizeof(TapC)) <= 200 * 1024) {
+        // cosines per (frame, pixel), then softmax + weighted sum of the on-the-fly warp: two machine-filling kernels
+        const int HW = H * W;
+        float *cosv = reinterpret_cast<float *>(ws);
+        embed_cos_kernel<<<dim3(ceil_div(HW, kEcPix), T), kEcPix * kEcGroups, 0, as_stream(stream)>>>(key_emb, ref_emb, cosv, C, HW);
+        note_launch();
+        const size_t sm = (size_t)T * kEaPix * (sizeof(float) + sizeof(TapC));
+        if (sm > 40 * 1024) cudaFuncSetAttribute(embed_apply_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        embed_apply_warp_kernel<<<dim3(ceil_div(HW, kEaPix), ceil_div(Cx, kEaCh)), kEaPix * kEaGroups, sm, as_stream(stream)>>>(
+            cosv, ref_x, flow, key_x, key_slot, out, T, Cx, H, W, Hf, Wf, s, inv_s);
+        note_launch();
+        return check_launch("vod_fgfa_warp_weighted_sum(2-kernel)");
+    }
     if (fused) {
         if (smem > 40 * 1024)
             cudaFuncSetAttribute(embed_weighted_sum_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -360,8 +463,9 @@ extern "C" int vod_embed_weighted_sum(const float *key_emb, const float *ref_emb
 
 extern "C" int vod_fgfa_warp_weighted_sum(const float *key_emb, const float *ref_emb, const float *raw_x,
                                           const float *flow, const float *key_x, int key_slot, float *out, int T,
-                                          int C, int Cx, int H, int W, int Hf, int Wf, vod_stream_t stream) {
+                                          int C, int Cx, int H, int W, int Hf, int Wf, void *ws, size_t ws_bytes,
+                                          vod_stream_t stream) {
     VOD_REQUIRE(flow, "vod_fgfa_warp_weighted_sum: null flow");
     VOD_REQUIRE(key_slot < 0 || key_x, "vod_fgfa_warp_weighted_sum: key_x required with key_slot");
-    return launch_embed(true, key_emb, ref_emb, raw_x, flow, key_x, key_slot, out, T, C, Cx, H, W, Hf, Wf, nullptr, 0, stream);
+    return launch_embed(true, key_emb, ref_emb, raw_x, flow, key_x, key_slot, out, T, C, Cx, H, W, Hf, Wf, ws, ws_bytes, stream);
 }

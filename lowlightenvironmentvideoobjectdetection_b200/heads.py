@@ -62,15 +62,25 @@ class SelsaBBoxHead(nn.Module):
         nn.init.constant_(self.fc_reg.bias, 0)
 
     @torch.no_grad()
-    def forward(self, x, ref_x):
-        """x [N, C, 7, 7] key RoI features, ref_x [M, C, 7, 7] reference RoI features
-        -> (cls_score [N, classes+1], bbox_pred [N, 4*classes])   (selsa_bbox_head.py:25-84)."""
-        x, x_cl = self._flatten(x)
+    def ref_fc0(self, ref_x):
+        """The first shared FC on the reference RoI features alone (selsa_bbox_head.py:51,55 for i = 0): independent of the
+        key branch, so SelsaRoIHead runs it on a side stream next to TemporalRoIAlign's key path."""
         ref_x, ref_cl = self._flatten(ref_x)
+        fc = self.shared_fcs[0]
+        return F.linear(ref_x, self._fc0_weight(ref_cl), fc.bias)
+
+    @torch.no_grad()
+    def forward(self, x, ref_x, ref_fc0=None):
+        """x [N, C, 7, 7] key RoI features, ref_x [M, C, 7, 7] reference RoI features
+        -> (cls_score [N, classes+1], bbox_pred [N, 4*classes])   (selsa_bbox_head.py:25-84).
+        ``ref_fc0``: ``self.ref_fc0(ref_x)`` when the caller already computed it (ref_x is then not touched)."""
+        x, x_cl = self._flatten(x)
+        if ref_fc0 is None:
+            ref_x, ref_cl = self._flatten(ref_x)
         for i, fc in enumerate(self.shared_fcs):
             if i == 0:
                 x = F.linear(x, self._fc0_weight(x_cl), fc.bias)
-                ref_x = F.linear(ref_x, self._fc0_weight(ref_cl), fc.bias)
+                ref_x = ref_fc0 if ref_fc0 is not None else F.linear(ref_x, self._fc0_weight(ref_cl), fc.bias)
             else:
                 x = fc(x)
                 ref_x = fc(ref_x)
@@ -256,15 +266,35 @@ class SelsaRoIHead(nn.Module):
             layer.channels_last_out = True
         self.test_cfg = test_cfg or dict(score_thr=0.0001, nms=dict(type='nms', iou_threshold=0.5), max_per_img=100)
         self.use_ref_cache = True     # simple_test(..., ref_img_metas=...) goes through the reference-frame cache
+        self.overlap = True           # independent branches of a step run on two streams (see _bbox_forward)
         self._clip_cache = None
 
     @torch.no_grad()
     def _bbox_forward(self, x, ref_x, rois, ref_rois):
         """selsa_roi_head.py:80-97."""
         n_in = self.bbox_roi_extractor.num_inputs
-        bbox_feats = self.bbox_roi_extractor(x[:n_in], rois, ref_feats=ref_x[:n_in])
-        ref_bbox_feats = self.bbox_roi_extractor(ref_x[:n_in], ref_rois)
-        cls_score, bbox_pred = self.bbox_head(bbox_feats, ref_bbox_feats)
+        if self.overlap and ref_x[0].is_cuda and ref_rois.shape[0] > 0 and n_in == 1:
+            # the reference branch (RoIAlign of the M reference RoIs + the first shared FC on them) is independent of the key
+            # branch (TemporalRoIAlign over the key RoIs): it runs on a side stream next to it and joins before layer 0's
+            # aggregator.  The layout pass of the reference maps is queued first so that both branches consume it.
+            from . import ops
+            from .roi_extractors import TemporalRoIAlign
+            if isinstance(self.bbox_roi_extractor, TemporalRoIAlign):
+                C = ref_x[0].shape[1]
+                ops.to_nhwc(ref_x[0], want_norm=True, want_unit_bf16=(C % 64 == 0 and C <= 512 and
+                                                                      self.bbox_roi_extractor.impl != ops.IMPL_SIMT))
+            else:
+                ops.to_nhwc(ref_x[0])
+            with ops.fork(ref_x[0].device) as branch:
+                ref_bbox_feats = self.bbox_roi_extractor(ref_x[:n_in], ref_rois)
+                ref_pre = self.bbox_head.ref_fc0(ref_bbox_feats)
+            bbox_feats = self.bbox_roi_extractor(x[:n_in], rois, ref_feats=ref_x[:n_in])
+            branch.join()
+            cls_score, bbox_pred = self.bbox_head(bbox_feats, None, ref_fc0=ref_pre)
+        else:
+            bbox_feats = self.bbox_roi_extractor(x[:n_in], rois, ref_feats=ref_x[:n_in])
+            ref_bbox_feats = self.bbox_roi_extractor(ref_x[:n_in], ref_rois)
+            cls_score, bbox_pred = self.bbox_head(bbox_feats, ref_bbox_feats)
         return dict(cls_score=cls_score, bbox_pred=bbox_pred, bbox_feats=bbox_feats)
 
     @torch.no_grad()

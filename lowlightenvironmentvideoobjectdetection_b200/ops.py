@@ -34,20 +34,63 @@ def _f32c(t):
 
 
 # ----------------------------------------------------------------------------- layout
-# One-entry memo: SelsaRoIHead._bbox_forward hands the SAME reference feature tensor to the extractor twice
-# (key call with ref_feats=, then the reference-RoI call); the second NHWC transposition is skipped.  The
-# entry keeps the source tensor alive and is validated by identity + in-place version counter.
+# Two-entry memo: SelsaRoIHead._bbox_forward hands the SAME reference feature tensor to the extractor twice (key call with
+# ref_feats=, then the reference-RoI call) with the key map's own layout pass in between; the second NHWC transposition of
+# the reference maps is skipped.  An entry keeps the source tensor alive and is validated by identity + in-place version
+# counter (writes through raw pointers are invisible to it: CUDA-graph capture clears the memo, see heads.capture_callable).
 _nhwc_memo = {}
 
 
 def to_nhwc(x, want_norm=False, want_unit_bf16=False):
-    m = _nhwc_memo.get('e')
-    if m is not None and m[0] is x and m[1] == x._version and (m[3] is not None or not want_norm) \
-            and (m[4] is not None or not want_unit_bf16):
-        return m[2], m[3], m[4]
+    for slot in ('a', 'b'):
+        m = _nhwc_memo.get(slot)
+        if m is not None and m[0] is x and m[1] == x._version and (m[3] is not None or not want_norm) \
+                and (m[4] is not None or not want_unit_bf16):
+            return m[2], m[3], m[4]
     res = _to_nhwc(x, want_norm, want_unit_bf16)
-    _nhwc_memo['e'] = (x, x._version, res[0], res[1], res[2])
+    _nhwc_memo['b'] = _nhwc_memo.get('a')
+    _nhwc_memo['a'] = (x, x._version, res[0], res[1], res[2])
     return res
+
+
+# ----------------------------------------------------------------------------- fork / join on a side stream
+_side_streams = {}
+
+
+class fork:
+    """``with fork(device) as f: ...`` runs the body's launches on a per-device side stream that first waits for everything
+    already queued on the current stream; ``f.join()`` makes the current stream wait for the side stream.  Independent
+    branches of a step (the key-slot embed conv + G product next to the most-similar search, the reference-RoI branch next to
+    the key branch) then overlap on the device -- also inside a captured CUDA graph, where the fork becomes two graph branches.
+
+    Discipline that keeps the caching allocator safe without record_stream: side-stream work only ever happens inside a
+    fork, and every fork starts with side.wait_stream(current), so a block freed by the consumer on the current stream is
+    never reused on the side stream before that consumer has been queued."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        key = (self.device.type, self.device.index)
+        if key not in _side_streams:
+            _side_streams[key] = torch.cuda.Stream(self.device)
+        self.side = _side_streams[key]
+        self.main = None
+        self._ctx = None
+
+    def __enter__(self):
+        self.main = torch.cuda.current_stream(self.device)
+        self.side.wait_stream(self.main)
+        self._ctx = torch.cuda.stream(self.side)
+        self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        self._ctx.__exit__(*exc)
+        if exc[0] is not None:                  # do not leave a dangling branch behind an exception (graph capture needs the join)
+            self.main.wait_stream(self.side)
+        return False
+
+    def join(self):
+        self.main.wait_stream(self.side)
 
 
 def _to_nhwc(x, want_norm=False, want_unit_bf16=False, out=None):
@@ -336,9 +379,10 @@ def fgfa_warp_weighted_sum(key_emb, ref_emb, raw_x, flow, key_x=None, key_slot=-
     T, C, H, W = ref_emb.shape
     Cx = raw_x.shape[1]
     out = torch.empty((1, Cx, H, W), dtype=torch.float32, device=raw_x.device)
+    ws = _ws.get(T * H * W * 4, raw_x.device)
     _lib.call('vod_fgfa_warp_weighted_sum', _lib.ptr(key_emb), _lib.ptr(ref_emb), _lib.ptr(raw_x), _lib.ptr(flow),
               _lib.ptr(key_x), int(key_slot), _lib.ptr(out), T, C, Cx, H, W, flow.shape[2], flow.shape[3],
-              _lib.stream_ptr(raw_x.device))
+              _lib.ptr(ws), ws.numel(), _lib.stream_ptr(raw_x.device))
     return out
 
 

@@ -144,18 +144,25 @@ class TemporalRoIAlign(SingleRoIExtractor):
         # stacked frames), True / False = forced on (where the shape is supported) / off
         self.keyproj = None
         self.keyproj_min_frames = 8
+        # the key-slot embed conv + G product depend on the key RoI features only: run them on a side stream next to the
+        # most-similar search (False = everything on one stream)
+        self.overlap = True
 
-    def _stack_key_and_refs(self, feat, rois, ref_feat, return_indices=False):
+    def _stack_key_and_refs(self, feat, rois, ref_feat, return_indices=False, want_prepared=False):
         """RoIAlign(key) + most-similar RoI features, stacked as x_all [T+1, N, P, C] (NHWC rows)."""
         C = ref_feat.shape[1]
         key_nhwc, _, _ = ops.to_nhwc(feat)
         want_tc = ref_feat.is_cuda and C % 64 == 0 and C <= 512 and self.impl != ops.IMPL_SIMT
         ref_nhwc, ref_norm, ref_unit = ops.to_nhwc(ref_feat, want_norm=True, want_unit_bf16=want_tc)
-        return self._stack_from_layout(key_nhwc.contiguous(), rois, ref_nhwc.contiguous(), ref_norm, ref_unit, return_indices)
+        return self._stack_from_layout(key_nhwc.contiguous(), rois, ref_nhwc.contiguous(), ref_norm, ref_unit, return_indices,
+                                       want_prepared)
 
-    def _stack_from_layout(self, key_nhwc, rois, ref_nhwc, ref_norm, ref_unit, return_indices=False):
+    def _stack_from_layout(self, key_nhwc, rois, ref_nhwc, ref_norm, ref_unit, return_indices=False, want_prepared=False):
         """Same, from maps that are already laid out: key_nhwc [1,H,W,C], ref_nhwc [T,H,W,C] fp32 contiguous, ref_norm [T*H*W],
-        ref_unit [T*H*W, C] bf16 (or None) -- the form a reference-frame cache holds (heads.RefFrameCache)."""
+        ref_unit [T*H*W, C] bf16 (or None) -- the form a reference-frame cache holds (heads.RefFrameCache).
+
+        ``want_prepared``: also returns what ``_tafa`` needs from the key slot alone (the key-projected G operand), computed
+        on a side stream WHILE the most-similar search runs (it only depends on the key RoI features)."""
         layer = self.roi_layers[0]
         ph, pw = layer.output_size
         N = rois.shape[0]
@@ -164,10 +171,21 @@ class TemporalRoIAlign(SingleRoIExtractor):
         # temporal_roi_align.py:186 -- key RoI features, emitted as [N, 49, C] rows into slot 0
         ops.roi_align_nhwc(key_nhwc, rois, (ph, pw), layer.spatial_scale, layer.sampling_ratio,
                            layer.aligned, out_nhwc=True, out=x_all[0])
+        prepared, branch = None, None
+        if want_prepared and self.num_temporal_attention_blocks > 0 and self._keyproj_chunk(T + 1, ph * pw, C):
+            if self.overlap and x_all.is_cuda:
+                with ops.fork(x_all.device) as branch:
+                    prepared = self._keyproj_prepare(x_all[0], N, ph, pw, C, T + 1)
+            else:
+                prepared = self._keyproj_prepare(x_all[0], N, ph, pw, C, T + 1)
         # temporal_roi_align.py:99-181
         res = ops.msra_topk_sample(x_all[0].view(N * ph * pw, C), ref_nhwc,
                                    k=self.num_most_similar_points, ref_norm=ref_norm, ref_unit=ref_unit,
                                    impl=self.impl, return_indices=return_indices, out=x_all[1:])
+        if branch is not None:
+            branch.join()
+        if want_prepared:
+            return x_all, prepared
         return (x_all, res[1], res[2]) if return_indices else x_all
 
     def forward_from_layout(self, key_nhwc, rois, ref_nhwc, ref_norm, ref_unit, out=None):
@@ -177,8 +195,8 @@ class TemporalRoIAlign(SingleRoIExtractor):
         out_size = self.roi_layers[0].output_size
         if len(rois) == 0:
             return key_nhwc.new_zeros(0, self.out_channels, *out_size)
-        x_all = self._stack_from_layout(key_nhwc, rois, ref_nhwc, ref_norm, ref_unit)
-        return self._tafa(x_all, out_size[0], out_size[1], out=out)
+        x_all, prepared = self._stack_from_layout(key_nhwc, rois, ref_nhwc, ref_norm, ref_unit, want_prepared=True)
+        return self._tafa(x_all, out_size[0], out_size[1], out=out, prepared=prepared)
 
     @torch.no_grad()
     def most_similar_roi_align(self, roi_feats, ref_feats):
@@ -228,7 +246,21 @@ class TemporalRoIAlign(SingleRoIExtractor):
             return 0
         return ops.tafa_keyproj_chunk(T1, P, C, heads)
 
-    def _tafa(self, x_all, rh, rw, out=None):
+    def _keyproj_prepare(self, x_key, N, rh, rw, C, T1):
+        """temporal_roi_align.py:72-93 with the embed conv applied to the KEY slot only: the conv is linear, so
+        <conv(x_t), ek>_head = <x_t, ek_head . W_head>; G = ek_head . W_head is one batched GEMM with the FLOPs of one slot's
+        conv.  x_key [N, P, C] (slot 0 of x_all) -> (G [heads, N*P, 9*C], channel-chunk width)."""
+        heads = self.num_temporal_attention_blocks
+        conv = self.embed_network.conv
+        P = rh * rw
+        cc = self._keyproj_chunk(T1, P, C)
+        key_patches = x_key.view(N, rh, rw, C).permute(0, 3, 1, 2)
+        ek = torch.nn.functional.conv2d(key_patches, self._conv_weight_cl(conv), conv.bias, 1, 1)
+        ek = ek.permute(0, 2, 3, 1).contiguous().view(N * P, heads, C // heads)   # no copy (channels_last)
+        G = torch.bmm(ek.transpose(0, 1), self._keyproj_weight(conv, heads, cc))  # [heads, N*P, 9*C]
+        return G, cc
+
+    def _tafa(self, x_all, rh, rw, out=None, prepared=None):
         T1, N, P, C = x_all.shape
         cl_out = self.roi_layers[0].channels_last_out
         heads = self.num_temporal_attention_blocks
@@ -236,13 +268,8 @@ class TemporalRoIAlign(SingleRoIExtractor):
             conv = self.embed_network.conv
             cc = self._keyproj_chunk(T1, P, C)
             if cc:
-                # temporal_roi_align.py:72-93 with the embed conv applied to the KEY slot only: the conv is linear, so
-                # <conv(x_t), ek>_head = <x_t, ek_head . W_head>; G = ek_head . W_head is one batched GEMM with the FLOPs of
-                # one slot's conv, the contraction of x_t with G runs in vod_tafa_keyproj_logits
-                key_patches = x_all[0].view(N, rh, rw, C).permute(0, 3, 1, 2)
-                ek = torch.nn.functional.conv2d(key_patches, self._conv_weight_cl(conv), conv.bias, 1, 1)
-                ek = ek.permute(0, 2, 3, 1).contiguous().view(N * P, heads, C // heads)   # no copy (channels_last)
-                G = torch.bmm(ek.transpose(0, 1), self._keyproj_weight(conv, heads, cc))  # [heads, N*P, 9*C]
+                # the contraction of x_t with G runs in vod_tafa_keyproj_logits
+                G, cc = prepared if prepared is not None else self._keyproj_prepare(x_all[0], N, rh, rw, C, T1)
                 parts = ops.tafa_keyproj_logits(x_all, G, (rh, rw), heads, cc)
                 out = ops.tafa_weighted_sum_logits(x_all, parts, heads, out_nhwc=cl_out, out=out)
             else:
@@ -272,5 +299,5 @@ class TemporalRoIAlign(SingleRoIExtractor):
         if len(rois) == 0:
             return feats[0].new_zeros(0, self.out_channels, *out_size)
         # only the last level of the reference maps is used (:195-196)
-        x_all = self._stack_key_and_refs(feats[0], rois, ref_feats[-1])
-        return self._tafa(x_all, out_size[0], out_size[1]).to(feats[0].dtype)
+        x_all, prepared = self._stack_key_and_refs(feats[0], rois, ref_feats[-1], want_prepared=True)
+        return self._tafa(x_all, out_size[0], out_size[1], prepared=prepared).to(feats[0].dtype)

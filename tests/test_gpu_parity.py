@@ -518,7 +518,7 @@ def test_temporal_roi_align_sweep_size_properties():
     rois = rpn_like_rois(g, N, 1).to(DEV)
     stacks = []
     tafa = m._tafa
-    m._tafa = lambda x_all, rh, rw: (stacks.append(x_all), tafa(x_all, rh, rw))[1]
+    m._tafa = lambda x_all, rh, rw, **kw: (stacks.append(x_all), tafa(x_all, rh, rw, **kw))[1]
     out = m((x,), rois, ref_feats=(ref,))
     assert out.shape == (N, 512, 7, 7) and bool(torch.isfinite(out).all())
     out2 = m((x,), rois, ref_feats=(ref,))

@@ -210,6 +210,12 @@ def kernel_rooflines(cfg, device, peaks):
     t = timeit(lambda: ops.roi_align_nhwc(ref_nhwc, rois, 7, 1 / 16, 2, True, out_nhwc=True))
     out['roi_align_refs'] = dict(bound='hbm', seconds=t, achieved=b / t / 1e9, peak=peaks['hbm'], unit='GB/s', bytes=b,
                                  note='channels_last output, the layout SelsaRoIHead consumes')
+    # the key frame's N RoIs alone (what a step through the reference-frame cache runs): latency-, not bandwidth-bound
+    key_map = ref_nhwc[T - 1:T].contiguous()
+    t = timeit(lambda: ops.roi_align_nhwc(key_map, key_rois, 7, 1 / 16, 2, True, out_nhwc=True))
+    b = (C * H * W + N * C * P) * 4
+    out['roi_align_key'] = dict(bound='hbm', seconds=t, achieved=b / t / 1e9, peak=peaks['hbm'], unit='GB/s', bytes=b,
+                                note='%d RoIs of one map: too few CTAs to fill the machine' % N)
     if cfg['troi']:
         key_rows = ops.roi_align_nhwc(ref_nhwc[T - 1:T].contiguous(), key_rois, 7, 1 / 16, 2, True, out_nhwc=True).view(N * P, C)
         # (4) most-similar sampling: flops = 2*N*P*C*T*HW
@@ -1158,6 +1164,37 @@ def bench_dff(ctx, cfg):
         t_e2e = ctx.timed(lambda: (clip_loop(frames_total, from_host=True), sink.gather()))
         interval_loop(2 * interval)
         t_int = ctx.timed(lambda: (interval_loop(frames_total), sink.gather()))
+        # ---- with the flow network in the loop: FlowNetSimple (bf16 cuDNN convs, channels_last) on the frame pair,
+        # its low-resolution prediction handed straight to the warp (no full-resolution flow tensor), vs the reference's hand-off
+        flownet_res = None
+        try:
+            torch.manual_seed(1)
+            net = vod.build_motion(dict(type='FlowNetSimple', img_scale_factor=0.5)).to(dev).eval()
+            net = net.to(torch.bfloat16).to(memory_format=torch.channels_last)
+            metas = [dict(img_shape=IMG_SHAPE, img_norm_cfg=dict(mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375]))]
+            pair = torch.randn(1, 6, H * 16, W * 16, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+
+            def net_lowres():
+                lr, info = net(pair, metas, return_lowres=True)
+                feat = vod.flow_warp_feats_lowres(key_map, lr.float(), **info)
+                return detect_on_map(vod, head, feat, st_cls, st_reg, anchors)
+
+            def net_fullres():
+                flow = net(pair, metas)
+                feat = vod.flow_warp_feats(key_map, flow.float())
+                return detect_on_map(vod, head, feat, st_cls, st_reg, anchors)
+            g_lr, _ = vod.SelsaRoIHead.capture_callable(net_lowres)
+            g_fr, _ = vod.SelsaRoIHead.capture_callable(net_fullres)
+            k = 50
+            t_lr = ctx.timed(lambda: [g_lr.replay() for _ in range(k)])
+            t_fr = ctx.timed(lambda: [g_fr.replay() for _ in range(k)])
+            flownet_res = {'non_key_frame_us_lowres_handoff': 1e6 * t_lr / k, 'non_key_frame_us_fullres_flow': 1e6 * t_fr / k,
+                           'note': 'non-key frame INCLUDING FlowNetSimple (bf16, channels_last, cuDNN) on the 608x1008 frame pair; '
+                                   'lowres: vod_flow_warp_lowres consumes the 76x126 prediction; fullres: interpolate x8 + scaling '
+                                   'materialised as in flownet_simple.py:229-236, then vod_flow_warp'}
+            del net, g_lr, g_fr
+        except Exception as e:
+            flownet_res = {'unavailable': '%s: %s' % (type(e).__name__, str(e)[:200])}
     frames = frames_total * ctx.world
     launches = (l1 - l0) // 3 * (frames_total // interval) + (l2 - l1) // 3 * (frames_total - frames_total // interval)
     map_b, flow_b, rpn_b = key_map.numel() * 4, st_flow.numel() * 4, (st_cls.numel() + st_reg.numel()) * 4
@@ -1174,6 +1211,7 @@ def bench_dff(ctx, cfg):
                    'interval_batched': {'value': frames / t_int, 'unit': UNIT, 'us_per_frame': 1e6 * t_int / frames_total,
                                         'note': 'the 9 non-key frames of an interval in ONE graph: one shared-map warp launch '
                                                 '(vod_flow_warp_shared), one RPN stage and one RoIAlign / FC pass over 9 frames (SURVEY row N4)'},
+                   'with_flownet': flownet_res,
                    'gpu_launches': int(launches), 'clocks': sampler.summary()})
     if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline and reference_available():
         from oracle import ref_step

@@ -83,6 +83,15 @@ int vod_flow_warp(const float *x, const float *flow, float *out, int N, int C, i
  * at a time). */
 int vod_flow_warp_shared(const float *x, const float *flow, float *out, int N, int x_frames, int C, int H,
                          int W, int Hf, int Wf, vod_stream_t stream);
+/* Warp driven by the flow network's LOW-RESOLUTION prediction flow_lr [N,2,hl,wl]: the full-resolution flow
+ *   mult2 * (mult1 * interpolate(flow_lr, scale_factor=up_scale, bilinear, align_corners=False))   [N,2,Hf,Wf]
+ * that FlowNetSimple materialises (mmtracking/mmtrack/models/motion/flownet_simple.py:229-236: up_scale = mult1 =
+ * 4 / img_scale_factor, mult2 = flow_scale_factor) is evaluated on the fly at the 4 of every 256 values flow_warp_feats reads,
+ * instead of being written and re-read.  Same result as vod_flow_warp_shared on the materialised flow (same arithmetic).
+ * replaces: the tail of FlowNetSimple.forward + mmtrack.core.flow_warp_feats (core/motion/flow.py:4-41). */
+int vod_flow_warp_lowres(const float *x, const float *flow_lr, float *out, int N, int x_frames, int C, int H,
+                         int W, int hl, int wl, int Hf, int Wf, double up_scale, float mult1, float mult2,
+                         vod_stream_t stream);
 /* key_emb [1,C,H,W], ref_emb [T,C,H,W], ref_x [T,Cx,H,W] -> out [1,Cx,H,W]:
  * cosine(key_emb, ref_emb[t]) over C, softmax over t, weighted sum of ref_x.
  * replaces: the weighting half of EmbedAggregator.forward,

@@ -32,6 +32,7 @@ SIGNATURES = {
     'vod_roi_align_fwd': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _I, _P]),
     'vod_flow_warp': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     'vod_flow_warp_shared': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'vod_flow_warp_lowres': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _c.c_double, _F, _F, _P]),
     'vod_embed_weighted_sum': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _SZ, _P]),
     'vod_fgfa_warp_weighted_sum': (_I, [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _SZ, _P]),
     'vod_selsa_attn_workspace_bytes': (_SZ, [_I, _I, _I, _I]),

@@ -25,14 +25,49 @@ __device__ __forceinline__ void resize_src(int dst, float inv_scale, int in_size
     l1 = src - (float)a;
 }
 
+// Where the full-resolution flow comes from.  LOWRES: the flow network's last prediction [2, hl, wl] is upsampled on the fly --
+// FlowNetSimple ends with interpolate(scale_factor=up, bilinear, align_corners=False) followed by two scalar multiplies
+// (mmtracking/mmtrack/models/motion/flownet_simple.py:229-236) and flow_warp_feats immediately shrinks the result by 1/16,
+// touching 4 of every 256 upsampled values: evaluating just those skips writing and re-reading the [N, 2, Hf, Wf] tensor.
+struct FlowSrc {
+    const float *p;       // full-res [2, Hf, Wf] of this frame, or low-res [2, hl, wl]
+    int Hf, Wf;           // full-resolution size (virtual when lowres)
+    int hl, wl;           // low-res size (lowres only)
+    float up_inv, m1, m2; // 1 / upsample factor; the two post-multipliers, applied in the reference's order
+    int lowres;
+};
+template <bool LOWRES>
+__device__ __forceinline__ float flow_at(const FlowSrc &f, int ch, int Y, int X) {
+    if (!LOWRES) return __ldg(f.p + ((size_t)ch * f.Hf + Y) * f.Wf + X);
+    int y0, y1, x0, x1;
+    float ly, lx;
+    resize_src(Y, f.up_inv, f.hl, y0, y1, ly);
+    resize_src(X, f.up_inv, f.wl, x0, x1, lx);
+    const float *q = f.p + (size_t)ch * f.hl * f.wl;
+    const float a = __ldg(q + (size_t)y0 * f.wl + x0), b = __ldg(q + (size_t)y0 * f.wl + x1);
+    const float c = __ldg(q + (size_t)y1 * f.wl + x0), d = __ldg(q + (size_t)y1 * f.wl + x1);
+    // ATen upsample_bilinear2d: h0 * (w0 * a + w1 * b) + h1 * (w0 * c + w1 * d)
+    const float top = __fadd_rn(__fmul_rn(1.0f - lx, a), __fmul_rn(lx, b));
+    const float bot = __fadd_rn(__fmul_rn(1.0f - lx, c), __fmul_rn(lx, d));
+    const float v = __fadd_rn(__fmul_rn(1.0f - ly, top), __fmul_rn(ly, bot));
+    return __fmul_rn(__fmul_rn(v, f.m1), f.m2);
+}
+
 // Sampling position of pixel (h, w) of frame n: resized+scaled flow -> normalised grid -> border-clamped bilinear, as the base
 // plane offset, the steps to the east / south neighbours (0 at a clamped border) and the two lerp fractions.
 struct TapF {
     int i00, dx, dy;
     float tx, ty;
 };
-__device__ __forceinline__ TapF make_tap_frac(const float *__restrict__ flow_n, int h, int w, int H, int W, int Hf,
-                                              int Wf, float s, float inv_s) {
+__device__ __forceinline__ FlowSrc full_res_flow(const float *flow_n, int Hf, int Wf) {
+    FlowSrc f;
+    f.p = flow_n; f.Hf = Hf; f.Wf = Wf; f.hl = 0; f.wl = 0; f.up_inv = 1.f; f.m1 = 1.f; f.m2 = 1.f; f.lowres = 0;
+    return f;
+}
+
+template <bool LOWRES>
+__device__ __forceinline__ TapF make_tap_frac(const FlowSrc &src, int h, int w, int H, int W, float s, float inv_s) {
+    const int Hf = src.Hf, Wf = src.Wf;
     int y0, y1, x0, x1;
     float ly, lx;
     resize_src(h, inv_s, Hf, y0, y1, ly);
@@ -40,9 +75,8 @@ __device__ __forceinline__ TapF make_tap_frac(const float *__restrict__ flow_n, 
     float f[2];
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
-        const float *p = flow_n + (size_t)ch * Hf * Wf;
-        float a = __ldg(p + (size_t)y0 * Wf + x0), b = __ldg(p + (size_t)y0 * Wf + x1);
-        float c = __ldg(p + (size_t)y1 * Wf + x0), d = __ldg(p + (size_t)y1 * Wf + x1);
+        float a = flow_at<LOWRES>(src, ch, y0, x0), b = flow_at<LOWRES>(src, ch, y0, x1);
+        float c = flow_at<LOWRES>(src, ch, y1, x0), d = flow_at<LOWRES>(src, ch, y1, x1);
         float top = __fadd_rn(__fmul_rn(1.0f - lx, a), __fmul_rn(lx, b));
         float bot = __fadd_rn(__fmul_rn(1.0f - lx, c), __fmul_rn(lx, d));
         f[ch] = __fmul_rn(__fadd_rn(__fmul_rn(1.0f - ly, top), __fmul_rn(ly, bot)), s);
@@ -62,6 +96,21 @@ __device__ __forceinline__ TapF make_tap_frac(const float *__restrict__ flow_n, 
     t.dx = ix0 + 1 <= W - 1 ? 1 : 0;
     t.dy = iy0 + 1 <= H - 1 ? W : 0;
     t.i00 = iy0 * W + ix0;
+    return t;
+}
+
+__device__ __forceinline__ TapF make_tap_frac(const float *__restrict__ flow_n, int h, int w, int H, int W, int Hf,
+                                              int Wf, float s, float inv_s) {
+    return make_tap_frac<false>(full_res_flow(flow_n, Hf, Wf), h, w, H, W, s, inv_s);
+}
+
+__device__ __forceinline__ Taps taps_from_frac(const TapF &f) {
+    Taps t;
+    t.i00 = f.i00; t.i01 = f.i00 + f.dx; t.i10 = f.i00 + f.dy; t.i11 = f.i00 + f.dy + f.dx;
+    t.w00 = (1.0f - f.tx) * (1.0f - f.ty);
+    t.w01 = f.dx ? f.tx * (1.0f - f.ty) : 0.f;
+    t.w10 = f.dy ? (1.0f - f.tx) * f.ty : 0.f;
+    t.w11 = (f.dx && f.dy) ? f.tx * f.ty : 0.f;
     return t;
 }
 
@@ -91,14 +140,16 @@ constexpr int kWarpCh = 64;     // channels per CTA
 // grid (pixel blocks, channel chunks, N)
 // (min 16 CTAs per SM = 32 registers: the kernel lives on its 2048 resident threads; at 48 registers -- 1280 threads -- the
 // same code ran 117 us instead of 90 us at T = 31)
+template <bool LOWRES>
 __global__ void __launch_bounds__(kWarpPix, 16)
 flow_warp_kernel(const float *__restrict__ x, const float *__restrict__ flow, float *__restrict__ out, int C,
-                 int H, int W, int Hf, int Wf, float s, float inv_s, int x_frames) {
+                 int H, int W, FlowSrc src, float s, float inv_s, int x_frames) {
     const int n = blockIdx.z;
     const int p = blockIdx.x * kWarpPix + threadIdx.x;
     const int HW = H * W;
     if (p >= HW) return;
-    const Taps t = make_taps(flow + (size_t)n * 2 * Hf * Wf, p / W, p % W, H, W, Hf, Wf, s, inv_s);
+    src.p = flow + (size_t)n * 2 * (LOWRES ? src.hl * src.wl : src.Hf * src.Wf);
+    const Taps t = taps_from_frac(make_tap_frac<LOWRES>(src, p / W, p % W, H, W, s, inv_s));
     const int c0 = blockIdx.y * kWarpCh, c1 = min(C, c0 + kWarpCh);
     // x_frames == 1: every flow warps the SAME map (DFF: the non-key frames of an interval share the key frame's features)
     const float *xp = x + ((size_t)(x_frames == 1 ? 0 : n) * C + c0) * HW;
@@ -398,8 +449,29 @@ extern "C" int vod_flow_warp_shared(const float *x, const float *flow, float *ou
     float s, inv_s;
     flow_scale(W, Wf, s, inv_s);
     dim3 grid(ceil_div(H * W, kWarpPix), ceil_div(C, kWarpCh), N);
-    flow_warp_kernel<<<grid, kWarpPix, 0, as_stream(stream)>>>(x, flow, out, C, H, W, Hf, Wf, s, inv_s, x_frames); note_launch();
+    FlowSrc src;
+    src.p = nullptr; src.Hf = Hf; src.Wf = Wf; src.hl = 0; src.wl = 0; src.up_inv = 1.f; src.m1 = 1.f; src.m2 = 1.f; src.lowres = 0;
+    flow_warp_kernel<false><<<grid, kWarpPix, 0, as_stream(stream)>>>(x, flow, out, C, H, W, src, s, inv_s, x_frames); note_launch();
     return check_launch("vod_flow_warp");
+}
+
+extern "C" int vod_flow_warp_lowres(const float *x, const float *flow_lr, float *out, int N, int x_frames, int C, int H, int W,
+                                    int hl, int wl, int Hf, int Wf, double up_scale, float mult1, float mult2,
+                                    vod_stream_t stream) {
+    if (N == 0 || C == 0) return VOD_OK;
+    VOD_REQUIRE(x && flow_lr && out, "vod_flow_warp_lowres: null pointer");
+    VOD_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && hl > 0 && wl > 0 && Hf > 0 && Wf > 0 && up_scale > 0, "vod_flow_warp_lowres: bad dims");
+    VOD_REQUIRE(N <= 65535, "vod_flow_warp_lowres: N too large");
+    VOD_REQUIRE(x_frames == 1 || x_frames == N, "vod_flow_warp_lowres: x must hold 1 (shared) or N=%d maps, got %d", N, x_frames);
+    float s, inv_s;
+    flow_scale(W, Wf, s, inv_s);
+    dim3 grid(ceil_div(H * W, kWarpPix), ceil_div(C, kWarpCh), N);
+    FlowSrc src;
+    src.p = nullptr; src.Hf = Hf; src.Wf = Wf; src.hl = hl; src.wl = wl;
+    src.up_inv = (float)(1.0 / up_scale);      // ATen: static_cast<float>(1.0 / scale_factor)
+    src.m1 = mult1; src.m2 = mult2; src.lowres = 1;
+    flow_warp_kernel<true><<<grid, kWarpPix, 0, as_stream(stream)>>>(x, flow_lr, out, C, H, W, src, s, inv_s, x_frames); note_launch();
+    return check_launch("vod_flow_warp_lowres");
 }
 
 extern "C" int vod_flow_warp(const float *x, const float *flow, float *out, int N, int C, int H, int W, int Hf,

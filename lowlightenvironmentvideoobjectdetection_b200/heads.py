@@ -127,12 +127,14 @@ class SelsaBBoxHead(nn.Module):
         return self.fc_cls(x), self.fc_reg(x)
 
     @staticmethod
-    def _linear_few_rows(x, w, b, split=4):
+    def _linear_few_rows(x, w, b, split=16):
         """F.linear for a handful of rows against a long reduction (fc_0: 600 x 25088 -> 1024).  The library tiles the
-        [rows, out] plane only -- 40 CTAs on 148 SMs for 600 rows -- so the reduction axis is split into ``split`` slabs run as
-        one batched GEMM (4x the CTAs, each reading a quarter of the weight) and summed: 83 us -> ~35 us at cfg 3."""
+        [rows, out] plane only -- 40 CTAs on 148 SMs for 600 rows, each streaming 6 MB through its shared memory -- so the
+        reduction axis is split into ``split`` slabs run as one batched GEMM (640 CTAs) and summed."""
         rows, k = x.shape
-        if rows > 1024 or k < 8192 or k % split or not x.is_contiguous() or not w.is_contiguous():
+        while split > 1 and k % split:
+            split //= 2
+        if rows > 1024 or k < 8192 or split == 1 or not x.is_contiguous() or not w.is_contiguous():
             return F.linear(x, w, b)
         xs = x.view(rows, split, k // split).transpose(0, 1)              # [split, rows, k/split], no copy
         ws = w.view(w.shape[0], split, k // split).permute(1, 2, 0)       # [split, k/split, out], no copy

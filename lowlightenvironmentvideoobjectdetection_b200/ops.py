@@ -358,6 +358,22 @@ def flow_warp(x, flow):
     return out
 
 
+def flow_warp_lowres(x, flow_lr, full_size, up_scale, mult1, mult2):
+    """x [N,C,H,W] (or [1,C,H,W] shared), flow_lr [N,2,hl,wl]: warp by mult2 * (mult1 * upsample(flow_lr, up_scale)) of
+    size ``full_size`` = (Hf, Wf), the upsample evaluated on the fly (include/vodagg.h)."""
+    _lib.require_cuda(x, flow_lr)
+    x, flow_lr = _f32c(x), _f32c(flow_lr)
+    Nx, C, H, W = x.shape
+    N = flow_lr.shape[0]
+    assert Nx in (1, N)
+    out = torch.empty((N, C, H, W), dtype=torch.float32, device=x.device)
+    if out.numel():
+        _lib.call('vod_flow_warp_lowres', _lib.ptr(x), _lib.ptr(flow_lr), _lib.ptr(out), N, Nx, C, H, W, flow_lr.shape[2],
+                  flow_lr.shape[3], int(full_size[0]), int(full_size[1]), float(up_scale), float(mult1), float(mult2),
+                  _lib.stream_ptr(x.device))
+    return out
+
+
 def embed_weighted_sum(key_emb, ref_emb, ref_x):
     """key_emb [1,C,H,W], ref_emb [T,C,H,W], ref_x [T,Cx,H,W] -> [1,Cx,H,W]."""
     _lib.require_cuda(key_emb, ref_emb, ref_x)

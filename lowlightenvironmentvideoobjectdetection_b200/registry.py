@@ -83,6 +83,7 @@ def build_from_cfg(cfg, registry, default_args=None):
 AGGREGATORS = Registry('aggregator')
 ROI_EXTRACTORS = Registry('roi_extractor')
 HEADS = Registry('head')
+MOTION = Registry('motion')           # mmtracking/mmtrack/models/builder.py:8 (FlowNetSimple)
 
 
 def build_aggregator(cfg):
@@ -99,27 +100,44 @@ def build_head(cfg):
     return build_from_cfg(cfg, HEADS)
 
 
+def build_motion(cfg):
+    """mmtracking/mmtrack/models/builder.py:43-45."""
+    return build_from_cfg(cfg, MOTION)
+
+
 class ConvModule(nn.Module):
-    """The slice of mmcv.cnn.ConvModule the hot-path modules use: conv (+ReLU), sub-modules named
-    ``conv`` / ``activate`` so reference checkpoints load (checkpoint keys).
-    Weights use mmcv's default Kaiming-normal init."""
+    """The slice of mmcv.cnn.ConvModule the hot-path modules use: conv or transposed conv (``conv_cfg=dict(type='deconv')``)
+    + optional ReLU / LeakyReLU, sub-modules named ``conv`` / ``activate`` so reference checkpoints load (SURVEY section 5,
+    checkpoint keys).  Weights use mmcv's default Kaiming-normal init."""
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
                  bias='auto', conv_cfg=None, norm_cfg=None, act_cfg=dict(type='ReLU'), inplace=True, **kwargs):
         super().__init__()
         if norm_cfg is not None:
             raise NotImplementedError('norm layers are not part of the hot path (reference configs use norm_cfg=None)')
-        if conv_cfg is not None and conv_cfg.get('type', 'Conv2d') not in ('Conv2d', 'Conv'):
-            raise NotImplementedError('only plain Conv2d embed convs are supported')
+        conv_type = 'Conv2d' if conv_cfg is None else conv_cfg.get('type', 'Conv2d')
+        if conv_type not in ('Conv2d', 'Conv', 'deconv'):
+            raise NotImplementedError('conv type %r is not supported' % conv_type)
         self.with_activation = act_cfg is not None
         self.with_norm = False
-        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride=stride, padding=padding,
-                              dilation=dilation, groups=groups, bias=(bias == 'auto' or bool(bias)))
+        with_bias = (bias == 'auto' or bool(bias))
+        if conv_type == 'deconv':
+            self.conv = nn.ConvTranspose2d(in_channels, out_channels, kernel_size, stride=stride, padding=padding,
+                                           dilation=dilation, groups=groups, bias=with_bias)
+        else:
+            self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride=stride, padding=padding,
+                                  dilation=dilation, groups=groups, bias=with_bias)
+        slope = 0.0
         if self.with_activation:
-            if act_cfg.get('type', 'ReLU') != 'ReLU':
-                raise NotImplementedError('only ReLU activations are supported')
-            self.activate = nn.ReLU(inplace=inplace)
-        nn.init.kaiming_normal_(self.conv.weight, a=0, mode='fan_out', nonlinearity='relu')
+            act_type = act_cfg.get('type', 'ReLU')
+            if act_type == 'ReLU':
+                self.activate = nn.ReLU(inplace=inplace)
+            elif act_type == 'LeakyReLU':
+                slope = act_cfg.get('negative_slope', 0.01)
+                self.activate = nn.LeakyReLU(negative_slope=slope, inplace=inplace)
+            else:
+                raise NotImplementedError('only ReLU / LeakyReLU activations are supported')
+        nn.init.kaiming_normal_(self.conv.weight, a=slope, mode='fan_out', nonlinearity='leaky_relu' if slope else 'relu')
         if self.conv.bias is not None:
             nn.init.constant_(self.conv.bias, 0)
 

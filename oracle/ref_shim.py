@@ -70,15 +70,20 @@ def _build_from_cfg(cfg, registry, default_args=None):
 
 
 class _ConvModule(nn.Module):
-    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0,
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, bias=True,
                  conv_cfg=None, norm_cfg=None, act_cfg=dict(type='ReLU'), **kw):
         super().__init__()
         assert norm_cfg is None
-        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride=stride,
-                              padding=padding, bias=True)
+        conv_type = (conv_cfg or {}).get('type', 'Conv2d')
+        layer = nn.ConvTranspose2d if conv_type == 'deconv' else nn.Conv2d          # mmcv: 'deconv' -> nn.ConvTranspose2d
+        self.conv = layer(in_channels, out_channels, kernel_size, stride=stride,
+                          padding=padding, bias=(bias == 'auto' or bool(bias)))
         self.with_activation = act_cfg is not None
         if self.with_activation:
-            self.activate = nn.ReLU(inplace=False)
+            if act_cfg.get('type', 'ReLU') == 'LeakyReLU':
+                self.activate = nn.LeakyReLU(negative_slope=act_cfg.get('negative_slope', 0.01), inplace=False)
+            else:
+                self.activate = nn.ReLU(inplace=False)
 
     def forward(self, x):
         x = self.conv(x)
@@ -192,7 +197,9 @@ def load():
     _mod('mmtrack.core')
     _mod('mmtrack.core.motion')
     _mod('mmtrack.models')
-    _mod('mmtrack.models.builder', AGGREGATORS=AGGREGATORS)
+    MOTION = _Registry('motion')
+    _mod('mmtrack.models.builder', AGGREGATORS=AGGREGATORS, MOTION=MOTION)
+    _mod('mmtrack.models.motion')
     _mod('mmtrack.models.aggregators')
     _mod('mmtrack.models.roi_heads')
     _mod('mmtrack.models.roi_heads.roi_extractors')
@@ -215,6 +222,7 @@ def load():
     mm_single = _load('mmtrack.models.roi_heads.roi_extractors.single_level_roi_extractor',
                       t + 'models/roi_heads/roi_extractors/single_level_roi_extractor.py')
     flow = _load('mmtrack.core.motion.flow', t + 'core/motion/flow.py')
+    flownet = _load('mmtrack.models.motion.flownet_simple', t + 'models/motion/flownet_simple.py')
 
     ns = types.SimpleNamespace(
         SelsaAggregator=selsa.SelsaAggregator,
@@ -223,6 +231,7 @@ def load():
         SingleRoIExtractor=mm_single.SingleRoIExtractor,
         MMDetSingleRoIExtractor=single.SingleRoIExtractor,
         flow_warp_feats=flow.flow_warp_feats,
+        FlowNetSimple=flownet.FlowNetSimple,
         multiclass_nms=bbox_nms.multiclass_nms,
         batched_nms=_batched_nms,
         RoIAlign=_RoIAlign,

@@ -119,3 +119,50 @@ def test_split_k_first_fc_matches_linear():
     assert rel_err(got, want) < 1e-5
     big = torch.randn(2000, 64, device=DEV, generator=g)     # outside the few-rows regime: plain F.linear
     assert torch.equal(vod.SelsaBBoxHead._linear_few_rows(big, w[:, :64].contiguous(), b), torch.nn.functional.linear(big, w[:, :64].contiguous(), b))
+
+
+def test_flow_warp_from_lowres_flow_equals_materialised_flow():
+    """FlowNetSimple ends with a x8 bilinear upsample + two scalar multiplies (flownet_simple.py:229-236) whose
+    output flow_warp_feats immediately shrinks by 1/16.  vod_flow_warp_lowres evaluates the upsample at the 4 of every 256
+    values the warp reads: same result as warping with the materialised full-resolution flow (oracle on the CPU)."""
+    g = torch.Generator().manual_seed(12)
+    C, H, W, F_ = 64, 12, 20, 5
+    x = torch.relu(torch.randn(F_, C, H, W, generator=g))
+    flow_lr = torch.randn(F_, 2, H * 2, W * 2, generator=g) * 0.3                 # FlowNet predicts at 1/8 of the image
+    info = dict(up_scale=8.0, mult1=8.0, mult2=5.0, full_size=(H * 16, W * 16))
+    full = torch.nn.functional.interpolate(flow_lr, scale_factor=8.0, mode='bilinear', align_corners=False)
+    full = full * 8.0
+    full = full * 5.0
+    want = O.flow_warp_feats(x, full)
+    got = vod.flow_warp_feats_lowres(x.to(DEV), flow_lr.to(DEV), **info)
+    assert got.shape == want.shape and rel_err(got, want) < 2e-5
+    # ... and bit-identical to our own warp of the flow materialised on the device with the same arithmetic order
+    got_full = vod.flow_warp_feats(x.to(DEV), full.to(DEV))
+    assert rel_err(got, got_full) < 2e-6
+    # one key map shared by all flows (DFF interval), through the feature memo
+    memo = vod.DFFFeatureMemo(10)
+    memo.set_key((x[:1].to(DEV),))
+    shared = memo.extract_feats_lowres(flow_lr.to(DEV), info)[0]
+    assert rel_err(shared, O.flow_warp_feats(x[:1].expand(F_, C, H, W).contiguous(), full)) < 2e-5
+
+
+def test_flownet_simple_mirror_on_device():
+    """The FlowNetSimple mirror (library convs) on the GPU in fp32 and bf16 against itself on the CPU, and its low-resolution
+    hand-off: warp(full-res flow) == warp_lowres(low-res prediction)."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(0)
+    net = vod.build_motion(dict(type='FlowNetSimple', img_scale_factor=0.5)).eval()
+    g = torch.Generator().manual_seed(13)
+    imgs = torch.randn(2, 6, 192, 320, generator=g)
+    metas = [dict(img_shape=(180, 310, 3), img_norm_cfg=dict(mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375]))]
+    with torch.no_grad():
+        want = net(imgs.clone(), metas)
+        net = net.to(DEV)
+        got = net(imgs.to(DEV), metas)
+        assert got.shape == (2, 2, 192, 320) and rel_err(got, want) < 1e-3
+        lr, info = net(imgs.to(DEV), metas, return_lowres=True)
+        assert info['full_size'] == (192, 320) and lr.shape == (2, 2, 24, 40)
+        x = torch.relu(torch.randn(2, 32, 12, 20, generator=g)).to(DEV)
+        assert rel_err(vod.flow_warp_feats_lowres(x, lr, **info), vod.flow_warp_feats(x, got)) < 1e-5
+        half = net.to(torch.bfloat16)(imgs.to(DEV).bfloat16(), metas)
+        assert half.dtype == torch.bfloat16 and rel_err(half.float(), want) < 0.1        # bf16 convs: stated separately

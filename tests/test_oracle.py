@@ -112,3 +112,26 @@ def test_rpn_get_bboxes_matches_reference_golden(rpn_golden):
         for b in range(G['cls'].shape[0]):
             d = O.rpn_get_bboxes(G['cls'][b], G['reg'][b], G['anchors'], img_shape, int(nms_pre), thr, int(mx))
             assert torch.equal(d, G['dets_%s_%d' % (tag, b)])
+
+
+def test_flownet_simple_mirror_matches_the_reference():
+    """our FlowNetSimple (motion.py) has the reference's parameter names and, with the reference's weights,
+    gives the reference's flow bit for bit on the CPU (reference class loaded unmodified through oracle/ref_shim.py)."""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip('reference files not present (neither /root/reference nor oracle/_ref)')
+    import lowlightenvironmentvideoobjectdetection_b200 as vod
+    ns = ref_shim.load()
+    torch.manual_seed(0)
+    ref = ns.FlowNetSimple(img_scale_factor=0.5)
+    ours = vod.build_motion(dict(type='FlowNetSimple', img_scale_factor=0.5))
+    assert list(ours.state_dict()) == list(ref.state_dict())
+    ours.load_state_dict(ref.state_dict())
+    g = torch.Generator().manual_seed(3)
+    imgs = torch.randn(2, 6, 96, 128, generator=g)
+    metas = [dict(img_shape=(90, 120, 3), img_norm_cfg=dict(mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375]))]
+    with torch.no_grad():
+        a, b = ref(imgs.clone(), metas), ours(imgs.clone(), metas)
+        lr, info = ours(imgs.clone(), metas, return_lowres=True)
+    assert a.shape == (2, 2, 96, 128) and torch.equal(a, b)
+    assert lr.shape == (2, 2, 12, 16) and info == dict(up_scale=8.0, mult1=8.0, mult2=5.0, full_size=(96, 128))

@@ -131,11 +131,18 @@ class FlowNetSimple(nn.Module):
     def prepare_imgs(self, imgs, img_metas):
         """flownet_simple.py:148-191: undo the detector's normalisation, apply FlowNet's, zero the padding, rescale."""
         cfg = img_metas[0]['img_norm_cfg']
-
-        def six(v):
-            return torch.tensor(v, device=imgs.device, dtype=imgs.dtype).repeat(2)[None, :, None, None]
-        flow_img = imgs * six(cfg['std']) + six(cfg['mean'])
-        flow_img = flow_img / six(self.flow_img_norm_std) - six(self.flow_img_norm_mean)
+        # the four [1,6,1,1] constants are built once per (device, dtype, normalisation) -- the reference caches them on first
+        # use too (:166-180) -- so that later calls launch no host-to-device copy and can be captured into a CUDA graph
+        key = (imgs.device, imgs.dtype, tuple(cfg['mean']), tuple(cfg['std']))
+        consts = getattr(self, '_norm_consts', None)
+        if consts is None or consts[0] != key:
+            def six(v):
+                return torch.tensor(v, device=imgs.device, dtype=imgs.dtype).repeat(2)[None, :, None, None]
+            consts = (key, six(cfg['std']), six(cfg['mean']), six(self.flow_img_norm_std), six(self.flow_img_norm_mean))
+            self._norm_consts = consts
+        _, std, mean, flow_std, flow_mean = consts
+        flow_img = imgs * std + mean
+        flow_img = flow_img / flow_std - flow_mean
         h, w = img_metas[0]['img_shape'][:2]
         flow_img[:, :, h:, :] = 0.0
         flow_img[:, :, :, w:] = 0.0

@@ -650,7 +650,8 @@ class SelsaRunner:
         sink.put(i, d, l, c)
 
     # ---- reference-frame cache (row N2)
-    def capture_cached(self, tf32=True):
+    def setup_cached(self):
+        """Static buffers + the cache object of the cached loop (no capture)."""
         cfg, dev, head = self.cfg, self.ctx.device, self.head
         T, N = cfg['T'], cfg['N']
         self.cache = head.new_ref_cache(T, N, (C, H, W), dev)
@@ -660,6 +661,11 @@ class SelsaRunner:
         self.st_key = torch.empty((1, C, H, W), device=dev)
         self.st_key_rois = torch.zeros(N, 5, device=dev)
         self.st_key_ref_rois = torch.zeros(N, 5, device=dev)
+
+    def capture_cached(self, tf32=True):
+        self.setup_cached()
+        head = self.head
+        T = self.cfg['T']
         slots = list(range(T - 1))
         with torch.no_grad(), library_math(tf32):
             self.load_memo(*self.dev_sets[0])
@@ -746,6 +752,21 @@ def bench_selsa(ctx, cfg, cfg_name):
                 run_step(run.head, *run.dev_sets[i % n_sets], metas)
             t_eager = ctx.timed(lambda: [run_step(run.head, *run.dev_sets[i % n_sets], metas) for i in range(args.steps)])
 
+            # ... and the drop-in call an integrator makes with the cache: simple_test(..., ref_img_metas=...) in SELSA's
+            # adaptive-stride test mode (14 fixed memory frames + the key frame), eagerly
+            memo_metas = [dict(video_id=ctx.rank, frame_id=-(t + 1), img_shape=IMG_SHAPE, scale_factor=(1., 1., 1., 1.)) for t in range(T - 1)]
+            ref_x0, props0 = run.dev_sets[0]
+
+            def eager_cached(k):
+                for i in range(k):
+                    key_x, key_props = run.dev_sets[i % n_sets]
+                    km = dict(video_id=ctx.rank, frame_id=i, img_shape=IMG_SHAPE, scale_factor=(1., 1., 1., 1.))
+                    ref_x = torch.cat([ref_x0[:T - 1], key_x[T - 1:T]], 0)          # selsa.py:220-223: ref_x = cat(memo, key)
+                    run.head.simple_test((key_x[T - 1:T],), (ref_x,), [key_props[T]], [props0[t] for t in range(T - 1)] + [key_props[T - 1]],
+                                         [km], rescale=False, ref_img_metas=memo_metas + [km])
+            eager_cached(3)
+            t_eager_cached = ctx.timed(lambda: eager_cached(args.steps))
+
         # ------------------------------------------------ the same step with fp32 library GEMMs / convs
         run.capture('fp32', tf32=False)
         for i in range(min(args.warmup, 3)):
@@ -791,6 +812,9 @@ def bench_selsa(ctx, cfg, cfg_name):
         'eager_api': {'value': frames / t_eager, 'unit': UNIT,
                       'note': 'SelsaRoIHead.simple_test called eagerly (what an integrator gets without capture_graph: variable-length '
                               'outputs, one host read of the detection count per frame)'},
+        'eager_cached_api': {'value': frames / t_eager_cached, 'unit': UNIT,
+                             'note': 'the drop-in call with the cache, eagerly: SelsaRoIHead.simple_test(..., ref_img_metas=...) on '
+                                     'ref_x = cat(memo, key) as SELSA.simple_test builds it; includes the host-side cache bookkeeping'},
         'fp32_library_math': {'value': frames / t_fp32, 'unit': UNIT, 'ms_per_step': 1e3 * t_fp32 / args.steps,
                               'note': 'same graph-replayed step with cuBLAS / cuDNN in fp32 instead of tf32'},
         'cached': {'value': frames / t_cached, 'unit': UNIT, 'ms_per_step': 1e3 * t_cached / args.steps, 'clip_len': clip_len,
@@ -1242,9 +1266,8 @@ def reference_arm(args, cfg, cfg_name):
         return
     if cfg['family'] == 'sweep':
         cfg = dict(CONFIGS['cfg3'], workload=CONFIGS['sweep']['workload'] + ' -- reference arm: the (300, 14) cell')
-    if cfg['family'] != 'selsa':
-        print(json.dumps({'impl': 'reference', 'unavailable': 'the reference arm of %s is reported as cpu_baseline inside the GPU arm' % cfg_name}))
-        return
+    if cfg['family'] in ('fgfa', 'dff'):
+        return reference_arm_feature_level(args, cfg, cfg_name)
     warm = min(args.warmup, 1)
     times, cores, kind, _ = time_cpu(cfg, args.steps, warm)
     ms = 1e3 * sum(times) / len(times)
@@ -1260,6 +1283,49 @@ def reference_arm(args, cfg, cfg_name):
         'dtype': 'f32', 'data': 'synthetic', 'config': config,
         'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': kind,
                          'sample': '%d key frame(s) of the same workload on the host cores; steps bounded by a 150 s wall-clock budget' % len(times)},
+        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+
+
+def reference_arm_feature_level(args, cfg, cfg_name):
+    """cfg 2 / cfg 4: the reference's own flow_warp_feats (+ EmbedAggregator) + RPNHead._get_bboxes + RoIAlign + FCs + multiclass_nms on
+    the host cores (oracle/ref_step.py), same synthetic inputs as the GPU arm."""
+    if not reference_available():
+        print(json.dumps({'impl': 'reference', 'unavailable': 'reference files not staged (run python -m oracle.make_ref where /root/reference exists)'}))
+        return
+    from oracle import ref_step
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    fgfa = cfg['family'] == 'fgfa'
+    torch.manual_seed(0)
+    ref = ref_step.ReferenceFeatureLevelDetector(in_channels=C, fc_out_channels=D, num_classes=CLASSES, with_aggregator=fgfa).eval()
+    anchors = grid_anchors('cpu')
+    times, t_start = [], time.perf_counter()
+    warm = min(args.warmup, 1)
+    for i in range(warm + args.steps):
+        x, memo, flows, rpn_cls, rpn_reg = feature_level_inputs(i, cfg['T'] if fgfa else 1, low_light=not fgfa)
+        if fgfa:
+            x, memo = x.bfloat16().float(), memo.bfloat16().float()
+        t0 = time.perf_counter()
+        if fgfa:
+            ref.fgfa_step(x, memo, flows, cfg['num_left'], rpn_cls, rpn_reg, anchors, IMG_SHAPE)
+        else:
+            ref.dff_step(x, flows, rpn_cls, rpn_reg, anchors, IMG_SHAPE)
+        if i >= warm:
+            times.append(time.perf_counter() - t0)
+        if times and time.perf_counter() - t_start > 150.0:
+            break
+    ms = 1e3 * sum(times) / len(times)
+    val = 1e3 / ms
+    metric = 'VID frames/sec (FGFA feature path)' if fgfa else 'VID frames/sec (DFF feature-propagation path)'
+    config = dict(workload=cfg['workload'], execution='torch CPU eager on all host threads: the reference\'s own unmodified files '
+                  '(oracle/_ref) under the mmcv stand-ins of oracle/ref_shim.py' + ('' if fgfa else '; non-key frames (9 of 10)'),
+                  parallelism='rank 0 only')
+    print(json.dumps({
+        'impl': 'reference', 'metric': metric, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': len(times), 'warmup': warm,
+        'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': config,
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'reference',
+                         'sample': '%d frame(s) of the same workload on the host cores; bounded by a 150 s wall-clock budget' % len(times)},
         'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
 

@@ -88,13 +88,16 @@ def build_library(force=False, verbose=False, probes=False):
 
 def _build_probes(verbose=False):
     nvcc, cxx = _nvcc(), _host_cxx()
-    obj_dir = os.path.join(_HERE, '_build', 'obj_probes')
+    # VOD_EXTRA_DEFINES="-DVOD_WARP_PIX=512 -DVOD_WARP_CH=16" VOD_PROBES_TAG=b python -m ...build --probes -> libvodagg_probes_b.so
+    extra = os.environ.get('VOD_EXTRA_DEFINES', '').split()
+    tag = os.environ.get('VOD_PROBES_TAG', '')
+    obj_dir = os.path.join(_HERE, '_build', 'obj_probes' + tag)
     os.makedirs(obj_dir, exist_ok=True)
-    out = os.path.join(_HERE, 'libvodagg_probes.so')
+    out = os.path.join(_HERE, 'libvodagg_probes%s.so' % ('_' + tag if tag else ''))
 
     def compile_one(src):
         obj = os.path.join(obj_dir, src.replace('.cu', '.o'))
-        r = subprocess.run([nvcc, '-ccbin', cxx] + NVCC_FLAGS + ['-DVOD_PROBES', '-c', os.path.join(CSRC, src), '-o', obj],
+        r = subprocess.run([nvcc, '-ccbin', cxx] + NVCC_FLAGS + ['-DVOD_PROBES'] + extra + ['-c', os.path.join(CSRC, src), '-o', obj],
                            capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError('nvcc failed for %s:\n%s\n%s' % (src, r.stdout, r.stderr))

@@ -219,6 +219,7 @@ extern "C" int vod_roi_align_fwd(const float *feat_nhwc, const float *rois, floa
         // Few RoIs (a key frame's 300 proposals: 300 CTAs on 148 SMs) leave most of the machine idle behind per-CTA latency
         // (measured 40 us for 300 RoIs against 193 us for 4500): such launches are split into 128-channel slabs, 4x the CTAs
         // with a quarter of the work each.  Large launches keep one CTA per RoI (per-RoI set-up paid once for 2 KB per tap).
+        // (slabs for every launch size were measured too: 274 us instead of 193 us for 4500 RoIs)
         const bool few = (long)K * 4 <= 16L * num_sms();
         if (C > 256 && !few) return launch_roi<4, 4>(VOD_ROI_ARGS);
         if (C > 128 && !few) return launch_roi<4, 2>(VOD_ROI_ARGS);

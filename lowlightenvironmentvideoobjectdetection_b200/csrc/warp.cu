@@ -134,14 +134,21 @@ __device__ __forceinline__ float apply_taps(const float *__restrict__ plane, con
     return v;
 }
 
-constexpr int kWarpPix = 128;   // pixels per CTA
-constexpr int kWarpCh = 64;     // channels per CTA
+// Tile shapes are overridable at build time for experiments (python -m ...build --probes with VOD_EXTRA_DEFINES).  Measured in
+// round 2 at T = 31 (us): warp 128 px x 64 ch 98 | 256 x 32 114 | 512 x 16 127; weighting (cos + apply) 128 px x 4 groups 121 |
+// 256 x 2 136 | 512 x 1 135 -- longer contiguous runs per plane do NOT help, the small tiles' extra CTAs do.
+#ifndef VOD_WARP_PIX
+#define VOD_WARP_PIX 128
+#define VOD_WARP_CH 64
+#endif
+constexpr int kWarpPix = VOD_WARP_PIX;   // pixels per CTA
+constexpr int kWarpCh = VOD_WARP_CH;     // channels per CTA
 
 // grid (pixel blocks, channel chunks, N)
 // (min 16 CTAs per SM = 32 registers: the kernel lives on its 2048 resident threads; at 48 registers -- 1280 threads -- the
 // same code ran 117 us instead of 90 us at T = 31)
 template <bool LOWRES>
-__global__ void __launch_bounds__(kWarpPix, 16)
+__global__ void __launch_bounds__(kWarpPix, 2048 / kWarpPix)
 flow_warp_kernel(const float *__restrict__ x, const float *__restrict__ flow, float *__restrict__ out, int C,
                  int H, int W, FlowSrc src, float s, float inv_s, int x_frames) {
     const int n = blockIdx.z;
@@ -275,7 +282,11 @@ embed_weighted_sum_kernel(const float *__restrict__ key_emb, const float *__rest
 //   embed_apply_kernel grid (pixel blocks, channel chunks): softmax over t recomputed per CTA from the T cosines of
 //                      its pixels (cheap), then out[c] = sum_t w_t * ref_x[t][c]
 // Every input element is read once from HBM (the key embedding is re-read per frame, from L2).
-constexpr int kEcPix = 128, kEcGroups = 4;
+#ifndef VOD_EC_PIX
+#define VOD_EC_PIX 128
+#define VOD_EC_GROUPS 4
+#endif
+constexpr int kEcPix = VOD_EC_PIX, kEcGroups = VOD_EC_GROUPS;
 
 __global__ void __launch_bounds__(kEcPix *kEcGroups)
 embed_cos_kernel(const float *__restrict__ key_emb, const float *__restrict__ ref_emb, float *__restrict__ cosv, int C,
@@ -310,7 +321,11 @@ embed_cos_kernel(const float *__restrict__ key_emb, const float *__restrict__ re
     }
 }
 
-constexpr int kEaPix = 128, kEaGroups = 4, kEaChPerGroup = 4, kEaCh = kEaGroups * kEaChPerGroup;
+#ifndef VOD_EA_PIX
+#define VOD_EA_PIX 128
+#define VOD_EA_GROUPS 4
+#endif
+constexpr int kEaPix = VOD_EA_PIX, kEaGroups = VOD_EA_GROUPS, kEaChPerGroup = 4, kEaCh = kEaGroups * kEaChPerGroup;
 // CTA = 128 pixels x 4 channel groups (512 threads, 16 channels).  The softmax over t is computed once per CTA (group 0)
 // and shared; every thread then streams T frames of 4 channels with 8 independent loads in flight per channel pair
 // (the 128-thread version kept 16 warps per SM busy at 22 % of DRAM bandwidth: too few bytes in flight).

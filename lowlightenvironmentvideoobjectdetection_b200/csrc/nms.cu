@@ -17,7 +17,7 @@
 
 namespace vod {
 
-constexpr int kMaxImages = 64;
+constexpr int kMaxImages = 256;   // images (segments) per call; the table travels as a kernel parameter (1 KB)
 struct SegTable {
     int n_images;
     int off[kMaxImages + 1];

@@ -241,6 +241,13 @@ def kernel_rooflines(cfg, device, peaks):
         b = (G.numel() + x_all.numel()) * 4
         out['tafa_keyproj_logits'] = dict(bound='hbm', seconds=t, achieved=b / t / 1e9, peak=peaks['hbm'], unit='GB/s', bytes=b,
                                           traffic=1626.1e6, note='traffic: NOT measured in this run -- dram read+write per launch copied from the ncu --set full capture profiles/r01h_ncu_full_summary.csv')
+        # the same with G in bf16 (what TemporalRoIAlign feeds it when reduced-precision library math is allowed: the shipped step)
+        Gh = G.bfloat16()
+        t = timeit(lambda: ops.tafa_keyproj_logits(x_all, Gh, 7, 4, cc))
+        b = Gh.numel() * 2 + x_all.numel() * 4
+        out['tafa_keyproj_logits_bf16_g'] = dict(bound='hbm', seconds=t, achieved=b / t / 1e9, peak=peaks['hbm'], unit='GB/s', bytes=b,
+                                                 note='G streamed as bf16 (542 MB) + x_all fp32 (482 MB)')
+        del Gh
         parts = ops.tafa_keyproj_logits(x_all, G, 7, 4, cc)
         t = timeit(lambda: ops.tafa_weighted_sum_logits(x_all, parts, 4, out_nhwc=True))
         b = (x_all.numel() + N * P * C + parts.numel()) * 4
@@ -831,7 +838,7 @@ def bench_selsa(ctx, cfg, cfg_name):
             kr = kernel_rooflines(cfg, device, peaks)
         # the dominant kernel of THE TIMED STEP: composites (msra_topk_sample), alternates (NCHW-output RoIAlign) and the
         # kernels of the other detectors' shapes (FGFA/DFF T=31, RPN NMS), which the table also lists, do not qualify
-        in_step = ('roi_align_refs', 'msra_gemm_topk_kernel', 'tafa_keyproj_logits', 'tafa_weighted_sum_logits', 'selsa_attention',
+        in_step = ('roi_align_refs', 'msra_gemm_topk_kernel', 'tafa_keyproj_logits_bf16_g', 'tafa_weighted_sum_logits', 'selsa_attention',
                    'batched_nms_rcnn')
         single = {k: v for k, v in kr.items() if k in in_step}
         dom = max(single, key=lambda k: single[k]['seconds'])

@@ -191,14 +191,16 @@ int vod_tafa_weighted_sum(const float *x_all, const float *emb_all, const float 
  *   vod_tafa_keyproj_chunk: channel-chunk width CC the kernel wants G laid out with, 0 = unsupported
  *     shape (heads != 4, C % 32 != 0, or the [T1,P,CC] tile exceeds shared memory) -> use
  *     vod_tafa_weighted_sum with full embeddings instead.
- *   x_all [T1, N, P, C] fp32;  G [heads, N*P, C/CC, 9, CC] fp32 (tap = ky*3+kx of the 3x3, pad-1 conv);
+ *   x_all [T1, N, P, C] fp32;  G [heads, N*P, C/CC, 9, CC] (tap = ky*3+kx of the 3x3, pad-1 conv), g_dtype VOD_DTYPE_F32 or
+ *   VOD_DTYPE_BF16 (G is 70 % of this kernel's bytes; a bf16 G -- e.g. the output of a bf16 library GEMM -- is unpacked to fp32
+ *   on the fly, everything else stays fp32);
  *   parts [C/CC, N, P, heads, T1] fp32 out: per-chunk partial logits (unscaled).
  *   vod_tafa_weighted_sum_logits: sums the chunks, scales by 1/sqrt(C/heads), softmax over t, weighted sum.
  * replaces: temporal_roi_align.py:72-97 (embed_network over img_n*roi_n patches + multi-head weighting)
  */
 int vod_tafa_keyproj_chunk(int T1, int P, int C, int heads);
-int vod_tafa_keyproj_logits(const float *x_all, const float *G, float *parts, int T1, int N, int ph, int pw,
-                            int C, int heads, int cc, vod_stream_t stream);
+int vod_tafa_keyproj_logits(const float *x_all, const void *G, int g_dtype, float *parts, int T1, int N, int ph,
+                            int pw, int C, int heads, int cc, vod_stream_t stream);
 int vod_tafa_weighted_sum_logits(const float *x_all, const float *logit_parts, int nparts, float *out,
                                  int T1, int N, int P, int C, int heads, int out_layout, vod_stream_t stream);
 

@@ -43,7 +43,7 @@ SIGNATURES = {
     'vod_msra_gemm_candidates': (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     'vod_tafa_weighted_sum': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     'vod_tafa_keyproj_chunk': (_I, [_I, _I, _I, _I]),
-    'vod_tafa_keyproj_logits': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'vod_tafa_keyproj_logits': (_I, [_P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     'vod_tafa_weighted_sum_logits': (_I, [_P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
     'vod_nms_workspace_bytes': (_SZ, [_I, _I]),
     'vod_batched_nms': (_I, [_P, _P, _P, _I, _c.POINTER(_I), _I, _F, _I, _I, _P, _P, _P, _SZ, _P]),

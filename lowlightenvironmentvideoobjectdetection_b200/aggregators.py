@@ -96,11 +96,12 @@ class SelsaAggregator(nn.Module):
         torch.mm(self.ref_fc.weight.float(), ref_x.t(), out=vt_out)
         return k, vt_out, True
 
-    def attend(self, x, k, v, M, v_transposed):
+    def attend(self, x, k, v, M, v_transposed, q=None):
         """fc(softmax(fc_embed(x) K^T / sqrt(d)) V) for the first ``M`` reference rows of k / columns of V^T
-        (selsa_aggregator.py:50,57-72)."""
+        (selsa_aggregator.py:50,57-72).  ``q``: fc_embed(x) when the caller already computed it."""
         roi_n = x.shape[0]
-        q = self.fc_embed(x.float())                           # :50
+        if q is None:
+            q = self.fc_embed(x.float())                       # :50
         k = k[:M]
         if not v_transposed:
             v = v[:M]

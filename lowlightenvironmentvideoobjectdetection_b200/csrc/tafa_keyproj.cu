@@ -31,6 +31,8 @@
 //   FFMA2 / LDS core (bulk-copy issue, mbarrier waits, butterfly, tap control) -- the next thing to cut.
 #include <stdlib.h>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -38,8 +40,11 @@ namespace vod {
 
 constexpr int kKpHeads = 4;
 constexpr int kKpCC = 32;                         // channels per tile
-constexpr int kKpRowFloats = 9 * kKpCC;           // one (head, position) row of G for this chunk
-constexpr int kKpStageFloats = kKpHeads * kKpRowFloats;
+constexpr int kKpRowFloats = 9 * kKpCC;           // ELEMENTS of one (head, position) row of G for this chunk
+constexpr int kKpStageFloats = kKpHeads * kKpRowFloats;   // elements of one ring stage (4 head rows)
+// G element size GE: 4 = fp32, 2 = bf16 (round 2: G is 70 % of the kernel's bytes and a library GEMM's output; when the caller
+// allows reduced-precision library math it is produced and streamed in bf16 -- half the bytes here and in the GEMM that writes
+// it -- and unpacked to fp32 on the fly: one shift / mask per element, amortised over the lane's 4 frames).
 constexpr int kKpMaxWarps = 16;
 
 __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
@@ -60,8 +65,17 @@ __device__ __forceinline__ unsigned kp_tap_mask(int p, int ph, int pw) {
 
 // One output position: contract the 3x3 neighbourhood of p in the frame tile (xlane = tile + this lane's (tg, cg) offset) with
 // the four G rows in `gs`; returns the NV/8 sums this lane owns after the butterfly: v = cg*NV/8 + k, frame = v / H, head = v % H.
-template <int FR>
-__device__ __forceinline__ void kp_position(const float *__restrict__ xlane, const float *__restrict__ gs, int p, int P, int pw,
+// 4 consecutive G elements at element offset `e` of a ring stage (fp32: one 128-bit load; bf16: one 64-bit load + unpack)
+template <int GE>
+__device__ __forceinline__ float4 kp_load_g(const unsigned char *__restrict__ stage, int e) {
+    if (GE == 4) return *reinterpret_cast<const float4 *>(stage + (size_t)e * 4);
+    const uint2 w = *reinterpret_cast<const uint2 *>(stage + (size_t)e * 2);
+    return make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xffff0000u),
+                       __uint_as_float(w.y << 16), __uint_as_float(w.y & 0xffff0000u));
+}
+
+template <int FR, int GE>
+__device__ __forceinline__ void kp_position(const float *__restrict__ xlane, const unsigned char *__restrict__ gs, int p, int P, int pw,
                                             unsigned taps, int cg, float (&vc)[FR * kKpHeads / 8]) {
     constexpr int H = kKpHeads, CC = kKpCC, NV = FR * H;
     const int frame_floats = P * CC, row_floats = pw * CC;
@@ -79,7 +93,7 @@ __device__ __forceinline__ void kp_position(const float *__restrict__ xlane, con
         const float *xq = xp + (tap / 3 - 1) * row_floats + (tap % 3 - 1) * CC;
         float4 g[H];
 #pragma unroll
-        for (int h = 0; h < H; ++h) g[h] = *reinterpret_cast<const float4 *>(gs + h * kKpRowFloats + tap * CC);
+        for (int h = 0; h < H; ++h) g[h] = kp_load_g<GE>(gs, h * kKpRowFloats + tap * CC + cg * 4);
 #pragma unroll
         for (int u = 0; u < FR; ++u) {
             const float4 xv = *reinterpret_cast<const float4 *>(xq + u * frame_floats);
@@ -130,9 +144,9 @@ __device__ __forceinline__ void kp_position(const float *__restrict__ xlane, con
 // <TB = 8, NBUF = 2>: 8-frame tiles, double-buffered (a warp may run one tile ahead of the slowest).
 // <TB = 16, NBUF = 1>: 16-frame tiles (twice the FMAs per shared-memory load and per G byte), one buffer: the next tile is
 //   requested when every warp has left the current one; the G rings keep streaming across that gap.
-template <int TB, int NBUF>
+template <int TB, int NBUF, int GE>
 __global__ void __launch_bounds__(kKpMaxWarps * 32, 1)
-tafa_keyproj_persist_kernel(const __grid_constant__ CUtensorMap tm_x, const float *__restrict__ G, float *__restrict__ parts,
+tafa_keyproj_persist_kernel(const __grid_constant__ CUtensorMap tm_x, const unsigned char *__restrict__ G, float *__restrict__ parts,
                             int T1, int N, int ph, int pw, int C, int depth, int tiles_per_cta, int dbg) {
     constexpr int H = kKpHeads, CC = kKpCC, FR = TB / 4, NV = FR * H;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -144,12 +158,13 @@ tafa_keyproj_persist_kernel(const __grid_constant__ CUtensorMap tm_x, const floa
     const int my_tiles = max(0, min(tiles_per_cta, total_tiles - tile0));
     const int tile_floats = TB * P * CC;
     float *xs = reinterpret_cast<float *>(smem_raw);                                    // [NBUF][TB][P][CC]
-    float *ring = xs + NBUF * (size_t)tile_floats;                                      // [nwc][depth][H][9][CC]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(ring + (size_t)nwc * depth * kKpStageFloats);   // [nwc][depth], xfull[2], xempty[2]
+    constexpr int kStageBytes = kKpStageFloats * GE, kRowBytes = kKpRowFloats * GE;
+    unsigned char *ring = reinterpret_cast<unsigned char *>(xs + NBUF * (size_t)tile_floats);   // [nwc][depth][H][9][CC] of GE bytes
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ring + (size_t)nwc * depth * kStageBytes);      // [nwc][depth], xfull[2], xempty[2]
     uint64_t *xfull = bars + nwc * depth, *xempty = xfull + 2;
     unsigned *tap_mask = reinterpret_cast<unsigned *>(xempty + 2);                      // [P]
     const size_t NP = (size_t)N * P;
-    const size_t head_stride = NP * 9 * (size_t)C;        // floats between the heads of G
+    const size_t head_stride = NP * 9 * (size_t)C * GE;   // bytes between the heads of G
 
     if (tid == 0) {
         for (int b = 0; b < NBUF; ++b) { tc::mbar_init(xfull + b, 1); tc::mbar_init(xempty + b, nwc); }
@@ -180,24 +195,24 @@ tafa_keyproj_persist_kernel(const __grid_constant__ CUtensorMap tm_x, const floa
     }
 
     // ---- consumers: warp w owns positions w, w + nwc, ... of the CTA's concatenated (tile, position) stream (nwc <= P)
-    float *my_ring = ring + (size_t)warp * depth * kKpStageFloats;
+    unsigned char *my_ring = ring + (size_t)warp * depth * kStageBytes;
     uint64_t *my_bars = bars + warp * depth;
     // lane 0 feeds the warp's own ring, `depth` positions ahead of the consumer: (ji, pi) = tile and position of the next
     // stage to request, si = its ring stage; gi_row = G row of (tile ji, position 0) for this chunk
     int ji = 0, pi = warp, si = 0, ji_cur = -1;
-    const float *gi_row = nullptr;
+    const unsigned char *gi_row = nullptr;
     auto issue = [&]() {
         if (ji >= my_tiles) return;
         if (ji != ji_cur) {
             ji_cur = ji;
             const unsigned nc = (unsigned)(tile0 + ji) / ntb;            // n*nch + chunk
-            gi_row = G + ((size_t)(nc / nch) * P * nch + (size_t)(nc % nch)) * kKpRowFloats;
+            gi_row = G + ((size_t)(nc / nch) * P * nch + (size_t)(nc % nch)) * kRowBytes;
         }
-        tc::mbar_arrive_expect_tx(my_bars + si, kKpStageFloats * 4);
-        const float *row = gi_row + (size_t)pi * nch * kKpRowFloats;
+        tc::mbar_arrive_expect_tx(my_bars + si, kStageBytes);
+        const unsigned char *row = gi_row + (size_t)pi * nch * kRowBytes;
 #pragma unroll
         for (int h = 0; h < H; ++h)
-            bulk_g2s(my_ring + (size_t)si * kKpStageFloats + h * kKpRowFloats, row + (size_t)h * head_stride, kKpRowFloats * 4,
+            bulk_g2s(my_ring + (size_t)si * kStageBytes + h * kRowBytes, row + (size_t)h * head_stride, kRowBytes,
                      my_bars + si);
         if (++si == depth) si = 0;
         pi += nwc;
@@ -223,7 +238,7 @@ tafa_keyproj_persist_kernel(const __grid_constant__ CUtensorMap tm_x, const floa
         }
         tc::mbar_wait(my_bars + s, phase);
         float vc[NV / 8];
-        kp_position<FR>(xlane, my_ring + (size_t)s * kKpStageFloats + cg * 4, p, P, pw, tap_mask[p], cg, vc);
+        kp_position<FR, GE>(xlane, my_ring + (size_t)s * kStageBytes, p, P, pw, tap_mask[p], cg, vc);
         // every lane's sums (hence its reads of stage s and of the frame tile) are complete once it has taken part in the
         // butterfly shuffles: lane 0 may hand the stage back to the copy engine
         if (lane == 0) {
@@ -248,9 +263,9 @@ tafa_keyproj_persist_kernel(const __grid_constant__ CUtensorMap tm_x, const floa
 
 // ------------------------------------------------------------------------------------------------ one CTA per tile
 // TB = frames per CTA: 8 -> [8][P][32] tile + 7 x 2 G stages = 112 KB, two CTAs per SM; 16 -> one CTA per SM, G read once.
-template <int TB, int MAXW, int MINB>
+template <int TB, int MAXW, int MINB, int GE>
 __global__ void __launch_bounds__(MAXW * 32, MINB)
-tafa_keyproj_logits_kernel(const __grid_constant__ CUtensorMap tm_x, const float *__restrict__ G, float *__restrict__ parts,
+tafa_keyproj_logits_kernel(const __grid_constant__ CUtensorMap tm_x, const unsigned char *__restrict__ G, float *__restrict__ parts,
                            int T1, int N, int ph, int pw, int C, int depth, int dbg) {
     constexpr int H = kKpHeads, CC = kKpCC, FR = TB / 4, NV = FR * H;   // FR frames per lane group, NV sums per lane
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -260,25 +275,26 @@ tafa_keyproj_logits_kernel(const __grid_constant__ CUtensorMap tm_x, const float
     const int tg = lane >> 3, cg = lane & 7;
     const int t0 = tb * TB, nt = min(TB, T1 - t0);
     float *xs = reinterpret_cast<float *>(smem_raw);                                   // [TB][P][CC]
-    float *ring = xs + (size_t)TB * P * CC;                                            // [nwarps][depth][H][9][CC]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(ring + (size_t)nwarps * depth * kKpStageFloats);   // [nwarps][depth] + 1
+    constexpr int kStageBytes = kKpStageFloats * GE, kRowBytes = kKpRowFloats * GE;
+    unsigned char *ring = reinterpret_cast<unsigned char *>(xs + (size_t)TB * P * CC);  // [nwarps][depth][H][9][CC] of GE bytes
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ring + (size_t)nwarps * depth * kStageBytes);   // [nwarps][depth] + 1
     uint64_t *xbar = bars + nwarps * depth;
     const size_t NP = (size_t)N * P;
-    const size_t head_stride = NP * 9 * (size_t)C;        // floats between the heads of G
-    const float *g_roi = G + ((size_t)n * P * nch + chunk) * kKpRowFloats;   // + p * nch*9*CC + h * head_stride
+    const size_t head_stride = NP * 9 * (size_t)C * GE;   // bytes between the heads of G
+    const unsigned char *g_roi = G + ((size_t)n * P * nch + chunk) * kRowBytes;   // + p * nch*9*CC*GE + h * head_stride
 
-    float *my_ring = ring + (size_t)warp * depth * kKpStageFloats;
+    unsigned char *my_ring = ring + (size_t)warp * depth * kStageBytes;
     uint64_t *my_bars = bars + warp * depth;
     auto issue = [&](int i) {
         const int p = warp + i * nwarps;
         if (p >= P) return;
         if ((dbg & 2) && i >= depth) return;
         const int s = i % depth;
-        tc::mbar_arrive_expect_tx(my_bars + s, kKpStageFloats * 4);
-        const float *row = g_roi + (size_t)p * nch * kKpRowFloats;
+        tc::mbar_arrive_expect_tx(my_bars + s, kStageBytes);
+        const unsigned char *row = g_roi + (size_t)p * nch * kRowBytes;
 #pragma unroll
         for (int h = 0; h < H; ++h)
-            bulk_g2s(my_ring + (size_t)s * kKpStageFloats + h * kKpRowFloats, row + (size_t)h * head_stride, kKpRowFloats * 4,
+            bulk_g2s(my_ring + (size_t)s * kStageBytes + h * kRowBytes, row + (size_t)h * head_stride, kRowBytes,
                      my_bars + s);
     };
     if (lane == 0) {
@@ -303,7 +319,7 @@ tafa_keyproj_logits_kernel(const __grid_constant__ CUtensorMap tm_x, const float
         const int s = i % depth;
         if (!((dbg & 2) && i >= depth)) tc::mbar_wait(my_bars + s, (uint32_t)((i / depth) & 1));
         float vc[NV / 8];
-        kp_position<FR>(xlane, my_ring + (size_t)s * kKpStageFloats + cg * 4, p, P, pw, (dbg & 1) ? 0u : kp_tap_mask(p, ph, pw), cg, vc);
+        kp_position<FR, GE>(xlane, my_ring + (size_t)s * kStageBytes, p, P, pw, (dbg & 1) ? 0u : kp_tap_mask(p, ph, pw), cg, vc);
         if (lane == 0) issue(i + depth);
 #pragma unroll
         for (int k = 0; k < NV / 8; ++k) {
@@ -318,8 +334,8 @@ tafa_keyproj_logits_kernel(const __grid_constant__ CUtensorMap tm_x, const float
 
 using namespace vod;
 
-static size_t kp_smem_bytes(int tile_frames, int P, int warps, int depth) {
-    return (size_t)tile_frames * P * kKpCC * sizeof(float) + (size_t)warps * depth * (kKpStageFloats * sizeof(float) + 8) + 64 + (size_t)P * 4;
+static size_t kp_smem_bytes(int tile_frames, int P, int warps, int depth, int ge = 4) {
+    return (size_t)tile_frames * P * kKpCC * sizeof(float) + (size_t)warps * depth * ((size_t)kKpStageFloats * ge + 8) + 64 + (size_t)P * 4;
 }
 constexpr size_t kKpSmemLimit = 227 * 1024;
 
@@ -332,8 +348,11 @@ extern "C" int vod_tafa_keyproj_chunk(int T1, int P, int C, int heads) {
     return kKpCC;
 }
 
-extern "C" int vod_tafa_keyproj_logits(const float *x_all, const float *G, float *parts, int T1, int N, int ph, int pw,
+extern "C" int vod_tafa_keyproj_logits(const float *x_all, const void *G_, int g_dtype, float *parts, int T1, int N, int ph, int pw,
                                        int C, int heads, int cc, vod_stream_t stream) {
+    const unsigned char *G = reinterpret_cast<const unsigned char *>(G_);
+    VOD_REQUIRE(g_dtype == VOD_DTYPE_F32 || g_dtype == VOD_DTYPE_BF16, "vod_tafa_keyproj_logits: g_dtype");
+    const int ge = g_dtype == VOD_DTYPE_BF16 ? 2 : 4;
     if (N == 0) return VOD_OK;
     VOD_REQUIRE(x_all && G && parts, "vod_tafa_keyproj_logits: null pointer");
     VOD_REQUIRE(T1 > 0 && N > 0 && ph > 0 && pw > 0 && C > 0, "vod_tafa_keyproj_logits: bad dims");
@@ -360,13 +379,13 @@ extern "C" int vod_tafa_keyproj_logits(const float *x_all, const float *G, float
 #endif
     if (persist) warps = min(warps, kKpMaxWarps - 1);      // + the producer warp
     const int tile_frames = persist ? 16 : tb;              // persistent: 2 x 8 frames (double buffer) or 1 x 16
-    while (warps > 4 && kp_smem_bytes(tile_frames, P, warps, depth) > kKpSmemLimit) --warps;
-    while (depth > 2 && kp_smem_bytes(tile_frames, P, warps, depth) > kKpSmemLimit) --depth;
-    if (persist && kp_smem_bytes(tile_frames, P, warps, depth) > kKpSmemLimit) {   // large patches: one tile per CTA
+    while (warps > 4 && kp_smem_bytes(tile_frames, P, warps, depth, ge) > kKpSmemLimit) --warps;
+    while (depth > 2 && kp_smem_bytes(tile_frames, P, warps, depth, ge) > kKpSmemLimit) --depth;
+    if (persist && kp_smem_bytes(tile_frames, P, warps, depth, ge) > kKpSmemLimit) {   // large patches: one tile per CTA
         persist = 0;
         tb = 8;
     }
-    const size_t smem = kp_smem_bytes(persist ? 16 : tb, P, warps, depth);
+    const size_t smem = kp_smem_bytes(persist ? 16 : tb, P, warps, depth, ge);
     VOD_REQUIRE(smem <= kKpSmemLimit, "vod_tafa_keyproj_logits: tile does not fit shared memory");
     // x_all [T1][N*P][C] as a 3-D tensor, box = (32 channels, P positions, tb frames)
     CUtensorMap tm_x;
@@ -385,18 +404,25 @@ extern "C" int vod_tafa_keyproj_logits(const float *x_all, const float *G, float
 #endif
         const int tiles_per_cta = (int)ceil_div(total_tiles, (long)sms);
         const int grid = (int)ceil_div(total_tiles, (long)tiles_per_cta);
-        if (tb == 16)
-            allow(tafa_keyproj_persist_kernel<16, 1>)<<<grid, (warps + 1) * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, tiles_per_cta, dbg);
-        else
-            allow(tafa_keyproj_persist_kernel<8, 2>)<<<grid, (warps + 1) * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, tiles_per_cta, dbg);
+#define VOD_KP_PERSIST(TB_, NB_)                                                                                                   \
+    do {                                                                                                                           \
+        if (ge == 2) allow(tafa_keyproj_persist_kernel<TB_, NB_, 2>)<<<grid, (warps + 1) * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, tiles_per_cta, dbg); \
+        else allow(tafa_keyproj_persist_kernel<TB_, NB_, 4>)<<<grid, (warps + 1) * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, tiles_per_cta, dbg);         \
+    } while (0)
+        if (tb == 16) VOD_KP_PERSIST(16, 1);
+        else VOD_KP_PERSIST(8, 2);
+#undef VOD_KP_PERSIST
     } else {
         dim3 grid(ceil_div(T1, tb), C / cc, N);
-        if (tb == 16)
-            allow(tafa_keyproj_logits_kernel<16, kKpMaxWarps, 1>)<<<grid, warps * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, dbg);
-        else if (warps <= 8 && kp_smem_bytes(tb, P, warps, depth) <= 113 * 1024)
-            allow(tafa_keyproj_logits_kernel<8, 8, 2>)<<<grid, warps * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, dbg);
-        else
-            allow(tafa_keyproj_logits_kernel<8, kKpMaxWarps, 1>)<<<grid, warps * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, dbg);
+#define VOD_KP_TILE(TB_, MW_, MB_)                                                                                                 \
+    do {                                                                                                                           \
+        if (ge == 2) allow(tafa_keyproj_logits_kernel<TB_, MW_, MB_, 2>)<<<grid, warps * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, dbg); \
+        else allow(tafa_keyproj_logits_kernel<TB_, MW_, MB_, 4>)<<<grid, warps * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, dbg);         \
+    } while (0)
+        if (tb == 16) VOD_KP_TILE(16, kKpMaxWarps, 1);
+        else if (warps <= 8 && kp_smem_bytes(tb, P, warps, depth, ge) <= 113 * 1024) VOD_KP_TILE(8, 8, 2);
+        else VOD_KP_TILE(8, kKpMaxWarps, 1);
+#undef VOD_KP_TILE
     }
     note_launch();
     return check_launch("vod_tafa_keyproj_logits");

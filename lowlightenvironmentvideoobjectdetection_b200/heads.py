@@ -107,6 +107,8 @@ class SelsaBBoxHead(nn.Module):
             w = self._fc0_weight(channels_last) if i == 0 else fc.weight
             y = self._linear_few_rows(y, w, fc.bias)                      # :53-55, key and new reference rows in one GEMM
             agg = self.aggregator[i]
+
+            # (running these small GEMMs on a side stream next to the key rows' Q projection was measured: 547.8 vs 547.4 frames/s)
             for j0, s0, n_run in runs:                                    # :55,64 of selsa_aggregator.py, new frames only
                 r = y[n_key + j0 * N:n_key + (j0 + n_run) * N]
                 lo, hi = s0 * N, (s0 + n_run) * N

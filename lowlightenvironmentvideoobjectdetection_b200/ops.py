@@ -532,16 +532,17 @@ def tafa_keyproj_chunk(T1, P, C, num_heads):
 
 
 def tafa_keyproj_logits(x_all, G, output_size, num_heads, cc):
-    """x_all [T1, N, P, C], G [heads, N*P, C/cc, 9, cc] (key embedding x conv weight, see include/vodagg.h)
+    """x_all [T1, N, P, C], G [heads, N*P, C/cc, 9, cc] fp32 or bf16 (key embedding x conv weight, see include/vodagg.h)
     -> per-chunk partial logits [C/cc, N, P, heads, T1] (unscaled)."""
     _lib.require_cuda(x_all, G)
     ph, pw = _pair(output_size)
     T1, N, P, C = x_all.shape
     assert P == ph * pw and x_all.is_contiguous() and x_all.dtype == torch.float32
-    assert G.is_contiguous() and G.dtype == torch.float32 and G.numel() == num_heads * N * P * 9 * C
+    assert G.is_contiguous() and G.dtype in (torch.float32, torch.bfloat16) and G.numel() == num_heads * N * P * 9 * C
     parts = torch.empty((C // cc, N, P, num_heads, T1), dtype=torch.float32, device=x_all.device)
     if N:
-        _lib.call('vod_tafa_keyproj_logits', _lib.ptr(x_all), _lib.ptr(G), _lib.ptr(parts), T1, N, ph, pw, C,
+        _lib.call('vod_tafa_keyproj_logits', _lib.ptr(x_all), _lib.ptr(G),
+                  _lib.VOD_DTYPE_F32 if G.dtype == torch.float32 else _lib.VOD_DTYPE_BF16, _lib.ptr(parts), T1, N, ph, pw, C,
                   int(num_heads), int(cc), _lib.stream_ptr(x_all.device))
     return parts
 

@@ -147,6 +147,11 @@ class TemporalRoIAlign(SingleRoIExtractor):
         # the key-slot embed conv + G product depend on the key RoI features only: run them on a side stream next to the
         # most-similar search (False = everything on one stream)
         self.overlap = True
+        # dtype of the key-projected G operand (a library GEMM's output, 70 % of the logits kernel's bytes): None = follow the
+        # caller's library-math switch -- bf16 when torch.backends.cuda.matmul.allow_tf32 permits reduced-precision GEMMs
+        # (features then agree with fp32 to ~5e-4 instead of ~1e-4, still inside the 1e-3 bar), fp32 otherwise;
+        # torch.float32 / torch.bfloat16 force it
+        self.keyproj_g_dtype = None
 
     def _stack_key_and_refs(self, feat, rois, ref_feat, return_indices=False, want_prepared=False):
         """RoIAlign(key) + most-similar RoI features, stacked as x_all [T+1, N, P, C] (NHWC rows)."""
@@ -224,16 +229,21 @@ class TemporalRoIAlign(SingleRoIExtractor):
             self._w_cl = (key, conv.weight.detach().contiguous(memory_format=torch.channels_last))
         return self._w_cl[1]
 
-    def _keyproj_weight(self, conv, heads, cc):
+    def _keyproj_weight(self, conv, heads, cc, dtype=torch.float32):
         """conv weight [C, C, 3, 3] -> [heads, C/heads, 9*C] with columns ordered (channel chunk, tap, channel in chunk):
         the right-hand side of the G GEMM, laid out so that each (RoI, chunk) CTA of the logits kernel reads contiguous rows."""
-        key = (conv.weight._version, conv.weight.data_ptr(), heads, cc)
+        key = (conv.weight._version, conv.weight.data_ptr(), heads, cc, dtype)
         if getattr(self, '_w_kp', None) is None or self._w_kp[0] != key:
             w = conv.weight.detach().float()
             C = w.shape[0]
             wr = w.view(heads, C // heads, C // cc, cc, 9).permute(0, 1, 2, 4, 3).reshape(heads, C // heads, 9 * C)
-            self._w_kp = (key, wr.contiguous())
+            self._w_kp = (key, wr.contiguous().to(dtype))
         return self._w_kp[1]
+
+    def _g_dtype(self):
+        if self.keyproj_g_dtype is not None:
+            return self.keyproj_g_dtype
+        return torch.bfloat16 if torch.backends.cuda.matmul.allow_tf32 else torch.float32
 
     def _keyproj_chunk(self, T1, P, C):
         """Channel-chunk width for the key-projected path, 0 when the full-embedding path must be taken."""
@@ -257,7 +267,9 @@ class TemporalRoIAlign(SingleRoIExtractor):
         key_patches = x_key.view(N, rh, rw, C).permute(0, 3, 1, 2)
         ek = torch.nn.functional.conv2d(key_patches, self._conv_weight_cl(conv), conv.bias, 1, 1)
         ek = ek.permute(0, 2, 3, 1).contiguous().view(N * P, heads, C // heads)   # no copy (channels_last)
-        G = torch.bmm(ek.transpose(0, 1), self._keyproj_weight(conv, heads, cc))  # [heads, N*P, 9*C]
+        gd = self._g_dtype()
+        # [heads, N*P, 9*C]; bf16: the GEMM runs on bf16 operands and writes half the bytes (it is write-bound)
+        G = torch.bmm(ek.transpose(0, 1).to(gd), self._keyproj_weight(conv, heads, cc, gd))
         return G, cc
 
     def _tafa(self, x_all, rh, rw, out=None, prepared=None):

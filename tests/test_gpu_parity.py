@@ -326,6 +326,50 @@ def test_tafa_keyproj_vs_oracle(T1, N, C):
         assert rel_err(out, want) < TIGHT
 
 
+@pytest.mark.parametrize('T1,N,C', [(16, 9, 512), (6, 3, 64), (19, 2, 128)])
+def test_tafa_keyproj_bf16_g_operand(T1, N, C):
+    """Round 2: G may arrive in bf16 (half the bytes of the kernel's dominant stream).  The kernel unpacks it to fp32 on the
+    fly, so feeding bf16 G must equal feeding the same values as fp32 -- bit for bit -- on every kernel variant (persistent
+    16-frame tiles, one CTA per 8-frame tile); against the un-rounded G the logits move by bf16 rounding only."""
+    g = torch.Generator().manual_seed(330 + T1)
+    x_all = torch.randn(T1, N, 49, C, generator=g).to(DEV)
+    cc = ops.tafa_keyproj_chunk(T1, 49, C, 4)
+    G = (torch.randn(4, N * 49, 9 * C, generator=g) * 0.1).to(DEV)
+    Gh = G.bfloat16()
+    a = ops.tafa_keyproj_logits(x_all, Gh, 7, 4, cc)
+    b = ops.tafa_keyproj_logits(x_all, Gh.float(), 7, 4, cc)
+    assert torch.equal(a, b)
+    full = ops.tafa_keyproj_logits(x_all, G, 7, 4, cc)
+    assert rel_err(a.sum(0), full.sum(0)) < 5e-3
+
+
+def test_temporal_roi_align_g_dtype_follows_the_library_math_switch():
+    """TemporalRoIAlign keeps G in bf16 only when the caller allows reduced-precision library GEMMs (allow_tf32); stated
+    tolerance of that mode against fp32: 1e-3 (measured 4.7e-4 at cfg 3)."""
+    torch.manual_seed(0)
+    g = torch.Generator().manual_seed(45)
+    m = vod.build_roi_extractor(dict(type='TemporalRoIAlign', num_most_similar_points=2, num_temporal_attention_blocks=4,
+                                     roi_layer=dict(type='RoIAlign', output_size=7, sampling_ratio=2),
+                                     out_channels=512, featmap_strides=[16])).to(DEV)
+    T, N = 9, 64
+    ref = torch.relu(torch.randn(T, 512, 38, 63, generator=g)).to(DEV)
+    rois = rpn_like_rois(g, N, 1).to(DEV)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    assert m._g_dtype() == torch.float32
+    exact = m((ref[-1:],), rois, ref_feats=(ref,))
+    m.keyproj_g_dtype = torch.bfloat16
+    forced = m((ref[-1:],), rois, ref_feats=(ref,))
+    m.keyproj_g_dtype = None
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    assert m._g_dtype() == torch.bfloat16
+    reduced = m((ref[-1:],), rois, ref_feats=(ref,))
+    assert rel_err(forced, exact) < 1e-3 and rel_err(reduced, exact) < 1e-3
+    m.keyproj_g_dtype = torch.float32
+    assert rel_err(m((ref[-1:],), rois, ref_feats=(ref,)), exact) < 3e-4      # tf32 conv / GEMM only
+
+
 def test_tafa_keyproj_unsupported_shapes_take_the_embedding_path():
     assert ops.tafa_keyproj_chunk(16, 49, 512, 4) == 32 and ops.tafa_keyproj_chunk(32, 49, 512, 4) == 32
     assert ops.tafa_keyproj_chunk(64, 49, 512, 4) == 32     # frames are tiled 16 per CTA

@@ -705,7 +705,9 @@ def bench_selsa(ctx, cfg, cfg_name):
     T, N = cfg['T'], cfg['N']
     config = dict(workload=cfg['workload'], proposals=N, ref_frames=T - 1, shared_fcs=cfg['fcs'],
                   execution='one CUDA graph per key-frame step (SelsaRoIHead.capture_graph), inputs copied into its static buffers',
-                  library_math='cuBLAS shared FCs / projections and the cuDNN key-slot conv in tf32 (fp32_library_math: the same in fp32)',
+                  library_math='reduced precision allowed (allow_tf32): cuBLAS shared FCs / projections and the cuDNN key-slot conv in tf32, '
+                               'TemporalRoIAlign\'s key-projected G operand in bf16; own kernels fp32 / tf32 tcgen05 (SELSA) / bf16 tcgen05 '
+                               'candidate pre-filter.  fp32_library_math: every library call and G in fp32',
                   feature='[T,512,38,63] fp32', l2_policy='per-step working set (>1.4 GB at cfg3) exceeds the 126 MB L2; '
                   'inputs rotate over 4 clip positions', parallelism='clip-sharded x%d' % world)
     run = SelsaRunner(ctx, cfg)

@@ -63,8 +63,8 @@ __device__ __forceinline__ unsigned kp_tap_mask(int p, int ph, int pw) {
     return m;
 }
 
-// One output position: contract the 3x3 neighbourhood of p in the frame tile (xlane = tile + this lane's (tg, cg) offset) with
-// the four G rows in `gs`; returns the NV/8 sums this lane owns after the butterfly: v = cg*NV/8 + k, frame = v / H, head = v % H.
+// One output position: contract the 3x3 neighbourhood of the position at `xp` (this lane's (tg, cg) slice of it; row_floats /
+// frame_floats = distance to the patch row below / to the next frame in the shared-memory tile) with the four G rows in `gs`; returns the NV/8 sums this lane owns after the butterfly: v = cg*NV/8 + k, frame = v / H, head = v % H.
 // 4 consecutive G elements at element offset `e` of a ring stage (fp32: one 128-bit load; bf16: one 64-bit load + unpack)
 template <int GE>
 __device__ __forceinline__ float4 kp_load_g(const unsigned char *__restrict__ stage, int e) {
@@ -75,11 +75,9 @@ __device__ __forceinline__ float4 kp_load_g(const unsigned char *__restrict__ st
 }
 
 template <int FR, int GE>
-__device__ __forceinline__ void kp_position(const float *__restrict__ xlane, const unsigned char *__restrict__ gs, int p, int P, int pw,
-                                            unsigned taps, int cg, float (&vc)[FR * kKpHeads / 8]) {
+__device__ __forceinline__ void kp_position(const float *__restrict__ xp, const unsigned char *__restrict__ gs, int row_floats,
+                                            int frame_floats, unsigned taps, int cg, float (&vc)[FR * kKpHeads / 8]) {
     constexpr int H = kKpHeads, CC = kKpCC, NV = FR * H;
-    const int frame_floats = P * CC, row_floats = pw * CC;
-    const float *xp = xlane + p * CC;
 
     // packed fp32x2 FMAs (FFMA2: the full-rate fp32 path of sm_100): even / odd channels accumulate separately
     float2 acc2[FR][H];
@@ -142,13 +140,22 @@ __device__ __forceinline__ void kp_position(const float *__restrict__ xlane, con
 // ------------------------------------------------------------------------------------------------ persistent kernel
 // blockDim = (nwc + 1) warps: warps 0..nwc-1 consume, warp nwc produces the frame tiles.  Requires nwc <= P.
 // <TB = 8, NBUF = 2>: 8-frame tiles, double-buffered (a warp may run one tile ahead of the slowest).
-// <TB = 16, NBUF = 1>: 16-frame tiles (twice the FMAs per shared-memory load and per G byte), one buffer: the next tile is
-//   requested when every warp has left the current one; the G rings keep streaming across that gap.
-template <int TB, int NBUF, int GE>
+// <TB = 16, NBUF = 1>: 16-frame tiles (twice the FMAs per shared-memory load and per G byte), one buffer.
+//   ROWP = false: the tile is one TMA box, requested when every warp has left the previous tile (ncu, round 2: the consumer
+//     warps then sit ~30 % of their time on that barrier -- 98 KB per tile cannot hide behind a one-tile buffer).
+//   ROWP = true (shipped): the tile is laid out [patch row][frame][pw][32] and travels as `ph` boxes (one per patch row, all
+//     16 frames), each with its own full / empty barrier pair.  A warp walks its positions in increasing order, so once every
+//     warp is past the positions that read patch row r (rows r-1 .. r+1 of the outputs), row r of the NEXT tile is requested
+//     while rows r+1.. of the current one are still being used: the single buffer behaves like a rolling window and the
+//     load of tile j+1 overlaps the FMAs of tile j.
+constexpr int kKpMaxRows = 16;                    // patch rows with their own barrier pair (ROWP)
+
+template <int TB, int NBUF, int GE, bool ROWP>
 __global__ void __launch_bounds__(kKpMaxWarps * 32, 1)
 tafa_keyproj_persist_kernel(const __grid_constant__ CUtensorMap tm_x, const unsigned char *__restrict__ G, float *__restrict__ parts,
                             int T1, int N, int ph, int pw, int C, int depth, int tiles_per_cta, int dbg) {
     constexpr int H = kKpHeads, CC = kKpCC, FR = TB / 4, NV = FR * H;
+    static_assert(!ROWP || NBUF == 1, "row pipelining replaces the double buffer");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int nch = C / CC, ntb = ceil_div(T1, TB), P = ph * pw;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwc = (blockDim.x >> 5) - 1;
@@ -157,35 +164,56 @@ tafa_keyproj_persist_kernel(const __grid_constant__ CUtensorMap tm_x, const unsi
     const int tile0 = blockIdx.x * tiles_per_cta;
     const int my_tiles = max(0, min(tiles_per_cta, total_tiles - tile0));
     const int tile_floats = TB * P * CC;
-    float *xs = reinterpret_cast<float *>(smem_raw);                                    // [NBUF][TB][P][CC]
+    // shared-memory tile: [TB][P][CC] (one box) or [ph][TB][pw][CC] (one box per patch row)
+    const int row_floats = ROWP ? TB * pw * CC : pw * CC, frame_floats = ROWP ? pw * CC : P * CC;
+    float *xs = reinterpret_cast<float *>(smem_raw);
     constexpr int kStageBytes = kKpStageFloats * GE, kRowBytes = kKpRowFloats * GE;
     unsigned char *ring = reinterpret_cast<unsigned char *>(xs + NBUF * (size_t)tile_floats);   // [nwc][depth][H][9][CC] of GE bytes
-    uint64_t *bars = reinterpret_cast<uint64_t *>(ring + (size_t)nwc * depth * kStageBytes);      // [nwc][depth], xfull[2], xempty[2]
-    uint64_t *xfull = bars + nwc * depth, *xempty = xfull + 2;
-    unsigned *tap_mask = reinterpret_cast<unsigned *>(xempty + 2);                      // [P]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ring + (size_t)nwc * depth * kStageBytes);      // [nwc][depth], xfull[], xempty[]
+    uint64_t *xfull = bars + nwc * depth, *xempty = xfull + kKpMaxRows;
+    unsigned *tap_mask = reinterpret_cast<unsigned *>(xempty + kKpMaxRows);             // [P]: tap mask | patch row << 16
     const size_t NP = (size_t)N * P;
     const size_t head_stride = NP * 9 * (size_t)C * GE;   // bytes between the heads of G
+    const int nxb = ROWP ? ph : NBUF;                     // frame-tile barrier pairs in use
 
     if (tid == 0) {
-        for (int b = 0; b < NBUF; ++b) { tc::mbar_init(xfull + b, 1); tc::mbar_init(xempty + b, nwc); }
+        for (int b = 0; b < nxb; ++b) { tc::mbar_init(xfull + b, 1); tc::mbar_init(xempty + b, nwc); }
         for (int s = 0; s < nwc * depth; ++s) tc::mbar_init(bars + s, 1);
         tc::fence_barrier_init();
     }
-    for (int q = tid; q < P; q += blockDim.x) tap_mask[q] = (dbg & 1) ? 0u : kp_tap_mask(q, ph, pw);
+    for (int q = tid; q < P; q += blockDim.x) tap_mask[q] = ((dbg & 1) ? 0u : kp_tap_mask(q, ph, pw)) | ((unsigned)(q / pw) << 16);
     __syncthreads();
     if (my_tiles == 0) return;
 
     if (warp == nwc) {
-        // ---- producer: frame tile j of this CTA -> buffer j & 1 as one 3-D TMA box (frames past T1 arrive as zeros)
+        // ---- producer (frames past T1 arrive as zeros)
         if (lane == 0) {
             for (int j = 0; j < my_tiles; ++j) {
+                const unsigned tile = tile0 + j, nc = tile / ntb;
+                const int c0 = (int)(nc % nch) * CC, r0 = (int)(nc / nch) * P, f0 = (int)(tile % ntb) * TB;
+                if (ROWP) {
+                    for (int r = 0; r < ph; ++r) {
+                        if (j > 0) tc::mbar_wait(xempty + r, (uint32_t)((j - 1) & 1));   // every warp is past row r of tile j-1
+                        if (!(dbg & 4)) {
+                            tc::mbar_arrive_expect_tx(xfull + r, (uint32_t)(row_floats * sizeof(float)));
+                            tc::tma_load_3d(xs + (size_t)r * row_floats, &tm_x, xfull + r, c0, r0 + r * pw, f0);
+                        } else {
+                            tc::mbar_arrive(xfull + r);
+                        }
+                    }
+                    continue;
+                }
                 const int b = j % NBUF;
                 if (j >= NBUF) tc::mbar_wait(xempty + b, (uint32_t)((j / NBUF - 1) & 1));   // consumers are done with tile j-NBUF
-                const unsigned tile = tile0 + j, nc = tile / ntb;
                 if (!(dbg & 4)) {
                     tc::mbar_arrive_expect_tx(xfull + b, (uint32_t)(tile_floats * sizeof(float)));
-                    tc::tma_load_3d(xs + (size_t)b * tile_floats, &tm_x, xfull + b, (int)(nc % nch) * CC, (int)(nc / nch) * P,
-                                    (int)(tile % ntb) * TB);
+                    tc::tma_load_3d(xs + (size_t)b * tile_floats, &tm_x, xfull + b, c0, r0, f0);
+                    // one buffer: the consumers cannot overlap the NEXT tile's load with their FMAs, so at least its HBM leg is
+                    // started now (L2 prefetch); the load issued when they leave this tile then comes from L2
+                    if (NBUF == 1 && j + 1 < my_tiles && !(dbg & 8)) {
+                        const unsigned t2 = tile + 1, nc2 = t2 / ntb;
+                        tc::tma_prefetch_3d(&tm_x, (int)(nc2 % nch) * CC, (int)(nc2 / nch) * P, (int)(t2 % ntb) * TB);
+                    }
                 } else {
                     tc::mbar_arrive(xfull + b);
                 }
@@ -224,6 +252,7 @@ tafa_keyproj_persist_kernel(const __grid_constant__ CUtensorMap tm_x, const unsi
     int j = 0, p = warp, s = 0;                           // current tile (local index), position, ring stage
     uint32_t phase = 0;
     int cur = -1, t0 = 0, nt = 0;
+    int rows_seen = 0, rows_freed = 0;                    // ROWP: patch rows of tile j waited for / handed back by this warp
     int refills = (dbg & 2) ? 0 : 0x7fffffff;
     float *out_tile = nullptr;
     const float *xlane = nullptr;
@@ -233,12 +262,22 @@ tafa_keyproj_persist_kernel(const __grid_constant__ CUtensorMap tm_x, const unsi
             const unsigned tile = tile0 + j, nc = tile / ntb;
             t0 = (int)(tile % ntb) * TB; nt = min(TB, T1 - t0);
             out_tile = parts + ((size_t)(nc % nch) * N + nc / nch) * P * H * T1 + t0;    // [chunk][n] + frame block
-            tc::mbar_wait(xfull + j % NBUF, (uint32_t)((j / NBUF) & 1));
-            xlane = xs + (size_t)(j % NBUF) * tile_floats + (size_t)tg * FR * P * CC + cg * 4;
+            if (ROWP) {
+                rows_seen = rows_freed = 0;
+                xlane = xs + (size_t)tg * FR * frame_floats + cg * 4;
+            } else {
+                tc::mbar_wait(xfull + j % NBUF, (uint32_t)((j / NBUF) & 1));
+                xlane = xs + (size_t)(j % NBUF) * tile_floats + (size_t)tg * FR * frame_floats + cg * 4;
+            }
         }
+        const unsigned tm = tap_mask[p];
+        const int py = (int)(tm >> 16);
+        if (ROWP)                                          // rows py-1 .. py+1 of this tile have landed
+            for (const int need = min(py + 2, ph); rows_seen < need; ++rows_seen) tc::mbar_wait(xfull + rows_seen, (uint32_t)(j & 1));
         tc::mbar_wait(my_bars + s, phase);
         float vc[NV / 8];
-        kp_position<FR, GE>(xlane, my_ring + (size_t)s * kStageBytes, p, P, pw, tap_mask[p], cg, vc);
+        kp_position<FR, GE>(ROWP ? xlane + py * row_floats + (p - py * pw) * CC : xlane + p * CC, my_ring + (size_t)s * kStageBytes,
+                            row_floats, frame_floats, tm & 0x1ffu, cg, vc);
         // every lane's sums (hence its reads of stage s and of the frame tile) are complete once it has taken part in the
         // butterfly shuffles: lane 0 may hand the stage back to the copy engine
         if (lane == 0) {
@@ -253,9 +292,16 @@ tafa_keyproj_persist_kernel(const __grid_constant__ CUtensorMap tm_x, const unsi
         }
         if (++s == depth) { s = 0; phase ^= 1; }
         p += nwc;
-        if (p >= P) {                                      // this warp's last position in tile j: release the frame buffer
+        const bool last = p >= P;                          // this warp's last position in tile j
+        if (ROWP) {                                        // rows no later position of this warp reads go back to the producer
+            const int keep_from = last ? ph : max((int)(tap_mask[p] >> 16) - 1, 0);
+            if (lane == 0)
+                for (int r = rows_freed; r < keep_from; ++r) tc::mbar_arrive(xempty + r);
+            rows_freed = max(rows_freed, keep_from);
+        }
+        if (last) {
             p -= P;
-            if (lane == 0) tc::mbar_arrive(xempty + j % NBUF);
+            if (!ROWP && lane == 0) tc::mbar_arrive(xempty + j % NBUF);
             ++j;
         }
     }
@@ -319,7 +365,7 @@ tafa_keyproj_logits_kernel(const __grid_constant__ CUtensorMap tm_x, const unsig
         const int s = i % depth;
         if (!((dbg & 2) && i >= depth)) tc::mbar_wait(my_bars + s, (uint32_t)((i / depth) & 1));
         float vc[NV / 8];
-        kp_position<FR, GE>(xlane, my_ring + (size_t)s * kStageBytes, p, P, pw, (dbg & 1) ? 0u : kp_tap_mask(p, ph, pw), cg, vc);
+        kp_position<FR, GE>(xlane + p * CC, my_ring + (size_t)s * kStageBytes, pw * CC, P * CC, (dbg & 1) ? 0u : kp_tap_mask(p, ph, pw), cg, vc);
         if (lane == 0) issue(i + depth);
 #pragma unroll
         for (int k = 0; k < NV / 8; ++k) {
@@ -335,7 +381,8 @@ tafa_keyproj_logits_kernel(const __grid_constant__ CUtensorMap tm_x, const unsig
 using namespace vod;
 
 static size_t kp_smem_bytes(int tile_frames, int P, int warps, int depth, int ge = 4) {
-    return (size_t)tile_frames * P * kKpCC * sizeof(float) + (size_t)warps * depth * ((size_t)kKpStageFloats * ge + 8) + 64 + (size_t)P * 4;
+    return (size_t)tile_frames * P * kKpCC * sizeof(float) + (size_t)warps * depth * ((size_t)kKpStageFloats * ge + 8) +
+           2 * kKpMaxRows * 8 + 32 + (size_t)P * 4;
 }
 constexpr size_t kKpSmemLimit = 227 * 1024;
 
@@ -366,7 +413,8 @@ extern "C" int vod_tafa_keyproj_logits(const float *x_all, const void *G_, int g
     // Measured at N=300, C=512 (B200).  16 stacked frames: persistent 16-frame tiles 381 us, one CTA per 16-frame tile 391 us,
     // persistent double-buffered 8-frame tiles 432 us, one CTA per 8-frame tile (two per SM) 458 us.  32 frames: persistent
     // 16-frame tiles 723 us, one CTA per tile 893 us.  8 frames: one CTA per 8-frame tile 241 us (5.6 TB/s).
-    int persist = T1 > 8, tb = T1 > 8 ? 16 : 8, warps = min(T1 > 8 ? 14 : 7, P), depth = 2, dbg = 0;
+    // (bf16 G halves the rings: room for a 15th consumer warp next to the 98 KB frame tile -- 361 vs 370 us)
+    int persist = T1 > 8, tb = T1 > 8 ? 16 : 8, warps = min(T1 > 8 ? (ge == 2 ? 15 : 14) : 7, P), depth = 2, dbg = 0;
     // Tuning / probe hooks (dbg: 1 = no FMAs, 2 = no G refills after the first ring fill, 4 = no frame tile loads) exist only
     // in a -DVOD_PROBES build: the production library ignores the environment, so a stray variable can never switch
     // parts of the computation off.
@@ -389,8 +437,12 @@ extern "C" int vod_tafa_keyproj_logits(const float *x_all, const void *G_, int g
     VOD_REQUIRE(smem <= kKpSmemLimit, "vod_tafa_keyproj_logits: tile does not fit shared memory");
     // x_all [T1][N*P][C] as a 3-D tensor, box = (32 channels, P positions, tb frames)
     CUtensorMap tm_x;
+    int rowp = persist && tb == 16 && ph <= kKpMaxRows;     // one TMA box per patch row (rolling single buffer)
+#ifdef VOD_PROBES
+    if (const char *e = getenv("VOD_KP_ROWP")) rowp = rowp && atoi(e) != 0;
+#endif
     if (int rc = make_tmap_f32_3d(&tm_x, x_all, (uint64_t)C, (uint64_t)N * P, (uint64_t)T1, (uint64_t)C * 4,
-                                  (uint64_t)N * P * C * 4, kKpCC, (uint32_t)P, (uint32_t)tb))
+                                  (uint64_t)N * P * C * 4, kKpCC, (uint32_t)(rowp ? pw : P), (uint32_t)tb))
         return rc;
     cudaStream_t st = as_stream(stream);
     // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute: set it on every call (cheap,
@@ -404,13 +456,14 @@ extern "C" int vod_tafa_keyproj_logits(const float *x_all, const void *G_, int g
 #endif
         const int tiles_per_cta = (int)ceil_div(total_tiles, (long)sms);
         const int grid = (int)ceil_div(total_tiles, (long)tiles_per_cta);
-#define VOD_KP_PERSIST(TB_, NB_)                                                                                                   \
+#define VOD_KP_PERSIST(TB_, NB_, RP_)                                                                                              \
     do {                                                                                                                           \
-        if (ge == 2) allow(tafa_keyproj_persist_kernel<TB_, NB_, 2>)<<<grid, (warps + 1) * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, tiles_per_cta, dbg); \
-        else allow(tafa_keyproj_persist_kernel<TB_, NB_, 4>)<<<grid, (warps + 1) * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, tiles_per_cta, dbg);         \
+        if (ge == 2) allow(tafa_keyproj_persist_kernel<TB_, NB_, 2, RP_>)<<<grid, (warps + 1) * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, tiles_per_cta, dbg); \
+        else allow(tafa_keyproj_persist_kernel<TB_, NB_, 4, RP_>)<<<grid, (warps + 1) * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, tiles_per_cta, dbg);         \
     } while (0)
-        if (tb == 16) VOD_KP_PERSIST(16, 1);
-        else VOD_KP_PERSIST(8, 2);
+        if (rowp) VOD_KP_PERSIST(16, 1, true);
+        else if (tb == 16) VOD_KP_PERSIST(16, 1, false);
+        else VOD_KP_PERSIST(8, 2, false);
 #undef VOD_KP_PERSIST
     } else {
         dim3 grid(ceil_div(T1, tb), C / cc, N);

@@ -78,6 +78,13 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m
         : "memory");
 }
 
+// L2 prefetch of a 3-D tensor box (no shared-memory destination, no barrier): the later cp.async.bulk.tensor load of the same box
+// is then served from L2
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *m, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
 // ------------------------------------------------------------------------------ clusters / CTA pairs
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;

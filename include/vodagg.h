@@ -262,13 +262,6 @@ int vod_bbox_decode_candidates(const float *rois, const float *cls_score, const 
 int vod_rpn_decode_topk(const int64_t *topk_idx, const float *deltas, const float *anchors, float *boxes, int B, int K,
                         int A, float max_ratio, float img_h, float img_w, vod_stream_t stream);
 
-/* ------------------------------------------------------------ diagnostics
- * Plain tcgen05 GEMM used by the unit tests to validate descriptors/pipeline:
- * D[M,N] (fp32) = A[M,K] * B[N,K]^T, A/B row-major (K contiguous), dtype bf16 or fp32(tf32).
- */
-int vod_test_gemm_nt(const void *a, const void *b, float *d, int M, int N, int K, int dtype,
-                     vod_stream_t stream);
-
 #ifdef __cplusplus
 }
 #endif

@@ -51,12 +51,20 @@ SIGNATURES = {
     'vod_bbox_decode_candidates': (_I, [_P, _P, _P, _I, _I, _I, _c.POINTER(_F), _c.POINTER(_F), _F, _F, _F,
                                         _c.POINTER(_F), _F, _P, _P, _P, _P, _P]),
     'vod_rpn_decode_topk': (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _F, _F, _P]),
-    'vod_test_gemm_nt': (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
 }
 
 _lib = None
+_selftest = None
 _lock = threading.Lock()
 launch_count = 0  # number of kernel-launching C-ABI calls made through this module (bench bookkeeping)
+
+
+# include/vodagg_selftest.h (libvodagg_selftest.so: test-only kernels, never on an operator's path)
+SELFTEST_LIB_PATH = os.path.join(_HERE, 'libvodagg_selftest.so')
+SELFTEST_SIGNATURES = {
+    'vod_last_error': (_c.c_char_p, []),
+    'vod_test_gemm_nt': (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+}
 
 
 class VodError(RuntimeError):
@@ -81,6 +89,32 @@ def load():
                     fn.argtypes = args
                 _lib = lib
     return _lib
+
+
+def load_selftest():
+    """Loads libvodagg_selftest.so (the tcgen05 / TMA building-block test kernels of include/vodagg_selftest.h)."""
+    global _selftest
+    if _selftest is None:
+        with _lock:
+            if _selftest is None:
+                if not os.path.exists(SELFTEST_LIB_PATH):
+                    raise VodError('libvodagg_selftest.so not found at %s: build it with '
+                                   '`python -m lowlightenvironmentvideoobjectdetection_b200.build`' % SELFTEST_LIB_PATH)
+                lib = ctypes.CDLL(SELFTEST_LIB_PATH)
+                for name, (res, args) in SELFTEST_SIGNATURES.items():
+                    fn = getattr(lib, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _selftest = lib
+    return _selftest
+
+
+def call_selftest(name, *args):
+    lib = load_selftest()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.vod_last_error()
+        raise VodError('%s failed (%d): %s' % (name, rc, msg.decode() if msg else ''))
 
 
 def check(rc, what):

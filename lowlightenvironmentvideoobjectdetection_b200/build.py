@@ -17,8 +17,13 @@ CSRC = os.path.join(_HERE, 'csrc')
 LIB_PATH = os.path.join(_HERE, 'libvodagg.so')
 _OBJ_DIR = os.path.join(_HERE, '_build', 'obj')
 
-SOURCES = ['common.cu', 'nms.cu', 'roi_align.cu', 'layout.cu', 'warp.cu', 'tafa.cu', 'tafa_keyproj.cu', 'selsa.cu',
-           'selsa_tc.cu', 'msra_gemm.cu', 'msra_overflow.cu', 'gemm_test.cu', 'decode.cu']
+SOURCES = ['common.cu', 'tmap.cu', 'nms.cu', 'roi_align.cu', 'layout.cu', 'warp.cu', 'tafa.cu', 'tafa_keyproj.cu', 'selsa.cu',
+           'selsa_tc.cu', 'msra_gemm.cu', 'msra_overflow.cu', 'decode.cu']
+# test-only kernels (include/vodagg_selftest.h): linked with the shared helpers into a SEPARATE library, so that
+# libvodagg.so carries no test code
+SELFTEST_LIB_PATH = os.path.join(_HERE, 'libvodagg_selftest.so')
+SELFTEST_SOURCES = ['gemm_test.cu']
+SELFTEST_SHARED = ['common.cu', 'tmap.cu']
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
@@ -40,7 +45,7 @@ def _host_cxx():
 
 def _digest():
     h = hashlib.sha256()
-    names = sorted(os.listdir(CSRC)) + ['../../include/vodagg.h']
+    names = sorted(os.listdir(CSRC)) + ['../../include/vodagg.h', '../../include/vodagg_selftest.h']
     for n in names:
         p = os.path.join(CSRC, n)
         if os.path.isfile(p):
@@ -51,7 +56,7 @@ def _digest():
 
 
 def build_library(force=False, verbose=False, probes=False):
-    """Compile every .cu for sm_100a and link libvodagg.so. Returns the library path.
+    """Compile every .cu for sm_100a and link libvodagg.so (+ libvodagg_selftest.so, the test-only kernels). Returns the library path.
 
     ``probes=True`` (``python -m ...build --probes``): an experiment build with -DVOD_PROBES (environment-selected kernel variants
     and probe hooks) written to libvodagg_probes.so; the production library never reads the environment."""
@@ -59,7 +64,7 @@ def build_library(force=False, verbose=False, probes=False):
         return _build_probes(verbose)
     stamp = os.path.join(_HERE, '_build', 'stamp')
     digest = _digest()
-    if (not force and os.path.exists(LIB_PATH) and os.path.exists(stamp)
+    if (not force and os.path.exists(LIB_PATH) and os.path.exists(SELFTEST_LIB_PATH) and os.path.exists(stamp)
             and open(stamp).read().strip() == digest):
         return LIB_PATH
     nvcc, cxx = _nvcc(), _host_cxx()
@@ -75,12 +80,13 @@ def build_library(force=False, verbose=False, probes=False):
             print(r.stderr)
         return obj
 
-    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
-        objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, '-ccbin', cxx, '-shared', '-o', LIB_PATH] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a']
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))
+    with concurrent.futures.ThreadPoolExecutor(max_workers=8) as ex:
+        objs = dict(zip(SOURCES + SELFTEST_SOURCES, ex.map(compile_one, SOURCES + SELFTEST_SOURCES)))
+    for out, names in ((LIB_PATH, SOURCES), (SELFTEST_LIB_PATH, SELFTEST_SHARED + SELFTEST_SOURCES)):
+        cmd = [nvcc, '-ccbin', cxx, '-shared', '-o', out] + [objs[n] for n in names] + ['-gencode', 'arch=compute_100a,code=sm_100a']
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))
     with open(stamp, 'w') as f:
         f.write(digest)
     return LIB_PATH

@@ -46,6 +46,7 @@ constexpr int kKpStageFloats = kKpHeads * kKpRowFloats;   // elements of one rin
 // allows reduced-precision library math it is produced and streamed in bf16 -- half the bytes here and in the GEMM that writes
 // it -- and unpacked to fp32 on the fly: one shift / mask per element, amortised over the lane's 4 frames).
 constexpr int kKpMaxWarps = 16;
+constexpr int kKpMaxWarpsMma = 21;                // tensor-core form: up to 20 consumer warps + the producer at 96 registers
 
 __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -137,6 +138,82 @@ __device__ __forceinline__ void kp_position(const float *__restrict__ xp, const 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ tensor-core form
+// Reduced-precision mode only (bf16 G, i.e. the caller allowed tf32 library math).  Per output position and 32-channel chunk the
+// contraction is a [4 heads] x [taps * 32 channels] x [16 frames] product whose BOTH operands change with the position -- a
+// batched small product, not a GEMM tile, so tcgen05's 128-row atoms do not apply; the warp-level m16n8k8 tf32 MMA does
+// (measured on B200: one per 8 clocks per sub-partition, 512 MAC/clk/SM -- scripts/micro/mma_rate.cu):
+//   A (16 rows) = heads (rows 0-3 used: the other rows compute sums nobody reads), B (8 columns) = frames (two column groups
+//   for 16 frames), K = 8 channels of one tap; 8 MMAs per tap.
+// What it buys is instruction issue, not flops: ~22 warp instructions per tap (4 LDS.128 + 2 LDS.64 + 8 unpack + 8 HMMA) and
+// no butterfly, against ~80 for the FFMA2 form (which ncu shows issue-bound at ~750 warp instructions per position).
+//   x tile: TMA box per patch row [16 frames][PW][32 ch], 128-byte swizzled and rounded to tf32 by the TMA unit.  Lane
+//   (g = lane / 4, t = lane % 4) reads channels 4t..4t+3 (+16 s) of frames f(g) and f(g) + 8 with 128-bit loads, where
+//   f(g) = g/2 + 4 (g & 1): the two frames of a quarter-warp then sit on 128-byte lines that differ in bit 2 of the line
+//   index, so its 8 loads cover all 32 banks.  MMA m of a 16-channel step uses K slot t <-> channel 4t + 2m and slot
+//   t + 4 <-> channel 4t + 2m + 1: the B fragment of an MMA is an aligned register PAIR of the 128-bit load (frames as the
+//   A operand would need 16 register moves per tap) and one 64-bit (4 x bf16) G load feeds the A fragments of four MMAs.
+//   G ring stage: the 4 head rows (576 B each) are placed 608 B apart, so the 4 heads' 64-bit loads hit different banks.
+constexpr int kKpMmaHeadPitch = kKpRowFloats * 2 + 32;
+
+__device__ __forceinline__ void mma_tf32_m16n8k8(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, float b0, float b1) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+
+// xrow = shared-memory address of the box of patch row py of the tile (1024-byte aligned), gs = of the G ring stage; returns
+// for head g (lanes with g < 4) the sums of frames t, t + 4, t + 8, t + 12.
+template <int PW>
+__device__ __forceinline__ void kp_position_mma(uint32_t xrow, uint32_t gs, int px, unsigned taps, int lane, float (&c)[4]) {
+    constexpr int kRowB = 16 * PW * 128;                  // bytes of one patch-row box
+    const int g = lane >> 2, t = lane & 3;
+    const int f0 = (g >> 1) + ((g & 1) << 2);              // B column g <-> frames f0 and f0 + 8 (second column group)
+    uint32_t off[3][2];                                    // [dx][column group]: address of channels 4t.. in patch row py
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int line = (f0 + 8 * hf) * PW + px + dx - 1;       // (-1 only for a masked tap)
+            off[dx][hf] = xrow + (uint32_t)(line * 128 + (((t ^ line) & 7) << 4));
+        }
+    const uint32_t ga = gs + (uint32_t)((g & 3) * kKpMmaHeadPitch + t * 8);
+    float acc[2][2][4];                                    // [column group][m]: independent accumulation chains
+#pragma unroll
+    for (int i = 0; i < 16; ++i) (&acc[0][0][0])[i] = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        if (!((taps >> tap) & 1u)) continue;                // warp-uniform
+        const int dyb = (tap / 3 - 1) * kRowB;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {                       // channels 16 s .. 16 s + 15: chunk index ^ 4 <=> address ^ 64
+            const float4 v0 = lds128((off[tap % 3][0] ^ (uint32_t)(s << 6)) + dyb);
+            const float4 v1 = lds128((off[tap % 3][1] ^ (uint32_t)(s << 6)) + dyb);
+            const uint2 w = lds64(ga + tap * 64 + s * 32);
+            const uint32_t a00 = w.x << 16, a01 = w.x & 0xffff0000u, a10 = w.y << 16, a11 = w.y & 0xffff0000u;
+            mma_tf32_m16n8k8(acc[0][0], a00, 0u, a01, 0u, v0.x, v0.y);
+            mma_tf32_m16n8k8(acc[1][0], a00, 0u, a01, 0u, v1.x, v1.y);
+            mma_tf32_m16n8k8(acc[0][1], a10, 0u, a11, 0u, v0.z, v0.w);
+            mma_tf32_m16n8k8(acc[1][1], a10, 0u, a11, 0u, v1.z, v1.w);
+        }
+    }
+    // C[row = head g][columns 2t, 2t+1 <-> frames t, t + 4]
+    c[0] = acc[0][0][0] + acc[0][1][0];
+    c[1] = acc[0][0][1] + acc[0][1][1];
+    c[2] = acc[1][0][0] + acc[1][1][0];
+    c[3] = acc[1][0][1] + acc[1][1][1];
+}
+
 // ------------------------------------------------------------------------------------------------ persistent kernel
 // blockDim = (nwc + 1) warps: warps 0..nwc-1 consume, warp nwc produces the frame tiles.  Requires nwc <= P.
 // <TB = 8, NBUF = 2>: 8-frame tiles, double-buffered (a warp may run one tile ahead of the slowest).
@@ -150,13 +227,16 @@ __device__ __forceinline__ void kp_position(const float *__restrict__ xp, const 
 //     load of tile j+1 overlaps the FMAs of tile j.
 constexpr int kKpMaxRows = 16;                    // patch rows with their own barrier pair (ROWP)
 
-template <int TB, int NBUF, int GE, bool ROWP>
-__global__ void __launch_bounds__(kKpMaxWarps * 32, 1)
+//   MPW > 0 (with ROWP, bf16 G): the tensor-core form above, for patches MPW positions wide.
+template <int TB, int NBUF, int GE, bool ROWP, int MPW>
+__global__ void __launch_bounds__((MPW > 0 ? kKpMaxWarpsMma : kKpMaxWarps) * 32, 1)
 tafa_keyproj_persist_kernel(const __grid_constant__ CUtensorMap tm_x, const unsigned char *__restrict__ G, float *__restrict__ parts,
                             int T1, int N, int ph, int pw, int C, int depth, int tiles_per_cta, int dbg) {
     constexpr int H = kKpHeads, CC = kKpCC, FR = TB / 4, NV = FR * H;
+    constexpr bool MMA = MPW > 0;
     static_assert(!ROWP || NBUF == 1, "row pipelining replaces the double buffer");
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    static_assert(!MMA || (ROWP && GE == 2 && TB == 16), "the mma form reads bf16 G and per-row swizzled 16-frame boxes");
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int nch = C / CC, ntb = ceil_div(T1, TB), P = ph * pw;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwc = (blockDim.x >> 5) - 1;
     const int tg = lane >> 3, cg = lane & 7;
@@ -167,8 +247,10 @@ tafa_keyproj_persist_kernel(const __grid_constant__ CUtensorMap tm_x, const unsi
     // shared-memory tile: [TB][P][CC] (one box) or [ph][TB][pw][CC] (one box per patch row)
     const int row_floats = ROWP ? TB * pw * CC : pw * CC, frame_floats = ROWP ? pw * CC : P * CC;
     float *xs = reinterpret_cast<float *>(smem_raw);
-    constexpr int kStageBytes = kKpStageFloats * GE, kRowBytes = kKpRowFloats * GE;
-    unsigned char *ring = reinterpret_cast<unsigned char *>(xs + NBUF * (size_t)tile_floats);   // [nwc][depth][H][9][CC] of GE bytes
+    // one ring stage = the 4 head rows of one position (kRowBytes each, copied separately), kHeadPitch apart
+    constexpr int kRowBytes = kKpRowFloats * GE, kHeadPitch = MMA ? kKpMmaHeadPitch : kRowBytes;
+    constexpr int kStageBytes = H * kHeadPitch, kStageTx = H * kRowBytes;
+    unsigned char *ring = reinterpret_cast<unsigned char *>(xs + NBUF * (size_t)tile_floats);   // [nwc][depth][H][kHeadPitch]
     uint64_t *bars = reinterpret_cast<uint64_t *>(ring + (size_t)nwc * depth * kStageBytes);      // [nwc][depth], xfull[], xempty[]
     uint64_t *xfull = bars + nwc * depth, *xempty = xfull + kKpMaxRows;
     unsigned *tap_mask = reinterpret_cast<unsigned *>(xempty + kKpMaxRows);             // [P]: tap mask | patch row << 16
@@ -177,6 +259,7 @@ tafa_keyproj_persist_kernel(const __grid_constant__ CUtensorMap tm_x, const unsi
     const int nxb = ROWP ? ph : NBUF;                     // frame-tile barrier pairs in use
 
     if (tid == 0) {
+        if (MMA && (tc::smem_u32(xs) & 1023u)) __trap();   // the swizzle pattern is a function of the absolute address
         for (int b = 0; b < nxb; ++b) { tc::mbar_init(xfull + b, 1); tc::mbar_init(xempty + b, nwc); }
         for (int s = 0; s < nwc * depth; ++s) tc::mbar_init(bars + s, 1);
         tc::fence_barrier_init();
@@ -236,11 +319,11 @@ tafa_keyproj_persist_kernel(const __grid_constant__ CUtensorMap tm_x, const unsi
             const unsigned nc = (unsigned)(tile0 + ji) / ntb;            // n*nch + chunk
             gi_row = G + ((size_t)(nc / nch) * P * nch + (size_t)(nc % nch)) * kRowBytes;
         }
-        tc::mbar_arrive_expect_tx(my_bars + si, kStageBytes);
+        tc::mbar_arrive_expect_tx(my_bars + si, kStageTx);
         const unsigned char *row = gi_row + (size_t)pi * nch * kRowBytes;
 #pragma unroll
         for (int h = 0; h < H; ++h)
-            bulk_g2s(my_ring + (size_t)si * kStageBytes + h * kRowBytes, row + (size_t)h * head_stride, kRowBytes,
+            bulk_g2s(my_ring + (size_t)si * kStageBytes + h * kHeadPitch, row + (size_t)h * head_stride, kRowBytes,
                      my_bars + si);
         if (++si == depth) si = 0;
         pi += nwc;
@@ -251,6 +334,7 @@ tafa_keyproj_persist_kernel(const __grid_constant__ CUtensorMap tm_x, const unsi
 
     int j = 0, p = warp, s = 0;                           // current tile (local index), position, ring stage
     uint32_t phase = 0;
+    const uint32_t xs_addr = tc::smem_u32(xs), ring_addr = tc::smem_u32(my_ring);
     int cur = -1, t0 = 0, nt = 0;
     int rows_seen = 0, rows_freed = 0;                    // ROWP: patch rows of tile j waited for / handed back by this warp
     int refills = (dbg & 2) ? 0 : 0x7fffffff;
@@ -275,20 +359,38 @@ tafa_keyproj_persist_kernel(const __grid_constant__ CUtensorMap tm_x, const unsi
         if (ROWP)                                          // rows py-1 .. py+1 of this tile have landed
             for (const int need = min(py + 2, ph); rows_seen < need; ++rows_seen) tc::mbar_wait(xfull + rows_seen, (uint32_t)(j & 1));
         tc::mbar_wait(my_bars + s, phase);
-        float vc[NV / 8];
-        kp_position<FR, GE>(ROWP ? xlane + py * row_floats + (p - py * pw) * CC : xlane + p * CC, my_ring + (size_t)s * kStageBytes,
-                            row_floats, frame_floats, tm & 0x1ffu, cg, vc);
-        // every lane's sums (hence its reads of stage s and of the frame tile) are complete once it has taken part in the
-        // butterfly shuffles: lane 0 may hand the stage back to the copy engine
-        if (lane == 0) {
-            if (refills > 0) issue();
-            else tc::mbar_arrive(my_bars + s);             // probe mode: keep the phases moving without a copy
-        }
+        if (MMA) {
+            float c[4];
+            kp_position_mma<MMA ? MPW : 1>(xs_addr + (uint32_t)(py * row_floats) * 4u, ring_addr + (uint32_t)(s * kStageBytes), p - py * pw,
+                                           tm & 0x1ffu, lane, c);
+            // the last (warp-synchronous) MMA has consumed every lane's loads of stage s and of the frame rows
+            if (lane == 0) {
+                if (refills > 0) issue();
+                else tc::mbar_arrive(my_bars + s);
+            }
+            const int g = lane >> 2, t2 = lane & 3;
+            if (g < 4) {                                   // head g: frames t2, t2 + 4, t2 + 8, t2 + 12
+                float *o = out_tile + ((size_t)p * H + g) * T1 + t2;
 #pragma unroll
-        for (int k = 0; k < NV / 8; ++k) {
-            const int v = cg * (NV / 8) + k;
-            const int t = tg * FR + v / H;
-            if (t < nt) out_tile[((size_t)p * H + v % H) * T1 + t] = vc[k];
+                for (int i = 0; i < 4; ++i)
+                    if (t2 + 4 * i < nt) o[4 * i] = c[i];
+            }
+        } else {
+            float vc[NV / 8];
+            kp_position<FR, GE>(ROWP ? xlane + py * row_floats + (p - py * pw) * CC : xlane + p * CC, my_ring + (size_t)s * kStageBytes,
+                                row_floats, frame_floats, tm & 0x1ffu, cg, vc);
+            // every lane's sums (hence its reads of stage s and of the frame tile) are complete once it has taken part in the
+            // butterfly shuffles: lane 0 may hand the stage back to the copy engine
+            if (lane == 0) {
+                if (refills > 0) issue();
+                else tc::mbar_arrive(my_bars + s);             // probe mode: keep the phases moving without a copy
+            }
+#pragma unroll
+            for (int k = 0; k < NV / 8; ++k) {
+                const int v = cg * (NV / 8) + k;
+                const int t = tg * FR + v / H;
+                if (t < nt) out_tile[((size_t)p * H + v % H) * T1 + t] = vc[k];
+            }
         }
         if (++s == depth) { s = 0; phase ^= 1; }
         p += nwc;
@@ -380,8 +482,9 @@ tafa_keyproj_logits_kernel(const __grid_constant__ CUtensorMap tm_x, const unsig
 
 using namespace vod;
 
-static size_t kp_smem_bytes(int tile_frames, int P, int warps, int depth, int ge = 4) {
-    return (size_t)tile_frames * P * kKpCC * sizeof(float) + (size_t)warps * depth * ((size_t)kKpStageFloats * ge + 8) +
+static size_t kp_smem_bytes(int tile_frames, int P, int warps, int depth, int ge = 4, bool mma = false) {
+    const size_t stage = mma ? (size_t)kKpHeads * kKpMmaHeadPitch : (size_t)kKpStageFloats * ge;
+    return (size_t)tile_frames * P * kKpCC * sizeof(float) + (size_t)warps * depth * (stage + 8) +
            2 * kKpMaxRows * 8 + 32 + (size_t)P * 4;
 }
 constexpr size_t kKpSmemLimit = 227 * 1024;
@@ -414,6 +517,8 @@ extern "C" int vod_tafa_keyproj_logits(const float *x_all, const void *G_, int g
     // persistent double-buffered 8-frame tiles 432 us, one CTA per 8-frame tile (two per SM) 458 us.  32 frames: persistent
     // 16-frame tiles 723 us, one CTA per tile 893 us.  8 frames: one CTA per 8-frame tile 241 us (5.6 TB/s).
     // (bf16 G halves the rings: room for a 15th consumer warp next to the 98 KB frame tile -- 361 vs 370 us)
+    // Round 2, 16 frames: + L2 prefetch of the next tile 352 (bf16 G) / 384; tile as one box per patch row (rolling buffer)
+    // 325 / 342; bf16 G with the tf32 mma.sync form 239-249 us (memory traffic alone, FMAs off: 193 us).
     int persist = T1 > 8, tb = T1 > 8 ? 16 : 8, warps = min(T1 > 8 ? (ge == 2 ? 15 : 14) : 7, P), depth = 2, dbg = 0;
     // Tuning / probe hooks (dbg: 1 = no FMAs, 2 = no G refills after the first ring fill, 4 = no frame tile loads) exist only
     // in a -DVOD_PROBES build: the production library ignores the environment, so a stray variable can never switch
@@ -421,28 +526,37 @@ extern "C" int vod_tafa_keyproj_logits(const float *x_all, const void *G_, int g
 #ifdef VOD_PROBES
     if (const char *e = getenv("VOD_KP_PERSIST")) persist = atoi(e) != 0;
     if (const char *e = getenv("VOD_KP_TB")) tb = atoi(e) == 16 ? 16 : 8;
-    if (const char *e = getenv("VOD_KP_WARPS")) warps = max(1, min(atoi(e), min(kKpMaxWarps, P)));
+    if (const char *e = getenv("VOD_KP_WARPS")) warps = max(1, min(atoi(e), min(kKpMaxWarpsMma, P)));
     if (const char *e = getenv("VOD_KP_DEPTH")) depth = max(1, min(atoi(e), 8));
     if (const char *e = getenv("VOD_KP_DBG")) dbg = atoi(e);
 #endif
-    if (persist) warps = min(warps, kKpMaxWarps - 1);      // + the producer warp
-    const int tile_frames = persist ? 16 : tb;              // persistent: 2 x 8 frames (double buffer) or 1 x 16
-    while (warps > 4 && kp_smem_bytes(tile_frames, P, warps, depth, ge) > kKpSmemLimit) --warps;
-    while (depth > 2 && kp_smem_bytes(tile_frames, P, warps, depth, ge) > kKpSmemLimit) --depth;
-    if (persist && kp_smem_bytes(tile_frames, P, warps, depth, ge) > kKpSmemLimit) {   // large patches: one tile per CTA
-        persist = 0;
-        tb = 8;
-    }
-    const size_t smem = kp_smem_bytes(persist ? 16 : tb, P, warps, depth, ge);
-    VOD_REQUIRE(smem <= kKpSmemLimit, "vod_tafa_keyproj_logits: tile does not fit shared memory");
-    // x_all [T1][N*P][C] as a 3-D tensor, box = (32 channels, P positions, tb frames)
-    CUtensorMap tm_x;
-    int rowp = persist && tb == 16 && ph <= kKpMaxRows;     // one TMA box per patch row (rolling single buffer)
+    // persistent 16-frame tiles: one TMA box per patch row (rolling single buffer); with bf16 G and 7-wide patches the
+    // tensor-core form (tf32 mma.sync; bf16 G already means the caller allowed reduced-precision math)
+    int rowp = persist && tb == 16 && ph <= kKpMaxRows;
+    int mma = rowp && ge == 2 && pw == 7;
 #ifdef VOD_PROBES
     if (const char *e = getenv("VOD_KP_ROWP")) rowp = rowp && atoi(e) != 0;
+    if (const char *e = getenv("VOD_KP_MMA")) mma = mma && atoi(e) != 0;
+    mma = mma && rowp;
 #endif
+#ifdef VOD_PROBES
+    if (!getenv("VOD_KP_WARPS"))
+#endif
+    if (mma) warps = min(kKpMaxWarpsMma - 1, P);           // few registers per thread: 20 consumer warps (measured 239-249 us vs 257-273 with 15)
+    warps = min(warps, (mma ? kKpMaxWarpsMma : kKpMaxWarps) - (persist ? 1 : 0));      // persistent: + the producer warp
+    const int tile_frames = persist ? 16 : tb;              // persistent: 2 x 8 frames (double buffer) or 1 x 16
+    while (warps > 4 && kp_smem_bytes(tile_frames, P, warps, depth, ge, mma) > kKpSmemLimit) --warps;
+    while (depth > 2 && kp_smem_bytes(tile_frames, P, warps, depth, ge, mma) > kKpSmemLimit) --depth;
+    if (persist && kp_smem_bytes(tile_frames, P, warps, depth, ge, mma) > kKpSmemLimit) {   // large patches: one tile per CTA
+        persist = rowp = mma = 0;
+        tb = 8;
+    }
+    const size_t smem = kp_smem_bytes(persist ? 16 : tb, P, warps, depth, ge, mma);
+    VOD_REQUIRE(smem <= kKpSmemLimit, "vod_tafa_keyproj_logits: tile does not fit shared memory");
+    // x_all [T1][N*P][C] as a 3-D tensor, box = (32 channels, P positions or one patch row, tb frames)
+    CUtensorMap tm_x;
     if (int rc = make_tmap_f32_3d(&tm_x, x_all, (uint64_t)C, (uint64_t)N * P, (uint64_t)T1, (uint64_t)C * 4,
-                                  (uint64_t)N * P * C * 4, kKpCC, (uint32_t)(rowp ? pw : P), (uint32_t)tb))
+                                  (uint64_t)N * P * C * 4, kKpCC, (uint32_t)(rowp ? pw : P), (uint32_t)tb, mma != 0))
         return rc;
     cudaStream_t st = as_stream(stream);
     // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute: set it on every call (cheap,
@@ -458,10 +572,11 @@ extern "C" int vod_tafa_keyproj_logits(const float *x_all, const void *G_, int g
         const int grid = (int)ceil_div(total_tiles, (long)tiles_per_cta);
 #define VOD_KP_PERSIST(TB_, NB_, RP_)                                                                                              \
     do {                                                                                                                           \
-        if (ge == 2) allow(tafa_keyproj_persist_kernel<TB_, NB_, 2, RP_>)<<<grid, (warps + 1) * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, tiles_per_cta, dbg); \
-        else allow(tafa_keyproj_persist_kernel<TB_, NB_, 4, RP_>)<<<grid, (warps + 1) * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, tiles_per_cta, dbg);         \
+        if (ge == 2) allow(tafa_keyproj_persist_kernel<TB_, NB_, 2, RP_, 0>)<<<grid, (warps + 1) * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, tiles_per_cta, dbg); \
+        else allow(tafa_keyproj_persist_kernel<TB_, NB_, 4, RP_, 0>)<<<grid, (warps + 1) * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, tiles_per_cta, dbg);         \
     } while (0)
-        if (rowp) VOD_KP_PERSIST(16, 1, true);
+        if (mma) allow(tafa_keyproj_persist_kernel<16, 1, 2, true, 7>)<<<grid, (warps + 1) * 32, smem, st>>>(tm_x, G, parts, T1, N, ph, pw, C, depth, tiles_per_cta, dbg);
+        else if (rowp) VOD_KP_PERSIST(16, 1, true);
         else if (tb == 16) VOD_KP_PERSIST(16, 1, false);
         else VOD_KP_PERSIST(8, 2, false);
 #undef VOD_KP_PERSIST

@@ -273,6 +273,6 @@ int make_tmap_2d_sw128(CUtensorMap *map, const void *base, int elem_bytes, uint6
 int make_tmap_kslices_sw128(CUtensorMap *map, const void *base, uint64_t rows, uint64_t C, uint32_t box_rows, uint32_t box_slices);
 int make_tmap_msra_b(CUtensorMap *map, const void *base, uint64_t T, uint64_t HW, uint64_t C, uint32_t box_slices);
 int make_tmap_f32_3d(CUtensorMap *map, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
-                     uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2);
+                     uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, bool tf32_sw128 = false);
 
 }  // namespace vod

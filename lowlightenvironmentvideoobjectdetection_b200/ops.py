@@ -561,7 +561,8 @@ def tafa_weighted_sum_logits(x_all, parts, num_heads, out_nhwc=False, out=None):
 
 
 def test_gemm_nt(a, b, a_in_tmem=False):
-    """D = A @ B^T on the tcgen05 path (unit-test hook for the descriptor/pipeline building blocks).
+    """D = A @ B^T on the tcgen05 path (unit-test hook for the descriptor/pipeline building blocks; lives in
+    libvodagg_selftest.so, not in the product library).
     ``a_in_tmem``: bf16 only; the A tile is written to TMEM with tcgen05.st and consumed by the TS-form MMA."""
     _lib.require_cuda(a, b)
     assert a.dtype == b.dtype and a.dtype in (torch.float32, torch.bfloat16)
@@ -569,7 +570,7 @@ def test_gemm_nt(a, b, a_in_tmem=False):
     M, K = a.shape
     N = b.shape[0]
     d = torch.empty((M, N), dtype=torch.float32, device=a.device)
-    _lib.call('vod_test_gemm_nt', _lib.ptr(a), _lib.ptr(b), _lib.ptr(d), M, N, K,
+    _lib.call_selftest('vod_test_gemm_nt', _lib.ptr(a), _lib.ptr(b), _lib.ptr(d), M, N, K,
               2 if a_in_tmem else (_lib.VOD_DTYPE_F32 if a.dtype == torch.float32 else _lib.VOD_DTYPE_BF16),
               _lib.stream_ptr(a.device))
     return d

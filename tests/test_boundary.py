@@ -31,6 +31,19 @@ def test_library_exports_every_declared_symbol():
     assert _lib.load().vod_device_is_sm100() in (0, 1)   # no compute call without a GPU
 
 
+def test_selftest_kernels_live_in_their_own_library():
+    """The tcgen05 building-block GEMM (include/vodagg_selftest.h) is test code: exported by libvodagg_selftest.so and absent
+    from the product library."""
+    header = open(os.path.join(ROOT, 'include', 'vodagg_selftest.h')).read()
+    declared = set(re.findall(r'\b(vod_[a-z0-9_]+)\s*\(', header))
+    declared.discard('vod_last_error')               # mentioned in the header comment; shared helper, exported by both libraries
+    assert declared == {'vod_test_gemm_nt'} and declared <= set(_lib.SELFTEST_SIGNATURES)
+    st = _lib.load_selftest()
+    product = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(st, name) and not hasattr(product, name)
+
+
 def test_sass_is_blackwell_native():
     """The shipped cubin carries tcgen05 MMAs (UTC*MMA), TMEM loads (LDTM) and TMA loads (UTMALDG)."""
     r = subprocess.run(['cuobjdump', '-sass', _lib.LIB_PATH], capture_output=True, text=True)

@@ -328,9 +328,11 @@ def test_tafa_keyproj_vs_oracle(T1, N, C):
 
 @pytest.mark.parametrize('T1,N,C', [(16, 9, 512), (6, 3, 64), (19, 2, 128)])
 def test_tafa_keyproj_bf16_g_operand(T1, N, C):
-    """Round 2: G may arrive in bf16 (half the bytes of the kernel's dominant stream).  The kernel unpacks it to fp32 on the
-    fly, so feeding bf16 G must equal feeding the same values as fp32 -- bit for bit -- on every kernel variant (persistent
-    16-frame tiles, one CTA per 8-frame tile); against the un-rounded G the logits move by bf16 rounding only."""
+    """Round 2: G may arrive in bf16 (half the bytes of the kernel's dominant stream).  Up to 8 frames the kernel unpacks it to
+    fp32 on the fly, so feeding bf16 G equals feeding the same values as fp32 bit for bit.  Above 8 frames (persistent 16-frame
+    tiles) bf16 G selects the tensor-core form: the frame tile is rounded to tf32 by the TMA unit (relative 2^-11 per element,
+    a quarter of G's own bf16 rounding), products and sums stay fp32 -- stated tolerance 1e-3 against the fp32-x result.
+    Against the un-rounded G the logits move by bf16 rounding only."""
     g = torch.Generator().manual_seed(330 + T1)
     x_all = torch.randn(T1, N, 49, C, generator=g).to(DEV)
     cc = ops.tafa_keyproj_chunk(T1, 49, C, 4)
@@ -338,7 +340,12 @@ def test_tafa_keyproj_bf16_g_operand(T1, N, C):
     Gh = G.bfloat16()
     a = ops.tafa_keyproj_logits(x_all, Gh, 7, 4, cc)
     b = ops.tafa_keyproj_logits(x_all, Gh.float(), 7, 4, cc)
-    assert torch.equal(a, b)
+    if T1 <= 8:
+        assert torch.equal(a, b)
+    else:
+        assert rel_err(a, b) < 1e-3 and rel_err(a.sum(0), b.sum(0)) < 1e-3
+        xr = (x_all.view(torch.int32) + 0x1000 & ~0x1fff).view(torch.float32)      # tf32 round-to-nearest (ties away) of x
+        assert rel_err(a, ops.tafa_keyproj_logits(xr, Gh.float(), 7, 4, cc)) < 2e-4   # ~ the same operands in the FFMA form
     full = ops.tafa_keyproj_logits(x_all, G, 7, 4, cc)
     assert rel_err(a.sum(0), full.sum(0)) < 5e-3
 

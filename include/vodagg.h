@@ -262,6 +262,20 @@ int vod_bbox_decode_candidates(const float *rois, const float *cls_score, const 
 int vod_rpn_decode_topk(const int64_t *topk_idx, const float *deltas, const float *anchors, float *boxes, int B, int K,
                         int A, float max_ratio, float img_h, float img_w, vod_stream_t stream);
 
+/* ------------------------------------------------------------ temporal attention fusion (the fork's Denoising2Aggergator)
+ * Sampling half of mmcv's modulated_deform_conv2d (DCNv2) as used by ModulatedDCNPack.forward
+ *   (mmtracking/mmtrack/models/aggregators/denoising2_aggregator.py:72-82): x [B,H,W,C] channels-last; p (and optional q,
+ *   added to it) = raw conv_offset outputs, channels-last [B or 1, Ho, Wo, 3*G*kh*kw] -- channels [0, 2GK) are the offsets
+ *   (deformable-group major, (dy, dx) interleaved per tap: chunk + cat of :76-77 leave them in place), [2GK, 3GK) the mask
+ *   logits (sigmoid applied here, :78).  p_shared / q_shared != 0: that map is one [Ho,Wo,3GK] map broadcast over B.
+ *   col [B*Ho*Wo, kh*kw*C] (column k*C + c) = mask * bilinear(x, tap position + offset), zero outside the map; the caller
+ *   multiplies by the [Cout, kh*kw*C] weight (groups == 1).  128-bit accesses when C / G is a multiple of 4, scalar otherwise. */
+int vod_mdcn_im2col(const float *x, const float *p, const float *q, float *col, int B, int C, int H, int W, int G,
+                    int kh, int kw, int stride, int pad, int dil, int p_shared, int q_shared, vod_stream_t stream);
+/* cor [I,T,E], x [T,E] -> out [I,E]: out[i] = sum_t softmax_t(cor[i,:,e])[t] * x[t,e]  (E % 4 == 0; any common element order).
+ * replaces: torch.softmax(x_cor, dim=0) and torch.sum(x_cor * x, dim=0) of TemporalAttentionFusion.forward (:145-146). */
+int vod_temporal_softmax_fuse(const float *cor, const float *x, float *out, int I, int T, long E, vod_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,7 @@ kernels from libvodagg.so through a C ABI (include/vodagg.h).  No Triton, no bac
 from . import _lib, ops  # noqa: F401
 from ._lib import VodError  # noqa: F401
 from .aggregators import EmbedAggregator, SelsaAggregator  # noqa: F401
+from .denoise import RDB, Denoising2Aggergator, ModulatedDCNPack, TemporalAttentionFusion  # noqa: F401
 from .heads import RefFrameCache, SelsaBBoxHead, SelsaRoIHead, Shared2FCBBoxHead, StandardRoIHead  # noqa: F401
 from .motion import DFFFeatureMemo, FlowNetSimple, flow_warp_feats, flow_warp_feats_lowres, flow_warp_feats_shared  # noqa: F401
 from .ops import RoIAlign, batched_nms, nms, roi_align  # noqa: F401

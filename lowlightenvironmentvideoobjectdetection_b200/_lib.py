@@ -45,6 +45,8 @@ SIGNATURES = {
     'vod_tafa_keyproj_chunk': (_I, [_I, _I, _I, _I]),
     'vod_tafa_keyproj_logits': (_I, [_P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     'vod_tafa_weighted_sum_logits': (_I, [_P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
+    'vod_mdcn_im2col': (_I, [_P, _P, _P, _P] + [_I] * 12 + [_P]),
+    'vod_temporal_softmax_fuse': (_I, [_P, _P, _P, _I, _I, _c.c_long, _P]),
     'vod_nms_workspace_bytes': (_SZ, [_I, _I]),
     'vod_batched_nms': (_I, [_P, _P, _P, _I, _c.POINTER(_I), _I, _F, _I, _I, _P, _P, _P, _SZ, _P]),
     'vod_batched_nms_ex': (_I, [_P, _P, _P, _I, _c.POINTER(_I), _I, _F, _I, _I, _P, _I, _P, _P, _P, _P, _P, _SZ, _P]),

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, 'libvodagg.so')
 _OBJ_DIR = os.path.join(_HERE, '_build', 'obj')
 
 SOURCES = ['common.cu', 'tmap.cu', 'nms.cu', 'roi_align.cu', 'layout.cu', 'warp.cu', 'tafa.cu', 'tafa_keyproj.cu', 'selsa.cu',
-           'selsa_tc.cu', 'msra_gemm.cu', 'msra_overflow.cu', 'decode.cu']
+           'selsa_tc.cu', 'msra_gemm.cu', 'msra_overflow.cu', 'decode.cu', 'deform.cu']
 # test-only kernels (include/vodagg_selftest.h): linked with the shared helpers into a SEPARATE library, so that
 # libvodagg.so carries no test code
 SELFTEST_LIB_PATH = os.path.join(_HERE, 'libvodagg_selftest.so')

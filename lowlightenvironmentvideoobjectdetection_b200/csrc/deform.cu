@@ -1,0 +1,146 @@
+// deform.cu -- the two memory-bound pieces of the fork's temporal-attention fusion (Denoising2Aggergator /
+// TemporalAttentionFusion, mmtracking/mmtrack/models/aggregators/denoising2_aggregator.py:117-152):
+//
+//   (1) vod_mdcn_im2col: the sampling half of mmcv's modulated_deform_conv2d (DCNv2; mmcv-full 1.2.x, source not vendored:
+//       restated from the published algorithm, oracle = oracle/vod_oracle.py:modulated_deform_conv2d pinned against
+//       torchvision.ops.deform_conv2d).  The reference builds, for each of the T*T (reference frame i, frame t) pairs, the
+//       offsets / masks with two convolutions of cat([x_t, x_i]) and chunk / cat / sigmoid passes (:72-79,:141-143).  Both
+//       convolutions are linear, so the host computes them once per FRAME (conv(cat[a, b]) = conv_a(a) + conv_b(b)) and this
+//       kernel takes the pair's raw offset/mask logits as the SUM of a per-t and a per-i map, applies the chunk / cat /
+//       sigmoid semantics in registers, gathers the 4 bilinear corners and writes the modulated columns channels-last, ready
+//       for one library GEMM with the [Cout, K*C] weight.  HBM-bound: reads x (L2-resident, 9x reuse) and 2 x 3*G*K logits per
+//       pixel, writes K*C floats per pixel.
+//   (2) vod_temporal_softmax_fuse: softmax over the frames of the correlation maps and the weighted sum of the frames'
+//       features (:145-147) in one pass (online softmax): reads cor [I, T, E] once and x [T, E] per i, writes [I, E].
+#include "common.cuh"
+
+namespace vod {
+
+// thread = (output pixel, tap k, VEC consecutive channels of one deformable group; VEC = 4 when C / G allows, else 1).  Layouts: x [B, H, W, C]; p / q: raw conv_offset outputs
+// [.., Ho, Wo, 3*G*K] (channels [0, 2GK): offsets, group-major, (dy, dx) interleaved per tap; [2GK, 3GK): mask logits);
+// col [B*Ho*Wo, K*C] with column k*C + c.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+mdcn_im2col_kernel(const float *__restrict__ x, const float *__restrict__ p, const float *__restrict__ q, float *__restrict__ col,
+                   long total, int H, int W, int C, int Ho, int Wo, int G, int kh, int kw, int stride, int pad, int dil,
+                   long p_batch_stride, long q_batch_stride) {
+    const int K = kh * kw, C4 = C / VEC, Cg = C / G;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(idx % C4);
+        long r = idx / C4;
+        const int k = (int)(r % K);
+        r /= K;                                            // output pixel (b, ho, wo)
+        const int wo = (int)(r % Wo);
+        const long r2 = r / Wo;
+        const int ho = (int)(r2 % Ho), b = (int)(r2 / Ho);
+        const int c = c4 * VEC, g = c / Cg;
+        const long pix = (long)ho * Wo + wo;
+        const int och = 3 * G * K;
+        const float *pp = p + b * p_batch_stride + pix * och;
+        const float *qq = q ? q + b * q_batch_stride + pix * och : nullptr;
+        const int io = g * 2 * K + 2 * k, im = 2 * G * K + g * K + k;
+        float dy = __ldg(pp + io), dx = __ldg(pp + io + 1), ml = __ldg(pp + im);
+        if (qq) { dy += __ldg(qq + io); dx += __ldg(qq + io + 1); ml += __ldg(qq + im); }
+        const float m = 1.f / (1.f + __expf(-ml));         // torch.sigmoid(mask) (:78)
+        const float h = (float)(ho * stride - pad + (k / kw) * dil) + dy;
+        const float w = (float)(wo * stride - pad + (k % kw) * dil) + dx;
+        float v[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) v[e] = 0.f;
+        if (h > -1.f && w > -1.f && h < (float)H && w < (float)W) {
+            const float hf = floorf(h), wf = floorf(w);
+            const int h0 = (int)hf, w0 = (int)wf, h1 = h0 + 1, w1 = w0 + 1;
+            const float lh = h - hf, lw = w - wf, hh = 1.f - lh, hw = 1.f - lw;
+            const float *xb = x + ((long)b * H * W) * C + c;
+            // corners outside the map contribute 0 (mmcv dmcn_im2col_bilinear)
+            const float a[4] = {(h0 >= 0 && w0 >= 0) ? hh * hw * m : 0.f, (h0 >= 0 && w1 <= W - 1) ? hh * lw * m : 0.f,
+                                (h1 <= H - 1 && w0 >= 0) ? lh * hw * m : 0.f, (h1 <= H - 1 && w1 <= W - 1) ? lh * lw * m : 0.f};
+            const long o[4] = {((long)h0 * W + w0) * C, ((long)h0 * W + w1) * C, ((long)h1 * W + w0) * C, ((long)h1 * W + w1) * C};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (a[j] == 0.f) continue;                 // outside (or zero weight): the address may be out of range
+                if (VEC == 4) {
+                    const float4 t = ldg_f4(xb + o[j]);
+                    v[0] += a[j] * t.x; v[1 % VEC] += a[j] * t.y; v[2 % VEC] += a[j] * t.z; v[3 % VEC] += a[j] * t.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) v[e] += a[j] * __ldg(xb + o[j] + e);
+                }
+            }
+        }
+        float *dst = col + (r * K + k) * (long)C + c;
+        if (VEC == 4) stg_cs_f4(dst, make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]));
+        else
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) dst[e] = v[e];
+    }
+}
+
+// thread = 4 consecutive elements of one output map i; one pass over the T frames with a running maximum
+__global__ void __launch_bounds__(256)
+temporal_softmax_fuse_kernel(const float *__restrict__ cor, const float *__restrict__ x, float *__restrict__ out, int I, int T,
+                             long E4) {
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < (long)I * E4; idx += (long)gridDim.x * blockDim.x) {
+        const long e = idx % E4;
+        const int i = (int)(idx / E4);
+        const float4 *cp = reinterpret_cast<const float4 *>(cor) + (long)i * T * E4 + e;
+        const float4 *xp = reinterpret_cast<const float4 *>(x) + e;
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, den[4] = {0.f, 0.f, 0.f, 0.f}, num[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int t = 0; t < T; ++t) {
+            const float4 c4 = __ldcs(cp + (long)t * E4);
+            const float4 x4 = __ldg(xp + (long)t * E4);
+            const float cv[4] = {c4.x, c4.y, c4.z, c4.w}, xv[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float nm = fmaxf(mx[j], cv[j]);
+                const float s = __expf(mx[j] - nm), w = __expf(cv[j] - nm);     // first frame: exp(-inf) = 0
+                den[j] = den[j] * s + w;
+                num[j] = num[j] * s + w * xv[j];
+                mx[j] = nm;
+            }
+        }
+        reinterpret_cast<float4 *>(out)[idx] = make_float4(num[0] / den[0], num[1] / den[1], num[2] / den[2], num[3] / den[3]);
+    }
+}
+
+}  // namespace vod
+
+using namespace vod;
+
+extern "C" int vod_mdcn_im2col(const float *x, const float *p, const float *q, float *col, int B, int C, int H, int W, int G,
+                               int kh, int kw, int stride, int pad, int dil, int p_shared, int q_shared, vod_stream_t stream) {
+    if (B == 0) return VOD_OK;
+    VOD_REQUIRE(x && p && col, "vod_mdcn_im2col: null pointer");
+    VOD_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && G > 0 && kh > 0 && kw > 0 && stride > 0 && pad >= 0 && dil > 0,
+                "vod_mdcn_im2col: bad dims");
+    VOD_REQUIRE(C % G == 0, "vod_mdcn_im2col: C must be a multiple of the deformable groups (C=%d G=%d)", C, G);
+    const bool vec4 = (C / G) % 4 == 0;                    // 128-bit accesses when a group's channels allow it
+    VOD_REQUIRE(!vec4 || ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(col)) & 15) == 0,
+                "vod_mdcn_im2col: x and col must be 16-byte aligned");
+    const int Ho = (H + 2 * pad - dil * (kh - 1) - 1) / stride + 1, Wo = (W + 2 * pad - dil * (kw - 1) - 1) / stride + 1;
+    VOD_REQUIRE(Ho > 0 && Wo > 0, "vod_mdcn_im2col: empty output");
+    const long total = (long)B * Ho * Wo * kh * kw * (C / (vec4 ? 4 : 1));
+    const long och = 3L * G * kh * kw, map = (long)Ho * Wo * och;
+    const int grid = (int)min((total + 255) / 256, (long)num_sms() * 32);
+    if (vec4)
+        mdcn_im2col_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(x, p, q, col, total, H, W, C, Ho, Wo, G, kh, kw, stride, pad, dil,
+                                                                  p_shared ? 0 : map, q_shared ? 0 : map);
+    else
+        mdcn_im2col_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(x, p, q, col, total, H, W, C, Ho, Wo, G, kh, kw, stride, pad, dil,
+                                                                  p_shared ? 0 : map, q_shared ? 0 : map);
+    note_launch();
+    return check_launch("vod_mdcn_im2col");
+}
+
+extern "C" int vod_temporal_softmax_fuse(const float *cor, const float *x, float *out, int I, int T, long E, vod_stream_t stream) {
+    if (I == 0 || E == 0) return VOD_OK;
+    VOD_REQUIRE(cor && x && out, "vod_temporal_softmax_fuse: null pointer");
+    VOD_REQUIRE(I > 0 && T > 0 && E > 0 && E % 4 == 0, "vod_temporal_softmax_fuse: bad dims (E must be a multiple of 4)");
+    VOD_REQUIRE(((reinterpret_cast<uintptr_t>(cor) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+                "vod_temporal_softmax_fuse: pointers must be 16-byte aligned");
+    const long total = (long)I * (E / 4);
+    const int grid = (int)min((total + 255) / 256, (long)num_sms() * 32);
+    temporal_softmax_fuse_kernel<<<grid, 256, 0, as_stream(stream)>>>(cor, x, out, I, T, E / 4);
+    note_launch();
+    return check_launch("vod_temporal_softmax_fuse");
+}

@@ -560,6 +560,49 @@ def tafa_weighted_sum_logits(x_all, parts, num_heads, out_nhwc=False, out=None):
     return out
 
 
+def mdcn_im2col(x_nhwc, p, q=None, deform_groups=1, kernel_size=3, stride=1, padding=1, dilation=1, out=None):
+    """Sampling half of mmcv's ``modulated_deform_conv2d`` (DCNv2) for ModulatedDCNPack
+    (denoising2_aggregator.py:72-82): x_nhwc [B,H,W,C]; ``p`` (+ optional ``q``) raw ``conv_offset`` outputs, channels-last
+    [B or 1, Ho, Wo, 3*G*K] (offsets then mask logits; a leading dim of 1 is broadcast over B).  Returns the modulated columns
+    [B*Ho*Wo, K*C]; ``columns @ weight.permute(0, 2, 3, 1).reshape(Cout, K*C).t() + bias`` is the op's channels-last output."""
+    _lib.require_cuda(x_nhwc, p, q)
+    kh, kw = _pair(kernel_size)
+    x_nhwc, p = _f32c(x_nhwc), _f32c(p)
+    B, H, W, C = x_nhwc.shape
+    Ho = (H + 2 * padding - dilation * (kh - 1) - 1) // stride + 1
+    Wo = (W + 2 * padding - dilation * (kw - 1) - 1) // stride + 1
+    och = 3 * deform_groups * kh * kw
+    assert p.shape[1:] == (Ho, Wo, och) and p.shape[0] in (1, B), (tuple(p.shape), (B, Ho, Wo, och))
+    if q is not None:
+        q = _f32c(q)
+        assert q.shape[1:] == (Ho, Wo, och) and q.shape[0] in (1, B), tuple(q.shape)
+    if out is None:
+        out = torch.empty((B * Ho * Wo, kh * kw * C), dtype=torch.float32, device=x_nhwc.device)
+    assert out.is_contiguous() and out.dtype == torch.float32 and out.numel() == B * Ho * Wo * kh * kw * C
+    if B:
+        _lib.call('vod_mdcn_im2col', _lib.ptr(x_nhwc), _lib.ptr(p), _lib.ptr(q), _lib.ptr(out), B, C, H, W, int(deform_groups),
+                  kh, kw, int(stride), int(padding), int(dilation), int(p.shape[0] == 1 and B > 1), int(q is not None and q.shape[0] == 1 and B > 1),
+                  _lib.stream_ptr(x_nhwc.device))
+    return out
+
+
+def temporal_softmax_fuse(cor, x, out=None):
+    """cor [I, T, ...], x [T, ...] (same trailing element order) -> [I, ...]: softmax over the T frames of ``cor`` and the
+    weighted sum of ``x`` in one pass (TemporalAttentionFusion.forward, denoising2_aggregator.py:145-146)."""
+    _lib.require_cuda(cor, x)
+    cor, x = _f32c(cor), _f32c(x)
+    I, T = cor.shape[:2]
+    assert x.shape[0] == T and cor.shape[2:] == x.shape[1:], (tuple(cor.shape), tuple(x.shape))
+    E = x[0].numel()
+    assert E % 4 == 0, 'temporal_softmax_fuse: per-frame element count must be a multiple of 4'
+    if out is None:
+        out = torch.empty((I,) + tuple(x.shape[1:]), dtype=torch.float32, device=x.device)
+    assert out.is_contiguous() and out.numel() == I * E
+    if I and E:
+        _lib.call('vod_temporal_softmax_fuse', _lib.ptr(cor), _lib.ptr(x), _lib.ptr(out), I, T, E, _lib.stream_ptr(x.device))
+    return out
+
+
 def test_gemm_nt(a, b, a_in_tmem=False):
     """D = A @ B^T on the tcgen05 path (unit-test hook for the descriptor/pipeline building blocks; lives in
     libvodagg_selftest.so, not in the product library).

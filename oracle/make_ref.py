@@ -33,6 +33,7 @@ FILES = [
     'mmtracking/mmtrack/models/roi_heads/roi_extractors/single_level_roi_extractor.py',
     'mmtracking/mmtrack/core/motion/flow.py',
     'mmtracking/mmtrack/models/motion/flownet_simple.py',
+    'mmtracking/mmtrack/models/aggregators/denoising2_aggregator.py',
 ]
 
 

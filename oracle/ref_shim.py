@@ -15,6 +15,8 @@ Stand-ins (the only arithmetic they carry is the un-vendored mmcv-full ops):
   mmcv.cnn.ConvModule      -> nn.Conv2d (+ReLU), sub-module named .conv
   mmcv.runner.force_fp32   -> identity decorator
   mmcv.utils.Registry      -> name -> class table with register_module/build
+  mmcv.ops.modulated_deform_conv2d / ModulatedDeformConv2d -> torchvision.ops.deform_conv2d(mask=...) (same DCN-derived
+                              offset layout and border rule; parameters ``weight`` / ``bias`` as mmcv's module)
 """
 import importlib.util
 import os
@@ -145,6 +147,41 @@ def _batched_nms(boxes, scores, idxs, nms_cfg, class_agnostic=False):
     return torch.cat([boxes, scores[:, None]], -1), keep
 
 
+def _modulated_deform_conv2d(input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, deform_groups=1):
+    from torchvision.ops import deform_conv2d
+    assert groups == 1 and offset.shape[1] == 2 * deform_groups * weight.shape[2] * weight.shape[3]
+    return deform_conv2d(input, offset, weight, bias, stride=stride, padding=padding, dilation=dilation, mask=mask)
+
+
+class _ModulatedDeformConv2d(nn.Module):
+    """mmcv.ops.ModulatedDeformConv2d's constructor contract (mmcv-full 1.2.x): attributes read by the reference's
+    ModulatedDCNPack (in_channels, kernel_size pair, stride, padding, deform_groups, ...), parameters ``weight`` / ``bias``."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, deform_groups=1, bias=True):
+        super().__init__()
+        pair = lambda v: (v, v) if isinstance(v, int) else tuple(v)
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size = pair(kernel_size)
+        self.stride, self.padding, self.dilation = stride, padding, dilation
+        self.groups, self.deform_groups = groups, deform_groups
+        self.weight = nn.Parameter(torch.Tensor(out_channels, in_channels // groups, *self.kernel_size))
+        self.bias = nn.Parameter(torch.Tensor(out_channels)) if bias else None
+        n = in_channels
+        for k in self.kernel_size:
+            n *= k
+        stdv = 1. / n ** 0.5
+        self.weight.data.uniform_(-stdv, stdv)
+        if self.bias is not None:
+            self.bias.data.zero_()
+
+
+def _constant_init(module, val, bias=0):
+    if hasattr(module, 'weight') and module.weight is not None:
+        nn.init.constant_(module.weight, val)
+    if hasattr(module, 'bias') and module.bias is not None:
+        nn.init.constant_(module.bias, bias)
+
+
 def _mod(name, **attrs):
     m = types.ModuleType(name)
     m.__path__ = []  # behave as a package so dotted children resolve
@@ -175,10 +212,11 @@ def load():
             raise RuntimeError('real %s already imported; shim refuses to shadow it' % name)
 
     ops_nms = _mod('mmcv.ops.nms', batched_nms=_batched_nms)
-    ops = _mod('mmcv.ops', RoIAlign=_RoIAlign, nms=ops_nms, batched_nms=_batched_nms)
+    ops = _mod('mmcv.ops', RoIAlign=_RoIAlign, nms=ops_nms, batched_nms=_batched_nms,
+               ModulatedDeformConv2d=_ModulatedDeformConv2d, modulated_deform_conv2d=_modulated_deform_conv2d)
     utils = _mod('mmcv.utils', Registry=_Registry, build_from_cfg=_build_from_cfg)
     bricks = _mod('mmcv.cnn.bricks', ConvModule=_ConvModule)
-    cnn = _mod('mmcv.cnn', ConvModule=_ConvModule, bricks=bricks)
+    cnn = _mod('mmcv.cnn', ConvModule=_ConvModule, bricks=bricks, constant_init=_constant_init)
     runner = _mod('mmcv.runner', force_fp32=_force_fp32)
     _mod('mmcv', ops=ops, utils=utils, cnn=cnn, runner=runner)
 
@@ -223,6 +261,9 @@ def load():
                       t + 'models/roi_heads/roi_extractors/single_level_roi_extractor.py')
     flow = _load('mmtrack.core.motion.flow', t + 'core/motion/flow.py')
     flownet = _load('mmtrack.models.motion.flownet_simple', t + 'models/motion/flownet_simple.py')
+    den_path = t + 'models/aggregators/denoising2_aggregator.py'
+    denoise = _load('mmtrack.models.aggregators.denoising2_aggregator', den_path) \
+        if os.path.exists(os.path.join(REF_ROOT, den_path)) else None
 
     ns = types.SimpleNamespace(
         SelsaAggregator=selsa.SelsaAggregator,
@@ -232,6 +273,9 @@ def load():
         MMDetSingleRoIExtractor=single.SingleRoIExtractor,
         flow_warp_feats=flow.flow_warp_feats,
         FlowNetSimple=flownet.FlowNetSimple,
+        Denoising2Aggergator=getattr(denoise, 'Denoising2Aggergator', None),
+        TemporalAttentionFusion=getattr(denoise, 'TemporalAttentionFusion', None),
+        ModulatedDCNPack=getattr(denoise, 'ModulatedDCNPack', None),
         multiclass_nms=bbox_nms.multiclass_nms,
         batched_nms=_batched_nms,
         RoIAlign=_RoIAlign,

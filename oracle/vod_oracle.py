@@ -361,3 +361,76 @@ def rpn_get_bboxes(cls_score, bbox_pred, anchors, img_shape, nms_pre=6000, nms_t
     ids = torch.zeros(len(scores), dtype=torch.long)                              # single level -> level id 0
     dets, _ = batched_nms(proposals, scores, ids, dict(type='nms', iou_threshold=nms_thr))   # :233-235
     return dets[:max_per_img]
+
+
+# ----------------------------------------------------------------------------- temporal attention fusion (Denoising2Aggergator)
+def _cpu32(t):
+    return t.detach().to('cpu', torch.float32).contiguous()
+
+
+def modulated_deform_conv2d(x, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, deform_groups=1):
+    """mmcv.ops.modulated_deform_conv2d (DCNv2) -- mmcv-full 1.2.x, NOT vendored in /root/reference; call site
+    mmtracking/mmtrack/models/aggregators/denoising2_aggregator.py:79-82.  Published algorithm (modulated_deformable_im2col):
+    for output pixel (ho, wo), tap k = (i, j) and deformable group g, the sample point is
+    (ho*stride - pad + i*dil + offset[g*2K + 2k], wo*stride - pad + j*dil + offset[g*2K + 2k + 1]); its value is the bilinear
+    interpolation of the input (corners outside the map contribute 0; 0 when the point is not inside (-1, H) x (-1, W)) times
+    mask[g*K + k]; the columns are then multiplied by the weight.  Pinned against torchvision.ops.deform_conv2d (the same
+    DCN-derived layout and border rule) in tests/test_oracle.py."""
+    assert groups == 1
+    x, offset, mask, weight = _cpu32(x), _cpu32(offset), _cpu32(mask), _cpu32(weight)
+    B, C, H, W = x.shape
+    Cout, _, kh, kw = weight.shape
+    K, G = kh * kw, deform_groups
+    Ho = (H + 2 * padding - dilation * (kh - 1) - 1) // stride + 1
+    Wo = (W + 2 * padding - dilation * (kw - 1) - 1) // stride + 1
+    assert offset.shape == (B, 2 * G * K, Ho, Wo) and mask.shape == (B, G * K, Ho, Wo)
+    Cg = C // G
+    ho = torch.arange(Ho, dtype=torch.float32).view(1, 1, Ho, 1) * stride - padding
+    wo = torch.arange(Wo, dtype=torch.float32).view(1, 1, 1, Wo) * stride - padding
+    ki = (torch.arange(K) // kw).float().view(1, K, 1, 1) * dilation
+    kj = (torch.arange(K) % kw).float().view(1, K, 1, 1) * dilation
+    cols = x.new_zeros(B, C, K, Ho, Wo)
+    xf = x.reshape(B, C, H * W)
+    for g in range(G):
+        off = offset[:, g * 2 * K:(g + 1) * 2 * K].view(B, K, 2, Ho, Wo)
+        h = ho + ki + off[:, :, 0]
+        w = wo + kj + off[:, :, 1]                                        # [B, K, Ho, Wo]
+        inside = (h > -1) & (w > -1) & (h < H) & (w < W)
+        h0, w0 = torch.floor(h), torch.floor(w)
+        lh, lw = h - h0, w - w0
+        val = x.new_zeros(B, Cg, K, Ho, Wo)
+        for dh, dw, wt in ((0, 0, (1 - lh) * (1 - lw)), (0, 1, (1 - lh) * lw), (1, 0, lh * (1 - lw)), (1, 1, lh * lw)):
+            hi, wi = (h0 + dh).long(), (w0 + dw).long()
+            ok = inside & (hi >= 0) & (hi <= H - 1) & (wi >= 0) & (wi <= W - 1)
+            lin = (hi.clamp(0, H - 1) * W + wi.clamp(0, W - 1)).view(B, 1, -1).expand(B, Cg, -1)
+            v = torch.gather(xf[:, g * Cg:(g + 1) * Cg], 2, lin).view(B, Cg, K, Ho, Wo)
+            val = val + v * (wt * ok)[:, None]
+        cols[:, g * Cg:(g + 1) * Cg] = val * mask[:, g * K:(g + 1) * K][:, None]
+    out = torch.einsum('ock,bckp->bop', weight.reshape(Cout, C, K), cols.reshape(B, C, K, Ho * Wo)).view(B, Cout, Ho, Wo)
+    if bias is not None:
+        out = out + _cpu32(bias).view(1, -1, 1, 1)
+    return out
+
+
+def temporal_attention_fusion(x, p):
+    """TemporalAttentionFusion.forward (denoising2_aggregator.py:135-152) with the parameters in ``p`` (state_dict names).
+    Written as the reference runs it: per reference frame i, T pair-wise offset convs, DCN, embed convs, softmax over frames."""
+    F_ = torch.nn.functional
+    x = torch.relu(F_.conv2d(_cpu32(x), p['conv1.weight'], p['conv1.bias'], padding=1))
+    T = x.shape[0]
+    n_emb = len([k for k in p if k.startswith('emb_conv.') and k.endswith('.weight')])
+    G = p['dcn_pack.conv_offset.weight'].shape[0] // 27
+    feat = []
+    for i in range(T):
+        x_ref = x[i:i + 1].repeat(T, 1, 1, 1)
+        x_set = F_.conv2d(torch.cat([x, x_ref], 1), p['offset_conv.weight'], p['offset_conv.bias'], padding=1)
+        o = F_.conv2d(x_set, p['dcn_pack.conv_offset.weight'], p['dcn_pack.conv_offset.bias'], padding=1)
+        o1, o2, m = torch.chunk(o, 3, dim=1)
+        x_dcn = modulated_deform_conv2d(x, torch.cat((o1, o2), 1), torch.sigmoid(m), p['dcn_pack.weight'], p['dcn_pack.bias'],
+                                        1, 1, 1, 1, G)
+        x_cor = x_dcn * x_ref
+        for e in range(n_emb):
+            x_cor = F_.conv2d(x_cor, p['emb_conv.%d.weight' % e], p['emb_conv.%d.bias' % e], padding=1)
+        feat.append((torch.softmax(x_cor, 0) * x).sum(0, keepdim=True))
+    out = torch.cat(feat, 0)
+    return torch.relu(F_.conv2d(out, p['conv2.weight'], p['conv2.bias'], padding=1))

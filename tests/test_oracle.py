@@ -135,3 +135,46 @@ def test_flownet_simple_mirror_matches_the_reference():
         lr, info = ours(imgs.clone(), metas, return_lowres=True)
     assert a.shape == (2, 2, 96, 128) and torch.equal(a, b)
     assert lr.shape == (2, 2, 12, 16) and info == dict(up_scale=8.0, mult1=8.0, mult2=5.0, full_size=(96, 128))
+
+
+def test_modulated_deform_conv_restatement_vs_torchvision():
+    """mmcv-full's modulated_deform_conv2d is not vendored: the oracle restates the published DCNv2 algorithm; pinned here
+    against torchvision.ops.deform_conv2d (same offset layout and border rule) incl. stride 2 and samples outside the map."""
+    from torchvision.ops import deform_conv2d
+    g = torch.Generator().manual_seed(0)
+    for (B, C, H, W, G, Co, stride) in [(2, 16, 9, 11, 4, 8, 1), (1, 8, 10, 7, 2, 5, 2)]:
+        Ho, Wo = (H + 2 - 3) // stride + 1, (W + 2 - 3) // stride + 1
+        x = torch.randn(B, C, H, W, generator=g)
+        off = torch.randn(B, 2 * G * 9, Ho, Wo, generator=g) * 3
+        m = torch.rand(B, G * 9, Ho, Wo, generator=g)
+        w, b = torch.randn(Co, C, 3, 3, generator=g), torch.randn(Co, generator=g)
+        want = deform_conv2d(x, off, w, b, stride=stride, padding=1, mask=m)
+        got = O.modulated_deform_conv2d(x, off, m, w, b, stride, 1, 1, 1, G)
+        assert (got - want).abs().max() <= 1e-5 * want.abs().max()
+
+
+def test_temporal_attention_fusion_restatement_vs_reference_file():
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip('reference files not staged')
+    R = ref_shim.load()
+    torch.manual_seed(0)
+    taf = R.TemporalAttentionFusion(16, 8, emb_nums=3).eval()
+    torch.nn.init.normal_(taf.dcn_pack.conv_offset.weight, 0, 0.05)
+    torch.nn.init.normal_(taf.dcn_pack.conv_offset.bias, 0, 0.5)
+    x = torch.randn(4, 16, 10, 13)
+    with torch.no_grad():
+        want = taf(x.clone())
+    got = O.temporal_attention_fusion(x, dict(taf.state_dict()))
+    assert (got - want).abs().max() <= 1e-5 * want.abs().max()
+
+
+def test_denoising_aggregator_mirror_has_the_reference_state_dict():
+    from oracle import ref_shim
+    import lowlightenvironmentvideoobjectdetection_b200 as vod
+    if not ref_shim.available():
+        pytest.skip('reference files not staged')
+    R = ref_shim.load()
+    ref, ours = R.Denoising2Aggergator(), vod.build_aggregator(dict(type='Denoising2Aggergator'))
+    a, b = ref.state_dict(), ours.state_dict()
+    assert list(a) == list(b) and all(a[k].shape == b[k].shape for k in a)

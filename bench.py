@@ -51,6 +51,9 @@ CONFIGS = {
                  workload='FGFA R-50-DC5 feature path, 2 ref frames (+key slot), flow 608x1008, bf16 maps, 300 proposals, 600x1000'),
     'cfg4': dict(family='dff', N=300, interval=10, clip=300,
                  workload='DFF R-50-DC5 feature propagation, key-frame interval 10, low-light clip of 300 frames, 300 proposals'),
+    'denoise': dict(family='denoise', T=9,
+                    workload='Denoising2Aggergator (RDB + deformable temporal attention fusion) over the ResNet-50 stage features of '
+                             '8 ref frames (+key), 608x1008 low-light clip'),
     'sweep': dict(family='sweep', Ns=(300, 500, 1000), refs=(2, 6, 14, 30), fcs=3, troi=True,
                   workload='SELSA+TemporalRoIAlign aggregation sweep: 300-1000 proposals x 2-30 ref frames (+key), 600x1000'),
 }
@@ -1277,6 +1280,8 @@ def reference_arm(args, cfg, cfg_name):
         cfg = dict(CONFIGS['cfg3'], workload=CONFIGS['sweep']['workload'] + ' -- reference arm: the (300, 14) cell')
     if cfg['family'] in ('fgfa', 'dff'):
         return reference_arm_feature_level(args, cfg, cfg_name)
+    if cfg['family'] == 'denoise':
+        return reference_arm_denoise(args, cfg)
     warm = min(args.warmup, 1)
     times, cores, kind, _ = time_cpu(cfg, args.steps, warm)
     ms = 1e3 * sum(times) / len(times)
@@ -1292,6 +1297,45 @@ def reference_arm(args, cfg, cfg_name):
         'dtype': 'f32', 'data': 'synthetic', 'config': config,
         'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': kind,
                          'sample': '%d key frame(s) of the same workload on the host cores; steps bounded by a 150 s wall-clock budget' % len(times)},
+        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+
+
+def reference_arm_denoise(args, cfg):
+    """``--impl reference --config denoise``: the reference's own denoising2_aggregator.py on the host cores.  One step = the
+    stage-3 TemporalAttentionFusion of the 9-frame clip (the bounded sample; the whole module is minutes per frame on a CPU), scaled
+    to frames/s by that stage's share of the module's fusion FLOPs."""
+    if not reference_available():
+        print(json.dumps({'impl': 'reference', 'unavailable': 'reference files not staged (run python -m oracle.make_ref where /root/reference exists)'}))
+        return
+    from oracle import ref_shim
+    R = ref_shim.load()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    T = cfg['T']
+    taf = R.TemporalAttentionFusion(1024, 256, emb_nums=3).eval()
+    flops_ref = sum(denoise_taf_flops(T, m, hw[0] * hw[1], True) for m, hw in zip(DENOISE_SPEC['mid_channel'], DENOISE_HW))
+    share = denoise_taf_flops(T, 256, 38 * 63, True) / flops_ref
+    times, t_start = [], time.perf_counter()
+    for i in range(args.steps):
+        x3 = denoise_inputs(i, T)[2]
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            taf(x3)
+            times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > 150.0:
+            break
+    ms = 1e3 * sum(times) / len(times) / share
+    val = 1e3 / ms
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'VID frames/sec (Denoising2Aggergator)', 'value': val, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': len(times), 'warmup': 0, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': dict(workload=cfg['workload'], frames=T, execution='torch CPU eager on all host threads: the reference\'s own unmodified '
+                       'file (oracle/_ref) under the mmcv stand-ins of oracle/ref_shim.py (DCN = torchvision.ops.deform_conv2d)', parallelism='rank 0 only'),
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'reference',
+                         'sample': 'stage-3 TemporalAttentionFusion of the 9-frame clip per step (%.1f %% of the module\'s fusion FLOPs), time scaled by '
+                                   'that share; bounded by a 150 s wall-clock budget' % (100 * share)},
         'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
 
@@ -1338,6 +1382,166 @@ def reference_arm_feature_level(args, cfg, cfg_name):
         'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
 
+
+# --------------------------------------------------------------------------------------------- denoising aggregator (8f N4)
+DENOISE_SPEC = dict(in_channel=[256, 512, 1024, 2048], mid_channel=[64, 128, 256, 512], out_channel=[512, 1024, 2048, 512],
+                    layer_name=['layer1', 'layer2', 'layer3', 'layer4'], rdb_blocks=[2, 2, 4, 2], rdb_channel_growth=[64, 64, 128, 128],
+                    taf_embs=[3, 3, 3, 3], downsample=[True, True, False, False], with_rdb=[True] * 4, with_taf=[True] * 4)
+DENOISE_HW = [(152, 252), (76, 126), (38, 63), (38, 63)]     # ResNet-50 strides (1,2,2,1) after the /4 stem, 608x1008 input
+
+
+def denoise_inputs(seed, T, device='cpu', pinned=False):
+    """Stage features of a low-light clip (post-ReLU statistics scaled by 0.25) + the detector's final map."""
+    g = torch.Generator().manual_seed(4321 + seed)
+    xs = [torch.relu(torch.randn(T, c, h, w, generator=g)) * 0.25 for c, (h, w) in zip(DENOISE_SPEC['in_channel'], DENOISE_HW)]
+    xs.append(torch.relu(torch.randn(T, 512, 38, 63, generator=g)) * 0.25)
+    if pinned:
+        xs = [t.pin_memory() for t in xs]
+    return [t.to(device) for t in xs]
+
+
+def denoise_taf_flops(T, mid, hw, reference):
+    """Convolution FLOPs of one TemporalAttentionFusion call without conv1 / conv2 (they are outside the T^2 part)."""
+    per_px = lambda cin, cout: 2 * 9 * cin * cout
+    pair = per_px(mid, mid) * (1 + 3)                                          # deformable conv + 3 embed convs per pair
+    if reference:
+        return hw * T * T * (pair + per_px(2 * mid, mid) + per_px(mid, 216))   # + offset_conv and conv_offset per pair
+    return hw * (T * T * pair + T * (2 * per_px(mid, mid) + 2 * per_px(mid, 216)))
+
+
+def bench_denoise(ctx, cfg):
+    import lowlightenvironmentvideoobjectdetection_b200 as vod
+    args, dev = ctx.args, ctx.device
+    T = cfg['T']
+    torch.manual_seed(0)
+    agg = vod.build_aggregator(dict(type='Denoising2Aggergator', **DENOISE_SPEC)).eval()
+    for name, mod in agg.named_modules():              # a trained pack has non-zero offsets: sample off-grid, some outside the map
+        if name.endswith('conv_offset'):
+            torch.nn.init.normal_(mod.weight, 0, 0.02)
+            torch.nn.init.normal_(mod.bias, 0, 0.5)
+    sd = {k: v.clone() for k, v in agg.state_dict().items()}
+    agg = agg.to(dev)
+    n_sets = 2
+    host = [denoise_inputs(ctx.rank * 100 + i, T, pinned=True) for i in range(n_sets)]
+    st = [t.to(dev) for t in host[0]]
+    lib = vod._lib.load()
+
+    def step():
+        noise_out, all_out = agg(st[:4], st[4:])
+        return all_out[0][-1:]                          # the key frame's fused map feeds the detector (selsa_new_darkfarm_detect.py:279-282)
+
+    out_host = torch.empty(1, 512, 38, 63).pin_memory()
+    with torch.no_grad(), library_math(True):
+        l0 = lib.vod_kernel_launch_count()
+        res = step()
+        torch.cuda.synchronize()
+        launches = lib.vod_kernel_launch_count() - l0
+        sampler = ClockSampler(ctx.local_rank); sampler.start()
+
+        def dev_loop(k):
+            for i in range(k):
+                step()
+        dev_loop(max(args.warmup, 3))
+        ctx.barrier()
+        sampler.first, sampler.reasons = len(sampler.samples), set()
+        t_dev = ctx.timed(lambda: dev_loop(args.steps))
+        sampler.stop_flag = True
+
+        # end to end: the key frame's own stage features arrive from pinned host memory every step (the other T-1 frames are the
+        # detector's resident memory, selsa_new_darkfarm_detect.py:258-278); the fused key map is read back
+        def e2e_loop(k):
+            for i in range(k):
+                for d_, h_ in zip(st, host[i % n_sets]):
+                    d_[-1:].copy_(h_[-1:], non_blocking=True)
+                out_host.copy_(step(), non_blocking=True)
+            torch.cuda.synchronize()
+        e2e_loop(1)
+        t_e2e = ctx.timed(lambda: e2e_loop(args.steps))
+        # our kernels inside the step, timed alone at the stage-1 shape (the largest): roofline of the dominant one
+        peaks = load_peaks()
+        mid, (h, w) = 64, DENOISE_HW[0]
+        y = torch.randn(T, h, w, mid, device=dev)
+        pq = torch.randn(T + 1, h, w, 216, device=dev) * 0.7       # offsets of ~1 pixel (sum of the per-t and per-i maps)
+        col = torch.empty(T * h * w, 9 * mid, device=dev)
+        cor = torch.randn(T, T, h, w, mid, device=dev)
+
+        def timeit(fn, reps=10):
+            fn(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+            return e0.elapsed_time(e1) * 1e-3 / reps
+        t_col = timeit(lambda: vod.ops.mdcn_im2col(y, pq[:T], pq[T:], 8, 3, 1, 1, 1, out=col))
+        t_fuse = timeit(lambda: vod.ops.temporal_softmax_fuse(cor, y))
+        b_col = (col.numel() + pq.numel() + y.numel()) * 4
+        b_fuse = (cor.numel() + y.numel() + T * y[0].numel()) * 4
+        del col, cor
+    frames = args.steps * ctx.world
+    flops_ours = sum(denoise_taf_flops(T, m, hw[0] * hw[1], False) for m, hw in zip(DENOISE_SPEC['mid_channel'], DENOISE_HW))
+    flops_ref = sum(denoise_taf_flops(T, m, hw[0] * hw[1], True) for m, hw in zip(DENOISE_SPEC['mid_channel'], DENOISE_HW))
+    h2d = sum(t[-1:].numel() * 4 for t in host[0])
+    config = dict(workload=cfg['workload'], frames=T, execution='eager launches (library convolutions, channels-last, tf32 library math) + vodagg kernels',
+                  step='conv1 -> RDBs -> TemporalAttentionFusion (4T offset convs, vod_mdcn_im2col + GEMM and 3 embed convs per pair, '
+                       'vod_temporal_softmax_fuse) -> conv2, four stages; fusion convolution work %.2f TFLOP (reference formulation: %.2f)'
+                       % (flops_ours / 1e12, flops_ref / 1e12),
+                  l2_policy='per-step working set of several GB: nothing survives in L2 between steps', parallelism='clip-sharded x%d' % ctx.world)
+    result = base_result(ctx, cfg, 'VID frames/sec (Denoising2Aggergator)', UNIT, frames / t_dev, t_dev / args.steps, 'tf32', config)
+    result.update({'e2e': {'value': frames / t_e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(out_host.numel() * 4)},
+                   'gpu_launches': int(launches * args.steps), 'clocks': sampler.summary(),
+                   'roofline': {'kernel': 'mdcn_im2col_kernel<4> (stage 1: 9 frames, 152x252, 64 channels, 8 deformable groups)', 'bound': 'hbm',
+                                'achieved': b_col / t_col / 1e9, 'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': b_col / t_col / 1e9 / peaks['hbm'],
+                                'traffic': None, 'seconds': t_col},
+                   'kernels': {'mdcn_im2col_stage1': {'seconds': t_col, 'achieved': b_col / t_col / 1e9, 'unit': 'GB/s', 'frac': b_col / t_col / 1e9 / peaks['hbm']},
+                               'temporal_softmax_fuse_stage1': {'seconds': t_fuse, 'achieved': b_fuse / t_fuse / 1e9, 'unit': 'GB/s',
+                                                                'frac': b_fuse / t_fuse / 1e9 / peaks['hbm']}}})
+    if ctx.rank == 0 and ctx.world == 1 and reference_available():
+        from oracle import ref_shim
+        R = ref_shim.load()
+        ref = R.Denoising2Aggergator(**DENOISE_SPEC).eval()
+        ref.load_state_dict(sd, strict=True)
+        if not args.no_eager_reference:
+            # second comparator: the reference's own file, torch-eager on the same B200 (mmcv's DCN -> torchvision's CUDA op)
+            ref_dev = ref.to(dev)
+            with torch.no_grad():
+                outs = {}
+                for name, tf32 in (('fp32', False), ('tf32', True)):
+                    with library_math(tf32):
+                        want = ref_dev([t.clone() for t in st[:4]], [t.clone() for t in st[4:]])
+                        torch.cuda.synchronize()
+                        t0 = time.perf_counter()
+                        for _ in range(2):
+                            ref_dev([t.clone() for t in st[:4]], [t.clone() for t in st[4:]])
+                        torch.cuda.synchronize()
+                        outs[name] = (time.perf_counter() - t0) / 2
+                        got = agg(st[:4], st[4:])
+                        err = max(_rel_err(a, b)[0] for a, b in zip(got[0] + got[1], want[0] + want[1]))
+                        outs[name + '_err'] = err
+                    del want, got
+            result['eager_cuda_reference'] = {'value': 1.0 / outs['tf32'], 'unit': UNIT, 'ms_per_step': 1e3 * outs['tf32'],
+                                              'fp32_library_math': {'value': 1.0 / outs['fp32'], 'ms_per_step': 1e3 * outs['fp32']},
+                                              'note': 'denoising2_aggregator.py unmodified on the same GPU; mmcv modulated_deform_conv2d = torchvision.ops.deform_conv2d (CUDA)'}
+            result['parity'] = {'against': 'eager_cuda_reference outputs (all denoised stage maps + fused map), same weights and inputs',
+                                'fp32_library_math_rel_err': outs['fp32_err'], 'tf32_library_math_rel_err': outs['tf32_err']}
+            ref = ref.cpu()
+        if not args.no_cpu_baseline:
+            # bounded CPU sample: the stage-3 fusion (1024 -> 256 channels, 38x63) of the same 9 frames, scaled by its share of the
+            # reference formulation's fusion FLOPs
+            torch.set_num_threads(os.cpu_count() or 1)
+            taf = ref.layers['layer3_taf']
+            x3 = host[0][2].float()
+            with torch.no_grad():
+                t0 = time.perf_counter()
+                taf(x3)
+                dt = time.perf_counter() - t0
+            share = denoise_taf_flops(T, 256, 38 * 63, True) / flops_ref
+            result['cpu_baseline'] = {'value': share / dt, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'reference',
+                                      'sample': 'stage-3 TemporalAttentionFusion of the same 9 frames (%.1f s on the host cores) = %.1f %% of the '
+                                                'module\'s fusion FLOPs; value = that share / its time (RDBs and stage convs not counted: an upper bound)'
+                                                % (dt, 100 * share)}
+    return result
+
 # --------------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -1374,6 +1578,8 @@ def main():
         result = bench_sweep(ctx, cfg)
     elif fam == 'fgfa':
         result = bench_fgfa(ctx, cfg)
+    elif fam == 'denoise':
+        result = bench_denoise(ctx, cfg)
     else:
         result = bench_dff(ctx, cfg)
     ctx.close()

@@ -13,7 +13,10 @@ reference runs as a Python loop over the reference frame i with, per i, T convol
     instead of 2 T^2, and the T^2 offset / mask tensors (216 channels each) are never materialised;
   * ``vod_mdcn_im2col`` takes P[t] + Q[i] directly, applies the chunk / cat / sigmoid semantics in registers and writes the
     modulated columns channels-last for ONE library GEMM per group of pairs (mmcv's op, absent here, does im2col + GEMM per image);
-  * ``vod_temporal_softmax_fuse`` does softmax over frames + weighted sum in one pass.
+  * ``vod_temporal_softmax_fuse`` does softmax over frames + weighted sum in one pass;
+  * the embed convs (:130-131) are a purely linear chain whose result only enters a softmax over the frames: their biases add
+    a map that is the same for every frame t (and every i), which that softmax cancels, so the chain runs without biases
+    (3 T^2 full-size bias passes less); everything runs channels-last so the library never re-lays tensors out between convs.
 """
 import torch
 import torch.nn as nn
@@ -25,6 +28,13 @@ from .registry import AGGREGATORS, inference_only
 
 def _cl(t):
     return t.contiguous(memory_format=torch.channels_last)
+
+
+def _conv_relu(conv, x):
+    """relu(conv(x) + bias) with the bias and the ReLU in the library convolution's epilogue (cuDNN fused op) on the GPU."""
+    if x.is_cuda and x.dtype == torch.float32:
+        return torch.cudnn_convolution_relu(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
+    return F.relu(conv(x))
 
 
 def _nhwc(t):
@@ -40,7 +50,7 @@ class DenseLayer(nn.Module):
         self.conv = nn.Conv2d(in_channels, out_channels, kernel_size=3, padding=1)
 
     def forward(self, x):
-        return torch.cat((x, F.relu(self.conv(x))), 1)
+        return torch.cat((x, _conv_relu(self.conv, x)), 1)
 
 
 class RDB(nn.Module):
@@ -115,7 +125,7 @@ class TemporalAttentionFusion(nn.Module):
         in_dtype = x.dtype
         T, _, H, W = x.shape
         mid = self.mid_channels
-        y = _cl(F.relu(self.conv1(_cl(x.float()))))                                         # :136
+        y = _cl(_conv_relu(self.conv1, _cl(x.float())))                                     # :136
         # offsets / mask logits of the pair (i, t) = P[t] + Q[i]   (:141-142 and :75 of the pack, both linear)
         w_off, co = self.offset_conv.weight, self.dcn_pack.conv_offset
         a = F.conv2d(y, w_off[:, :mid], None, padding=1)
@@ -128,12 +138,12 @@ class TemporalAttentionFusion(nn.Module):
             d = self.dcn_pack.from_logits(y_nhwc, p, q[i:i + 1]).view(T, H, W, mid)         # :143, frame t aligned to frame i
             d.mul_(y_nhwc[i])                                                               # :144
             c = d.permute(0, 3, 1, 2)                                                       # channels-last [T, mid, H, W]
-            for conv in self.emb_conv:
-                c = conv(c)
+            for conv in self.emb_conv:      # no bias: constant over t, cancelled by the softmax over frames below
+                c = F.conv2d(c, conv.weight, None, conv.stride, conv.padding)
             cor[i].copy_(c.permute(0, 2, 3, 1))
         fused = ops.temporal_softmax_fuse(cor, y_nhwc)                                      # :145-146 for every i
-        out = F.relu(self.conv2(fused.permute(0, 3, 1, 2)))                                 # :149-151
-        return out.contiguous().to(in_dtype)
+        out = _conv_relu(self.conv2, fused.permute(0, 3, 1, 2))                             # :149-151
+        return out.to(in_dtype)                     # channels-last strides; Denoising2Aggergator hands NCHW-contiguous maps out
 
 
 @AGGREGATORS.register_module()
@@ -168,6 +178,7 @@ class Denoising2Aggergator(nn.Module):
     def forward(self, x_noise, all_x):
         denoised, carried = [], None
         last = self.num_stage - 1
+        x_noise = [_cl(t) for t in x_noise]             # channels-last once: every conv / cat below then stays in that layout
         for s, name in enumerate(self.layer_name):
             f = x_noise[s] if s == 0 else torch.cat((x_noise[s], carried), 1)               # :222-225
             x = self.layers[name + '_conv1'](f)
@@ -176,7 +187,7 @@ class Denoising2Aggergator(nn.Module):
             if self.with_taf[s]:
                 x = self.layers[name + '_taf'](x)
             res = x + x_noise[s]
-            denoised.append(res)                                                            # :231
+            denoised.append(res.contiguous())                                               # :231
             carried = self.layers[name + '_conv2'](x if s == last else res)                 # :232-235
-        fused = all_x[-1] + carried                                                         # :238-242: the same sum per level
+        fused = (all_x[-1] + carried).contiguous()                                          # :238-242: the same sum per level
         return tuple(denoised), tuple(fused for _ in all_x)

@@ -2,7 +2,7 @@
 // TemporalAttentionFusion, mmtracking/mmtrack/models/aggregators/denoising2_aggregator.py:117-152):
 //
 //   (1) vod_mdcn_im2col: the sampling half of mmcv's modulated_deform_conv2d (DCNv2; mmcv-full 1.2.x, source not vendored:
-//       restated from the published algorithm, oracle = oracle/vod_oracle.py:modulated_deform_conv2d pinned against
+//       restated from the published algorithm; the test oracle's restatement is pinned against
 //       torchvision.ops.deform_conv2d).  The reference builds, for each of the T*T (reference frame i, frame t) pairs, the
 //       offsets / masks with two convolutions of cat([x_t, x_i]) and chunk / cat / sigmoid passes (:72-79,:141-143).  Both
 //       convolutions are linear, so the host computes them once per FRAME (conv(cat[a, b]) = conv_a(a) + conv_b(b)) and this

@@ -1517,7 +1517,7 @@ def bench_denoise(ctx, cfg):
     result = base_result(ctx, cfg, 'VID frames/sec (Denoising2Aggergator)', UNIT, frames / t_dev, t_dev / args.steps, 'tf32', config)
     result.update({'e2e': {'value': frames / t_e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(out_host.numel() * 4)},
                    'gpu_launches': int(launches * args.steps), 'clocks': sampler.summary(),
-                   'roofline': {'kernel': 'mdcn_im2col_kernel<4> (stage 1: 9 frames, 152x252, 64 channels, 8 deformable groups)', 'bound': 'hbm',
+                   'roofline': {'kernel': 'mdcn_im2col_tile_kernel (stage 1: 9 frames, 152x252, 64 channels, 8 deformable groups)', 'bound': 'hbm',
                                 'achieved': b_col / t_col / 1e9, 'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': b_col / t_col / 1e9 / peaks['hbm'],
                                 'traffic': None, 'seconds': t_col},
                    'kernels': {'mdcn_im2col_stage1': {'seconds': t_col, 'achieved': b_col / t_col / 1e9, 'unit': 'GB/s', 'frac': b_col / t_col / 1e9 / peaks['hbm']},

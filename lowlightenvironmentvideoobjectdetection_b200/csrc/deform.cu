@@ -130,7 +130,7 @@ mdcn_im2col_tile_kernel(const float *__restrict__ x, const float *__restrict__ p
             d.x += d2.x; d.y += d2.y;
             ml += __ldg(qq + 2 * G * K + g * 9 + k);
         }
-        const float m = 1.f / (1.f + __expf(-ml));
+        const float m = __frcp_rn(1.f + __expf(-ml));
         const float h = (float)(ho - 1 + k / 3) + d.x, w = (float)(wo - 1 + k % 3) + d.y;
         // 16-byte chunk pair (cl/4, cl/4 + 1): read the odd chunk first when bit 3 of the chunk index is set, so that the 8
         // threads of a quarter-warp (8 consecutive chunk pairs) cover the 8 bank groups in both loads
@@ -141,23 +141,38 @@ mdcn_im2col_tile_kernel(const float *__restrict__ x, const float *__restrict__ p
             const int h0 = (int)hf, w0 = (int)wf;
             const float lh = h - hf, lw = w - wf, hh = 1.f - lh, hw = 1.f - lw;
             const float a[4] = {hh * hw * m, hh * lw * m, lh * hw * m, lh * lw * m};
+            const int sy0 = h0 - (ho0 - kDcnHalo), sx0 = w0 - (wo0 - kDcnHalo);
+            if (h0 >= 0 && h0 < H - 1 && w0 >= 0 && w0 < W - 1 && sy0 >= 0 && sy0 < TS - 1 && sx0 >= 0 && sx0 < TS - 1) {
+                // common case: all four corners inside the map and inside the staged neighbourhood
+                const float *sp = s_x + (sy0 * TS + sx0) * CS + cl + 4 * flip;
+                const int o1 = 4 - 8 * flip;                  // offset of the chunk read second
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int hy = h0 + (j >> 1), wx = w0 + (j & 1);
-                if (hy < 0 || hy > H - 1 || wx < 0 || wx > W - 1) continue;      // corners outside the map contribute 0
-                const int sy = hy - (ho0 - kDcnHalo), sx = wx - (wo0 - kDcnHalo);
-                float4 t0, t1;
-                if (sy >= 0 && sy < TS && sx >= 0 && sx < TS) {
-                    const float *sp = s_x + (sy * TS + sx) * CS + cl;
-                    t0 = *reinterpret_cast<const float4 *>(sp + 4 * flip);
-                    t1 = *reinterpret_cast<const float4 *>(sp + 4 - 4 * flip);
-                } else {
-                    const float *gp = x + (((long)b * H + hy) * W + wx) * C + c0 + cl;
-                    t0 = ldg_f4(gp + 4 * flip);
-                    t1 = ldg_f4(gp + 4 - 4 * flip);
+                for (int j = 0; j < 4; ++j) {
+                    const float *sq = sp + ((j >> 1) * TS + (j & 1)) * CS;
+                    const float4 t0 = *reinterpret_cast<const float4 *>(sq);
+                    const float4 t1 = *reinterpret_cast<const float4 *>(sq + o1);
+                    u0.x += a[j] * t0.x; u0.y += a[j] * t0.y; u0.z += a[j] * t0.z; u0.w += a[j] * t0.w;
+                    u1.x += a[j] * t1.x; u1.y += a[j] * t1.y; u1.z += a[j] * t1.z; u1.w += a[j] * t1.w;
                 }
-                u0.x += a[j] * t0.x; u0.y += a[j] * t0.y; u0.z += a[j] * t0.z; u0.w += a[j] * t0.w;
-                u1.x += a[j] * t1.x; u1.y += a[j] * t1.y; u1.z += a[j] * t1.z; u1.w += a[j] * t1.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int hy = h0 + (j >> 1), wx = w0 + (j & 1);
+                    if (hy < 0 || hy > H - 1 || wx < 0 || wx > W - 1) continue;      // corners outside the map contribute 0
+                    const int sy = hy - (ho0 - kDcnHalo), sx = wx - (wo0 - kDcnHalo);
+                    float4 t0, t1;
+                    if (sy >= 0 && sy < TS && sx >= 0 && sx < TS) {
+                        const float *sp = s_x + (sy * TS + sx) * CS + cl;
+                        t0 = *reinterpret_cast<const float4 *>(sp + 4 * flip);
+                        t1 = *reinterpret_cast<const float4 *>(sp + 4 - 4 * flip);
+                    } else {
+                        const float *gp = x + (((long)b * H + hy) * W + wx) * C + c0 + cl;
+                        t0 = ldg_f4(gp + 4 * flip);
+                        t1 = ldg_f4(gp + 4 - 4 * flip);
+                    }
+                    u0.x += a[j] * t0.x; u0.y += a[j] * t0.y; u0.z += a[j] * t0.z; u0.w += a[j] * t0.w;
+                    u1.x += a[j] * t1.x; u1.y += a[j] * t1.y; u1.z += a[j] * t1.z; u1.w += a[j] * t1.w;
+                }
             }
         }
         float *dst = col + ((((long)b * H + ho) * W + wo) * K + k) * (long)C + c0 + cl;

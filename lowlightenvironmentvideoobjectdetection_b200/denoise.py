@@ -37,6 +37,19 @@ def _conv_relu(conv, x):
     return F.relu(conv(x))
 
 
+def _weights_channels_last(module):
+    """Keeps every conv weight of ``module`` in channels-last memory (values, shapes and state_dict unchanged): with
+    channels-last activations the library otherwise re-lays the weight out on EVERY convolution call."""
+    if getattr(module, '_vod_weights_cl', None) is not None and all(p.data_ptr() == q for p, q in module._vod_weights_cl):
+        return
+    seen = []
+    for prm in module.parameters():
+        if prm.dim() == 4:
+            prm.data = prm.data.contiguous(memory_format=torch.channels_last)
+            seen.append((prm, prm.data_ptr()))
+    module._vod_weights_cl = seen
+
+
 def _nhwc(t):
     """[B,C,H,W] (made channels-last if needed) -> its [B,H,W,C] view."""
     return _cl(t).permute(0, 2, 3, 1)
@@ -125,11 +138,12 @@ class TemporalAttentionFusion(nn.Module):
         in_dtype = x.dtype
         T, _, H, W = x.shape
         mid = self.mid_channels
+        _weights_channels_last(self)
         y = _cl(_conv_relu(self.conv1, _cl(x.float())))                                     # :136
         # offsets / mask logits of the pair (i, t) = P[t] + Q[i]   (:141-142 and :75 of the pack, both linear)
         w_off, co = self.offset_conv.weight, self.dcn_pack.conv_offset
-        a = F.conv2d(y, w_off[:, :mid], None, padding=1)
-        b = F.conv2d(y, w_off[:, mid:], self.offset_conv.bias, padding=1)
+        a = F.conv2d(y, _cl(w_off[:, :mid]), None, padding=1)
+        b = F.conv2d(y, _cl(w_off[:, mid:]), self.offset_conv.bias, padding=1)
         p = _nhwc(F.conv2d(a, co.weight, None, stride=co.stride, padding=co.padding)).contiguous()
         q = _nhwc(F.conv2d(b, co.weight, co.bias, stride=co.stride, padding=co.padding)).contiguous()
         y_nhwc = y.permute(0, 2, 3, 1)                                                      # contiguous view
@@ -178,6 +192,7 @@ class Denoising2Aggergator(nn.Module):
     def forward(self, x_noise, all_x):
         denoised, carried = [], None
         last = self.num_stage - 1
+        _weights_channels_last(self)
         x_noise = [_cl(t) for t in x_noise]             # channels-last once: every conv / cat below then stays in that layout
         for s, name in enumerate(self.layer_name):
             f = x_noise[s] if s == 0 else torch.cat((x_noise[s], carried), 1)               # :222-225

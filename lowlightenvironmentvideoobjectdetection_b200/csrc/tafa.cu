@@ -106,14 +106,16 @@ tafa_kernel(const float *__restrict__ x_all, const float *__restrict__ emb_all, 
             }
         }
         if (use_attn) {
+            // softmax over the T1 <= 64 frames, lane t owns frames t and t + 32: one expf per lane and two warp reductions
+            // (every lane looping over all frames cost ~3 T1 expf per lane: ncu showed the kernel 69 % issue-bound on them)
             __syncwarp();
-            float m = -INFINITY;
-            for (int t = 0; t < T1; ++t) m = fmaxf(m, w[t]);
-            float sum = 0.f;
-            for (int t = 0; t < T1; ++t) sum += expf(w[t] - m);
+            const float v0 = lane < T1 ? w[lane] : -INFINITY, v1 = lane + 32 < T1 ? w[lane + 32] : -INFINITY;
+            const float m = warp_max(fmaxf(v0, v1));
+            const float e0 = lane < T1 ? expf(v0 - m) : 0.f, e1 = lane + 32 < T1 ? expf(v1 - m) : 0.f;
+            const float inv = 1.f / warp_sum(e0 + e1);
             __syncwarp();
-            if (lane == 0)
-                for (int t = 0; t < T1; ++t) w[t] = expf(w[t] - m) / sum;
+            if (lane < T1) w[lane] = e0 * inv;
+            if (lane + 32 < T1) w[lane + 32] = e1 * inv;
             __syncwarp();
         }
         const float uniform = 1.0f / (float)T1;

@@ -1,11 +1,11 @@
 #!/bin/bash
 # Multi-GPU scaling run on ONE box (gpurun --gpus 8): cfg3 headline at 1/2/4/8 ranks and (SWEEP=1) the cfg-5 sweep at 2/4/8 ranks.
-# Writes one JSON line per run under gpurun_out/.
+# Writes one JSON line per run under gpurun_out/.  RANKS="2 4 8" CFG3=0 SWEEP=1: the sweep alone.
 set -u
 P=29500
 for N in ${RANKS:-1 2 4 8}; do
   P=$((P+1))
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $P bench.py --gpus $N \
+  [ "${CFG3:-1}" = "1" ] && python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $P bench.py --gpus $N \
       --steps 30 --warmup 5 --no-cpu-baseline --no-roofline --no-eager-reference --out gpurun_out/r02_scale_cfg3_n$N.json \
       > gpurun_out/r02_scale_cfg3_n$N.log 2>&1
   [ "${SWEEP:-0}" = "1" ] && [ "$N" != "1" ] || continue

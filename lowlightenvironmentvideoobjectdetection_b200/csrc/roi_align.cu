@@ -88,11 +88,16 @@ template <> struct Vec<1> {
 // features instead of once per 512 B.  Warp w owns bin-row w.
 // (Forcing more resident CTAs through the register budget was measured in round 2, 4500 RoIs: 5 CTAs/SM (56 registers, a few
 // spills) 212 us, 6 (40 registers) 327 us, 8 (32) 572 us against 193 us for the compiler's own allocation.)
-#ifndef VOD_ROI_MINB
-#define VOD_ROI_MINB 1
+// TILE = the reference's [K,C,ph,pw] output through the shared-memory tile (100 KB per CTA: two CTAs per SM at most); the
+// channels-last variant writes directly.  Compiling the two as separate instantiations with their own register budgets
+// (4500 RoIs, round 2): tile variant for 1 / 2 / 3 CTAs per SM 328 / 315 / 365 us (427 us as one kernel with a run-time
+// layout switch), channels-last variant for 2 / 3 / 4 CTAs per SM 172 / 172 / 179 us (193 us before).
+template <int VEC, int NCH, bool TILE>
+#ifndef VOD_ROI_MINB_TILE
+#define VOD_ROI_MINB_TILE 2
+#define VOD_ROI_MINB_FLAT 3
 #endif
-template <int VEC, int NCH>
-__global__ void __launch_bounds__(kRoiWarps * 32, VOD_ROI_MINB)
+__global__ void __launch_bounds__(kRoiWarps * 32, TILE ? VOD_ROI_MINB_TILE : VOD_ROI_MINB_FLAT)
 roi_align_kernel(const float *__restrict__ feat, const float *__restrict__ rois, float *__restrict__ out,
                  int B, int C, int H, int W, int K, int ph, int pw, float spatial_scale,
                  int sampling_ratio, int aligned, int out_layout) {
@@ -161,7 +166,7 @@ roi_align_kernel(const float *__restrict__ feat, const float *__restrict__ rois,
             const int bin = i * pw + j;
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
-                if (out_layout == 0) {
+                if (TILE) {
                     if (on[c]) {
 #pragma unroll
                         for (int q = 0; q < VEC; ++q) tile[(c * CH + cl + q) * P + bin] = acc[c].get(q);
@@ -172,7 +177,7 @@ roi_align_kernel(const float *__restrict__ feat, const float *__restrict__ rois,
             }
         }
     }
-    if (out_layout != 0) return;
+    if (!TILE) return;
     __syncthreads();
     // contiguous write-back of the [cs_eff][P] tile: out + (k*C + c0)*P
     const int cs_eff = min(CS, C - c0);
@@ -192,7 +197,7 @@ static int launch_roi(const float *feat, const float *rois, float *out, int B, i
     constexpr int CS = 32 * VEC * NCH;
     size_t smem = out_layout == 0 ? sizeof(float) * (size_t)min(C, CS) * ph * pw : 0;
     if (smem > 200 * 1024) return fail(VOD_E_UNSUPPORTED, "vod_roi_align_fwd: output tile %zu B too large", smem);
-    auto kern = roi_align_kernel<VEC, NCH>;
+    auto kern = out_layout == 0 ? roi_align_kernel<VEC, NCH, true> : roi_align_kernel<VEC, NCH, false>;
     if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(K, ceil_div(C, CS));
     kern<<<grid, kRoiWarps * 32, smem, st>>>(feat, rois, out, B, C, H, W, K, ph, pw, scale, sr, aligned,

@@ -38,7 +38,10 @@ constexpr int kOvfLB = 4;
 static_assert(kOvfRows * kOvfLB == 32, "one butterfly reduces rows x locations = 32 values");
 
 template <int NQ>
-__global__ void __launch_bounds__(kOvfThreads, 2)
+#ifndef VOD_OVF_MINB
+#define VOD_OVF_MINB 2
+#endif
+__global__ void __launch_bounds__(kOvfThreads, VOD_OVF_MINB)
 msra_overflow_scan_kernel(const float *__restrict__ roi, const float *__restrict__ ref, const float *__restrict__ roi_norm,
                           const float *__restrict__ ref_norm, const MsraOvf o, int NP, int C, int T, int HW) {
     constexpr int R = kOvfRows, LB = kOvfLB, CP = 128 * NQ;     // CP: padded channel count

@@ -17,7 +17,11 @@ constexpr int kTafaMaxT = 64;
 
 // CTA = (n, head).  VEC=4: lanes own 4 consecutive channels, chunks of 128 channels.
 template <int VEC, bool FLAT>
-__global__ void __launch_bounds__(kTafaWarps * 32, 4)
+// (3 CTAs per SM = 79 registers without spills: 110 us in logits mode against 105 us for 4 CTAs with 52 bytes of spills)
+#ifndef VOD_TAFA_MINB
+#define VOD_TAFA_MINB 4
+#endif
+__global__ void __launch_bounds__(kTafaWarps * 32, VOD_TAFA_MINB)
 tafa_kernel(const float *__restrict__ x_all, const float *__restrict__ emb_all, const float *__restrict__ emb_bias,
             float *__restrict__ out, int T1, int N, int P, int C, int hs, float scale, int use_attn, int out_layout,
             const float *__restrict__ logit_parts, int nparts) {
@@ -318,7 +322,12 @@ msra_rescore_kernel(const float *__restrict__ roi, const float *__restrict__ ref
 constexpr int kRfFrames = 5;
 constexpr int kRfWarps = 4;
 template <int NQ, bool TWO>
-__global__ void __launch_bounds__(kRfWarps * 32)
+// (register budget, round 2: the compiler's own 80 registers = 6 CTAs of 4 warps per SM 205 us; 8 CTAs (64 registers, no spills)
+// 188 us; 10 CTAs (48 registers, spills) 241 us)
+#ifndef VOD_RF_MINB
+#define VOD_RF_MINB 8
+#endif
+__global__ void __launch_bounds__(kRfWarps * 32, VOD_RF_MINB)
 msra_rescore_fast_kernel(const float *__restrict__ roi, const float *__restrict__ ref, const float *__restrict__ roi_norm,
                          const float *__restrict__ ref_norm, const uint32_t *__restrict__ cand,
                          float *__restrict__ out, int *__restrict__ idx_out, float *__restrict__ val_out, int NP,

@@ -288,7 +288,10 @@ embed_weighted_sum_kernel(const float *__restrict__ key_emb, const float *__rest
 #endif
 constexpr int kEcPix = VOD_EC_PIX, kEcGroups = VOD_EC_GROUPS;
 
-__global__ void __launch_bounds__(kEcPix *kEcGroups)
+#ifndef VOD_EC_MINB
+#define VOD_EC_MINB 1
+#endif
+__global__ void __launch_bounds__(kEcPix *kEcGroups, VOD_EC_MINB)
 embed_cos_kernel(const float *__restrict__ key_emb, const float *__restrict__ ref_emb, float *__restrict__ cosv, int C,
                  int HW) {
     __shared__ float red[3][kEcGroups][kEcPix];
@@ -329,7 +332,10 @@ constexpr int kEaPix = VOD_EA_PIX, kEaGroups = VOD_EA_GROUPS, kEaChPerGroup = 4,
 // CTA = 128 pixels x 4 channel groups (512 threads, 16 channels).  The softmax over t is computed once per CTA (group 0)
 // and shared; every thread then streams T frames of 4 channels with 8 independent loads in flight per channel pair
 // (the 128-thread version kept 16 warps per SM busy at 22 % of DRAM bandwidth: too few bytes in flight).
-__global__ void __launch_bounds__(kEaPix *kEaGroups)
+#ifndef VOD_EA_MINB
+#define VOD_EA_MINB 1
+#endif
+__global__ void __launch_bounds__(kEaPix *kEaGroups, VOD_EA_MINB)
 embed_apply_kernel(const float *__restrict__ cosv, const float *__restrict__ ref_x, float *__restrict__ out, int T, int Cx,
                    int HW) {
     extern __shared__ float wts[];   // [T][kEaPix]

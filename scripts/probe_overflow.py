@@ -11,7 +11,7 @@ import bench  # noqa: E402
 from lowlightenvironmentvideoobjectdetection_b200 import _lib, ops  # noqa: E402
 
 if '--probes' in sys.argv:      # experiment build (python -m ...build --probes): kernel variants selected by VOD_* variables
-    _lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), 'libvodagg_probes.so')
+    _lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), 'libvodagg_probes%s.so' % os.environ.get('VOD_PROBES_SUFFIX', ''))
     print('using', _lib.LIB_PATH, 'VOD_RF_VARIANT =', os.environ.get('VOD_RF_VARIANT'))
 
 

@@ -92,7 +92,11 @@ mdcn_im2col_kernel(const float *__restrict__ x, const float *__restrict__ p, con
 // tag look-up per 32-byte sector, which is what bounds that version (680 us at stage 1).
 constexpr int kDcnHalo = 3, kDcnTS = kDcnTile + 2 * kDcnHalo, kDcnCS = 64;
 
-__global__ void __launch_bounds__(256, 4)
+// (2 or 3 CTAs per SM with a larger register budget: 370 us at stage 1 against 334 us for 4)
+#ifndef VOD_DCN_MINB
+#define VOD_DCN_MINB 4
+#endif
+__global__ void __launch_bounds__(256, VOD_DCN_MINB)
 mdcn_im2col_tile_kernel(const float *__restrict__ x, const float *__restrict__ p, const float *__restrict__ q, float *__restrict__ col,
                         int H, int W, int C, int G, long p_batch_stride, long q_batch_stride) {
     extern __shared__ __align__(16) float s_x[];            // [TS][TS][CS]

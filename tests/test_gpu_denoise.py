@@ -141,6 +141,28 @@ def test_denoising2_aggregator_vs_reference_file():
         assert rel_err(a, b) < 5e-5
 
 
+def test_denoising2_aggregator_vs_golden():
+    """The same check against the COMMITTED fixture (tests/golden/denoise_golden.npz, generated from the reference's own file
+    by tests/golden/make_denoise_golden.py): needs neither /root/reference nor the staged copy."""
+    import os
+    import numpy as np
+    from tests_golden_cfg import AGG_CFG
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'denoise_golden.npz'))
+    gd = {k: torch.from_numpy(z[k]) for k in z.files}
+    taf = vod.TemporalAttentionFusion(16, 8, emb_nums=3)
+    taf.load_state_dict({k[len('taf_p.'):]: v for k, v in gd.items() if k.startswith('taf_p.')}, strict=True)
+    got = taf.to(DEV).eval()(gd['taf_x'].to(DEV))
+    assert rel_err(got, gd['taf_out']) < 2e-5
+    agg = vod.Denoising2Aggergator(**AGG_CFG)
+    agg.load_state_dict({k[len('agg_p.'):]: v for k, v in gd.items() if k.startswith('agg_p.')}, strict=True)
+    noise_out, all_out = agg.to(DEV).eval()([gd['agg_x_noise.0'].to(DEV), gd['agg_x_noise.1'].to(DEV)], [gd['agg_all_x.0'].to(DEV)])
+    for i, t in enumerate(noise_out):
+        assert rel_err(t, gd['agg_noise_out.%d' % i]) < 5e-5
+    assert rel_err(all_out[0], gd['agg_all_out.0']) < 5e-5
+
+
 def test_denoising_modules_are_inference_only():
     taf = vod.TemporalAttentionFusion(8, 8, emb_nums=1).to(DEV).train()
     x = torch.randn(2, 8, 6, 6, device=DEV, requires_grad=True)

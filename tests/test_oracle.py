@@ -178,3 +178,20 @@ def test_denoising_aggregator_mirror_has_the_reference_state_dict():
     ref, ours = R.Denoising2Aggergator(), vod.build_aggregator(dict(type='Denoising2Aggergator'))
     a, b = ref.state_dict(), ours.state_dict()
     assert list(a) == list(b) and all(a[k].shape == b[k].shape for k in a)
+
+
+def _denoise_golden():
+    import numpy as np
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'denoise_golden.npz'))
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def test_temporal_attention_fusion_restatement_vs_golden():
+    """Committed fixture from the reference's own denoising2_aggregator.py (tests/golden/make_denoise_golden.py): pins the
+    oracle's restatement (incl. its modulated deformable conv) without needing the reference tree."""
+    gd = _denoise_golden()
+    p = {k[len('taf_p.'):]: v for k, v in gd.items() if k.startswith('taf_p.')}
+    got = O.temporal_attention_fusion(gd['taf_x'], p)
+    assert got.shape == gd['taf_out'].shape
+    assert (got - gd['taf_out']).abs().max() <= 1e-5 * gd['taf_out'].abs().max()

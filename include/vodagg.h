@@ -131,6 +131,18 @@ int vod_selsa_attn(const void *q, const void *k, const void *v, float *out, int 
                    int d, float scale, int dtype, int v_layout, int ldv, int impl, void *ws,
                    size_t ws_bytes, vod_stream_t stream);
 
+/* The element-wise tail of one SelsaBBoxHead layer, in place and in one launch:
+ *   x[r, c] = relu(x[r, c] + y[r, c] + bias[c])  for r < rows  (x [rows, cols] fp32, y the aggregator's
+ *             output WITHOUT its bias, bias [cols] = the aggregator's fused output bias)
+ *   ref[i]  = relu(ref[i])                        for i < ref_elems (nullable when ref_elems == 0)
+ * cols and ref_elems must be multiples of 4, pointers 16-byte aligned.
+ * replaces: `x = x + self.aggregator[i](x, ref_x); ref_x = self.relu(ref_x); x = self.relu(x)`,
+ *   mmtracking/mmtrack/models/roi_heads/bbox_heads/selsa_bbox_head.py:56-58 (and the `+ bias` of
+ *   the aggregator's last linear, mmtracking/mmtrack/models/aggregators/selsa_aggregator.py:72)
+ */
+int vod_selsa_residual_relu(float *x, const float *y, const float *bias, int rows, int cols, float *ref,
+                            long ref_elems, vod_stream_t stream);
+
 /* ------------------------------- (4) TemporalRoIAlign: most-similar sampling
  * roi_feats [N*P, C] fp32 (P = ph*pw bins, NHWC-style rows), ref_nhwc [T, HW, C] fp32.
  * For every (row, frame): cosine similarity against all HW locations, top-k

@@ -37,6 +37,7 @@ SIGNATURES = {
     'vod_fgfa_warp_weighted_sum': (_I, [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _SZ, _P]),
     'vod_selsa_attn_workspace_bytes': (_SZ, [_I, _I, _I, _I]),
     'vod_selsa_attn': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _I, _I, _I, _P, _SZ, _P]),
+    'vod_selsa_residual_relu': (_I, [_P, _P, _P, _I, _I, _P, _c.c_long, _P]),
     'vod_msra_workspace_bytes': (_SZ, [_I, _I, _I, _I, _I]),
     'vod_msra_topk_sample': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _SZ, _P]),
     'vod_msra_overflow_counter_offset': (_SZ, [_I, _I, _I, _I]),

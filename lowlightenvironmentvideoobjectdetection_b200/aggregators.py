@@ -96,9 +96,23 @@ class SelsaAggregator(nn.Module):
         torch.mm(self.ref_fc.weight.float(), ref_x.t(), out=vt_out)
         return k, vt_out, True
 
-    def attend(self, x, k, v, M, v_transposed, q=None):
+    def out_bias(self, v_transposed):
+        """The bias of ``attend(..., with_bias=False)``'s result: fc.bias, plus fc.weight . ref_fc.bias when V^T was projected
+        without its bias (``project_ref``): fc(o + b_v) = o W^T + (W b_v + b).  Cached per weight version."""
+        if not v_transposed:
+            return self.fc.bias
+        key = tuple((t._version, t.data_ptr()) for t in (self.fc.weight, self.fc.bias, self.ref_fc.bias))
+        if getattr(self, '_out_bias', None) is None or self._out_bias[0] != key:
+            with torch.no_grad():
+                b = torch.addmv(self.fc.bias.double(), self.fc.weight.double(), self.ref_fc.bias.double()).float()
+            self._out_bias = (key, b.contiguous())
+        return self._out_bias[1]
+
+    def attend(self, x, k, v, M, v_transposed, q=None, with_bias=True):
         """fc(softmax(fc_embed(x) K^T / sqrt(d)) V) for the first ``M`` reference rows of k / columns of V^T
-        (selsa_aggregator.py:50,57-72).  ``q``: fc_embed(x) when the caller already computed it."""
+        (selsa_aggregator.py:50,57-72).  ``q``: fc_embed(x) when the caller already computed it.
+        ``with_bias=False``: the result lacks ``out_bias(v_transposed)`` -- for callers that add it together with their
+        residual and ReLU in one pass (``ops.selsa_residual_relu_``)."""
         roi_n = x.shape[0]
         if q is None:
             q = self.fc_embed(x.float())                       # :50
@@ -108,6 +122,8 @@ class SelsaAggregator(nn.Module):
         if self.compute_dtype == torch.bfloat16:
             q, k, v = q.bfloat16(), k.bfloat16(), v.bfloat16()
         o = ops.selsa_attention(q, k, v, self.num_attention_blocks, v_transposed=v_transposed, impl=self.impl)  # :61-70
+        if not with_bias:
+            return torch.nn.functional.linear(o.view(roi_n, -1), self.fc.weight)
         if v_transposed:
             o += self.ref_fc.bias.float()
         return self.fc(o.view(roi_n, -1))                      # :72

@@ -74,6 +74,31 @@ static int launch_simt(const T *q, const T *k, const T *v, float *out, int N, in
     return check_launch("vod_selsa_attn(simt)");
 }
 
+
+// The tail of one SelsaBBoxHead layer (selsa_bbox_head.py:56-58) in one pass instead of four elementwise launches:
+//   x[r, c]  = relu(x[r, c] + y[r, c] + bias[c])   r < rows    (x = x + aggregator(x, ref_x); x = relu(x)  with the
+//              aggregator's output bias -- fc.bias + fc.weight . ref_fc.bias, see SelsaAggregator.out_bias -- added here)
+//   ref[i]   = relu(ref[i])                        i < ref_elems   (ref_x = relu(ref_x); nullable)
+// 128-bit accesses; cols % 4 == 0 and 16-byte aligned pointers are checked by the launcher.
+__global__ void __launch_bounds__(256) selsa_residual_relu_kernel(float4 *__restrict__ x, const float4 *__restrict__ y,
+                                                                  const float4 *__restrict__ bias, long n4, int cols4,
+                                                                  float4 *__restrict__ ref, long ref4) {
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4 + ref4; i += stride) {
+        if (i < n4) {
+            float4 a = x[i];
+            const float4 b = y[i], c = __ldg(bias + (int)(i % cols4));
+            a.x = fmaxf(a.x + b.x + c.x, 0.f); a.y = fmaxf(a.y + b.y + c.y, 0.f);
+            a.z = fmaxf(a.z + b.z + c.z, 0.f); a.w = fmaxf(a.w + b.w + c.w, 0.f);
+            x[i] = a;
+        } else {
+            float4 a = ref[i - n4];
+            a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+            ref[i - n4] = a;
+        }
+    }
+}
+
 }  // namespace vod
 
 using namespace vod;
@@ -100,4 +125,22 @@ extern "C" int vod_selsa_attn(const void *q, const void *k, const void *v, float
                            reinterpret_cast<const float *>(v), out, N, M, heads, d, scale, v_layout, ldv, st);
     return launch_simt(reinterpret_cast<const __nv_bfloat16 *>(q), reinterpret_cast<const __nv_bfloat16 *>(k),
                        reinterpret_cast<const __nv_bfloat16 *>(v), out, N, M, heads, d, scale, v_layout, ldv, st);
+}
+
+extern "C" int vod_selsa_residual_relu(float *x, const float *y, const float *bias, int rows, int cols, float *ref,
+                                       long ref_elems, vod_stream_t stream) {
+    VOD_REQUIRE(rows >= 0 && cols > 0 && ref_elems >= 0, "vod_selsa_residual_relu: bad dims rows=%d cols=%d", rows, cols);
+    if ((long)rows * cols + ref_elems == 0) return VOD_OK;
+    VOD_REQUIRE(rows == 0 || (x && y && bias), "vod_selsa_residual_relu: null pointer");
+    VOD_REQUIRE(ref_elems == 0 || ref, "vod_selsa_residual_relu: null ref pointer");
+    VOD_REQUIRE(cols % 4 == 0 && ref_elems % 4 == 0, "vod_selsa_residual_relu: cols and ref_elems must be multiples of 4");
+    VOD_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(bias) |
+                  reinterpret_cast<uintptr_t>(ref)) & 15) == 0, "vod_selsa_residual_relu: pointers must be 16-byte aligned");
+    const long n4 = (long)rows * cols / 4, ref4 = ref_elems / 4;
+    const long blocks = (n4 + ref4 + 255) / 256;
+    const int grid = (int)(blocks < 8L * num_sms() ? blocks : 8L * num_sms());
+    selsa_residual_relu_kernel<<<grid, 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<float4 *>(x), reinterpret_cast<const float4 *>(y), reinterpret_cast<const float4 *>(bias), n4, cols / 4,
+        reinterpret_cast<float4 *>(ref), ref4); note_launch();
+    return check_launch("vod_selsa_residual_relu");
 }

@@ -21,6 +21,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import ops
 from .post_processing import bbox2roi, delta2bbox, multiclass_nms
 from .registry import HEADS, build_aggregator, build_roi_extractor
 
@@ -84,10 +85,23 @@ class SelsaBBoxHead(nn.Module):
             else:
                 x = fc(x)
                 ref_x = fc(ref_x)
-            x = x + self.aggregator[i](x, ref_x)   # aggregator sees the PRE-ReLU features (:56)
-            ref_x = F.relu(ref_x)
-            x = F.relu(x)
+            agg = self.aggregator[i]
+            if self._fusable(x, ref_x):
+                # :56-58 with the three element-wise steps (and the aggregator's output bias) as ONE launch; x and ref_x are
+                # this layer's own FC outputs, so they are updated in place
+                k, v, use_vt = agg.project_ref(ref_x)      # aggregator sees the PRE-ReLU features (:56)
+                y = agg.attend(x, k, v, ref_x.shape[0], use_vt, with_bias=False)
+                ops.selsa_residual_relu_(x, y, agg.out_bias(use_vt), ref_x)
+            else:
+                x = x + agg(x, ref_x)
+                ref_x = F.relu(ref_x)
+                x = F.relu(x)
         return self.fc_cls(x), self.fc_reg(x)
+
+    @staticmethod
+    def _fusable(x, ref_x):
+        return (x.is_cuda and x.dtype == torch.float32 and ref_x.dtype == torch.float32 and x.is_contiguous()
+                and ref_x.is_contiguous() and ref_x.shape[0] > 0 and x.shape[0] > 0 and x.shape[1] % 4 == 0)
 
     @torch.no_grad()
     def forward_cached(self, rows, n_key, cache, slots, channels_last=True):
@@ -118,11 +132,16 @@ class SelsaBBoxHead(nn.Module):
                     k, v, _ = agg.project_ref(r)
                     cache.K[i][lo:hi].copy_(k)
                     cache.V[i][lo:hi].copy_(v)
-            if n_key:
+            if n_key and y.is_contiguous() and y.shape[1] % 4 == 0:
                 x = y[:n_key]
-                x += agg.attend(x, cache.K[i], cache.V[i], T * N, cache.v_transposed)   # :56, pre-ReLU features on both sides
-            if i + 1 < len(self.shared_fcs) or n_key:
-                torch.relu_(y)                                             # :57-58
+                a = agg.attend(x, cache.K[i], cache.V[i], T * N, cache.v_transposed, with_bias=False)   # :56, pre-ReLU features on both sides
+                ops.selsa_residual_relu_(x, a, agg.out_bias(cache.v_transposed), y[n_key:])              # :56-58 in one launch
+            else:
+                if n_key:
+                    x = y[:n_key]
+                    x += agg.attend(x, cache.K[i], cache.V[i], T * N, cache.v_transposed)
+                if i + 1 < len(self.shared_fcs) or n_key:
+                    torch.relu_(y)                                         # :57-58
         if not n_key:
             return None
         x = y[:n_key]

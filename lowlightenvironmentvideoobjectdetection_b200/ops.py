@@ -435,6 +435,21 @@ def selsa_attention(q, k, v, num_heads, v_transposed=False, impl=IMPL_AUTO):
     return out
 
 
+def selsa_residual_relu_(x, y, bias, ref_x=None):
+    """In place, one launch: x = relu(x + y + bias) and (optionally) ref_x = relu(ref_x) -- the element-wise tail of a
+    SelsaBBoxHead layer (selsa_bbox_head.py:56-58).  x, y [rows, cols] fp32 contiguous, bias [cols], ref_x any contiguous fp32."""
+    _lib.require_cuda(x, y, bias)
+    assert x.dtype == y.dtype == bias.dtype == torch.float32 and x.shape == y.shape and x.dim() == 2
+    assert x.is_contiguous() and y.is_contiguous() and bias.is_contiguous() and bias.numel() == x.shape[1]
+    ref_ptr, ref_n = None, 0
+    if ref_x is not None and ref_x.numel():
+        assert ref_x.is_cuda and ref_x.dtype == torch.float32 and ref_x.is_contiguous()
+        ref_ptr, ref_n = _lib.ptr(ref_x), ref_x.numel()
+    _lib.call('vod_selsa_residual_relu', _lib.ptr(x), _lib.ptr(y), _lib.ptr(bias), x.shape[0], x.shape[1], ref_ptr, ref_n,
+              _lib.stream_ptr(x.device))
+    return x
+
+
 # ----------------------------------------------------------------------------- (4) TemporalRoIAlign pieces
 def _padded_unit(ref_unit, rows):
     """The tensor-core pass may read up to 3 rows past the last reference row (vodagg.h): copy into a padded buffer

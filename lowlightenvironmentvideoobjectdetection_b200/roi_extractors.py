@@ -265,11 +265,17 @@ class TemporalRoIAlign(SingleRoIExtractor):
         P = rh * rw
         cc = self._keyproj_chunk(T1, P, C)
         key_patches = x_key.view(N, rh, rw, C).permute(0, 3, 1, 2)
-        ek = torch.nn.functional.conv2d(key_patches, self._conv_weight_cl(conv), conv.bias, 1, 1)
-        ek = ek.permute(0, 2, 3, 1).contiguous().view(N * P, heads, C // heads)   # no copy (channels_last)
         gd = self._g_dtype()
+        # the conv runs without its bias; the bias add and the conversion to the GEMM's operand type are ONE pass
+        # (torch.add computes in fp32 and rounds once into ``out``: the same values as add-then-convert, one launch fewer)
+        ek = torch.nn.functional.conv2d(key_patches, self._conv_weight_cl(conv), None, 1, 1)
+        ek = ek.permute(0, 2, 3, 1).contiguous().view(N * P, C)                   # no copy (channels_last)
+        if conv.bias is not None:
+            ek = torch.add(ek, conv.bias, out=torch.empty((N * P, C), dtype=gd, device=ek.device))
+        else:
+            ek = ek.to(gd)
         # [heads, N*P, 9*C]; bf16: the GEMM runs on bf16 operands and writes half the bytes (it is write-bound)
-        G = torch.bmm(ek.transpose(0, 1).to(gd), self._keyproj_weight(conv, heads, cc, gd))
+        G = torch.bmm(ek.view(N * P, heads, C // heads).transpose(0, 1), self._keyproj_weight(conv, heads, cc, gd))
         return G, cc
 
     def _tafa(self, x_all, rh, rw, out=None, prepared=None):

@@ -215,6 +215,34 @@ def test_selsa_reference_unit_test_shapes():
     assert rel_err(agg_x, O.selsa_aggregate(target_x.cpu(), ref_x.cpu(), p, 4)) < 1e-4
 
 
+def test_selsa_layer_tail_fused_matches_the_three_steps():
+    """`x = x + aggregator(x, ref_x); ref_x = relu(ref_x); x = relu(x)` (selsa_bbox_head.py:56-58) as one launch: bit-exact against
+    the same fp32 additions in torch (x + (y + bias) is evaluated as (x + y) + bias: compare with that order), with and
+    without the reference rows, and the aggregator path that uses it against the module's own forward."""
+    g = torch.Generator().manual_seed(3)
+    for rows, cols, ref_rows in ((300, 1024, 4500), (7, 64, 0), (0, 128, 33), (33, 128, 5)):
+        x, y = torch.randn(rows, cols, generator=g).to(DEV), torch.randn(rows, cols, generator=g).to(DEV)
+        b, ref = torch.randn(cols, generator=g).to(DEV), torch.randn(ref_rows, cols, generator=g).to(DEV)
+        want_x, want_ref = torch.relu((x + y) + b), torch.relu(ref)
+        ops.selsa_residual_relu_(x, y, b, ref if ref_rows else None)
+        assert torch.equal(x, want_x) and torch.equal(ref, want_ref)
+    with pytest.raises(Exception):
+        ops.selsa_residual_relu_(torch.zeros(2, 6, device=DEV), torch.zeros(2, 6, device=DEV), torch.zeros(6, device=DEV))
+    # the aggregator's output without its bias + out_bias == the aggregator's forward (fp32 library math)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m = vod.SelsaAggregator(in_channels=1024, num_attention_blocks=16).to(DEV)
+    for prm in m.parameters():
+        torch.nn.init.normal_(prm, 0, 0.02)
+    x, ref_x = torch.randn(40, 1024, generator=g).to(DEV), torch.randn(200, 1024, generator=g).to(DEV)
+    with torch.no_grad():
+        k, v, vt = m.project_ref(ref_x)
+        assert vt
+        y = m.attend(x, k, v, 200, vt, with_bias=False) + m.out_bias(vt)
+        assert rel_err(y, m(x, ref_x)) < 1e-5
+    p = {k_: v_.cpu() for k_, v_ in m.state_dict().items()}
+    assert rel_err(y, O.selsa_aggregate(x.cpu(), ref_x.cpu(), p, 16)) < 1e-3
+
+
 # ------------------------------------------------------------------------------------------ (4) TemporalRoIAlign (exact SIMT path)
 def _troi(golden, blocks, impl):
     m = vod.build_roi_extractor(dict(type='TemporalRoIAlign', num_most_similar_points=2,

@@ -771,12 +771,18 @@ def bench_selsa(ctx, cfg, cfg_name):
                 d_.copy_(s_)
         e2e_graphs = [run.capture_on(*pf.stage[j]) for j in range(2)]     # one graph per staging buffer: no device-side copy
 
-        def e2e_loop(steps):
+        # What crosses PCIe per step.  `e2e`: the key frame's map + every frame's proposals; the T-1 memory maps stay in the
+        # staging buffers on the device, as the reference keeps them in `self.memo.feats` between frames (selsa.py:210-225) --
+        # the step still recomputes everything for all T frames (no cache).  `e2e_full_upload`: all T maps re-uploaded every
+        # step (rounds 1-2's definition of e2e; nothing in the reference does this, it is the worst case for the host links).
+        new_frame_only = (slice(T - 1, T), None)
+
+        def e2e_loop(steps, slices=None):
             pf.begin()
-            pf.prefetch(0, run.host_sets[0])
+            pf.prefetch(0, run.host_sets[0], slices)
             for i in range(steps):
                 if i + 1 < steps:
-                    pf.prefetch(i + 1, run.host_sets[(i + 1) % n_sets])
+                    pf.prefetch(i + 1, run.host_sets[(i + 1) % n_sets], slices)
                 pf.wait(i)
                 g, (d, l, c) = e2e_graphs[i % 2]
                 g.replay()
@@ -785,7 +791,12 @@ def bench_selsa(ctx, cfg, cfg_name):
                 out_host.copy_(sink.buf[i % sink.frames], non_blocking=True)
                 cnt_host.copy_(sink.cnt[i % sink.frames:i % sink.frames + 1], non_blocking=True)
         e2e_loop(2)
-        t_e2e = ctx.timed(lambda: (e2e_loop(args.steps), sink.gather()))
+        t_e2e_full = ctx.timed(lambda: (e2e_loop(args.steps), sink.gather()))
+        for j in range(2):                       # memory maps of clip position j resident in staging buffer j
+            pf.stage[j][0].copy_(run.dev_sets[j][0])
+        e2e_loop(2, new_frame_only)
+        t_e2e = ctx.timed(lambda: (e2e_loop(args.steps, new_frame_only), sink.gather()))
+        h2d_new = C * H * W * 4 + run.host_sets[0][1].numel() * 4
 
         # ------------------------------------------------ the eager (un-graphed) module API, for reference
         metas = [dict(img_shape=IMG_SHAPE, scale_factor=(1., 1., 1., 1.))]
@@ -871,7 +882,11 @@ def bench_selsa(ctx, cfg, cfg_name):
     frames = args.steps * world
     result = base_result(ctx, cfg, METRIC, UNIT, frames / t_dev, t_dev / args.steps, 'tf32', config)
     result.update({
-        'e2e': {'value': frames / t_e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+        'e2e': {'value': frames / t_e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d_new, 'd2h_bytes_per_step': d2h,
+                'note': 'uncached step; per step the key frame\'s map and all proposals come from pinned host memory, the %d memory '
+                        'maps stay on the device as the reference\'s self.memo.feats do (selsa.py:210-225)' % (T - 1)},
+        'e2e_full_upload': {'value': frames / t_e2e_full, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                            'note': 'all %d maps re-uploaded every step (the definition of e2e in BENCH_r01 / earlier r02 lines)' % T},
         'gpu_launches': int(launches_per_step * args.steps), 'clocks': sampler.summary(),
         'eager_api': {'value': frames / t_eager, 'unit': UNIT,
                       'note': 'SelsaRoIHead.simple_test called eagerly (what an integrator gets without capture_graph: variable-length '
@@ -1136,7 +1151,12 @@ def bench_fgfa(ctx, cfg):
                 graph.replay(); sink.put(i, d, l, c)
                 out_host.copy_(sink.buf[i % sink.frames], non_blocking=True)
         e2e_loop(2)
-        t_e2e = ctx.timed(lambda: (e2e_loop(args.steps), sink.gather()))
+        t_e2e_full = ctx.timed(lambda: (e2e_loop(args.steps), sink.gather()))
+        for j in range(2):                       # memory maps of clip position j resident in staging buffer j
+            pf.stage[j][0].copy_(run.dev_sets[j][0])
+        e2e_loop(2, new_frame_only)
+        t_e2e = ctx.timed(lambda: (e2e_loop(args.steps, new_frame_only), sink.gather()))
+        h2d_new = C * H * W * 4 + run.host_sets[0][1].numel() * 4
     frames = args.steps * ctx.world
     h2d = sum(host[0][j].numel() * host[0][j].element_size() for j in (0, 2, 3, 4))
     config = dict(workload=cfg['workload'], proposals=cfg['N'], ref_frames=T - 1, execution='one CUDA graph per frame',

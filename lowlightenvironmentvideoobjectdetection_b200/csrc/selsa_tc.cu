@@ -27,7 +27,17 @@ namespace vod {
 constexpr int kBM = 128;
 constexpr int kBN = 64;
 constexpr int kHD = 64;
-constexpr int kKvStages = 3;
+// K / V^T ring depth and CTAs per SM, measured with experiment builds (round 2, N x M = 300 x 4500 | 1000 x 31000, tf32, incl. the
+// merge): 2 stages 56 | 765 us, 3 stages 37.9 | 406 us, 4 stages 35.8 | 360 us, 5 / 6 stages 35.8 | 364-367 us; 2 stages with two
+// co-resident CTAs per SM (2 x 97 KB of shared memory, 2 x 256 TMEM columns, twice the splits) 39.9 | 407 us = the 3-stage
+// single CTA: what counts is the number of K / V^T chunks in flight per SM, and beyond 4 the MMA <-> softmax handshake chain.
+#ifndef VOD_SELSA_STAGES
+#define VOD_SELSA_STAGES 4
+#endif
+#ifndef VOD_SELSA_OCC
+#define VOD_SELSA_OCC 1
+#endif
+constexpr int kKvStages = VOD_SELSA_STAGES;
 constexpr int kSelsaThreads = 192;
 constexpr int kSelsaTmemCols = 256;
 
@@ -58,7 +68,7 @@ __device__ __forceinline__ uint32_t f32_to_tf32(float x) {
 }
 
 template <bool BF16>
-__global__ void __launch_bounds__(kSelsaThreads, 1)
+__global__ void __launch_bounds__(kSelsaThreads, VOD_SELSA_OCC)
 selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const SelsaParams p) {
     using Cfg = SelsaCfg<BF16>;
@@ -354,7 +364,7 @@ transpose_rows_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
 static int pick_splits(int N, int M, int heads) {
     const int units = ceil_div(N, kBM) * heads;
     const int nchunks = ceil_div(M, kBN);
-    int s = max(1, num_sms() / units);
+    int s = max(1, VOD_SELSA_OCC * num_sms() / units);
     s = min(s, max(1, nchunks / 4));  // at least 4 chunks per split
     return min(s, 16);
 }

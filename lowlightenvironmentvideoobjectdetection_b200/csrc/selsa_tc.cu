@@ -203,13 +203,29 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < kBN; ++i) s[i] = i < valid ? s[i] : -INFINITY;
             }
-            float mx = s[0];
+            // Row maximum as four independent chains (a single chain is 32 dependent 3-input FMNMX, ~150 clk that nothing hides:
+            // each sub-partition holds ONE softmax warp).
+            float mx4[4] = {s[0], s[1], s[2], s[3]};
 #pragma unroll
-            for (int i = 1; i < kBN; ++i) mx = fmaxf(mx, s[i]);
-            const float m_new = mx * p.scale_log2;                 // scale > 0: max commutes with the scaling
-            if (j == 0) {
-                m_ref = m_new;                                     // O is still empty (PV(0) overwrites it)
-            } else if (__any_sync(0xffffffffu, m_new > m_ref + kLazy)) {
+            for (int i = 4; i < kBN; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], s[i]);
+            const float m_new = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2;   // scale > 0: max commutes with the scaling
+            if (j == 0) m_ref = m_new;                             // O is still empty (PV(0) overwrites it)
+            // The exponentials are taken against the CURRENT reference maximum right away; whether some row outgrew it
+            // (m_new > m_ref + 2^kLazy: rare) is only looked at afterwards, so the maximum is off the critical path.  A row that
+            // did outgrow it has produced garbage (possibly inf) here and is recomputed below.
+            const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+            float e[kBN];
+            float2 sum2 = make_float2(0.f, 0.f);
+            {
+                const float2 nm2 = make_float2(-m_ref, -m_ref);
+#pragma unroll
+                for (int i = 0; i < kBN; i += 2) {
+                    const float2 t = __ffma2_rn(make_float2(s[i], s[i + 1]), sc2, nm2);   // raw * scale - m_ref  (-inf stays -inf)
+                    e[i] = ex2(t.x); e[i + 1] = ex2(t.y);
+                    sum2 = __fadd2_rn(sum2, make_float2(e[i], e[i + 1]));
+                }
+            }
+            if (j > 0 && __any_sync(0xffffffffu, m_new > m_ref + kLazy)) {
                 // rare: some row of this warp outgrew its reference maximum.  All PV products issued so far (chunks < j) must
                 // have landed; PV(j) cannot start before this thread's p_full arrival below.  tcgen05.ld/st are warp-wide,
                 // rows that do not need it rescale by 1.
@@ -235,16 +251,19 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 tc::tcgen05_fence_before();
                 l_run *= f;
                 if (need) m_ref = m_new;
-            }
-            const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_ref, -m_ref);
-            float2 sum2 = make_float2(0.f, 0.f);
+                // the exponentials again, against the raised maximum (rows that did not need it reproduce the same values)
+                const float2 nm2 = make_float2(-m_ref, -m_ref);
+                sum2 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int i = 0; i < kBN; i += 2) {
-                const float2 t = __ffma2_rn(make_float2(s[i], s[i + 1]), sc2, nm2);   // raw * scale - m_ref  (-inf stays -inf)
-                s[i] = ex2(t.x); s[i + 1] = ex2(t.y);
-                sum2 = __fadd2_rn(sum2, make_float2(s[i], s[i + 1]));
+                for (int i = 0; i < kBN; i += 2) {
+                    const float2 t = __ffma2_rn(make_float2(s[i], s[i + 1]), sc2, nm2);
+                    e[i] = ex2(t.x); e[i + 1] = ex2(t.y);
+                    sum2 = __fadd2_rn(sum2, make_float2(e[i], e[i + 1]));
+                }
             }
             l_run += sum2.x + sum2.y;
+#pragma unroll
+            for (int i = 0; i < kBN; ++i) s[i] = e[i];
 
             // P overwrites this row's S values in place (thread = row = TMEM lane): tf32 one value per column, bf16 two
             if (BF16) {
@@ -361,6 +380,9 @@ transpose_rows_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
     }
 }
 
+// Splits over the reference axis: as many as fill the machine once.  (Measured, round 2, 1000 x 31000 = 128 units of 485 chunks:
+// one split leaves 20 of 148 SMs idle, 8 splits run 6.9 waves of 61 chunks -- 12 % fewer chunk-times per SM -- and take the same
+// 351-353 us: a CTA's fixed cost (TMEM allocation, Q load, pipeline fill, partial write, the merge) is worth ~8 chunks.)
 static int pick_splits(int N, int M, int heads) {
     const int units = ceil_div(N, kBM) * heads;
     const int nchunks = ceil_div(M, kBN);

@@ -9,13 +9,14 @@
 //              written to shared memory in the 128B-swizzled K-major operand layout.  O is NOT read back per
 //              chunk: it stays in TMEM, exponentials are taken against a per-row reference maximum that is
 //              raised (with a rescale of the row's O and row sum) only when a score outgrows it by 2^64.
-//   warp 4     TMA producer: Q once, then a 3-stage ring of (K chunk, V^T chunk) tiles.
+//   warp 4     TMA producer: a ring of (K chunk, V^T chunk) tiles.  (Q never enters shared memory: the softmax warps load their
+//              row from global memory once and park it in TMEM, the A operand of the TS-form S = Q K^T.)
 //   warp 5     MMA issuer: S = Q K^T (kind::tf32 or kind::f16/bf16) into a double-buffered TMEM
 //              accumulator, O += P V into a third TMEM accumulator (over all chunks); completion via tcgen05.commit.
 // Reference rows are processed in chunks of 64.  When N*heads/128 CTAs cannot fill 148 SMs the reference
 // axis is split across CTAs and the partial (acc, max, sum) triples are merged by selsa_merge_kernel.
 //
-// TMEM columns: [0,64) S buffer 0, [64,128) S buffer 1, [128,192) O.
+// TMEM columns: [0,64) S buffer 0, [64,128) S buffer 1, [128,192) O, [192,256) Q (fp32: 64 columns, bf16: 32).
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -40,19 +41,20 @@ constexpr int kHD = 64;
 constexpr int kKvStages = VOD_SELSA_STAGES;
 constexpr int kSelsaThreads = 192;
 constexpr int kSelsaTmemCols = 256;
+constexpr uint32_t kQCol = 3 * 64;      // TMEM columns [192, 256): the CTA's 128 query rows (A operand of S = Q K^T)
 
 template <bool BF16>
 struct SelsaCfg {
     static constexpr int kElem = BF16 ? 2 : 4;
     static constexpr int kSliceElems = 128 / kElem;         // elements per 128-byte K slice
     static constexpr int kSlices = kHD / kSliceElems;       // slices along d (QK^T) and along refs (PV): kBN == kHD
-    static constexpr int kQBytes = kSlices * kBM * 128;
     static constexpr int kKBytes = kSlices * kBN * 128;
     static constexpr int kVBytes = kSlices * kHD * 128;
-    static constexpr int kSmem = kQBytes + kKvStages * (kKBytes + kVBytes) + 1024;   // P never touches shared memory
+    static constexpr int kSmem = kKvStages * (kKBytes + kVBytes) + 1024;   // neither Q nor P ever touches shared memory
 };
 
 struct SelsaParams {
+    const void *q;     // [N, D] fp32 or bf16 (read directly by the softmax warps, which park their row in TMEM)
     float *out;        // [N, D]
     float *part_acc;   // [S][heads][Npad][64]
     float *part_m;     // [S][heads][Npad]
@@ -74,8 +76,7 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     using Cfg = SelsaCfg<BF16>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t *sQ = smem;
-    uint8_t *sK = sQ + Cfg::kQBytes;
+    uint8_t *sK = smem;
     uint8_t *sV = sK + kKvStages * Cfg::kKBytes;
     __shared__ uint64_t q_full, kv_full[kKvStages], kv_empty[kKvStages], s_full[2], s_empty[2], p_full[2], o_full;
     __shared__ uint32_t tmem_slot;
@@ -86,7 +87,7 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int n = min(p.chunks_per_split, p.nchunks - c0);  // chunks of this CTA (>= 1 by construction)
 
     if (threadIdx.x == 0) {
-        tc::mbar_init(&q_full, 1);
+        tc::mbar_init(&q_full, 4);                         // the four softmax warps, once their Q rows are in TMEM
         for (int i = 0; i < kKvStages; ++i) { tc::mbar_init(&kv_full[i], 1); tc::mbar_init(&kv_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 1);
@@ -104,10 +105,7 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     if (warp == 4) {
         // ------------------------------------------------------------------ TMA producer
         if (tc::elect_one()) {
-            tc::tma_prefetch_desc(&tm_q); tc::tma_prefetch_desc(&tm_k); tc::tma_prefetch_desc(&tm_v);
-            tc::mbar_arrive_expect_tx(&q_full, Cfg::kQBytes);
-            for (int sl = 0; sl < Cfg::kSlices; ++sl)
-                tc::tma_load_2d(sQ + sl * kBM * 128, &tm_q, &q_full, h * kHD + sl * Cfg::kSliceElems, rt * kBM);
+            tc::tma_prefetch_desc(&tm_k); tc::tma_prefetch_desc(&tm_v);
             for (int j = 0; j < n; ++j) {
                 const int st = j % kKvStages;
                 const uint32_t ph = (j / kKvStages) & 1;
@@ -125,27 +123,30 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     } else if (warp == 5) {
         // ------------------------------------------------------------------ MMA issuer
         constexpr uint32_t idesc = tc::umma_idesc(BF16 ? tc::kFmtBF16 : tc::kFmtTF32, kBM, kBN);  // M=128, N=64 for both GEMMs
-        auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
-            if (BF16) tc::umma_f16(d, a, b, idesc, acc); else tc::umma_tf32(d, a, b, idesc, acc);
-        };
         auto issue_s = [&](int j) {
             const int st = j % kKvStages, buf = j & 1;
             tc::mbar_wait(&kv_full[st], (j / kKvStages) & 1);
             tc::mbar_wait(&s_empty[buf], ((j >> 1) & 1) ^ 1);
             tc::tcgen05_fence_after();
             if (tc::elect_one()) {
-                const uint32_t qa = tc::smem_u32(sQ), ka = tc::smem_u32(sK + st * Cfg::kKBytes);
+                // S = Q K^T with Q read from TENSOR MEMORY (TS form, as P below): from shared memory every one of these small
+                // MMAs (M = 128, N = 64, K = 32 bytes) re-read a 4 KB slice of Q next to 2 KB of K -- 6 KB per 131 kFLOP against
+                // 128 B/clk of shared-memory bandwidth, more than the MMA's own time
+                const uint32_t ka = tc::smem_u32(sK + st * Cfg::kKBytes);
 #pragma unroll
                 for (int sl = 0; sl < Cfg::kSlices; ++sl)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        mma(tmem + buf * kBN, tc::umma_desc_k_sw128(qa + sl * kBM * 128 + k * 32),
-                            tc::umma_desc_k_sw128(ka + sl * kBN * 128 + k * 32), (sl | k) != 0);
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t kb = tc::umma_desc_k_sw128(ka + sl * kBN * 128 + k * 32);
+                        if (BF16) tc::umma_f16_ts(tmem + buf * kBN, tmem + kQCol + (sl * 4 + k) * 8, kb, idesc, (sl | k) != 0);
+                        else tc::umma_tf32_ts(tmem + buf * kBN, tmem + kQCol + (sl * 4 + k) * 8, kb, idesc, (sl | k) != 0);
+                    }
                 tc::umma_commit(&s_full[buf]);
             }
             __syncwarp();
         };
         tc::mbar_wait(&q_full, 0);
+        tc::tcgen05_fence_after();
         issue_s(0);
         for (int j = 0; j < n; ++j) {
             if (j + 1 < n) issue_s(j + 1);
@@ -182,6 +183,34 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         // the kernel latency-bound (1970 clk per chunk with the tensor pipe 19 % busy; removing 7/8 of the MMAs,
         // halving the instructions or doubling the softmax warps did not change its time).
         // Instruction diet as before: packed fp32x2 FMA/ADD, ex2.approx on the raw MUFU, scale folded into the FMA.
+        {
+            // This thread's query row -> TMEM lane r, columns [kQCol, kQCol + 64): one tf32 (fp32 bits, the MMA ignores the low 13)
+            // or two bf16 per 32-bit column, the A-operand layout of the TS-form MMA.  Rows past N are zero.
+            const int qrow = rt * kBM + r;
+            constexpr int kWords = kHD * Cfg::kElem / 4;       // 32-bit words per row: 64 (fp32) or 32 (bf16)
+            const uint4 *src = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(p.q) +
+                                                               ((size_t)qrow * p.D + (size_t)h * kHD) * Cfg::kElem);
+#pragma unroll
+            for (int c = 0; c < kWords; c += 16) {
+                uint32_t v[16];
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const uint4 w4 = qrow < p.N ? __ldg(src + c / 4 + q4) : make_uint4(0u, 0u, 0u, 0u);
+                    v[4 * q4] = w4.x; v[4 * q4 + 1] = w4.y; v[4 * q4 + 2] = w4.z; v[4 * q4 + 3] = w4.w;
+                }
+                if (!BF16) {
+                    // an A operand read from TMEM is TRUNCATED to tf32 by the MMA (measured: parked as raw fp32 bits the output
+                    // error at N x M = 1000 x 31000 doubled, 6e-4 -> 1.3e-3): round to nearest here, once per row
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = f32_to_tf32(__uint_as_float(v[i]));
+                }
+                tc::tmem_st_32x16(tl + kQCol + c, v);
+            }
+            tc::tmem_st_wait();
+            tc::tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&q_full);
+        }
         constexpr float kLazy = 64.f;   // P <= 2^64: no overflow in fp32 / tf32 / bf16, same relative precision
         float m_ref = -INFINITY, l_run = 0.f;
         auto ex2 = [](float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; };
@@ -437,6 +466,7 @@ static int launch_tc(const void *q, const void *k, const void *vt, int ldv, floa
     // V^T [D, M] with row stride ldv: columns >= M are out of bounds -> zero fill
     if ((rc = make_tmap_2d_sw128(&tv, vt, Cfg::kElem, D, M, (uint64_t)ldv * Cfg::kElem, kHD))) return rc;
     SelsaParams p;
+    p.q = q;
     p.out = out;
     p.part_acc = reinterpret_cast<float *>(ws + w.acc_off);
     p.part_m = reinterpret_cast<float *>(ws + w.m_off);

@@ -16,7 +16,7 @@
 // Reference rows are processed in chunks of 64.  When N*heads/128 CTAs cannot fill 148 SMs the reference
 // axis is split across CTAs and the partial (acc, max, sum) triples are merged by selsa_merge_kernel.
 //
-// TMEM columns: [0,64) S buffer 0, [64,128) S buffer 1, [128,192) O, [192,256) Q (fp32: 64 columns, bf16: 32).
+// TMEM columns: kSBufs S / P tiles of 64 columns, then O (64 columns), then Q (fp32: 64 columns, bf16: 32).
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -39,9 +39,16 @@ constexpr int kHD = 64;
 #define VOD_SELSA_OCC 1
 #endif
 constexpr int kKvStages = VOD_SELSA_STAGES;
+#ifndef VOD_SELSA_SBUFS
+#define VOD_SELSA_SBUFS 2
+#endif
+constexpr int kSBufs = VOD_SELSA_SBUFS;                  // S / P tiles in TMEM (the MMA issuer runs kSBufs - 1 score tiles ahead)
 constexpr int kSelsaThreads = 192;
-constexpr int kSelsaTmemCols = 256;
-constexpr uint32_t kQCol = 3 * 64;      // TMEM columns [192, 256): the CTA's 128 query rows (A operand of S = Q K^T)
+constexpr int kSelsaTmemCols = (kSBufs + 2) * 64 <= 256 ? 256 : 512;
+constexpr uint32_t kOCol = kSBufs * 64;                  // O accumulator: 64 TMEM columns after the score tiles
+constexpr uint32_t kQCol = kOCol + 64;                   // then the CTA's 128 query rows (A operand of S = Q K^T)
+static_assert((kSBufs + 2) * 64 <= 512 && kSBufs >= 2, "TMEM columns");
+static_assert(VOD_SELSA_OCC * kSelsaTmemCols <= 512, "TMEM columns per SM");
 
 template <bool BF16>
 struct SelsaCfg {
@@ -78,7 +85,7 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *sK = smem;
     uint8_t *sV = sK + kKvStages * Cfg::kKBytes;
-    __shared__ uint64_t q_full, kv_full[kKvStages], kv_empty[kKvStages], s_full[2], s_empty[2], p_full[2], o_full;
+    __shared__ uint64_t q_full, kv_full[kKvStages], kv_empty[kKvStages], s_full[kSBufs], s_empty[kSBufs], p_full[kSBufs];
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -89,11 +96,10 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     if (threadIdx.x == 0) {
         tc::mbar_init(&q_full, 4);                         // the four softmax warps, once their Q rows are in TMEM
         for (int i = 0; i < kKvStages; ++i) { tc::mbar_init(&kv_full[i], 1); tc::mbar_init(&kv_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kSBufs; ++i) {
             tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 1);
             tc::mbar_init(&p_full[i], 128);
         }
-        tc::mbar_init(&o_full, 1);
         tc::fence_barrier_init();
     }
     if (warp == 5) tc::tmem_alloc(&tmem_slot, kSelsaTmemCols);
@@ -124,9 +130,9 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         // ------------------------------------------------------------------ MMA issuer
         constexpr uint32_t idesc = tc::umma_idesc(BF16 ? tc::kFmtBF16 : tc::kFmtTF32, kBM, kBN);  // M=128, N=64 for both GEMMs
         auto issue_s = [&](int j) {
-            const int st = j % kKvStages, buf = j & 1;
+            const int st = j % kKvStages, buf = j % kSBufs;
             tc::mbar_wait(&kv_full[st], (j / kKvStages) & 1);
-            tc::mbar_wait(&s_empty[buf], ((j >> 1) & 1) ^ 1);
+            tc::mbar_wait(&s_empty[buf], ((j / kSBufs) & 1) ^ 1);
             tc::tcgen05_fence_after();
             if (tc::elect_one()) {
                 // S = Q K^T with Q read from TENSOR MEMORY (TS form, as P below): from shared memory every one of these small
@@ -147,11 +153,11 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         };
         tc::mbar_wait(&q_full, 0);
         tc::tcgen05_fence_after();
-        issue_s(0);
+        for (int j = 0; j < kSBufs - 1 && j < n; ++j) issue_s(j);
         for (int j = 0; j < n; ++j) {
-            if (j + 1 < n) issue_s(j + 1);
-            const int st = j % kKvStages, buf = j & 1;
-            tc::mbar_wait(&p_full[buf], (j >> 1) & 1);   // also orders any rescale of O (done before the P store) before this PV
+            if (j + kSBufs - 1 < n) issue_s(j + kSBufs - 1);
+            const int st = j % kKvStages, buf = j % kSBufs;
+            tc::mbar_wait(&p_full[buf], (j / kSBufs) & 1);   // also orders any rescale of O (done before the P store) before this PV
             tc::tcgen05_fence_after();
             if (tc::elect_one()) {
                 // O += P V with P read from TENSOR MEMORY (TS form): the softmax warps wrote it over the S tile in place, so
@@ -162,12 +168,14 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < kSteps; ++i) {
                     const uint64_t vb = tc::umma_desc_k_sw128(va + (i >> 2) * kHD * 128 + (i & 3) * 32);
-                    if (BF16) tc::umma_f16_ts(tmem + 2 * kBN, tmem + buf * kBN + i * 8, vb, idesc, (j | i) != 0);
-                    else tc::umma_tf32_ts(tmem + 2 * kBN, tmem + buf * kBN + i * 8, vb, idesc, (j | i) != 0);   // O accumulates over all chunks
+                    if (BF16) tc::umma_f16_ts(tmem + kOCol, tmem + buf * kBN + i * 8, vb, idesc, (j | i) != 0);
+                    else tc::umma_tf32_ts(tmem + kOCol, tmem + buf * kBN + i * 8, vb, idesc, (j | i) != 0);   // O accumulates over all chunks
                 }
-                tc::umma_commit(&o_full);
                 tc::umma_commit(&kv_empty[st]);
-                tc::umma_commit(&s_empty[buf]);   // the S/P tile may be overwritten by S(j + 2)
+                // the S/P tile may be overwritten by S(j + kSBufs); the same barrier tells the softmax warps that PV(j) -- and, the
+                // tensor pipe being in order, every earlier PV -- has landed (a per-chunk "O ready" barrier would alias in parity
+                // once the softmax warps run more than one chunk ahead of the PV products)
+                tc::umma_commit(&s_empty[buf]);
             }
             __syncwarp();
         }
@@ -216,8 +224,8 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         auto ex2 = [](float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; };
 
         for (int j = 0; j < n; ++j) {
-            const int buf = j & 1;
-            tc::mbar_wait(&s_full[buf], (j >> 1) & 1);
+            const int buf = j % kSBufs;
+            tc::mbar_wait(&s_full[buf], (j / kSBufs) & 1);
             tc::tcgen05_fence_after();
             uint32_t s0[32], s1[32];
             tc::tmem_ld_32x32(tl + buf * kBN, s0);
@@ -258,14 +266,14 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 // rare: some row of this warp outgrew its reference maximum.  All PV products issued so far (chunks < j) must
                 // have landed; PV(j) cannot start before this thread's p_full arrival below.  tcgen05.ld/st are warp-wide,
                 // rows that do not need it rescale by 1.
-                tc::mbar_wait(&o_full, (j - 1) & 1);
+                tc::mbar_wait(&s_empty[(j - 1) % kSBufs], ((j - 1) / kSBufs) & 1);   // PV(j - 1) and all before it
                 tc::tcgen05_fence_after();
                 const bool need = m_new > m_ref + kLazy;
                 const float f = need ? ex2(m_ref - m_new) : 1.0f;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     uint32_t o[32];
-                    tc::tmem_ld_32x32(tl + 2 * kBN + half * 32, o);
+                    tc::tmem_ld_32x32(tl + kOCol + half * 32, o);
                     tc::tmem_ld_wait();
                     uint32_t lo[16], hi[16];
 #pragma unroll
@@ -273,8 +281,8 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                         lo[i] = __float_as_uint(__uint_as_float(o[i]) * f);
                         hi[i] = __float_as_uint(__uint_as_float(o[16 + i]) * f);
                     }
-                    tc::tmem_st_32x16(tl + 2 * kBN + half * 32, lo);
-                    tc::tmem_st_32x16(tl + 2 * kBN + half * 32 + 16, hi);
+                    tc::tmem_st_32x16(tl + kOCol + half * 32, lo);
+                    tc::tmem_st_32x16(tl + kOCol + half * 32 + 16, hi);
                 }
                 tc::tmem_st_wait();
                 tc::tcgen05_fence_before();
@@ -322,13 +330,13 @@ selsa_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             tc::mbar_arrive(&p_full[buf]);
         }
         // the finished accumulator: all PV products have landed once the last commit fires
-        tc::mbar_wait(&o_full, (n - 1) & 1);
+        tc::mbar_wait(&s_empty[(n - 1) % kSBufs], ((n - 1) / kSBufs) & 1);
         tc::tcgen05_fence_after();
         float acc[kHD];
         {
             uint32_t o0[32], o1[32];
-            tc::tmem_ld_32x32(tl + 2 * kBN, o0);
-            tc::tmem_ld_32x32(tl + 2 * kBN + 32, o1);
+            tc::tmem_ld_32x32(tl + kOCol, o0);
+            tc::tmem_ld_32x32(tl + kOCol + 32, o1);
             tc::tmem_ld_wait();
             tc::tcgen05_fence_before();
 #pragma unroll

@@ -1151,12 +1151,7 @@ def bench_fgfa(ctx, cfg):
                 graph.replay(); sink.put(i, d, l, c)
                 out_host.copy_(sink.buf[i % sink.frames], non_blocking=True)
         e2e_loop(2)
-        t_e2e_full = ctx.timed(lambda: (e2e_loop(args.steps), sink.gather()))
-        for j in range(2):                       # memory maps of clip position j resident in staging buffer j
-            pf.stage[j][0].copy_(run.dev_sets[j][0])
-        e2e_loop(2, new_frame_only)
-        t_e2e = ctx.timed(lambda: (e2e_loop(args.steps, new_frame_only), sink.gather()))
-        h2d_new = C * H * W * 4 + run.host_sets[0][1].numel() * 4
+        t_e2e = ctx.timed(lambda: (e2e_loop(args.steps), sink.gather()))
     frames = args.steps * ctx.world
     h2d = sum(host[0][j].numel() * host[0][j].element_size() for j in (0, 2, 3, 4))
     config = dict(workload=cfg['workload'], proposals=cfg['N'], ref_frames=T - 1, execution='one CUDA graph per frame',

@@ -319,8 +319,14 @@ msra_rescore_kernel(const float *__restrict__ roi, const float *__restrict__ ref
 //     (the field is monotone in the similarity), the margin is 6 quanta of 2^-11 (>= kMsraMargin);
 //   * same arithmetic as the generic kernel for the exact similarity, the softmax and the weighted sum.
 // The generic kernel above needed ~1300 warp instructions per (row, frame); this one ~300.
-constexpr int kRfFrames = 5;
-constexpr int kRfWarps = 4;
+#ifndef VOD_RF_FRAMES
+#define VOD_RF_FRAMES 5
+#endif
+#ifndef VOD_RF_WARPS
+#define VOD_RF_WARPS 4
+#endif
+constexpr int kRfFrames = VOD_RF_FRAMES;
+constexpr int kRfWarps = VOD_RF_WARPS;
 template <int NQ, bool TWO>
 // (register budget, round 2: the compiler's own 80 registers = 6 CTAs of 4 warps per SM 205 us; 8 CTAs (64 registers, no spills)
 // 188 us; 10 CTAs (48 registers, spills) 241 us)

@@ -1,7 +1,7 @@
 """Times the msra similarity GEMM alone and the whole msra_topk_sample op (GEMM + 2 norms + re-score) at cfg-3 size."""
-import sys, torch
+import os, sys, torch
 sys.path.insert(0, '.')
-from lowlightenvironmentvideoobjectdetection_b200 import ops
+from lowlightenvironmentvideoobjectdetection_b200 import _lib, ops
 N, T, C, H, W = 300, 15, 512, 38, 63
 HW = H * W
 g = torch.Generator(device='cuda').manual_seed(0)
@@ -19,7 +19,10 @@ def timeit(fn, iters=10):
         e0.record(); fn(); e1.record(); torch.cuda.synchronize()
         tot += e0.elapsed_time(e1)
     return tot / iters * 1e3
-tg = timeit(lambda: ops.msra_gemm_candidates(ru, unit, T))
 out = torch.empty(T, N * 49, C, device='cuda')
-tf = timeit(lambda: ops.msra_topk_sample(rows, ref_nhwc, 2, ref_norm=norm, ref_unit=unit, out=out))
-print('gemm %.1f us (%.0f TFLOP/s)   msra_topk_sample %.1f us   norms+rescore %.1f us' % (tg, 2.0 * N * 49 * T * HW * C / tg / 1e6, tf, tf - tg))
+for path in (sys.argv[1:] or [_lib.LIB_PATH]):       # optional: experiment builds of the library, each in turn
+    _lib.LIB_PATH, _lib._lib = os.path.abspath(path), None
+    tg = timeit(lambda: ops.msra_gemm_candidates(ru, unit, T))
+    tf = timeit(lambda: ops.msra_topk_sample(rows, ref_nhwc, 2, ref_norm=norm, ref_unit=unit, out=out))
+    print('%-28s gemm %.1f us (%.0f TFLOP/s)   msra_topk_sample %.1f us   norms+rescore(+overflow) %.1f us' % (
+        os.path.basename(path), tg, 2.0 * N * 49 * T * HW * C / tg / 1e6, tf, tf - tg), flush=True)

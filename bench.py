@@ -819,6 +819,12 @@ def bench_selsa(ctx, cfg, cfg_name):
                                          [km], rescale=False, ref_img_metas=memo_metas + [km])
             eager_cached(3)
             t_eager_cached = ctx.timed(lambda: eager_cached(args.steps))
+            # the same drop-in call with head.use_cuda_graphs: one captured key-frame step replayed per call
+            run.head.use_cuda_graphs = True
+            eager_cached(3)
+            t_graph_cached = ctx.timed(lambda: eager_cached(args.steps))
+            run.head.use_cuda_graphs = False
+            run.head._step_graphs.clear()
 
         # ------------------------------------------------ the same step with fp32 library GEMMs / convs
         run.capture('fp32', tf32=False)
@@ -894,6 +900,9 @@ def bench_selsa(ctx, cfg, cfg_name):
         'eager_cached_api': {'value': frames / t_eager_cached, 'unit': UNIT,
                              'note': 'the drop-in call with the cache, eagerly: SelsaRoIHead.simple_test(..., ref_img_metas=...) on '
                                      'ref_x = cat(memo, key) as SELSA.simple_test builds it; includes the host-side cache bookkeeping'},
+        'cached_api_cuda_graphs': {'value': frames / t_graph_cached, 'unit': UNIT,
+                                   'note': 'the same drop-in call with head.use_cuda_graphs = True (opt-in): the key-frame step is one '
+                                           'graph replay, inputs copied into its static buffers, one host read of the detection count'},
         'fp32_library_math': {'value': frames / t_fp32, 'unit': UNIT, 'ms_per_step': 1e3 * t_fp32 / args.steps,
                               'note': 'same graph-replayed step with cuBLAS / cuDNN in fp32 instead of tf32'},
         'cached': {'value': frames / t_cached, 'unit': UNIT, 'ms_per_step': 1e3 * t_cached / args.steps, 'clip_len': clip_len,

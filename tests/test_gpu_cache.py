@@ -84,6 +84,37 @@ def test_cached_simple_test_matches_uncached_over_a_clip(troi, T, mode):
     assert computed[1:] == ([1] * (steps - 1) if mode == 'fifo' else [])
 
 
+@pytest.mark.parametrize('mode,T', [('fifo', 5), ('adaptive', 9)])
+def test_cached_simple_test_with_cuda_graphs_matches_eager(mode, T):
+    """``head.use_cuda_graphs = True``: the cached drop-in call replays one captured key-frame step per call (the frames that
+    enter the reference set are still processed eagerly).  Over a clip with memory turnover the detections equal the eager cached
+    call's -- same kernels on the same inputs, so bit for bit -- one graph serves the whole clip, and the caller's outputs are
+    not aliased by the next call."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    N, steps = 20, 12
+    eager, graphed = _head(True), _head(True)
+    graphed.load_state_dict(eager.state_dict())
+    graphed.use_cuda_graphs = True
+    maps, props, metas = _clip(steps + T, N, 31 + T)
+    left = T // 2
+    kept = []
+    for step in range(steps):
+        if mode == 'fifo':
+            k = left + step
+            ids = list(range(k - left, k - left + T))
+        else:
+            k = T - 1 + step
+            ids = list(range(T - 1)) + [k]
+        args = ((maps[k:k + 1],), (maps[ids],), [props[k]], [props[i] for i in ids], [metas[k]])
+        want = eager.simple_test(*args, ref_img_metas=[metas[i] for i in ids])
+        got = graphed.simple_test(*args, ref_img_metas=[metas[i] for i in ids])
+        assert torch.equal(got[0][0], want[0][0]) and torch.equal(got[1][0], want[1][0])
+        kept.append((got[0][0], want[0][0].clone()))
+    assert len(graphed._step_graphs) == 1
+    assert all(torch.equal(a, b) for a, b in kept)          # earlier results were not overwritten by later replays
+
+
 def test_cached_device_step_our_kernels_bit_identical():
     """Device-level API: fill the cache once, then every key frame's RoI features (RoIAlign, most-similar sampling, TAFA: our
     kernels + the same-shape key-slot conv) are bit-identical to the uncached extractor; the head's scores agree to fp32 GEMM

@@ -805,6 +805,13 @@ def bench_selsa(ctx, cfg, cfg_name):
                 run_step(run.head, *run.dev_sets[i % n_sets], metas)
             t_eager = ctx.timed(lambda: [run_step(run.head, *run.dev_sets[i % n_sets], metas) for i in range(args.steps)])
 
+            run.head.use_cuda_graphs = True          # the same call, replaying the captured step (opt-in)
+            for i in range(2):
+                run_step(run.head, *run.dev_sets[i % n_sets], metas)
+            t_eager_graphs = ctx.timed(lambda: [run_step(run.head, *run.dev_sets[i % n_sets], metas) for i in range(args.steps)])
+            run.head.use_cuda_graphs = False
+            run.head._step_graphs.clear()
+
             # ... and the drop-in call an integrator makes with the cache: simple_test(..., ref_img_metas=...) in SELSA's
             # adaptive-stride test mode (14 fixed memory frames + the key frame), eagerly
             memo_metas = [dict(video_id=ctx.rank, frame_id=-(t + 1), img_shape=IMG_SHAPE, scale_factor=(1., 1., 1., 1.)) for t in range(T - 1)]
@@ -900,6 +907,9 @@ def bench_selsa(ctx, cfg, cfg_name):
         'eager_cached_api': {'value': frames / t_eager_cached, 'unit': UNIT,
                              'note': 'the drop-in call with the cache, eagerly: SelsaRoIHead.simple_test(..., ref_img_metas=...) on '
                                      'ref_x = cat(memo, key) as SELSA.simple_test builds it; includes the host-side cache bookkeeping'},
+        'eager_api_cuda_graphs': {'value': frames / t_eager_graphs, 'unit': UNIT,
+                                  'note': 'SelsaRoIHead.simple_test with head.use_cuda_graphs = True (opt-in): the uncached step as one graph '
+                                          'replay per call, inputs copied into its static buffers'},
         'cached_api_cuda_graphs': {'value': frames / t_graph_cached, 'unit': UNIT,
                                    'note': 'the same drop-in call with head.use_cuda_graphs = True (opt-in): the key-frame step is one '
                                            'graph replay, inputs copied into its static buffers, one host read of the detection count'},

@@ -342,6 +342,13 @@ class SelsaRoIHead(nn.Module):
         """selsa_roi_head.py:147-187."""
         rois = bbox2roi(proposals)
         ref_rois = bbox2roi(ref_proposals)
+        if (self.use_cuda_graphs and len(proposals) == 1 and len(x) == 1 and len(ref_x) == 1 and x[0].is_cuda and rois.shape[0] > 0
+                and ref_rois.shape[0] > 0 and rcnn_test_cfg is self.test_cfg and rcnn_test_cfg.get('max_per_img', 0) > 0
+                and rcnn_test_cfg['nms'].get('type', 'nms') == 'nms' and not torch.cuda.is_current_stream_capturing()):
+            dets, labels, count = self._graph_step(x[0], ref_x[0], rois, ref_rois, img_metas[0]['img_shape'],
+                                                   img_metas[0]['scale_factor'], rescale)
+            n = int(count)
+            return [dets[:n]], [labels[:n]]
         bbox_results = self._bbox_forward(x, ref_x, rois, ref_rois)
         img_shapes = tuple(meta['img_shape'] for meta in img_metas)
         scale_factors = tuple(meta['scale_factor'] for meta in img_metas)
@@ -523,6 +530,24 @@ class SelsaRoIHead(nn.Module):
         cache.keys[key_slot] = key_key
         n = int(count)
         return [dets[:n]], [labels[:n]]
+
+    def _graph_step(self, feat, ref_feat, rois, ref_rois, img_shape, scale_factor, rescale):
+        """The uncached step (``simple_test_device``) as a replay of the graph captured for these shapes: the caller's maps and
+        RoIs are copied into the graph's static inputs, the outputs are copies of its static outputs (``use_cuda_graphs``)."""
+        key = ('uncached', tuple(feat.shape), tuple(ref_feat.shape), feat.dtype, rois.shape[0], ref_rois.shape[0], tuple(img_shape),
+               tuple(scale_factor), bool(rescale), torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32,
+               torch.cuda.current_device(), RefFrameCache._weights_tag(self))
+        entry = self._step_graphs.get(key)
+        if entry is None:
+            if len(self._step_graphs) >= 4:
+                self._step_graphs.pop(next(iter(self._step_graphs)))
+            st = [t.clone() for t in (feat, ref_feat, rois, ref_rois)]
+            graph, outs = self.capture_graph((st[0],), (st[1],), st[2], st[3], img_shape, scale_factor, rescale)
+            entry = self._step_graphs[key] = dict(cache=None, graph=graph, outs=outs, st=st)
+        for dst, src in zip(entry['st'], (feat, ref_feat, rois, ref_rois)):
+            dst.copy_(src)
+        entry['graph'].replay()
+        return tuple(o.clone() for o in entry['outs'])
 
     def _cached_step(self, x, rois, key_ref_rois, cache, key_slot, img_shape, scale_factor, rescale):
         """``simple_test_cached_device``, eagerly or -- with ``use_cuda_graphs`` -- as a replay of the step captured for this

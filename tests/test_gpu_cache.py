@@ -115,6 +115,30 @@ def test_cached_simple_test_with_cuda_graphs_matches_eager(mode, T):
     assert all(torch.equal(a, b) for a, b in kept)          # earlier results were not overwritten by later replays
 
 
+def test_uncached_simple_test_with_cuda_graphs_matches_eager():
+    """``head.use_cuda_graphs = True`` without ``ref_img_metas``: the plain (uncached) drop-in call replays the captured
+    ``simple_test_device`` step; same detections as the eager call for every frame of a clip, one graph for the clip, a second one
+    when the proposal count changes."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    T, N, steps = 5, 20, 6
+    eager, graphed = _head(True), _head(True)
+    graphed.load_state_dict(eager.state_dict())
+    graphed.use_cuda_graphs = True
+    maps, props, metas = _clip(steps + T, N, 57)
+    for step in range(steps):
+        ids = list(range(step, step + T))
+        k = ids[-1]
+        args = ((maps[k:k + 1],), (maps[ids],), [props[k]], [props[i] for i in ids], [metas[k]])
+        want, got = eager.simple_test(*args), graphed.simple_test(*args)
+        assert torch.equal(got[0][0], want[0][0]) and torch.equal(got[1][0], want[1][0])
+    assert len(graphed._step_graphs) == 1
+    args = ((maps[k:k + 1],), (maps[ids],), [props[k][:11]], [props[i] for i in ids], [metas[k]])
+    want, got = eager.simple_test(*args), graphed.simple_test(*args)
+    assert torch.equal(got[0][0], want[0][0]) and torch.equal(got[1][0], want[1][0])
+    assert len(graphed._step_graphs) == 2
+
+
 def test_cached_device_step_our_kernels_bit_identical():
     """Device-level API: fill the cache once, then every key frame's RoI features (RoIAlign, most-similar sampling, TAFA: our
     kernels + the same-shape key-slot conv) are bit-identical to the uncached extractor; the head's scores agree to fp32 GEMM

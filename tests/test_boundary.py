@@ -321,3 +321,30 @@ def test_ref_frame_cache_bookkeeping_cpu():
     with torch.no_grad():
         head.bbox_head.shared_fcs[0].weight.mul_(2.0)
     assert not c.compatible(head, T, N, (64, 3, 4), 'cpu')
+
+
+def test_selsa_fused_tail_algebra_cpu():
+    """The identities behind vod_selsa_residual_relu (host side, CPU): projecting V^T without ref_fc's bias and adding
+    ``SelsaAggregator.out_bias`` = fc.bias + fc.weight . ref_fc.bias after the last linear gives the reference's
+    fc(softmax(.) (V + b_v)) (selsa_aggregator.py:64-72: softmax rows sum to one), and the layer tail
+    relu(x + y + bias) / relu(ref_x) is selsa_bbox_head.py:56-58.  The bias is cached per weight version."""
+    from oracle import vod_oracle as O
+    torch.manual_seed(3)
+    m = vod.SelsaAggregator(in_channels=128, num_attention_blocks=2)       # d = 64: the V^T (bias-free) projection layout
+    for prm in m.parameters():
+        torch.nn.init.normal_(prm, 0, 0.05)
+    x, ref_x = torch.randn(7, 128), torch.randn(19, 128)
+    p = {k: v.detach() for k, v in m.state_dict().items()}
+    want = O.selsa_aggregate(x, ref_x, p, 2)
+    with torch.no_grad():
+        q, k = m.fc_embed(x), m.ref_fc_embed(ref_x)
+        v0 = ref_x @ m.ref_fc.weight.t()                                    # V without its bias
+        w = torch.softmax((q.view(7, 2, 64).transpose(0, 1) @ k.view(19, 2, 64).permute(1, 2, 0)) / 8.0, dim=-1)
+        o = (w @ v0.view(19, 2, 64).transpose(0, 1)).transpose(0, 1).reshape(7, 128)
+        y = torch.nn.functional.linear(o, m.fc.weight)                      # what attend(..., with_bias=False) returns
+        b = m.out_bias(True)
+        assert torch.allclose(y + b, want, atol=1e-5)
+        assert m.out_bias(True) is b                                        # cached
+        assert m.out_bias(False) is m.fc.bias                               # V projected with its bias: nothing to fold
+        m.ref_fc.bias.add_(1.0)                                             # a weight change invalidates the cached bias
+        assert not torch.equal(m.out_bias(True), b)

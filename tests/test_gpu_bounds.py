@@ -170,3 +170,46 @@ def test_denoise_kernels_bounds():
         xt = torch.randn(T, 16, H, W, generator=g).to(DEV)
         with torch.no_grad():
             _run('TemporalAttentionFusion T=%d %dx%d' % (T, H, W), lambda: taf(xt))
+
+
+def test_ops_concurrent_on_two_streams():
+    """SURVEY 8b threading contract: the entry points keep no device-global state and take their stream explicitly, so the same
+    operator may run on two streams at once (per-stream workspaces, `_lib.Workspace`).  Each operator is issued alternately on
+    two streams with two different inputs, several rounds deep, and every result must equal the one computed alone."""
+    g = torch.Generator().manual_seed(9)
+    T, C, H, W, N = 3, 64, 12, 20, 37
+    cases = []
+    for seed in range(2):
+        maps = torch.relu(torch.randn(T, C, H, W, generator=g)).to(DEV)
+        nhwc, norm, unit = ops._to_nhwc(maps, True, True)
+        rois = rpn_like_rois(g, N, 1, W * 16., H * 16.).to(DEV)
+        rows = ops.roi_align_nhwc(nhwc[T - 1:T].contiguous(), rois, 7, 1 / 16., 2, True, out_nhwc=True).view(N * 49, C)
+        q, k, v = (torch.randn(n, 1024, generator=g).to(DEV) for n in (150, 700, 700))
+        boxes, scores = clustered_boxes(g, 3000, 300).to(DEV), torch.rand(3000, generator=g).to(DEV)
+        ids = torch.randint(0, 30, (3000,), generator=g).to(DEV)
+        x_all = torch.randn(T + 1, N, 49, C, generator=g).to(DEV)
+        emb = torch.randn(T + 1, N, 49, C, generator=g).to(DEV)
+        cases.append(dict(nhwc=nhwc.contiguous(), norm=norm, unit=unit, rois=rois, rows=rows, q=q, k=k, v=v, boxes=boxes,
+                          scores=scores, ids=ids, x_all=x_all, emb=emb))
+    fns = {
+        'roi_align': lambda c: ops.roi_align_nhwc(c['nhwc'], torch.cat([c['rois']] * 8), 7, 1 / 16., 2, True),
+        'msra_topk_sample': lambda c: ops.msra_topk_sample(c['rows'], c['nhwc'], 2, ref_norm=c['norm'], ref_unit=c['unit']),
+        'selsa_attention': lambda c: ops.selsa_attention(c['q'], c['k'], c['v'], 16),
+        'batched_nms': lambda c: ops.batched_nms(c['boxes'], c['scores'], c['ids'], dict(type='nms', iou_threshold=0.5))[1],
+        'tafa_weighted_sum': lambda c: ops.tafa_weighted_sum(c['x_all'], c['emb'], 4),
+    }
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for name, fn in fns.items():
+        want = [fn(c) for c in cases]
+        torch.cuda.synchronize()
+        got = [[], []]
+        for s in streams:
+            s.wait_stream(torch.cuda.current_stream())
+        for rnd in range(6):
+            for lane in (0, 1):
+                with torch.cuda.stream(streams[lane]):
+                    got[lane].append(fn(cases[lane]))
+        torch.cuda.synchronize()
+        for lane in (0, 1):
+            for out in got[lane]:
+                assert _same(out, want[lane]), '%s: result on stream %d differs from the result computed alone' % (name, lane)
